@@ -1,0 +1,194 @@
+/*
+ * b200hevc_worklist.h — wire format of the per-frame packed work list ("blob v1").
+ *
+ * The host side of the decoder (openHEVC's CABAC parse / MV / BS derivation, which
+ * stays on the CPU) does not execute pixel kernels any more: every call it makes
+ * through the HEVCDSPContext / HEVCPredContext function tables
+ * (reference: libavcodec/hevcdsp.h:44-124, libavcodec/hevcpred.h:31-41) is
+ * *recorded* as one fixed-size record below.  One blob describes one picture and
+ * is uploaded with a single cudaMemcpyAsync; one kernel per stage consumes it.
+ *
+ * Plain C, no CUDA / torch types: shared by the CUDA engine, the recorder,
+ * the CPU oracle (oracle/hevc_oracle.c) and mirrored by numpy dtypes in
+ * openhevc_b200/worklist.py.
+ */
+#ifndef B200HEVC_WORKLIST_H
+#define B200HEVC_WORKLIST_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define B200_BLOB_MAGIC   0x4C573242u /* "B2WL" */
+#define B200_BLOB_VERSION 1u
+
+/* blob sections; every section start is 256-byte aligned inside the blob */
+enum {
+    B200_SEC_COEFF = 0,   /* int16 pool: dequantised coefficients / PCM samples; count = #int16   */
+    B200_SEC_TU4,         /* B200TuRec, 4x4 blocks   (transform_add[0] call sites)                  */
+    B200_SEC_TU8,         /* B200TuRec, 8x8                                                        */
+    B200_SEC_TU16,        /* B200TuRec, 16x16                                                      */
+    B200_SEC_TU32,        /* B200TuRec, 32x32                                                      */
+    B200_SEC_INTRA,       /* B200IntraRec in decode order (intra_pred[] call sites)                */
+    B200_SEC_MC,          /* B200McRec, one per <=256-sample tile of a put_hevc_{q,e}pel* call     */
+    B200_SEC_DBK,         /* uint16 edge-parameter grids, layout B200DbkLayout (count = #uint16)   */
+    B200_SEC_SAO,         /* B200SaoRec grid [3][ctb_count] (count = 3*ctb_count) or 0 = no SAO    */
+    B200_SEC_COUNT
+};
+
+typedef struct B200Section {
+    uint32_t off;    /* byte offset from blob start */
+    uint32_t count;  /* number of elements          */
+} B200Section;
+
+typedef struct B200BlobHeader {
+    uint32_t magic;
+    uint32_t version;
+    uint32_t total_bytes;
+    int32_t  poc;
+    uint16_t width, height;      /* luma samples (sps->width / sps->height)                    */
+    uint8_t  chroma_format_idc;  /* 1 = 4:2:0, 2 = 4:2:2, 3 = 4:4:4                            */
+    uint8_t  bit_depth;          /* 8..12                                                      */
+    uint8_t  log2_ctb_size;      /* 4..6                                                       */
+    uint8_t  cur_slot;           /* DPB slot that receives this picture                        */
+    uint32_t flags;              /* B200_FRAME_*                                               */
+    B200Section sec[B200_SEC_COUNT];
+    uint32_t reserved[64 - 6 - 2 * B200_SEC_COUNT];
+} B200BlobHeader;               /* 256 bytes */
+
+#define B200_FRAME_HAS_DEBLOCK 1u
+#define B200_FRAME_HAS_SAO     2u
+
+/* ---- residual stage (K2) ------------------------------------------------------------- */
+enum {
+    B200_TU_IDCT   = 0, /* hevcdsp.idct[log2-2](coeffs, col_limit)   hevc_cabac.c:1934 */
+    B200_TU_DC     = 1, /* hevcdsp.idct_dc[log2-2](coeffs)           hevc_cabac.c:1925 */
+    B200_TU_DST    = 2, /* hevcdsp.idct_4x4_luma(coeffs)             hevc_cabac.c:1921 */
+    B200_TU_SKIP   = 3, /* hevcdsp.transform_skip(coeffs, log2)      hevc_cabac.c:1885 */
+    B200_TU_BYPASS = 4, /* cu_transquant_bypass: coeffs are the residual  hevc_cabac.c:1868 */
+    B200_TU_PCM    = 5  /* hevcdsp.put_pcm: pool holds final samples (already << (BD-pcm_bd)), stored not added */
+};
+#define B200_TUF_RDPCM      1u /* followed by hevcdsp.transform_rdpcm()      hevc_cabac.c:1873,1892 */
+#define B200_TUF_RDPCM_VERT 2u /* rdpcm mode 1 (running sum down the columns)                      */
+#define B200_TUF_PARK       4u /* intra TU: leave the residual in the pool (K3 adds it after prediction) */
+
+typedef struct B200TuRec {       /* 16 bytes */
+    uint16_t x, y;               /* top-left sample in its plane                                  */
+    uint8_t  plane;              /* 0 Y, 1 Cb, 2 Cr                                               */
+    uint8_t  log2;               /* 2..5; PCM: log2 of the (square) block in this plane, 1..6 lives in the TU4 list with w/h in col_limit */
+    uint8_t  kind;               /* B200_TU_*                                                     */
+    uint8_t  flags;              /* B200_TUF_*                                                    */
+    uint8_t  col_limit;          /* IDCT only (hevc_cabac.c:1927-1933)                            */
+    uint8_t  pad[3];
+    uint32_t coeff_off;          /* int16 index into the COEFF pool (multiple of 8)               */
+} B200TuRec;
+
+/* ---- intra stage (K3) ------------------------------------------------------------------ */
+#define B200_INF_UP_LEFT     1u  /* cand_up_left      (after z-scan / CIP checks, hevcpred_template.c:100-104) */
+#define B200_INF_UP          2u
+#define B200_INF_UP_RIGHT    4u
+#define B200_INF_LEFT        8u
+#define B200_INF_BOTTOM_LEFT 16u
+#define B200_INF_FILTER      32u /* !intra_smoothing_disabled && (c_idx==0 || chroma_array_type==3)  :288 */
+#define B200_INF_STRONG      64u /* sps_strong_intra_smoothing_enable_flag                           :296 */
+
+typedef struct B200IntraRec {    /* 16 bytes */
+    uint16_t x, y;               /* top-left sample in its plane */
+    uint8_t  plane;              /* c_idx */
+    uint8_t  log2;               /* 2..5 */
+    uint8_t  mode;               /* 0 planar, 1 DC, 2..34 angular */
+    uint8_t  flags;              /* B200_INF_* */
+    uint8_t  top_right_size;     /* samples really inside the picture, hevcpred_template.c:108-109 */
+    uint8_t  bottom_left_size;   /* hevcpred_template.c:106-107 */
+    uint8_t  pad[2];
+    uint32_t resid_off;          /* int16 index of the parked residual in COEFF, 0xFFFFFFFF = cbf 0 */
+} B200IntraRec;
+#define B200_NO_RESID 0xFFFFFFFFu
+
+/* ---- inter stage (K1) -------------------------------------------------------------------- */
+#define B200_MCF_BI       1u
+#define B200_MCF_WEIGHTED 2u
+#define B200_MCF_CHROMA   4u     /* 4-tap epel filters, fractions in 1/8 units */
+
+typedef struct B200McRec {       /* 32 bytes */
+    uint16_t x, y;               /* destination top-left sample in its plane */
+    uint8_t  w, h;               /* tile size, w*h <= 256 after recorder splitting, w<=32 */
+    uint8_t  plane;
+    uint8_t  flags;              /* B200_MCF_* */
+    int16_t  sx0, sy0;           /* integer source position in ref0's plane (may lie outside: samples clamp, videodsp_template.c:26-100) */
+    int16_t  sx1, sy1;
+    uint8_t  ref0, ref1;         /* DPB slots */
+    uint8_t  frac0, frac1;       /* mx | my << 4 */
+    int16_t  w0, w1;             /* weights  (hevc.c:1677-1683, 1763-1773) */
+    int16_t  o0, o1;             /* offsets, un-scaled as passed to the *_w table functions */
+    uint8_t  denom;
+    uint8_t  pad[3];
+} B200McRec;
+
+/* ---- deblocking (K4) ----------------------------------------------------------------------
+ * One uint16 per 4-sample edge segment, dense grids (0 = edge not filtered):
+ *   bits 0..5  tc   (8-bit scale, as in the tc[] argument)      bits 6..12 beta (8-bit scale)
+ *   bit 13 no_p   bit 14 no_q   bit 15 present
+ * Vertical-edge grid of a plane  : index (y>>2) * ew + (x>>3),   ew = (pw+7)>>3, rows (ph+3)>>2
+ * Horizontal-edge grid of a plane: index (y>>3) * sw + (x>>2),   sw = (pw+3)>>2, rows (ph+7)>>3
+ * x,y,pw,ph are in samples of that plane.  Section order: Y-vert, Y-horz, Cb-vert, Cb-horz, Cr-vert, Cr-horz,
+ * each grid start rounded up to 64 uint16.  (hevc_filter.c:345-581 call sites.) */
+#define B200_DBK_TC(e)    ((e) & 63)
+#define B200_DBK_BETA(e)  (((e) >> 6) & 127)
+#define B200_DBK_NOP(e)   (((e) >> 13) & 1)
+#define B200_DBK_NOQ(e)   (((e) >> 14) & 1)
+#define B200_DBK_PRESENT  0x8000u
+#define B200_DBK_PACK(tc, beta, nop, noq) \
+    ((uint16_t)(B200_DBK_PRESENT | ((tc) & 63) | (((beta) & 127) << 6) | (((nop) & 1) << 13) | (((noq) & 1) << 14)))
+
+typedef struct B200DbkLayout {   /* derived from the picture geometry, never stored */
+    uint32_t off[3][2];          /* [plane][0 vert,1 horz] start index in uint16 units */
+    uint32_t stride[3][2];       /* grid row stride */
+    uint32_t rows[3][2];
+    uint32_t total;              /* total uint16 count */
+} B200DbkLayout;
+
+/* ---- SAO (K5) ---------------------------------------------------------------------------- */
+enum { B200_SAO_NONE = 0, B200_SAO_BAND = 1, B200_SAO_EDGE = 2 };
+
+typedef struct B200SaoRec {      /* 16 bytes; grid index = plane * ctb_count + ctb_addr_rs */
+    uint8_t  type;               /* B200_SAO_* (sao->type_idx at call time)                          */
+    uint8_t  param;              /* band_position (band) or eo_class (edge)                           */
+    uint8_t  borders;            /* bit0 left, bit1 top, bit2 right, bit3 bottom picture border      */
+    uint8_t  edges;              /* bit0-1 vert_edge[2], bit2-3 horiz_edge[2], bit4-7 diag_edge[4]; only variant 1 */
+    uint8_t  variant;            /* 0 = sao_edge_filter[0], 1 = sao_edge_filter[1] (restore)          */
+    uint8_t  pad;
+    int16_t  offset_val[5];      /* sao->offset_val[c_idx][0..4]                                      */
+} B200SaoRec;
+
+static inline uint32_t b200_align_u32(uint32_t v, uint32_t a) { return (v + a - 1) / a * a; }
+
+static inline void b200_plane_dims(int width, int height, int chroma_format_idc, int plane, int *pw, int *ph)
+{
+    int hs = plane && chroma_format_idc != 3, vs = plane && chroma_format_idc == 1;
+    *pw = width >> hs;
+    *ph = height >> vs;
+}
+
+static inline void b200_dbk_layout(int width, int height, int chroma_format_idc, B200DbkLayout *L)
+{
+    uint32_t o = 0;
+    for (int p = 0; p < 3; p++) {
+        int pw, ph;
+        b200_plane_dims(width, height, chroma_format_idc, p, &pw, &ph);
+        L->stride[p][0] = (uint32_t)(pw + 7) >> 3; L->rows[p][0] = (uint32_t)(ph + 3) >> 2;
+        L->stride[p][1] = (uint32_t)(pw + 3) >> 2; L->rows[p][1] = (uint32_t)(ph + 7) >> 3;
+        for (int d = 0; d < 2; d++) {
+            L->off[p][d] = o;
+            o = b200_align_u32(o + L->stride[p][d] * L->rows[p][d], 64);
+        }
+    }
+    L->total = o;
+}
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B200HEVC_WORKLIST_H */

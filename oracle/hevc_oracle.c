@@ -1,0 +1,587 @@
+/*
+ * hevc_oracle.c — TEST INFRASTRUCTURE ONLY (never linked into, imported by or executed
+ * from the product path; only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline
+ * leg may use it).
+ *
+ * Plain-C restatement of openHEVC's per-CTU pixel-reconstruction path, i.e. of the
+ * functions behind HEVCDSPContext / HEVCPredContext, operating on the packed work list
+ * of include/b200hevc_worklist.h.  Each function cites the reference file:line it
+ * follows.  It is *restated*, not copied: transforms are written as masked matrix
+ * products, MC as one generic separable FIR with clamped addressing, deblocking / SAO
+ * as whole-picture passes.
+ *
+ * Parity pinning: the reference ships no golden vectors, so this file is
+ * pinned against the reference's own C tables compiled from /root/reference into
+ * oracle/_ref/libohevc_ref.so (oracle/build_ref.sh) by oracle/kat_ref.c, function by
+ * function, and against committed fixtures in tests/golden/ produced by that harness.
+ */
+#include <stdint.h>
+#include <stdlib.h>
+#include <string.h>
+#include "../include/b200hevc_worklist.h"
+
+typedef uint16_t pix_t; /* the oracle stores every sample as uint16, whatever the bit depth */
+
+static inline int clip3(int v, int lo, int hi) { return v < lo ? lo : v > hi ? hi : v; }
+static inline int clip16(int v) { return clip3(v, -32768, 32767); }
+static inline int clip_pix(int v, int bd) { return clip3(v, 0, (1 << bd) - 1); }
+static inline int iabs(int v) { return v < 0 ? -v : v; }
+
+/* ------------------------------------------------------------------------------------------
+ * Inverse transforms.  Reference: libavcodec/hevcdsp_template.c:165-326, matrix
+ * libavcodec/hevcdsp.c:879-944 (the standard HEVC core transform).
+ * ---------------------------------------------------------------------------------------- */
+static int8_t g_T[32][32];
+static int g_T_ready;
+
+/* |64*sqrt(2)*cos(j*pi/64)| as standardised (hand-tuned integers), j = 0..32; j=0 is the DC row gain 64 */
+static const int8_t k_cos_tab[33] = { 64, 90, 90, 90, 89, 88, 87, 85, 83, 82, 80, 78, 75, 73, 70, 67, 64,
+                                      61, 57, 54, 50, 46, 43, 38, 36, 31, 25, 22, 18, 13, 9, 4, 0 };
+
+static void build_matrix(void)
+{
+    if (g_T_ready) return;
+    for (int k = 0; k < 32; k++)
+        for (int n = 0; n < 32; n++) {
+            int m = ((2 * n + 1) * k) & 127, v;
+            if (m <= 32)      v =  k_cos_tab[m];
+            else if (m <= 64) v = -k_cos_tab[64 - m];
+            else if (m < 96)  v = -k_cos_tab[m - 64];
+            else              v =  k_cos_tab[128 - m];
+            g_T[k][n] = (int8_t)v;
+        }
+    g_T_ready = 1;
+}
+const int8_t *orc_transform_matrix(void) { build_matrix(); return &g_T[0][0]; }
+
+/* Which input index j of an N-point 1-D transform the reference's pruned butterflies really read
+ * when called with `end` (TR_8/16/32 macros, hevcdsp_template.c:223-269): odd terms are cut at
+ * `end` on each recursion level that receives it, the innermost levels always read everything. */
+static int idct_keep(int n, int j, int end)
+{
+    if (n == 4) return 1;
+    if (n == 8 || n == 16) return !(j & 1) || j < end;
+    /* n == 32 */
+    if (j & 1) return j < end;
+    if ((j & 3) == 2) return (j >> 1) < end / 2;
+    return 1;
+}
+
+/* hevcdsp.idct[log2-2](coeffs, col_limit), in place */
+void orc_idct(int16_t *c, int log2, int col_limit, int bd)
+{
+    build_matrix();
+    const int n = 1 << log2, step = 32 >> log2;
+    int tmp[32 * 32];
+    int limit  = col_limit < n ? col_limit : n;           /* IDCT_VAR8: limit  */
+    int limit2 = col_limit + 4 < n ? col_limit + 4 : n;   /*            limit2 */
+    for (int i = 0; i < n; i++) {                         /* first stage: columns, >>7 */
+        for (int r = 0; r < n; r++) {
+            int acc = 0;
+            for (int j = 0; j < n; j++)
+                if (idct_keep(n, j, limit2))
+                    acc += g_T[j * step][r] * c[j * n + i];
+            tmp[r * n + i] = clip16((acc + 64) >> 7);
+        }
+        if (limit2 < n && (i & 3) == 0 && i) limit2 -= 4; /* hevcdsp_template.c:288-292 */
+    }
+    const int shift = 20 - bd, add = 1 << (shift - 1);
+    for (int r = 0; r < n; r++)                           /* second stage: rows */
+        for (int x = 0; x < n; x++) {
+            int acc = 0;
+            for (int j = 0; j < n; j++)
+                if (idct_keep(n, j, limit))
+                    acc += g_T[j * step][x] * tmp[r * n + j];
+            c[r * n + x] = (int16_t)clip16((acc + add) >> shift);
+        }
+}
+
+/* hevcdsp.idct_dc[log2-2], hevcdsp_template.c:303-316 */
+void orc_idct_dc(int16_t *c, int log2, int bd)
+{
+    const int shift = 14 - bd, add = 1 << (shift - 1);
+    const int v = (((c[0] + 1) >> 1) + add) >> shift;
+    for (int i = 0; i < (1 << (2 * log2)); i++) c[i] = (int16_t)v;
+}
+
+/* hevcdsp.idct_4x4_luma (inverse DST-VII), hevcdsp_template.c:170-203 */
+void orc_dst4(int16_t *c, int bd)
+{
+    static const int8_t M[4][4] = { { 29, 55, 74, 84 }, { 74, 74, 0, -74 }, { 84, -29, -74, 55 }, { 55, -84, 74, -29 } };
+    int tmp[16];
+    for (int i = 0; i < 4; i++)
+        for (int r = 0; r < 4; r++) {
+            int acc = 0;
+            for (int j = 0; j < 4; j++) acc += M[j][r] * c[j * 4 + i];
+            tmp[r * 4 + i] = clip16((acc + 64) >> 7);
+        }
+    const int shift = 20 - bd, add = 1 << (shift - 1);
+    for (int r = 0; r < 4; r++)
+        for (int x = 0; x < 4; x++) {
+            int acc = 0;
+            for (int j = 0; j < 4; j++) acc += M[j][x] * tmp[r * 4 + j];
+            c[r * 4 + x] = (int16_t)clip16((acc + add) >> shift);
+        }
+}
+
+/* hevcdsp.transform_skip, hevcdsp_template.c:139-163 */
+void orc_transform_skip(int16_t *c, int log2, int bd)
+{
+    const int shift = 15 - bd - log2, n2 = 1 << (2 * log2);
+    if (shift > 0) { for (int i = 0; i < n2; i++) c[i] = (int16_t)((c[i] + (1 << (shift - 1))) >> shift); }
+    else           { for (int i = 0; i < n2; i++) c[i] = (int16_t)(c[i] << -shift); }
+}
+
+/* hevcdsp.transform_rdpcm, hevcdsp_template.c:114-136: running sums kept in int16 (wraps) */
+void orc_rdpcm(int16_t *c, int log2, int vertical)
+{
+    const int n = 1 << log2;
+    if (vertical) { for (int y = 1; y < n; y++) for (int x = 0; x < n; x++) c[y * n + x] = (int16_t)(c[y * n + x] + c[(y - 1) * n + x]); }
+    else          { for (int y = 0; y < n; y++) for (int x = 1; x < n; x++) c[y * n + x] = (int16_t)(c[y * n + x] + c[y * n + x - 1]); }
+}
+
+/* residual of one TU record, in place in the pool */
+static void tu_residual(const B200TuRec *t, int16_t *c, int bd)
+{
+    switch (t->kind) {
+    case B200_TU_IDCT:   orc_idct(c, t->log2, t->col_limit, bd); break;
+    case B200_TU_DC:     orc_idct_dc(c, t->log2, bd); break;
+    case B200_TU_DST:    orc_dst4(c, bd); break;
+    case B200_TU_SKIP:   orc_transform_skip(c, t->log2, bd); break;
+    default: break;
+    }
+    if (t->flags & B200_TUF_RDPCM) orc_rdpcm(c, t->log2, !!(t->flags & B200_TUF_RDPCM_VERT));
+}
+
+/* hevcdsp.transform_add[log2-2], hevcdsp_template.c:45-111 */
+void orc_add_residual(pix_t *dst, int stride, const int16_t *r, int n, int bd)
+{
+    for (int y = 0; y < n; y++)
+        for (int x = 0; x < n; x++)
+            dst[y * stride + x] = (pix_t)clip_pix(dst[y * stride + x] + r[y * n + x], bd);
+}
+
+/* ------------------------------------------------------------------------------------------
+ * Inter prediction.  Reference: hevcdsp_template.c:610-1609 (put_hevc_{qpel,epel}*),
+ * filters hevcdsp.c:1028-1042, edge emulation videodsp_template.c:26-100 (== clamp).
+ * ---------------------------------------------------------------------------------------- */
+static const int8_t k_qpel[4][8] = { { 0, 0, 0, 64, 0, 0, 0, 0 }, { -1, 4, -10, 58, 17, -5, 1, 0 },
+                                     { -1, 4, -11, 40, 40, -11, 4, -1 }, { 0, 1, -5, 17, 58, -10, 4, -1 } };
+static const int8_t k_epel[8][4] = { { 0, 64, 0, 0 }, { -2, 58, 10, -2 }, { -4, 54, 16, -2 }, { -6, 46, 28, -4 },
+                                     { -4, 36, 36, -4 }, { -4, 28, 46, -6 }, { -2, 16, 54, -4 }, { -2, 10, 58, -2 } };
+
+static inline int ref_px(const pix_t *ref, int pw, int ph, int x, int y)
+{
+    return ref[clip3(y, 0, ph - 1) * pw + clip3(x, 0, pw - 1)];
+}
+
+/* 14-bit intermediate of one reference list at output sample (x,y): the value put_hevc_qpel /
+ * put_hevc_epel would write into its int16 dst */
+static int mc_intermediate(const pix_t *ref, int pw, int ph, int x, int y, int mx, int my, int chroma, int bd)
+{
+    const int taps = chroma ? 4 : 8, before = chroma ? 1 : 3;
+    const int8_t *fx = chroma ? k_epel[mx] : k_qpel[mx];
+    const int8_t *fy = chroma ? k_epel[my] : k_qpel[my];
+    if (!mx && !my) return ref_px(ref, pw, ph, x, y) << (14 - bd);
+    if (mx && !my) {
+        int acc = 0;
+        for (int k = 0; k < taps; k++) acc += fx[k] * ref_px(ref, pw, ph, x + k - before, y);
+        return acc >> (bd - 8);
+    }
+    if (!mx && my) {
+        int acc = 0;
+        for (int k = 0; k < taps; k++) acc += fy[k] * ref_px(ref, pw, ph, x, y + k - before);
+        return acc >> (bd - 8);
+    }
+    int acc2 = 0;
+    for (int j = 0; j < taps; j++) {
+        int acc = 0;
+        for (int k = 0; k < taps; k++) acc += fx[k] * ref_px(ref, pw, ph, x + k - before, y + j - before);
+        acc2 += fy[j] * (int16_t)(acc >> (bd - 8));   /* tmp[] is int16, hevcdsp_template.c:774 */
+    }
+    return acc2 >> 6;
+}
+
+void orc_mc_rec(const B200McRec *m, pix_t *dst, int dst_stride, const pix_t *ref0, const pix_t *ref1,
+                int pw, int ph, int bd)
+{
+    const int chroma = !!(m->flags & B200_MCF_CHROMA);
+    const int mx0 = m->frac0 & 15, my0 = m->frac0 >> 4, mx1 = m->frac1 & 15, my1 = m->frac1 >> 4;
+    const int shift = 14 - bd;
+    for (int y = 0; y < m->h; y++)
+        for (int x = 0; x < m->w; x++) {
+            pix_t *d = &dst[(m->y + y) * dst_stride + m->x + x];
+            int v0 = mc_intermediate(ref0, pw, ph, m->sx0 + x, m->sy0 + y, mx0, my0, chroma, bd), out;
+            if (!(m->flags & B200_MCF_BI)) {
+                if (!(m->flags & B200_MCF_WEIGHTED)) {
+                    /* put_hevc_*_uni_*: full-pel is a plain copy (:626-640), else (v + off) >> (14-BD) */
+                    out = (!mx0 && !my0) ? (v0 >> shift) : clip_pix((v0 + (1 << (shift - 1))) >> shift, bd);
+                } else {
+                    /* put_hevc_*_uni_w_*  :668-690 */
+                    const int s = m->denom + shift;
+                    out = clip_pix(((v0 * m->w0 + (1 << (s - 1))) >> s) + m->o0 * (1 << (bd - 8)), bd);
+                }
+            } else {
+                int v1 = mc_intermediate(ref1, pw, ph, m->sx1 + x, m->sy1 + y, mx1, my1, chroma, bd);
+                v0 = (int16_t)v0;                       /* first list goes through the int16 tmp[] (hevc.c:1761) */
+                if (!(m->flags & B200_MCF_WEIGHTED)) {
+                    out = clip_pix((v1 + v0 + (1 << shift)) >> (shift + 1), bd);        /* :642-666 */
+                } else {
+                    const int log2wd = m->denom + shift;                                   /* :692-720 */
+                    const int o = (m->o0 + m->o1) * (1 << (bd - 8)) + 1;
+                    out = clip_pix((v1 * m->w1 + v0 * m->w0 + (o << log2wd)) >> (log2wd + 1), bd);
+                }
+            }
+            *d = (pix_t)out;
+        }
+}
+
+/* ------------------------------------------------------------------------------------------
+ * Intra prediction.  Reference: hevcpred_template.c:30-344 (neighbour gathering, substitution,
+ * smoothing), :359-384 planar, :388-417 DC, :419-538 angular.  constrained_intra_pred is
+ * resolved on the host (flags in the record are final); the CIP substitution chain itself
+ * (:116-249) is not restated (out of scope for the gate configurations).
+ * ---------------------------------------------------------------------------------------- */
+static const int8_t k_intra_angle[33] = { 32, 26, 21, 17, 13, 9, 5, 2, 0, -2, -5, -9, -13, -17, -21, -26, -32,
+                                          -26, -21, -17, -13, -9, -5, -2, 0, 2, 5, 9, 13, 17, 21, 26, 32 };
+static const int16_t k_inv_angle[15] = { -4096, -1638, -910, -630, -482, -390, -315, -256, -315, -390, -482, -630, -910, -1638, -4096 };
+
+void orc_intra_rec(const B200IntraRec *r, pix_t *plane, int stride, int bd)
+{
+    const int n = 1 << r->log2, n2 = 2 * n;
+    pix_t *src = plane + r->y * stride + r->x;
+    int lbuf[2][65], tbuf[2][65];          /* index 0 holds [-1] */
+    int *left = lbuf[0] + 1, *top = tbuf[0] + 1;
+    int up_left = !!(r->flags & B200_INF_UP_LEFT), up = !!(r->flags & B200_INF_UP), up_right = !!(r->flags & B200_INF_UP_RIGHT);
+    int lft = !!(r->flags & B200_INF_LEFT), bottom_left = !!(r->flags & B200_INF_BOTTOM_LEFT);
+    int i;
+    for (i = -1; i < n2; i++) left[i] = top[i] = 0;
+
+    /* gather what exists (:164-183) */
+    if (up_left) left[-1] = top[-1] = src[-stride - 1];
+    if (up) for (i = 0; i < n; i++) top[i] = src[-stride + i];
+    if (up_right) {
+        for (i = 0; i < r->top_right_size; i++) top[n + i] = src[-stride + n + i];
+        for (; i < n; i++) top[n + i] = src[-stride + n + r->top_right_size - 1];
+    }
+    if (lft) for (i = 0; i < n; i++) left[i] = src[i * stride - 1];
+    if (bottom_left) {
+        for (i = 0; i < r->bottom_left_size; i++) left[n + i] = src[(n + i) * stride - 1];
+        for (; i < n; i++) left[n + i] = src[(n + r->bottom_left_size - 1) * stride - 1];
+    }
+    /* substitution chain (:250-286) */
+    if (!bottom_left) {
+        if (lft) { for (i = 0; i < n; i++) left[n + i] = left[n - 1]; }
+        else if (up_left) { for (i = 0; i < n2; i++) left[i] = left[-1]; lft = 1; }
+        else if (up) { left[-1] = top[0]; for (i = 0; i < n2; i++) left[i] = left[-1]; up_left = lft = 1; }
+        else if (up_right) {
+            for (i = 0; i < n; i++) top[i] = top[n];
+            left[-1] = top[n];
+            for (i = 0; i < n2; i++) left[i] = left[-1];
+            up = up_left = lft = 1;
+        } else {
+            left[-1] = 1 << (bd - 1);
+            for (i = 0; i < n2; i++) top[i] = left[i] = left[-1];
+        }
+    }
+    if (!lft) for (i = 0; i < n; i++) left[i] = left[n];
+    if (!up_left) left[-1] = left[0];
+    if (!up) for (i = 0; i < n; i++) top[i] = left[-1];
+    if (!up_right) for (i = 0; i < n; i++) top[n + i] = top[n - 1];
+    top[-1] = left[-1];
+
+    /* smoothing (:288-327) */
+    const int mode = r->mode;
+    if ((r->flags & B200_INF_FILTER) && mode != 1 && n != 4) {
+        static const int thresh[3] = { 7, 1, 0 };
+        int d26 = iabs(mode - 26), d10 = iabs(mode - 10), dist = d26 < d10 ? d26 : d10;
+        if (dist > thresh[r->log2 - 3]) {
+            int *fl = lbuf[1] + 1, *ft = tbuf[1] + 1;
+            if ((r->flags & B200_INF_STRONG) && r->plane == 0 && r->log2 == 5 &&
+                iabs(top[-1] + top[63] - 2 * top[31]) < (1 << (bd - 5)) &&
+                iabs(left[-1] + left[63] - 2 * left[31]) < (1 << (bd - 5))) {
+                ft[-1] = top[-1]; ft[63] = top[63]; fl[-1] = left[-1]; fl[63] = left[63];
+                for (i = 0; i < 63; i++) {
+                    ft[i] = ((63 - i) * top[-1] + (i + 1) * top[63] + 32) >> 6;
+                    fl[i] = ((63 - i) * left[-1] + (i + 1) * left[63] + 32) >> 6;
+                }
+            } else {
+                fl[n2 - 1] = left[n2 - 1]; ft[n2 - 1] = top[n2 - 1];
+                for (i = n2 - 2; i >= 0; i--) {
+                    fl[i] = (left[i + 1] + 2 * left[i] + left[i - 1] + 2) >> 2;
+                    ft[i] = (top[i + 1] + 2 * top[i] + top[i - 1] + 2) >> 2;
+                }
+                ft[-1] = fl[-1] = (left[0] + 2 * left[-1] + top[0] + 2) >> 2;
+            }
+            left = fl; top = ft;
+        }
+    }
+
+    if (mode == 0) {                                    /* planar :359-371 */
+        for (int y = 0; y < n; y++)
+            for (int x = 0; x < n; x++)
+                src[y * stride + x] = (pix_t)(((n - 1 - x) * left[y] + (x + 1) * top[n] + (n - 1 - y) * top[x] + (y + 1) * left[n] + n) >> (r->log2 + 1));
+    } else if (mode == 1) {                             /* DC :388-417 */
+        int dc = n;
+        for (i = 0; i < n; i++) dc += left[i] + top[i];
+        dc >>= r->log2 + 1;
+        for (int y = 0; y < n; y++) for (int x = 0; x < n; x++) src[y * stride + x] = (pix_t)dc;
+        if (r->plane == 0 && n < 32) {
+            src[0] = (pix_t)((left[0] + 2 * dc + top[0] + 2) >> 2);
+            for (int x = 1; x < n; x++) src[x] = (pix_t)((top[x] + 3 * dc + 2) >> 2);
+            for (int y = 1; y < n; y++) src[y * stride] = (pix_t)((left[y] + 3 * dc + 2) >> 2);
+        }
+    } else {                                            /* angular :419-510 */
+        const int angle = k_intra_angle[mode - 2], last = (n * angle) >> 5;
+        const int vertical = mode >= 18;
+        const int *mainr = vertical ? top : left, *side = vertical ? left : top;
+        int refbuf[3 * 32 + 4], *ref = refbuf + 32;     /* ref[k] == main[k-1] */
+        for (i = 0; i <= n2; i++) ref[i] = mainr[i - 1];
+        if (angle < 0 && last < -1)
+            for (i = last; i <= -1; i++) ref[i] = side[-1 + ((i * k_inv_angle[mode - 11] + 128) >> 8)];
+        for (int a = 0; a < n; a++) {                   /* a runs along the prediction direction */
+            const int idx = ((a + 1) * angle) >> 5, fact = ((a + 1) * angle) & 31;
+            for (int b = 0; b < n; b++) {
+                int v = fact ? ((32 - fact) * ref[b + idx + 1] + fact * ref[b + idx + 2] + 16) >> 5 : ref[b + idx + 1];
+                if (vertical) src[a * stride + b] = (pix_t)v; else src[b * stride + a] = (pix_t)v;
+            }
+        }
+        if (r->plane == 0 && n < 32) {
+            if (mode == 26) for (int y = 0; y < n; y++) src[y * stride] = (pix_t)clip_pix(top[0] + ((left[y] - left[-1]) >> 1), bd);
+            if (mode == 10) for (int x = 0; x < n; x++) src[x] = (pix_t)clip_pix(left[0] + ((top[x] - top[-1]) >> 1), bd);
+        }
+    }
+}
+
+/* ------------------------------------------------------------------------------------------
+ * Deblocking.  Reference: hevcdsp_template.c:1629-1723 (luma), :1725-1755 (chroma).
+ * One call of the table function covers two 4-line segments; here one segment at a time.
+ * xs = step across the edge, ys = step along it.
+ * ---------------------------------------------------------------------------------------- */
+void orc_deblock_luma_seg(pix_t *pix, int xs, int ys, int beta8, int tc8, int no_p, int no_q, int bd)
+{
+    const int beta = beta8 << (bd - 8), tc = tc8 << (bd - 8);
+#define PX(i, l) ((int)pix[(i) * xs + (l) * ys])
+    const int dp0 = iabs(PX(-3, 0) - 2 * PX(-2, 0) + PX(-1, 0)), dq0 = iabs(PX(2, 0) - 2 * PX(1, 0) + PX(0, 0));
+    const int dp3 = iabs(PX(-3, 3) - 2 * PX(-2, 3) + PX(-1, 3)), dq3 = iabs(PX(2, 3) - 2 * PX(1, 3) + PX(0, 3));
+    const int d0 = dp0 + dq0, d3 = dp3 + dq3;
+    if (d0 + d3 >= beta) return;
+    const int tc25 = (tc * 5 + 1) >> 1;
+    const int strong = iabs(PX(-4, 0) - PX(-1, 0)) + iabs(PX(3, 0) - PX(0, 0)) < (beta >> 3) && iabs(PX(-1, 0) - PX(0, 0)) < tc25 &&
+                       iabs(PX(-4, 3) - PX(-1, 3)) + iabs(PX(3, 3) - PX(0, 3)) < (beta >> 3) && iabs(PX(-1, 3) - PX(0, 3)) < tc25 &&
+                       (d0 << 1) < (beta >> 2) && (d3 << 1) < (beta >> 2);
+    const int nd_p = dp0 + dp3 < ((beta + (beta >> 1)) >> 3), nd_q = dq0 + dq3 < ((beta + (beta >> 1)) >> 3);
+    for (int l = 0; l < 4; l++) {
+        const int p3 = PX(-4, l), p2 = PX(-3, l), p1 = PX(-2, l), p0 = PX(-1, l);
+        const int q0 = PX(0, l), q1 = PX(1, l), q2 = PX(2, l), q3 = PX(3, l);
+        pix_t *p = pix + l * ys;
+        if (strong) {
+            const int t2 = tc << 1;
+            if (!no_p) {
+                p[-1 * xs] = (pix_t)(p0 + clip3(((p2 + 2 * p1 + 2 * p0 + 2 * q0 + q1 + 4) >> 3) - p0, -t2, t2));
+                p[-2 * xs] = (pix_t)(p1 + clip3(((p2 + p1 + p0 + q0 + 2) >> 2) - p1, -t2, t2));
+                p[-3 * xs] = (pix_t)(p2 + clip3(((2 * p3 + 3 * p2 + p1 + p0 + q0 + 4) >> 3) - p2, -t2, t2));
+            }
+            if (!no_q) {
+                p[0]      = (pix_t)(q0 + clip3(((p1 + 2 * p0 + 2 * q0 + 2 * q1 + q2 + 4) >> 3) - q0, -t2, t2));
+                p[xs]     = (pix_t)(q1 + clip3(((p0 + q0 + q1 + q2 + 2) >> 2) - q1, -t2, t2));
+                p[2 * xs] = (pix_t)(q2 + clip3(((2 * q3 + 3 * q2 + q1 + q0 + p0 + 4) >> 3) - q2, -t2, t2));
+            }
+        } else {
+            int delta = (9 * (q0 - p0) - 3 * (q1 - p1) + 8) >> 4;
+            if (iabs(delta) < 10 * tc) {
+                const int th = tc >> 1;
+                delta = clip3(delta, -tc, tc);
+                if (!no_p) p[-1 * xs] = (pix_t)clip_pix(p0 + delta, bd);
+                if (!no_q) p[0]       = (pix_t)clip_pix(q0 - delta, bd);
+                if (!no_p && nd_p) p[-2 * xs] = (pix_t)clip_pix(p1 + clip3((((p2 + p0 + 1) >> 1) - p1 + delta) >> 1, -th, th), bd);
+                if (!no_q && nd_q) p[xs]      = (pix_t)clip_pix(q1 + clip3((((q2 + q0 + 1) >> 1) - q1 - delta) >> 1, -th, th), bd);
+            }
+        }
+    }
+#undef PX
+}
+
+void orc_deblock_chroma_seg(pix_t *pix, int xs, int ys, int tc8, int no_p, int no_q, int bd)
+{
+    const int tc = tc8 << (bd - 8);
+    if (tc <= 0) return;
+    for (int l = 0; l < 4; l++) {
+        pix_t *p = pix + l * ys;
+        const int p1 = p[-2 * xs], p0 = p[-xs], q0 = p[0], q1 = p[xs];
+        const int delta = clip3((((q0 - p0) * 4) + p1 - q1 + 4) >> 3, -tc, tc);
+        if (!no_p) p[-xs] = (pix_t)clip_pix(p0 + delta, bd);
+        if (!no_q) p[0]   = (pix_t)clip_pix(q0 - delta, bd);
+    }
+}
+
+/* whole-picture deblocking of one plane: every vertical edge, then every horizontal edge
+ * (the semantic order; the reference's CTB-staggered schedule hevc_filter.c:1027-1064 is equivalent) */
+static void deblock_plane(pix_t *pl, int pw, int ph, int plane, const uint16_t *grid, const B200DbkLayout *L, int bd)
+{
+    for (int dir = 0; dir < 2; dir++) {
+        const uint16_t *g = grid + L->off[plane][dir];
+        const int gs = (int)L->stride[plane][dir];
+        if (dir == 0) {
+            for (int y = 0; y + 4 <= ph; y += 4)
+                for (int x = 8; x < pw; x += 8) {
+                    uint16_t e = g[(y >> 2) * gs + (x >> 3)];
+                    if (!(e & B200_DBK_PRESENT)) continue;
+                    if (plane == 0) orc_deblock_luma_seg(pl + y * pw + x, 1, pw, B200_DBK_BETA(e), B200_DBK_TC(e), B200_DBK_NOP(e), B200_DBK_NOQ(e), bd);
+                    else            orc_deblock_chroma_seg(pl + y * pw + x, 1, pw, B200_DBK_TC(e), B200_DBK_NOP(e), B200_DBK_NOQ(e), bd);
+                }
+        } else {
+            for (int y = 8; y < ph; y += 8)
+                for (int x = 0; x + 4 <= pw; x += 4) {
+                    uint16_t e = g[(y >> 3) * gs + (x >> 2)];
+                    if (!(e & B200_DBK_PRESENT)) continue;
+                    if (plane == 0) orc_deblock_luma_seg(pl + y * pw + x, pw, 1, B200_DBK_BETA(e), B200_DBK_TC(e), B200_DBK_NOP(e), B200_DBK_NOQ(e), bd);
+                    else            orc_deblock_chroma_seg(pl + y * pw + x, pw, 1, B200_DBK_TC(e), B200_DBK_NOP(e), B200_DBK_NOQ(e), bd);
+                }
+        }
+    }
+}
+
+/* ------------------------------------------------------------------------------------------
+ * SAO.  Reference: hevcdsp_template.c:340-365 (band), :372-567 (edge + border / restore rules);
+ * driver hevc_filter.c:197-322.  src = deblocked picture (never modified), dst = output.
+ * ---------------------------------------------------------------------------------------- */
+void orc_sao_ctb(const B200SaoRec *s, pix_t *dst, const pix_t *src, int stride, int x0, int y0, int w, int h, int bd)
+{
+    if (s->type == B200_SAO_BAND) {
+        int tab[32] = { 0 };
+        for (int k = 0; k < 4; k++) tab[(k + s->param) & 31] = s->offset_val[k + 1];
+        for (int y = 0; y < h; y++)
+            for (int x = 0; x < w; x++) {
+                int v = src[(y0 + y) * stride + x0 + x];
+                dst[(y0 + y) * stride + x0 + x] = (pix_t)clip_pix(v + tab[v >> (bd - 5)], bd);
+            }
+        return;
+    }
+    static const int8_t pos[4][2][2] = { { { -1, 0 }, { 1, 0 } }, { { 0, -1 }, { 0, 1 } }, { { -1, -1 }, { 1, 1 } }, { { 1, -1 }, { -1, 1 } } };
+    static const uint8_t edge_idx[5] = { 1, 2, 0, 3, 4 };
+    const int cls = s->param;
+    const int bl = s->borders & 1, bt = (s->borders >> 1) & 1, br = (s->borders >> 2) & 1, bb = (s->borders >> 3) & 1;
+    const int ve0 = s->edges & 1, ve1 = (s->edges >> 1) & 1, he0 = (s->edges >> 2) & 1, he1 = (s->edges >> 3) & 1;
+    const int de0 = (s->edges >> 4) & 1, de1 = (s->edges >> 5) & 1, de2 = (s->edges >> 6) & 1, de3 = (s->edges >> 7) & 1;
+    /* geometry after the border trimming of :433-471 */
+    const int init_x = (cls != 1 && bl) ? 1 : 0, wid = (cls != 1 && br) ? w - 1 : w;
+    const int hei = (cls != 0 && bb) ? h - 1 : h;
+    for (int y = 0; y < h; y++)
+        for (int x = 0; x < w; x++) {
+            const pix_t *c = src + (y0 + y) * stride + x0 + x;
+            int v = *c, out;
+            int zero_off = 0;                           /* picture-border lines: offset_val[0] (== 0) */
+            if (cls != 1 && ((bl && x == 0) || (br && x == w - 1))) zero_off = 1;
+            if (cls != 0 && ((bt && y == 0) || (bb && y == h - 1))) zero_off = 1;
+            if (zero_off) out = clip_pix(v + s->offset_val[0], bd);
+            else {
+                int a = c[pos[cls][0][0] + pos[cls][0][1] * stride], b = c[pos[cls][1][0] + pos[cls][1][1] * stride];
+                int d0 = (v > a) - (v < a), d1 = (v > b) - (v < b);
+                out = clip_pix(v + s->offset_val[edge_idx[2 + d0 + d1]], bd);
+            }
+            if (s->variant) {                           /* :533-566 not-across-boundary restore */
+                const int sul = !de0 && cls == 2 && !bl && !bt, sur = !de1 && cls == 3 && !bt && !br;   /* 2 = SAO_EO_135D, 3 = SAO_EO_45D */
+                const int slr = !de2 && cls == 2 && !br && !bb, sll = !de3 && cls == 3 && !bl && !bb;
+                int restore = 0;
+                if (ve0 && cls != 1 && x == 0 && y >= sul && y < hei - sll) restore = 1;
+                if (ve1 && cls != 1 && x == wid - 1 && y >= sur && y < hei - slr) restore = 1;
+                if (he0 && cls != 0 && y == 0 && x >= init_x + sul && x < wid - sur) restore = 1;
+                if (he1 && cls != 0 && y == hei - 1 && x >= init_x + sll && x < wid - slr) restore = 1;
+                if (de0 && cls == 2 && x == 0 && y == 0) restore = 1;
+                if (de1 && cls == 3 && x == wid - 1 && y == 0) restore = 1;
+                if (de2 && cls == 2 && x == wid - 1 && y == hei - 1) restore = 1;
+                if (de3 && cls == 3 && x == 0 && y == hei - 1) restore = 1;
+                if (restore) out = v;
+            }
+            dst[(y0 + y) * stride + x0 + x] = (pix_t)out;
+        }
+}
+
+/* ------------------------------------------------------------------------------------------
+ * Whole-picture executor: the CPU statement of what the GPU stages K1..K5 compute for one blob.
+ * planes[slot*3 + c] = uint16 plane of DPB slot `slot`, stride = plane width.
+ * Returns 0, or a negative number for a malformed blob.
+ * ---------------------------------------------------------------------------------------- */
+int orc_execute_blob(const uint8_t *blob, uint16_t **planes, int n_slots)
+{
+    const B200BlobHeader *h = (const B200BlobHeader *)blob;
+    if (h->magic != B200_BLOB_MAGIC || h->version != B200_BLOB_VERSION) return -1;
+    if (h->cur_slot >= n_slots) return -2;
+    const int bd = h->bit_depth, cfi = h->chroma_format_idc;
+    int pw[3], ph[3];
+    for (int p = 0; p < 3; p++) b200_plane_dims(h->width, h->height, cfi, p, &pw[p], &ph[p]);
+    pix_t **cur = planes + 3 * h->cur_slot;
+
+    /* private copy of the pool: residuals are produced in place */
+    const uint32_t n_coeff = h->sec[B200_SEC_COEFF].count;
+    int16_t *pool = (int16_t *)malloc((size_t)(n_coeff + 8) * sizeof(int16_t));
+    if (!pool) return -3;
+    memcpy(pool, blob + h->sec[B200_SEC_COEFF].off, (size_t)n_coeff * sizeof(int16_t));
+
+    /* K1 inter */
+    const B200McRec *mc = (const B200McRec *)(blob + h->sec[B200_SEC_MC].off);
+    for (uint32_t i = 0; i < h->sec[B200_SEC_MC].count; i++) {
+        const B200McRec *m = &mc[i];
+        if (m->ref0 >= n_slots || ((m->flags & B200_MCF_BI) && m->ref1 >= n_slots)) { free(pool); return -4; }
+        const int p = m->plane;
+        orc_mc_rec(m, cur[p], pw[p], planes[3 * m->ref0 + p], planes[3 * ((m->flags & B200_MCF_BI) ? m->ref1 : m->ref0) + p], pw[p], ph[p], bd);
+    }
+    /* K2 residual */
+    for (int s = B200_SEC_TU4; s <= B200_SEC_TU32; s++) {
+        const B200TuRec *tu = (const B200TuRec *)(blob + h->sec[s].off);
+        for (uint32_t i = 0; i < h->sec[s].count; i++) {
+            const B200TuRec *t = &tu[i];
+            int16_t *c = pool + t->coeff_off;
+            const int n = 1 << t->log2, p = t->plane;
+            if (t->kind == B200_TU_PCM) {
+                for (int y = 0; y < n; y++) for (int x = 0; x < n; x++) cur[p][(t->y + y) * pw[p] + t->x + x] = (pix_t)c[y * n + x];
+                continue;
+            }
+            tu_residual(t, c, bd);
+            if (!(t->flags & B200_TUF_PARK))
+                orc_add_residual(cur[p] + t->y * pw[p] + t->x, pw[p], c, n, bd);
+        }
+    }
+    /* K3 intra, decode order */
+    const B200IntraRec *ir = (const B200IntraRec *)(blob + h->sec[B200_SEC_INTRA].off);
+    for (uint32_t i = 0; i < h->sec[B200_SEC_INTRA].count; i++) {
+        const B200IntraRec *r = &ir[i];
+        const int p = r->plane;
+        orc_intra_rec(r, cur[p], pw[p], bd);
+        if (r->resid_off != B200_NO_RESID)
+            orc_add_residual(cur[p] + r->y * pw[p] + r->x, pw[p], pool + r->resid_off, 1 << r->log2, bd);
+    }
+    free(pool);
+    /* K4 deblock */
+    if (h->sec[B200_SEC_DBK].count) {
+        B200DbkLayout L;
+        b200_dbk_layout(h->width, h->height, cfi, &L);
+        const uint16_t *grid = (const uint16_t *)(blob + h->sec[B200_SEC_DBK].off);
+        for (int p = 0; p < 3; p++) deblock_plane(cur[p], pw[p], ph[p], p, grid, &L, bd);
+    }
+    /* K5 SAO */
+    if (h->sec[B200_SEC_SAO].count) {
+        const B200SaoRec *sg = (const B200SaoRec *)(blob + h->sec[B200_SEC_SAO].off);
+        const int ctb = 1 << h->log2_ctb_size;
+        const int cw = (h->width + ctb - 1) >> h->log2_ctb_size, chh = (h->height + ctb - 1) >> h->log2_ctb_size;
+        for (int p = 0; p < 3; p++) {
+            const int hs = p && cfi != 3, vs = p && cfi == 1;
+            pix_t *copy = (pix_t *)malloc((size_t)pw[p] * ph[p] * sizeof(pix_t));
+            if (!copy) return -3;
+            memcpy(copy, cur[p], (size_t)pw[p] * ph[p] * sizeof(pix_t));
+            for (int cy = 0; cy < chh; cy++)
+                for (int cx = 0; cx < cw; cx++) {
+                    const B200SaoRec *s = &sg[p * cw * chh + cy * cw + cx];
+                    if (s->type == B200_SAO_NONE) continue;
+                    const int x0 = (cx << h->log2_ctb_size) >> hs, y0 = (cy << h->log2_ctb_size) >> vs;
+                    int w = ctb >> hs, hh = ctb >> vs;
+                    if (w > pw[p] - x0) w = pw[p] - x0;
+                    if (hh > ph[p] - y0) hh = ph[p] - y0;
+                    orc_sao_ctb(s, cur[p], copy, pw[p], x0, y0, w, hh, bd);
+                }
+            free(copy);
+        }
+    }
+    return 0;
+}
