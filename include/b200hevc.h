@@ -1,0 +1,108 @@
+/*
+ * b200hevc.h — C ABI of libb200hevc.so, the B200 (sm_100a) back end for openHEVC's
+ * per-CTU pixel-reconstruction path.
+ *
+ * Layering:
+ *   reference call sites (hevc.c / hevc_cabac.c / hevc_filter.c, unchanged)
+ *     -> table slots installed by ff_hevcdsp_init_b200() & co. (include/b200hevc_tables.h; the
+ *        same mechanism as ff_hevcdsp_init_x86, reference libavcodec/hevcdsp.c:1326-1327)
+ *     -> recorder  b200_rec_*()        : appends one record per table call to the frame's blob
+ *     -> engine    b200_frame_submit() : one pinned cudaMemcpyAsync + one kernel per stage
+ *
+ * Everything here is plain C: pointers, sizes, ints.  No CUDA / torch types.
+ * All functions returning int return 0 on success or a negative B200_E* code; the text of the
+ * last error of a context is available from b200_last_error().  Nothing here falls back to the
+ * CPU: without a CUDA device b200_ctx_create() fails.
+ */
+#ifndef B200HEVC_H
+#define B200HEVC_H
+
+#include <stddef.h>
+#include <stdint.h>
+#include "b200hevc_worklist.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define B200_EINVAL   (-1)  /* bad argument / malformed blob        */
+#define B200_ECUDA    (-2)  /* CUDA runtime error (latched)         */
+#define B200_ENOMEM   (-3)
+#define B200_ESTATE   (-4)  /* call sequence error                  */
+#define B200_ENOTSUP  (-5)  /* feature outside the implemented path */
+
+typedef struct B200Ctx B200Ctx;
+typedef struct B200Rec B200Rec;
+
+typedef struct B200Config {
+    int32_t device;             /* CUDA device ordinal                                               */
+    int32_t width, height;      /* luma samples: sps->width / sps->height (libavcodec/hevc.h)        */
+    int32_t chroma_format_idc;  /* 1 = 4:2:0, 2 = 4:2:2, 3 = 4:4:4                                   */
+    int32_t bit_depth;          /* 8..12 (luma == chroma, as the reference requires hevc_ps.c:1654)   */
+    int32_t log2_ctb_size;      /* 4..6                                                              */
+    int32_t n_slots;            /* device-resident DPB slots (reference: HEVCFrame DPB[32], hevc.h:1207) */
+    int32_t n_arenas;           /* blobs in flight (upload of frame k+1 overlaps kernels of frame k)  */
+    uint64_t max_blob_bytes;    /* capacity of one device arena; 0 = worst case for the geometry     */
+    void    *ext_frame_mem;     /* optional caller-owned device memory for the DPB (e.g. a torch      */
+    uint64_t ext_frame_bytes;   /*   tensor, so that torch.distributed can broadcast slots), else NULL/0 */
+} B200Config;
+
+/* ---- context --------------------------------------------------------------------------------- */
+int         b200_ctx_create(const B200Config *cfg, B200Ctx **out);
+void        b200_ctx_destroy(B200Ctx *ctx);
+const char *b200_last_error(const B200Ctx *ctx);          /* ctx may be NULL: error of the failed create */
+uint64_t    b200_dpb_bytes(const B200Config *cfg);         /* device bytes needed for cfg->n_slots slots   */
+uint64_t    b200_slot_bytes(const B200Ctx *ctx);           /* bytes of one slot (3 planes, pitched)        */
+void       *b200_slot_devptr(const B200Ctx *ctx, int slot, int plane, uint64_t *pitch_bytes);
+void       *b200_stream(const B200Ctx *ctx);               /* the compute cudaStream_t, for external event waits */
+
+/* ---- pinned host memory for blobs / frames ---------------------------------------------------- */
+void *b200_host_alloc(uint64_t bytes);
+void  b200_host_free(void *p);
+
+/* ---- per-frame execution ---------------------------------------------------------------------- */
+/* Upload `blob` (include/b200hevc_worklist.h) into arena `arena` on the copy stream (asynchronous when the blob
+ * lives in b200_host_alloc memory).  Waits (stream-side) until the arena's previous frame has finished. */
+int b200_frame_upload(B200Ctx *ctx, const void *blob, uint64_t nbytes, int arena);
+/* Run K1..K5 for the blob resident in `arena`: reconstructs the picture into DPB slot hdr.cur_slot. */
+int b200_frame_execute(B200Ctx *ctx, int arena);
+/* upload + execute, arenas used round-robin: the call the recorder's frame_end makes (hevc.c:3446). */
+int b200_frame_submit(B200Ctx *ctx, const void *blob, uint64_t nbytes);
+
+/* Planes are exchanged in the reference's AVFrame layout: planar, uint8 samples for 8-bit,
+ * little-endian uint16 above; strides in bytes.  (libavcodec/hevc_ps.c:1666-1688) */
+int b200_slot_upload(B200Ctx *ctx, int slot, const void *const planes[3], const int64_t strides[3]);
+int b200_slot_readback(B200Ctx *ctx, int slot, void *const planes[3], const int64_t strides[3]); /* async after the slot's last writer */
+int b200_slot_fill(B200Ctx *ctx, int slot, int value);    /* generate_missing_ref, hevc_refs.c:538-606 */
+int b200_sync(B200Ctx *ctx);                               /* wait for everything, surface latched errors */
+
+/* ---- measurement ------------------------------------------------------------------------------ */
+enum { B200_ST_MC = 0, B200_ST_RESIDUAL, B200_ST_INTRA, B200_ST_DEBLOCK, B200_ST_SAO, B200_ST_TOTAL, B200_ST_COUNT };
+int      b200_set_profiling(B200Ctx *ctx, int on);         /* CUDA events around every stage            */
+int      b200_get_stage_ms(B200Ctx *ctx, float ms[B200_ST_COUNT]); /* of the last executed frame (syncs) */
+uint64_t b200_launch_count(const B200Ctx *ctx);            /* kernels launched by this context so far   */
+
+/* ---- recorder: host side, builds one blob per picture ------------------------------------------
+ * One B200Rec per decoding thread context and picture in flight.  b200_rec_* mirror the table
+ * slots one to one; coordinates are in samples of `plane`. */
+int  b200_rec_create(const B200Config *cfg, B200Rec **out);
+void b200_rec_destroy(B200Rec *r);
+int  b200_rec_begin(B200Rec *r, int cur_slot, int poc);                   /* hevc_frame_start, hevc.c:3197 */
+/* transform_add[log2-2](dst, coeffs, stride) preceded by kind/flags recorded from idct*/
+int  b200_rec_tu(B200Rec *r, int plane, int x, int y, int log2, int kind, int flags, int col_limit,
+                 const int16_t *coeffs, int intra_linked);
+int  b200_rec_pcm(B200Rec *r, int plane, int x, int y, int log2, const int16_t *samples);
+int  b200_rec_intra(B200Rec *r, int plane, int x, int y, int log2, int mode, int flags,
+                    int top_right_size, int bottom_left_size);
+/* one put_hevc_{q,e}pel_{uni,uni_w} call, or a put_hevc_*pel + put_hevc_*pel_bi[_w] pair (split into tiles here) */
+int  b200_rec_mc(B200Rec *r, const B200McRec *whole_block /* w,h up to 64 */);
+int  b200_rec_deblock(B200Rec *r, int plane, int vertical, int x, int y, int beta, const int tc[2],
+                      const uint8_t no_p[2], const uint8_t no_q[2]);
+int  b200_rec_sao(B200Rec *r, int plane, int x, int y, const B200SaoRec *params);
+/* finish: returns the blob (pinned memory owned by the recorder, valid until the next begin) */
+int  b200_rec_finish(B200Rec *r, const void **blob, uint64_t *nbytes);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B200HEVC_H */

@@ -55,7 +55,7 @@ typedef struct B200BlobHeader {
     uint8_t  cur_slot;           /* DPB slot that receives this picture                        */
     uint32_t flags;              /* B200_FRAME_*                                               */
     B200Section sec[B200_SEC_COUNT];
-    uint32_t reserved[64 - 6 - 2 * B200_SEC_COUNT];
+    uint32_t reserved[64 - 7 - 2 * B200_SEC_COUNT];
 } B200BlobHeader;               /* 256 bytes */
 
 #define B200_FRAME_HAS_DEBLOCK 1u
@@ -162,6 +162,14 @@ typedef struct B200SaoRec {      /* 16 bytes; grid index = plane * ctb_count + c
     uint8_t  pad;
     int16_t  offset_val[5];      /* sao->offset_val[c_idx][0..4]                                      */
 } B200SaoRec;
+
+#ifdef __cplusplus
+static_assert(sizeof(B200BlobHeader) == 256 && sizeof(B200TuRec) == 16 && sizeof(B200IntraRec) == 16 &&
+              sizeof(B200McRec) == 32 && sizeof(B200SaoRec) == 16, "blob v1 layout");
+#else
+_Static_assert(sizeof(B200BlobHeader) == 256 && sizeof(B200TuRec) == 16 && sizeof(B200IntraRec) == 16 &&
+               sizeof(B200McRec) == 32 && sizeof(B200SaoRec) == 16, "blob v1 layout");
+#endif
 
 static inline uint32_t b200_align_u32(uint32_t v, uint32_t a) { return (v + a - 1) / a * a; }
 

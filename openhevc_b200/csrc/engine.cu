@@ -1,0 +1,442 @@
+// engine.cu — context, device-resident DPB, upload arenas and the per-frame stage pipeline
+// behind the C ABI of include/b200hevc.h.
+//
+// Streams: `copy` carries the one pinned H2D upload per picture, `compute` runs K1..K5 in
+// submission (= decode) order so inter-picture dependencies are stream order, `down` carries
+// read-backs.  Arenas are double(+)-buffered: the upload of picture k+1 overlaps the kernels
+// of picture k (events ev_uploaded / ev_done per arena).
+#include <cuda_runtime.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <stdarg.h>
+#include <mutex>
+#include "../../include/b200hevc.h"
+#include "common.cuh"
+
+#define MAX_SLOTS 64
+#define MAX_ARENAS 8
+
+struct Arena {
+    uint8_t *dev = nullptr;
+    uint8_t *stage = nullptr;       // pinned staging for blobs that are not in pinned memory
+    B200BlobHeader hdr;             // host copy of the resident blob's header
+    bool resident = false;
+    cudaEvent_t ev_uploaded = nullptr, ev_done = nullptr;
+};
+
+struct B200Ctx {
+    B200Config cfg;
+    int pw[3], ph[3], pitch[3];
+    size_t plane_off[3], slot_bytes;
+    uint8_t *dpb = nullptr;          // n_slots + 1 frames (last = pre-SAO work picture)
+    bool own_dpb = false;
+    uint8_t *work = nullptr;
+    FrameDesc *dpb_desc_dev = nullptr;
+    FrameDesc slot_desc[MAX_SLOTS + 1];
+    uint32_t *flags[3] = { nullptr, nullptr, nullptr };
+    int flag_stride[3];
+    uint32_t *counter = nullptr;
+    Arena arena[MAX_ARENAS];
+    uint64_t arena_bytes = 0;
+    int next_arena = 0;
+    cudaStream_t st_copy = nullptr, st_compute = nullptr, st_down = nullptr;
+    cudaEvent_t slot_done[MAX_SLOTS];
+    cudaEvent_t prof[B200_ST_COUNT + 1];
+    bool profiling = false, prof_valid = false;
+    uint64_t launches = 0;
+    B200DbkLayout dbk;
+    int ctb_w, ctb_h;
+    char err[512];
+    int err_code = 0;
+};
+
+static char g_create_err[512];
+static std::mutex g_mu;
+
+static int fail(B200Ctx *ctx, int code, const char *fmt, ...)
+{
+    char *dst = ctx ? ctx->err : g_create_err;
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(dst, 512, fmt, ap);
+    va_end(ap);
+    if (ctx && !ctx->err_code) ctx->err_code = code;
+    return code;
+}
+#define CU(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) return fail(ctx, B200_ECUDA, "%s: %s", #call, cudaGetErrorString(e_)); } while (0)
+
+static void geometry(const B200Config *c, int pw[3], int ph[3], int pitch[3], size_t off[3], size_t *slot_bytes)
+{
+    const int B = c->bit_depth > 8 ? 2 : 1;
+    size_t o = 0;
+    for (int p = 0; p < 3; p++) {
+        b200_plane_dims(c->width, c->height, c->chroma_format_idc, p, &pw[p], &ph[p]);
+        pitch[p] = (pw[p] * B + 255) & ~255;
+        off[p] = o;
+        o += (size_t)pitch[p] * ph[p];
+        o = (o + 1023) & ~(size_t)1023;
+    }
+    *slot_bytes = o;
+}
+
+static uint64_t worst_blob_bytes(const B200Config *c)
+{
+    // every sample coded (int16) + a record per 4x4 of every list + grids + slack
+    uint64_t samples = 0;
+    for (int p = 0; p < 3; p++) { int w, h; b200_plane_dims(c->width, c->height, c->chroma_format_idc, p, &w, &h); samples += (uint64_t)w * h; }
+    B200DbkLayout L;
+    b200_dbk_layout(c->width, c->height, c->chroma_format_idc, &L);
+    const uint64_t u = samples / 16;
+    return 4096 + samples * 2 + u * (16 + 16 + 32) + (uint64_t)L.total * 2 + (1u << 20);
+}
+
+static bool config_ok(const B200Config *c)
+{
+    return c && c->width >= 16 && c->height >= 16 && c->width <= 16384 && c->height <= 16384 && !(c->width & 7) && !(c->height & 7) &&
+           c->chroma_format_idc >= 1 && c->chroma_format_idc <= 3 && c->bit_depth >= 8 && c->bit_depth <= 12 &&
+           c->log2_ctb_size >= 4 && c->log2_ctb_size <= 6 && c->n_slots >= 1 && c->n_slots <= MAX_SLOTS &&
+           c->n_arenas >= 1 && c->n_arenas <= MAX_ARENAS;
+}
+
+extern "C" uint64_t b200_dpb_bytes(const B200Config *cfg)
+{
+    if (!config_ok(cfg)) return 0;
+    int pw[3], ph[3], pitch[3];
+    size_t off[3], sb;
+    geometry(cfg, pw, ph, pitch, off, &sb);
+    return (uint64_t)sb * cfg->n_slots;
+}
+
+extern "C" const char *b200_last_error(const B200Ctx *ctx) { return ctx ? ctx->err : g_create_err; }
+extern "C" uint64_t b200_slot_bytes(const B200Ctx *ctx) { return ctx->slot_bytes; }
+extern "C" void *b200_stream(const B200Ctx *ctx) { return ctx->st_compute; }
+extern "C" uint64_t b200_launch_count(const B200Ctx *ctx) { return ctx->launches; }
+
+extern "C" void *b200_slot_devptr(const B200Ctx *ctx, int slot, int plane, uint64_t *pitch_bytes)
+{
+    if (!ctx || slot < 0 || slot >= ctx->cfg.n_slots || plane < 0 || plane > 2) return nullptr;
+    if (pitch_bytes) *pitch_bytes = ctx->pitch[plane];
+    return ctx->slot_desc[slot].p[plane].base;
+}
+
+extern "C" void *b200_host_alloc(uint64_t bytes)
+{
+    void *p = nullptr;
+    if (cudaHostAlloc(&p, bytes, cudaHostAllocDefault) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+    return p;
+}
+extern "C" void b200_host_free(void *p) { if (p) cudaFreeHost(p); }
+
+extern "C" void b200_ctx_destroy(B200Ctx *ctx)
+{
+    if (!ctx) return;
+    cudaSetDevice(ctx->cfg.device);
+    cudaDeviceSynchronize();
+    for (int i = 0; i < MAX_ARENAS; i++) {
+        if (ctx->arena[i].dev) cudaFree(ctx->arena[i].dev);
+        if (ctx->arena[i].stage) cudaFreeHost(ctx->arena[i].stage);
+        if (ctx->arena[i].ev_uploaded) cudaEventDestroy(ctx->arena[i].ev_uploaded);
+        if (ctx->arena[i].ev_done) cudaEventDestroy(ctx->arena[i].ev_done);
+    }
+    for (int i = 0; i < MAX_SLOTS; i++) if (ctx->slot_done[i]) cudaEventDestroy(ctx->slot_done[i]);
+    for (int i = 0; i <= B200_ST_COUNT; i++) if (ctx->prof[i]) cudaEventDestroy(ctx->prof[i]);
+    if (ctx->own_dpb && ctx->dpb) cudaFree(ctx->dpb);
+    if (ctx->work) cudaFree(ctx->work);
+    if (ctx->dpb_desc_dev) cudaFree(ctx->dpb_desc_dev);
+    for (int p = 0; p < 3; p++) if (ctx->flags[p]) cudaFree(ctx->flags[p]);
+    if (ctx->counter) cudaFree(ctx->counter);
+    if (ctx->st_copy) cudaStreamDestroy(ctx->st_copy);
+    if (ctx->st_compute) cudaStreamDestroy(ctx->st_compute);
+    if (ctx->st_down) cudaStreamDestroy(ctx->st_down);
+    delete ctx;
+}
+
+static int ctx_init(B200Ctx *ctx)
+{
+    const B200Config &c = ctx->cfg;
+    CU(cudaSetDevice(c.device));
+    cudaDeviceProp prop;
+    CU(cudaGetDeviceProperties(&prop, c.device));
+    if (prop.major < 10) return fail(ctx, B200_ENOTSUP, "device %d is sm_%d%d; this library carries sm_100a code only", c.device, prop.major, prop.minor);
+    geometry(&c, ctx->pw, ctx->ph, ctx->pitch, ctx->plane_off, &ctx->slot_bytes);
+    const uint64_t need = (uint64_t)ctx->slot_bytes * c.n_slots;
+    if (c.ext_frame_mem) {
+        if (c.ext_frame_bytes < need) return fail(ctx, B200_EINVAL, "ext_frame_bytes %llu < required %llu", (unsigned long long)c.ext_frame_bytes, (unsigned long long)need);
+        if ((uintptr_t)c.ext_frame_mem & 255) return fail(ctx, B200_EINVAL, "ext_frame_mem must be 256-byte aligned");
+        ctx->dpb = (uint8_t *)c.ext_frame_mem;
+    } else {
+        CU(cudaMalloc(&ctx->dpb, need));
+        ctx->own_dpb = true;
+        CU(cudaMemset(ctx->dpb, 0, need));
+    }
+    CU(cudaMalloc(&ctx->work, ctx->slot_bytes));
+    CU(cudaMemset(ctx->work, 0, ctx->slot_bytes));
+    for (int s = 0; s <= c.n_slots; s++) {
+        uint8_t *base = s < c.n_slots ? ctx->dpb + (size_t)s * ctx->slot_bytes : ctx->work;
+        for (int p = 0; p < 3; p++) {
+            PlaneDesc &d = ctx->slot_desc[s].p[p];
+            d.base = base + ctx->plane_off[p]; d.pitch = ctx->pitch[p]; d.w = ctx->pw[p]; d.h = ctx->ph[p];
+        }
+    }
+    CU(cudaMalloc(&ctx->dpb_desc_dev, sizeof(FrameDesc) * (c.n_slots + 1)));
+    CU(cudaMemcpy(ctx->dpb_desc_dev, ctx->slot_desc, sizeof(FrameDesc) * (c.n_slots + 1), cudaMemcpyHostToDevice));
+    for (int p = 0; p < 3; p++) {
+        ctx->flag_stride[p] = (ctx->pw[p] + 3) / 4 + 1;
+        const size_t n = (size_t)ctx->flag_stride[p] * ((ctx->ph[p] + 3) / 4 + 1);
+        CU(cudaMalloc(&ctx->flags[p], n * 4));
+        CU(cudaMemset(ctx->flags[p], 1, n * 4));     // non-zero = reconstructed
+    }
+    CU(cudaMalloc(&ctx->counter, 256));
+    CU(cudaMemset(ctx->counter, 0, 256));
+    ctx->arena_bytes = c.max_blob_bytes ? c.max_blob_bytes : worst_blob_bytes(&c);
+    ctx->arena_bytes = (ctx->arena_bytes + 4095) & ~(uint64_t)4095;
+    CU(cudaStreamCreateWithFlags(&ctx->st_copy, cudaStreamNonBlocking));
+    CU(cudaStreamCreateWithFlags(&ctx->st_compute, cudaStreamNonBlocking));
+    CU(cudaStreamCreateWithFlags(&ctx->st_down, cudaStreamNonBlocking));
+    for (int i = 0; i < c.n_arenas; i++) {
+        CU(cudaMalloc(&ctx->arena[i].dev, ctx->arena_bytes));
+        CU(cudaEventCreateWithFlags(&ctx->arena[i].ev_uploaded, cudaEventDisableTiming));
+        CU(cudaEventCreateWithFlags(&ctx->arena[i].ev_done, cudaEventDisableTiming));
+    }
+    for (int i = 0; i < c.n_slots; i++) CU(cudaEventCreateWithFlags(&ctx->slot_done[i], cudaEventDisableTiming));
+    for (int i = 0; i <= B200_ST_COUNT; i++) CU(cudaEventCreate(&ctx->prof[i]));
+    b200_dbk_layout(c.width, c.height, c.chroma_format_idc, &ctx->dbk);
+    ctx->ctb_w = (c.width + (1 << c.log2_ctb_size) - 1) >> c.log2_ctb_size;
+    ctx->ctb_h = (c.height + (1 << c.log2_ctb_size) - 1) >> c.log2_ctb_size;
+    return 0;
+}
+
+extern "C" int b200_ctx_create(const B200Config *cfg, B200Ctx **out)
+{
+    std::lock_guard<std::mutex> lk(g_mu);
+    if (!out) return B200_EINVAL;
+    *out = nullptr;
+    if (!config_ok(cfg)) return fail(nullptr, B200_EINVAL, "bad B200Config (dims must be multiples of 8, depth 8..12, cfi 1..3)");
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0) {
+        cudaGetLastError();
+        return fail(nullptr, B200_ECUDA, "no CUDA device: libb200hevc has no CPU fallback");
+    }
+    if (cfg->device < 0 || cfg->device >= ndev) return fail(nullptr, B200_EINVAL, "device %d out of range (0..%d)", cfg->device, ndev - 1);
+    B200Ctx *ctx = new B200Ctx();
+    memset(ctx->slot_done, 0, sizeof(ctx->slot_done));
+    memset(ctx->prof, 0, sizeof(ctx->prof));
+    ctx->err[0] = 0;
+    ctx->cfg = *cfg;
+    int rc = ctx_init(ctx);
+    if (rc) {
+        memcpy(g_create_err, ctx->err, sizeof(g_create_err));
+        b200_ctx_destroy(ctx);
+        return rc;
+    }
+    *out = ctx;
+    return 0;
+}
+
+static int check_blob(B200Ctx *ctx, const B200BlobHeader *h, uint64_t nbytes)
+{
+    const B200Config &c = ctx->cfg;
+    if (nbytes < sizeof(B200BlobHeader) || h->magic != B200_BLOB_MAGIC || h->version != B200_BLOB_VERSION)
+        return fail(ctx, B200_EINVAL, "not a B200 work-list blob (magic/version)");
+    if (h->total_bytes != nbytes || nbytes > ctx->arena_bytes) return fail(ctx, B200_EINVAL, "blob size %llu (header %u, arena %llu)", (unsigned long long)nbytes, h->total_bytes, (unsigned long long)ctx->arena_bytes);
+    if (h->width != c.width || h->height != c.height || h->chroma_format_idc != c.chroma_format_idc || h->bit_depth != c.bit_depth || h->log2_ctb_size != c.log2_ctb_size)
+        return fail(ctx, B200_EINVAL, "blob geometry does not match the context");
+    if (h->cur_slot >= c.n_slots) return fail(ctx, B200_EINVAL, "cur_slot %d out of range", h->cur_slot);
+    static const uint32_t esz[B200_SEC_COUNT] = { 2, 16, 16, 16, 16, 16, 32, 2, 16 };
+    for (int s = 0; s < B200_SEC_COUNT; s++) {
+        const uint64_t end = (uint64_t)h->sec[s].off + (uint64_t)h->sec[s].count * esz[s];
+        if (h->sec[s].count && ((h->sec[s].off & 15) || end > nbytes)) return fail(ctx, B200_EINVAL, "section %d out of bounds", s);
+    }
+    if (h->sec[B200_SEC_DBK].count && h->sec[B200_SEC_DBK].count != ctx->dbk.total) return fail(ctx, B200_EINVAL, "deblock grid size %u != %u", h->sec[B200_SEC_DBK].count, ctx->dbk.total);
+    if (h->sec[B200_SEC_SAO].count && h->sec[B200_SEC_SAO].count != (uint32_t)(3 * ctx->ctb_w * ctx->ctb_h)) return fail(ctx, B200_EINVAL, "SAO grid size mismatch");
+    return 0;
+}
+
+// optional deep validation (every record in range): B200_VALIDATE=1
+static int deep_check(B200Ctx *ctx, const uint8_t *blob)
+{
+    const B200BlobHeader *h = (const B200BlobHeader *)blob;
+    const uint32_t ncoef = h->sec[B200_SEC_COEFF].count;
+    for (int s = B200_SEC_TU4; s <= B200_SEC_TU32; s++) {
+        const B200TuRec *t = (const B200TuRec *)(blob + h->sec[s].off);
+        const int n = 4 << (s - B200_SEC_TU4);
+        for (uint32_t i = 0; i < h->sec[s].count; i++) {
+            if (t[i].plane > 2 || (1 << t[i].log2) != n || t[i].x + n > ctx->pw[t[i].plane] || t[i].y + n > ctx->ph[t[i].plane] ||
+                (uint64_t)t[i].coeff_off + n * n > ncoef || t[i].kind > B200_TU_PCM || (t[i].kind == B200_TU_DST && n != 4))
+                return fail(ctx, B200_EINVAL, "TU record %u of size %d invalid", i, n);
+        }
+    }
+    const B200IntraRec *ir = (const B200IntraRec *)(blob + h->sec[B200_SEC_INTRA].off);
+    for (uint32_t i = 0; i < h->sec[B200_SEC_INTRA].count; i++) {
+        const int n = 1 << ir[i].log2;
+        if (ir[i].plane > 2 || ir[i].log2 < 2 || ir[i].log2 > 5 || ir[i].mode > 34 || (ir[i].x & 3) || (ir[i].y & 3) ||
+            ir[i].x + n > ctx->pw[ir[i].plane] || ir[i].y + n > ctx->ph[ir[i].plane] ||
+            (ir[i].resid_off != B200_NO_RESID && (uint64_t)ir[i].resid_off + n * n > ncoef) ||
+            ((ir[i].flags & B200_INF_UP_RIGHT) && (ir[i].top_right_size < 1 || ir[i].top_right_size > n || ir[i].x + n + ir[i].top_right_size > ctx->pw[ir[i].plane])) ||
+            ((ir[i].flags & B200_INF_BOTTOM_LEFT) && (ir[i].bottom_left_size < 1 || ir[i].bottom_left_size > n || ir[i].y + n + ir[i].bottom_left_size > ctx->ph[ir[i].plane])) ||
+            ((ir[i].flags & (B200_INF_UP | B200_INF_UP_RIGHT | B200_INF_UP_LEFT)) && ir[i].y == 0) ||
+            ((ir[i].flags & (B200_INF_LEFT | B200_INF_BOTTOM_LEFT | B200_INF_UP_LEFT)) && ir[i].x == 0))
+            return fail(ctx, B200_EINVAL, "intra record %u invalid", i);
+    }
+    const B200McRec *mc = (const B200McRec *)(blob + h->sec[B200_SEC_MC].off);
+    for (uint32_t i = 0; i < h->sec[B200_SEC_MC].count; i++) {
+        const B200McRec &m = mc[i];
+        const int maxf = (m.flags & B200_MCF_CHROMA) ? 7 : 3;
+        if (m.plane > 2 || !m.w || !m.h || m.w > 32 || m.w * m.h > 256 || m.x + m.w > ctx->pw[m.plane] || m.y + m.h > ctx->ph[m.plane] ||
+            m.ref0 >= ctx->cfg.n_slots || ((m.flags & B200_MCF_BI) && m.ref1 >= ctx->cfg.n_slots) ||
+            (m.frac0 & 15) > maxf || (m.frac0 >> 4) > maxf || (m.frac1 & 15) > maxf || (m.frac1 >> 4) > maxf || m.denom > 7 ||
+            ((m.w > 16) ? m.h > 8 : m.h > 16))
+            return fail(ctx, B200_EINVAL, "MC record %u invalid", i);
+    }
+    return 0;
+}
+
+extern "C" int b200_frame_upload(B200Ctx *ctx, const void *blob, uint64_t nbytes, int arena)
+{
+    if (!ctx || !blob || arena < 0 || arena >= ctx->cfg.n_arenas) return B200_EINVAL;
+    if (ctx->err_code) return ctx->err_code;
+    const B200BlobHeader *h = (const B200BlobHeader *)blob;
+    int rc = check_blob(ctx, h, nbytes);
+    if (rc) { ctx->err_code = 0; return rc; }
+    static const bool deep = getenv("B200_VALIDATE") && atoi(getenv("B200_VALIDATE"));
+    if (deep && (rc = deep_check(ctx, (const uint8_t *)blob))) { ctx->err_code = 0; return rc; }
+    CU(cudaSetDevice(ctx->cfg.device));
+    Arena &a = ctx->arena[arena];
+    const void *src = blob;
+    cudaPointerAttributes at;
+    bool pinned = cudaPointerGetAttributes(&at, blob) == cudaSuccess && at.type == cudaMemoryTypeHost;
+    cudaGetLastError();
+    if (!pinned) {   // stage through pinned memory so the copy stays asynchronous w.r.t. compute
+        if (!a.stage) CU(cudaHostAlloc(&a.stage, ctx->arena_bytes, cudaHostAllocDefault));
+        if (a.resident) CU(cudaEventSynchronize(a.ev_uploaded));
+        memcpy(a.stage, blob, nbytes);
+        src = a.stage;
+    }
+    if (a.resident) CU(cudaStreamWaitEvent(ctx->st_copy, a.ev_done, 0));   // previous picture of this arena finished
+    CU(cudaMemcpyAsync(a.dev, src, nbytes, cudaMemcpyHostToDevice, ctx->st_copy));
+    CU(cudaEventRecord(a.ev_uploaded, ctx->st_copy));
+    a.hdr = *h;
+    a.resident = true;
+    return 0;
+}
+
+extern "C" int b200_frame_execute(B200Ctx *ctx, int arena)
+{
+    if (!ctx || arena < 0 || arena >= ctx->cfg.n_arenas) return B200_EINVAL;
+    if (ctx->err_code) return ctx->err_code;
+    Arena &a = ctx->arena[arena];
+    if (!a.resident) return fail(ctx, B200_ESTATE, "arena %d holds no blob", arena);
+    CU(cudaSetDevice(ctx->cfg.device));
+    const B200BlobHeader &h = a.hdr;
+    cudaStream_t st = ctx->st_compute;
+    const int bd = ctx->cfg.bit_depth;
+    const bool has_sao = h.sec[B200_SEC_SAO].count != 0;
+    const FrameDesc &out = ctx->slot_desc[h.cur_slot];
+    const FrameDesc &cur = has_sao ? ctx->slot_desc[ctx->cfg.n_slots] : out;   // reconstruct + deblock here
+    const bool pf = ctx->profiling;
+    CU(cudaStreamWaitEvent(st, a.ev_uploaded, 0));
+    if (pf) CU(cudaEventRecord(ctx->prof[0], st));
+    // K1 inter
+    ctx->launches += launch_mc(st, (const B200McRec *)(a.dev + h.sec[B200_SEC_MC].off), (int)h.sec[B200_SEC_MC].count, cur, ctx->dpb_desc_dev, bd);
+    if (pf) CU(cudaEventRecord(ctx->prof[1], st));
+    // K2 residual
+    int16_t *pool = (int16_t *)(a.dev + h.sec[B200_SEC_COEFF].off);
+    const B200TuRec *tu[4]; int ntu[4];
+    for (int s = 0; s < 4; s++) { tu[s] = (const B200TuRec *)(a.dev + h.sec[B200_SEC_TU4 + s].off); ntu[s] = (int)h.sec[B200_SEC_TU4 + s].count; }
+    ctx->launches += launch_residual(st, tu, ntu, pool, cur, bd);
+    if (pf) CU(cudaEventRecord(ctx->prof[2], st));
+    // K3 intra
+    ctx->launches += launch_intra(st, (const B200IntraRec *)(a.dev + h.sec[B200_SEC_INTRA].off), (int)h.sec[B200_SEC_INTRA].count, pool, cur, bd,
+                                  ctx->flags, ctx->flag_stride, ctx->counter);
+    if (pf) CU(cudaEventRecord(ctx->prof[3], st));
+    // K4 deblock
+    if (h.sec[B200_SEC_DBK].count)
+        ctx->launches += launch_deblock(st, (const uint16_t *)(a.dev + h.sec[B200_SEC_DBK].off), ctx->dbk, cur, bd);
+    if (pf) CU(cudaEventRecord(ctx->prof[4], st));
+    // K5 SAO
+    if (has_sao)
+        ctx->launches += launch_sao(st, (const B200SaoRec *)(a.dev + h.sec[B200_SEC_SAO].off), cur, out, bd, ctx->cfg.log2_ctb_size, ctx->ctb_w, ctx->ctb_h, ctx->cfg.chroma_format_idc);
+    if (pf) { CU(cudaEventRecord(ctx->prof[5], st)); ctx->prof_valid = true; }
+    CU(cudaEventRecord(a.ev_done, st));
+    CU(cudaEventRecord(ctx->slot_done[h.cur_slot], st));
+    CU(cudaGetLastError());
+    return 0;
+}
+
+extern "C" int b200_frame_submit(B200Ctx *ctx, const void *blob, uint64_t nbytes)
+{
+    if (!ctx) return B200_EINVAL;
+    const int a = ctx->next_arena;
+    int rc = b200_frame_upload(ctx, blob, nbytes, a);
+    if (rc) return rc;
+    ctx->next_arena = (a + 1) % ctx->cfg.n_arenas;
+    return b200_frame_execute(ctx, a);
+}
+
+extern "C" int b200_slot_upload(B200Ctx *ctx, int slot, const void *const planes[3], const int64_t strides[3])
+{
+    if (!ctx || slot < 0 || slot >= ctx->cfg.n_slots || !planes || !strides) return B200_EINVAL;
+    if (ctx->err_code) return ctx->err_code;
+    CU(cudaSetDevice(ctx->cfg.device));
+    const int B = ctx->cfg.bit_depth > 8 ? 2 : 1;
+    for (int p = 0; p < 3; p++)
+        CU(cudaMemcpy2DAsync(ctx->slot_desc[slot].p[p].base, ctx->pitch[p], planes[p], (size_t)strides[p], (size_t)ctx->pw[p] * B, ctx->ph[p], cudaMemcpyHostToDevice, ctx->st_compute));
+    CU(cudaEventRecord(ctx->slot_done[slot], ctx->st_compute));
+    return 0;
+}
+
+extern "C" int b200_slot_readback(B200Ctx *ctx, int slot, void *const planes[3], const int64_t strides[3])
+{
+    if (!ctx || slot < 0 || slot >= ctx->cfg.n_slots || !planes || !strides) return B200_EINVAL;
+    if (ctx->err_code) return ctx->err_code;
+    CU(cudaSetDevice(ctx->cfg.device));
+    const int B = ctx->cfg.bit_depth > 8 ? 2 : 1;
+    CU(cudaStreamWaitEvent(ctx->st_down, ctx->slot_done[slot], 0));
+    for (int p = 0; p < 3; p++)
+        CU(cudaMemcpy2DAsync(planes[p], (size_t)strides[p], ctx->slot_desc[slot].p[p].base, ctx->pitch[p], (size_t)ctx->pw[p] * B, ctx->ph[p], cudaMemcpyDeviceToHost, ctx->st_down));
+    return 0;
+}
+
+extern "C" int b200_slot_fill(B200Ctx *ctx, int slot, int value)
+{
+    if (!ctx || slot < 0 || slot >= ctx->cfg.n_slots) return B200_EINVAL;
+    if (ctx->err_code) return ctx->err_code;
+    CU(cudaSetDevice(ctx->cfg.device));
+    ctx->launches += launch_fill(ctx->st_compute, ctx->slot_desc[slot], ctx->cfg.bit_depth, value);
+    CU(cudaEventRecord(ctx->slot_done[slot], ctx->st_compute));
+    CU(cudaGetLastError());
+    return 0;
+}
+
+extern "C" int b200_sync(B200Ctx *ctx)
+{
+    if (!ctx) return B200_EINVAL;
+    CU(cudaSetDevice(ctx->cfg.device));
+    CU(cudaStreamSynchronize(ctx->st_copy));
+    CU(cudaStreamSynchronize(ctx->st_compute));
+    CU(cudaStreamSynchronize(ctx->st_down));
+    uint32_t st[2] = { 0, 0 };
+    CU(cudaMemcpy(st, ctx->counter, sizeof(st), cudaMemcpyDeviceToHost));
+    if (st[1]) return fail(ctx, B200_EINVAL, "intra work list is not in decode order (dependency wait timed out)");
+    return ctx->err_code;
+}
+
+extern "C" int b200_set_profiling(B200Ctx *ctx, int on)
+{
+    if (!ctx) return B200_EINVAL;
+    ctx->profiling = on != 0;
+    ctx->prof_valid = false;
+    return 0;
+}
+
+extern "C" int b200_get_stage_ms(B200Ctx *ctx, float ms[B200_ST_COUNT])
+{
+    if (!ctx || !ms) return B200_EINVAL;
+    if (!ctx->prof_valid) return fail(ctx, B200_ESTATE, "no profiled frame");
+    CU(cudaSetDevice(ctx->cfg.device));
+    CU(cudaEventSynchronize(ctx->prof[5]));
+    for (int s = 0; s < 5; s++) CU(cudaEventElapsedTime(&ms[s], ctx->prof[s], ctx->prof[s + 1]));
+    CU(cudaEventElapsedTime(&ms[B200_ST_TOTAL], ctx->prof[0], ctx->prof[5]));
+    return 0;
+}

@@ -1,0 +1,793 @@
+// kernels.cu — hand-written sm_100a kernels for openHEVC's pixel-reconstruction path.
+//
+// One kernel per stage, each consuming one section of the per-frame work list
+// (include/b200hevc_worklist.h):
+//   K1 k_mc        put_hevc_{qpel,epel}{,_uni,_bi}{,_w}        hevcdsp_template.c:610-1609
+//   K2 k_residual  idct / idct_dc / idct_4x4_luma / transform_skip / rdpcm + transform_add   :45-326
+//   K3 k_intra     intra_pred + pred_planar / pred_dc / pred_angular (+ fused residual add)   hevcpred_template.c:30-538
+//   K4 k_deblock   hevc_{h,v}_loop_filter_{luma,chroma}                                       hevcdsp_template.c:1629-1787
+//   K5 k_sao       sao_band_filter / sao_edge_filter[0,1]                                     :340-567
+// All arithmetic is integer and bit-exact with the reference's C templates (tests/ compare with
+// oracle/, which is pinned against the reference build).  No tensor cores: the path is HBM / L2
+// bound integer work.
+#include "common.cuh"
+
+// --------------------------------------------------------------------------------------------
+// constants
+// --------------------------------------------------------------------------------------------
+__constant__ int8_t c_qpel[4][8] = { { 0, 0, 0, 64, 0, 0, 0, 0 }, { -1, 4, -10, 58, 17, -5, 1, 0 },
+                                     { -1, 4, -11, 40, 40, -11, 4, -1 }, { 0, 1, -5, 17, 58, -10, 4, -1 } };
+__constant__ int8_t c_epel[8][4] = { { 0, 64, 0, 0 }, { -2, 58, 10, -2 }, { -4, 54, 16, -2 }, { -6, 46, 28, -4 },
+                                     { -4, 36, 36, -4 }, { -4, 28, 46, -6 }, { -2, 16, 54, -4 }, { -2, 10, 58, -2 } };
+__constant__ int8_t c_intra_angle[33] = { 32, 26, 21, 17, 13, 9, 5, 2, 0, -2, -5, -9, -13, -17, -21, -26, -32,
+                                          -26, -21, -17, -13, -9, -5, -2, 0, 2, 5, 9, 13, 17, 21, 26, 32 };
+__constant__ int16_t c_inv_angle[15] = { -4096, -1638, -910, -630, -482, -390, -315, -256, -315, -390, -482, -630, -910, -1638, -4096 };
+
+// HEVC core transform coefficient T[k][n] = sign * |64*sqrt2*cos((2n+1)k*pi/64)| (standardised integers).
+// Evaluated at compile time after full unrolling: the butterflies below carry their multipliers as immediates.
+__host__ __device__ constexpr int hevc_cos(int j)
+{
+    constexpr int t[33] = { 64, 90, 90, 90, 89, 88, 87, 85, 83, 82, 80, 78, 75, 73, 70, 67, 64,
+                            61, 57, 54, 50, 46, 43, 38, 36, 31, 25, 22, 18, 13, 9, 4, 0 };
+    return t[j];
+}
+__host__ __device__ constexpr int hevc_T(int k, int n)
+{
+    int m = ((2 * n + 1) * k) & 127;
+    return m <= 32 ? hevc_cos(m) : m <= 64 ? -hevc_cos(64 - m) : m < 96 ? -hevc_cos(m - 64) : hevc_cos(128 - m);
+}
+
+// --------------------------------------------------------------------------------------------
+// K2: residual.  N lanes per TU (one column, then one row each); 32/N TUs per warp.
+// 1-D inverse DCT as register butterflies (even/odd decomposition), transposition through
+// a padded shared tile.  The int16 clip between the two stages is kept (Appendix A.2).
+// --------------------------------------------------------------------------------------------
+template <int N> struct Idct1D {
+    static constexpr int STEP = 32 / N;
+    __device__ __forceinline__ static void run(const int (&v)[N], int (&out)[N])
+    {
+        int ein[N / 2], e[N / 2];
+#pragma unroll
+        for (int j = 0; j < N / 2; j++) ein[j] = v[2 * j];
+        Idct1D<N / 2>::run(ein, e);
+#pragma unroll
+        for (int k = 0; k < N / 2; k++) {
+            int o = 0;
+#pragma unroll
+            for (int j = 1; j < N; j += 2) o += hevc_T(j * STEP, k) * v[j];
+            out[k] = e[k] + o;
+            out[N - 1 - k] = e[k] - o;
+        }
+    }
+};
+template <> struct Idct1D<4> {
+    __device__ __forceinline__ static void run(const int (&v)[4], int (&out)[4])
+    {
+        const int e0 = 64 * (v[0] + v[2]), e1 = 64 * (v[0] - v[2]);
+        const int o0 = 83 * v[1] + 36 * v[3], o1 = 36 * v[1] - 83 * v[3];
+        out[0] = e0 + o0; out[1] = e1 + o1; out[2] = e1 - o1; out[3] = e0 - o0;
+    }
+};
+
+// which inputs the reference's pruned butterflies read for a given `end` (hevcdsp_template.c:223-277)
+template <int N> __device__ __forceinline__ bool idct_keep(int j, int end)
+{
+    if (N == 4) return true;
+    if (N == 8 || N == 16) return !(j & 1) || j < end;
+    if (j & 1) return j < end;
+    if ((j & 3) == 2) return (j >> 1) < end / 2;
+    return true;
+}
+
+template <int N> __device__ __forceinline__ void dst4_1d(const int (&v)[N], int (&out)[N])
+{
+    if (N == 4) {   // inverse DST-VII, hevcdsp_template.c:170-183
+        const int c0 = v[0] + v[2], c1 = v[2] + v[3], c2 = v[0] - v[3], c3 = 74 * v[1];
+        out[0] = 29 * c0 + 55 * c1 + c3;
+        out[1] = 55 * c2 - 29 * c1 + c3;
+        out[2] = 74 * (v[0] - v[2] + v[3]);
+        out[3] = 55 * c0 + 29 * c2 - c3;
+    }
+}
+
+template <typename PIX, int N>
+__global__ void __launch_bounds__(128) k_residual(const B200TuRec *__restrict__ recs, int count, int16_t *pool, FrameDesc f, int bd)
+{
+    constexpr int G = 32 / N;            // TUs per warp
+    constexpr int TS = N * (N + 1);      // padded tile
+    __shared__ int tile_s[4][G * TS];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int g = lane / N, col = lane % N;
+    const int ti = (blockIdx.x * 4 + warp) * G + g;
+    const bool active = ti < count;
+    int *tile = tile_s[warp] + g * TS;
+
+    B200TuRec rec;
+    if (active) {
+        const int4 raw = __ldg(reinterpret_cast<const int4 *>(recs + ti));
+        memcpy(&rec, &raw, 16);
+    } else {
+        memset(&rec, 0, 16);
+        rec.kind = B200_TU_BYPASS;
+    }
+    int16_t *c = pool + rec.coeff_off;
+    const int kind = rec.kind;
+    int v[N], t[N];
+    if (active) {
+#pragma unroll
+        for (int j = 0; j < N; j++) v[j] = c[j * N + col];
+    } else {
+#pragma unroll
+        for (int j = 0; j < N; j++) v[j] = 0;
+    }
+    const int lim_row = min((int)rec.col_limit, N);
+    // ---- first stage (columns) ----
+    if (kind == B200_TU_IDCT) {
+        int lim = min((int)rec.col_limit + 4, N);
+        if (lim < N && col > 0) lim -= 4 * ((col - 1) >> 2);
+#pragma unroll
+        for (int j = 0; j < N; j++) if (!idct_keep<N>(j, lim)) v[j] = 0;
+        int o[N];
+        Idct1D<N>::run(v, o);
+#pragma unroll
+        for (int j = 0; j < N; j++) t[j] = clip16i((o[j] + 64) >> 7);
+    } else if (kind == B200_TU_DST) {
+        int o[N];
+        dst4_1d<N>(v, o);
+#pragma unroll
+        for (int j = 0; j < N; j++) t[j] = clip16i((o[j] + 64) >> 7);
+    } else if (kind == B200_TU_DC) {
+        const int shift = 14 - bd;
+        const int dc = active ? (((c[0] + 1) >> 1) + (1 << (shift - 1))) >> shift : 0;
+#pragma unroll
+        for (int j = 0; j < N; j++) t[j] = (int16_t)dc;
+    } else if (kind == B200_TU_SKIP) {
+        const int shift = 15 - bd - rec.log2;
+#pragma unroll
+        for (int j = 0; j < N; j++) t[j] = shift > 0 ? (int16_t)((v[j] + (1 << (shift - 1))) >> shift) : (int16_t)(v[j] << -shift);
+    } else {
+#pragma unroll
+        for (int j = 0; j < N; j++) t[j] = v[j];
+    }
+    if ((rec.flags & (B200_TUF_RDPCM | B200_TUF_RDPCM_VERT)) == (B200_TUF_RDPCM | B200_TUF_RDPCM_VERT)) {
+#pragma unroll
+        for (int j = 1; j < N; j++) t[j] = (int16_t)(t[j] + t[j - 1]);   // running sum down the column, int16 wrap
+    }
+    // ---- transpose ----
+#pragma unroll
+    for (int j = 0; j < N; j++) tile[j * (N + 1) + col] = t[j];
+    __syncwarp();
+#pragma unroll
+    for (int j = 0; j < N; j++) v[j] = tile[col * (N + 1) + j];          // lane now owns row `col`
+    // ---- second stage (rows) ----
+    if (kind == B200_TU_IDCT || kind == B200_TU_DST) {
+        int o[N];
+        if (kind == B200_TU_IDCT) {
+#pragma unroll
+            for (int j = 0; j < N; j++) if (!idct_keep<N>(j, lim_row)) v[j] = 0;
+            Idct1D<N>::run(v, o);
+        } else {
+            dst4_1d<N>(v, o);
+        }
+        const int shift = 20 - bd, add = 1 << (shift - 1);
+#pragma unroll
+        for (int j = 0; j < N; j++) t[j] = clip16i((o[j] + add) >> shift);
+    } else {
+#pragma unroll
+        for (int j = 0; j < N; j++) t[j] = v[j];
+    }
+    if ((rec.flags & (B200_TUF_RDPCM | B200_TUF_RDPCM_VERT)) == B200_TUF_RDPCM) {
+#pragma unroll
+        for (int j = 1; j < N; j++) t[j] = (int16_t)(t[j] + t[j - 1]);   // running sum along the row
+    }
+    __syncwarp();
+#pragma unroll
+    for (int j = 0; j < N; j++) tile[col * (N + 1) + j] = t[j];          // tile[row][x]
+    __syncwarp();
+    if (!active) return;
+    // ---- output: rows of N consecutive samples per TU ----
+    if (rec.flags & B200_TUF_PARK) {
+#pragma unroll
+        for (int y = 0; y < N; y++) c[y * N + col] = (int16_t)tile[y * (N + 1) + col];
+    } else {
+        const PlaneDesc pd = f.p[rec.plane];
+        const int maxv = (1 << bd) - 1;
+        const bool pcm = kind == B200_TU_PCM;
+#pragma unroll
+        for (int y = 0; y < N; y++) {
+            PIX *d = px_ptr<PIX>(pd, rec.x + col, rec.y + y);
+            const int r = tile[y * (N + 1) + col];
+            *d = (PIX)(pcm ? r : clip3i((int)*d + r, 0, maxv));
+        }
+    }
+}
+
+// --------------------------------------------------------------------------------------------
+// K1: inter prediction.  One warp per tile record (<= 256 samples, <= 32 wide).
+// Reference window staged in shared memory with clamped addressing (== emulated_edge_mc),
+// separable FIR with the 14-bit intermediate of the reference.
+// --------------------------------------------------------------------------------------------
+#define MC_WIN_MAX 608
+#define MC_TMP_MAX 512
+
+template <typename PIX, int TAPS>
+__device__ __forceinline__ void mc_list(const PlaneDesc &rp, int sx, int sy, int mx, int my, int w, int h, int bd, int lane,
+                                        uint16_t *win, int16_t *tmp, int (&val)[8])
+{
+    constexpr int BEFORE = TAPS == 8 ? 3 : 1;
+    const int8_t *fx = TAPS == 8 ? c_qpel[mx] : c_epel[mx];
+    const int8_t *fy = TAPS == 8 ? c_qpel[my] : c_epel[my];
+    const int cols = w + (mx ? TAPS - 1 : 0), rows = h + (my ? TAPS - 1 : 0);
+    const int ox = sx - (mx ? BEFORE : 0), oy = sy - (my ? BEFORE : 0);
+    __syncwarp();
+    for (int i = lane; i < rows * cols; i += 32) {
+        const int r = i / cols, cc = i - r * cols;
+        const int x = clip3i(ox + cc, 0, rp.w - 1), y = clip3i(oy + r, 0, rp.h - 1);
+        win[i] = __ldg(px_ptr<PIX>(rp, x, y));
+    }
+    __syncwarp();
+    if (mx && my) {
+        for (int i = lane; i < rows * w; i += 32) {
+            const int r = i / w, x = i - r * w;
+            int acc = 0;
+#pragma unroll
+            for (int k = 0; k < TAPS; k++) acc += fx[k] * win[r * cols + x + k];
+            tmp[i] = (int16_t)(acc >> (bd - 8));
+        }
+        __syncwarp();
+    }
+    const int n = w * h;
+#pragma unroll
+    for (int k = 0; k < 8; k++) {
+        const int i = lane + 32 * k;
+        int out = 0;
+        if (i < n) {
+            const int y = i / w, x = i - y * w;
+            if (mx && my) {
+                int acc = 0;
+#pragma unroll
+                for (int j = 0; j < TAPS; j++) acc += fy[j] * tmp[(y + j) * w + x];
+                out = acc >> 6;
+            } else if (mx) {
+                int acc = 0;
+#pragma unroll
+                for (int j = 0; j < TAPS; j++) acc += fx[j] * win[y * cols + x + j];
+                out = acc >> (bd - 8);
+            } else if (my) {
+                int acc = 0;
+#pragma unroll
+                for (int j = 0; j < TAPS; j++) acc += fy[j] * win[(y + j) * cols + x];
+                out = acc >> (bd - 8);
+            } else {
+                out = win[y * cols + x] << (14 - bd);
+            }
+        }
+        val[k] = out;
+    }
+}
+
+template <typename PIX>
+__global__ void __launch_bounds__(256) k_mc(const B200McRec *__restrict__ recs, int count, FrameDesc cur, const FrameDesc *__restrict__ dpb, int bd)
+{
+    __shared__ uint16_t win_s[8][MC_WIN_MAX];
+    __shared__ int16_t tmp_s[8][MC_TMP_MAX];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int ri = blockIdx.x * 8 + warp;
+    if (ri >= count) return;
+    B200McRec m;
+    {
+        const int4 *p = reinterpret_cast<const int4 *>(recs + ri);
+        const int4 a = __ldg(p), b = __ldg(p + 1);
+        memcpy(&m, &a, 16);
+        memcpy(reinterpret_cast<char *>(&m) + 16, &b, 16);
+    }
+    const int w = m.w, h = m.h, plane = m.plane;
+    const bool chroma = m.flags & B200_MCF_CHROMA, bi = m.flags & B200_MCF_BI, weighted = m.flags & B200_MCF_WEIGHTED;
+    int v0[8], v1[8];
+    {
+        const PlaneDesc rp = dpb[m.ref0].p[plane];
+        if (chroma) mc_list<PIX, 4>(rp, m.sx0, m.sy0, m.frac0 & 15, m.frac0 >> 4, w, h, bd, lane, win_s[warp], tmp_s[warp], v0);
+        else        mc_list<PIX, 8>(rp, m.sx0, m.sy0, m.frac0 & 15, m.frac0 >> 4, w, h, bd, lane, win_s[warp], tmp_s[warp], v0);
+    }
+    if (bi) {
+        const PlaneDesc rp = dpb[m.ref1].p[plane];
+        if (chroma) mc_list<PIX, 4>(rp, m.sx1, m.sy1, m.frac1 & 15, m.frac1 >> 4, w, h, bd, lane, win_s[warp], tmp_s[warp], v1);
+        else        mc_list<PIX, 8>(rp, m.sx1, m.sy1, m.frac1 & 15, m.frac1 >> 4, w, h, bd, lane, win_s[warp], tmp_s[warp], v1);
+    }
+    const PlaneDesc dp = cur.p[plane];
+    const int shift = 14 - bd, maxv = (1 << bd) - 1, n = w * h;
+    const bool fullpel0 = !(m.frac0 & 15) && !(m.frac0 >> 4);
+#pragma unroll
+    for (int k = 0; k < 8; k++) {
+        const int i = lane + 32 * k;
+        if (i >= n) break;
+        const int y = i / w, x = i - y * w;
+        int out;
+        if (!bi) {
+            if (!weighted) out = fullpel0 ? (v0[k] >> shift) : clip3i((v0[k] + (1 << (shift - 1))) >> shift, 0, maxv);
+            else {
+                const int s = m.denom + shift;
+                out = clip3i(((v0[k] * m.w0 + (1 << (s - 1))) >> s) + m.o0 * (1 << (bd - 8)), 0, maxv);
+            }
+        } else {
+            const int a = (int16_t)v0[k];          // list 0 travels through the reference's int16 tmp[] (hevc.c:1761)
+            if (!weighted) out = clip3i((v1[k] + a + (1 << shift)) >> (shift + 1), 0, maxv);
+            else {
+                const int l2 = m.denom + shift, o = (m.o0 + m.o1) * (1 << (bd - 8)) + 1;
+                out = clip3i((v1[k] * m.w1 + a * m.w0 + (o << l2)) >> (l2 + 1), 0, maxv);
+            }
+        }
+        *px_ptr<PIX>(dp, m.x + x, m.y + y) = (PIX)out;
+    }
+}
+
+// --------------------------------------------------------------------------------------------
+// K3: intra prediction.  Persistent warps take TUs in decode order from an atomic counter and
+// wait on per-4x4-unit "reconstructed" flags of exactly the neighbours they read (TU-granular
+// wavefront); prediction + parked residual are fused, so the serial chain is short.
+// --------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t ld_acquire(const uint32_t *p)
+{
+    uint32_t v;
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release(uint32_t *p, uint32_t v)
+{
+    asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+
+struct IntraFlags {
+    uint32_t *f[3];
+    int stride[3];
+};
+
+__global__ void k_intra_prepass(const B200IntraRec *__restrict__ recs, int count, IntraFlags fl)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= count) return;
+    const int4 raw = __ldg(reinterpret_cast<const int4 *>(recs + i));
+    B200IntraRec r;
+    memcpy(&r, &raw, 16);
+    const int u = 1 << (r.log2 - 2), ux = r.x >> 2, uy = r.y >> 2;
+    uint32_t *f = fl.f[r.plane];
+    const int fs = fl.stride[r.plane];
+    for (int y = 0; y < u; y++)
+        for (int x = 0; x < u; x++) f[(uy + y) * fs + ux + x] = 0;
+}
+
+template <typename PIX>
+__global__ void __launch_bounds__(128) k_intra(const B200IntraRec *__restrict__ recs, int count, const int16_t *__restrict__ pool,
+                                               FrameDesc f, int bd, IntraFlags fl, uint32_t *counter)
+{
+    __shared__ int s_g[4][2][66];     // gathered   [0]=top [1]=left, element [k] holds index k-1
+    __shared__ int s_f[4][2][66];     // substituted
+    __shared__ int s_ff[4][2][66];    // smoothed
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int maxv = (1 << bd) - 1;
+    for (;;) {
+        int idx = 0;
+        if (lane == 0) idx = atomicAdd(counter, 1u);
+        idx = __shfl_sync(0xffffffffu, idx, 0);
+        if (idx >= count) break;
+        B200IntraRec r;
+        {
+            const int4 raw = __ldg(reinterpret_cast<const int4 *>(recs + idx));
+            memcpy(&r, &raw, 16);
+        }
+        const int n = 1 << r.log2, n2 = 2 * n, x0 = r.x, y0 = r.y;
+        const PlaneDesc pd = f.p[r.plane];
+        const bool ul = r.flags & B200_INF_UP_LEFT, up = r.flags & B200_INF_UP, ur = r.flags & B200_INF_UP_RIGHT;
+        const bool lf = r.flags & B200_INF_LEFT, bl = r.flags & B200_INF_BOTTOM_LEFT;
+        const int trs = r.top_right_size, bls = r.bottom_left_size;
+        uint32_t *flg = fl.f[r.plane];
+        const int fs = fl.stride[r.plane];
+        // ---- wait for the neighbours this TU reads ----
+        for (int k = lane; k < 33; k += 32) {
+            int ux = -1, uy = -1;
+            if (k == 0) { if (ul) { ux = (x0 - 1) >> 2; uy = (y0 - 1) >> 2; } }
+            else if (k <= 16) {
+                const int o = 4 * (k - 1);
+                if ((o < n && up) || (o >= n && ur && o < n + trs)) { ux = (x0 + o) >> 2; uy = (y0 - 1) >> 2; }
+            } else {
+                const int o = 4 * (k - 17);
+                if ((o < n && lf) || (o >= n && bl && o < n + bls)) { ux = (x0 - 1) >> 2; uy = (y0 + o) >> 2; }
+            }
+            if (ux >= 0) {
+                // a malformed list (dependency on a later TU) must not hang the GPU: give up after ~0.25 s and latch an error
+                const uint32_t *p = flg + uy * fs + ux;
+                uint32_t spins = 0;
+                while (ld_acquire(p) == 0) {
+                    __nanosleep(64);
+                    if ((++spins & 1023) == 0 && (spins > (1u << 21) || ld_acquire(counter + 1))) { st_release(counter + 1, 1u); break; }
+                }
+            }
+        }
+        __syncwarp();
+        // ---- gather (L2 loads: neighbours were written by other SMs) ----
+        int *gt = s_g[warp][0], *gl = s_g[warp][1];
+        for (int k = lane; k <= n2; k += 32) {
+            const int t = k - 1;
+            int tv = 0, lv = 0;
+            if (t < 0) { if (ul) tv = lv = __ldcg(px_ptr<PIX>(pd, x0 - 1, y0 - 1)); }
+            else {
+                if (t < n ? up : ur) tv = __ldcg(px_ptr<PIX>(pd, x0 + (t < n ? t : min(t, n + trs - 1)), y0 - 1));
+                if (t < n ? lf : bl) lv = __ldcg(px_ptr<PIX>(pd, x0 - 1, y0 + (t < n ? t : min(t, n + bls - 1))));
+            }
+            gt[k] = tv; gl[k] = lv;
+        }
+        __syncwarp();
+        // ---- substitution (hevcpred_template.c:250-286) in closed form ----
+        int *ft = s_f[warp][0], *fleft = s_f[warp][1];
+        {
+            const int s = lf ? gl[n] /*left[n-1]*/ : ul ? gl[0] : up ? gt[1] : ur ? gt[n + 1] : (1 << (bd - 1));
+            const int bl0 = bl ? gl[n + 1] : s;                 // final left[n]
+            const int l0 = lf ? gl[1] : bl0;                    // final left[0]
+            const int corner = ul ? gl[0] : l0;
+            const int un1 = up ? gt[n] : corner;                // final top[n-1]
+            for (int k = lane; k <= n2; k += 32) {
+                const int t = k - 1;
+                int tv, lv;
+                if (t < 0) tv = lv = corner;
+                else if (t < n) { tv = up ? gt[k] : corner; lv = lf ? gl[k] : bl0; }
+                else { tv = ur ? gt[k] : un1; lv = bl ? gl[k] : s; }
+                ft[k] = tv; fleft[k] = lv;
+            }
+        }
+        __syncwarp();
+        const int mode = r.mode;
+        const int *top = ft + 1, *left = fleft + 1;
+        // ---- smoothing (:288-327) ----
+        if ((r.flags & B200_INF_FILTER) && mode != 1 && n != 4) {
+            const int d26 = abs(mode - 26), d10 = abs(mode - 10), dist = min(d26, d10);
+            const int thr = r.log2 == 3 ? 7 : r.log2 == 4 ? 1 : 0;
+            if (dist > thr) {
+                int *qt = s_ff[warp][0], *ql = s_ff[warp][1];
+                const bool strong = (r.flags & B200_INF_STRONG) && r.plane == 0 && r.log2 == 5 &&
+                                    abs(top[-1] + top[63] - 2 * top[31]) < (1 << (bd - 5)) &&
+                                    abs(left[-1] + left[63] - 2 * left[31]) < (1 << (bd - 5));
+                for (int k = lane; k <= n2; k += 32) {
+                    const int t = k - 1;
+                    int tv, lv;
+                    if (strong) {
+                        if (t < 0 || t == 63) { tv = top[t]; lv = left[t]; }
+                        else { tv = ((63 - t) * top[-1] + (t + 1) * top[63] + 32) >> 6; lv = ((63 - t) * left[-1] + (t + 1) * left[63] + 32) >> 6; }
+                    } else {
+                        if (t < 0) tv = lv = (left[0] + 2 * left[-1] + top[0] + 2) >> 2;
+                        else if (t == n2 - 1) { tv = top[t]; lv = left[t]; }
+                        else { tv = (top[t + 1] + 2 * top[t] + top[t - 1] + 2) >> 2; lv = (left[t + 1] + 2 * left[t] + left[t - 1] + 2) >> 2; }
+                    }
+                    qt[k] = tv; ql[k] = lv;
+                }
+                __syncwarp();
+                top = qt + 1; left = ql + 1;
+            }
+        }
+        // ---- predictor ----
+        int dc = 0;
+        if (mode == 1) {
+            int sum = 0;
+            for (int i = lane; i < n; i += 32) sum += left[i] + top[i];
+#pragma unroll
+            for (int o = 16; o; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+            dc = (sum + n) >> (r.log2 + 1);
+        }
+        const int angle = mode >= 2 ? c_intra_angle[mode - 2] : 0;
+        const bool vertical = mode >= 18;
+        const int *mainr = vertical ? top : left, *side = vertical ? left : top;
+        const int inv = (mode >= 11 && mode <= 25) ? c_inv_angle[mode - 11] : 0;
+        const bool edge = r.plane == 0 && n < 32;
+        const int16_t *res = r.resid_off != B200_NO_RESID ? pool + r.resid_off : nullptr;
+        for (int i = lane; i < n * n; i += 32) {
+            const int y = i >> r.log2, x = i & (n - 1);
+            int v;
+            if (mode == 0) {
+                v = ((n - 1 - x) * left[y] + (x + 1) * top[n] + (n - 1 - y) * top[x] + (y + 1) * left[n] + n) >> (r.log2 + 1);
+            } else if (mode == 1) {
+                v = dc;
+                if (edge) {
+                    if (x == 0 && y == 0) v = (left[0] + 2 * dc + top[0] + 2) >> 2;
+                    else if (y == 0) v = (top[x] + 3 * dc + 2) >> 2;
+                    else if (x == 0) v = (left[y] + 3 * dc + 2) >> 2;
+                }
+            } else {
+                const int a = vertical ? y : x, b = vertical ? x : y;     // a along the prediction direction
+                const int pos = (a + 1) * angle, id = pos >> 5, fact = pos & 31;
+                const int k0 = b + id + 1;                                 // ref[k] == main[k-1]; k < 0 -> projected side samples
+                const int r0 = k0 >= 0 ? mainr[k0 - 1] : side[-1 + ((k0 * inv + 128) >> 8)];
+                if (fact) {
+                    const int k1 = k0 + 1;
+                    const int r1 = k1 >= 0 ? mainr[k1 - 1] : side[-1 + ((k1 * inv + 128) >> 8)];
+                    v = ((32 - fact) * r0 + fact * r1 + 16) >> 5;
+                } else v = r0;
+                if (edge) {
+                    if (mode == 26 && x == 0) v = clip3i(top[0] + ((left[y] - left[-1]) >> 1), 0, maxv);
+                    if (mode == 10 && y == 0) v = clip3i(left[0] + ((top[x] - top[-1]) >> 1), 0, maxv);
+                }
+            }
+            if (res) v = clip3i(v + res[i], 0, maxv);
+            *px_ptr<PIX>(pd, x0 + x, y0 + y) = (PIX)v;
+        }
+        // ---- publish ----
+        __threadfence();
+        __syncwarp();
+        {
+            const int u = n >> 2, ux = x0 >> 2, uy = y0 >> 2;
+            for (int k = lane; k < u * u; k += 32) st_release(flg + (uy + k / u) * fs + ux + (k % u), 1u);
+        }
+        __syncwarp();
+    }
+}
+
+// --------------------------------------------------------------------------------------------
+// K4: deblocking, both directions in ONE pass.  Tiles are offset by (-4,-4) from the 8x8 edge
+// grid, so every sample an edge reads or writes (<= 4 each side) belongs to exactly one tile:
+// load tile -> all vertical edges -> all horizontal edges -> store, no halo, in place.
+// --------------------------------------------------------------------------------------------
+#define DBK_TW 64
+#define DBK_TH 32
+#define DBK_PITCH 66
+
+__device__ __forceinline__ void dbk_luma_line(int (&p)[8], int beta, int tc, bool no_p, bool no_q, int bd, int lane)
+{
+    // p[0..3] = P3..P0, p[4..7] = Q0..Q3.  Decisions use lines 0 and 3 of the 4-line segment (quad of lanes).
+    const int base = lane & ~3;
+    const int dp = abs(p[1] - 2 * p[2] + p[3]), dq = abs(p[6] - 2 * p[5] + p[4]);
+    const int sa = abs(p[0] - p[3]) + abs(p[7] - p[4]), sb = abs(p[3] - p[4]);
+    const int dp0 = __shfl_sync(0xffffffffu, dp, base), dp3 = __shfl_sync(0xffffffffu, dp, base + 3);
+    const int dq0 = __shfl_sync(0xffffffffu, dq, base), dq3 = __shfl_sync(0xffffffffu, dq, base + 3);
+    const int sa0 = __shfl_sync(0xffffffffu, sa, base), sa3 = __shfl_sync(0xffffffffu, sa, base + 3);
+    const int sb0 = __shfl_sync(0xffffffffu, sb, base), sb3 = __shfl_sync(0xffffffffu, sb, base + 3);
+    beta <<= bd - 8; tc <<= bd - 8;
+    const int d0 = dp0 + dq0, d3 = dp3 + dq3;
+    if (d0 + d3 >= beta) return;
+    const int tc25 = (tc * 5 + 1) >> 1, maxv = (1 << bd) - 1;
+    const bool strong = sa0 < (beta >> 3) && sb0 < tc25 && sa3 < (beta >> 3) && sb3 < tc25 && (d0 << 1) < (beta >> 2) && (d3 << 1) < (beta >> 2);
+    const int p3 = p[0], p2 = p[1], p1 = p[2], p0 = p[3], q0 = p[4], q1 = p[5], q2 = p[6], q3 = p[7];
+    if (strong) {
+        const int t2 = tc << 1;
+        if (!no_p) {
+            p[3] = p0 + clip3i(((p2 + 2 * p1 + 2 * p0 + 2 * q0 + q1 + 4) >> 3) - p0, -t2, t2);
+            p[2] = p1 + clip3i(((p2 + p1 + p0 + q0 + 2) >> 2) - p1, -t2, t2);
+            p[1] = p2 + clip3i(((2 * p3 + 3 * p2 + p1 + p0 + q0 + 4) >> 3) - p2, -t2, t2);
+        }
+        if (!no_q) {
+            p[4] = q0 + clip3i(((p1 + 2 * p0 + 2 * q0 + 2 * q1 + q2 + 4) >> 3) - q0, -t2, t2);
+            p[5] = q1 + clip3i(((p0 + q0 + q1 + q2 + 2) >> 2) - q1, -t2, t2);
+            p[6] = q2 + clip3i(((2 * q3 + 3 * q2 + q1 + q0 + p0 + 4) >> 3) - q2, -t2, t2);
+        }
+    } else {
+        int delta = (9 * (q0 - p0) - 3 * (q1 - p1) + 8) >> 4;
+        if (abs(delta) < 10 * tc) {
+            const int th = tc >> 1, side = (beta + (beta >> 1)) >> 3;
+            delta = clip3i(delta, -tc, tc);
+            if (!no_p) p[3] = clip3i(p0 + delta, 0, maxv);
+            if (!no_q) p[4] = clip3i(q0 - delta, 0, maxv);
+            if (!no_p && dp0 + dp3 < side) p[2] = clip3i(p1 + clip3i((((p2 + p0 + 1) >> 1) - p1 + delta) >> 1, -th, th), 0, maxv);
+            if (!no_q && dq0 + dq3 < side) p[5] = clip3i(q1 + clip3i((((q2 + q0 + 1) >> 1) - q1 - delta) >> 1, -th, th), 0, maxv);
+        }
+    }
+}
+
+__device__ __forceinline__ void dbk_chroma_line(int (&p)[8], int tc, bool no_p, bool no_q, int bd)
+{
+    tc <<= bd - 8;
+    if (tc <= 0) return;
+    const int maxv = (1 << bd) - 1;
+    const int p1 = p[2], p0 = p[3], q0 = p[4], q1 = p[5];
+    const int delta = clip3i((((q0 - p0) * 4) + p1 - q1 + 4) >> 3, -tc, tc);
+    if (!no_p) p[3] = clip3i(p0 + delta, 0, maxv);
+    if (!no_q) p[4] = clip3i(q0 - delta, 0, maxv);
+}
+
+template <typename PIX>
+__global__ void __launch_bounds__(256) k_deblock(const uint16_t *__restrict__ grid, B200DbkLayout L, FrameDesc f, int bd)
+{
+    const int plane = blockIdx.z;
+    const PlaneDesc pd = f.p[plane];
+    const int gx0 = DBK_TW * blockIdx.x - 4, gy0 = DBK_TH * blockIdx.y - 4;
+    if (gx0 >= pd.w || gy0 >= pd.h) return;
+    __shared__ uint16_t t[DBK_TH][DBK_PITCH];
+    const int tid = threadIdx.x, lane = tid & 31;
+    // ---- load (units of 4 samples; plane widths are multiples of 4) ----
+    for (int u = tid; u < DBK_TH * (DBK_TW / 4); u += 256) {
+        const int row = u / (DBK_TW / 4), ux = u % (DBK_TW / 4), gx = gx0 + 4 * ux, gy = gy0 + row;
+        uint16_t a = 0, b = 0, c = 0, d = 0;
+        if (gx >= 0 && gx < pd.w && gy >= 0 && gy < pd.h) {
+            const PIX *s = px_ptr<PIX>(pd, gx, gy);
+            if (sizeof(PIX) == 2) { const uint2 q = *reinterpret_cast<const uint2 *>(s); a = q.x & 0xffff; b = q.x >> 16; c = q.y & 0xffff; d = q.y >> 16; }
+            else { const uint32_t q = *reinterpret_cast<const uint32_t *>(s); a = q & 0xff; b = (q >> 8) & 0xff; c = (q >> 16) & 0xff; d = q >> 24; }
+        }
+        t[row][4 * ux] = a; t[row][4 * ux + 1] = b; t[row][4 * ux + 2] = c; t[row][4 * ux + 3] = d;
+    }
+    __syncthreads();
+    // ---- vertical edges: thread = (edge column e, row) ----
+    {
+        const int e = tid >> 5, row = tid & 31, gxe = DBK_TW * blockIdx.x + 8 * e, gy = gy0 + row;
+        const bool valid = gxe > 0 && gxe < pd.w && gy >= 0 && gy < pd.h;
+        const uint16_t en = valid ? __ldg(grid + L.off[plane][0] + (gy >> 2) * L.stride[plane][0] + (gxe >> 3)) : 0;
+        int p[8];
+#pragma unroll
+        for (int i = 0; i < 8; i++) p[i] = t[row][8 * e + i];
+        const bool on = en & B200_DBK_PRESENT;
+        if (plane == 0) dbk_luma_line(p, on ? B200_DBK_BETA(en) : 0, on ? B200_DBK_TC(en) : 0, B200_DBK_NOP(en), B200_DBK_NOQ(en), bd, lane);
+        else if (on) dbk_chroma_line(p, B200_DBK_TC(en), B200_DBK_NOP(en), B200_DBK_NOQ(en), bd);
+        if (on) {
+#pragma unroll
+            for (int i = 1; i < 7; i++) t[row][8 * e + i] = (uint16_t)p[i];
+        }
+    }
+    __syncthreads();
+    // ---- horizontal edges: thread = (edge row f, column) ----
+    {
+        const int fr = tid >> 6, col = tid & 63, gye = DBK_TH * blockIdx.y + 8 * fr, gx = gx0 + col;
+        const bool valid = gye > 0 && gye < pd.h && gx >= 0 && gx < pd.w;
+        const uint16_t en = valid ? __ldg(grid + L.off[plane][1] + (gye >> 3) * L.stride[plane][1] + (gx >> 2)) : 0;
+        int p[8];
+#pragma unroll
+        for (int i = 0; i < 8; i++) p[i] = t[8 * fr + i][col];
+        const bool on = en & B200_DBK_PRESENT;
+        if (plane == 0) dbk_luma_line(p, on ? B200_DBK_BETA(en) : 0, on ? B200_DBK_TC(en) : 0, B200_DBK_NOP(en), B200_DBK_NOQ(en), bd, lane);
+        else if (on) dbk_chroma_line(p, B200_DBK_TC(en), B200_DBK_NOP(en), B200_DBK_NOQ(en), bd);
+        if (on) {
+#pragma unroll
+            for (int i = 1; i < 7; i++) t[8 * fr + i][col] = (uint16_t)p[i];
+        }
+    }
+    __syncthreads();
+    // ---- store ----
+    for (int u = tid; u < DBK_TH * (DBK_TW / 4); u += 256) {
+        const int row = u / (DBK_TW / 4), ux = u % (DBK_TW / 4), gx = gx0 + 4 * ux, gy = gy0 + row;
+        if (gx >= 0 && gx < pd.w && gy >= 0 && gy < pd.h) {
+            PIX *s = px_ptr<PIX>(pd, gx, gy);
+            const uint32_t a = t[row][4 * ux], b = t[row][4 * ux + 1], c = t[row][4 * ux + 2], d = t[row][4 * ux + 3];
+            if (sizeof(PIX) == 2) *reinterpret_cast<uint2 *>(s) = make_uint2(a | (b << 16), c | (d << 16));
+            else *reinterpret_cast<uint32_t *>(s) = a | (b << 8) | (c << 16) | (d << 24);
+        }
+    }
+}
+
+// --------------------------------------------------------------------------------------------
+// K5: SAO.  One CTA per CTB-plane tile; source = deblocked picture (never modified), destination
+// = DPB slot, so the reference's sao_frame copy / SAO_APPLIED bookkeeping (hevc_filter.c:267-319)
+// has no equivalent here.  CTBs without SAO are copied through.
+// --------------------------------------------------------------------------------------------
+#define SAO_PITCH 68
+
+template <typename PIX>
+__global__ void __launch_bounds__(256) k_sao(const B200SaoRec *__restrict__ grid, FrameDesc src, FrameDesc dst, int bd,
+                                             int log2_ctb, int ctb_w, int ctb_h, int cfi)
+{
+    const int plane = blockIdx.z, cx = blockIdx.x, cy = blockIdx.y;
+    const PlaneDesc sp = src.p[plane], dp = dst.p[plane];
+    const int hs = plane && cfi != 3, vs = plane && cfi == 1;
+    const int x0 = (cx << log2_ctb) >> hs, y0 = (cy << log2_ctb) >> vs;
+    const int w = min((1 << log2_ctb) >> hs, sp.w - x0), h = min((1 << log2_ctb) >> vs, sp.h - y0);
+    __shared__ uint16_t t[66][SAO_PITCH];
+    __shared__ B200SaoRec s_rec;
+    const int tid = threadIdx.x;
+    if (tid < 4) reinterpret_cast<uint32_t *>(&s_rec)[tid] = __ldg(reinterpret_cast<const uint32_t *>(grid + (plane * ctb_h + cy) * ctb_w + cx) + tid);
+    for (int i = tid; i < (h + 2) * (w + 2); i += 256) {
+        const int r = i / (w + 2), c = i - r * (w + 2);
+        const int gx = clip3i(x0 + c - 1, 0, sp.w - 1), gy = clip3i(y0 + r - 1, 0, sp.h - 1);
+        t[r][c] = *px_ptr<PIX>(sp, gx, gy);
+    }
+    __syncthreads();
+    const B200SaoRec s = s_rec;
+    const int maxv = (1 << bd) - 1;
+    const int cls = s.param;
+    const bool b_l = s.borders & 1, b_t = s.borders & 2, b_r = s.borders & 4, b_b = s.borders & 8;
+    const int dx0 = cls == 0 ? -1 : cls == 1 ? 0 : cls == 2 ? -1 : 1, dy0 = cls == 0 ? 0 : -1;
+    const int init_x = (cls != 1 && b_l) ? 1 : 0, wid = (cls != 1 && b_r) ? w - 1 : w, hei = (cls != 0 && b_b) ? h - 1 : h;
+    for (int i = tid; i < h * w; i += 256) {
+        const int y = i / w, x = i - y * w;
+        const int v = t[y + 1][x + 1];
+        int out = v;
+        if (s.type == B200_SAO_BAND) {
+            const int k = ((v >> (bd - 5)) - s.param) & 31;
+            if (k < 4) out = clip3i(v + s.offset_val[k + 1], 0, maxv);
+        } else if (s.type == B200_SAO_EDGE) {
+            const bool zero = (cls != 1 && ((b_l && x == 0) || (b_r && x == w - 1))) || (cls != 0 && ((b_t && y == 0) || (b_b && y == h - 1)));
+            if (zero) out = clip3i(v + s.offset_val[0], 0, maxv);
+            else {
+                const int a = t[y + 1 + dy0][x + 1 + dx0], b = t[y + 1 - dy0][x + 1 - dx0];
+                const int e = 2 + (v > a) - (v < a) + (v > b) - (v < b);
+                const int ei = e == 0 ? 1 : e == 1 ? 2 : e == 2 ? 0 : e;     // edge_idx[] = {1,2,0,3,4}
+                out = clip3i(v + s.offset_val[ei], 0, maxv);
+            }
+            if (s.variant) {   // not-across-boundary restore, hevcdsp_template.c:533-566 (2 = SAO_EO_135D, 3 = SAO_EO_45D)
+                const bool ve0 = s.edges & 1, ve1 = s.edges & 2, he0 = s.edges & 4, he1 = s.edges & 8;
+                const bool de0 = s.edges & 16, de1 = s.edges & 32, de2 = s.edges & 64, de3 = s.edges & 128;
+                const int sul = !de0 && cls == 2 && !b_l && !b_t, sur = !de1 && cls == 3 && !b_t && !b_r;
+                const int slr = !de2 && cls == 2 && !b_r && !b_b, sll = !de3 && cls == 3 && !b_l && !b_b;
+                bool rs = false;
+                rs |= ve0 && cls != 1 && x == 0 && y >= sul && y < hei - sll;
+                rs |= ve1 && cls != 1 && x == wid - 1 && y >= sur && y < hei - slr;
+                rs |= he0 && cls != 0 && y == 0 && x >= init_x + sul && x < wid - sur;
+                rs |= he1 && cls != 0 && y == hei - 1 && x >= init_x + sll && x < wid - slr;
+                rs |= de0 && cls == 2 && x == 0 && y == 0;
+                rs |= de1 && cls == 3 && x == wid - 1 && y == 0;
+                rs |= de2 && cls == 2 && x == wid - 1 && y == hei - 1;
+                rs |= de3 && cls == 3 && x == 0 && y == hei - 1;
+                if (rs) out = v;
+            }
+        }
+        *px_ptr<PIX>(dp, x0 + x, y0 + y) = (PIX)out;
+    }
+}
+
+template <typename PIX>
+__global__ void k_fill(FrameDesc f, int value)
+{
+    const int plane = blockIdx.z;
+    const PlaneDesc pd = f.p[plane];
+    const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
+    if (x < pd.w && y < pd.h) *px_ptr<PIX>(pd, x, y) = (PIX)value;
+}
+
+// --------------------------------------------------------------------------------------------
+// launchers
+// --------------------------------------------------------------------------------------------
+int launch_mc(cudaStream_t st, const B200McRec *recs, int count, const FrameDesc &cur, const FrameDesc *dpb_dev, int bd)
+{
+    if (!count) return 0;
+    const int grid = (count + 7) / 8;
+    if (bd > 8) k_mc<uint16_t><<<grid, 256, 0, st>>>(recs, count, cur, dpb_dev, bd);
+    else        k_mc<uint8_t><<<grid, 256, 0, st>>>(recs, count, cur, dpb_dev, bd);
+    return 1;
+}
+
+template <typename PIX>
+static int launch_residual_t(cudaStream_t st, const B200TuRec *const recs[4], const int counts[4], int16_t *pool, const FrameDesc &cur, int bd)
+{
+    int n = 0;
+    if (counts[0]) { k_residual<PIX, 4><<<(counts[0] + 31) / 32, 128, 0, st>>>(recs[0], counts[0], pool, cur, bd); n++; }
+    if (counts[1]) { k_residual<PIX, 8><<<(counts[1] + 15) / 16, 128, 0, st>>>(recs[1], counts[1], pool, cur, bd); n++; }
+    if (counts[2]) { k_residual<PIX, 16><<<(counts[2] + 7) / 8, 128, 0, st>>>(recs[2], counts[2], pool, cur, bd); n++; }
+    if (counts[3]) { k_residual<PIX, 32><<<(counts[3] + 3) / 4, 128, 0, st>>>(recs[3], counts[3], pool, cur, bd); n++; }
+    return n;
+}
+int launch_residual(cudaStream_t st, const B200TuRec *const recs[4], const int counts[4], int16_t *pool, const FrameDesc &cur, int bd)
+{
+    return bd > 8 ? launch_residual_t<uint16_t>(st, recs, counts, pool, cur, bd) : launch_residual_t<uint8_t>(st, recs, counts, pool, cur, bd);
+}
+
+int launch_intra(cudaStream_t st, const B200IntraRec *recs, int count, const int16_t *pool, const FrameDesc &cur, int bd,
+                 uint32_t *flags[3], const int flag_stride[3], uint32_t *counter)
+{
+    if (!count) return 0;
+    IntraFlags fl;
+    for (int p = 0; p < 3; p++) { fl.f[p] = flags[p]; fl.stride[p] = flag_stride[p]; }
+    cudaMemsetAsync(counter, 0, sizeof(uint32_t), st);   // counter[1] = sticky abort flag, cleared at context creation
+    k_intra_prepass<<<(count + 255) / 256, 256, 0, st>>>(recs, count, fl);
+    int grid = (count + 3) / 4;
+    if (grid > 148 * 8) grid = 148 * 8;   // persistent: 8 CTAs of 4 warps per SM
+    if (bd > 8) k_intra<uint16_t><<<grid, 128, 0, st>>>(recs, count, pool, cur, bd, fl, counter);
+    else        k_intra<uint8_t><<<grid, 128, 0, st>>>(recs, count, pool, cur, bd, fl, counter);
+    return 2;
+}
+
+int launch_deblock(cudaStream_t st, const uint16_t *grid, const B200DbkLayout &L, const FrameDesc &cur, int bd)
+{
+    const dim3 g((cur.p[0].w + 4 + DBK_TW - 1) / DBK_TW, (cur.p[0].h + 4 + DBK_TH - 1) / DBK_TH, 3);
+    if (bd > 8) k_deblock<uint16_t><<<g, 256, 0, st>>>(grid, L, cur, bd);
+    else        k_deblock<uint8_t><<<g, 256, 0, st>>>(grid, L, cur, bd);
+    return 1;
+}
+
+int launch_sao(cudaStream_t st, const B200SaoRec *grid, const FrameDesc &src, const FrameDesc &dst, int bd,
+               int log2_ctb, int ctb_w, int ctb_h, int cfi)
+{
+    const dim3 g(ctb_w, ctb_h, 3);
+    if (bd > 8) k_sao<uint16_t><<<g, 256, 0, st>>>(grid, src, dst, bd, log2_ctb, ctb_w, ctb_h, cfi);
+    else        k_sao<uint8_t><<<g, 256, 0, st>>>(grid, src, dst, bd, log2_ctb, ctb_w, ctb_h, cfi);
+    return 1;
+}
+
+int launch_fill(cudaStream_t st, const FrameDesc &f, int bd, int value)
+{
+    const dim3 g((f.p[0].w + 255) / 256, f.p[0].h, 3);
+    if (bd > 8) k_fill<uint16_t><<<g, 256, 0, st>>>(f, value);
+    else        k_fill<uint8_t><<<g, 256, 0, st>>>(f, value);
+    return 1;
+}

@@ -1,0 +1,230 @@
+// recorder.cpp — host side of the drop-in: turns the reference's per-block table calls into
+// one packed work-list blob per picture (include/b200hevc_worklist.h).  Pure host code.
+//
+// Blob layout produced here:  header | deblock grids | SAO grid | coefficient pool (grows while
+// recording) | TU4 | TU8 | TU16 | TU32 | INTRA | MC   (lists appended by b200_rec_finish).
+#include <stdlib.h>
+#include <string.h>
+#include <vector>
+#include "../../include/b200hevc.h"
+
+struct B200Rec {
+    B200Config cfg;
+    int pw[3], ph[3];
+    B200DbkLayout dbk;
+    int ctb_w, ctb_h;
+    uint8_t *blob = nullptr;
+    bool pinned = false;
+    uint64_t cap = 0;
+    uint32_t off_dbk, off_sao, off_pool;
+    uint32_t ncoef = 0;
+    std::vector<B200TuRec> tu[4];
+    std::vector<B200IntraRec> intra;
+    std::vector<B200McRec> mc;
+    int last_intra[3];
+    bool any_dbk = false, any_sao = false, open = false;
+    int cur_slot = 0, poc = 0;
+    uint64_t nbytes = 0;
+};
+
+static uint64_t rec_capacity(const B200Config *c, const B200DbkLayout &L, int nctb)
+{
+    uint64_t samples = 0;
+    for (int p = 0; p < 3; p++) { int w, h; b200_plane_dims(c->width, c->height, c->chroma_format_idc, p, &w, &h); samples += (uint64_t)w * h; }
+    const uint64_t u = samples / 16;
+    uint64_t v = 4096 + samples * 2 + u * (16 + 16 + 32) + (uint64_t)L.total * 2 + (uint64_t)nctb * 3 * 16 + (1u << 20);
+    if (c->max_blob_bytes && c->max_blob_bytes < v) v = c->max_blob_bytes;
+    return (v + 4095) & ~(uint64_t)4095;
+}
+
+extern "C" int b200_rec_create(const B200Config *cfg, B200Rec **out)
+{
+    if (!cfg || !out || cfg->width < 16 || cfg->height < 16 || (cfg->width & 7) || (cfg->height & 7) ||
+        cfg->chroma_format_idc < 1 || cfg->chroma_format_idc > 3 || cfg->bit_depth < 8 || cfg->bit_depth > 12 ||
+        cfg->log2_ctb_size < 4 || cfg->log2_ctb_size > 6)
+        return B200_EINVAL;
+    B200Rec *r = new B200Rec();
+    r->cfg = *cfg;
+    for (int p = 0; p < 3; p++) b200_plane_dims(cfg->width, cfg->height, cfg->chroma_format_idc, p, &r->pw[p], &r->ph[p]);
+    b200_dbk_layout(cfg->width, cfg->height, cfg->chroma_format_idc, &r->dbk);
+    const int ctb = 1 << cfg->log2_ctb_size;
+    r->ctb_w = (cfg->width + ctb - 1) >> cfg->log2_ctb_size;
+    r->ctb_h = (cfg->height + ctb - 1) >> cfg->log2_ctb_size;
+    r->cap = rec_capacity(cfg, r->dbk, r->ctb_w * r->ctb_h);
+    r->blob = (uint8_t *)b200_host_alloc(r->cap);           // pinned when a GPU is present
+    r->pinned = r->blob != nullptr;
+    if (!r->blob && posix_memalign((void **)&r->blob, 4096, r->cap)) { delete r; return B200_ENOMEM; }
+    r->off_dbk = 256;
+    r->off_sao = b200_align_u32(r->off_dbk + r->dbk.total * 2, 256);
+    r->off_pool = b200_align_u32(r->off_sao + (uint32_t)(3 * r->ctb_w * r->ctb_h) * 16, 256);
+    *out = r;
+    return 0;
+}
+
+extern "C" void b200_rec_destroy(B200Rec *r)
+{
+    if (!r) return;
+    if (r->pinned) b200_host_free(r->blob); else free(r->blob);
+    delete r;
+}
+
+extern "C" int b200_rec_begin(B200Rec *r, int cur_slot, int poc)
+{
+    if (!r || cur_slot < 0 || cur_slot > 255) return B200_EINVAL;
+    memset(r->blob + r->off_dbk, 0, r->off_pool - r->off_dbk);
+    for (int s = 0; s < 4; s++) r->tu[s].clear();
+    r->intra.clear(); r->mc.clear();
+    r->ncoef = 0; r->any_dbk = r->any_sao = false;
+    r->last_intra[0] = r->last_intra[1] = r->last_intra[2] = -1;
+    r->cur_slot = cur_slot; r->poc = poc; r->open = true; r->nbytes = 0;
+    return 0;
+}
+
+static int16_t *pool_take(B200Rec *r, int n, uint32_t *off)
+{
+    const uint32_t o = (r->ncoef + 7) & ~7u;
+    if ((uint64_t)r->off_pool + ((uint64_t)o + n) * 2 + (1u << 16) > r->cap) return nullptr;
+    *off = o;
+    r->ncoef = o + n;
+    return (int16_t *)(r->blob + r->off_pool) + o;
+}
+
+extern "C" int b200_rec_tu(B200Rec *r, int plane, int x, int y, int log2, int kind, int flags, int col_limit,
+                           const int16_t *coeffs, int intra_linked)
+{
+    if (!r || !r->open || !coeffs || plane < 0 || plane > 2 || log2 < 2 || log2 > 5 || kind < 0 || kind > B200_TU_PCM) return B200_EINVAL;
+    const int n = 1 << log2;
+    if (x < 0 || y < 0 || x + n > r->pw[plane] || y + n > r->ph[plane]) return B200_EINVAL;
+    if (kind == B200_TU_DST && log2 != 2) return B200_EINVAL;
+    uint32_t off;
+    int16_t *dst = pool_take(r, n * n, &off);
+    if (!dst) return B200_ENOMEM;
+    memcpy(dst, coeffs, (size_t)n * n * 2);
+    B200TuRec t;
+    memset(&t, 0, sizeof(t));
+    t.x = (uint16_t)x; t.y = (uint16_t)y; t.plane = (uint8_t)plane; t.log2 = (uint8_t)log2; t.kind = (uint8_t)kind;
+    t.flags = (uint8_t)(flags & (B200_TUF_RDPCM | B200_TUF_RDPCM_VERT));
+    t.col_limit = (uint8_t)(col_limit < 0 ? 0 : col_limit > 255 ? 255 : col_limit);
+    t.coeff_off = off;
+    // residual of an intra TU: park it, the intra kernel adds it right after predicting the block
+    const int li = r->last_intra[plane];
+    bool link = false;
+    if (li >= 0 && kind != B200_TU_PCM) {
+        B200IntraRec &ir = r->intra[li];
+        link = ir.x == x && ir.y == y && ir.log2 == log2 && ir.resid_off == B200_NO_RESID;
+        if (intra_linked == 0) link = false;
+        if (link) { ir.resid_off = off; t.flags |= B200_TUF_PARK; }
+    }
+    if (intra_linked == 1 && !link) return B200_ESTATE;
+    r->tu[log2 - 2].push_back(t);
+    return 0;
+}
+
+extern "C" int b200_rec_pcm(B200Rec *r, int plane, int x, int y, int log2, const int16_t *samples)
+{
+    return b200_rec_tu(r, plane, x, y, log2, B200_TU_PCM, 0, 0, samples, 0);
+}
+
+extern "C" int b200_rec_intra(B200Rec *r, int plane, int x, int y, int log2, int mode, int flags, int top_right_size, int bottom_left_size)
+{
+    if (!r || !r->open || plane < 0 || plane > 2 || log2 < 2 || log2 > 5 || mode < 0 || mode > 34) return B200_EINVAL;
+    const int n = 1 << log2;
+    if (x < 0 || y < 0 || (x & 3) || (y & 3) || x + n > r->pw[plane] || y + n > r->ph[plane]) return B200_EINVAL;
+    B200IntraRec ir;
+    memset(&ir, 0, sizeof(ir));
+    ir.x = (uint16_t)x; ir.y = (uint16_t)y; ir.plane = (uint8_t)plane; ir.log2 = (uint8_t)log2; ir.mode = (uint8_t)mode;
+    ir.flags = (uint8_t)flags;
+    ir.top_right_size = (uint8_t)((flags & B200_INF_UP_RIGHT) ? top_right_size : 0);
+    ir.bottom_left_size = (uint8_t)((flags & B200_INF_BOTTOM_LEFT) ? bottom_left_size : 0);
+    ir.resid_off = B200_NO_RESID;
+    r->last_intra[plane] = (int)r->intra.size();
+    r->intra.push_back(ir);
+    return 0;
+}
+
+extern "C" int b200_rec_mc(B200Rec *r, const B200McRec *b)
+{
+    if (!r || !r->open || !b || b->plane > 2 || !b->w || !b->h || b->w > 64 || b->h > 64) return B200_EINVAL;
+    if (b->x + b->w > r->pw[b->plane] || b->y + b->h > r->ph[b->plane]) return B200_EINVAL;
+    // split into tiles of <= 32 x 8 or <= 16 x 16 samples: one warp each on the device
+    for (int tx = 0; tx < b->w;) {
+        const int tw = b->w - tx > 32 ? 32 : b->w - tx;
+        const int maxh = tw > 16 ? 8 : 16;
+        for (int ty = 0; ty < b->h; ty += maxh) {
+            const int th = b->h - ty > maxh ? maxh : b->h - ty;
+            B200McRec t = *b;
+            t.x = (uint16_t)(b->x + tx); t.y = (uint16_t)(b->y + ty); t.w = (uint8_t)tw; t.h = (uint8_t)th;
+            t.sx0 = (int16_t)(b->sx0 + tx); t.sy0 = (int16_t)(b->sy0 + ty);
+            t.sx1 = (int16_t)(b->sx1 + tx); t.sy1 = (int16_t)(b->sy1 + ty);
+            r->mc.push_back(t);
+        }
+        tx += tw;
+    }
+    return 0;
+}
+
+extern "C" int b200_rec_deblock(B200Rec *r, int plane, int vertical, int x, int y, int beta, const int tc[2],
+                                const uint8_t no_p[2], const uint8_t no_q[2])
+{
+    if (!r || !r->open || plane < 0 || plane > 2 || !tc || !no_p || !no_q) return B200_EINVAL;
+    if (x < 0 || y < 0 || x >= r->pw[plane] || y >= r->ph[plane]) return B200_EINVAL;
+    if (vertical ? ((x & 7) || (y & 3) || !x) : ((y & 7) || (x & 3) || !y)) return B200_EINVAL;
+    if (beta < 0 || beta > 127 || tc[0] < 0 || tc[0] > 63 || tc[1] < 0 || tc[1] > 63) return B200_ENOTSUP;
+    uint16_t *g = (uint16_t *)(r->blob + r->off_dbk) + r->dbk.off[plane][vertical ? 0 : 1];
+    const int gs = (int)r->dbk.stride[plane][vertical ? 0 : 1];
+    for (int j = 0; j < 2; j++) {
+        const int sx = vertical ? x : x + 4 * j, sy = vertical ? y + 4 * j : y;
+        if (sx >= r->pw[plane] || sy >= r->ph[plane]) continue;
+        const int idx = vertical ? (sy >> 2) * gs + (sx >> 3) : (sy >> 3) * gs + (sx >> 2);
+        g[idx] = B200_DBK_PACK(tc[j], plane ? 0 : beta, no_p[j] != 0, no_q[j] != 0);
+    }
+    r->any_dbk = true;
+    return 0;
+}
+
+extern "C" int b200_rec_sao(B200Rec *r, int plane, int x, int y, const B200SaoRec *p)
+{
+    if (!r || !r->open || !p || plane < 0 || plane > 2 || x < 0 || y < 0 || x >= r->pw[plane] || y >= r->ph[plane]) return B200_EINVAL;
+    const int hs = plane && r->cfg.chroma_format_idc != 3, vs = plane && r->cfg.chroma_format_idc == 1;
+    const int cx = (x << hs) >> r->cfg.log2_ctb_size, cy = (y << vs) >> r->cfg.log2_ctb_size;
+    B200SaoRec *g = (B200SaoRec *)(r->blob + r->off_sao);
+    g[(plane * r->ctb_h + cy) * r->ctb_w + cx] = *p;
+    if (p->type != B200_SAO_NONE) r->any_sao = true;
+    return 0;
+}
+
+extern "C" int b200_rec_finish(B200Rec *r, const void **blob, uint64_t *nbytes)
+{
+    if (!r || !r->open || !blob || !nbytes) return B200_EINVAL;
+    B200BlobHeader *h = (B200BlobHeader *)r->blob;
+    memset(h, 0, sizeof(*h));
+    h->magic = B200_BLOB_MAGIC; h->version = B200_BLOB_VERSION;
+    h->poc = r->poc;
+    h->width = (uint16_t)r->cfg.width; h->height = (uint16_t)r->cfg.height;
+    h->chroma_format_idc = (uint8_t)r->cfg.chroma_format_idc; h->bit_depth = (uint8_t)r->cfg.bit_depth;
+    h->log2_ctb_size = (uint8_t)r->cfg.log2_ctb_size; h->cur_slot = (uint8_t)r->cur_slot;
+    h->flags = (r->any_dbk ? B200_FRAME_HAS_DEBLOCK : 0) | (r->any_sao ? B200_FRAME_HAS_SAO : 0);
+    h->sec[B200_SEC_DBK].off = r->off_dbk; h->sec[B200_SEC_DBK].count = r->any_dbk ? r->dbk.total : 0;
+    h->sec[B200_SEC_SAO].off = r->off_sao; h->sec[B200_SEC_SAO].count = r->any_sao ? (uint32_t)(3 * r->ctb_w * r->ctb_h) : 0;
+    h->sec[B200_SEC_COEFF].off = r->off_pool; h->sec[B200_SEC_COEFF].count = (r->ncoef + 7) & ~7u;
+    uint64_t o = b200_align_u32(r->off_pool + h->sec[B200_SEC_COEFF].count * 2, 256);
+    uint64_t need = o;
+    for (int s = 0; s < 4; s++) need += ((uint64_t)r->tu[s].size() * 16 + 255) & ~(uint64_t)255;
+    need += (((uint64_t)r->intra.size() * 16 + 255) & ~(uint64_t)255) + (((uint64_t)r->mc.size() * 32 + 255) & ~(uint64_t)255);
+    if (need > r->cap) return B200_ENOMEM;
+    for (int s = 0; s < 4; s++) {
+        h->sec[B200_SEC_TU4 + s].off = (uint32_t)o; h->sec[B200_SEC_TU4 + s].count = (uint32_t)r->tu[s].size();
+        if (!r->tu[s].empty()) memcpy(r->blob + o, r->tu[s].data(), r->tu[s].size() * 16);
+        o = (o + r->tu[s].size() * 16 + 255) & ~(uint64_t)255;
+    }
+    h->sec[B200_SEC_INTRA].off = (uint32_t)o; h->sec[B200_SEC_INTRA].count = (uint32_t)r->intra.size();
+    if (!r->intra.empty()) memcpy(r->blob + o, r->intra.data(), r->intra.size() * 16);
+    o = (o + r->intra.size() * 16 + 255) & ~(uint64_t)255;
+    h->sec[B200_SEC_MC].off = (uint32_t)o; h->sec[B200_SEC_MC].count = (uint32_t)r->mc.size();
+    if (!r->mc.empty()) memcpy(r->blob + o, r->mc.data(), r->mc.size() * 32);
+    o = (o + r->mc.size() * 32 + 255) & ~(uint64_t)255;
+    h->total_bytes = (uint32_t)o;
+    r->nbytes = o; r->open = false;
+    *blob = r->blob; *nbytes = o;
+    return 0;
+}

@@ -1,0 +1,75 @@
+"""TEST INFRASTRUCTURE: ctypes access to the CPU oracle (oracle/hevc_oracle.c) and helpers that
+compare the CUDA path with it.  Never imported by the product package."""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ORACLE_DIR = os.path.join(ROOT, "oracle")
+ORACLE_SO = os.path.join(ORACLE_DIR, "_ref", "libhevc_oracle.so")
+KAT_REF = os.path.join(ORACLE_DIR, "_ref", "kat_ref")
+REF_SO = os.path.join(ORACLE_DIR, "_ref", "libohevc_ref.so")
+
+_lib = None
+
+
+def build_oracle():
+    subprocess.run(["make", "-C", ORACLE_DIR], check=True, capture_output=True)
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        if not os.path.exists(ORACLE_SO):
+            build_oracle()
+        _lib = C.CDLL(ORACLE_SO)
+        _lib.orc_execute_blob.restype = C.c_int
+        _lib.orc_execute_blob.argtypes = [C.c_void_p, C.POINTER(C.c_void_p), C.c_int]
+    return _lib
+
+
+def execute(blob, dpb):
+    """dpb: list of slots, each a list of three numpy planes (any unsigned dtype).  Executes the blob on the
+    CPU oracle and returns the reconstructed picture of slot hdr.cur_slot as three uint16 planes."""
+    blob = np.ascontiguousarray(blob, np.uint8)
+    planes16 = [[np.ascontiguousarray(p, np.uint16).copy() for p in slot] for slot in dpb]
+    flat = [p for slot in planes16 for p in slot]
+    ptrs = (C.c_void_p * len(flat))(*[p.ctypes.data for p in flat])
+    rc = lib().orc_execute_blob(blob.ctypes.data, ptrs, len(dpb))
+    if rc:
+        raise RuntimeError(f"orc_execute_blob failed: {rc}")
+    cur = int(blob[23])
+    return planes16[cur]
+
+
+def check_decode_order(blob):
+    """host-side validation of a blob's intra list: every neighbour unit an intra TU reads must be final
+    (not covered by a *later* intra TU).  A violation would make the device wavefront wait forever."""
+    from openhevc_b200 import worklist as W
+    hdr, secs = W.parse_blob(blob)
+    intra = secs[W.SEC_INTRA]
+    w, h, cfi = int(hdr["width"]), int(hdr["height"]), int(hdr["chroma_format_idc"])
+    order = []
+    for p in range(3):
+        pw, ph = W.plane_dims(w, h, cfi, p)
+        order.append(np.full((ph // 4 + 1, pw // 4 + 1), -1, np.int64))
+    for i, r in enumerate(intra):
+        u = 1 << (int(r["log2"]) - 2)
+        o = order[int(r["plane"])]
+        assert (o[int(r["y"]) // 4:int(r["y"]) // 4 + u, int(r["x"]) // 4:int(r["x"]) // 4 + u] == -1).all(), f"intra TU {i} overlaps an earlier one"
+        o[int(r["y"]) // 4:int(r["y"]) // 4 + u, int(r["x"]) // 4:int(r["x"]) // 4 + u] = i
+    for i, r in enumerate(intra):
+        n, x, y, f = 1 << int(r["log2"]), int(r["x"]), int(r["y"]), int(r["flags"])
+        o = order[int(r["plane"])]
+        need = []
+        if f & W.INF_UP_LEFT: need.append((x - 1, y - 1))
+        if f & W.INF_UP: need += [(x + k, y - 1) for k in range(0, n, 4)]
+        if f & W.INF_UP_RIGHT: need += [(x + n + k, y - 1) for k in range(0, int(r["top_right_size"]), 4)]
+        if f & W.INF_LEFT: need += [(x - 1, y + k) for k in range(0, n, 4)]
+        if f & W.INF_BOTTOM_LEFT: need += [(x - 1, y + n + k) for k in range(0, int(r["bottom_left_size"]), 4)]
+        for (px, py) in need:
+            assert px >= 0 and py >= 0, f"intra TU {i} reads outside the picture"
+            assert o[py // 4, px // 4] < i, f"intra TU {i} depends on later TU {o[py // 4, px // 4]}"
+    return True
