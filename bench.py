@@ -1,0 +1,309 @@
+#!/usr/bin/env python
+"""bench.py — decoded frames/s of openHEVC's pixel-reconstruction path on B200 (driver contract).
+
+Workload (BASELINE.json configs[2]/[3]): 3840x2160 Main10 4:2:0 random-access stream, hierarchical-B GOP 8,
+intra period 32, synthetic work lists (openhevc_b200/synth.py).  One *step* = one GOP
+(8 pictures) per rank; pictures of GOP g are decoded by rank g mod N, anchors are broadcast over NCCL
+(openhevc_b200/frame_parallel.py).  `value` = pictures/s with all work lists resident in HBM;
+`e2e` = the same through the host-facing C ABI: pinned host blob -> H2D -> K1..K5 -> D2H of the picture.
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+import numpy as np  # noqa: E402
+
+WORKLOADS = {
+    "c3_4k_main10_ra": dict(width=3840, height=2160, cfi=1, bit_depth=10),
+    "c2_1080p_main_ra": dict(width=1920, height=1080, cfi=1, bit_depth=8),
+    "c1_832x480_main": dict(width=832, height=480, cfi=1, bit_depth=8),
+}
+METRIC, UNIT = "decoded_frames_per_sec", "frames/s"
+
+
+def make_blobs(wl, out_alloc=None):
+    """the 9 distinct pictures of the periodic stream; symbolic reference table [0, 1], cur_slot 2"""
+    from openhevc_b200.synth import FrameSynth
+    from openhevc_b200 import frame_parallel as FP
+    blobs, stats = [], []
+    for i, (name, n_ref) in enumerate(FP.blob_specs()):
+        s = FrameSynth(wl["width"], wl["height"], wl["cfi"], wl["bit_depth"], seed=0xB2000003 + i, refs=list(range(n_ref)),
+                       cur_slot=2, poc=i, p_intra=0.08 if n_ref else 1.0, weighted=False)
+        blob, st = s.generate()
+        if out_alloc is not None:
+            buf = out_alloc(blob.nbytes)
+            buf[:blob.nbytes] = blob
+            blob = buf[:blob.nbytes]
+        blobs.append(blob); stats.append(st)
+    return blobs, stats
+
+
+def stream_mix():
+    """how often each blob occurs per intra period (4 GOPs = 32 pictures)"""
+    from openhevc_b200 import frame_parallel as FP
+    mix = {}
+    for g in range(FP.INTRA_PERIOD_GOPS):
+        for p in FP.gop_pictures(g):
+            mix[p.blob] = mix.get(p.blob, 0) + 1
+    return mix
+
+
+class ClockSampler:
+    Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index):
+        self.rows, self.proc = [], None
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append((time.time(), line.strip()))
+
+    def stop(self, t0, t1):
+        if not self.proc:
+            return None
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        for (t, line) in self.rows:
+            if t < t0 - 0.05 or t > t1 + 0.15:
+                continue
+            f = [x.strip() for x in line.split(",")]
+            try:
+                sm.append(float(f[0])); mx.append(float(f[1]))
+            except Exception:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        if not sm:
+            return None
+        return {"sm_mhz": statistics.median(sm), "sm_max_mhz": max(mx), "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def run_reference(args, wl, rank):
+    """--impl reference: the reference's own C functions (oracle/_ref, built from /root/reference) replaying the
+    same work lists on the host cores, frame-parallel over pthreads like its frame threads."""
+    if rank != 0:
+        return
+    import oracle_lib
+    from openhevc_b200.synth import smooth_frame
+    if oracle_lib.ref_lib() is None:
+        print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/libreplay_ref.so missing (reference build not shipped)"}))
+        return
+    blobs, _ = make_blobs(wl)
+    mix = stream_mix()
+    seq = [blobs[b] for b, n in sorted(mix.items()) for _ in range(n)]
+    rng = np.random.default_rng(1)
+    seq = [seq[i] for i in rng.permutation(len(seq))]
+    dpb = [smooth_frame(wl["width"], wl["height"], wl["cfi"], wl["bit_depth"], 7 + k) for k in range(3)]
+    threads = os.cpu_count() or 1
+    threads = min(threads, 256)
+
+    def iters_for(gops):
+        return max(1, -(-gops * 8 // threads))
+    if args.warmup:
+        oracle_lib.ref_bench(seq, dpb, threads, 1)
+    it = iters_for(args.steps)
+    sec = oracle_lib.ref_bench(seq, dpb, threads, it)
+    n = threads * it
+    fps = n / sec
+    line = {"metric": METRIC, "value": fps, "unit": UNIT, "impl": "reference", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": 1e3 * sec / max(1, n / 8), "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u16" if wl["bit_depth"] > 8 else "u8",
+            "data": "synthetic", "config": {"workload": args.workload, "gop": "hierarchical-B 8, intra period 32", "pictures_timed": n},
+            "mpixels_per_s": fps * wl["width"] * wl["height"] / 1e6,
+            "cpu_baseline": {"value": fps, "unit": UNIT, "cores": threads, "kind": "reference",
+                             "sample": f"{n} pictures of the bench stream mix, {threads} threads x {it} pictures, reference C tables (-O3 -fno-tree-vectorize, no asm)"},
+            "e2e": {"value": fps, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=16, help="GOPs (8 pictures) per rank in the timed region")
+    ap.add_argument("--warmup", type=int, default=4)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="c3_4k_main10_ra", choices=sorted(WORKLOADS))
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    wl = WORKLOADS[args.workload]
+    rank, world, local = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1)), int(os.environ.get("LOCAL_RANK", 0))
+    if args.impl == "reference":
+        return run_reference(args, wl, rank)
+    args.warmup = max(args.warmup, 3)
+
+    import torch
+    import torch.distributed as dist
+    from openhevc_b200 import FrameEngine, _lib
+    from openhevc_b200 import frame_parallel as FP
+    from openhevc_b200.synth import smooth_frame
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; openhevc_b200 has no CPU fallback")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    # ---- engine with the DPB inside a torch tensor (so NCCL can address slots) --------------------------------
+    lib = _lib.load()
+    cfg = _lib.B200Config(local, wl["width"], wl["height"], wl["cfi"], wl["bit_depth"], 6, FP.N_SLOTS, 16, 0, None, 0)
+    slot_bytes = int(lib.b200_dpb_bytes(cfg)) // FP.N_SLOTS
+    dpb = torch.zeros(FP.N_SLOTS * slot_bytes, dtype=torch.uint8, device=f"cuda:{local}")
+    eng = FrameEngine(wl["width"], wl["height"], wl["cfi"], wl["bit_depth"], n_slots=FP.N_SLOTS, n_arenas=16, device=local,
+                      ext_frame_mem=dpb.data_ptr(), ext_frame_bytes=dpb.numel())
+    assert eng.slot_bytes() == slot_bytes
+    blobs, stats = make_blobs(wl, out_alloc=eng.pinned)
+    mix = stream_mix()
+    npic_mix = sum(mix.values())
+    eng.upload_slot(FP.anchor_slot(-1), smooth_frame(wl["width"], wl["height"], wl["cfi"], wl["bit_depth"], 7))
+    for b, blob in enumerate(blobs):
+        eng.upload(blob, b)
+    eng.sync()
+    backend = FP.GpuBackend(eng, dpb, slot_bytes, world, list(range(FP.N_BLOBS)))
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- value: device-resident work lists ----------------------------------------------------------------------
+    FP.run_schedule(backend, rank, world, args.warmup)
+    eng.sync(); barrier()
+    sampler = ClockSampler(local) if rank == 0 else None
+    l0 = eng.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0 = time.time()
+    e0.record(backend.compute)
+    n_mine = FP.run_schedule(backend, rank, world, args.steps)
+    e1.record(backend.compute)
+    eng.sync(); torch.cuda.synchronize()
+    t1 = time.time()
+    ms = torch.tensor([e0.elapsed_time(e1)], device=f"cuda:{local}")
+    launches = eng.launch_count() - l0
+    barrier()
+    clocks = sampler.stop(t0, t1) if sampler else None
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    ms = float(ms.item())
+    n_total = args.steps * 8 * world
+    fps = n_total / (ms * 1e-3)
+
+    # ---- per-stage times of every distinct picture (CUDA events inside the library, on its compute stream) ----
+    eng.set_profiling(True)
+    stage_ms = {k: 0.0 for k in ("mc", "residual", "intra", "deblock", "sao", "total")}
+    reps = 3
+    for b in range(FP.N_BLOBS):
+        pic = next(p for g in range(FP.INTRA_PERIOD_GOPS) for p in FP.gop_pictures(g) if p.blob == b)
+        acc = {k: 0.0 for k in stage_ms}
+        for _ in range(reps):
+            eng.execute(b, pic.cur_slot, pic.ref_slots)
+            for k, v in eng.stage_ms().items():
+                acc[k] += v / reps
+        for k in stage_ms:
+            stage_ms[k] += acc[k] * mix[b] / npic_mix
+    eng.set_profiling(False)
+    B = 2 if wl["bit_depth"] > 8 else 1
+    abytes = {k: sum(stats[b]["bytes_" + k] * mix[b] for b in mix) / npic_mix for k in ("mc", "residual", "intra", "deblock", "sao")}
+    peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(peaks_path):
+        peak, peak_src = float(json.load(open(peaks_path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    else:
+        peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
+    stages = {k: {"ms": stage_ms[k], "algorithmic_bytes": abytes[k], "gbps": abytes[k] / (stage_ms[k] * 1e-3) / 1e9 if stage_ms[k] > 0 else None}
+              for k in abytes}
+    dom = max(abytes, key=lambda k: stage_ms[k])
+    roofline = {"bound": "hbm", "kernel": {"mc": "k_mc", "residual": "k_residual", "intra": "k_intra", "deblock": "k_deblock", "sao": "k_sao"}[dom],
+                "achieved": stages[dom]["gbps"], "peak": peak, "unit": "GB/s", "frac": stages[dom]["gbps"] / peak, "peak_source": peak_src,
+                "traffic": None, "share_of_step": stage_ms[dom] / stage_ms["total"], "stages": stages,
+                "whole_picture": {"algorithmic_bytes": sum(abytes.values()), "ms": stage_ms["total"],
+                                  "gbps": sum(abytes.values()) / (stage_ms["total"] * 1e-3) / 1e9}}
+
+    # ---- e2e: pinned host work list -> H2D -> kernels -> D2H of the reconstructed picture, every picture ----------
+    host_out = [eng.new_host_frame(pinned=True) for _ in range(8)]
+
+    class E2E(FP.GpuBackend):
+        def __init__(self, *a):
+            super().__init__(*a)
+            self.k = 0
+
+        def decode(self, pic):
+            a = self.k % 16
+            self.eng.upload(blobs[pic.blob], a)
+            self.eng.execute(a, pic.cur_slot, pic.ref_slots)
+            self.eng.readback(pic.cur_slot, host_out[self.k % 8], sync=False)
+            self.k += 1
+            if self.k % 8 == 0:                 # bound the run-ahead of the host thread (host buffers are reused)
+                self.eng.sync()
+
+    be2 = E2E(eng, dpb, slot_bytes, world, list(range(FP.N_BLOBS)))
+    e2e_steps = max(2, args.steps // 2)
+    FP.run_schedule(be2, rank, world, 1)
+    eng.sync(); barrier()
+    w0 = time.perf_counter()
+    FP.run_schedule(be2, rank, world, e2e_steps)
+    eng.sync(); torch.cuda.synchronize()
+    w1 = torch.tensor([time.perf_counter() - w0], device=f"cuda:{local}")
+    barrier()
+    if world > 1:
+        dist.all_reduce(w1, op=dist.ReduceOp.MAX)
+    e2e_fps = e2e_steps * 8 * world / float(w1.item())
+    h2d = sum(blobs[b].nbytes * mix[b] for b in mix) / npic_mix * 8
+    d2h = sum(int(np.prod(eng.plane_shape(p))) for p in range(3)) * B * 8
+    for b in range(FP.N_BLOBS):                  # e2e rotated the arenas: restore nothing needed, blobs are re-uploaded on demand
+        pass
+
+    # ---- CPU baseline: the reference's own C path on this box's host cores (rank 0, N=1 only) --------------------
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        try:
+            import oracle_lib
+            if oracle_lib.ref_lib() is not None:
+                rng = np.random.default_rng(1)
+                seq = [np.array(blobs[b]) for b, n in sorted(mix.items()) for _ in range(n)]
+                seq = [seq[i] for i in rng.permutation(len(seq))]
+                cdpb = [smooth_frame(wl["width"], wl["height"], wl["cfi"], wl["bit_depth"], 7 + k) for k in range(3)]
+                threads = min(os.cpu_count() or 1, 256)
+                it = 2 if wl["width"] >= 3840 else 8
+                sec = oracle_lib.ref_bench(seq, cdpb, threads, it)
+                cpu = {"value": threads * it / sec, "unit": UNIT, "cores": threads, "kind": "reference",
+                       "sample": f"{threads * it} pictures of the same stream mix ({threads} threads x {it}), reference C tables via oracle/replay_ref.c, {sec:.1f} s"}
+        except Exception as ex:                  # the baseline is a report, never a reason to lose the bench line
+            cpu = {"value": None, "unit": UNIT, "cores": 0, "kind": "reference", "sample": f"failed: {ex}"}
+
+    if rank == 0:
+        line = {"metric": METRIC, "value": fps, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+                "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "dtype": "u16" if wl["bit_depth"] > 8 else "u8", "data": "synthetic",
+                "config": {"workload": args.workload, "picture": f"{wl['width']}x{wl['height']} 4:2:0 {wl['bit_depth']}-bit", "gop": "hierarchical-B 8, intra period 32",
+                           "step": "1 GOP (8 pictures) per rank", "parallelism": f"frame-parallel x{world}, anchor broadcast over NCCL" if world > 1 else "single GPU",
+                           "l2": "inputs larger than L2: 9 work lists (%.0f MB) + 23-slot DPB (%.0f MB) cycled" % (sum(b.nbytes for b in blobs) / 1e6, FP.N_SLOTS * slot_bytes / 1e6)},
+                "mpixels_per_s": fps * wl["width"] * wl["height"] / 1e6,
+                "gpu_launches": int(launches), "clocks": clocks,
+                "e2e": {"value": e2e_fps, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h), "steps": e2e_steps,
+                        "mpixels_per_s": e2e_fps * wl["width"] * wl["height"] / 1e6},
+                "roofline": roofline, "cpu_baseline": cpu,
+                "nccl_bcast_bytes_per_step": int(slot_bytes) if world > 1 else 0}
+        print(json.dumps(line))
+    eng.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -66,6 +66,9 @@ void  b200_host_free(void *p);
 int b200_frame_upload(B200Ctx *ctx, const void *blob, uint64_t nbytes, int arena);
 /* Run K1..K5 for the blob resident in `arena`: reconstructs the picture into DPB slot hdr.cur_slot. */
 int b200_frame_execute(B200Ctx *ctx, int arena);
+/* Same, with the DPB placement overridden: cur_slot < 0 / ref_slots == NULL keep the header's values.  Lets a
+ * resident work list be replayed against a rotating DPB (GOP-periodic streams, frame-parallel multi-GPU). */
+int b200_frame_execute_ex(B200Ctx *ctx, int arena, int cur_slot, const uint8_t *ref_slots, int n_ref);
 /* upload + execute, arenas used round-robin: the call the recorder's frame_end makes (hevc.c:3446). */
 int b200_frame_submit(B200Ctx *ctx, const void *blob, uint64_t nbytes);
 
@@ -88,6 +91,9 @@ uint64_t b200_launch_count(const B200Ctx *ctx);            /* kernels launched b
 int  b200_rec_create(const B200Config *cfg, B200Rec **out);
 void b200_rec_destroy(B200Rec *r);
 int  b200_rec_begin(B200Rec *r, int cur_slot, int poc);                   /* hevc_frame_start, hevc.c:3197 */
+/* the picture's reference table: DPB slot of every frame the RefPicLists can address (hevc_refs.c ff_hevc_slice_rpl);
+ * B200McRec.ref0/ref1 passed to b200_rec_mc() index it */
+int  b200_rec_set_refs(B200Rec *r, const uint8_t *slots, int n);
 /* transform_add[log2-2](dst, coeffs, stride) preceded by kind/flags recorded from idct*/
 int  b200_rec_tu(B200Rec *r, int plane, int x, int y, int log2, int kind, int flags, int col_limit,
                  const int16_t *coeffs, int intra_linked);

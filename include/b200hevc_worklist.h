@@ -55,7 +55,11 @@ typedef struct B200BlobHeader {
     uint8_t  cur_slot;           /* DPB slot that receives this picture                        */
     uint32_t flags;              /* B200_FRAME_*                                               */
     B200Section sec[B200_SEC_COUNT];
-    uint32_t reserved[64 - 7 - 2 * B200_SEC_COUNT];
+    uint8_t  ref_slot[16];       /* DPB slot of each entry of the picture's reference table (from the RPS /
+                                    RefPicList, hevc_refs.c); B200McRec.ref0/ref1 index this table            */
+    uint8_t  n_ref;
+    uint8_t  pad[3];
+    uint32_t reserved[64 - 12 - 2 * B200_SEC_COUNT];
 } B200BlobHeader;               /* 256 bytes */
 
 #define B200_FRAME_HAS_DEBLOCK 1u
@@ -119,7 +123,7 @@ typedef struct B200McRec {       /* 32 bytes */
     uint8_t  flags;              /* B200_MCF_* */
     int16_t  sx0, sy0;           /* integer source position in ref0's plane (may lie outside: samples clamp, videodsp_template.c:26-100) */
     int16_t  sx1, sy1;
-    uint8_t  ref0, ref1;         /* DPB slots */
+    uint8_t  ref0, ref1;         /* indices into B200BlobHeader.ref_slot[] */
     uint8_t  frac0, frac1;       /* mx | my << 4 */
     int16_t  w0, w1;             /* weights  (hevc.c:1677-1683, 1763-1773) */
     int16_t  o0, o1;             /* offsets, un-scaled as passed to the *_w table functions */

@@ -15,9 +15,9 @@ class B200Config(C.Structure):
 
 EXPORTS = [  # every symbol include/b200hevc.h declares
     "b200_ctx_create", "b200_ctx_destroy", "b200_last_error", "b200_dpb_bytes", "b200_slot_bytes", "b200_slot_devptr",
-    "b200_stream", "b200_host_alloc", "b200_host_free", "b200_frame_upload", "b200_frame_execute", "b200_frame_submit",
+    "b200_stream", "b200_host_alloc", "b200_host_free", "b200_frame_upload", "b200_frame_execute", "b200_frame_execute_ex", "b200_frame_submit",
     "b200_slot_upload", "b200_slot_readback", "b200_slot_fill", "b200_sync", "b200_set_profiling", "b200_get_stage_ms",
-    "b200_launch_count", "b200_rec_create", "b200_rec_destroy", "b200_rec_begin", "b200_rec_tu", "b200_rec_pcm",
+    "b200_launch_count", "b200_rec_create", "b200_rec_destroy", "b200_rec_begin", "b200_rec_set_refs", "b200_rec_tu", "b200_rec_pcm",
     "b200_rec_intra", "b200_rec_mc", "b200_rec_deblock", "b200_rec_sao", "b200_rec_finish",
 ]
 
@@ -40,6 +40,7 @@ def load():
         "b200_host_free": (None, [vp]),
         "b200_frame_upload": (i32, [vp, vp, u64, i32]),
         "b200_frame_execute": (i32, [vp, i32]),
+        "b200_frame_execute_ex": (i32, [vp, i32, i32, C.c_char_p, i32]),
         "b200_frame_submit": (i32, [vp, vp, u64]),
         "b200_slot_upload": (i32, [vp, i32, C.POINTER(vp), C.POINTER(i64)]),
         "b200_slot_readback": (i32, [vp, i32, C.POINTER(vp), C.POINTER(i64)]),
@@ -51,6 +52,7 @@ def load():
         "b200_rec_create": (i32, [C.POINTER(B200Config), C.POINTER(vp)]),
         "b200_rec_destroy": (None, [vp]),
         "b200_rec_begin": (i32, [vp, i32, i32]),
+        "b200_rec_set_refs": (i32, [vp, C.c_char_p, i32]),
         "b200_rec_tu": (i32, [vp, i32, i32, i32, i32, i32, i32, i32, vp, i32]),
         "b200_rec_pcm": (i32, [vp, i32, i32, i32, i32, vp]),
         "b200_rec_intra": (i32, [vp, i32, i32, i32, i32, i32, i32, i32, i32]),

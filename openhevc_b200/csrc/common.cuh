@@ -12,6 +12,9 @@ struct PlaneDesc {
 struct FrameDesc {
     PlaneDesc p[3];
 };
+struct RefTable {
+    uint8_t slot[16];   // B200BlobHeader.ref_slot (possibly overridden at execute time)
+};
 
 __device__ __forceinline__ int clip3i(int v, int lo, int hi) { return min(max(v, lo), hi); }
 __device__ __forceinline__ int clip16i(int v) { return min(max(v, -32768), 32767); }
@@ -23,8 +26,8 @@ __device__ __forceinline__ PIX *px_ptr(const PlaneDesc &p, int x, int y)
 }
 
 // launchers (kernels.cu) -- all asynchronous on `st`; return number of kernels launched
-int launch_mc(cudaStream_t st, const B200McRec *recs, int count, const FrameDesc &cur, const FrameDesc *dpb_dev, int bd);
-int launch_residual(cudaStream_t st, const B200TuRec *const recs[4], const int counts[4], int16_t *pool, const FrameDesc &cur, int bd);
+int launch_mc(cudaStream_t st, const B200McRec *recs, int count, const FrameDesc &cur, const FrameDesc *dpb_dev, const RefTable &rt, int bd);
+int launch_residual(cudaStream_t st, const B200TuRec *const recs[4], const int counts[4], const int16_t *pool, int16_t *parked, const FrameDesc &cur, int bd);
 int launch_intra(cudaStream_t st, const B200IntraRec *recs, int count, const int16_t *pool, const FrameDesc &cur, int bd,
                  uint32_t *flags[3], const int flag_stride[3], uint32_t *counter);
 int launch_deblock(cudaStream_t st, const uint16_t *grid, const B200DbkLayout &L, const FrameDesc &cur, int bd);

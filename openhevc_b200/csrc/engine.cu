@@ -15,7 +15,7 @@
 #include "common.cuh"
 
 #define MAX_SLOTS 64
-#define MAX_ARENAS 8
+#define MAX_ARENAS 16
 
 struct Arena {
     uint8_t *dev = nullptr;
@@ -37,6 +37,7 @@ struct B200Ctx {
     uint32_t *flags[3] = { nullptr, nullptr, nullptr };
     int flag_stride[3];
     uint32_t *counter = nullptr;
+    int16_t *parked = nullptr;       // residuals of intra TUs (K2 -> K3), indexed like the coefficient pool
     Arena arena[MAX_ARENAS];
     uint64_t arena_bytes = 0;
     int next_arena = 0;
@@ -146,6 +147,7 @@ extern "C" void b200_ctx_destroy(B200Ctx *ctx)
     if (ctx->dpb_desc_dev) cudaFree(ctx->dpb_desc_dev);
     for (int p = 0; p < 3; p++) if (ctx->flags[p]) cudaFree(ctx->flags[p]);
     if (ctx->counter) cudaFree(ctx->counter);
+    if (ctx->parked) cudaFree(ctx->parked);
     if (ctx->st_copy) cudaStreamDestroy(ctx->st_copy);
     if (ctx->st_compute) cudaStreamDestroy(ctx->st_compute);
     if (ctx->st_down) cudaStreamDestroy(ctx->st_down);
@@ -191,6 +193,7 @@ static int ctx_init(B200Ctx *ctx)
     CU(cudaMemset(ctx->counter, 0, 256));
     ctx->arena_bytes = c.max_blob_bytes ? c.max_blob_bytes : worst_blob_bytes(&c);
     ctx->arena_bytes = (ctx->arena_bytes + 4095) & ~(uint64_t)4095;
+    CU(cudaMalloc(&ctx->parked, ctx->arena_bytes));
     CU(cudaStreamCreateWithFlags(&ctx->st_copy, cudaStreamNonBlocking));
     CU(cudaStreamCreateWithFlags(&ctx->st_compute, cudaStreamNonBlocking));
     CU(cudaStreamCreateWithFlags(&ctx->st_down, cudaStreamNonBlocking));
@@ -284,7 +287,7 @@ static int deep_check(B200Ctx *ctx, const uint8_t *blob)
         const B200McRec &m = mc[i];
         const int maxf = (m.flags & B200_MCF_CHROMA) ? 7 : 3;
         if (m.plane > 2 || !m.w || !m.h || m.w > 32 || m.w * m.h > 256 || m.x + m.w > ctx->pw[m.plane] || m.y + m.h > ctx->ph[m.plane] ||
-            m.ref0 >= ctx->cfg.n_slots || ((m.flags & B200_MCF_BI) && m.ref1 >= ctx->cfg.n_slots) ||
+            m.ref0 >= h->n_ref || ((m.flags & B200_MCF_BI) && m.ref1 >= h->n_ref) ||
             (m.frac0 & 15) > maxf || (m.frac0 >> 4) > maxf || (m.frac1 & 15) > maxf || (m.frac1 >> 4) > maxf || m.denom > 7 ||
             ((m.w > 16) ? m.h > 8 : m.h > 16))
             return fail(ctx, B200_EINVAL, "MC record %u invalid", i);
@@ -321,14 +324,32 @@ extern "C" int b200_frame_upload(B200Ctx *ctx, const void *blob, uint64_t nbytes
     return 0;
 }
 
-extern "C" int b200_frame_execute(B200Ctx *ctx, int arena)
+extern "C" int b200_frame_execute(B200Ctx *ctx, int arena) { return b200_frame_execute_ex(ctx, arena, -1, nullptr, 0); }
+
+extern "C" int b200_frame_execute_ex(B200Ctx *ctx, int arena, int cur_slot, const uint8_t *ref_slots, int n_ref)
 {
     if (!ctx || arena < 0 || arena >= ctx->cfg.n_arenas) return B200_EINVAL;
     if (ctx->err_code) return ctx->err_code;
     Arena &a = ctx->arena[arena];
     if (!a.resident) return fail(ctx, B200_ESTATE, "arena %d holds no blob", arena);
     CU(cudaSetDevice(ctx->cfg.device));
-    const B200BlobHeader &h = a.hdr;
+    B200BlobHeader h = a.hdr;
+    if (cur_slot >= 0) {                       // same work list, different DPB placement (GOP-periodic streams)
+        if (cur_slot >= ctx->cfg.n_slots) return fail(ctx, B200_EINVAL, "cur_slot override %d out of range", cur_slot);
+        h.cur_slot = (uint8_t)cur_slot;
+    }
+    if (ref_slots) {
+        if (n_ref < 0 || n_ref > 16) return fail(ctx, B200_EINVAL, "n_ref %d", n_ref);
+        h.n_ref = (uint8_t)n_ref;
+        memcpy(h.ref_slot, ref_slots, (size_t)n_ref);
+    }
+    RefTable rt;
+    memset(&rt, 0, sizeof(rt));
+    for (int i = 0; i < h.n_ref && i < 16; i++) {
+        if (h.ref_slot[i] >= ctx->cfg.n_slots) return fail(ctx, B200_EINVAL, "reference table entry %d -> slot %d out of range", i, h.ref_slot[i]);
+        rt.slot[i] = h.ref_slot[i];
+    }
+    if (h.sec[B200_SEC_MC].count && !h.n_ref) return fail(ctx, B200_EINVAL, "inter records without a reference table");
     cudaStream_t st = ctx->st_compute;
     const int bd = ctx->cfg.bit_depth;
     const bool has_sao = h.sec[B200_SEC_SAO].count != 0;
@@ -338,16 +359,16 @@ extern "C" int b200_frame_execute(B200Ctx *ctx, int arena)
     CU(cudaStreamWaitEvent(st, a.ev_uploaded, 0));
     if (pf) CU(cudaEventRecord(ctx->prof[0], st));
     // K1 inter
-    ctx->launches += launch_mc(st, (const B200McRec *)(a.dev + h.sec[B200_SEC_MC].off), (int)h.sec[B200_SEC_MC].count, cur, ctx->dpb_desc_dev, bd);
+    ctx->launches += launch_mc(st, (const B200McRec *)(a.dev + h.sec[B200_SEC_MC].off), (int)h.sec[B200_SEC_MC].count, cur, ctx->dpb_desc_dev, rt, bd);
     if (pf) CU(cudaEventRecord(ctx->prof[1], st));
     // K2 residual
-    int16_t *pool = (int16_t *)(a.dev + h.sec[B200_SEC_COEFF].off);
+    const int16_t *pool = (const int16_t *)(a.dev + h.sec[B200_SEC_COEFF].off);
     const B200TuRec *tu[4]; int ntu[4];
     for (int s = 0; s < 4; s++) { tu[s] = (const B200TuRec *)(a.dev + h.sec[B200_SEC_TU4 + s].off); ntu[s] = (int)h.sec[B200_SEC_TU4 + s].count; }
-    ctx->launches += launch_residual(st, tu, ntu, pool, cur, bd);
+    ctx->launches += launch_residual(st, tu, ntu, pool, ctx->parked, cur, bd);
     if (pf) CU(cudaEventRecord(ctx->prof[2], st));
     // K3 intra
-    ctx->launches += launch_intra(st, (const B200IntraRec *)(a.dev + h.sec[B200_SEC_INTRA].off), (int)h.sec[B200_SEC_INTRA].count, pool, cur, bd,
+    ctx->launches += launch_intra(st, (const B200IntraRec *)(a.dev + h.sec[B200_SEC_INTRA].off), (int)h.sec[B200_SEC_INTRA].count, ctx->parked, cur, bd,
                                   ctx->flags, ctx->flag_stride, ctx->counter);
     if (pf) CU(cudaEventRecord(ctx->prof[3], st));
     // K4 deblock

@@ -91,7 +91,8 @@ template <int N> __device__ __forceinline__ void dst4_1d(const int (&v)[N], int 
 }
 
 template <typename PIX, int N>
-__global__ void __launch_bounds__(128) k_residual(const B200TuRec *__restrict__ recs, int count, int16_t *pool, FrameDesc f, int bd)
+__global__ void __launch_bounds__(128) k_residual(const B200TuRec *__restrict__ recs, int count, const int16_t *__restrict__ pool,
+                                                  int16_t *__restrict__ parked, FrameDesc f, int bd)
 {
     constexpr int G = 32 / N;            // TUs per warp
     constexpr int TS = N * (N + 1);      // padded tile
@@ -110,7 +111,7 @@ __global__ void __launch_bounds__(128) k_residual(const B200TuRec *__restrict__ 
         memset(&rec, 0, 16);
         rec.kind = B200_TU_BYPASS;
     }
-    int16_t *c = pool + rec.coeff_off;
+    const int16_t *c = pool + rec.coeff_off;
     const int kind = rec.kind;
     int v[N], t[N];
     if (active) {
@@ -187,8 +188,9 @@ __global__ void __launch_bounds__(128) k_residual(const B200TuRec *__restrict__ 
     if (!active) return;
     // ---- output: rows of N consecutive samples per TU ----
     if (rec.flags & B200_TUF_PARK) {
+        int16_t *pk = parked + rec.coeff_off;      // the blob stays read-only: parked residuals live in their own pool
 #pragma unroll
-        for (int y = 0; y < N; y++) c[y * N + col] = (int16_t)tile[y * (N + 1) + col];
+        for (int y = 0; y < N; y++) pk[y * N + col] = (int16_t)tile[y * (N + 1) + col];
     } else {
         const PlaneDesc pd = f.p[rec.plane];
         const int maxv = (1 << bd) - 1;
@@ -267,7 +269,7 @@ __device__ __forceinline__ void mc_list(const PlaneDesc &rp, int sx, int sy, int
 }
 
 template <typename PIX>
-__global__ void __launch_bounds__(256) k_mc(const B200McRec *__restrict__ recs, int count, FrameDesc cur, const FrameDesc *__restrict__ dpb, int bd)
+__global__ void __launch_bounds__(256) k_mc(const B200McRec *__restrict__ recs, int count, FrameDesc cur, const FrameDesc *__restrict__ dpb, RefTable rt, int bd)
 {
     __shared__ uint16_t win_s[8][MC_WIN_MAX];
     __shared__ int16_t tmp_s[8][MC_TMP_MAX];
@@ -285,12 +287,12 @@ __global__ void __launch_bounds__(256) k_mc(const B200McRec *__restrict__ recs, 
     const bool chroma = m.flags & B200_MCF_CHROMA, bi = m.flags & B200_MCF_BI, weighted = m.flags & B200_MCF_WEIGHTED;
     int v0[8], v1[8];
     {
-        const PlaneDesc rp = dpb[m.ref0].p[plane];
+        const PlaneDesc rp = dpb[rt.slot[m.ref0 & 15]].p[plane];
         if (chroma) mc_list<PIX, 4>(rp, m.sx0, m.sy0, m.frac0 & 15, m.frac0 >> 4, w, h, bd, lane, win_s[warp], tmp_s[warp], v0);
         else        mc_list<PIX, 8>(rp, m.sx0, m.sy0, m.frac0 & 15, m.frac0 >> 4, w, h, bd, lane, win_s[warp], tmp_s[warp], v0);
     }
     if (bi) {
-        const PlaneDesc rp = dpb[m.ref1].p[plane];
+        const PlaneDesc rp = dpb[rt.slot[m.ref1 & 15]].p[plane];
         if (chroma) mc_list<PIX, 4>(rp, m.sx1, m.sy1, m.frac1 & 15, m.frac1 >> 4, w, h, bd, lane, win_s[warp], tmp_s[warp], v1);
         else        mc_list<PIX, 8>(rp, m.sx1, m.sy1, m.frac1 & 15, m.frac1 >> 4, w, h, bd, lane, win_s[warp], tmp_s[warp], v1);
     }
@@ -728,28 +730,28 @@ __global__ void k_fill(FrameDesc f, int value)
 // --------------------------------------------------------------------------------------------
 // launchers
 // --------------------------------------------------------------------------------------------
-int launch_mc(cudaStream_t st, const B200McRec *recs, int count, const FrameDesc &cur, const FrameDesc *dpb_dev, int bd)
+int launch_mc(cudaStream_t st, const B200McRec *recs, int count, const FrameDesc &cur, const FrameDesc *dpb_dev, const RefTable &rt, int bd)
 {
     if (!count) return 0;
     const int grid = (count + 7) / 8;
-    if (bd > 8) k_mc<uint16_t><<<grid, 256, 0, st>>>(recs, count, cur, dpb_dev, bd);
-    else        k_mc<uint8_t><<<grid, 256, 0, st>>>(recs, count, cur, dpb_dev, bd);
+    if (bd > 8) k_mc<uint16_t><<<grid, 256, 0, st>>>(recs, count, cur, dpb_dev, rt, bd);
+    else        k_mc<uint8_t><<<grid, 256, 0, st>>>(recs, count, cur, dpb_dev, rt, bd);
     return 1;
 }
 
 template <typename PIX>
-static int launch_residual_t(cudaStream_t st, const B200TuRec *const recs[4], const int counts[4], int16_t *pool, const FrameDesc &cur, int bd)
+static int launch_residual_t(cudaStream_t st, const B200TuRec *const recs[4], const int counts[4], const int16_t *pool, int16_t *parked, const FrameDesc &cur, int bd)
 {
     int n = 0;
-    if (counts[0]) { k_residual<PIX, 4><<<(counts[0] + 31) / 32, 128, 0, st>>>(recs[0], counts[0], pool, cur, bd); n++; }
-    if (counts[1]) { k_residual<PIX, 8><<<(counts[1] + 15) / 16, 128, 0, st>>>(recs[1], counts[1], pool, cur, bd); n++; }
-    if (counts[2]) { k_residual<PIX, 16><<<(counts[2] + 7) / 8, 128, 0, st>>>(recs[2], counts[2], pool, cur, bd); n++; }
-    if (counts[3]) { k_residual<PIX, 32><<<(counts[3] + 3) / 4, 128, 0, st>>>(recs[3], counts[3], pool, cur, bd); n++; }
+    if (counts[0]) { k_residual<PIX, 4><<<(counts[0] + 31) / 32, 128, 0, st>>>(recs[0], counts[0], pool, parked, cur, bd); n++; }
+    if (counts[1]) { k_residual<PIX, 8><<<(counts[1] + 15) / 16, 128, 0, st>>>(recs[1], counts[1], pool, parked, cur, bd); n++; }
+    if (counts[2]) { k_residual<PIX, 16><<<(counts[2] + 7) / 8, 128, 0, st>>>(recs[2], counts[2], pool, parked, cur, bd); n++; }
+    if (counts[3]) { k_residual<PIX, 32><<<(counts[3] + 3) / 4, 128, 0, st>>>(recs[3], counts[3], pool, parked, cur, bd); n++; }
     return n;
 }
-int launch_residual(cudaStream_t st, const B200TuRec *const recs[4], const int counts[4], int16_t *pool, const FrameDesc &cur, int bd)
+int launch_residual(cudaStream_t st, const B200TuRec *const recs[4], const int counts[4], const int16_t *pool, int16_t *parked, const FrameDesc &cur, int bd)
 {
-    return bd > 8 ? launch_residual_t<uint16_t>(st, recs, counts, pool, cur, bd) : launch_residual_t<uint8_t>(st, recs, counts, pool, cur, bd);
+    return bd > 8 ? launch_residual_t<uint16_t>(st, recs, counts, pool, parked, cur, bd) : launch_residual_t<uint8_t>(st, recs, counts, pool, parked, cur, bd);
 }
 
 int launch_intra(cudaStream_t st, const B200IntraRec *recs, int count, const int16_t *pool, const FrameDesc &cur, int bd,

@@ -24,8 +24,18 @@ struct B200Rec {
     int last_intra[3];
     bool any_dbk = false, any_sao = false, open = false;
     int cur_slot = 0, poc = 0;
+    uint8_t ref_slot[16];
+    int n_ref = 0;
     uint64_t nbytes = 0;
 };
+
+extern "C" int b200_rec_set_refs(B200Rec *r, const uint8_t *slots, int n)
+{
+    if (!r || !r->open || n < 0 || n > 16 || (n && !slots)) return B200_EINVAL;
+    r->n_ref = n;
+    if (n) memcpy(r->ref_slot, slots, (size_t)n);
+    return 0;
+}
 
 static uint64_t rec_capacity(const B200Config *c, const B200DbkLayout &L, int nctb)
 {
@@ -76,7 +86,7 @@ extern "C" int b200_rec_begin(B200Rec *r, int cur_slot, int poc)
     r->intra.clear(); r->mc.clear();
     r->ncoef = 0; r->any_dbk = r->any_sao = false;
     r->last_intra[0] = r->last_intra[1] = r->last_intra[2] = -1;
-    r->cur_slot = cur_slot; r->poc = poc; r->open = true; r->nbytes = 0;
+    r->cur_slot = cur_slot; r->poc = poc; r->open = true; r->nbytes = 0; r->n_ref = 0;
     return 0;
 }
 
@@ -204,6 +214,8 @@ extern "C" int b200_rec_finish(B200Rec *r, const void **blob, uint64_t *nbytes)
     h->chroma_format_idc = (uint8_t)r->cfg.chroma_format_idc; h->bit_depth = (uint8_t)r->cfg.bit_depth;
     h->log2_ctb_size = (uint8_t)r->cfg.log2_ctb_size; h->cur_slot = (uint8_t)r->cur_slot;
     h->flags = (r->any_dbk ? B200_FRAME_HAS_DEBLOCK : 0) | (r->any_sao ? B200_FRAME_HAS_SAO : 0);
+    h->n_ref = (uint8_t)r->n_ref;
+    memcpy(h->ref_slot, r->ref_slot, (size_t)r->n_ref);
     h->sec[B200_SEC_DBK].off = r->off_dbk; h->sec[B200_SEC_DBK].count = r->any_dbk ? r->dbk.total : 0;
     h->sec[B200_SEC_SAO].off = r->off_sao; h->sec[B200_SEC_SAO].count = r->any_sao ? (uint32_t)(3 * r->ctb_w * r->ctb_h) : 0;
     h->sec[B200_SEC_COEFF].off = r->off_pool; h->sec[B200_SEC_COEFF].count = (r->ncoef + 7) & ~7u;

@@ -109,8 +109,12 @@ class FrameEngine:
     def upload(self, blob, arena):
         self._chk(self.lib.b200_frame_upload(self.h, blob.ctypes.data, blob.nbytes, arena))
 
-    def execute(self, arena):
-        self._chk(self.lib.b200_frame_execute(self.h, arena))
+    def execute(self, arena, cur_slot=-1, ref_slots=None):
+        if cur_slot < 0 and ref_slots is None:
+            self._chk(self.lib.b200_frame_execute(self.h, arena))
+        else:
+            rs = bytes(ref_slots) if ref_slots is not None else None
+            self._chk(self.lib.b200_frame_execute_ex(self.h, arena, cur_slot, rs, len(rs) if rs is not None else 0))
 
     def readback(self, slot, out=None, sync=True):
         out = out if out is not None else self.new_host_frame()

@@ -190,7 +190,7 @@ class FrameSynth:
     def _pu(self, x, y, w, h):
         r = self.rng
         bi = r.random() < self.bi_frac and len(self.refs) > 0 and (w + h) != 12
-        refs = [int(r.choice(self.refs)), int(r.choice(self.refs))]
+        refs = [int(r.integers(0, len(self.refs))), int(r.integers(0, len(self.refs)))]     # indices into the reference table
         mvs = [(int(r.integers(-4 * self.max_mv, 4 * self.max_mv + 1)), int(r.integers(-4 * self.max_mv, 4 * self.max_mv + 1))) for _ in range(2)]
         if r.random() < 0.1:
             mvs[0] = (mvs[0][0] & ~3, mvs[0][1] & ~3)            # full-pel
@@ -215,8 +215,8 @@ class FrameSynth:
                     mx, my = mvx & ((1 << (2 + hs)) - 1), mvy & ((1 << (2 + vs)) - 1)
                     fx, fy = mx << (1 - hs), my << (1 - vs)
                     ix, iy = mvx >> (2 + hs), mvy >> (2 + vs)
-                sx = int(np.clip((x >> hs) + ix, -80, pw_ + 16))      # beyond that every sample clamps to the same border
-                sy = int(np.clip((y >> vs) + iy, -80, ph_ + 16))
+                sx = min(max((x >> hs) + ix, -80), pw_ + 16)        # beyond that every sample clamps to the same border
+                sy = min(max((y >> vs) + iy, -80), ph_ + 16)
                 rec["sx%d" % l], rec["sy%d" % l], rec["frac%d" % l] = sx, sy, fx | (fy << 4)
                 wt = wts[l] if plane == 0 else cwts[l]
                 rec["w%d" % l], rec["o%d" % l] = wt
@@ -232,7 +232,7 @@ class FrameSynth:
         r = self.rng
         n = 1 << log2
         intra = not self.refs or r.random() < self.p_intra
-        qp = int(np.clip(self.qp + r.integers(-4, 5), 0, 51))
+        qp = min(max(self.qp + int(r.integers(-4, 5)), 0), 51)
         self.qp_map[y >> 3:(y + n) >> 3, x >> 3:(x + n) >> 3] = qp
         self._mark_edges(x, y, n, n, 2 if intra else 1)
         if intra:
@@ -397,13 +397,14 @@ class FrameSynth:
             assert (ro != -2).all()
             intra["resid_off"] = np.where(ro < 0, W.NO_RESID, ro).astype(np.uint32)
         mc = np.zeros(len(self.mc), W.mc_dt)
-        for k, rec in enumerate(self.mc):
-            for name, v in rec.items():
-                mc[k][name] = v
+        if self.mc:
+            for name in self.mc[0]:
+                mc[name] = [rec[name] for rec in self.mc]
         mc = W.split_mc_tiles(mc)
         dbk = self._deblock_grid() if self.deblock else None
         sao = self._sao_grid() if self.sao else None
-        blob = W.build_blob(self.W, self.H, self.cfi, self.bd, self.log2_ctb, self.cur_slot, self.poc, pool, tu, intra, mc, dbk, sao, out=out)
+        blob = W.build_blob(self.W, self.H, self.cfi, self.bd, self.log2_ctb, self.cur_slot, self.poc, pool, tu, intra, mc, dbk, sao, out=out,
+                            ref_slots=self.refs)
         B = 2 if self.bd > 8 else 1
         S = sum(np.prod(W.plane_dims(self.W, self.H, self.cfi, p)) for p in range(3))
         st = self.stats

@@ -22,7 +22,8 @@ header_dt = np.dtype([
     ("magic", "<u4"), ("version", "<u4"), ("total_bytes", "<u4"), ("poc", "<i4"),
     ("width", "<u2"), ("height", "<u2"), ("chroma_format_idc", "u1"), ("bit_depth", "u1"),
     ("log2_ctb_size", "u1"), ("cur_slot", "u1"), ("flags", "<u4"),
-    ("sec", section_dt, (SEC_COUNT,)), ("reserved", "<u4", (64 - 7 - 2 * SEC_COUNT,)),
+    ("sec", section_dt, (SEC_COUNT,)), ("ref_slot", "u1", (16,)), ("n_ref", "u1"), ("pad", "u1", (3,)),
+    ("reserved", "<u4", (64 - 12 - 2 * SEC_COUNT,)),
 ])
 tu_dt = np.dtype([("x", "<u2"), ("y", "<u2"), ("plane", "u1"), ("log2", "u1"), ("kind", "u1"), ("flags", "u1"),
                   ("col_limit", "u1"), ("pad", "u1", (3,)), ("coeff_off", "<u4")])
@@ -69,25 +70,30 @@ class DbkLayout:
 
 
 def split_mc_tiles(recs):
-    """Same tiling as b200_rec_mc(): every block becomes tiles of <= 32x8 or <= 16x16 samples."""
+    """Same tiling as b200_rec_mc(): every block becomes tiles of <= 32x8 or <= 16x16 samples (vectorised per block shape)."""
+    if len(recs) == 0:
+        return np.zeros(0, mc_dt)
     out = []
-    for b in recs:
-        w, h = int(b["w"]), int(b["h"])
-        tx = 0
+    shapes = np.unique(np.stack([recs["w"], recs["h"]], 1), axis=0)
+    for w, h in shapes:
+        w, h = int(w), int(h)
+        sel = recs[(recs["w"] == w) & (recs["h"] == h)]
+        tiles, tx = [], 0
         while tx < w:
             tw = min(32, w - tx)
             maxh = 8 if tw > 16 else 16
-            for ty in range(0, h, maxh):
-                t = b.copy()
-                t["x"] += tx; t["y"] += ty; t["w"] = tw; t["h"] = min(maxh, h - ty)
-                t["sx0"] += tx; t["sy0"] += ty; t["sx1"] += tx; t["sy1"] += ty
-                out.append(t)
+            tiles += [(tx, ty, tw, min(maxh, h - ty)) for ty in range(0, h, maxh)]
             tx += tw
-    return np.array(out, dtype=mc_dt) if out else np.zeros(0, mc_dt)
+        for (tx, ty, tw, th) in tiles:
+            t = sel.copy()
+            t["x"] += tx; t["y"] += ty; t["w"] = tw; t["h"] = th
+            t["sx0"] += tx; t["sy0"] += ty; t["sx1"] += tx; t["sy1"] += ty
+            out.append(t)
+    return np.concatenate(out)
 
 
 def build_blob(width, height, cfi, bit_depth, log2_ctb, cur_slot, poc=0, coeff=None, tu=None, intra=None, mc=None,
-               dbk=None, sao=None, out=None):
+               dbk=None, sao=None, out=None, ref_slots=()):
     """Assemble a blob.  tu: dict {2,3,4,5 -> tu_dt array}; dbk: uint16 array (DbkLayout.total) or None;
     sao: sao_dt array [3*ctb_count] or None.  `out`: optional uint8 buffer (e.g. pinned) to build into."""
     coeff = np.zeros(0, np.int16) if coeff is None else np.ascontiguousarray(coeff, np.int16)
@@ -104,6 +110,9 @@ def build_blob(width, height, cfi, bit_depth, log2_ctb, cur_slot, poc=0, coeff=N
     hdr["magic"], hdr["version"], hdr["poc"] = MAGIC, VERSION, poc
     hdr["width"], hdr["height"], hdr["chroma_format_idc"], hdr["bit_depth"] = width, height, cfi, bit_depth
     hdr["log2_ctb_size"], hdr["cur_slot"] = log2_ctb, cur_slot
+    assert len(ref_slots) <= 16
+    hdr["n_ref"] = len(ref_slots)
+    hdr["ref_slot"][0][:len(ref_slots)] = list(ref_slots)
     hdr["flags"] = (FRAME_HAS_DEBLOCK if len(parts[SEC_DBK]) else 0) | (FRAME_HAS_SAO if len(parts[SEC_SAO]) else 0)
     off = 256
     for s, p in enumerate(parts):

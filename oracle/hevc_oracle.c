@@ -523,9 +523,10 @@ int orc_execute_blob(const uint8_t *blob, uint16_t **planes, int n_slots)
     const B200McRec *mc = (const B200McRec *)(blob + h->sec[B200_SEC_MC].off);
     for (uint32_t i = 0; i < h->sec[B200_SEC_MC].count; i++) {
         const B200McRec *m = &mc[i];
-        if (m->ref0 >= n_slots || ((m->flags & B200_MCF_BI) && m->ref1 >= n_slots)) { free(pool); return -4; }
+        const int i0 = m->ref0, i1 = (m->flags & B200_MCF_BI) ? m->ref1 : m->ref0;
+        if (i0 >= h->n_ref || i1 >= h->n_ref || h->ref_slot[i0] >= n_slots || h->ref_slot[i1] >= n_slots) { free(pool); return -4; }
         const int p = m->plane;
-        orc_mc_rec(m, cur[p], pw[p], planes[3 * m->ref0 + p], planes[3 * ((m->flags & B200_MCF_BI) ? m->ref1 : m->ref0) + p], pw[p], ph[p], bd);
+        orc_mc_rec(m, cur[p], pw[p], planes[3 * h->ref_slot[i0] + p], planes[3 * h->ref_slot[i1] + p], pw[p], ph[p], bd);
     }
     /* K2 residual */
     for (int s = B200_SEC_TU4; s <= B200_SEC_TU32; s++) {

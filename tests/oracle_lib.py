@@ -44,6 +44,56 @@ def execute(blob, dpb):
     return planes16[cur]
 
 
+REPLAY_SO = os.path.join(ORACLE_DIR, "_ref", "libreplay_ref.so")
+_ref = None
+
+
+def ref_lib():
+    """the UNMODIFIED reference's tables driven by oracle/replay_ref.c (prebuilt into oracle/_ref/)"""
+    global _ref
+    if _ref is None:
+        if not os.path.exists(REPLAY_SO):
+            build_oracle()
+        if not os.path.exists(REPLAY_SO):
+            return None
+        _ref = C.CDLL(REPLAY_SO)
+        _ref.ref_execute_blob.restype = C.c_int
+        _ref.ref_execute_blob.argtypes = [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_int64), C.c_int]
+        _ref.ref_bench.restype = C.c_double
+        _ref.ref_bench.argtypes = [C.POINTER(C.c_void_p), C.c_int, C.POINTER(C.c_void_p), C.POINTER(C.c_int64), C.c_int, C.c_int, C.c_int]
+    return _ref
+
+
+def _native(dpb, bit_depth):
+    dt = np.uint16 if bit_depth > 8 else np.uint8
+    planes = [[np.ascontiguousarray(p, dt).copy() for p in slot] for slot in dpb]
+    flat = [p for slot in planes for p in slot]
+    ptrs = (C.c_void_p * len(flat))(*[p.ctypes.data for p in flat])
+    strides = (C.c_int64 * len(flat))(*[p.strides[0] for p in flat])
+    return planes, ptrs, strides
+
+
+def ref_execute(blob, dpb):
+    """same contract as execute(), computed by the reference's own C functions"""
+    blob = np.ascontiguousarray(blob, np.uint8)
+    planes, ptrs, strides = _native(dpb, int(blob[21]))
+    rc = ref_lib().ref_execute_blob(blob.ctypes.data, ptrs, strides, len(dpb))
+    if rc:
+        raise RuntimeError(f"ref_execute_blob failed: {rc}")
+    return planes[int(blob[23])]
+
+
+def ref_bench(blobs, dpb, n_threads, iters):
+    """seconds of wall time for n_threads x iters pictures on the reference C path"""
+    blobs = [np.ascontiguousarray(b, np.uint8) for b in blobs]
+    planes, ptrs, strides = _native(dpb, int(blobs[0][21]))
+    bp = (C.c_void_p * len(blobs))(*[b.ctypes.data for b in blobs])
+    t = ref_lib().ref_bench(bp, len(blobs), ptrs, strides, len(dpb), n_threads, iters)
+    if t < 0:
+        raise RuntimeError(f"ref_bench failed: {t}")
+    return t
+
+
 def check_decode_order(blob):
     """host-side validation of a blob's intra list: every neighbour unit an intra TU reads must be final
     (not covered by a *later* intra TU).  A violation would make the device wavefront wait forever."""

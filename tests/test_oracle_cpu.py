@@ -47,6 +47,22 @@ def test_synth_is_in_decode_order_and_oracle_runs(cfi, bd, refs):
     assert all((a == b).all() for a, b in zip(out, out2))
 
 
+@pytest.mark.parametrize("cfi,bd,refs,kw", [(1, 8, [], {}), (1, 10, [1, 2], dict(weighted=True)), (2, 10, [1, 2], {}), (3, 8, [2], dict(sao_restore=True)), (1, 12, [1], {})])
+def test_oracle_equals_reference_at_picture_level(built, cfi, bd, refs, kw):
+    """whole synthetic pictures: restatement (oracle/hevc_oracle.c) == the reference's own table functions
+    driven by oracle/replay_ref.c -- MC incl. emulated edges, all transforms, intra_pred(), deblock, SAO."""
+    if oracle_lib.ref_lib() is None:
+        pytest.skip("oracle/_ref/libreplay_ref.so not available")
+    w, h = 320, 192
+    blob, st = FrameSynth(w, h, cfi=cfi, bit_depth=bd, seed=90 + cfi + bd, refs=refs, cur_slot=0, exotic=0.05, max_mv=100, **kw).generate()
+    dpb = [smooth_frame(w, h, cfi, bd, 200 + k) for k in range(3)]
+    a = oracle_lib.execute(blob, dpb)
+    b = oracle_lib.ref_execute(blob, dpb)
+    for p in range(3):
+        bad = np.argwhere(a[p] != b[p])
+        assert len(bad) == 0, f"plane {p}: {len(bad)} differ, first {tuple(bad[0])}"
+
+
 def test_oracle_properties_linearity_of_residual():
     """size-independent property: with prediction 0 and no clipping the IDCT stage is linear:
     recon(a) + recon(b) - recon(0) == recon(a + b) whenever intermediate clips do not trigger."""
@@ -99,6 +115,7 @@ def test_recorder_matches_numpy_builder(built):
     r = C.c_void_p()
     assert lib.b200_rec_create(C.byref(cfg), C.byref(r)) == 0
     assert lib.b200_rec_begin(r, 3, 0) == 0
+    assert lib.b200_rec_set_refs(r, bytes(hdr["ref_slot"][:int(hdr["n_ref"])]), int(hdr["n_ref"])) == 0
     pool = secs[W.SEC_COEFF]
     # replay in an order the decoder could have used: intra pred call immediately followed by its residual
     parked = {}
@@ -153,6 +170,7 @@ def test_recorder_matches_numpy_builder(built):
     bp, nb = C.c_void_p(), C.c_uint64()
     assert lib.b200_rec_finish(r, C.byref(bp), C.byref(nb)) == 0
     rblob = np.ctypeslib.as_array(C.cast(bp, C.POINTER(C.c_uint8)), shape=(nb.value,)).copy()
+
     lib.b200_rec_destroy(r)
     # same picture on the oracle from both blobs
     dpb = [smooth_frame(w, h, cfi, bd, 50 + k) for k in range(4)]

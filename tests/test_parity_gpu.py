@@ -105,13 +105,14 @@ def test_malformed_blobs_are_rejected_not_executed():
         eng.close()
 
 
-def test_out_of_order_intra_list_times_out_instead_of_hanging():
-    """a work list whose intra TUs are not in decode order must not hang the device"""
+def test_cyclic_intra_dependencies_time_out_instead_of_hanging():
+    """a work list whose intra TUs wait on each other (cannot come from a real decode order) must not hang the device"""
     w, h = 128, 64
-    blob, _ = FrameSynth(w, h, 1, 8, seed=6, cur_slot=0).generate()
-    hdr, secs = W.parse_blob(blob)
-    intra = secs[W.SEC_INTRA]
-    intra[:] = intra[::-1].copy()
+    intra = np.zeros(2, W.intra_dt)
+    # A at (0,8) claims its up-right block B=(8,0) is available, B claims its bottom-left block A is available
+    intra[0] = (0, 8, 0, 3, 1, W.INF_UP | W.INF_UP_RIGHT, 8, 0, (0, 0), W.NO_RESID)
+    intra[1] = (8, 0, 0, 3, 1, W.INF_LEFT | W.INF_BOTTOM_LEFT, 0, 8, (0, 0), W.NO_RESID)
+    blob = W.build_blob(w, h, 1, 8, 6, 0, intra=intra)
     eng = FrameEngine(w, h, 1, 8, n_slots=2)
     try:
         with pytest.raises(B200Error, match="decode order"):
