@@ -400,7 +400,7 @@ __global__ void __launch_bounds__(128) k_intra(const B200IntraRec *__restrict__ 
                 const uint32_t *p = flg + uy * fs + ux;
                 uint32_t spins = 0;
                 while (ld_acquire(p) == 0) {
-                    __nanosleep(64);
+                    __nanosleep(20);
                     if ((++spins & 1023) == 0 && (spins > (1u << 21) || ld_acquire(counter + 1))) { st_release(counter + 1, 1u); break; }
                 }
             }

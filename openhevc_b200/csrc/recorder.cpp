@@ -230,7 +230,24 @@ extern "C" int b200_rec_finish(B200Rec *r, const void **blob, uint64_t *nbytes)
         o = (o + r->tu[s].size() * 16 + 255) & ~(uint64_t)255;
     }
     h->sec[B200_SEC_INTRA].off = (uint32_t)o; h->sec[B200_SEC_INTRA].count = (uint32_t)r->intra.size();
-    if (!r->intra.empty()) memcpy(r->blob + o, r->intra.data(), r->intra.size() * 16);
+    if (!r->intra.empty()) {
+        // decode order -> CTB-wavefront order (key = ctb_x + 2*ctb_y, then ctb_y; stable inside a CTB): still a
+        // topological order of the intra dependencies (left, up, up-right CTBs have smaller keys), but the device's
+        // in-order window then covers whole anti-diagonals of CTBs.  Counting sort, O(n).
+        const int lc = r->cfg.log2_ctb_size, nkeys = (r->ctb_w + 2 * r->ctb_h) * r->ctb_h + 1;
+        std::vector<uint32_t> start(nkeys + 1, 0);
+        std::vector<uint32_t> key(r->intra.size());
+        for (size_t i = 0; i < r->intra.size(); i++) {
+            const B200IntraRec &ir = r->intra[i];
+            const int hs = ir.plane && r->cfg.chroma_format_idc != 3, vs = ir.plane && r->cfg.chroma_format_idc == 1;
+            const int cx = (ir.x << hs) >> lc, cy = (ir.y << vs) >> lc;
+            key[i] = (uint32_t)((cx + 2 * cy) * r->ctb_h + cy);
+            start[key[i] + 1]++;
+        }
+        for (int k = 0; k < nkeys; k++) start[k + 1] += start[k];
+        B200IntraRec *dst = (B200IntraRec *)(r->blob + o);
+        for (size_t i = 0; i < r->intra.size(); i++) dst[start[key[i]]++] = r->intra[i];
+    }
     o = (o + r->intra.size() * 16 + 255) & ~(uint64_t)255;
     h->sec[B200_SEC_MC].off = (uint32_t)o; h->sec[B200_SEC_MC].count = (uint32_t)r->mc.size();
     if (!r->mc.empty()) memcpy(r->blob + o, r->mc.data(), r->mc.size() * 32);

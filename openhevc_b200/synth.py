@@ -396,6 +396,7 @@ class FrameSynth:
             ro = a[:, 8]
             assert (ro != -2).all()
             intra["resid_off"] = np.where(ro < 0, W.NO_RESID, ro).astype(np.uint32)
+            intra = intra[W.wavefront_order(intra, self.cfi, self.log2_ctb)]
         mc = np.zeros(len(self.mc), W.mc_dt)
         if self.mc:
             for name in self.mc[0]:

@@ -92,6 +92,18 @@ def split_mc_tiles(recs):
     return np.concatenate(out)
 
 
+def wavefront_order(intra, cfi, log2_ctb):
+    """Permutation that puts decode-order intra records into CTB-wavefront order (key = ctb_x + 2*ctb_y, the
+    WPP dependency order; stable inside a CTB).  Still a topological order of the intra dependencies, but the
+    device's in-order window then spans whole anti-diagonals of CTBs instead of one CTB row.  Same rule as
+    b200_rec_finish()."""
+    hs = np.where((intra["plane"] > 0) & (cfi != 3), 1, 0)
+    vs = np.where((intra["plane"] > 0) & (cfi == 1), 1, 0)
+    cx = (intra["x"].astype(np.int64) << hs) >> log2_ctb
+    cy = (intra["y"].astype(np.int64) << vs) >> log2_ctb
+    return np.lexsort((np.arange(len(intra)), cy, cx + 2 * cy))
+
+
 def build_blob(width, height, cfi, bit_depth, log2_ctb, cur_slot, poc=0, coeff=None, tu=None, intra=None, mc=None,
                dbk=None, sao=None, out=None, ref_slots=()):
     """Assemble a blob.  tu: dict {2,3,4,5 -> tu_dt array}; dbk: uint16 array (DbkLayout.total) or None;
