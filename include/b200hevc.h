@@ -105,6 +105,9 @@ int  b200_rec_mc(B200Rec *r, const B200McRec *whole_block /* w,h up to 64 */);
 int  b200_rec_deblock(B200Rec *r, int plane, int vertical, int x, int y, int beta, const int tc[2],
                       const uint8_t no_p[2], const uint8_t no_q[2]);
 int  b200_rec_sao(B200Rec *r, int plane, int x, int y, const B200SaoRec *params);
+/* host helper shared by the recorder and by external blob builders: permutation (perm[new] = old) that sorts decode-order
+ * intra records by dependency level (stable); returns the number of levels (>= 0) or a negative error */
+int  b200_intra_level_order(const B200IntraRec *recs, uint32_t n, int width, int height, int chroma_format_idc, uint32_t *perm);
 /* finish: returns the blob (pinned memory owned by the recorder, valid until the next begin) */
 int  b200_rec_finish(B200Rec *r, const void **blob, uint64_t *nbytes);
 

@@ -1,0 +1,47 @@
+/*
+ * b200hevc_tables.h — the reference-facing entry points of libb200hevc_shim.so: what a maintainer of
+ * openHEVC links against to route the HEVCDSPContext / HEVCPredContext / VideoDSPContext function
+ * tables to the B200.  Each one replaces / complements a hook of the reference:
+ *
+ *   ff_hevcdsp_init_b200   like ff_hevcdsp_init_x86 / _arm, called at the end of ff_hevc_dsp_init
+ *                          (reference libavcodec/hevcdsp.c:1326-1327, prototypes hevcdsp.h:173-174)
+ *   ff_hevcpred_init_b200  like ff_hevcpred_init_x86 (libavcodec/hevcpred.c:84, hevcpred.h:44)
+ *   ff_videodsp_init_b200  like ff_videodsp_init_x86 (libavcodec/videodsp.c:51-58, videodsp.h:94-97)
+ *   b200_frame_begin       after hevc_frame_start() has chosen the DPB slot      (libavcodec/hevc.c:3245)
+ *   b200_frame_end         when every CTB of the picture has been parsed          (libavcodec/hevc.c:3446)
+ *   b200_frame_readback    before the picture is hashed or output                 (libavcodec/hevc.c:4145, 4178)
+ *
+ * The structs are the reference's own (opaque here); the implementation
+ * (openhevc_b200/csrc/shim/hevcdsp_init_b200.c) is compiled against the reference headers.
+ * All int functions return 0 or a negative B200_E* code (include/b200hevc.h); the table functions
+ * themselves return void like the slots they replace, errors are latched and reported by
+ * b200_frame_end / b200_frame_readback, text from b200_shim_error().
+ */
+#ifndef B200HEVC_TABLES_H
+#define B200HEVC_TABLES_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+struct HEVCDSPContext;
+struct HEVCPredContext;
+struct VideoDSPContext;
+struct HEVCContext;
+struct AVFrame;
+
+void ff_hevcdsp_init_b200(struct HEVCDSPContext *c, const int bit_depth);
+void ff_hevcpred_init_b200(struct HEVCPredContext *c, const int bit_depth);
+void ff_videodsp_init_b200(struct VideoDSPContext *c, int bpc);
+
+int  b200_frame_begin(struct HEVCContext *s);
+int  b200_frame_end(struct HEVCContext *s);
+int  b200_frame_readback(struct HEVCContext *s, struct AVFrame *frame);
+int  b200_frame_upload_ref(struct HEVCContext *s, struct AVFrame *frame);   /* host-only reference picture -> device slot */
+void b200_shim_close(void);
+const char *b200_shim_error(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B200HEVC_TABLES_H */

@@ -11,6 +11,7 @@
 // oracle/, which is pinned against the reference build).  No tensor cores: the path is HBM / L2
 // bound integer work.
 #include "common.cuh"
+#include <stdlib.h>
 
 // --------------------------------------------------------------------------------------------
 // constants
@@ -334,6 +335,16 @@ __device__ __forceinline__ uint32_t ld_acquire(const uint32_t *p)
     asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
     return v;
 }
+__device__ __forceinline__ uint32_t ld_relaxed(const uint32_t *p)
+{
+    uint32_t v;
+    asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_relaxed(uint32_t *p, uint32_t v)
+{
+    asm volatile("st.relaxed.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
 __device__ __forceinline__ void st_release(uint32_t *p, uint32_t v)
 {
     asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
@@ -358,6 +369,144 @@ __global__ void k_intra_prepass(const B200IntraRec *__restrict__ recs, int count
         for (int x = 0; x < u; x++) f[(uy + y) * fs + ux + x] = 0;
 }
 
+
+// Fast path for 4x4 / 8x8 intra TUs (the bulk of every dependency chain): the <= 33 reference samples live one per
+// lane in two registers (fT: lane k = top[k-1], fL: lane k = left[k]); gathering, substitution, [1 2 1] smoothing and
+// the predictors use warp shuffles only -- no shared memory, no loops -- so one wavefront step is ~150 instructions.
+template <typename PIX>
+__device__ __forceinline__ void intra_small(const B200IntraRec &r, const int16_t *__restrict__ pool, const PlaneDesc &pd, int bd,
+                                            uint32_t *flg, int fs, uint32_t *counter, int lane)
+{
+    const unsigned FULL = 0xffffffffu;
+    const int n = 1 << r.log2, n2 = 2 * n, x0 = r.x, y0 = r.y, maxv = (1 << bd) - 1;
+    const bool ul = r.flags & B200_INF_UP_LEFT, up = r.flags & B200_INF_UP, ur = r.flags & B200_INF_UP_RIGHT;
+    const bool lf = r.flags & B200_INF_LEFT, bl = r.flags & B200_INF_BOTTOM_LEFT;
+    const int trs = r.top_right_size, bls = r.bottom_left_size;
+    // residual prefetch (independent of the neighbours)
+    const int npx = n * n;
+    const int16_t *res = r.resid_off != B200_NO_RESID ? pool + r.resid_off : nullptr;
+    int rs0 = 0, rs1 = 0;
+    if (res) { if (lane < npx) rs0 = res[lane]; if (lane + 32 < npx) rs1 = res[lane + 32]; }
+    // ---- wait: lane 0 corner, lanes 1..4 top units, lanes 5..8 left units ----
+    {
+        int ux = -1, uy = -1;
+        if (lane == 0) { if (ul) { ux = (x0 - 1) >> 2; uy = (y0 - 1) >> 2; } }
+        else if (lane <= 4) { const int o = 4 * (lane - 1); if ((o < n && up) || (o >= n && o < n2 && ur && o < n + trs)) { ux = (x0 + o) >> 2; uy = (y0 - 1) >> 2; } }
+        else if (lane <= 8) { const int o = 4 * (lane - 5); if ((o < n && lf) || (o >= n && o < n2 && bl && o < n + bls)) { ux = (x0 - 1) >> 2; uy = (y0 + o) >> 2; } }
+        if (ux >= 0) {
+            const uint32_t *p = flg + uy * fs + ux;
+            uint32_t spins = 0;
+            while (ld_relaxed(p) == 0) {
+                __nanosleep(20);
+                if ((++spins & 1023) == 0 && (spins > (1u << 21) || ld_relaxed(counter + 1))) { st_release(counter + 1, 1u); break; }
+            }
+        }
+    }
+    __threadfence();
+    __syncwarp();
+    // ---- gather: lanes 0..2n -> top[lane-1], lanes 0..2n-1 -> left[lane] ----
+    int gT = 0, gL = 0;
+    {
+        const int t = lane - 1;
+        if (lane == 0) { if (ul) gT = __ldcg(px_ptr<PIX>(pd, x0 - 1, y0 - 1)); }
+        else if (t < n) { if (up) gT = __ldcg(px_ptr<PIX>(pd, x0 + t, y0 - 1)); }
+        else if (t < n2) { if (ur) gT = __ldcg(px_ptr<PIX>(pd, x0 + min(t, n + trs - 1), y0 - 1)); }
+        if (lane < n) { if (lf) gL = __ldcg(px_ptr<PIX>(pd, x0 - 1, y0 + lane)); }
+        else if (lane < n2) { if (bl) gL = __ldcg(px_ptr<PIX>(pd, x0 - 1, y0 + min(lane, n + bls - 1))); }
+    }
+    // ---- substitution (hevcpred_template.c:250-286), closed form on broadcast scalars ----
+    const int g_corner = __shfl_sync(FULL, gT, 0), g_top0 = __shfl_sync(FULL, gT, 1), g_topn1 = __shfl_sync(FULL, gT, n), g_topn = __shfl_sync(FULL, gT, n + 1);
+    const int g_left0 = __shfl_sync(FULL, gL, 0), g_leftn1 = __shfl_sync(FULL, gL, n - 1), g_leftn = __shfl_sync(FULL, gL, n);
+    const int sub = lf ? g_leftn1 : ul ? g_corner : up ? g_top0 : ur ? g_topn : (1 << (bd - 1));
+    const int bl0 = bl ? g_leftn : sub, l0 = lf ? g_left0 : bl0, corner = ul ? g_corner : l0, un1 = up ? g_topn1 : corner;
+    int fT, fL;
+    {
+        const int t = lane - 1;
+        fT = t < 0 ? corner : t < n ? (up ? gT : corner) : (ur ? gT : un1);
+        fL = lane < n ? (lf ? gL : bl0) : (bl ? gL : sub);
+    }
+    const int mode = r.mode;
+    // ---- [1 2 1] smoothing (:288-327); strong smoothing needs 32x32, never here ----
+    if ((r.flags & B200_INF_FILTER) && mode != 1 && n == 8) {
+        const int d26 = abs(mode - 26), d10 = abs(mode - 10);
+        if (min(d26, d10) > 7) {
+            const int tm = __shfl_up_sync(FULL, fT, 1), tp = __shfl_down_sync(FULL, fT, 1);
+            const int lm = __shfl_up_sync(FULL, fL, 1), lp = __shfl_down_sync(FULL, fL, 1);
+            const int top0 = __shfl_sync(FULL, fT, 1), left0 = __shfl_sync(FULL, fL, 0);
+            int qT, qL;
+            if (lane == 0) qT = (left0 + 2 * corner + top0 + 2) >> 2;
+            else if (lane == n2) qT = fT;                                  // top[2n-1]
+            else qT = (tp + 2 * fT + tm + 2) >> 2;
+            if (lane == n2 - 1) qL = fL;
+            else qL = (lp + 2 * fL + (lane == 0 ? corner : lm) + 2) >> 2;
+            fT = qT; fL = qL;
+        }
+    }
+#define TOPS(i) __shfl_sync(FULL, fT, ((i) + 1) & 31)
+#define LEFTS(i) __shfl_sync(FULL, fL, (i) & 31)
+    const int cornerf = __shfl_sync(FULL, fT, 0);
+    // ---- predictors ----
+    int dc = 0;
+    if (mode == 1) {
+        int sum = (lane < n ? fL : 0) + ((lane >= 1 && lane <= n) ? fT : 0);
+#pragma unroll
+        for (int o = 16; o; o >>= 1) sum += __shfl_xor_sync(FULL, sum, o);
+        dc = (sum + n) >> (r.log2 + 1);
+    }
+    const int angle = mode >= 2 ? c_intra_angle[mode - 2] : 0;
+    const bool vertical = mode >= 18;
+    const int inv = (mode >= 11 && mode <= 25) ? c_inv_angle[mode - 11] : 0;
+    const bool edge = r.plane == 0;                                       // n < 32 always here
+    const int topn_f = TOPS(n), leftn_f = LEFTS(n), top0_f = TOPS(0), left0_f = LEFTS(0);
+#pragma unroll
+    for (int it = 0; it < 2; it++) {
+        const int i = lane + 32 * it;
+        if (it * 32 >= npx) break;                                         // uniform
+        const int y = (i >> r.log2) & (n - 1), x = i & (n - 1);
+        const int ty = TOPS(x), lx = LEFTS(y);                             // top[x], left[y]
+        int v;
+        if (mode == 0) {
+            v = ((n - 1 - x) * lx + (x + 1) * topn_f + (n - 1 - y) * ty + (y + 1) * leftn_f + n) >> (r.log2 + 1);
+        } else if (mode == 1) {
+            v = dc;
+            if (edge) {
+                if (x == 0 && y == 0) v = (left0_f + 2 * dc + top0_f + 2) >> 2;
+                else if (y == 0) v = (ty + 3 * dc + 2) >> 2;
+                else if (x == 0) v = (lx + 3 * dc + 2) >> 2;
+            }
+        } else {
+            const int a = vertical ? y : x, b = vertical ? x : y;
+            const int pos = (a + 1) * angle, id = pos >> 5, fact = pos & 31;
+            const int k0 = b + id + 1, k1 = k0 + 1;                        // ref[k] = main[k-1]; k < 0: projected side sample
+            // source of ref[k]: main[k-1] (k>=0) or side[j], j = -1 + ((k*inv+128)>>8); index -1 of either array is the corner (fT lane 0)
+            const int j0 = k0 >= 0 ? k0 - 1 : -1 + ((k0 * inv + 128) >> 8), j1 = k1 >= 0 ? k1 - 1 : -1 + ((k1 * inv + 128) >> 8);
+            const bool t0 = (k0 >= 0) == vertical, t1 = (k1 >= 0) == vertical;   // read from the top register?
+            const int a0 = __shfl_sync(FULL, fT, (j0 + 1) & 31), b0 = __shfl_sync(FULL, fL, j0 & 31);
+            const int a1 = __shfl_sync(FULL, fT, (j1 + 1) & 31), b1 = __shfl_sync(FULL, fL, j1 & 31);
+            const int r0 = (t0 || j0 < 0) ? a0 : b0, r1 = (t1 || j1 < 0) ? a1 : b1;
+            v = fact ? ((32 - fact) * r0 + fact * r1 + 16) >> 5 : r0;
+            if (edge) {
+                if (mode == 26 && x == 0) v = clip3i(top0_f + ((lx - cornerf) >> 1), 0, maxv);
+                if (mode == 10 && y == 0) v = clip3i(left0_f + ((ty - cornerf) >> 1), 0, maxv);
+            }
+        }
+        if (i < npx) {
+            if (res) v = clip3i(v + (it ? rs1 : rs0), 0, maxv);
+            *px_ptr<PIX>(pd, x0 + x, y0 + y) = (PIX)v;
+        }
+    }
+#undef TOPS
+#undef LEFTS
+    // ---- publish ----
+    __threadfence();
+    __syncwarp();
+    {
+        const int u = n >> 2, ux = x0 >> 2, uy = y0 >> 2;
+        if (lane < u * u) st_relaxed(flg + (uy + lane / u) * fs + ux + (lane % u), 1u);
+    }
+    __syncwarp();
+}
+
 template <typename PIX>
 __global__ void __launch_bounds__(128) k_intra(const B200IntraRec *__restrict__ recs, int count, const int16_t *__restrict__ pool,
                                                FrameDesc f, int bd, IntraFlags fl, uint32_t *counter)
@@ -376,6 +525,10 @@ __global__ void __launch_bounds__(128) k_intra(const B200IntraRec *__restrict__ 
         {
             const int4 raw = __ldg(reinterpret_cast<const int4 *>(recs + idx));
             memcpy(&r, &raw, 16);
+        }
+        if (r.log2 <= 3) {
+            intra_small<PIX>(r, pool, f.p[r.plane], bd, fl.f[r.plane], fl.stride[r.plane], counter, lane);
+            continue;
         }
         const int n = 1 << r.log2, n2 = 2 * n, x0 = r.x, y0 = r.y;
         const PlaneDesc pd = f.p[r.plane];
@@ -399,12 +552,13 @@ __global__ void __launch_bounds__(128) k_intra(const B200IntraRec *__restrict__ 
                 // a malformed list (dependency on a later TU) must not hang the GPU: give up after ~0.25 s and latch an error
                 const uint32_t *p = flg + uy * fs + ux;
                 uint32_t spins = 0;
-                while (ld_acquire(p) == 0) {
+                while (ld_relaxed(p) == 0) {       // relaxed polls; ONE acquire fence after the wait (below)
                     __nanosleep(20);
-                    if ((++spins & 1023) == 0 && (spins > (1u << 21) || ld_acquire(counter + 1))) { st_release(counter + 1, 1u); break; }
+                    if ((++spins & 1023) == 0 && (spins > (1u << 21) || ld_relaxed(counter + 1))) { st_release(counter + 1, 1u); break; }
                 }
             }
         }
+        __threadfence();      // acquire side: orders the flag reads above before the neighbour loads below
         __syncwarp();
         // ---- gather (L2 loads: neighbours were written by other SMs) ----
         int *gt = s_g[warp][0], *gl = s_g[warp][1];
@@ -511,11 +665,12 @@ __global__ void __launch_bounds__(128) k_intra(const B200IntraRec *__restrict__ 
             *px_ptr<PIX>(pd, x0 + x, y0 + y) = (PIX)v;
         }
         // ---- publish ----
+        // message passing with one fence per side: every lane fences its own pixel stores, then relaxed flag stores
         __threadfence();
         __syncwarp();
         {
             const int u = n >> 2, ux = x0 >> 2, uy = y0 >> 2;
-            for (int k = lane; k < u * u; k += 32) st_release(flg + (uy + k / u) * fs + ux + (k % u), 1u);
+            for (int k = lane; k < u * u; k += 32) st_relaxed(flg + (uy + k / u) * fs + ux + (k % u), 1u);
         }
         __syncwarp();
     }
@@ -763,7 +918,10 @@ int launch_intra(cudaStream_t st, const B200IntraRec *recs, int count, const int
     cudaMemsetAsync(counter, 0, sizeof(uint32_t), st);   // counter[1] = sticky abort flag, cleared at context creation
     k_intra_prepass<<<(count + 255) / 256, 256, 0, st>>>(recs, count, fl);
     int grid = (count + 3) / 4;
-    if (grid > 148 * 8) grid = 148 * 8;   // persistent: 8 CTAs of 4 warps per SM
+    // persistent warps.  The list is sorted by dependency level, so the TUs that can run together are adjacent and a
+    // small window exposes all the parallelism there is; more waiting warps would only add polling traffic on L2.
+    static const int max_ctas = getenv("B200_INTRA_CTAS") ? atoi(getenv("B200_INTRA_CTAS")) : 148 * 2;
+    if (grid > max_ctas) grid = max_ctas;
     if (bd > 8) k_intra<uint16_t><<<grid, 128, 0, st>>>(recs, count, pool, cur, bd, fl, counter);
     else        k_intra<uint8_t><<<grid, 128, 0, st>>>(recs, count, pool, cur, bd, fl, counter);
     return 2;

@@ -29,6 +29,53 @@ struct B200Rec {
     uint64_t nbytes = 0;
 };
 
+// Decode order -> dependency-level order.  level(TU) = 1 + max level of the 4x4 units it reads (0 for units no intra
+// TU of this picture writes); sorting by level (stable) is still a topological order of the intra dependencies, and
+// it puts the TUs that can run concurrently next to each other, so the device needs only a small in-flight window
+// (few warps polling) to expose all the parallelism the picture has.  O(n * neighbours), host only.
+extern "C" int b200_intra_level_order(const B200IntraRec *recs, uint32_t n, int width, int height, int cfi, uint32_t *perm)
+{
+    if (!recs || !perm) return B200_EINVAL;
+    std::vector<uint32_t> lvl[3];
+    int fs[3];
+    for (int p = 0; p < 3; p++) {
+        int pw, ph;
+        b200_plane_dims(width, height, cfi, p, &pw, &ph);
+        fs[p] = pw / 4 + 2;
+        lvl[p].assign((size_t)fs[p] * (ph / 4 + 2), 0);
+    }
+    std::vector<uint32_t> level(n);
+    uint32_t maxl = 0;
+    for (uint32_t i = 0; i < n; i++) {
+        const B200IntraRec &r = recs[i];
+        if (r.plane > 2 || r.log2 < 2 || r.log2 > 5) return B200_EINVAL;
+        std::vector<uint32_t> &L = lvl[r.plane];
+        const int s = fs[r.plane], u = 1 << (r.log2 - 2), ux = r.x >> 2, uy = r.y >> 2, nn = 1 << r.log2;
+        if ((size_t)(uy + u) * s + ux + u >= L.size() + s) return B200_EINVAL;
+        uint32_t m = 0;
+        if ((r.flags & B200_INF_UP_LEFT) && ux && uy) m = L[(size_t)(uy - 1) * s + ux - 1];
+        if (uy) {
+            int cnt = (r.flags & B200_INF_UP) ? u : 0, from = (r.flags & B200_INF_UP) ? 0 : u;
+            if (r.flags & B200_INF_UP_RIGHT) cnt = u + (r.top_right_size + 3) / 4;
+            for (int k = from; k < cnt; k++) { const size_t idx = (size_t)(uy - 1) * s + ux + k; if (idx < L.size() && L[idx] > m) m = L[idx]; }
+        }
+        if (ux) {
+            int cnt = (r.flags & B200_INF_LEFT) ? u : 0, from = (r.flags & B200_INF_LEFT) ? 0 : u;
+            if (r.flags & B200_INF_BOTTOM_LEFT) cnt = u + (r.bottom_left_size + 3) / 4;
+            for (int k = from; k < cnt; k++) { const size_t idx = (size_t)(uy + k) * s + ux - 1; if (idx < L.size() && L[idx] > m) m = L[idx]; }
+        }
+        (void)nn;
+        level[i] = m + 1;
+        if (level[i] > maxl) maxl = level[i];
+        for (int y = 0; y < u; y++) for (int x = 0; x < u; x++) L[(size_t)(uy + y) * s + ux + x] = m + 1;
+    }
+    std::vector<uint32_t> start(maxl + 2, 0);
+    for (uint32_t i = 0; i < n; i++) start[level[i] + 1]++;
+    for (uint32_t k = 0; k <= maxl; k++) start[k + 1] += start[k];
+    for (uint32_t i = 0; i < n; i++) perm[start[level[i]]++] = i;
+    return (int)maxl;
+}
+
 extern "C" int b200_rec_set_refs(B200Rec *r, const uint8_t *slots, int n)
 {
     if (!r || !r->open || n < 0 || n > 16 || (n && !slots)) return B200_EINVAL;
@@ -231,22 +278,10 @@ extern "C" int b200_rec_finish(B200Rec *r, const void **blob, uint64_t *nbytes)
     }
     h->sec[B200_SEC_INTRA].off = (uint32_t)o; h->sec[B200_SEC_INTRA].count = (uint32_t)r->intra.size();
     if (!r->intra.empty()) {
-        // decode order -> CTB-wavefront order (key = ctb_x + 2*ctb_y, then ctb_y; stable inside a CTB): still a
-        // topological order of the intra dependencies (left, up, up-right CTBs have smaller keys), but the device's
-        // in-order window then covers whole anti-diagonals of CTBs.  Counting sort, O(n).
-        const int lc = r->cfg.log2_ctb_size, nkeys = (r->ctb_w + 2 * r->ctb_h) * r->ctb_h + 1;
-        std::vector<uint32_t> start(nkeys + 1, 0);
-        std::vector<uint32_t> key(r->intra.size());
-        for (size_t i = 0; i < r->intra.size(); i++) {
-            const B200IntraRec &ir = r->intra[i];
-            const int hs = ir.plane && r->cfg.chroma_format_idc != 3, vs = ir.plane && r->cfg.chroma_format_idc == 1;
-            const int cx = (ir.x << hs) >> lc, cy = (ir.y << vs) >> lc;
-            key[i] = (uint32_t)((cx + 2 * cy) * r->ctb_h + cy);
-            start[key[i] + 1]++;
-        }
-        for (int k = 0; k < nkeys; k++) start[k + 1] += start[k];
+        std::vector<uint32_t> perm(r->intra.size());
+        b200_intra_level_order(r->intra.data(), (uint32_t)r->intra.size(), r->cfg.width, r->cfg.height, r->cfg.chroma_format_idc, perm.data());
         B200IntraRec *dst = (B200IntraRec *)(r->blob + o);
-        for (size_t i = 0; i < r->intra.size(); i++) dst[start[key[i]]++] = r->intra[i];
+        for (size_t i = 0; i < perm.size(); i++) dst[i] = r->intra[perm[i]];
     }
     o = (o + r->intra.size() * 16 + 255) & ~(uint64_t)255;
     h->sec[B200_SEC_MC].off = (uint32_t)o; h->sec[B200_SEC_MC].count = (uint32_t)r->mc.size();

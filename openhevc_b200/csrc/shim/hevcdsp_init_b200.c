@@ -1,0 +1,436 @@
+/*
+ * hevcdsp_init_b200.c — the drop-in boundary: re-populates openHEVC's own function tables with
+ * recorders that feed libb200hevc.so.  The B200 analogue of libavcodec/x86/hevcdsp_init.c:
+ *
+ *   ff_hevcdsp_init_b200(HEVCDSPContext *, bit_depth)   <- hook after hevcdsp.c:1326-1327
+ *   ff_hevcpred_init_b200(HEVCPredContext *, bit_depth) <- hook after hevcpred.c:84
+ *   ff_videodsp_init_b200(VideoDSPContext *, bpc)       <- hook after videodsp.c:51-58
+ *   b200_frame_begin / b200_frame_end / b200_frame_readback <- hevc.c:3245 / 3446 / 4145
+ *
+ * Every installed function has exactly the signature of the slot it replaces (hevcdsp.h:45-105,
+ * hevcpred.h:32-40, videodsp.h:66-70) and never touches pixels: it maps the pointers it is given
+ * back to (DPB slot, plane, x, y) through the planes registered at frame begin and appends one record.
+ * Compiled against the reference's headers where they lie (-I/root/reference); it contains no
+ * reference code.  Round-1 limits: one decoder instance, threads=1 (state below is process-global),
+ * constrained_intra_pred / cross-component prediction / pcm+transquant-bypass SAO restore are
+ * rejected with an error from b200_frame_end.
+ */
+#include <stdint.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include "libavcodec/hevc.h"
+#include "libavcodec/hevcdsp.h"
+#include "libavcodec/hevcpred.h"
+#include "libavcodec/videodsp.h"
+#include "libavcodec/get_bits.h"
+#include "b200hevc.h"
+#include "b200hevc_tables.h"
+
+#define MAX_REG 33
+
+typedef struct RegPlane { const uint8_t *base; ptrdiff_t linesize; int slot, plane, w, h; } RegPlane;
+
+static struct {
+    B200Ctx *ctx;
+    B200Rec *rec;
+    B200Config cfg;
+    int bd, B, cfi;
+    int pw[3], ph[3];
+    RegPlane reg[MAX_REG * 3];
+    int n_reg;
+    const uint8_t *cur_base[3]; ptrdiff_t cur_ls[3]; int cur_slot;
+    uint8_t ref_slot[16]; int n_ref;
+    /* pending in-place transform on the per-thread coefficient scratch (hevc.h:1063) */
+    const int16_t *pend_ptr; int pend_kind, pend_flags, pend_col_limit;
+    /* first list of a bi-predicted block: put_hevc_*pel() into the caller's tmp[] (hevc.c:1761) */
+    const int16_t *first_tmp; B200McRec first;
+    /* emulated_edge_mc results, keyed by destination buffer (lc->edge_emu_buffer / edge_emu_buffer2) */
+    struct { const uint8_t *buf; ptrdiff_t ls; int slot, plane, x, y; } emu[2];
+    int emu_next;
+    int err; char errmsg[256];
+    int in_frame;
+} g;
+
+static void fail(int code, const char *msg)
+{
+    if (!g.err) { g.err = code; snprintf(g.errmsg, sizeof(g.errmsg), "%s", msg); }
+}
+const char *b200_shim_error(void) { return g.err ? g.errmsg : (g.ctx ? b200_last_error(g.ctx) : ""); }
+
+/* ---- pointer -> (slot, plane, x, y) ---------------------------------------------------------------- */
+static int locate_cur(const uint8_t *p, int *plane, int *x, int *y)
+{
+    for (int c = 0; c < 3; c++) {
+        ptrdiff_t off = p - g.cur_base[c];
+        if (off >= 0 && off < g.cur_ls[c] * g.ph[c]) {
+            *plane = c; *y = (int)(off / g.cur_ls[c]); *x = (int)(off % g.cur_ls[c]) / g.B;
+            return 0;
+        }
+    }
+    fail(B200_EINVAL, "destination pointer is not inside the current picture");
+    return -1;
+}
+
+static int locate_ref(const uint8_t *p, int plane_hint, int *slot, int *x, int *y)
+{
+    for (int e = 0; e < 2; e++)          /* source inside an edge-emulation buffer? (hevc.c:1673) */
+        if (g.emu[e].buf && p >= g.emu[e].buf && p < g.emu[e].buf + g.emu[e].ls * (MAX_PB_SIZE + 7)) {
+            ptrdiff_t off = p - g.emu[e].buf;
+            *slot = g.emu[e].slot; *y = g.emu[e].y + (int)(off / g.emu[e].ls); *x = g.emu[e].x + (int)(off % g.emu[e].ls) / g.B;
+            return g.emu[e].plane;
+        }
+    for (int i = 0; i < g.n_reg; i++) {
+        const RegPlane *r = &g.reg[i];
+        ptrdiff_t off = p - r->base;
+        if (off >= 0 && off < r->linesize * r->h && (plane_hint < 0 || r->plane == plane_hint)) {
+            *slot = r->slot; *y = (int)(off / r->linesize); *x = (int)(off % r->linesize) / g.B;
+            return r->plane;
+        }
+    }
+    fail(B200_EINVAL, "source pointer is not inside a registered reference picture");
+    return -1;
+}
+
+static int ref_index(int slot)
+{
+    for (int i = 0; i < g.n_ref; i++) if (g.ref_slot[i] == slot) return i;
+    if (g.n_ref == 16) { fail(B200_ENOTSUP, "more than 16 reference pictures"); return 0; }
+    g.ref_slot[g.n_ref] = (uint8_t)slot;
+    return g.n_ref++;
+}
+
+/* ---- residual slots --------------------------------------------------------------------------------- */
+static void rec_idct(int16_t *c, int col_limit) { g.pend_ptr = c; g.pend_kind = B200_TU_IDCT; g.pend_flags = 0; g.pend_col_limit = col_limit; }
+static void rec_idct_dc(int16_t *c) { g.pend_ptr = c; g.pend_kind = B200_TU_DC; g.pend_flags = 0; g.pend_col_limit = 0; }
+static void rec_idct_4x4_luma(int16_t *c) { g.pend_ptr = c; g.pend_kind = B200_TU_DST; g.pend_flags = 0; g.pend_col_limit = 0; }
+static void rec_transform_skip(int16_t *c, int16_t log2_size) { (void)log2_size; g.pend_ptr = c; g.pend_kind = B200_TU_SKIP; g.pend_flags = 0; g.pend_col_limit = 0; }
+static void rec_transform_rdpcm(int16_t *c, int16_t log2_size, int mode)
+{
+    (void)log2_size;
+    if (g.pend_ptr != c) { g.pend_ptr = c; g.pend_kind = B200_TU_BYPASS; g.pend_col_limit = 0; }
+    g.pend_flags = B200_TUF_RDPCM | (mode ? B200_TUF_RDPCM_VERT : 0);
+}
+static void rec_transform_add(uint8_t *dst, int16_t *coeffs, ptrdiff_t stride, int log2)
+{
+    int plane, x, y;
+    (void)stride;
+    if (locate_cur(dst, &plane, &x, &y)) return;
+    int kind = B200_TU_BYPASS, flags = 0, cl = 0;
+    if (g.pend_ptr == coeffs) { kind = g.pend_kind; flags = g.pend_flags; cl = g.pend_col_limit; }
+    g.pend_ptr = NULL;
+    int rc = b200_rec_tu(g.rec, plane, x, y, log2, kind, flags, cl, coeffs, -1);
+    if (rc) fail(rc, "b200_rec_tu failed");
+}
+static void rec_add4(uint8_t *d, int16_t *c, ptrdiff_t s) { rec_transform_add(d, c, s, 2); }
+static void rec_add8(uint8_t *d, int16_t *c, ptrdiff_t s) { rec_transform_add(d, c, s, 3); }
+static void rec_add16(uint8_t *d, int16_t *c, ptrdiff_t s) { rec_transform_add(d, c, s, 4); }
+static void rec_add32(uint8_t *d, int16_t *c, ptrdiff_t s) { rec_transform_add(d, c, s, 5); }
+
+static void rec_put_pcm(uint8_t *dst, ptrdiff_t stride, int width, int height, GetBitContext *gb, int pcm_bit_depth)
+{
+    int plane, x, y;
+    int16_t smp[32 * 32];
+    (void)stride;
+    if (locate_cur(dst, &plane, &x, &y)) return;
+    if (width > 32 || height > 64) { fail(B200_ENOTSUP, "pcm block too large"); return; }
+    /* square blocks per plane; 4:2:2 chroma (w x 2w) is recorded as two squares */
+    for (int part = 0; part < height / width; part++) {
+        for (int i = 0; i < width * width; i++) smp[i] = (int16_t)(get_bits(gb, pcm_bit_depth) << (g.bd - pcm_bit_depth));
+        int log2 = 0;
+        while ((1 << log2) < width) log2++;
+        if (log2 < 2) { fail(B200_ENOTSUP, "pcm block smaller than 4x4"); return; }
+        int rc = b200_rec_pcm(g.rec, plane, x, y + part * width, log2, smp);
+        if (rc) fail(rc, "b200_rec_pcm failed");
+    }
+}
+
+/* ---- inter prediction slots --------------------------------------------------------------------------- */
+static int mc_fill(B200McRec *m, int list, const uint8_t *src, int mx, int my, int chroma_hint)
+{
+    int slot, sx, sy;
+    int plane = locate_ref(src, -1, &slot, &sx, &sy);
+    if (plane < 0) return -1;
+    (void)chroma_hint;
+    const int ri = ref_index(slot);
+    /* positions far outside the picture clamp sample by sample: pre-clamp the origin so that it fits int16 */
+    const int pw = g.pw[plane], ph = g.ph[plane];
+    if (sx < -80) sx = -80; if (sx > pw + 16) sx = pw + 16;
+    if (sy < -80) sy = -80; if (sy > ph + 16) sy = ph + 16;
+    if (list == 0) { m->ref0 = (uint8_t)ri; m->sx0 = (int16_t)sx; m->sy0 = (int16_t)sy; m->frac0 = (uint8_t)(mx | (my << 4)); }
+    else           { m->ref1 = (uint8_t)ri; m->sx1 = (int16_t)sx; m->sy1 = (int16_t)sy; m->frac1 = (uint8_t)(mx | (my << 4)); }
+    return plane;
+}
+
+static void mc_first(int16_t *dst, uint8_t *src, int height, intptr_t mx, intptr_t my, int width, int chroma)
+{
+    memset(&g.first, 0, sizeof(g.first));
+    g.first.w = (uint8_t)width; g.first.h = (uint8_t)height;
+    g.first.flags = (uint8_t)(B200_MCF_BI | (chroma ? B200_MCF_CHROMA : 0));
+    if (mc_fill(&g.first, 0, src, (int)mx, (int)my, chroma) < 0) return;
+    g.first_tmp = dst;
+}
+static void mc_emit(B200McRec *m, uint8_t *dst)
+{
+    int plane, x, y;
+    if (locate_cur(dst, &plane, &x, &y)) return;
+    m->plane = (uint8_t)plane; m->x = (uint16_t)x; m->y = (uint16_t)y;
+    int rc = b200_rec_mc(g.rec, m);
+    if (rc) fail(rc, "b200_rec_mc failed");
+}
+static void mc_uni(uint8_t *dst, uint8_t *src, int height, int mx, int my, int width, int chroma, int weighted, int denom, int wx, int ox)
+{
+    B200McRec m;
+    memset(&m, 0, sizeof(m));
+    m.w = (uint8_t)width; m.h = (uint8_t)height;
+    m.flags = (uint8_t)((chroma ? B200_MCF_CHROMA : 0) | (weighted ? B200_MCF_WEIGHTED : 0));
+    m.denom = (uint8_t)denom; m.w0 = (int16_t)wx; m.o0 = (int16_t)ox;
+    if (mc_fill(&m, 0, src, mx, my, chroma) < 0) return;
+    mc_emit(&m, dst);
+}
+static void mc_bi(uint8_t *dst, uint8_t *src, int16_t *src2, int height, int mx, int my, int width, int chroma, int weighted,
+                  int denom, int wx0, int wx1, int ox0, int ox1)
+{
+    if (src2 != g.first_tmp) { fail(B200_ESTATE, "put_hevc_*_bi without the matching first-list call"); return; }
+    B200McRec m = g.first;
+    g.first_tmp = NULL;
+    if (m.w != width || m.h != height) { fail(B200_ESTATE, "bi-prediction block size mismatch"); return; }
+    m.flags |= weighted ? B200_MCF_WEIGHTED : 0;
+    m.denom = (uint8_t)denom; m.w0 = (int16_t)wx0; m.w1 = (int16_t)wx1; m.o0 = (int16_t)ox0; m.o1 = (int16_t)ox1;
+    if (mc_fill(&m, 1, src, mx, my, chroma) < 0) return;
+    mc_emit(&m, dst);
+}
+
+#define MC_FAMILY(T, CH) \
+static void rec_##T(int16_t *dst, ptrdiff_t ds, uint8_t *src, ptrdiff_t ss, int h, intptr_t mx, intptr_t my, int w) \
+{ (void)ds; (void)ss; mc_first(dst, src, h, mx, my, w, CH); } \
+static void rec_##T##_uni(uint8_t *dst, ptrdiff_t ds, uint8_t *src, ptrdiff_t ss, int h, intptr_t mx, intptr_t my, int w) \
+{ (void)ds; (void)ss; mc_uni(dst, src, h, (int)mx, (int)my, w, CH, 0, 0, 0, 0); } \
+static void rec_##T##_uni_w(uint8_t *dst, ptrdiff_t ds, uint8_t *src, ptrdiff_t ss, int h, int denom, int wx, int ox, intptr_t mx, intptr_t my, int w) \
+{ (void)ds; (void)ss; mc_uni(dst, src, h, (int)mx, (int)my, w, CH, 1, denom, wx, ox); } \
+static void rec_##T##_bi(uint8_t *dst, ptrdiff_t ds, uint8_t *src, ptrdiff_t ss, int16_t *src2, ptrdiff_t s2, int h, intptr_t mx, intptr_t my, int w) \
+{ (void)ds; (void)ss; (void)s2; mc_bi(dst, src, src2, h, (int)mx, (int)my, w, CH, 0, 0, 0, 0, 0, 0); } \
+static void rec_##T##_bi_w(uint8_t *dst, ptrdiff_t ds, uint8_t *src, ptrdiff_t ss, int16_t *src2, ptrdiff_t s2, int h, int denom, int wx0, int wx1, int ox0, int ox1, intptr_t mx, intptr_t my, int w) \
+{ (void)ds; (void)ss; (void)s2; mc_bi(dst, src, src2, h, (int)mx, (int)my, w, CH, 1, denom, wx0, wx1, ox0, ox1); }
+MC_FAMILY(qpel, 0)
+MC_FAMILY(epel, 1)
+
+/* vdsp.emulated_edge_mc: remember where the window really comes from; nothing is copied (the device clamps) */
+static void rec_emulated_edge_mc(uint8_t *buf, const uint8_t *src, ptrdiff_t buf_linesize, ptrdiff_t src_linesize,
+                                 int block_w, int block_h, int src_x, int src_y, int w, int h)
+{
+    (void)block_w; (void)block_h; (void)w; (void)h;
+    const uint8_t *base = src - ((ptrdiff_t)src_y * src_linesize + (ptrdiff_t)src_x * g.B);
+    for (int i = 0; i < g.n_reg; i++)
+        if (g.reg[i].base == base && g.reg[i].linesize == src_linesize) {
+            int e = (g.emu[0].buf == buf) ? 0 : (g.emu[1].buf == buf) ? 1 : (g.emu_next++ & 1);
+            g.emu[e].buf = buf; g.emu[e].ls = buf_linesize; g.emu[e].slot = g.reg[i].slot; g.emu[e].plane = g.reg[i].plane;
+            g.emu[e].x = src_x; g.emu[e].y = src_y;
+            return;
+        }
+    fail(B200_EINVAL, "emulated_edge_mc source does not belong to a registered reference picture");
+}
+
+/* ---- deblocking slots ------------------------------------------------------------------------------------ */
+static void rec_dbk(uint8_t *pix, int vertical, int beta, int *tc, uint8_t *no_p, uint8_t *no_q)
+{
+    int plane, x, y;
+    if (locate_cur(pix, &plane, &x, &y)) return;
+    int rc = b200_rec_deblock(g.rec, plane, vertical, x, y, beta, tc, no_p, no_q);
+    if (rc) fail(rc, "b200_rec_deblock failed");
+}
+static void rec_h_luma(uint8_t *p, ptrdiff_t s, int beta, int *tc, uint8_t *np, uint8_t *nq) { (void)s; rec_dbk(p, 0, beta, tc, np, nq); }
+static void rec_v_luma(uint8_t *p, ptrdiff_t s, int beta, int *tc, uint8_t *np, uint8_t *nq) { (void)s; rec_dbk(p, 1, beta, tc, np, nq); }
+static void rec_h_chroma(uint8_t *p, ptrdiff_t s, int *tc, uint8_t *np, uint8_t *nq) { (void)s; rec_dbk(p, 0, 0, tc, np, nq); }
+static void rec_v_chroma(uint8_t *p, ptrdiff_t s, int *tc, uint8_t *np, uint8_t *nq) { (void)s; rec_dbk(p, 1, 0, tc, np, nq); }
+
+/* ---- SAO slots (dst = picture, src = the host's sao_frame copy, which the device does not need) ---------- */
+static void rec_sao(uint8_t *dst, SAOParams *sao, int *borders, int c_idx, int type, int variant, uint8_t *ve, uint8_t *he, uint8_t *de)
+{
+    int plane, x, y;
+    if (locate_cur(dst, &plane, &x, &y)) return;
+    B200SaoRec r;
+    memset(&r, 0, sizeof(r));
+    r.type = (uint8_t)type;
+    r.param = type == B200_SAO_BAND ? sao->band_position[c_idx] : sao->eo_class[c_idx];
+    r.borders = (uint8_t)((borders[0] ? 1 : 0) | (borders[1] ? 2 : 0) | (borders[2] ? 4 : 0) | (borders[3] ? 8 : 0));
+    if (variant) r.edges = (uint8_t)((ve[0] ? 1 : 0) | (ve[1] ? 2 : 0) | (he[0] ? 4 : 0) | (he[1] ? 8 : 0) | (de[0] ? 16 : 0) | (de[1] ? 32 : 0) | (de[2] ? 64 : 0) | (de[3] ? 128 : 0));
+    r.variant = (uint8_t)variant;
+    for (int k = 0; k < 5; k++) r.offset_val[k] = sao->offset_val[c_idx][k];
+    int rc = b200_rec_sao(g.rec, plane, x, y, &r);
+    if (rc) fail(rc, "b200_rec_sao failed");
+}
+static void rec_sao_band(uint8_t *dst, uint8_t *src, ptrdiff_t sd, ptrdiff_t ss, SAOParams *sao, int *borders, int w, int h, int c_idx)
+{ (void)src; (void)sd; (void)ss; (void)w; (void)h; rec_sao(dst, sao, borders, c_idx, B200_SAO_BAND, 0, NULL, NULL, NULL); }
+static void rec_sao_edge0(uint8_t *dst, uint8_t *src, ptrdiff_t sd, ptrdiff_t ss, SAOParams *sao, int *borders, int w, int h, int c_idx, uint8_t *ve, uint8_t *he, uint8_t *de)
+{ (void)src; (void)sd; (void)ss; (void)w; (void)h; rec_sao(dst, sao, borders, c_idx, B200_SAO_EDGE, 0, ve, he, de); }
+static void rec_sao_edge1(uint8_t *dst, uint8_t *src, ptrdiff_t sd, ptrdiff_t ss, SAOParams *sao, int *borders, int w, int h, int c_idx, uint8_t *ve, uint8_t *he, uint8_t *de)
+{ (void)src; (void)sd; (void)ss; (void)w; (void)h; rec_sao(dst, sao, borders, c_idx, B200_SAO_EDGE, 1, ve, he, de); }
+
+/* ---- intra slot: the availability derivation of hevcpred_template.c:82-109, then one record ------------------ */
+static void rec_intra(HEVCContext *s, int x0, int y0, int log2_size, int c_idx)
+{
+    HEVCLocalContext *lc = s->HEVClc;
+    const HEVCSPS *sps = s->sps;
+    if (s->pps->constrained_intra_pred_flag) { fail(B200_ENOTSUP, "constrained_intra_pred is not supported by the B200 path yet"); return; }
+    const int hshift = sps->hshift[c_idx], vshift = sps->vshift[c_idx];
+    const int size = 1 << log2_size;
+    const int size_l_h = size << hshift, size_l_v = size << vshift;
+    const int tbs_h = size_l_h >> sps->log2_min_tb_size, tbs_v = size_l_v >> sps->log2_min_tb_size;
+    const int x_tb = (x0 >> sps->log2_min_tb_size) & sps->tb_mask, y_tb = (y0 >> sps->log2_min_tb_size) & sps->tb_mask;
+    const int zstride = sps->tb_mask + 2;
+    const int *zs = s->pps->min_tb_addr_zs;
+    const int cur = zs[y_tb * zstride + x_tb];
+    const int bl = lc->na.cand_bottom_left && cur > zs[((y_tb + tbs_v) & sps->tb_mask) * zstride + x_tb - 1];
+    const int ur = lc->na.cand_up_right && cur > zs[(y_tb - 1) * zstride + ((x_tb + tbs_h) & sps->tb_mask)];
+    int bls = (FFMIN(y0 + 2 * size_l_v, sps->height) - (y0 + size_l_v)) >> vshift;
+    int trs = (FFMIN(x0 + 2 * size_l_h, sps->width) - (x0 + size_l_h)) >> hshift;
+    int flags = (lc->na.cand_up_left ? B200_INF_UP_LEFT : 0) | (lc->na.cand_up ? B200_INF_UP : 0) | (ur ? B200_INF_UP_RIGHT : 0) |
+                (lc->na.cand_left ? B200_INF_LEFT : 0) | (bl ? B200_INF_BOTTOM_LEFT : 0);
+    if (!sps->spsRext.intra_smoothing_disabled_flag && (c_idx == 0 || sps->chroma_array_type == 3)) flags |= B200_INF_FILTER;
+    if (sps->sps_strong_intra_smoothing_enable_flag) flags |= B200_INF_STRONG;
+    if (ur && trs <= 0) { flags &= ~B200_INF_UP_RIGHT; if (!(flags & B200_INF_UP)) fail(B200_ENOTSUP, "up-right available with no sample inside the picture"); }
+    if (bl && bls <= 0) { flags &= ~B200_INF_BOTTOM_LEFT; if (!(flags & B200_INF_LEFT)) fail(B200_ENOTSUP, "bottom-left available with no sample inside the picture"); }
+    const int mode = c_idx ? lc->tu.intra_pred_mode_c : lc->tu.intra_pred_mode;
+    int rc = b200_rec_intra(g.rec, c_idx, x0 >> hshift, y0 >> vshift, log2_size, mode, flags, trs, bls);
+    if (rc) fail(rc, "b200_rec_intra failed");
+}
+static void rec_intra_2(HEVCContext *s, int x0, int y0, int c) { rec_intra(s, x0, y0, 2, c); }
+static void rec_intra_3(HEVCContext *s, int x0, int y0, int c) { rec_intra(s, x0, y0, 3, c); }
+static void rec_intra_4(HEVCContext *s, int x0, int y0, int c) { rec_intra(s, x0, y0, 4, c); }
+static void rec_intra_5(HEVCContext *s, int x0, int y0, int c) { rec_intra(s, x0, y0, 5, c); }
+
+/* ---- table installation ------------------------------------------------------------------------------------- */
+void ff_hevcdsp_init_b200(HEVCDSPContext *c, const int bit_depth)
+{
+    (void)bit_depth;
+    c->put_pcm = rec_put_pcm;
+    c->transform_add[0] = rec_add4; c->transform_add[1] = rec_add8; c->transform_add[2] = rec_add16; c->transform_add[3] = rec_add32;
+    c->transform_skip = rec_transform_skip;
+    c->transform_rdpcm = rec_transform_rdpcm;
+    c->idct_4x4_luma = rec_idct_4x4_luma;
+    for (int i = 0; i < 4; i++) { c->idct[i] = rec_idct; c->idct_dc[i] = rec_idct_dc; }
+    c->sao_band_filter = rec_sao_band;
+    c->sao_edge_filter[0] = rec_sao_edge0; c->sao_edge_filter[1] = rec_sao_edge1;
+    for (int i = 0; i < 10; i++)
+        for (int j = 0; j < 2; j++)
+            for (int k = 0; k < 2; k++) {
+                c->put_hevc_qpel[i][j][k] = rec_qpel; c->put_hevc_qpel_uni[i][j][k] = rec_qpel_uni; c->put_hevc_qpel_uni_w[i][j][k] = rec_qpel_uni_w;
+                c->put_hevc_qpel_bi[i][j][k] = rec_qpel_bi; c->put_hevc_qpel_bi_w[i][j][k] = rec_qpel_bi_w;
+                c->put_hevc_epel[i][j][k] = rec_epel; c->put_hevc_epel_uni[i][j][k] = rec_epel_uni; c->put_hevc_epel_uni_w[i][j][k] = rec_epel_uni_w;
+                c->put_hevc_epel_bi[i][j][k] = rec_epel_bi; c->put_hevc_epel_bi_w[i][j][k] = rec_epel_bi_w;
+            }
+    c->hevc_h_loop_filter_luma = rec_h_luma; c->hevc_v_loop_filter_luma = rec_v_luma;
+    c->hevc_h_loop_filter_chroma = rec_h_chroma; c->hevc_v_loop_filter_chroma = rec_v_chroma;
+    c->hevc_h_loop_filter_luma_c = rec_h_luma; c->hevc_v_loop_filter_luma_c = rec_v_luma;
+    c->hevc_h_loop_filter_chroma_c = rec_h_chroma; c->hevc_v_loop_filter_chroma_c = rec_v_chroma;
+}
+
+void ff_hevcpred_init_b200(HEVCPredContext *c, const int bit_depth)
+{
+    (void)bit_depth;
+    c->intra_pred[0] = rec_intra_2; c->intra_pred[1] = rec_intra_3; c->intra_pred[2] = rec_intra_4; c->intra_pred[3] = rec_intra_5;
+    /* pred_planar / pred_dc / pred_angular are only reached through intra_pred: left untouched */
+}
+
+void ff_videodsp_init_b200(VideoDSPContext *c, int bpc)
+{
+    (void)bpc;
+    c->emulated_edge_mc = rec_emulated_edge_mc;
+}
+
+/* ---- frame life cycle ----------------------------------------------------------------------------------------- */
+static int ensure_ctx(const HEVCContext *s)
+{
+    const HEVCSPS *sps = s->sps;
+    if (g.ctx && g.cfg.width == sps->width && g.cfg.height == sps->height && g.cfg.bit_depth == sps->bit_depth && g.cfg.chroma_format_idc == sps->chroma_format_idc)
+        return 0;
+    if (g.ctx) { b200_rec_destroy(g.rec); b200_ctx_destroy(g.ctx); g.ctx = NULL; g.rec = NULL; }
+    memset(&g.cfg, 0, sizeof(g.cfg));
+    const char *dev = getenv("B200_DEVICE");
+    g.cfg.device = dev ? atoi(dev) : 0;
+    g.cfg.width = sps->width; g.cfg.height = sps->height; g.cfg.chroma_format_idc = sps->chroma_format_idc;
+    g.cfg.bit_depth = sps->bit_depth; g.cfg.log2_ctb_size = sps->log2_ctb_size;
+    g.cfg.n_slots = 32;                /* == FF_ARRAY_ELEMS(s->DPB), hevc.h:1207 */
+    g.cfg.n_arenas = 2;
+    int rc = b200_ctx_create(&g.cfg, &g.ctx);
+    if (rc) { fail(rc, b200_last_error(NULL)); return rc; }
+    rc = b200_rec_create(&g.cfg, &g.rec);
+    if (rc) { fail(rc, "b200_rec_create failed"); return rc; }
+    g.bd = sps->bit_depth; g.B = g.bd > 8 ? 2 : 1; g.cfi = sps->chroma_format_idc;
+    for (int p = 0; p < 3; p++) b200_plane_dims(sps->width, sps->height, g.cfi, p, &g.pw[p], &g.ph[p]);
+    return 0;
+}
+
+int b200_frame_begin(HEVCContext *s)
+{
+    if (g.err) return g.err;
+    if (ensure_ctx(s)) return g.err;
+    g.n_reg = 0;
+    for (int i = 0; i < 32; i++) {
+        AVFrame *f = s->DPB[i].frame;
+        if (!f || !f->data[0]) continue;
+        for (int p = 0; p < 3; p++) {
+            RegPlane *r = &g.reg[g.n_reg++];
+            r->base = f->data[p]; r->linesize = f->linesize[p]; r->slot = i; r->plane = p; r->w = g.pw[p]; r->h = g.ph[p];
+        }
+    }
+    g.cur_slot = (int)(s->ref - s->DPB);
+    for (int p = 0; p < 3; p++) { g.cur_base[p] = s->frame->data[p]; g.cur_ls[p] = s->frame->linesize[p]; }
+    g.n_ref = 0; g.pend_ptr = NULL; g.first_tmp = NULL; g.emu[0].buf = g.emu[1].buf = NULL;
+    int rc = b200_rec_begin(g.rec, g.cur_slot, s->poc);
+    if (rc) { fail(rc, "b200_rec_begin failed"); return rc; }
+    g.in_frame = 1;
+    return 0;
+}
+
+int b200_frame_end(HEVCContext *s)
+{
+    (void)s;
+    if (!g.in_frame) return g.err ? g.err : B200_ESTATE;
+    g.in_frame = 0;
+    if (g.err) return g.err;
+    const void *blob; uint64_t n;
+    int rc = b200_rec_set_refs(g.rec, g.ref_slot, g.n_ref);
+    if (!rc) rc = b200_rec_finish(g.rec, &blob, &n);
+    if (!rc) rc = b200_frame_submit(g.ctx, blob, n);
+    if (!rc) rc = b200_sync(g.ctx);          /* the recorder's blob memory is reused by the next picture */
+    if (rc) fail(rc, g.ctx ? b200_last_error(g.ctx) : "frame_end failed");
+    return rc;
+}
+
+int b200_frame_readback(HEVCContext *s, AVFrame *frame)
+{
+    if (g.err) return g.err;
+    int slot = -1;
+    for (int i = 0; i < 32; i++) if (s->DPB[i].frame && s->DPB[i].frame->data[0] == frame->data[0]) slot = i;
+    if (slot < 0) { fail(B200_EINVAL, "readback of a frame that is not in the DPB"); return g.err; }
+    void *planes[3] = { frame->data[0], frame->data[1], frame->data[2] };
+    int64_t strides[3] = { frame->linesize[0], frame->linesize[1], frame->linesize[2] };
+    int rc = b200_slot_readback(g.ctx, slot, planes, strides);
+    if (!rc) rc = b200_sync(g.ctx);
+    if (rc) fail(rc, b200_last_error(g.ctx));
+    return rc;
+}
+
+/* reference pictures that exist only on the host (e.g. produced before the hook was active) */
+int b200_frame_upload_ref(HEVCContext *s, AVFrame *frame)
+{
+    if (ensure_ctx(s)) return g.err;
+    int slot = -1;
+    for (int i = 0; i < 32; i++) if (s->DPB[i].frame && s->DPB[i].frame->data[0] == frame->data[0]) slot = i;
+    if (slot < 0) { fail(B200_EINVAL, "upload of a frame that is not in the DPB"); return g.err; }
+    const void *planes[3] = { frame->data[0], frame->data[1], frame->data[2] };
+    int64_t strides[3] = { frame->linesize[0], frame->linesize[1], frame->linesize[2] };
+    int rc = b200_slot_upload(g.ctx, slot, planes, strides);
+    if (!rc) rc = b200_sync(g.ctx);
+    if (rc) fail(rc, b200_last_error(g.ctx));
+    return rc;
+}
+
+void b200_shim_close(void)
+{
+    if (g.rec) b200_rec_destroy(g.rec);
+    if (g.ctx) b200_ctx_destroy(g.ctx);
+    memset(&g, 0, sizeof(g));
+}

@@ -396,7 +396,8 @@ class FrameSynth:
             ro = a[:, 8]
             assert (ro != -2).all()
             intra["resid_off"] = np.where(ro < 0, W.NO_RESID, ro).astype(np.uint32)
-            intra = intra[W.wavefront_order(intra, self.cfi, self.log2_ctb)]
+            perm, self.stats["intra_levels"] = W.level_order(intra, self.W, self.H, self.cfi)
+            intra = intra[perm]
         mc = np.zeros(len(self.mc), W.mc_dt)
         if self.mc:
             for name in self.mc[0]:

@@ -92,16 +92,17 @@ def split_mc_tiles(recs):
     return np.concatenate(out)
 
 
-def wavefront_order(intra, cfi, log2_ctb):
-    """Permutation that puts decode-order intra records into CTB-wavefront order (key = ctb_x + 2*ctb_y, the
-    WPP dependency order; stable inside a CTB).  Still a topological order of the intra dependencies, but the
-    device's in-order window then spans whole anti-diagonals of CTBs instead of one CTB row.  Same rule as
-    b200_rec_finish()."""
-    hs = np.where((intra["plane"] > 0) & (cfi != 3), 1, 0)
-    vs = np.where((intra["plane"] > 0) & (cfi == 1), 1, 0)
-    cx = (intra["x"].astype(np.int64) << hs) >> log2_ctb
-    cy = (intra["y"].astype(np.int64) << vs) >> log2_ctb
-    return np.lexsort((np.arange(len(intra)), cy, cx + 2 * cy))
+def level_order(intra, width, height, cfi):
+    """Permutation that sorts decode-order intra records by dependency level (stable) -- computed by the same host
+    routine the C recorder uses (b200_intra_level_order in libb200hevc.so; pure host code, no GPU needed)."""
+    from . import _lib
+    lib = _lib.load()
+    intra = np.ascontiguousarray(intra, intra_dt)
+    perm = np.zeros(len(intra), np.uint32)
+    rc = lib.b200_intra_level_order(intra.ctypes.data, len(intra), width, height, cfi, perm.ctypes.data)
+    if rc < 0:
+        raise ValueError(f"b200_intra_level_order failed: {rc}")
+    return perm, rc
 
 
 def build_blob(width, height, cfi, bit_depth, log2_ctb, cur_slot, poc=0, coeff=None, tu=None, intra=None, mc=None,

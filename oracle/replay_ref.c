@@ -20,6 +20,8 @@
 #include "libavcodec/hevcdsp.h"
 #include "libavcodec/hevcpred.h"
 #include "libavcodec/videodsp.h"
+#include "libavcodec/get_bits.h"
+#include <dlfcn.h>
 #include "../include/b200hevc_worklist.h"
 
 extern const uint8_t ff_hevc_pel_weight[65];
@@ -53,6 +55,7 @@ static RefCtx *ref_ctx_new(const B200BlobHeader *h)
     sps->tb_mask = (1 << (h->log2_ctb_size - 2)) - 1;
     sps->min_pu_width = c->W / 4; sps->min_pu_height = c->H / 4; sps->chroma_array_type = c->cfi; sps->pixel_shift = c->bd > 8;
     sps->hshift[1] = sps->hshift[2] = c->cfi != 3; sps->vshift[1] = sps->vshift[2] = c->cfi == 1;
+    sps->bit_depth = c->bd; sps->chroma_format_idc = c->cfi;
     const int tw = sps->tb_mask + 2;
     c->zs = malloc(sizeof(int) * tw * tw);
     for (int i = 0; i < tw * tw; i++) c->zs[i] = -1;     /* every neighbour "earlier in z-scan": the record flags are already final */
@@ -65,6 +68,12 @@ static void ref_ctx_free(RefCtx *c)
 }
 
 typedef struct HostFrame { uint8_t *p[3]; int stride[3]; } HostFrame;
+
+static int cmp_park(const void *a, const void *b)
+{
+    const B200TuRec *x = *(const B200TuRec *const *)a, *y = *(const B200TuRec *const *)b;
+    return x->coeff_off < y->coeff_off ? -1 : x->coeff_off > y->coeff_off;
+}
 
 /* ---- K1: inter, following hevc.c:1641-1949 ------------------------------------------------------ */
 static void replay_mc(RefCtx *c, const B200BlobHeader *hd, const B200McRec *m, HostFrame *cur, HostFrame *dpb)
@@ -170,36 +179,56 @@ static int execute(RefCtx *c, const uint8_t *blob, uint8_t **planes, const int64
     for (uint32_t i = 0; i < h->sec[B200_SEC_MC].count; i++) replay_mc(c, h, &mc[i], cur, dpb);
 
     const int16_t *pool = (const int16_t *)(blob + h->sec[B200_SEC_COEFF].off);
-    int16_t *parked = NULL;
-    if (h->sec[B200_SEC_INTRA].count) parked = malloc(((size_t)h->sec[B200_SEC_COEFF].count + 1024) * 2);
     DECLARE_ALIGNED(32, int16_t, coeffs[32 * 32]);
+    /* residuals of intra TUs are applied right after their prediction, as hls_transform_unit does (hevc.c:1212-1291):
+     * index the parked TU records by pool offset */
+    size_t npark = 0;
+    for (int sidx = B200_SEC_TU4; sidx <= B200_SEC_TU32; sidx++) {
+        const B200TuRec *tu = (const B200TuRec *)(blob + h->sec[sidx].off);
+        for (uint32_t i = 0; i < h->sec[sidx].count; i++) npark += !!(tu[i].flags & B200_TUF_PARK);
+    }
+    const B200TuRec **park = malloc((npark + 1) * sizeof(*park));
+    npark = 0;
     for (int sidx = B200_SEC_TU4; sidx <= B200_SEC_TU32; sidx++) {
         const B200TuRec *tu = (const B200TuRec *)(blob + h->sec[sidx].off);
         for (uint32_t i = 0; i < h->sec[sidx].count; i++) {
             const B200TuRec *t = &tu[i];
+            if (t->flags & B200_TUF_PARK) { park[npark++] = t; continue; }
             const int n = 1 << t->log2, p = t->plane;
-            memcpy(coeffs, pool + t->coeff_off, (size_t)n * n * 2);
             uint8_t *dst = cur->p[p] + (ptrdiff_t)t->y * cur->stride[p] + t->x * B;
-            if (t->kind == B200_TU_PCM) {       /* put_pcm reads a bitstream; the recorder already extracted the samples */
-                for (int y = 0; y < n; y++) for (int x = 0; x < n; x++) { if (B == 2) ((uint16_t *)(dst + y * cur->stride[p]))[x] = coeffs[y * n + x]; else dst[y * cur->stride[p] + x] = (uint8_t)coeffs[y * n + x]; }
+            if (t->kind == B200_TU_PCM) {       /* hls_pcm_sample (hevc.c:1587-1623): put_pcm reads the samples from the bitstream */
+                uint8_t bits[32 * 32 * 2 + 16];
+                GetBitContext gb;
+                memset(bits, 0, sizeof(bits));
+                for (int k = 0, bp = 0; k < n * n; k++)
+                    for (int bit = c->bd - 1; bit >= 0; bit--, bp++)
+                        if ((pool[t->coeff_off + k] >> bit) & 1) bits[bp >> 3] |= 0x80 >> (bp & 7);
+                init_get_bits(&gb, bits, n * n * c->bd);
+                d->put_pcm(dst, cur->stride[p], n, n, &gb, c->bd);
                 continue;
             }
+            memcpy(coeffs, pool + t->coeff_off, (size_t)n * n * 2);
             replay_tu_residual(c, t, coeffs);
-            if (t->flags & B200_TUF_PARK) memcpy(parked + t->coeff_off, coeffs, (size_t)n * n * 2);
-            else d->transform_add[t->log2 - 2](dst, coeffs, cur->stride[p]);
+            d->transform_add[t->log2 - 2](dst, coeffs, cur->stride[p]);
         }
     }
+    qsort(park, npark, sizeof(*park), cmp_park);
     const B200IntraRec *ir = (const B200IntraRec *)(blob + h->sec[B200_SEC_INTRA].off);
     for (uint32_t i = 0; i < h->sec[B200_SEC_INTRA].count; i++) {
         const B200IntraRec *r = &ir[i];
         replay_intra(c, r);
         if (r->resid_off != B200_NO_RESID) {
+            size_t lo = 0, hi = npark;
+            while (lo + 1 < hi) { size_t mid = (lo + hi) / 2; if (park[mid]->coeff_off <= r->resid_off) lo = mid; else hi = mid; }
+            const B200TuRec *t = park[lo];
+            if (!npark || t->coeff_off != r->resid_off) { free(park); return -5; }
             const int n = 1 << r->log2;
-            memcpy(coeffs, parked + r->resid_off, (size_t)n * n * 2);
+            memcpy(coeffs, pool + t->coeff_off, (size_t)n * n * 2);
+            replay_tu_residual(c, t, coeffs);
             d->transform_add[r->log2 - 2](cur->p[r->plane] + (ptrdiff_t)r->y * cur->stride[r->plane] + r->x * B, coeffs, cur->stride[r->plane]);
         }
     }
-    free(parked);
+    free(park);
 
     if (h->sec[B200_SEC_DBK].count) {              /* every vertical edge of the picture, then every horizontal one */
         B200DbkLayout L;
@@ -263,6 +292,51 @@ int ref_execute_blob(const uint8_t *blob, uint8_t **planes, const int64_t *strid
     if (h->magic != B200_BLOB_MAGIC || h->version != B200_BLOB_VERSION) return -1;
     RefCtx *c = ref_ctx_new(h);
     int rc = execute(c, blob, planes, strides, n_slots);
+    ref_ctx_free(c);
+    return rc;
+}
+
+/* ---- the same call sequence through the B200 drop-in: the tables are re-populated by libb200hevc_shim.so
+ * (ff_hevcdsp_init_b200 & co.), the calls are recorded, b200_frame_end runs the GPU, b200_frame_readback returns
+ * the picture.  This is the reference-side half of INTEGRATION.md exercised without a bitstream. */
+int ref_execute_blob_b200(const uint8_t *blob, uint8_t **planes, const int64_t *strides, int n_slots, const char *shim_path, char *err, int errlen)
+{
+    const B200BlobHeader *h = (const B200BlobHeader *)blob;
+    if (h->magic != B200_BLOB_MAGIC || h->version != B200_BLOB_VERSION || n_slots > 32 || h->cur_slot >= n_slots) return -1;
+    void *so = dlopen(shim_path, RTLD_NOW | RTLD_GLOBAL);
+    if (!so) { snprintf(err, errlen, "dlopen: %s", dlerror()); return -10; }
+    void (*init_dsp)(HEVCDSPContext *, int) = dlsym(so, "ff_hevcdsp_init_b200");
+    void (*init_pred)(HEVCPredContext *, int) = dlsym(so, "ff_hevcpred_init_b200");
+    void (*init_vdsp)(VideoDSPContext *, int) = dlsym(so, "ff_videodsp_init_b200");
+    int (*fbegin)(HEVCContext *) = dlsym(so, "b200_frame_begin");
+    int (*fend)(HEVCContext *) = dlsym(so, "b200_frame_end");
+    int (*fread)(HEVCContext *, AVFrame *) = dlsym(so, "b200_frame_readback");
+    int (*fup)(HEVCContext *, AVFrame *) = dlsym(so, "b200_frame_upload_ref");
+    const char *(*ferr)(void) = dlsym(so, "b200_shim_error");
+    if (!init_dsp || !init_pred || !init_vdsp || !fbegin || !fend || !fread || !fup || !ferr) { snprintf(err, errlen, "shim lacks an entry point"); return -11; }
+    RefCtx *c = ref_ctx_new(h);
+    init_dsp(&c->s->hevcdsp, c->bd);          /* exactly what ff_hevc_dsp_init would do last (hevcdsp.c:1326) */
+    init_pred(&c->s->hpc, c->bd);
+    init_vdsp(&c->vdsp, c->bd);
+    AVFrame *fr = calloc(n_slots, sizeof(AVFrame));
+    for (int s = 0; s < n_slots; s++) {
+        for (int p = 0; p < 3; p++) { fr[s].data[p] = planes[3 * s + p]; fr[s].linesize[p] = (int)strides[3 * s + p]; }
+        c->s->DPB[s].frame = &fr[s];
+    }
+    c->s->ref = &c->s->DPB[h->cur_slot];
+    c->s->poc = h->poc;
+    AVFrame *keep = c->fr;
+    c->s->frame = &fr[h->cur_slot];
+    c->fr = &fr[h->cur_slot];
+    int rc = 0;
+    for (int i = 0; i < h->n_ref && !rc; i++) rc = fup(c->s, &fr[h->ref_slot[i]]);
+    if (!rc) rc = fbegin(c->s);
+    if (!rc) rc = execute(c, blob, planes, strides, n_slots);
+    if (!rc) rc = fend(c->s); else fend(c->s);
+    if (!rc) rc = fread(c->s, &fr[h->cur_slot]);
+    if (rc) snprintf(err, errlen, "%s", ferr());
+    c->fr = keep;
+    free(fr);
     ref_ctx_free(c);
     return rc;
 }

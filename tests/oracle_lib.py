@@ -83,6 +83,24 @@ def ref_execute(blob, dpb):
     return planes[int(blob[23])]
 
 
+SHIM_SO = os.path.join(ROOT, "openhevc_b200", "libb200hevc_shim.so")
+
+
+def ref_execute_b200(blob, dpb):
+    """The reference-side call sequence (oracle/replay_ref.c) issued through the B200 drop-in tables
+    (libb200hevc_shim.so -> recorder -> GPU -> readback).  Needs a GPU."""
+    blob = np.ascontiguousarray(blob, np.uint8)
+    planes, ptrs, strides = _native(dpb, int(blob[21]))
+    L = ref_lib()
+    L.ref_execute_blob_b200.restype = C.c_int
+    L.ref_execute_blob_b200.argtypes = [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_int64), C.c_int, C.c_char_p, C.c_char_p, C.c_int]
+    err = C.create_string_buffer(512)
+    rc = L.ref_execute_blob_b200(blob.ctypes.data, ptrs, strides, len(dpb), SHIM_SO.encode(), err, 512)
+    if rc:
+        raise RuntimeError(f"ref_execute_blob_b200 failed: {rc}: {err.value.decode()}")
+    return planes[int(blob[23])]
+
+
 def ref_bench(blobs, dpb, n_threads, iters):
     """seconds of wall time for n_threads x iters pictures on the reference C path"""
     blobs = [np.ascontiguousarray(b, np.uint8) for b in blobs]
