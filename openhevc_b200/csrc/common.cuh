@@ -13,11 +13,23 @@ struct FrameDesc {
     PlaneDesc p[3];
 };
 struct RefTable {
-    uint8_t slot[16];   // B200BlobHeader.ref_slot (possibly overridden at execute time)
+    uint64_t w[2];      // B200BlobHeader.ref_slot[16] packed little-endian (possibly overridden at execute time)
 };
 
 __device__ __forceinline__ int clip3i(int v, int lo, int hi) { return min(max(v, lo), hi); }
 __device__ __forceinline__ int clip16i(int v) { return min(max(v, -32768), 32767); }
+
+// plane descriptor of a kernel-parameter FrameDesc by register selects: indexing the parameter struct with a runtime
+// plane number would make the compiler copy it to local memory (an L2 round trip per access for a cold warp)
+__device__ __forceinline__ PlaneDesc plane_of(const FrameDesc &f, int plane)
+{
+    PlaneDesc d;
+    d.base = plane == 0 ? f.p[0].base : plane == 1 ? f.p[1].base : f.p[2].base;
+    d.pitch = plane == 0 ? f.p[0].pitch : plane == 1 ? f.p[1].pitch : f.p[2].pitch;
+    d.w = plane == 0 ? f.p[0].w : plane == 1 ? f.p[1].w : f.p[2].w;
+    d.h = plane == 0 ? f.p[0].h : plane == 1 ? f.p[1].h : f.p[2].h;
+    return d;
+}
 
 template <typename PIX>
 __device__ __forceinline__ PIX *px_ptr(const PlaneDesc &p, int x, int y)
@@ -33,4 +45,5 @@ int launch_intra(cudaStream_t st, const B200IntraRec *recs, int count, const int
 int launch_deblock(cudaStream_t st, const uint16_t *grid, const B200DbkLayout &L, const FrameDesc &cur, int bd);
 int launch_sao(cudaStream_t st, const B200SaoRec *grid, const FrameDesc &src, const FrameDesc &dst, int bd,
                int log2_ctb, int ctb_w, int ctb_h, int chroma_format_idc);
+int set_intra_trace(unsigned long long *p);
 int launch_fill(cudaStream_t st, const FrameDesc &f, int bd, int value);

@@ -193,7 +193,7 @@ __global__ void __launch_bounds__(128) k_residual(const B200TuRec *__restrict__ 
 #pragma unroll
         for (int y = 0; y < N; y++) pk[y * N + col] = (int16_t)tile[y * (N + 1) + col];
     } else {
-        const PlaneDesc pd = f.p[rec.plane];
+        const PlaneDesc pd = plane_of(f, rec.plane);
         const int maxv = (1 << bd) - 1;
         const bool pcm = kind == B200_TU_PCM;
 #pragma unroll
@@ -269,6 +269,12 @@ __device__ __forceinline__ void mc_list(const PlaneDesc &rp, int sx, int sy, int
     }
 }
 
+__device__ __forceinline__ int ref_slot_of(const RefTable &rt, int i)
+{
+    const uint64_t w = (i & 8) ? rt.w[1] : rt.w[0];      // no runtime indexing of the parameter struct (would go through local memory)
+    return (int)((w >> (8 * (i & 7))) & 0xff);
+}
+
 template <typename PIX>
 __global__ void __launch_bounds__(256) k_mc(const B200McRec *__restrict__ recs, int count, FrameDesc cur, const FrameDesc *__restrict__ dpb, RefTable rt, int bd)
 {
@@ -288,16 +294,16 @@ __global__ void __launch_bounds__(256) k_mc(const B200McRec *__restrict__ recs, 
     const bool chroma = m.flags & B200_MCF_CHROMA, bi = m.flags & B200_MCF_BI, weighted = m.flags & B200_MCF_WEIGHTED;
     int v0[8], v1[8];
     {
-        const PlaneDesc rp = dpb[rt.slot[m.ref0 & 15]].p[plane];
+        const PlaneDesc rp = dpb[ref_slot_of(rt, m.ref0)].p[plane];
         if (chroma) mc_list<PIX, 4>(rp, m.sx0, m.sy0, m.frac0 & 15, m.frac0 >> 4, w, h, bd, lane, win_s[warp], tmp_s[warp], v0);
         else        mc_list<PIX, 8>(rp, m.sx0, m.sy0, m.frac0 & 15, m.frac0 >> 4, w, h, bd, lane, win_s[warp], tmp_s[warp], v0);
     }
     if (bi) {
-        const PlaneDesc rp = dpb[rt.slot[m.ref1 & 15]].p[plane];
+        const PlaneDesc rp = dpb[ref_slot_of(rt, m.ref1)].p[plane];
         if (chroma) mc_list<PIX, 4>(rp, m.sx1, m.sy1, m.frac1 & 15, m.frac1 >> 4, w, h, bd, lane, win_s[warp], tmp_s[warp], v1);
         else        mc_list<PIX, 8>(rp, m.sx1, m.sy1, m.frac1 & 15, m.frac1 >> 4, w, h, bd, lane, win_s[warp], tmp_s[warp], v1);
     }
-    const PlaneDesc dp = cur.p[plane];
+    const PlaneDesc dp = plane_of(cur, plane);
     const int shift = 14 - bd, maxv = (1 << bd) - 1, n = w * h;
     const bool fullpel0 = !(m.frac0 & 15) && !(m.frac0 >> 4);
 #pragma unroll
@@ -335,6 +341,20 @@ __device__ __forceinline__ uint32_t ld_acquire(const uint32_t *p)
     asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
     return v;
 }
+// debug: per-TU timestamps (ns, %globaltimer) [grab, deps ready, gathered, predicted, fenced, published]; null = off
+__device__ unsigned long long *g_intra_trace = nullptr;
+__device__ __forceinline__ unsigned long long gtime() { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; }
+#define TRACE(slot) do { if (tr && lane == 0) tr[slot] = gtime(); } while (0)
+int set_intra_trace(unsigned long long *p) { return (int)cudaMemcpyToSymbol(g_intra_trace, &p, sizeof(p)); }
+
+// Message passing between intra TUs costs one light fence on the producer side and none on the consumer side:
+//  producer: pixel stores; fence.acq_rel.gpu (MEMBAR.ALL.GPU -- not __threadfence(), which is fence.sc + an L1
+//            invalidate, ~2 us on B200); relaxed flag store.
+//  consumer: relaxed flag polls at L2; the neighbour loads that follow are issued after the flag-dependent branch
+//            and bypass L1 (ld.global.cg), so they are served by L2 after the producer's stores became visible there.
+__device__ __forceinline__ void fence_release_gpu() { asm volatile("fence.acq_rel.gpu;" ::: "memory"); }
+__device__ __forceinline__ void consumer_barrier() { asm volatile("" ::: "memory"); }
+
 __device__ __forceinline__ uint32_t ld_relaxed(const uint32_t *p)
 {
     uint32_t v;
@@ -350,6 +370,16 @@ __device__ __forceinline__ void st_release(uint32_t *p, uint32_t v)
     asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
 
+__device__ __forceinline__ B200IntraRec decode_intra(const int4 raw)
+{
+    B200IntraRec r;
+    r.x = (uint16_t)(raw.x & 0xffff); r.y = (uint16_t)((unsigned)raw.x >> 16);
+    r.plane = (uint8_t)(raw.y & 0xff); r.log2 = (uint8_t)((raw.y >> 8) & 0xff); r.mode = (uint8_t)((raw.y >> 16) & 0xff); r.flags = (uint8_t)((unsigned)raw.y >> 24);
+    r.top_right_size = (uint8_t)(raw.z & 0xff); r.bottom_left_size = (uint8_t)((raw.z >> 8) & 0xff); r.pad[0] = r.pad[1] = 0;
+    r.resid_off = (uint32_t)raw.w;
+    return r;
+}
+
 struct IntraFlags {
     uint32_t *f[3];
     int stride[3];
@@ -359,23 +389,42 @@ __global__ void k_intra_prepass(const B200IntraRec *__restrict__ recs, int count
 {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= count) return;
-    const int4 raw = __ldg(reinterpret_cast<const int4 *>(recs + i));
-    B200IntraRec r;
-    memcpy(&r, &raw, 16);
+    const B200IntraRec r = decode_intra(__ldg(reinterpret_cast<const int4 *>(recs + i)));
     const int u = 1 << (r.log2 - 2), ux = r.x >> 2, uy = r.y >> 2;
-    uint32_t *f = fl.f[r.plane];
-    const int fs = fl.stride[r.plane];
+    uint32_t *f = r.plane == 0 ? fl.f[0] : r.plane == 1 ? fl.f[1] : fl.f[2];
+    const int fs = r.plane == 0 ? fl.stride[0] : r.plane == 1 ? fl.stride[1] : fl.stride[2];
     for (int y = 0; y < u; y++)
         for (int x = 0; x < u; x++) f[(uy + y) * fs + ux + x] = 0;
 }
 
+
+
+// Wait until the flag this lane watches (nullptr = none) is set, for every lane of the warp.  The loop is executed by
+// all 32 lanes with a uniform exit (vote), so the warp leaves it CONVERGED: a per-lane `while (flag == 0)` lets the
+// lanes exit one by one and the rest of the TU then runs as several diverged fragments (every instruction issued
+// once per fragment, shuffles through the BRA.DIV slow path) -- measured 5100 vs ~700 cycles for a 4x4 TU.
+// A malformed list (dependency cycle) must not hang the GPU: give up after ~0.3 s and latch an error in counter[1].
+__device__ __forceinline__ void wait_units(const uint32_t *p, uint32_t *counter)
+{
+    bool ready = p == nullptr;
+    uint32_t spins = 0;
+    for (;;) {
+        if (!ready) ready = ld_relaxed(p) != 0;
+        if (__all_sync(0xffffffffu, ready)) break;
+        __nanosleep(20);
+        if ((++spins & 1023) == 0) {
+            const bool abort = spins > (1u << 21) || ld_relaxed(counter + 1) != 0;
+            if (__any_sync(0xffffffffu, abort)) { st_release(counter + 1, 1u); break; }
+        }
+    }
+}
 
 // Fast path for 4x4 / 8x8 intra TUs (the bulk of every dependency chain): the <= 33 reference samples live one per
 // lane in two registers (fT: lane k = top[k-1], fL: lane k = left[k]); gathering, substitution, [1 2 1] smoothing and
 // the predictors use warp shuffles only -- no shared memory, no loops -- so one wavefront step is ~150 instructions.
 template <typename PIX>
 __device__ __forceinline__ void intra_small(const B200IntraRec &r, const int16_t *__restrict__ pool, const PlaneDesc &pd, int bd,
-                                            uint32_t *flg, int fs, uint32_t *counter, int lane)
+                                            uint32_t *flg, int fs, uint32_t *counter, int lane, unsigned long long *tr)
 {
     const unsigned FULL = 0xffffffffu;
     const int n = 1 << r.log2, n2 = 2 * n, x0 = r.x, y0 = r.y, maxv = (1 << bd) - 1;
@@ -393,17 +442,11 @@ __device__ __forceinline__ void intra_small(const B200IntraRec &r, const int16_t
         if (lane == 0) { if (ul) { ux = (x0 - 1) >> 2; uy = (y0 - 1) >> 2; } }
         else if (lane <= 4) { const int o = 4 * (lane - 1); if ((o < n && up) || (o >= n && o < n2 && ur && o < n + trs)) { ux = (x0 + o) >> 2; uy = (y0 - 1) >> 2; } }
         else if (lane <= 8) { const int o = 4 * (lane - 5); if ((o < n && lf) || (o >= n && o < n2 && bl && o < n + bls)) { ux = (x0 - 1) >> 2; uy = (y0 + o) >> 2; } }
-        if (ux >= 0) {
-            const uint32_t *p = flg + uy * fs + ux;
-            uint32_t spins = 0;
-            while (ld_relaxed(p) == 0) {
-                __nanosleep(20);
-                if ((++spins & 1023) == 0 && (spins > (1u << 21) || ld_relaxed(counter + 1))) { st_release(counter + 1, 1u); break; }
-            }
-        }
+        wait_units(ux >= 0 ? flg + uy * fs + ux : nullptr, counter);
     }
-    __threadfence();
+    consumer_barrier();
     __syncwarp();
+    TRACE(1);
     // ---- gather: lanes 0..2n -> top[lane-1], lanes 0..2n-1 -> left[lane] ----
     int gT = 0, gL = 0;
     {
@@ -415,6 +458,8 @@ __device__ __forceinline__ void intra_small(const B200IntraRec &r, const int16_t
         else if (lane < n2) { if (bl) gL = __ldcg(px_ptr<PIX>(pd, x0 - 1, y0 + min(lane, n + bls - 1))); }
     }
     // ---- substitution (hevcpred_template.c:250-286), closed form on broadcast scalars ----
+    TRACE(2);
+    if (tr && lane == 0) tr[6] = clock64();
     const int g_corner = __shfl_sync(FULL, gT, 0), g_top0 = __shfl_sync(FULL, gT, 1), g_topn1 = __shfl_sync(FULL, gT, n), g_topn = __shfl_sync(FULL, gT, n + 1);
     const int g_left0 = __shfl_sync(FULL, gL, 0), g_leftn1 = __shfl_sync(FULL, gL, n - 1), g_leftn = __shfl_sync(FULL, gL, n);
     const int sub = lf ? g_leftn1 : ul ? g_corner : up ? g_top0 : ur ? g_topn : (1 << (bd - 1));
@@ -498,13 +543,17 @@ __device__ __forceinline__ void intra_small(const B200IntraRec &r, const int16_t
 #undef TOPS
 #undef LEFTS
     // ---- publish ----
-    __threadfence();
+    TRACE(3);
+    if (tr && lane == 0) tr[7] = clock64();
+    fence_release_gpu();
     __syncwarp();
+    TRACE(4);
     {
         const int u = n >> 2, ux = x0 >> 2, uy = y0 >> 2;
         if (lane < u * u) st_relaxed(flg + (uy + lane / u) * fs + ux + (lane % u), 1u);
     }
     __syncwarp();
+    TRACE(5);
 }
 
 template <typename PIX>
@@ -521,26 +570,27 @@ __global__ void __launch_bounds__(128) k_intra(const B200IntraRec *__restrict__ 
         if (lane == 0) idx = atomicAdd(counter, 1u);
         idx = __shfl_sync(0xffffffffu, idx, 0);
         if (idx >= count) break;
-        B200IntraRec r;
-        {
-            const int4 raw = __ldg(reinterpret_cast<const int4 *>(recs + idx));
-            memcpy(&r, &raw, 16);
-        }
+        const B200IntraRec r = decode_intra(__ldg(reinterpret_cast<const int4 *>(recs + idx)));
         if (r.log2 <= 3) {
-            intra_small<PIX>(r, pool, f.p[r.plane], bd, fl.f[r.plane], fl.stride[r.plane], counter, lane);
+            unsigned long long *tr = g_intra_trace ? g_intra_trace + 8ull * idx : nullptr;
+            TRACE(0);
+            intra_small<PIX>(r, pool, plane_of(f, r.plane), bd, r.plane == 0 ? fl.f[0] : r.plane == 1 ? fl.f[1] : fl.f[2],
+                             r.plane == 0 ? fl.stride[0] : r.plane == 1 ? fl.stride[1] : fl.stride[2], counter, lane, tr);
             continue;
         }
         const int n = 1 << r.log2, n2 = 2 * n, x0 = r.x, y0 = r.y;
-        const PlaneDesc pd = f.p[r.plane];
+        const PlaneDesc pd = plane_of(f, r.plane);
         const bool ul = r.flags & B200_INF_UP_LEFT, up = r.flags & B200_INF_UP, ur = r.flags & B200_INF_UP_RIGHT;
         const bool lf = r.flags & B200_INF_LEFT, bl = r.flags & B200_INF_BOTTOM_LEFT;
         const int trs = r.top_right_size, bls = r.bottom_left_size;
-        uint32_t *flg = fl.f[r.plane];
-        const int fs = fl.stride[r.plane];
+        uint32_t *flg = r.plane == 0 ? fl.f[0] : r.plane == 1 ? fl.f[1] : fl.f[2];
+        const int fs = r.plane == 0 ? fl.stride[0] : r.plane == 1 ? fl.stride[1] : fl.stride[2];
         // ---- wait for the neighbours this TU reads ----
-        for (int k = lane; k < 33; k += 32) {
+        for (int it = 0; it < 2; it++) {            // every lane runs both rounds: wait_units() votes warp-wide
+            const int k = lane + 32 * it;
             int ux = -1, uy = -1;
-            if (k == 0) { if (ul) { ux = (x0 - 1) >> 2; uy = (y0 - 1) >> 2; } }
+            if (k >= 33) { }
+            else if (k == 0) { if (ul) { ux = (x0 - 1) >> 2; uy = (y0 - 1) >> 2; } }
             else if (k <= 16) {
                 const int o = 4 * (k - 1);
                 if ((o < n && up) || (o >= n && ur && o < n + trs)) { ux = (x0 + o) >> 2; uy = (y0 - 1) >> 2; }
@@ -548,17 +598,9 @@ __global__ void __launch_bounds__(128) k_intra(const B200IntraRec *__restrict__ 
                 const int o = 4 * (k - 17);
                 if ((o < n && lf) || (o >= n && bl && o < n + bls)) { ux = (x0 - 1) >> 2; uy = (y0 + o) >> 2; }
             }
-            if (ux >= 0) {
-                // a malformed list (dependency on a later TU) must not hang the GPU: give up after ~0.25 s and latch an error
-                const uint32_t *p = flg + uy * fs + ux;
-                uint32_t spins = 0;
-                while (ld_relaxed(p) == 0) {       // relaxed polls; ONE acquire fence after the wait (below)
-                    __nanosleep(20);
-                    if ((++spins & 1023) == 0 && (spins > (1u << 21) || ld_relaxed(counter + 1))) { st_release(counter + 1, 1u); break; }
-                }
-            }
+            wait_units(ux >= 0 ? flg + uy * fs + ux : nullptr, counter);
         }
-        __threadfence();      // acquire side: orders the flag reads above before the neighbour loads below
+        consumer_barrier();
         __syncwarp();
         // ---- gather (L2 loads: neighbours were written by other SMs) ----
         int *gt = s_g[warp][0], *gl = s_g[warp][1];
@@ -665,8 +707,8 @@ __global__ void __launch_bounds__(128) k_intra(const B200IntraRec *__restrict__ 
             *px_ptr<PIX>(pd, x0 + x, y0 + y) = (PIX)v;
         }
         // ---- publish ----
-        // message passing with one fence per side: every lane fences its own pixel stores, then relaxed flag stores
-        __threadfence();
+        // every lane fences its own pixel stores, then relaxed flag stores
+        fence_release_gpu();
         __syncwarp();
         {
             const int u = n >> 2, ux = x0 >> 2, uy = y0 >> 2;
@@ -741,7 +783,7 @@ template <typename PIX>
 __global__ void __launch_bounds__(256) k_deblock(const uint16_t *__restrict__ grid, B200DbkLayout L, FrameDesc f, int bd)
 {
     const int plane = blockIdx.z;
-    const PlaneDesc pd = f.p[plane];
+    const PlaneDesc pd = plane_of(f, plane);
     const int gx0 = DBK_TW * blockIdx.x - 4, gy0 = DBK_TH * blockIdx.y - 4;
     if (gx0 >= pd.w || gy0 >= pd.h) return;
     __shared__ uint16_t t[DBK_TH][DBK_PITCH];
@@ -816,7 +858,7 @@ __global__ void __launch_bounds__(256) k_sao(const B200SaoRec *__restrict__ grid
                                              int log2_ctb, int ctb_w, int ctb_h, int cfi)
 {
     const int plane = blockIdx.z, cx = blockIdx.x, cy = blockIdx.y;
-    const PlaneDesc sp = src.p[plane], dp = dst.p[plane];
+    const PlaneDesc sp = plane_of(src, plane), dp = plane_of(dst, plane);
     const int hs = plane && cfi != 3, vs = plane && cfi == 1;
     const int x0 = (cx << log2_ctb) >> hs, y0 = (cy << log2_ctb) >> vs;
     const int w = min((1 << log2_ctb) >> hs, sp.w - x0), h = min((1 << log2_ctb) >> vs, sp.h - y0);
@@ -830,7 +872,7 @@ __global__ void __launch_bounds__(256) k_sao(const B200SaoRec *__restrict__ grid
         t[r][c] = *px_ptr<PIX>(sp, gx, gy);
     }
     __syncthreads();
-    const B200SaoRec s = s_rec;
+    const B200SaoRec &s = s_rec;
     const int maxv = (1 << bd) - 1;
     const int cls = s.param;
     const bool b_l = s.borders & 1, b_t = s.borders & 2, b_r = s.borders & 4, b_b = s.borders & 8;
@@ -877,7 +919,7 @@ template <typename PIX>
 __global__ void k_fill(FrameDesc f, int value)
 {
     const int plane = blockIdx.z;
-    const PlaneDesc pd = f.p[plane];
+    const PlaneDesc pd = plane_of(f, plane);
     const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
     if (x < pd.w && y < pd.h) *px_ptr<PIX>(pd, x, y) = (PIX)value;
 }
