@@ -104,7 +104,7 @@ def run_reference(args, wl, rank):
     import oracle_lib
     from openhevc_b200.synth import smooth_frame
     if oracle_lib.ref_lib() is None:
-        print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/libreplay_ref.so missing (reference build not shipped)"}))
+        print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/libreplay_ref.so missing (reference build not shipped)"}), file=_REAL_STDOUT, flush=True)
         return
     blobs, _ = make_blobs(wl)
     mix = stream_mix()
@@ -130,10 +130,19 @@ def run_reference(args, wl, rank):
             "cpu_baseline": {"value": fps, "unit": UNIT, "cores": threads, "kind": "reference",
                              "sample": f"{n} pictures of the bench stream mix, {threads} threads x {it} pictures, reference C tables (-O3 -fno-tree-vectorize, no asm)"},
             "e2e": {"value": fps, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(line))
+    print(json.dumps(line), file=_REAL_STDOUT, flush=True)
+
+
+_REAL_STDOUT = sys.stdout
 
 
 def main():
+    # keep stdout clean for the ONE JSON line: libraries (NCCL banner, ...) write to fd 1; everything but the final
+    # line goes to stderr
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=16, help="GOPs (8 pictures) per rank in the timed region")
@@ -299,7 +308,7 @@ def main():
                         "mpixels_per_s": e2e_fps * wl["width"] * wl["height"] / 1e6},
                 "roofline": roofline, "cpu_baseline": cpu,
                 "nccl_bcast_bytes_per_step": int(slot_bytes) if world > 1 else 0}
-        print(json.dumps(line))
+        print(json.dumps(line), file=_REAL_STDOUT, flush=True)
     eng.close()
     if world > 1:
         dist.destroy_process_group()

@@ -210,64 +210,8 @@ __global__ void __launch_bounds__(128) k_residual(const B200TuRec *__restrict__ 
 // Reference window staged in shared memory with clamped addressing (== emulated_edge_mc),
 // separable FIR with the 14-bit intermediate of the reference.
 // --------------------------------------------------------------------------------------------
-#define MC_WIN_MAX 608
-#define MC_TMP_MAX 512
-
-template <typename PIX, int TAPS>
-__device__ __forceinline__ void mc_list(const PlaneDesc &rp, int sx, int sy, int mx, int my, int w, int h, int bd, int lane,
-                                        uint16_t *win, int16_t *tmp, int (&val)[8])
-{
-    constexpr int BEFORE = TAPS == 8 ? 3 : 1;
-    const int8_t *fx = TAPS == 8 ? c_qpel[mx] : c_epel[mx];
-    const int8_t *fy = TAPS == 8 ? c_qpel[my] : c_epel[my];
-    const int cols = w + (mx ? TAPS - 1 : 0), rows = h + (my ? TAPS - 1 : 0);
-    const int ox = sx - (mx ? BEFORE : 0), oy = sy - (my ? BEFORE : 0);
-    __syncwarp();
-    for (int i = lane; i < rows * cols; i += 32) {
-        const int r = i / cols, cc = i - r * cols;
-        const int x = clip3i(ox + cc, 0, rp.w - 1), y = clip3i(oy + r, 0, rp.h - 1);
-        win[i] = __ldg(px_ptr<PIX>(rp, x, y));
-    }
-    __syncwarp();
-    if (mx && my) {
-        for (int i = lane; i < rows * w; i += 32) {
-            const int r = i / w, x = i - r * w;
-            int acc = 0;
-#pragma unroll
-            for (int k = 0; k < TAPS; k++) acc += fx[k] * win[r * cols + x + k];
-            tmp[i] = (int16_t)(acc >> (bd - 8));
-        }
-        __syncwarp();
-    }
-    const int n = w * h;
-#pragma unroll
-    for (int k = 0; k < 8; k++) {
-        const int i = lane + 32 * k;
-        int out = 0;
-        if (i < n) {
-            const int y = i / w, x = i - y * w;
-            if (mx && my) {
-                int acc = 0;
-#pragma unroll
-                for (int j = 0; j < TAPS; j++) acc += fy[j] * tmp[(y + j) * w + x];
-                out = acc >> 6;
-            } else if (mx) {
-                int acc = 0;
-#pragma unroll
-                for (int j = 0; j < TAPS; j++) acc += fx[j] * win[y * cols + x + j];
-                out = acc >> (bd - 8);
-            } else if (my) {
-                int acc = 0;
-#pragma unroll
-                for (int j = 0; j < TAPS; j++) acc += fy[j] * win[(y + j) * cols + x];
-                out = acc >> (bd - 8);
-            } else {
-                out = win[y * cols + x] << (14 - bd);
-            }
-        }
-        val[k] = out;
-    }
-}
+#define MC_WIN_MAX 640      // (32+7+1) x 15 = 600, (16+7+1) x 23 = 552, + slack for padded reads
+#define MC_TMP_MAX 512      // 15 x 32, 23 x 16
 
 __device__ __forceinline__ int ref_slot_of(const RefTable &rt, int i)
 {
@@ -275,58 +219,175 @@ __device__ __forceinline__ int ref_slot_of(const RefTable &rt, int i)
     return (int)((w >> (8 * (i & 7))) & 0xff);
 }
 
+struct McGeom {
+    int w, h;
+    int wsh, parts, rows_per;   // stage B: lane = column (1 << wsh per row group), `parts` row groups of rows_per rows
+    int wpad, lsh, q;           // stage A: 4 outputs per lane, q quads per row, (1 << lsh) lanes per row
+};
+
+// One reference list of one tile: fills val[j] (j < rows_per) with the 14-bit intermediate of sample
+// (x = lane & (wpw-1), y = part * rows_per + j), exactly the value put_hevc_{q,e}pel* would hold.
+template <typename PIX, int TAPS>
+__device__ __forceinline__ void mc_list(const PlaneDesc &rp, int sx, int sy, int mx, int my, const McGeom &g, int bd, int lane,
+                                        uint16_t *win, int16_t *tmp, int (&val)[8])
+{
+    constexpr int BEFORE = TAPS == 8 ? 3 : 1;
+    const int w = g.w, h = g.h;
+    const int C = w + (mx ? TAPS - 1 : 0), R = h + (my ? TAPS - 1 : 0);
+    const int ox = sx - (mx ? BEFORE : 0), oy = sy - (my ? BEFORE : 0);
+    const int skew = ox & 1, ax = ox - skew;               // window origin aligned down to an even sample
+    const int np = (C + skew + 1) >> 1, Ws = 2 * np;        // sample pairs per row, shared-memory row stride
+    __syncwarp();
+    if (ax >= 0 && ax + Ws <= rp.w && oy >= 0 && oy + R <= rp.h) {
+        // interior: one 2-sample load per lane, 1 or 2 rows per pass, no clamping
+        const int two = np <= 16;
+        const int pi = two ? (lane & 15) : lane, rsub = two ? (lane >> 4) : 0, rstep = two ? 2 : 1;
+        if (pi < np) {
+            const uint8_t *src = rp.base + (size_t)(oy + rsub) * rp.pitch + (size_t)(ax + 2 * pi) * sizeof(PIX);
+            uint32_t *dst = reinterpret_cast<uint32_t *>(win) + rsub * np + pi;
+            for (int r = rsub; r < R; r += rstep) {
+                uint32_t v;
+                if (sizeof(PIX) == 2) v = __ldg(reinterpret_cast<const uint32_t *>(src));
+                else { const uint32_t t = __ldg(reinterpret_cast<const uint16_t *>(src)); v = (t & 0xff) | ((t & 0xff00) << 8); }
+                *dst = v;
+                src += (size_t)rstep * rp.pitch; dst += rstep * np;
+            }
+        }
+    } else {
+        // window hangs over the picture border: clamp sample by sample (== emulated_edge_mc)
+        for (int i = lane; i < R * Ws; i += 32) {
+            const int r = i / Ws, cc = i - r * Ws;
+            const int x = clip3i(ax + cc, 0, rp.w - 1), y = clip3i(oy + r, 0, rp.h - 1);
+            win[i] = __ldg(px_ptr<PIX>(rp, x, y));
+        }
+    }
+    __syncwarp();
+    const int8_t *fxp = TAPS == 8 ? c_qpel[mx] : c_epel[mx];
+    const int8_t *fyp = TAPS == 8 ? c_qpel[my] : c_epel[my];
+    if (mx) {
+        // stage A: horizontal FIR, 4 outputs per lane, rows_per_pass = 32 >> lsh
+        int fx[TAPS];
+#pragma unroll
+        for (int k = 0; k < TAPS; k++) fx[k] = fxp[k];
+        const int qi = lane & ((1 << g.lsh) - 1), rstep = 32 >> g.lsh;
+        if (qi < g.q) {
+            const int sh = bd - 8;
+            for (int r = lane >> g.lsh; r < R; r += rstep) {
+                const uint16_t *s = win + r * Ws + skew + 4 * qi;
+                int p[TAPS + 3];
+#pragma unroll
+                for (int k = 0; k < TAPS + 3; k++) p[k] = s[k];
+                int o[4];
+#pragma unroll
+                for (int j = 0; j < 4; j++) {
+                    int acc = 0;
+#pragma unroll
+                    for (int k = 0; k < TAPS; k++) acc += fx[k] * p[j + k];
+                    o[j] = (acc >> sh) & 0xffff;
+                }
+                uint32_t *d = reinterpret_cast<uint32_t *>(tmp + r * g.wpad + 4 * qi);
+                d[0] = (uint32_t)o[0] | ((uint32_t)o[1] << 16);
+                d[1] = (uint32_t)o[2] | ((uint32_t)o[3] << 16);
+            }
+        }
+        __syncwarp();
+    }
+    // stage B: vertical FIR (or pass-through), lane = column, up to 8 rows per lane with a register sliding window
+    const int xl = lane & ((1 << g.wsh) - 1), y0 = (lane >> g.wsh) * g.rows_per;
+    const bool act = xl < w && y0 < h;
+    int a[8 + TAPS - 1];
+    if (mx) {
+        const int16_t *s = tmp + y0 * g.wpad + xl;
+#pragma unroll
+        for (int k = 0; k < 8 + TAPS - 1; k++) a[k] = (act && k < g.rows_per + (my ? TAPS - 1 : 0) && y0 + k < R) ? (int)s[k * g.wpad] : 0;
+    } else {
+        const uint16_t *s = win + y0 * Ws + skew + xl;
+#pragma unroll
+        for (int k = 0; k < 8 + TAPS - 1; k++) a[k] = (act && k < g.rows_per + (my ? TAPS - 1 : 0) && y0 + k < R) ? (int)s[k * Ws] : 0;
+    }
+    if (my) {
+        int fy[TAPS];
+#pragma unroll
+        for (int k = 0; k < TAPS; k++) fy[k] = fyp[k];
+        const int sh = mx ? 6 : bd - 8;
+#pragma unroll
+        for (int j = 0; j < 8; j++) {
+            int acc = 0;
+#pragma unroll
+            for (int k = 0; k < TAPS; k++) acc += fy[k] * a[j + k];
+            val[j] = acc >> sh;
+        }
+    } else {
+        const int sh = mx ? 0 : 14 - bd;
+#pragma unroll
+        for (int j = 0; j < 8; j++) val[j] = a[j] << sh;
+    }
+}
+
 template <typename PIX>
 __global__ void __launch_bounds__(256) k_mc(const B200McRec *__restrict__ recs, int count, FrameDesc cur, const FrameDesc *__restrict__ dpb, RefTable rt, int bd)
 {
-    __shared__ uint16_t win_s[8][MC_WIN_MAX];
-    __shared__ int16_t tmp_s[8][MC_TMP_MAX];
+    __shared__ __align__(16) uint16_t win_s[8][MC_WIN_MAX];
+    __shared__ __align__(16) int16_t tmp_s[8][MC_TMP_MAX];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int ri = blockIdx.x * 8 + warp;
     if (ri >= count) return;
-    B200McRec m;
-    {
-        const int4 *p = reinterpret_cast<const int4 *>(recs + ri);
-        const int4 a = __ldg(p), b = __ldg(p + 1);
-        memcpy(&m, &a, 16);
-        memcpy(reinterpret_cast<char *>(&m) + 16, &b, 16);
-    }
-    const int w = m.w, h = m.h, plane = m.plane;
-    const bool chroma = m.flags & B200_MCF_CHROMA, bi = m.flags & B200_MCF_BI, weighted = m.flags & B200_MCF_WEIGHTED;
+    const int4 *rp4 = reinterpret_cast<const int4 *>(recs + ri);
+    const int4 ra = __ldg(rp4), rb = __ldg(rp4 + 1);
+    // B200McRec fields straight from registers
+    const int mxy = ra.x, whpf = ra.y;
+    const int dx = mxy & 0xffff, dy = (unsigned)mxy >> 16;
+    const int w = whpf & 0xff, h = (whpf >> 8) & 0xff, plane = (whpf >> 16) & 0xff, flags = (unsigned)whpf >> 24;
+    const int sx0 = (int16_t)(ra.z & 0xffff), sy0 = (int16_t)((unsigned)ra.z >> 16), sx1 = (int16_t)(ra.w & 0xffff), sy1 = (int16_t)((unsigned)ra.w >> 16);
+    const int ref0 = rb.x & 0xff, ref1 = (rb.x >> 8) & 0xff, frac0 = (rb.x >> 16) & 0xff, frac1 = (unsigned)rb.x >> 24;
+    const int w0 = (int16_t)(rb.y & 0xffff), w1 = (int16_t)((unsigned)rb.y >> 16), o0 = (int16_t)(rb.z & 0xffff), o1 = (int16_t)((unsigned)rb.z >> 16);
+    const int denom = rb.w & 0xff;
+    const bool chroma = flags & B200_MCF_CHROMA, bi = flags & B200_MCF_BI, weighted = flags & B200_MCF_WEIGHTED;
+    McGeom g;
+    g.w = w; g.h = h;
+    g.wsh = w <= 2 ? 1 : w <= 4 ? 2 : w <= 8 ? 3 : w <= 16 ? 4 : 5;
+    g.parts = 32 >> g.wsh;
+    g.rows_per = (h + g.parts - 1) / g.parts;
+    g.wpad = (w + 3) & ~3;
+    g.q = g.wpad >> 2;
+    g.lsh = g.q <= 1 ? 0 : g.q <= 2 ? 1 : g.q <= 4 ? 2 : 3;
     int v0[8], v1[8];
     {
-        const PlaneDesc rp = dpb[ref_slot_of(rt, m.ref0)].p[plane];
-        if (chroma) mc_list<PIX, 4>(rp, m.sx0, m.sy0, m.frac0 & 15, m.frac0 >> 4, w, h, bd, lane, win_s[warp], tmp_s[warp], v0);
-        else        mc_list<PIX, 8>(rp, m.sx0, m.sy0, m.frac0 & 15, m.frac0 >> 4, w, h, bd, lane, win_s[warp], tmp_s[warp], v0);
+        const PlaneDesc rp = dpb[ref_slot_of(rt, ref0)].p[plane];
+        if (chroma) mc_list<PIX, 4>(rp, sx0, sy0, frac0 & 15, frac0 >> 4, g, bd, lane, win_s[warp], tmp_s[warp], v0);
+        else        mc_list<PIX, 8>(rp, sx0, sy0, frac0 & 15, frac0 >> 4, g, bd, lane, win_s[warp], tmp_s[warp], v0);
     }
     if (bi) {
-        const PlaneDesc rp = dpb[ref_slot_of(rt, m.ref1)].p[plane];
-        if (chroma) mc_list<PIX, 4>(rp, m.sx1, m.sy1, m.frac1 & 15, m.frac1 >> 4, w, h, bd, lane, win_s[warp], tmp_s[warp], v1);
-        else        mc_list<PIX, 8>(rp, m.sx1, m.sy1, m.frac1 & 15, m.frac1 >> 4, w, h, bd, lane, win_s[warp], tmp_s[warp], v1);
+        const PlaneDesc rp = dpb[ref_slot_of(rt, ref1)].p[plane];
+        if (chroma) mc_list<PIX, 4>(rp, sx1, sy1, frac1 & 15, frac1 >> 4, g, bd, lane, win_s[warp], tmp_s[warp], v1);
+        else        mc_list<PIX, 8>(rp, sx1, sy1, frac1 & 15, frac1 >> 4, g, bd, lane, win_s[warp], tmp_s[warp], v1);
     }
     const PlaneDesc dp = plane_of(cur, plane);
-    const int shift = 14 - bd, maxv = (1 << bd) - 1, n = w * h;
-    const bool fullpel0 = !(m.frac0 & 15) && !(m.frac0 >> 4);
+    const int shift = 14 - bd, maxv = (1 << bd) - 1;
+    const bool fullpel0 = frac0 == 0;
+    const int xl = lane & ((1 << g.wsh) - 1), y0 = (lane >> g.wsh) * g.rows_per;
+    if (xl >= w) return;
+    PIX *d = px_ptr<PIX>(dp, dx + xl, dy + y0);
 #pragma unroll
-    for (int k = 0; k < 8; k++) {
-        const int i = lane + 32 * k;
-        if (i >= n) break;
-        const int y = i / w, x = i - y * w;
+    for (int j = 0; j < 8; j++) {
+        if (j >= g.rows_per || y0 + j >= h) break;
         int out;
         if (!bi) {
-            if (!weighted) out = fullpel0 ? (v0[k] >> shift) : clip3i((v0[k] + (1 << (shift - 1))) >> shift, 0, maxv);
+            if (!weighted) out = fullpel0 ? (v0[j] >> shift) : clip3i((v0[j] + (1 << (shift - 1))) >> shift, 0, maxv);
             else {
-                const int s = m.denom + shift;
-                out = clip3i(((v0[k] * m.w0 + (1 << (s - 1))) >> s) + m.o0 * (1 << (bd - 8)), 0, maxv);
+                const int s = denom + shift;
+                out = clip3i(((v0[j] * w0 + (1 << (s - 1))) >> s) + o0 * (1 << (bd - 8)), 0, maxv);
             }
         } else {
-            const int a = (int16_t)v0[k];          // list 0 travels through the reference's int16 tmp[] (hevc.c:1761)
-            if (!weighted) out = clip3i((v1[k] + a + (1 << shift)) >> (shift + 1), 0, maxv);
+            const int a = (int16_t)v0[j];          // list 0 travels through the reference's int16 tmp[] (hevc.c:1761)
+            if (!weighted) out = clip3i((v1[j] + a + (1 << shift)) >> (shift + 1), 0, maxv);
             else {
-                const int l2 = m.denom + shift, o = (m.o0 + m.o1) * (1 << (bd - 8)) + 1;
-                out = clip3i((v1[k] * m.w1 + a * m.w0 + (o << l2)) >> (l2 + 1), 0, maxv);
+                const int l2 = denom + shift, o = (o0 + o1) * (1 << (bd - 8)) + 1;
+                out = clip3i((v1[j] * w1 + a * w0 + (o << l2)) >> (l2 + 1), 0, maxv);
             }
         }
-        *px_ptr<PIX>(dp, m.x + x, m.y + y) = (PIX)out;
+        *d = (PIX)out;
+        d = reinterpret_cast<PIX *>(reinterpret_cast<uint8_t *>(d) + dp.pitch);
     }
 }
 
