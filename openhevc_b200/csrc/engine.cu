@@ -34,7 +34,7 @@ struct B200Ctx {
     uint8_t *work = nullptr;
     FrameDesc *dpb_desc_dev = nullptr;
     FrameDesc slot_desc[MAX_SLOTS + 1];
-    uint32_t *flags[3] = { nullptr, nullptr, nullptr };
+    uint2 *flags[3] = { nullptr, nullptr, nullptr };   // intra edge records, 16 B per 4x4 unit
     int flag_stride[3];
     uint32_t *counter = nullptr;
     int16_t *parked = nullptr;       // residuals of intra TUs (K2 -> K3), indexed like the coefficient pool
@@ -186,8 +186,8 @@ static int ctx_init(B200Ctx *ctx)
     for (int p = 0; p < 3; p++) {
         ctx->flag_stride[p] = (ctx->pw[p] + 3) / 4 + 1;
         const size_t n = (size_t)ctx->flag_stride[p] * ((ctx->ph[p] + 3) / 4 + 1);
-        CU(cudaMalloc(&ctx->flags[p], n * 4));
-        CU(cudaMemset(ctx->flags[p], 1, n * 4));     // non-zero = reconstructed
+        CU(cudaMalloc(&ctx->flags[p], n * 16));
+        CU(cudaMemset(ctx->flags[p], 0, n * 16));
     }
     CU(cudaMalloc(&ctx->counter, 256));
     CU(cudaMemset(ctx->counter, 0, 256));

@@ -392,29 +392,18 @@ __global__ void __launch_bounds__(256) k_mc(const B200McRec *__restrict__ recs, 
 }
 
 // --------------------------------------------------------------------------------------------
-// K3: intra prediction.  Persistent warps take TUs in decode order from an atomic counter and
-// wait on per-4x4-unit "reconstructed" flags of exactly the neighbours they read (TU-granular
-// wavefront); prediction + parked residual are fused, so the serial chain is short.
+// K3: intra prediction.  Persistent warps take TUs in dependency-level order from an atomic counter.
+// Neighbouring TUs exchange their border samples through per-4x4-unit *edge records* (bottom row and
+// right column, 4 samples + valid bits in one 8-byte word each): the record IS the message, so a
+// dependent TU polls the very data it needs -- no separate flag, no fence on either side, one L2
+// round trip per wavefront step.  The picture itself is written with plain stores for the later stages.
+// Prediction + parked residual are fused, so the serial chain is short.
 // --------------------------------------------------------------------------------------------
-__device__ __forceinline__ uint32_t ld_acquire(const uint32_t *p)
-{
-    uint32_t v;
-    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-    return v;
-}
-// debug: per-TU timestamps (ns, %globaltimer) [grab, deps ready, gathered, predicted, fenced, published]; null = off
+// debug: per-TU timestamps (ns, %globaltimer) [grab, -, neighbours in, predicted, -, published]; null = off
 __device__ unsigned long long *g_intra_trace = nullptr;
 __device__ __forceinline__ unsigned long long gtime() { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; }
 #define TRACE(slot) do { if (tr && lane == 0) tr[slot] = gtime(); } while (0)
 int set_intra_trace(unsigned long long *p) { return (int)cudaMemcpyToSymbol(g_intra_trace, &p, sizeof(p)); }
-
-// Message passing between intra TUs costs one light fence on the producer side and none on the consumer side:
-//  producer: pixel stores; fence.acq_rel.gpu (MEMBAR.ALL.GPU -- not __threadfence(), which is fence.sc + an L1
-//            invalidate, ~2 us on B200); relaxed flag store.
-//  consumer: relaxed flag polls at L2; the neighbour loads that follow are issued after the flag-dependent branch
-//            and bypass L1 (ld.global.cg), so they are served by L2 after the producer's stores became visible there.
-__device__ __forceinline__ void fence_release_gpu() { asm volatile("fence.acq_rel.gpu;" ::: "memory"); }
-__device__ __forceinline__ void consumer_barrier() { asm volatile("" ::: "memory"); }
 
 __device__ __forceinline__ uint32_t ld_relaxed(const uint32_t *p)
 {
@@ -426,9 +415,26 @@ __device__ __forceinline__ void st_relaxed(uint32_t *p, uint32_t v)
 {
     asm volatile("st.relaxed.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
-__device__ __forceinline__ void st_release(uint32_t *p, uint32_t v)
+// 8-byte edge words: naturally aligned 64-bit accesses are single-copy atomic, so a reader sees a whole record or none
+__device__ __forceinline__ uint2 ld_edge(const uint2 *p)
 {
-    asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+    uint2 v;
+    asm volatile("ld.relaxed.gpu.global.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_edge(uint2 *p, uint2 v)
+{
+    asm volatile("st.relaxed.gpu.global.v2.u32 [%0], {%1, %2};" ::"l"(p), "r"(v.x), "r"(v.y) : "memory");
+}
+#define EDGE_VALID 0x8000u
+__device__ __forceinline__ uint2 edge_pack(int a, int b, int c, int d)
+{
+    return make_uint2((uint32_t)a | EDGE_VALID | (((uint32_t)b | EDGE_VALID) << 16), (uint32_t)c | EDGE_VALID | (((uint32_t)d | EDGE_VALID) << 16));
+}
+__device__ __forceinline__ int edge_elem(uint2 v, int i)
+{
+    const uint32_t w = (i & 2) ? v.y : v.x;
+    return (int)((w >> ((i & 1) * 16)) & 0x7fff);
 }
 
 __device__ __forceinline__ B200IntraRec decode_intra(const int4 raw)
@@ -441,86 +447,109 @@ __device__ __forceinline__ B200IntraRec decode_intra(const int4 raw)
     return r;
 }
 
-struct IntraFlags {
-    uint32_t *f[3];
-    int stride[3];
+struct IntraEdges {
+    uint2 *e[3];        // per plane: [2 * unit] = bottom row of the 4x4 unit, [2 * unit + 1] = its right column
+    int stride[3];      // units per row
 };
+__device__ __forceinline__ uint2 *edges_of(const IntraEdges &ed, int plane) { return plane == 0 ? ed.e[0] : plane == 1 ? ed.e[1] : ed.e[2]; }
+__device__ __forceinline__ int estride_of(const IntraEdges &ed, int plane) { return plane == 0 ? ed.stride[0] : plane == 1 ? ed.stride[1] : ed.stride[2]; }
 
-__global__ void k_intra_prepass(const B200IntraRec *__restrict__ recs, int count, IntraFlags fl)
+// records of every unit from the picture as it stands after K1/K2 (inter blocks are final at that point)
+template <typename PIX>
+__global__ void k_intra_edges_init(FrameDesc f, IntraEdges ed)
+{
+    const int plane = blockIdx.z;
+    const PlaneDesc pd = plane_of(f, plane);
+    const int ux = blockIdx.x * blockDim.x + threadIdx.x, uy = blockIdx.y;
+    if (4 * ux >= pd.w || 4 * uy >= pd.h) return;
+    const PIX *b = px_ptr<PIX>(pd, 4 * ux, 4 * uy + 3);
+    const int r0 = *px_ptr<PIX>(pd, 4 * ux + 3, 4 * uy), r1 = *px_ptr<PIX>(pd, 4 * ux + 3, 4 * uy + 1), r2 = *px_ptr<PIX>(pd, 4 * ux + 3, 4 * uy + 2);
+    const uint2 bot = edge_pack(b[0], b[1], b[2], b[3]), rgt = edge_pack(r0, r1, r2, b[3]);
+    uint4 *dst = reinterpret_cast<uint4 *>(edges_of(ed, plane) + 2 * ((size_t)uy * estride_of(ed, plane) + ux));
+    *dst = make_uint4(bot.x, bot.y, rgt.x, rgt.y);
+}
+
+// units an intra TU of this picture will write: not valid yet
+__global__ void k_intra_prepass(const B200IntraRec *__restrict__ recs, int count, IntraEdges ed)
 {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= count) return;
     const B200IntraRec r = decode_intra(__ldg(reinterpret_cast<const int4 *>(recs + i)));
     const int u = 1 << (r.log2 - 2), ux = r.x >> 2, uy = r.y >> 2;
-    uint32_t *f = r.plane == 0 ? fl.f[0] : r.plane == 1 ? fl.f[1] : fl.f[2];
-    const int fs = r.plane == 0 ? fl.stride[0] : r.plane == 1 ? fl.stride[1] : fl.stride[2];
+    uint2 *e = edges_of(ed, r.plane);
+    const int fs = estride_of(ed, r.plane);
     for (int y = 0; y < u; y++)
-        for (int x = 0; x < u; x++) f[(uy + y) * fs + ux + x] = 0;
+        for (int x = 0; x < u; x++) *reinterpret_cast<uint4 *>(e + 2 * ((size_t)(uy + y) * fs + ux + x)) = make_uint4(0, 0, 0, 0);
 }
 
-
-
-// Wait until the flag this lane watches (nullptr = none) is set, for every lane of the warp.  The loop is executed by
-// all 32 lanes with a uniform exit (vote), so the warp leaves it CONVERGED: a per-lane `while (flag == 0)` lets the
-// lanes exit one by one and the rest of the TU then runs as several diverged fragments (every instruction issued
-// once per fragment, shuffles through the BRA.DIV slow path) -- measured 5100 vs ~700 cycles for a 4x4 TU.
-// A malformed list (dependency cycle) must not hang the GPU: give up after ~0.3 s and latch an error in counter[1].
-__device__ __forceinline__ void wait_units(const uint32_t *p, uint32_t *counter)
+// Poll until every lane of the warp has its record(s).  Executed by all 32 lanes with a uniform (vote) exit so the
+// warp leaves the loop CONVERGED -- a per-lane `while (!valid)` lets lanes leave one by one and the rest of the TU
+// then runs as diverged fragments (measured 5100 vs ~700 cycles for a 4x4 TU).  A malformed list (dependency cycle)
+// must not hang the GPU: give up after ~0.3 s and latch an error in counter[1].
+// `pa_alt`: alternative source of record a (the up-left corner sample is the last element of BOTH halves of its unit,
+// and depending on the neighbour's geometry only the bottom row or only the right column of that unit is published).
+__device__ __forceinline__ void fetch_edges(const uint2 *pa, const uint2 *pa_alt, uint2 &va, const uint2 *pb, uint2 &vb, uint32_t *counter)
 {
-    bool ready = p == nullptr;
+    bool ha = pa == nullptr, hb = pb == nullptr;
     uint32_t spins = 0;
+    va = vb = make_uint2(0, 0);
     for (;;) {
-        if (!ready) ready = ld_relaxed(p) != 0;
-        if (__all_sync(0xffffffffu, ready)) break;
+        if (!ha) {
+            va = ld_edge(pa); ha = va.x & EDGE_VALID;
+            if (!ha && pa_alt) { const uint2 t = ld_edge(pa_alt); if (t.x & EDGE_VALID) { va = t; ha = true; } }
+        }
+        if (!hb) { vb = ld_edge(pb); hb = vb.x & EDGE_VALID; }
+        if (__all_sync(0xffffffffu, ha && hb)) break;
         __nanosleep(20);
         if ((++spins & 1023) == 0) {
             const bool abort = spins > (1u << 21) || ld_relaxed(counter + 1) != 0;
-            if (__any_sync(0xffffffffu, abort)) { st_release(counter + 1, 1u); break; }
+            if (__any_sync(0xffffffffu, abort)) { st_relaxed(counter + 1, 1u); break; }
         }
     }
 }
 
+// publish the bottom row / right column of a finished TU: sb[x] = row n-1, sr[y] = column n-1 (shared memory)
+__device__ __forceinline__ void publish_edges(uint2 *e, int fs, int ux, int uy, int u, const uint16_t *sb, const uint16_t *sr, int lane)
+{
+    if (lane < u) st_edge(e + 2 * ((size_t)(uy + u - 1) * fs + ux + lane), edge_pack(sb[4 * lane], sb[4 * lane + 1], sb[4 * lane + 2], sb[4 * lane + 3]));
+    else if (lane >= 8 && lane < 8 + u) {
+        const int k = lane - 8;
+        st_edge(e + 2 * ((size_t)(uy + k) * fs + ux + u - 1) + 1, edge_pack(sr[4 * k], sr[4 * k + 1], sr[4 * k + 2], sr[4 * k + 3]));
+    }
+}
+
 // Fast path for 4x4 / 8x8 intra TUs (the bulk of every dependency chain): the <= 33 reference samples live one per
-// lane in two registers (fT: lane k = top[k-1], fL: lane k = left[k]); gathering, substitution, [1 2 1] smoothing and
-// the predictors use warp shuffles only -- no shared memory, no loops -- so one wavefront step is ~150 instructions.
+// lane in two registers (fT: lane k = top[k-1], fL: lane k = left[k]); substitution, [1 2 1] smoothing and the
+// predictors use warp shuffles only, so one wavefront step is ~150 instructions.
 template <typename PIX>
 __device__ __forceinline__ void intra_small(const B200IntraRec &r, const int16_t *__restrict__ pool, const PlaneDesc &pd, int bd,
-                                            uint32_t *flg, int fs, uint32_t *counter, int lane, unsigned long long *tr)
+                                            uint2 *e, int fs, uint32_t *counter, int lane, uint16_t *sbr, unsigned long long *tr)
 {
     const unsigned FULL = 0xffffffffu;
     const int n = 1 << r.log2, n2 = 2 * n, x0 = r.x, y0 = r.y, maxv = (1 << bd) - 1;
     const bool ul = r.flags & B200_INF_UP_LEFT, up = r.flags & B200_INF_UP, ur = r.flags & B200_INF_UP_RIGHT;
     const bool lf = r.flags & B200_INF_LEFT, bl = r.flags & B200_INF_BOTTOM_LEFT;
     const int trs = r.top_right_size, bls = r.bottom_left_size;
-    // residual prefetch (independent of the neighbours)
     const int npx = n * n;
     const int16_t *res = r.resid_off != B200_NO_RESID ? pool + r.resid_off : nullptr;
-    int rs0 = 0, rs1 = 0;
+    int rs0 = 0, rs1 = 0;                                  // residual prefetch (independent of the neighbours)
     if (res) { if (lane < npx) rs0 = res[lane]; if (lane + 32 < npx) rs1 = res[lane + 32]; }
-    // ---- wait: lane 0 corner, lanes 1..4 top units, lanes 5..8 left units ----
-    {
-        int ux = -1, uy = -1;
-        if (lane == 0) { if (ul) { ux = (x0 - 1) >> 2; uy = (y0 - 1) >> 2; } }
-        else if (lane <= 4) { const int o = 4 * (lane - 1); if ((o < n && up) || (o >= n && o < n2 && ur && o < n + trs)) { ux = (x0 + o) >> 2; uy = (y0 - 1) >> 2; } }
-        else if (lane <= 8) { const int o = 4 * (lane - 5); if ((o < n && lf) || (o >= n && o < n2 && bl && o < n + bls)) { ux = (x0 - 1) >> 2; uy = (y0 + o) >> 2; } }
-        wait_units(ux >= 0 ? flg + uy * fs + ux : nullptr, counter);
-    }
-    consumer_barrier();
-    __syncwarp();
-    TRACE(1);
-    // ---- gather: lanes 0..2n -> top[lane-1], lanes 0..2n-1 -> left[lane] ----
+    // ---- neighbours: lane k polls the record holding top[k-1] and the one holding left[k] ----
     int gT = 0, gL = 0;
     {
         const int t = lane - 1;
-        if (lane == 0) { if (ul) gT = __ldcg(px_ptr<PIX>(pd, x0 - 1, y0 - 1)); }
-        else if (t < n) { if (up) gT = __ldcg(px_ptr<PIX>(pd, x0 + t, y0 - 1)); }
-        else if (t < n2) { if (ur) gT = __ldcg(px_ptr<PIX>(pd, x0 + min(t, n + trs - 1), y0 - 1)); }
-        if (lane < n) { if (lf) gL = __ldcg(px_ptr<PIX>(pd, x0 - 1, y0 + lane)); }
-        else if (lane < n2) { if (bl) gL = __ldcg(px_ptr<PIX>(pd, x0 - 1, y0 + min(lane, n + bls - 1))); }
+        const bool needT = lane == 0 ? ul : t < n ? up : (t < n2 && ur);
+        const bool needL = lane < n ? lf : (lane < n2 && bl);
+        const int tx = x0 + (lane == 0 ? -1 : min(t, n + trs - 1)), ly = y0 + min(lane, n + bls - 1);
+        const uint2 *pT = needT ? e + 2 * ((size_t)((y0 - 1) >> 2) * fs + (tx >> 2)) : nullptr;
+        const uint2 *pL = needL ? e + 2 * ((size_t)(ly >> 2) * fs + ((x0 - 1) >> 2)) + 1 : nullptr;
+        uint2 vT, vL;
+        fetch_edges(pT, (lane == 0 && pT) ? pT + 1 : nullptr, vT, pL, vL, counter);
+        if (needT) gT = edge_elem(vT, tx & 3);
+        if (needL) gL = edge_elem(vL, ly & 3);
     }
-    // ---- substitution (hevcpred_template.c:250-286), closed form on broadcast scalars ----
     TRACE(2);
-    if (tr && lane == 0) tr[6] = clock64();
+    // ---- substitution (hevcpred_template.c:250-286), closed form on broadcast scalars ----
     const int g_corner = __shfl_sync(FULL, gT, 0), g_top0 = __shfl_sync(FULL, gT, 1), g_topn1 = __shfl_sync(FULL, gT, n), g_topn = __shfl_sync(FULL, gT, n + 1);
     const int g_left0 = __shfl_sync(FULL, gL, 0), g_leftn1 = __shfl_sync(FULL, gL, n - 1), g_leftn = __shfl_sync(FULL, gL, n);
     const int sub = lf ? g_leftn1 : ul ? g_corner : up ? g_top0 : ur ? g_topn : (1 << (bd - 1));
@@ -551,7 +580,6 @@ __device__ __forceinline__ void intra_small(const B200IntraRec &r, const int16_t
 #define TOPS(i) __shfl_sync(FULL, fT, ((i) + 1) & 31)
 #define LEFTS(i) __shfl_sync(FULL, fL, (i) & 31)
     const int cornerf = __shfl_sync(FULL, fT, 0);
-    // ---- predictors ----
     int dc = 0;
     if (mode == 1) {
         int sum = (lane < n ? fL : 0) + ((lane >= 1 && lane <= n) ? fT : 0);
@@ -564,6 +592,7 @@ __device__ __forceinline__ void intra_small(const B200IntraRec &r, const int16_t
     const int inv = (mode >= 11 && mode <= 25) ? c_inv_angle[mode - 11] : 0;
     const bool edge = r.plane == 0;                                       // n < 32 always here
     const int topn_f = TOPS(n), leftn_f = LEFTS(n), top0_f = TOPS(0), left0_f = LEFTS(0);
+    uint16_t *sb = sbr, *sr = sbr + 32;
 #pragma unroll
     for (int it = 0; it < 2; it++) {
         const int i = lane + 32 * it;
@@ -599,31 +628,27 @@ __device__ __forceinline__ void intra_small(const B200IntraRec &r, const int16_t
         if (i < npx) {
             if (res) v = clip3i(v + (it ? rs1 : rs0), 0, maxv);
             *px_ptr<PIX>(pd, x0 + x, y0 + y) = (PIX)v;
+            if (y == n - 1) sb[x] = (uint16_t)v;
+            if (x == n - 1) sr[y] = (uint16_t)v;
         }
     }
 #undef TOPS
 #undef LEFTS
-    // ---- publish ----
     TRACE(3);
-    if (tr && lane == 0) tr[7] = clock64();
-    fence_release_gpu();
     __syncwarp();
-    TRACE(4);
-    {
-        const int u = n >> 2, ux = x0 >> 2, uy = y0 >> 2;
-        if (lane < u * u) st_relaxed(flg + (uy + lane / u) * fs + ux + (lane % u), 1u);
-    }
+    publish_edges(e, fs, x0 >> 2, y0 >> 2, n >> 2, sb, sr, lane);
     __syncwarp();
     TRACE(5);
 }
 
 template <typename PIX>
 __global__ void __launch_bounds__(128) k_intra(const B200IntraRec *__restrict__ recs, int count, const int16_t *__restrict__ pool,
-                                               FrameDesc f, int bd, IntraFlags fl, uint32_t *counter)
+                                               FrameDesc f, int bd, IntraEdges ed, uint32_t *counter)
 {
     __shared__ int s_g[4][2][66];     // gathered   [0]=top [1]=left, element [k] holds index k-1
     __shared__ int s_f[4][2][66];     // substituted
     __shared__ int s_ff[4][2][66];    // smoothed
+    __shared__ uint16_t s_st[4][2][64];   // staging: neighbour samples by position / border of the finished TU
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int maxv = (1 << bd) - 1;
     for (;;) {
@@ -632,11 +657,12 @@ __global__ void __launch_bounds__(128) k_intra(const B200IntraRec *__restrict__ 
         idx = __shfl_sync(0xffffffffu, idx, 0);
         if (idx >= count) break;
         const B200IntraRec r = decode_intra(__ldg(reinterpret_cast<const int4 *>(recs + idx)));
+        uint2 *e = edges_of(ed, r.plane);
+        const int fs = estride_of(ed, r.plane);
         if (r.log2 <= 3) {
             unsigned long long *tr = g_intra_trace ? g_intra_trace + 8ull * idx : nullptr;
             TRACE(0);
-            intra_small<PIX>(r, pool, plane_of(f, r.plane), bd, r.plane == 0 ? fl.f[0] : r.plane == 1 ? fl.f[1] : fl.f[2],
-                             r.plane == 0 ? fl.stride[0] : r.plane == 1 ? fl.stride[1] : fl.stride[2], counter, lane, tr);
+            intra_small<PIX>(r, pool, plane_of(f, r.plane), bd, e, fs, counter, lane, &s_st[warp][0][0], tr);
             continue;
         }
         const int n = 1 << r.log2, n2 = 2 * n, x0 = r.x, y0 = r.y;
@@ -644,34 +670,37 @@ __global__ void __launch_bounds__(128) k_intra(const B200IntraRec *__restrict__ 
         const bool ul = r.flags & B200_INF_UP_LEFT, up = r.flags & B200_INF_UP, ur = r.flags & B200_INF_UP_RIGHT;
         const bool lf = r.flags & B200_INF_LEFT, bl = r.flags & B200_INF_BOTTOM_LEFT;
         const int trs = r.top_right_size, bls = r.bottom_left_size;
-        uint32_t *flg = r.plane == 0 ? fl.f[0] : r.plane == 1 ? fl.f[1] : fl.f[2];
-        const int fs = r.plane == 0 ? fl.stride[0] : r.plane == 1 ? fl.stride[1] : fl.stride[2];
-        // ---- wait for the neighbours this TU reads ----
-        for (int it = 0; it < 2; it++) {            // every lane runs both rounds: wait_units() votes warp-wide
-            const int k = lane + 32 * it;
-            int ux = -1, uy = -1;
-            if (k >= 33) { }
-            else if (k == 0) { if (ul) { ux = (x0 - 1) >> 2; uy = (y0 - 1) >> 2; } }
-            else if (k <= 16) {
-                const int o = 4 * (k - 1);
-                if ((o < n && up) || (o >= n && ur && o < n + trs)) { ux = (x0 + o) >> 2; uy = (y0 - 1) >> 2; }
-            } else {
-                const int o = 4 * (k - 17);
-                if ((o < n && lf) || (o >= n && bl && o < n + bls)) { ux = (x0 - 1) >> 2; uy = (y0 + o) >> 2; }
+        uint16_t *stg_t = s_st[warp][0], *stg_l = s_st[warp][1];
+        // ---- neighbours: lane k fetches the bottom row of top unit k (4 samples), lane k the right column of left unit k;
+        //      16x16: 8 + 8 units, 32x32: 16 + 16 units; the corner comes with the up-left unit's bottom row ----
+        int g_corner = 0;
+        {
+            const int nu = n2 >> 2;                                            // units along 2n samples
+            const int ot = 4 * lane, ol = 4 * lane;
+            const bool needT = lane < nu && ((ot < n && up) || (ot >= n && ur && ot < n + trs));
+            const bool needL = lane < nu && ((ol < n && lf) || (ol >= n && bl && ol < n + bls));
+            const uint2 *pT = needT ? e + 2 * ((size_t)((y0 - 1) >> 2) * fs + ((x0 + ot) >> 2)) : nullptr;
+            const uint2 *pL = needL ? e + 2 * ((size_t)((y0 + ol) >> 2) * fs + ((x0 - 1) >> 2)) + 1 : nullptr;
+            uint2 vT, vL, vC, vD;
+            fetch_edges(pT, nullptr, vT, pL, vL, counter);
+            const uint2 *pC = (lane == 0 && ul) ? e + 2 * ((size_t)((y0 - 1) >> 2) * fs + ((x0 - 1) >> 2)) : nullptr;
+            fetch_edges(pC, pC ? pC + 1 : nullptr, vC, nullptr, vD, counter);
+            if (lane < 16) {
+#pragma unroll
+                for (int k = 0; k < 4; k++) { stg_t[4 * lane + k] = needT ? (uint16_t)edge_elem(vT, k) : 0; stg_l[4 * lane + k] = needL ? (uint16_t)edge_elem(vL, k) : 0; }
             }
-            wait_units(ux >= 0 ? flg + uy * fs + ux : nullptr, counter);
+            g_corner = __shfl_sync(0xffffffffu, pC ? edge_elem(vC, 3) : 0, 0);
         }
-        consumer_barrier();
         __syncwarp();
-        // ---- gather (L2 loads: neighbours were written by other SMs) ----
+        // ---- the reference arrays, with the replication of the last in-picture sample (hevcpred_template.c:170-183) ----
         int *gt = s_g[warp][0], *gl = s_g[warp][1];
         for (int k = lane; k <= n2; k += 32) {
             const int t = k - 1;
             int tv = 0, lv = 0;
-            if (t < 0) { if (ul) tv = lv = __ldcg(px_ptr<PIX>(pd, x0 - 1, y0 - 1)); }
+            if (t < 0) { if (ul) tv = lv = g_corner; }
             else {
-                if (t < n ? up : ur) tv = __ldcg(px_ptr<PIX>(pd, x0 + (t < n ? t : min(t, n + trs - 1)), y0 - 1));
-                if (t < n ? lf : bl) lv = __ldcg(px_ptr<PIX>(pd, x0 - 1, y0 + (t < n ? t : min(t, n + bls - 1))));
+                if (t < n ? up : ur) tv = stg_t[t < n ? t : min(t, n + trs - 1)];
+                if (t < n ? lf : bl) lv = stg_l[t < n ? t : min(t, n + bls - 1)];
             }
             gt[k] = tv; gl[k] = lv;
         }
@@ -737,8 +766,8 @@ __global__ void __launch_bounds__(128) k_intra(const B200IntraRec *__restrict__ 
         const int inv = (mode >= 11 && mode <= 25) ? c_inv_angle[mode - 11] : 0;
         const bool edge = r.plane == 0 && n < 32;
         const int16_t *res = r.resid_off != B200_NO_RESID ? pool + r.resid_off : nullptr;
-        for (int i = lane; i < n * n; i += 32) {
-            const int y = i >> r.log2, x = i & (n - 1);
+        __syncwarp();                                           // staging buffers are reused for the TU's own border below
+        auto predict = [&](int x, int y) -> int {
             int v;
             if (mode == 0) {
                 v = ((n - 1 - x) * left[y] + (x + 1) * top[n] + (n - 1 - y) * top[x] + (y + 1) * left[n] + n) >> (r.log2 + 1);
@@ -764,16 +793,23 @@ __global__ void __launch_bounds__(128) k_intra(const B200IntraRec *__restrict__ 
                     if (mode == 10 && y == 0) v = clip3i(left[0] + ((top[x] - top[-1]) >> 1), 0, maxv);
                 }
             }
-            if (res) v = clip3i(v + res[i], 0, maxv);
-            *px_ptr<PIX>(pd, x0 + x, y0 + y) = (PIX)v;
+            if (res) v = clip3i(v + res[y * n + x], 0, maxv);
+            return v;
+        };
+        // ---- the border first: the bottom row and right column are all a dependent TU ever reads, so they are
+        //      predicted and published before the interior -- the interior is off the wavefront's critical path ----
+        for (int i = lane; i < 2 * n - 1; i += 32) {
+            const int x = i < n ? i : n - 1, y = i < n ? n - 1 : i - n;
+            const int v = predict(x, y);
+            if (i < n) stg_t[x] = (uint16_t)v; else stg_l[y] = (uint16_t)v;
+            if (i == n - 1) stg_l[n - 1] = (uint16_t)v;
         }
-        // ---- publish ----
-        // every lane fences its own pixel stores, then relaxed flag stores
-        fence_release_gpu();
         __syncwarp();
-        {
-            const int u = n >> 2, ux = x0 >> 2, uy = y0 >> 2;
-            for (int k = lane; k < u * u; k += 32) st_relaxed(flg + (uy + k / u) * fs + ux + (k % u), 1u);
+        publish_edges(e, fs, x0 >> 2, y0 >> 2, n >> 2, stg_t, stg_l, lane);
+        // ---- then the whole block ----
+        for (int i = lane; i < n * n; i += 32) {
+            const int y = i >> r.log2, x = i & (n - 1);
+            *px_ptr<PIX>(pd, x0 + x, y0 + y) = (PIX)predict(x, y);
         }
         __syncwarp();
     }
@@ -1013,21 +1049,24 @@ int launch_residual(cudaStream_t st, const B200TuRec *const recs[4], const int c
 }
 
 int launch_intra(cudaStream_t st, const B200IntraRec *recs, int count, const int16_t *pool, const FrameDesc &cur, int bd,
-                 uint32_t *flags[3], const int flag_stride[3], uint32_t *counter)
+                 uint2 *edges[3], const int edge_stride[3], uint32_t *counter)
 {
     if (!count) return 0;
-    IntraFlags fl;
-    for (int p = 0; p < 3; p++) { fl.f[p] = flags[p]; fl.stride[p] = flag_stride[p]; }
+    IntraEdges ed;
+    for (int p = 0; p < 3; p++) { ed.e[p] = edges[p]; ed.stride[p] = edge_stride[p]; }
     cudaMemsetAsync(counter, 0, sizeof(uint32_t), st);   // counter[1] = sticky abort flag, cleared at context creation
-    k_intra_prepass<<<(count + 255) / 256, 256, 0, st>>>(recs, count, fl);
+    const dim3 gi((cur.p[0].w / 4 + 127) / 128, cur.p[0].h / 4, 3);
+    if (bd > 8) k_intra_edges_init<uint16_t><<<gi, 128, 0, st>>>(cur, ed);
+    else        k_intra_edges_init<uint8_t><<<gi, 128, 0, st>>>(cur, ed);
+    k_intra_prepass<<<(count + 255) / 256, 256, 0, st>>>(recs, count, ed);
     int grid = (count + 3) / 4;
     // persistent warps.  The list is sorted by dependency level, so the TUs that can run together are adjacent and a
     // small window exposes all the parallelism there is; more waiting warps would only add polling traffic on L2.
     static const int max_ctas = getenv("B200_INTRA_CTAS") ? atoi(getenv("B200_INTRA_CTAS")) : 148 * 2;
     if (grid > max_ctas) grid = max_ctas;
-    if (bd > 8) k_intra<uint16_t><<<grid, 128, 0, st>>>(recs, count, pool, cur, bd, fl, counter);
-    else        k_intra<uint8_t><<<grid, 128, 0, st>>>(recs, count, pool, cur, bd, fl, counter);
-    return 2;
+    if (bd > 8) k_intra<uint16_t><<<grid, 128, 0, st>>>(recs, count, pool, cur, bd, ed, counter);
+    else        k_intra<uint8_t><<<grid, 128, 0, st>>>(recs, count, pool, cur, bd, ed, counter);
+    return 3;
 }
 
 int launch_deblock(cudaStream_t st, const uint16_t *grid, const B200DbkLayout &L, const FrameDesc &cur, int bd)
