@@ -26,6 +26,7 @@ WORKLOADS = {
     "c3_4k_main10_ra": dict(width=3840, height=2160, cfi=1, bit_depth=10),
     "c2_1080p_main_ra": dict(width=1920, height=1080, cfi=1, bit_depth=8),
     "c1_832x480_main": dict(width=832, height=480, cfi=1, bit_depth=8),
+    "c5_8k_422_main10": dict(width=7680, height=4320, cfi=2, bit_depth=10),
 }
 METRIC, UNIT = "decoded_frames_per_sec", "frames/s"
 

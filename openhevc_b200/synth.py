@@ -237,6 +237,14 @@ class FrameSynth:
         self._mark_edges(x, y, n, n, 2 if intra else 1)
         if intra:
             self.is_intra[y >> 2:(y + n) >> 2, x >> 2:(x + n) >> 2] = True
+            if 3 <= log2 <= 5 and r.random() < self.exotic * 0.5:
+                # pcm_flag CU (hls_pcm_sample, hevc.c:1587-1623): raw samples for the three planes, no prediction, no residual
+                self.tu[log2].append((0, x, y, W.TU_PCM, 0, None))
+                for plane in (1, 2):
+                    for (cx, cy, lc) in self._chroma_tbs(x, y, log2):
+                        self.tu[lc].append((plane, cx >> self.hs, cy >> self.vs, W.TU_PCM, 0, None))
+                self.stats["resid_samples"] += n * n * 3 // 2
+                return
             lmode = int(r.integers(0, 35))
             cmode = int(r.choice([0, 1, 10, 26, 34, lmode]))
             if log2 == 3 and r.random() < 0.3:            # PART_NxN: four 4x4 luma blocks with their own modes
@@ -293,6 +301,9 @@ class FrameSynth:
                 big = r.random(m) < 0.02                   # a few saturating blocks
                 coef[big] *= 40
                 coef = np.clip(coef, -32768, 32767).astype(np.int16)
+                pcm = kinds == W.TU_PCM
+                if pcm.any():                                # PCM blocks carry final samples, already << (BD - pcm_bit_depth)
+                    coef[pcm] = r.integers(0, 1 << self.bd, (int(pcm.sum()), n, n)).astype(np.int16)
                 nz = coef != 0
                 lx = np.where(nz.any(axis=1), np.arange(n)[None], 0).max(axis=1)
                 ly = np.where(nz.any(axis=2), np.arange(n)[None], 0).max(axis=1)

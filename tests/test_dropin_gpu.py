@@ -16,7 +16,7 @@ pytestmark = pytest.mark.gpu
 @pytest.mark.parametrize("w,h,cfi,bd,refs,kw", [
     (256, 128, 1, 8, [], {}),
     (256, 128, 1, 10, [1, 2], dict(weighted=True)),
-    (320, 192, 1, 8, [1, 2], dict(max_mv=150, exotic=0.05)),
+    (320, 192, 1, 8, [1, 2], dict(max_mv=150, exotic=0.3)),
     (192, 128, 2, 10, [2], {}),
     (192, 128, 3, 8, [1, 2], dict(sao_restore=True)),
     (832, 480, 1, 8, [], {}),

@@ -88,6 +88,28 @@ def test_config_c3_4k_main10_b_picture():
         eng.close()
 
 
+def test_config_c5_8k_422_main10():
+    """BASELINE config 5 geometry: 7680x4320 4:2:2 10-bit (RExt chroma format), inter picture with deblock + SAO"""
+    w, h, cfi, bd = 7680, 4320, 2, 10
+    eng = FrameEngine(w, h, cfi, bd, n_slots=2)
+    try:
+        dpb = [smooth_frame(w, h, cfi, bd, 90 + k) for k in range(2)]
+        eng.upload_slot(1, dpb[1])
+        blob, st = FrameSynth(w, h, cfi, bd, seed=91, refs=[1], cur_slot=0, split_bias=0.4, coded_frac=0.3).generate()
+        got = eng.decode(blob)
+        want = oracle_lib.execute(blob, dpb)
+        for p in range(3):
+            assert (got[p] == want[p]).all()
+    finally:
+        eng.close()
+
+
+def test_pcm_and_exotic_transform_paths():
+    """pcm CUs (put_pcm), transform-skip, rdpcm, transquant-bypass TUs in one sequence"""
+    run_sequence(256, 128, 1, 8, seeds=[95, 96], exotic=0.3)
+    run_sequence(192, 128, 2, 10, seeds=[97, 98], exotic=0.3)
+
+
 def test_malformed_blobs_are_rejected_not_executed():
     eng = FrameEngine(128, 64, 1, 8, n_slots=2)
     try:
