@@ -22,11 +22,11 @@ extern "C" {
 #endif
 
 #define B200_BLOB_MAGIC   0x4C573242u /* "B2WL" */
-#define B200_BLOB_VERSION 1u
+#define B200_BLOB_VERSION 2u
 
 /* blob sections; every section start is 256-byte aligned inside the blob */
 enum {
-    B200_SEC_COEFF = 0,   /* int16 pool: dequantised coefficients / PCM samples; count = #int16   */
+    B200_SEC_COEFF = 0,   /* int16 pool: dequantised coefficients (sparse pairs or dense blocks) / PCM samples; count = #int16 */
     B200_SEC_TU4,         /* B200TuRec, 4x4 blocks   (transform_add[0] call sites)                  */
     B200_SEC_TU8,         /* B200TuRec, 8x8                                                        */
     B200_SEC_TU16,        /* B200TuRec, 16x16                                                      */
@@ -85,9 +85,12 @@ typedef struct B200TuRec {       /* 16 bytes */
     uint8_t  kind;               /* B200_TU_*                                                     */
     uint8_t  flags;              /* B200_TUF_*                                                    */
     uint8_t  col_limit;          /* IDCT only (hevc_cabac.c:1927-1933)                            */
-    uint8_t  pad[3];
-    uint32_t coeff_off;          /* int16 index into the COEFF pool (multiple of 8)               */
+    uint8_t  pad;
+    uint16_t nnz;                /* sparse transport: number of (position, value) int16 pairs; B200_TU_DENSE = dense NxN block */
+    uint32_t coeff_off;          /* int16 index of this TU's data in the COEFF pool.  PARK TUs: the first two int16 are
+                                    the (lo, hi) halves of the TU's index in the parked-residual pool, data follows  */
 } B200TuRec;
+#define B200_TU_DENSE 0xFFFFu
 
 /* ---- intra stage (K3) ------------------------------------------------------------------ */
 #define B200_INF_UP_LEFT     1u  /* cand_up_left      (after z-scan / CIP checks, hevcpred_template.c:100-104) */
@@ -174,6 +177,22 @@ static_assert(sizeof(B200BlobHeader) == 256 && sizeof(B200TuRec) == 16 && sizeof
 _Static_assert(sizeof(B200BlobHeader) == 256 && sizeof(B200TuRec) == 16 && sizeof(B200IntraRec) == 16 &&
                sizeof(B200McRec) == 32 && sizeof(B200SaoRec) == 16, "blob v1 layout");
 #endif
+
+/* data of a TU inside the pool; *park_off receives the parked-pool index of PARK TUs */
+static inline const int16_t *b200_tu_data(const B200TuRec *t, const int16_t *pool, uint32_t *park_off)
+{
+    const int16_t *p = pool + t->coeff_off;
+    if (t->flags & B200_TUF_PARK) { *park_off = (uint32_t)(uint16_t)p[0] | ((uint32_t)(uint16_t)p[1] << 16); p += 2; }
+    return p;
+}
+/* dense NxN coefficients of a TU (what lc->tu.coeffs held at transform_add time) */
+static inline void b200_tu_expand(const B200TuRec *t, const int16_t *data, int16_t *dense)
+{
+    const int n2 = 1 << (2 * t->log2);
+    if (t->nnz == B200_TU_DENSE) { for (int i = 0; i < n2; i++) dense[i] = data[i]; return; }
+    for (int i = 0; i < n2; i++) dense[i] = 0;
+    for (int e = 0; e < t->nnz; e++) dense[(uint16_t)data[2 * e] & (n2 - 1)] = data[2 * e + 1];
+}
 
 static inline uint32_t b200_align_u32(uint32_t v, uint32_t a) { return (v + a - 1) / a * a; }
 

@@ -266,7 +266,9 @@ static int deep_check(B200Ctx *ctx, const uint8_t *blob)
         const int n = 4 << (s - B200_SEC_TU4);
         for (uint32_t i = 0; i < h->sec[s].count; i++) {
             if (t[i].plane > 2 || (1 << t[i].log2) != n || t[i].x + n > ctx->pw[t[i].plane] || t[i].y + n > ctx->ph[t[i].plane] ||
-                (uint64_t)t[i].coeff_off + n * n > ncoef || t[i].kind > B200_TU_PCM || (t[i].kind == B200_TU_DST && n != 4))
+                (uint64_t)t[i].coeff_off + ((t[i].flags & B200_TUF_PARK) ? 2 : 0) + (t[i].nnz == B200_TU_DENSE ? n * n : 2 * (uint64_t)t[i].nnz) > ncoef ||
+                (t[i].nnz != B200_TU_DENSE && (int)t[i].nnz > n * n) || (t[i].kind == B200_TU_PCM && t[i].nnz != B200_TU_DENSE) ||
+                t[i].kind > B200_TU_PCM || (t[i].kind == B200_TU_DST && n != 4))
                 return fail(ctx, B200_EINVAL, "TU record %u of size %d invalid", i, n);
         }
     }
@@ -275,7 +277,7 @@ static int deep_check(B200Ctx *ctx, const uint8_t *blob)
         const int n = 1 << ir[i].log2;
         if (ir[i].plane > 2 || ir[i].log2 < 2 || ir[i].log2 > 5 || ir[i].mode > 34 || (ir[i].x & 3) || (ir[i].y & 3) ||
             ir[i].x + n > ctx->pw[ir[i].plane] || ir[i].y + n > ctx->ph[ir[i].plane] ||
-            (ir[i].resid_off != B200_NO_RESID && (uint64_t)ir[i].resid_off + n * n > ncoef) ||
+            (ir[i].resid_off != B200_NO_RESID && ((uint64_t)ir[i].resid_off + n * n) * 2 > ctx->arena_bytes) ||
             ((ir[i].flags & B200_INF_UP_RIGHT) && (ir[i].top_right_size < 1 || ir[i].top_right_size > n || ir[i].x + n + ir[i].top_right_size > ctx->pw[ir[i].plane])) ||
             ((ir[i].flags & B200_INF_BOTTOM_LEFT) && (ir[i].bottom_left_size < 1 || ir[i].bottom_left_size > n || ir[i].y + n + ir[i].bottom_left_size > ctx->ph[ir[i].plane])) ||
             ((ir[i].flags & (B200_INF_UP | B200_INF_UP_RIGHT | B200_INF_UP_LEFT)) && ir[i].y == 0) ||

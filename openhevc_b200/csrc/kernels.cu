@@ -114,14 +114,29 @@ __global__ void __launch_bounds__(128) k_residual(const B200TuRec *__restrict__ 
     }
     const int16_t *c = pool + rec.coeff_off;
     const int kind = rec.kind;
+    uint32_t park_off = 0;
+    if (active && (rec.flags & B200_TUF_PARK)) { park_off = (uint32_t)(uint16_t)c[0] | ((uint32_t)(uint16_t)c[1] << 16); c += 2; }
+    const bool sparse = rec.nnz != B200_TU_DENSE;
     int v[N], t[N];
-    if (active) {
+    // sparse transport: (position, value) pairs are scattered into the zeroed tile, then every lane picks up its column
+#pragma unroll
+    for (int j = 0; j < N; j++) tile[j * (N + 1) + col] = 0;
+    __syncwarp();
+    if (active && sparse)
+        for (int e = col; e < rec.nnz; e += N) {
+            const int pos = (uint16_t)c[2 * e] & (N * N - 1);
+            tile[(pos / N) * (N + 1) + (pos % N)] = c[2 * e + 1];
+        }
+    __syncwarp();
+    const int c00 = !active ? 0 : sparse ? tile[0] : c[0];
+    if (active && !sparse) {
 #pragma unroll
         for (int j = 0; j < N; j++) v[j] = c[j * N + col];
     } else {
 #pragma unroll
-        for (int j = 0; j < N; j++) v[j] = 0;
+        for (int j = 0; j < N; j++) v[j] = tile[j * (N + 1) + col];
     }
+    __syncwarp();
     const int lim_row = min((int)rec.col_limit, N);
     // ---- first stage (columns) ----
     if (kind == B200_TU_IDCT) {
@@ -140,7 +155,7 @@ __global__ void __launch_bounds__(128) k_residual(const B200TuRec *__restrict__ 
         for (int j = 0; j < N; j++) t[j] = clip16i((o[j] + 64) >> 7);
     } else if (kind == B200_TU_DC) {
         const int shift = 14 - bd;
-        const int dc = active ? (((c[0] + 1) >> 1) + (1 << (shift - 1))) >> shift : 0;
+        const int dc = active ? (((c00 + 1) >> 1) + (1 << (shift - 1))) >> shift : 0;
 #pragma unroll
         for (int j = 0; j < N; j++) t[j] = (int16_t)dc;
     } else if (kind == B200_TU_SKIP) {
@@ -189,7 +204,7 @@ __global__ void __launch_bounds__(128) k_residual(const B200TuRec *__restrict__ 
     if (!active) return;
     // ---- output: rows of N consecutive samples per TU ----
     if (rec.flags & B200_TUF_PARK) {
-        int16_t *pk = parked + rec.coeff_off;      // the blob stays read-only: parked residuals live in their own pool
+        int16_t *pk = parked + park_off;           // the blob stays read-only: parked residuals live in their own pool
 #pragma unroll
         for (int y = 0; y < N; y++) pk[y * N + col] = (int16_t)tile[y * (N + 1) + col];
     } else {

@@ -18,6 +18,7 @@ struct B200Rec {
     uint64_t cap = 0;
     uint32_t off_dbk, off_sao, off_pool;
     uint32_t ncoef = 0;
+    uint32_t npark = 0;          // int16 used in the parked-residual pool
     std::vector<B200TuRec> tu[4];
     std::vector<B200IntraRec> intra;
     std::vector<B200McRec> mc;
@@ -131,7 +132,7 @@ extern "C" int b200_rec_begin(B200Rec *r, int cur_slot, int poc)
     memset(r->blob + r->off_dbk, 0, r->off_pool - r->off_dbk);
     for (int s = 0; s < 4; s++) r->tu[s].clear();
     r->intra.clear(); r->mc.clear();
-    r->ncoef = 0; r->any_dbk = r->any_sao = false;
+    r->ncoef = 0; r->npark = 0; r->any_dbk = r->any_sao = false;
     r->last_intra[0] = r->last_intra[1] = r->last_intra[2] = -1;
     r->cur_slot = cur_slot; r->poc = poc; r->open = true; r->nbytes = 0; r->n_ref = 0;
     return 0;
@@ -153,25 +154,43 @@ extern "C" int b200_rec_tu(B200Rec *r, int plane, int x, int y, int log2, int ki
     const int n = 1 << log2;
     if (x < 0 || y < 0 || x + n > r->pw[plane] || y + n > r->ph[plane]) return B200_EINVAL;
     if (kind == B200_TU_DST && log2 != 2) return B200_EINVAL;
-    uint32_t off;
-    int16_t *dst = pool_take(r, n * n, &off);
-    if (!dst) return B200_ENOMEM;
-    memcpy(dst, coeffs, (size_t)n * n * 2);
-    B200TuRec t;
-    memset(&t, 0, sizeof(t));
-    t.x = (uint16_t)x; t.y = (uint16_t)y; t.plane = (uint8_t)plane; t.log2 = (uint8_t)log2; t.kind = (uint8_t)kind;
-    t.flags = (uint8_t)(flags & (B200_TUF_RDPCM | B200_TUF_RDPCM_VERT));
-    t.col_limit = (uint8_t)(col_limit < 0 ? 0 : col_limit > 255 ? 255 : col_limit);
-    t.coeff_off = off;
     // residual of an intra TU: park it, the intra kernel adds it right after predicting the block
     const int li = r->last_intra[plane];
     bool link = false;
     if (li >= 0 && kind != B200_TU_PCM) {
-        B200IntraRec &ir = r->intra[li];
+        const B200IntraRec &ir = r->intra[li];
         link = ir.x == x && ir.y == y && ir.log2 == log2 && ir.resid_off == B200_NO_RESID;
         if (intra_linked == 0) link = false;
-        if (link) { ir.resid_off = off; t.flags |= B200_TUF_PARK; }
     }
+    // sparse transport: most dequantised coefficients are zero, send (position, value) pairs
+    int nnz = 0;
+    for (int i = 0; i < n * n; i++) nnz += coeffs[i] != 0;
+    const bool sparse = kind != B200_TU_PCM && 2 * nnz < n * n;
+    uint32_t off;
+    int16_t *dst = pool_take(r, (link ? 2 : 0) + (sparse ? 2 * nnz : n * n), &off);
+    if (!dst) return B200_ENOMEM;
+    B200TuRec t;
+    memset(&t, 0, sizeof(t));
+    if (link) {
+        const uint32_t po = (r->npark + 7) & ~7u;
+        r->npark = po + n * n;
+        dst[0] = (int16_t)(po & 0xffff); dst[1] = (int16_t)(po >> 16);
+        dst += 2;
+        r->intra[li].resid_off = po;
+        t.flags |= B200_TUF_PARK;
+    }
+    if (sparse) {
+        for (int i = 0, e = 0; i < n * n; i++)
+            if (coeffs[i]) { dst[2 * e] = (int16_t)i; dst[2 * e + 1] = coeffs[i]; e++; }
+        t.nnz = (uint16_t)nnz;
+    } else {
+        memcpy(dst, coeffs, (size_t)n * n * 2);
+        t.nnz = B200_TU_DENSE;
+    }
+    t.x = (uint16_t)x; t.y = (uint16_t)y; t.plane = (uint8_t)plane; t.log2 = (uint8_t)log2; t.kind = (uint8_t)kind;
+    t.flags |= (uint8_t)(flags & (B200_TUF_RDPCM | B200_TUF_RDPCM_VERT));
+    t.col_limit = (uint8_t)(col_limit < 0 ? 0 : col_limit > 255 ? 255 : col_limit);
+    t.coeff_off = off;
     if (intra_linked == 1 && !link) return B200_ESTATE;
     r->tu[log2 - 2].push_back(t);
     return 0;

@@ -286,6 +286,7 @@ class FrameSynth:
     def _coefficients(self):
         r = self.rng
         pool_parts, tu_arrays, off = [], {}, 0
+        self._npark = 0
         for log2 in (2, 3, 4, 5):
             lst = self.tu[log2]
             m, n = len(lst), 1 << log2
@@ -313,12 +314,36 @@ class FrameSynth:
                 arr["plane"] = [t[0] for t in lst]; arr["x"] = [t[1] for t in lst]; arr["y"] = [t[2] for t in lst]
                 arr["log2"] = log2; arr["kind"] = kinds; arr["flags"] = [t[4] for t in lst]
                 arr["col_limit"] = np.minimum(col_limit, 255)
-                arr["coeff_off"] = off + np.arange(m) * n * n
-                for k, t in enumerate(lst):
-                    if t[5] is not None:
-                        self.intra[t[5]][8] = int(arr["coeff_off"][k])
-                pool_parts.append(coef.reshape(-1))
-                off += m * n * n
+                # transport as the recorder does: sparse (position, value) pairs unless that is not smaller than the dense
+                # block; PARK TUs carry their index in the parked-residual pool in front of their data
+                flat = coef.reshape(m, n * n)
+                cnt = (flat != 0).sum(axis=1)
+                dense = pcm | (2 * cnt >= n * n)
+                park = np.array([t[5] is not None for t in lst])
+                size = np.where(dense, n * n, 2 * cnt) + 2 * park
+                start = off + np.concatenate(([0], np.cumsum(size)[:-1]))
+                part = np.zeros(int(size.sum()), np.int16)
+                local = start - off
+                if park.any():
+                    po = self._npark + np.arange(int(park.sum())) * n * n
+                    self._npark += int(park.sum()) * n * n
+                    pidx = np.nonzero(park)[0]
+                    part[local[pidx]] = (po & 0xffff).astype(np.uint16).view(np.int16)
+                    part[local[pidx] + 1] = (po >> 16).astype(np.uint16).view(np.int16)
+                    for k, o in zip(pidx, po):
+                        self.intra[lst[k][5]][8] = int(o)
+                data0 = local + 2 * park
+                for k in np.nonzero(dense)[0]:
+                    part[data0[k]:data0[k] + n * n] = flat[k]
+                ti, pos = np.nonzero(np.where(dense[:, None], 0, flat))
+                if len(ti):
+                    rank = np.arange(len(ti)) - np.concatenate(([0], np.cumsum(np.bincount(ti, minlength=m))[:-1]))[ti]
+                    part[data0[ti] + 2 * rank] = pos.astype(np.int16)
+                    part[data0[ti] + 2 * rank + 1] = flat[ti, pos]
+                arr["nnz"] = np.where(dense, W.TU_DENSE, cnt)
+                arr["coeff_off"] = start
+                pool_parts.append(part)
+                off += int(size.sum())
             tu_arrays[log2] = arr
         pool = np.concatenate(pool_parts) if pool_parts else np.zeros(0, np.int16)
         return pool, tu_arrays
@@ -425,7 +450,9 @@ class FrameSynth:
                   blob_bytes=int(blob.nbytes),
                   # algorithmic bytes per stage, SURVEY.md §8(d)
                   bytes_mc=int(st["mc_bytes"]),
-                  bytes_residual=int(st["resid_samples"] * (2 + 2 * B) + st["resid_parked"] * 4),
+                  # coefficient transport is sparse: the pool is read once; non-parked samples are read-modify-written,
+                  # parked residuals are written (int16) for K3
+                  bytes_residual=int(pool.nbytes + st["resid_samples"] * 2 * B + st["resid_parked"] * 2),
                   bytes_intra=int(st["intra_bytes"] + st["resid_parked"] * 2),
                   bytes_deblock=int(2 * B * S + (dbk.nbytes if dbk is not None else 0)) if self.deblock else 0,
                   bytes_sao=int(2 * B * S + (sao.nbytes if sao is not None else 0)) if self.sao else 0)

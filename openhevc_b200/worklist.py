@@ -6,7 +6,8 @@ is what the C recorder (csrc/recorder.cpp) produces for the same table calls.
 import numpy as np
 
 MAGIC = 0x4C573242
-VERSION = 1
+VERSION = 2
+TU_DENSE = 0xFFFF
 (SEC_COEFF, SEC_TU4, SEC_TU8, SEC_TU16, SEC_TU32, SEC_INTRA, SEC_MC, SEC_DBK, SEC_SAO, SEC_COUNT) = range(10)
 
 TU_IDCT, TU_DC, TU_DST, TU_SKIP, TU_BYPASS, TU_PCM = range(6)
@@ -26,7 +27,7 @@ header_dt = np.dtype([
     ("reserved", "<u4", (64 - 12 - 2 * SEC_COUNT,)),
 ])
 tu_dt = np.dtype([("x", "<u2"), ("y", "<u2"), ("plane", "u1"), ("log2", "u1"), ("kind", "u1"), ("flags", "u1"),
-                  ("col_limit", "u1"), ("pad", "u1", (3,)), ("coeff_off", "<u4")])
+                  ("col_limit", "u1"), ("pad", "u1"), ("nnz", "<u2"), ("coeff_off", "<u4")])
 intra_dt = np.dtype([("x", "<u2"), ("y", "<u2"), ("plane", "u1"), ("log2", "u1"), ("mode", "u1"), ("flags", "u1"),
                      ("top_right_size", "u1"), ("bottom_left_size", "u1"), ("pad", "u1", (2,)), ("resid_off", "<u4")])
 mc_dt = np.dtype([("x", "<u2"), ("y", "<u2"), ("w", "u1"), ("h", "u1"), ("plane", "u1"), ("flags", "u1"),
@@ -90,6 +91,22 @@ def split_mc_tiles(recs):
             t["sx0"] += tx; t["sy0"] += ty; t["sx1"] += tx; t["sy1"] += ty
             out.append(t)
     return np.concatenate(out)
+
+
+def tu_dense(t, pool):
+    """(dense NxN coefficients, parked-pool index or None) of one TU record -- mirror of b200_tu_data / b200_tu_expand"""
+    n2 = 1 << (2 * int(t["log2"]))
+    o = int(t["coeff_off"])
+    park = None
+    if t["flags"] & TUF_PARK:
+        park = int(pool[o].astype(np.uint16)) | (int(pool[o + 1].astype(np.uint16)) << 16)
+        o += 2
+    if t["nnz"] == TU_DENSE:
+        return np.array(pool[o:o + n2]), park
+    d = np.zeros(n2, np.int16)
+    e = pool[o:o + 2 * int(t["nnz"])].reshape(-1, 2)
+    d[e[:, 0].astype(np.uint16)] = e[:, 1]
+    return d, park
 
 
 def level_order(intra, width, height, cfi):

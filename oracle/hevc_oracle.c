@@ -513,18 +513,27 @@ int orc_execute_blob(const uint8_t *blob, uint16_t **planes, int n_slots)
     for (int p = 0; p < 3; p++) b200_plane_dims(h->width, h->height, cfi, p, &pw[p], &ph[p]);
     pix_t **cur = planes + 3 * h->cur_slot;
 
-    /* private copy of the pool: residuals are produced in place */
-    const uint32_t n_coeff = h->sec[B200_SEC_COEFF].count;
-    int16_t *pool = (int16_t *)malloc((size_t)(n_coeff + 8) * sizeof(int16_t));
-    if (!pool) return -3;
-    memcpy(pool, blob + h->sec[B200_SEC_COEFF].off, (size_t)n_coeff * sizeof(int16_t));
+    const int16_t *pool = (const int16_t *)(blob + h->sec[B200_SEC_COEFF].off);
+    /* parked residuals (intra TUs): sized by a first pass over the PARK records */
+    size_t park_len = 8;
+    for (int s = B200_SEC_TU4; s <= B200_SEC_TU32; s++) {
+        const B200TuRec *tu = (const B200TuRec *)(blob + h->sec[s].off);
+        for (uint32_t i = 0; i < h->sec[s].count; i++)
+            if (tu[i].flags & B200_TUF_PARK) {
+                uint32_t po = 0;
+                b200_tu_data(&tu[i], pool, &po);
+                if ((size_t)po + (1u << (2 * tu[i].log2)) > park_len) park_len = (size_t)po + (1u << (2 * tu[i].log2));
+            }
+    }
+    int16_t *parked = (int16_t *)calloc(park_len, sizeof(int16_t));
+    if (!parked) return -3;
 
     /* K1 inter */
     const B200McRec *mc = (const B200McRec *)(blob + h->sec[B200_SEC_MC].off);
     for (uint32_t i = 0; i < h->sec[B200_SEC_MC].count; i++) {
         const B200McRec *m = &mc[i];
         const int i0 = m->ref0, i1 = (m->flags & B200_MCF_BI) ? m->ref1 : m->ref0;
-        if (i0 >= h->n_ref || i1 >= h->n_ref || h->ref_slot[i0] >= n_slots || h->ref_slot[i1] >= n_slots) { free(pool); return -4; }
+        if (i0 >= h->n_ref || i1 >= h->n_ref || h->ref_slot[i0] >= n_slots || h->ref_slot[i1] >= n_slots) { free(parked); return -4; }
         const int p = m->plane;
         orc_mc_rec(m, cur[p], pw[p], planes[3 * h->ref_slot[i0] + p], planes[3 * h->ref_slot[i1] + p], pw[p], ph[p], bd);
     }
@@ -533,15 +542,17 @@ int orc_execute_blob(const uint8_t *blob, uint16_t **planes, int n_slots)
         const B200TuRec *tu = (const B200TuRec *)(blob + h->sec[s].off);
         for (uint32_t i = 0; i < h->sec[s].count; i++) {
             const B200TuRec *t = &tu[i];
-            int16_t *c = pool + t->coeff_off;
+            int16_t c[32 * 32];
+            uint32_t po = 0;
+            b200_tu_expand(t, b200_tu_data(t, pool, &po), c);
             const int n = 1 << t->log2, p = t->plane;
             if (t->kind == B200_TU_PCM) {
                 for (int y = 0; y < n; y++) for (int x = 0; x < n; x++) cur[p][(t->y + y) * pw[p] + t->x + x] = (pix_t)c[y * n + x];
                 continue;
             }
             tu_residual(t, c, bd);
-            if (!(t->flags & B200_TUF_PARK))
-                orc_add_residual(cur[p] + t->y * pw[p] + t->x, pw[p], c, n, bd);
+            if (t->flags & B200_TUF_PARK) memcpy(parked + po, c, (size_t)n * n * sizeof(int16_t));
+            else orc_add_residual(cur[p] + t->y * pw[p] + t->x, pw[p], c, n, bd);
         }
     }
     /* K3 intra, decode order */
@@ -551,9 +562,9 @@ int orc_execute_blob(const uint8_t *blob, uint16_t **planes, int n_slots)
         const int p = r->plane;
         orc_intra_rec(r, cur[p], pw[p], bd);
         if (r->resid_off != B200_NO_RESID)
-            orc_add_residual(cur[p] + r->y * pw[p] + r->x, pw[p], pool + r->resid_off, 1 << r->log2, bd);
+            orc_add_residual(cur[p] + r->y * pw[p] + r->x, pw[p], parked + r->resid_off, 1 << r->log2, bd);
     }
-    free(pool);
+    free(parked);
     /* K4 deblock */
     if (h->sec[B200_SEC_DBK].count) {
         B200DbkLayout L;

@@ -69,10 +69,11 @@ static void ref_ctx_free(RefCtx *c)
 
 typedef struct HostFrame { uint8_t *p[3]; int stride[3]; } HostFrame;
 
+typedef struct Parked { uint32_t off; const B200TuRec *t; } Parked;
 static int cmp_park(const void *a, const void *b)
 {
-    const B200TuRec *x = *(const B200TuRec *const *)a, *y = *(const B200TuRec *const *)b;
-    return x->coeff_off < y->coeff_off ? -1 : x->coeff_off > y->coeff_off;
+    const Parked *x = a, *y = b;
+    return x->off < y->off ? -1 : x->off > y->off;
 }
 
 /* ---- K1: inter, following hevc.c:1641-1949 ------------------------------------------------------ */
@@ -187,13 +188,15 @@ static int execute(RefCtx *c, const uint8_t *blob, uint8_t **planes, const int64
         const B200TuRec *tu = (const B200TuRec *)(blob + h->sec[sidx].off);
         for (uint32_t i = 0; i < h->sec[sidx].count; i++) npark += !!(tu[i].flags & B200_TUF_PARK);
     }
-    const B200TuRec **park = malloc((npark + 1) * sizeof(*park));
+    Parked *park = malloc((npark + 1) * sizeof(*park));
     npark = 0;
     for (int sidx = B200_SEC_TU4; sidx <= B200_SEC_TU32; sidx++) {
         const B200TuRec *tu = (const B200TuRec *)(blob + h->sec[sidx].off);
         for (uint32_t i = 0; i < h->sec[sidx].count; i++) {
             const B200TuRec *t = &tu[i];
-            if (t->flags & B200_TUF_PARK) { park[npark++] = t; continue; }
+            uint32_t po = 0;
+            const int16_t *data = b200_tu_data(t, pool, &po);
+            if (t->flags & B200_TUF_PARK) { park[npark].off = po; park[npark++].t = t; continue; }
             const int n = 1 << t->log2, p = t->plane;
             uint8_t *dst = cur->p[p] + (ptrdiff_t)t->y * cur->stride[p] + t->x * B;
             if (t->kind == B200_TU_PCM) {       /* hls_pcm_sample (hevc.c:1587-1623): put_pcm reads the samples from the bitstream */
@@ -202,12 +205,12 @@ static int execute(RefCtx *c, const uint8_t *blob, uint8_t **planes, const int64
                 memset(bits, 0, sizeof(bits));
                 for (int k = 0, bp = 0; k < n * n; k++)
                     for (int bit = c->bd - 1; bit >= 0; bit--, bp++)
-                        if ((pool[t->coeff_off + k] >> bit) & 1) bits[bp >> 3] |= 0x80 >> (bp & 7);
+                        if ((data[k] >> bit) & 1) bits[bp >> 3] |= 0x80 >> (bp & 7);
                 init_get_bits(&gb, bits, n * n * c->bd);
                 d->put_pcm(dst, cur->stride[p], n, n, &gb, c->bd);
                 continue;
             }
-            memcpy(coeffs, pool + t->coeff_off, (size_t)n * n * 2);
+            b200_tu_expand(t, data, coeffs);
             replay_tu_residual(c, t, coeffs);
             d->transform_add[t->log2 - 2](dst, coeffs, cur->stride[p]);
         }
@@ -219,11 +222,11 @@ static int execute(RefCtx *c, const uint8_t *blob, uint8_t **planes, const int64
         replay_intra(c, r);
         if (r->resid_off != B200_NO_RESID) {
             size_t lo = 0, hi = npark;
-            while (lo + 1 < hi) { size_t mid = (lo + hi) / 2; if (park[mid]->coeff_off <= r->resid_off) lo = mid; else hi = mid; }
-            const B200TuRec *t = park[lo];
-            if (!npark || t->coeff_off != r->resid_off) { free(park); return -5; }
-            const int n = 1 << r->log2;
-            memcpy(coeffs, pool + t->coeff_off, (size_t)n * n * 2);
+            while (lo + 1 < hi) { size_t mid = (lo + hi) / 2; if (park[mid].off <= r->resid_off) lo = mid; else hi = mid; }
+            if (!npark || park[lo].off != r->resid_off) { free(park); return -5; }
+            const B200TuRec *t = park[lo].t;
+            uint32_t po = 0;
+            b200_tu_expand(t, b200_tu_data(t, pool, &po), coeffs);
             replay_tu_residual(c, t, coeffs);
             d->transform_add[r->log2 - 2](cur->p[r->plane] + (ptrdiff_t)r->y * cur->stride[r->plane] + r->x * B, coeffs, cur->stride[r->plane]);
         }

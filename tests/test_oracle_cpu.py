@@ -122,21 +122,19 @@ def test_recorder_matches_numpy_builder(built):
     for k in range(4):
         for t in secs[W.SEC_TU4 + k]:
             if t["flags"] & W.TUF_PARK:
-                parked[int(t["coeff_off"])] = t
+                parked[W.tu_dense(t, pool)[1]] = t
     for ir in secs[W.SEC_INTRA]:
         assert lib.b200_rec_intra(r, int(ir["plane"]), int(ir["x"]), int(ir["y"]), int(ir["log2"]), int(ir["mode"]), int(ir["flags"]),
                                   int(ir["top_right_size"]), int(ir["bottom_left_size"])) == 0
         if ir["resid_off"] != W.NO_RESID:
             t = parked[int(ir["resid_off"])]
-            n = 1 << int(t["log2"])
-            c = np.ascontiguousarray(pool[int(t["coeff_off"]):int(t["coeff_off"]) + n * n])
+            c = np.ascontiguousarray(W.tu_dense(t, pool)[0])
             assert lib.b200_rec_tu(r, int(t["plane"]), int(t["x"]), int(t["y"]), int(t["log2"]), int(t["kind"]), int(t["flags"]), int(t["col_limit"]), c.ctypes.data, 1) == 0
     for k in range(4):
         for t in secs[W.SEC_TU4 + k]:
             if t["flags"] & W.TUF_PARK:
                 continue
-            n = 1 << int(t["log2"])
-            c = np.ascontiguousarray(pool[int(t["coeff_off"]):int(t["coeff_off"]) + n * n])
+            c = np.ascontiguousarray(W.tu_dense(t, pool)[0])
             assert lib.b200_rec_tu(r, int(t["plane"]), int(t["x"]), int(t["y"]), int(t["log2"]), int(t["kind"]), int(t["flags"]), int(t["col_limit"]), c.ctypes.data, -1) == 0
     for m in secs[W.SEC_MC]:
         mm = np.array([m])
