@@ -245,7 +245,7 @@ def main():
                                   "gbps": sum(abytes.values()) / (stage_ms["total"] * 1e-3) / 1e9}}
 
     # ---- e2e: pinned host work list -> H2D -> kernels -> D2H of the reconstructed picture, every picture ----------
-    host_out = [eng.new_host_frame(pinned=True) for _ in range(8)]
+    host_out = [eng.new_host_frame(pinned=True) for _ in range(24)]
 
     class E2E(FP.GpuBackend):
         def __init__(self, *a):
@@ -256,9 +256,9 @@ def main():
             a = self.k % 16
             self.eng.upload(blobs[pic.blob], a)
             self.eng.execute(a, pic.cur_slot, pic.ref_slots)
-            self.eng.readback(pic.cur_slot, host_out[self.k % 8], sync=False)
+            self.eng.readback(pic.cur_slot, host_out[self.k % 24], sync=False)
             self.k += 1
-            if self.k % 8 == 0:                 # bound the run-ahead of the host thread (host buffers are reused)
+            if self.k % 16 == 0:                # bound the run-ahead of the host thread (arenas and host buffers are reused)
                 self.eng.sync()
 
     be2 = E2E(eng, dpb, slot_bytes, world, list(range(FP.N_BLOBS)))

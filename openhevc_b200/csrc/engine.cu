@@ -416,8 +416,12 @@ extern "C" int b200_slot_readback(B200Ctx *ctx, int slot, void *const planes[3],
     CU(cudaSetDevice(ctx->cfg.device));
     const int B = ctx->cfg.bit_depth > 8 ? 2 : 1;
     CU(cudaStreamWaitEvent(ctx->st_down, ctx->slot_done[slot], 0));
-    for (int p = 0; p < 3; p++)
-        CU(cudaMemcpy2DAsync(planes[p], (size_t)strides[p], ctx->slot_desc[slot].p[p].base, ctx->pitch[p], (size_t)ctx->pw[p] * B, ctx->ph[p], cudaMemcpyDeviceToHost, ctx->st_down));
+    for (int p = 0; p < 3; p++) {
+        if (strides[p] == ctx->pitch[p])     // contiguous on both sides: one linear copy
+            CU(cudaMemcpyAsync(planes[p], ctx->slot_desc[slot].p[p].base, (size_t)ctx->pitch[p] * ctx->ph[p], cudaMemcpyDeviceToHost, ctx->st_down));
+        else
+            CU(cudaMemcpy2DAsync(planes[p], (size_t)strides[p], ctx->slot_desc[slot].p[p].base, ctx->pitch[p], (size_t)ctx->pw[p] * B, ctx->ph[p], cudaMemcpyDeviceToHost, ctx->st_down));
+    }
     return 0;
 }
 
