@@ -1,0 +1,40 @@
+#!/bin/bash
+# TEST INFRASTRUCTURE — builds the reference decoder WITH the B200 hooks of INTEGRATION.md into
+# oracle/_ref/libohevc_b200.so: the four files that receive a hook are copied to oracle/_ref/patched/ (git-ignored),
+# the hook lines are inserted with sed, every other object is reused from the plain reference build.
+# Needs /root/reference; on the GPU box the prebuilt library is used.
+set -euo pipefail
+REF=${REF:-/root/reference}
+HERE=$(cd "$(dirname "$0")" && pwd)
+OUT=$HERE/_ref
+ROOT=$(dirname "$HERE")
+if [ ! -d "$REF/libavcodec" ]; then echo "build_patched: $REF not present - keeping prebuilt"; exit 0; fi
+[ -f "$OUT/libohevc_ref.so" ] || "$HERE/build_ref.sh"
+P=$OUT/patched/libavcodec
+mkdir -p "$P" "$OUT/obj_b200"
+for f in hevc.c hevcdsp.c hevcpred.c videodsp.c; do cp "$REF/libavcodec/$f" "$P/$f"; done
+inc='#include "b200hevc_tables.h"'
+# table hooks: one more arch-init call, exactly where the x86 / arm ones are (hevcdsp.c:1326-1327, hevcpred.c:84, videodsp.c:57-58)
+sed -i -e "0,/^#include/s//$inc\n#include/" \
+       -e 's/^\(\s*\)if (ARCH_ARM) ff_hevcdsp_init_arm(hevcdsp, bit_depth);/&\n\1ff_hevcdsp_init_b200(hevcdsp, bit_depth);/' "$P/hevcdsp.c"
+sed -i -e "0,/^#include/s//$inc\n#include/" \
+       -e 's/^\(\s*\)if (ARCH_X86) ff_hevcpred_init_x86(hpc, bit_depth);/&\n\1ff_hevcpred_init_b200(hpc, bit_depth);/' "$P/hevcpred.c"
+sed -i -e "0,/^#include/s//$inc\n#include/" \
+       -e '/ff_videodsp_init_x86(ctx, bpc);/a\    ff_videodsp_init_b200(ctx, bpc);' "$P/videodsp.c"
+# frame life cycle (hevc.c:3271 / 3446 / 4145)
+sed -i -e "0,/^#include/s//$inc\n#include/" \
+       -e 's/^\(\s*\)ff_thread_finish_setup(s->avctx);/\1if ((ret = b200_frame_begin(s)) < 0) goto fail;\n&/' \
+       -e 's/^\(\s*\)s->is_decoded = 1;/&\n\1if ((ret = b200_frame_end(s)) < 0) goto fail;/' \
+       -e 's|^\(\s*\)/\* verify the SEI checksum \*/|\1if (s->is_decoded \&\& s->ref) b200_frame_readback(s, s->ref->frame);\n&|' "$P/hevc.c"
+for pat in ff_hevcdsp_init_b200 ff_hevcpred_init_b200 ff_videodsp_init_b200 b200_frame_begin b200_frame_end b200_frame_readback; do
+  grep -q "$pat" "$P"/*.c || { echo "hook $pat was not inserted" >&2; exit 1; }
+done
+CFLAGS=$(cat "$OUT/cflags.txt")
+for f in hevc hevcdsp hevcpred videodsp; do
+  gcc $CFLAGS -fPIC -std=gnu99 -w -DPIC -I"$OUT/gen" -I"$REF/libavcodec" -I"$REF" -I"$REF/gpac/modules/openhevc_dec" -I"$ROOT/include" \
+      -c "$P/$f.c" -o "$OUT/obj_b200/libavcodec_$f.o"
+done
+objs=$(ls "$OUT"/obj/*.o | grep -v -e 'libavcodec_hevc\.o' -e 'libavcodec_hevcdsp\.o' -e 'libavcodec_hevcpred\.o' -e 'libavcodec_videodsp\.o')
+gcc -shared -o "$OUT/libohevc_b200.so" $objs "$OUT"/obj_b200/*.o -L"$ROOT/openhevc_b200" -lb200hevc_shim -lb200hevc \
+    -Wl,-rpath,'$ORIGIN/../../openhevc_b200' -lm -lpthread
+echo "built $OUT/libohevc_b200.so"

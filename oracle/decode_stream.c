@@ -1,0 +1,73 @@
+/*
+ * decode_stream.c — TEST INFRASTRUCTURE: headless equivalent of the reference's CLI (main_hm/main.c:115-309
+ * without SDL): decodes an Annex-B file through the public libOpenHevc* API (single thread) and prints one line
+ * per output picture with the MD5 of each plane.  Linked once against the plain reference build
+ * (decode_ref) and once against the build carrying the B200 hooks (decode_b200); identical output == the
+ * drop-in is bit-exact on that stream.
+ */
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <time.h>
+#include "openHevcWrapper.h"
+#include "libavformat/avformat.h"
+#include "libavutil/md5.h"
+
+static void plane_md5(const uint8_t *p, int pitch, int w_bytes, int h, char *hex)
+{
+    struct AVMD5 *m = av_md5_alloc();
+    uint8_t d[16];
+    av_md5_init(m);
+    for (int y = 0; y < h; y++) av_md5_update(m, p + (size_t)y * pitch, w_bytes);
+    av_md5_final(m, d);
+    for (int i = 0; i < 16; i++) sprintf(hex + 2 * i, "%02x", d[i]);
+    av_free(m);
+}
+
+int main(int argc, char **argv)
+{
+    if (argc < 2) { fprintf(stderr, "usage: %s stream.hevc [quiet]\n", argv[0]); return 2; }
+    const int quiet = argc > 2;
+    OpenHevc_Handle h = libOpenHevcInit(1, 1);
+    if (!h) return 3;
+    libOpenHevcSetCheckMD5(h, 0);
+    av_register_all();
+    AVFormatContext *fmt = avformat_alloc_context();
+    if (avformat_open_input(&fmt, argv[1], NULL, NULL) != 0) { fprintf(stderr, "cannot open %s\n", argv[1]); return 4; }
+    int vs = av_find_best_stream(fmt, AVMEDIA_TYPE_VIDEO, -1, -1, NULL, 0);
+    if (vs < 0) { fprintf(stderr, "no video stream\n"); return 5; }
+    libOpenHevcSetDebugMode(h, 0);
+    libOpenHevcStartDecoder(h);
+    libOpenHevcSetTemporalLayer_id(h, 7);
+    libOpenHevcSetActiveDecoders(h, 0);
+    libOpenHevcSetViewLayers(h, 0);
+    AVPacket pkt;
+    int stop = 0, stop_dec = 0, nframes = 0;
+    struct timespec t0, t1;
+    clock_gettime(CLOCK_MONOTONIC, &t0);
+    while (!stop) {
+        if (!stop_dec && av_read_frame(fmt, &pkt) < 0) stop_dec = 1;
+        if (stop_dec || pkt.stream_index == vs) {
+            int got = libOpenHevcDecode(h, stop_dec ? NULL : pkt.data, stop_dec ? 0 : pkt.size, stop_dec ? 0 : pkt.pts);
+            if (got > 0) {
+                OpenHevc_Frame f;
+                libOpenHevcGetOutput(h, 1, &f);
+                const int B = f.frameInfo.nBitDepth > 8 ? 2 : 1;
+                const int cw = f.frameInfo.chromat_format == YUV444 ? f.frameInfo.nWidth : f.frameInfo.nWidth / 2;
+                const int ch = f.frameInfo.chromat_format == YUV420 ? f.frameInfo.nHeight / 2 : f.frameInfo.nHeight;
+                char a[33], b[33], c[33];
+                plane_md5((const uint8_t *)f.pvY, f.frameInfo.nYPitch, f.frameInfo.nWidth * B, f.frameInfo.nHeight, a);
+                plane_md5((const uint8_t *)f.pvU, f.frameInfo.nUPitch, cw * B, ch, b);
+                plane_md5((const uint8_t *)f.pvV, f.frameInfo.nVPitch, cw * B, ch, c);
+                if (!quiet) printf("frame %d %dx%d bd%d %s %s %s\n", nframes, f.frameInfo.nWidth, f.frameInfo.nHeight, f.frameInfo.nBitDepth, a, b, c);
+                nframes++;
+            } else if (stop_dec) stop = 1;
+        }
+        if (!stop_dec) av_free_packet(&pkt);
+    }
+    clock_gettime(CLOCK_MONOTONIC, &t1);
+    double sec = (t1.tv_sec - t0.tv_sec) + 1e-9 * (t1.tv_nsec - t0.tv_nsec);
+    printf("frames %d time %.3f fps %.2f\n", nframes, sec, nframes / (sec > 0 ? sec : 1));
+    libOpenHevcClose(h);
+    return 0;
+}

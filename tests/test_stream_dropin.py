@@ -1,0 +1,46 @@
+"""The real decoder, end to end: committed synthetic Annex-B streams (tools/hevc_stream_gen.py) decoded by
+ (a) the UNMODIFIED reference (oracle/_ref/decode_ref -> libohevc_ref.so) and
+ (b) the reference carrying the three table hooks + three frame hooks of INTEGRATION.md
+     (oracle/_ref/decode_b200 -> libohevc_b200.so -> libb200hevc_shim.so -> GPU),
+both through the public libOpenHevc* API, single thread.  Per-picture plane MD5s must be identical
+(BASELINE config 1: 832x480 8-bit, I pictures, bit-exact gate)."""
+import glob
+import os
+import subprocess
+
+import pytest
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+REFDIR = os.path.join(os.path.dirname(HERE), "oracle", "_ref")
+STREAMS = sorted(glob.glob(os.path.join(HERE, "golden", "streams", "*.hevc")))
+
+
+def run(binary, stream):
+    out = subprocess.run([os.path.join(REFDIR, binary), stream], capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0, out.stderr[-2000:]
+    return [l for l in out.stdout.splitlines() if l.startswith("frame ")]
+
+
+def test_streams_committed():
+    assert len(STREAMS) >= 3
+
+
+@pytest.mark.parametrize("stream", STREAMS, ids=[os.path.basename(s) for s in STREAMS])
+def test_reference_decoder_reproduces_committed_md5(stream):
+    """CPU: the plain reference build still produces the committed hashes (pins the fixtures)"""
+    if not os.path.exists(os.path.join(REFDIR, "decode_ref")):
+        pytest.skip("oracle/_ref/decode_ref not built")
+    want = open(stream[:-5] + ".md5").read().splitlines()
+    assert run("decode_ref", stream) == want
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("stream", STREAMS, ids=[os.path.basename(s) for s in STREAMS])
+def test_hooked_decoder_is_bit_exact_on_the_same_stream(stream):
+    if not os.path.exists(os.path.join(REFDIR, "decode_b200")):
+        pytest.skip("oracle/_ref/decode_b200 not built")
+    want = open(stream[:-5] + ".md5").read().splitlines()
+    got = run("decode_b200", stream)
+    assert len(got) == len(want)
+    for g, w in zip(got, want):
+        assert g == w, f"picture differs:\n got {g}\nwant {w}"

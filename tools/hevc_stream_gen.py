@@ -1,0 +1,688 @@
+#!/usr/bin/env python
+"""Synthetic Annex-B HEVC stream writer (intra pictures) — TEST INFRASTRUCTURE.
+
+No encoder or sample bit stream exists in the build environment, so the streams that drive the
+*real* reference decoder (oracle/_ref/decode_ref vs decode_b200, tests/test_stream_*.py) are written here: a random
+but syntax-valid coding structure (CTB quadtrees, 2Nx2N / NxN intra CUs with MPM / remaining-mode signalling,
+residual quadtrees, residual_coding() with last-position, coded-sub-block, significance, greater1/2, remaining
+levels and signs, per-CTB SAO, in-loop deblocking on) entropy-coded with a from-scratch CABAC *encoder*
+(ITU-T H.265 9.3.4).  The context initialisation values and their layout are standard tables; they are parsed at
+generation time from the reference source (libavcodec/hevc_cabac.c: num_bins_in_se / init_values) so that the
+context numbering is guaranteed to be the decoder's — which is why this tool runs in the build container only;
+the streams it produces are committed under tests/golden/.
+"""
+import argparse
+import os
+import re
+import sys
+
+import numpy as np
+
+REF = os.environ.get("REF", "/root/reference")
+
+# ----------------------------------------------------------------------------------------------------------------
+# bit writing / NAL units
+# ----------------------------------------------------------------------------------------------------------------
+class BitWriter:
+    def __init__(self):
+        self.bits = []
+
+    def u(self, n, v):
+        for i in range(n - 1, -1, -1):
+            self.bits.append((v >> i) & 1)
+
+    def ue(self, v):
+        v += 1
+        n = v.bit_length()
+        self.u(n - 1, 0)
+        self.u(n, v)
+
+    def se(self, v):
+        self.ue(2 * v - 1 if v > 0 else -2 * v)
+
+    def trailing(self):
+        self.bits.append(1)
+        while len(self.bits) % 8:
+            self.bits.append(0)
+
+    def bytes(self):
+        assert len(self.bits) % 8 == 0
+        return bytes(int("".join(map(str, self.bits[i:i + 8])), 2) for i in range(0, len(self.bits), 8))
+
+
+def nal(nal_type, payload, layer=0, tid=0):
+    hdr = bytes([(nal_type << 1) | (layer >> 5), ((layer & 31) << 3) | (tid + 1)])
+    out, zeros = bytearray(), 0
+    for b in payload:                     # emulation prevention
+        if zeros >= 2 and b <= 3:
+            out.append(3)
+            zeros = 0
+        out.append(b)
+        zeros = zeros + 1 if b == 0 else 0
+    return b"\x00\x00\x00\x01" + hdr + bytes(out)
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# CABAC encoder (H.265 9.3.4.x, encoder side as in the HM description)
+# ----------------------------------------------------------------------------------------------------------------
+RANGE_TAB_LPS = [
+    [128, 176, 208, 240], [128, 167, 197, 227], [128, 158, 187, 216], [123, 150, 178, 205], [116, 142, 169, 195], [111, 135, 160, 185], [105, 128, 152, 175], [100, 122, 144, 166],
+    [95, 116, 137, 158], [90, 110, 130, 150], [85, 104, 123, 142], [81, 99, 117, 135], [77, 94, 111, 128], [73, 89, 105, 122], [69, 85, 100, 116], [66, 80, 95, 110],
+    [62, 76, 90, 104], [59, 72, 86, 99], [56, 69, 81, 94], [53, 65, 77, 89], [51, 62, 73, 85], [48, 59, 69, 80], [46, 56, 66, 76], [43, 53, 63, 72],
+    [41, 50, 59, 69], [39, 48, 56, 65], [37, 45, 54, 62], [35, 43, 51, 59], [33, 41, 48, 56], [32, 39, 46, 53], [30, 37, 43, 50], [29, 35, 41, 48],
+    [27, 33, 39, 45], [26, 31, 37, 43], [24, 30, 35, 41], [23, 28, 33, 39], [22, 27, 32, 37], [21, 26, 30, 35], [20, 24, 29, 33], [19, 23, 27, 31],
+    [18, 22, 26, 30], [17, 21, 25, 28], [16, 20, 23, 27], [15, 19, 22, 25], [14, 18, 21, 24], [14, 17, 20, 23], [13, 16, 19, 22], [12, 15, 18, 21],
+    [12, 14, 17, 20], [11, 14, 16, 19], [11, 13, 15, 18], [10, 12, 15, 17], [10, 12, 14, 16], [9, 11, 13, 15], [9, 11, 12, 14], [8, 10, 12, 14],
+    [8, 9, 11, 13], [7, 9, 11, 12], [7, 9, 10, 12], [7, 8, 10, 11], [6, 8, 9, 11], [6, 7, 9, 10], [6, 7, 8, 9], [2, 2, 2, 2]]
+TRANS_LPS = [0, 0, 1, 2, 2, 4, 4, 5, 6, 7, 8, 9, 9, 11, 11, 12, 13, 13, 15, 15, 16, 16, 18, 18, 19, 19, 21, 21, 22, 22, 23, 24,
+             24, 25, 26, 26, 27, 27, 28, 29, 29, 30, 30, 30, 31, 32, 32, 33, 33, 33, 34, 34, 35, 35, 35, 36, 36, 36, 37, 37, 37, 38, 38, 63]
+
+
+def verify_tables_against_reference():
+    """the range table above is typed from the standard; check it against the decoder's own generated table"""
+    import ctypes
+    so = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "oracle", "_ref", "libohevc_ref.so")
+    if not os.path.exists(so):
+        return
+    lib = ctypes.CDLL(so)
+    lib.ff_init_cabac_states()
+    tab = (ctypes.c_uint8 * (512 + 4 * 2 * 64 + 4 * 64 + 63)).in_dll(lib, "ff_h264_cabac_tables")
+    for q in range(4):
+        for st in range(64):
+            for mps in range(2):
+                assert tab[512 + 128 * q + 2 * st + mps] == RANGE_TAB_LPS[st][q], (q, st)
+    for st in range(63):
+        assert tab[1024 + 128 + 2 * st] >> 1 == min(st + 1, 62), st                   # MPS transition
+    for st in range(1, 63):
+        assert tab[1024 + 127 - 2 * st] >> 1 == TRANS_LPS[st], (st, tab[1024 + 127 - 2 * st])   # LPS transition
+
+
+class Cabac:
+    def __init__(self, init_values, qp):
+        self.low, self.range, self.outstanding, self.first = 0, 510, 0, True
+        self.bits = []
+        self.state = []
+        for iv in init_values:
+            m, n = (iv >> 4) * 5 - 45, ((iv & 15) << 3) - 16
+            pre = min(max(((m * min(max(qp, 0), 51)) >> 4) + n, 1), 126)
+            self.state.append([pre - 64, 1] if pre > 63 else [63 - pre, 0])
+
+    def _put(self, b):
+        if self.first:
+            self.first = False
+        else:
+            self.bits.append(b)
+        while self.outstanding:
+            self.bits.append(1 - b)
+            self.outstanding -= 1
+
+    def _renorm(self):
+        while self.range < 256:
+            if self.low < 256:
+                self._put(0)
+            elif self.low >= 512:
+                self.low -= 512
+                self._put(1)
+            else:
+                self.low -= 256
+                self.outstanding += 1
+            self.range <<= 1
+            self.low <<= 1
+
+    def encode(self, ctx, b):
+        st = self.state[ctx]
+        lps = RANGE_TAB_LPS[st[0]][(self.range >> 6) & 3]
+        self.range -= lps
+        if b != st[1]:
+            self.low += self.range
+            self.range = lps
+            if st[0] == 0:
+                st[1] = 1 - st[1]
+            st[0] = TRANS_LPS[st[0]]
+        else:
+            st[0] = min(st[0] + 1, 62)
+        self._renorm()
+
+    def bypass(self, b):
+        self.low <<= 1
+        if b:
+            self.low += self.range
+        if self.low >= 1024:
+            self._put(1)
+            self.low -= 1024
+        elif self.low < 512:
+            self._put(0)
+        else:
+            self.low -= 512
+            self.outstanding += 1
+
+    def bypass_bits(self, n, v):
+        for i in range(n - 1, -1, -1):
+            self.bypass((v >> i) & 1)
+
+    def terminate(self, b):
+        self.range -= 2
+        if b:
+            self.low += self.range
+            self.range = 2
+            self._renorm()
+            self._put((self.low >> 9) & 1)
+            self.bits.append((self.low >> 8) & 1)
+            self.bits.append(1)                      # rbsp_stop_one_bit doubles as the last written bit (9.3.4.5)
+        else:
+            self._renorm()
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# context layout, parsed from the decoder's own tables
+# ----------------------------------------------------------------------------------------------------------------
+def load_contexts():
+    src = open(os.path.join(REF, "libavcodec", "hevc_cabac.c")).read()
+    src = re.sub(r"#if COM16_C806_EMT.*?#endif", "", src, flags=re.S)
+    body = src[src.index("num_bins_in_se[]"):]
+    body = body[body.index("{") + 1:body.index("};")]
+    names, counts = [], []
+    for m in re.finditer(r"(\d+)\s*,\s*//\s*([A-Za-z0-9_,\[\] ]+)", body):
+        counts.append(int(m.group(1)))
+        names.append(m.group(2).strip())
+    off, o = {}, 0
+    for nme, c in zip(names, counts):
+        off[nme] = o
+        o += c
+    iv = src[src.index("init_values[3][HEVC_CONTEXTS]"):]
+    first = iv[iv.index("{", iv.index("{") + 1) + 1:]
+    first = first[:first.index("},")]
+    first = re.sub(r"//.*", "", first).replace("CNU", "154")
+    vals = [int(v) for v in re.findall(r"\d+", first)]
+    assert len(vals) == o, (len(vals), o)
+    return off, vals
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# scans (6.5.3 - 6.5.5)
+# ----------------------------------------------------------------------------------------------------------------
+def diag_scan(n):
+    out, x, y = [], 0, 0
+    while len(out) < n * n:
+        while y >= 0:
+            if x < n and y < n:
+                out.append((x, y))
+            y -= 1
+            x += 1
+        y, x = x, 0
+    return out
+
+
+def horiz_scan(n):
+    return [(x, y) for y in range(n) for x in range(n)]
+
+
+def scan_tables(log2, scan_idx):
+    """(sub-block order, position order inside a sub-block) as lists of (x, y)"""
+    nsb = 1 << (log2 - 2)
+    if scan_idx == 0:
+        return diag_scan(nsb), diag_scan(4)
+    if scan_idx == 1:
+        return horiz_scan(nsb), horiz_scan(4)
+    return [(y, x) for (x, y) in horiz_scan(nsb)], [(y, x) for (x, y) in horiz_scan(4)]
+
+
+SIG_CTX_4x4 = [0, 1, 4, 5, 2, 3, 4, 5, 6, 6, 8, 8, 7, 7, 8, 8]
+
+
+class StreamGen:
+    def __init__(self, width, height, bit_depth=8, seed=1, qp=30, sao=True, ctb_log2=6):
+        self.W, self.H, self.bd, self.qp, self.sao, self.ctb_log2 = width, height, bit_depth, qp, sao, ctb_log2
+        self.rng = np.random.default_rng(seed)
+        self.off, self.init_vals = load_contexts()
+        self.min_cb_log2, self.min_tb_log2, self.max_tb_log2 = 3, 2, 5
+        self.max_th_depth_intra = 2
+
+    # ---- parameter sets -------------------------------------------------------------------------------------
+    def ptl(self, w):
+        w.u(2, 0); w.u(1, 0); w.u(5, 2 if self.bd > 8 else 1)            # profile space, tier, profile idc
+        for i in range(32):
+            w.u(1, 1 if i in (1, 2) else 0)
+        w.u(1, 1); w.u(1, 0); w.u(1, 0); w.u(1, 1)                        # progressive, interlaced, non-packed, frame-only
+        w.u(16, 0); w.u(16, 0); w.u(12, 0)
+        w.u(8, 153)                                                        # level 5.1
+
+    def vps(self):
+        w = BitWriter()
+        w.u(4, 0); w.u(2, 3); w.u(6, 0); w.u(3, 0); w.u(1, 1); w.u(16, 0xFFFF)
+        self.ptl(w)
+        w.u(1, 1); w.ue(4); w.ue(0); w.ue(0)                              # sub_layer_ordering_info, dpb 5, reorder 0, latency
+        w.u(6, 0); w.ue(0)                                                 # max_layer_id, num_layer_sets_minus1
+        w.u(1, 0)                                                          # timing info
+        w.u(1, 0)                                                          # extension
+        w.trailing()
+        return nal(32, w.bytes())
+
+    def sps(self):
+        w = BitWriter()
+        w.u(4, 0); w.u(3, 0); w.u(1, 1)
+        self.ptl(w)
+        w.ue(0)                                                            # sps id
+        w.ue(1)                                                            # chroma_format_idc 4:2:0
+        w.ue(self.W); w.ue(self.H)
+        w.u(1, 0)                                                          # conformance window
+        w.ue(self.bd - 8); w.ue(self.bd - 8)
+        w.ue(4)                                                            # log2_max_poc_lsb - 4
+        w.u(1, 1); w.ue(4); w.ue(0); w.ue(0)
+        w.ue(self.min_cb_log2 - 3); w.ue(self.ctb_log2 - self.min_cb_log2)
+        w.ue(self.min_tb_log2 - 2); w.ue(self.max_tb_log2 - self.min_tb_log2)
+        w.ue(2); w.ue(self.max_th_depth_intra)                             # max_transform_hierarchy_depth inter / intra
+        w.u(1, 0)                                                          # scaling lists
+        w.u(1, 0)                                                          # amp
+        w.u(1, 1 if self.sao else 0)                                       # sample_adaptive_offset_enabled
+        w.u(1, 0)                                                          # pcm
+        w.ue(0)                                                            # num_short_term_ref_pic_sets
+        w.u(1, 0)                                                          # long term refs
+        w.u(1, 0)                                                          # temporal mvp
+        w.u(1, 1)                                                          # strong intra smoothing
+        w.u(1, 0)                                                          # vui
+        w.u(1, 0)                                                          # extension
+        w.trailing()
+        return nal(33, w.bytes())
+
+    def pps(self):
+        w = BitWriter()
+        w.ue(0); w.ue(0)
+        w.u(1, 0); w.u(1, 0); w.u(3, 0)                                    # dependent slices, output flag, extra bits
+        w.u(1, 0)                                                          # sign data hiding
+        w.u(1, 0)                                                          # cabac_init_present
+        w.ue(0); w.ue(0)
+        w.se(0)                                                            # init_qp_minus26
+        w.u(1, 0)                                                          # constrained intra pred
+        w.u(1, 0)                                                          # transform skip
+        w.u(1, 0)                                                          # cu_qp_delta
+        w.se(0); w.se(0)                                                   # cb / cr qp offsets
+        w.u(1, 0)                                                          # slice chroma qp offsets present
+        w.u(1, 0); w.u(1, 0)                                               # weighted pred / bipred
+        w.u(1, 0)                                                          # transquant bypass
+        w.u(1, 0); w.u(1, 0)                                               # tiles, wpp
+        w.u(1, 1)                                                          # loop filter across slices
+        w.u(1, 0)                                                          # deblocking filter control present
+        w.u(1, 0)                                                          # scaling list data
+        w.u(1, 0)                                                          # lists modification
+        w.ue(0)                                                            # log2_parallel_merge_level - 2
+        w.u(1, 0)                                                          # slice header extension
+        w.u(1, 0)                                                          # pps extension
+        w.trailing()
+        return nal(34, w.bytes())
+
+    # ---- slice ----------------------------------------------------------------------------------------------------
+    def slice_nal(self):
+        w = BitWriter()
+        w.u(1, 1)                                                          # first_slice_segment_in_pic
+        w.u(1, 0)                                                          # no_output_of_prior_pics (IRAP)
+        w.ue(0)                                                            # pps id
+        w.ue(2)                                                            # slice_type I
+        if self.sao:
+            w.u(1, 1); w.u(1, 1)                                           # slice_sao_luma / chroma
+        w.se(self.qp - 26)                                                 # slice_qp_delta
+        if self.sao or True:
+            w.u(1, 1)                                                      # slice_loop_filter_across_slices_enabled
+        w.bits.append(1)                                                   # byte_alignment()
+        while len(w.bits) % 8:
+            w.bits.append(0)
+        self.c = Cabac(self.init_vals, self.qp)
+        self.slice_data()
+        body = w.bits + self.c.bits
+        while len(body) % 8:
+            body.append(0)
+        wb = BitWriter()
+        wb.bits = body
+        return nal(19, wb.bytes())                                         # IDR_W_RADL
+
+    def slice_data(self):
+        ctb = 1 << self.ctb_log2
+        self.cw, self.ch = (self.W + ctb - 1) >> self.ctb_log2, (self.H + ctb - 1) >> self.ctb_log2
+        self.ct_depth = np.zeros((self.H >> 3, self.W >> 3), np.int32)
+        self.ipm = np.ones((self.H >> 2, self.W >> 2), np.int32)           # INTRA_DC default
+        n = self.cw * self.ch
+        for a in range(n):
+            self.rx, self.ry = a % self.cw, a // self.cw
+            if self.sao:
+                self.sao_syntax()
+            self.quadtree(self.rx << self.ctb_log2, self.ry << self.ctb_log2, self.ctb_log2, 0)
+            self.c.terminate(1 if a == n - 1 else 0)                       # end_of_slice_segment_flag
+
+    def sao_syntax(self):
+        c, r, o = self.c, self.rng, self.off
+        if self.rx > 0:
+            m = int(r.random() < 0.2)
+            c.encode(o["sao_merge_flag"], m)
+            if m:
+                return
+        if self.ry > 0:
+            m = int(r.random() < 0.2)
+            c.encode(o["sao_merge_flag"], m)
+            if m:
+                return
+        for cidx in range(2):                                              # Cr shares type / class with Cb
+            t = int(r.choice([0, 1, 2], p=[0.3, 0.3, 0.4]))
+            c.encode(o["sao_type_idx"], int(t != 0))
+            if t:
+                c.bypass(0 if t == 1 else 1)
+            planes = [0] if cidx == 0 else [1, 2]
+            if not t:
+                continue
+            for p in planes:
+                maxv = (1 << (min(self.bd, 10) - 5)) - 1
+                absv = [int(r.integers(0, maxv + 1)) for _ in range(4)]
+                for v in absv:
+                    for k in range(v):
+                        c.bypass(1)
+                    if v < maxv:
+                        c.bypass(0)
+                if t == 1:
+                    for v in absv:
+                        if v:
+                            c.bypass(int(r.integers(0, 2)))
+                    c.bypass_bits(5, int(r.integers(0, 32)))
+                elif p != 2:
+                    c.bypass_bits(2, int(r.integers(0, 4)))
+
+    def quadtree(self, x0, y0, log2, depth):
+        c, o = self.c, self.off
+        size = 1 << log2
+        if x0 + size <= self.W and y0 + size <= self.H and log2 > self.min_cb_log2:
+            inc = 0
+            if x0 > 0:
+                inc += int(self.ct_depth[y0 >> 3, (x0 >> 3) - 1] > depth)
+            if y0 > 0:
+                inc += int(self.ct_depth[(y0 >> 3) - 1, x0 >> 3] > depth)
+            split = int(self.rng.random() < {6: 0.9, 5: 0.65, 4: 0.45}[log2])
+            c.encode(o["split_coding_unit_flag"] + inc, split)
+        else:
+            split = int(log2 > self.min_cb_log2)
+        if split:
+            h = size >> 1
+            for dx, dy in ((0, 0), (h, 0), (0, h), (h, h)):
+                if x0 + dx < self.W and y0 + dy < self.H:
+                    self.quadtree(x0 + dx, y0 + dy, log2 - 1, depth + 1)
+        else:
+            self.coding_unit(x0, y0, log2, depth)
+
+    def mpm_candidates(self, x0, y0):
+        ctb = 1 << self.ctb_log2
+        left = self.ipm[y0 >> 2, (x0 >> 2) - 1] if x0 > 0 else 1
+        up = self.ipm[(y0 >> 2) - 1, x0 >> 2] if (y0 > 0 and (y0 - 1) >= (y0 // ctb) * ctb) else 1
+        if left == up:
+            if left < 2:
+                return [0, 1, 26]
+            return [left, 2 + ((left - 2 - 1 + 32) & 31), 2 + ((left - 2 + 1) & 31)]
+        cand = [left, up]
+        if 0 not in cand:
+            cand.append(0)
+        elif 1 not in cand:
+            cand.append(1)
+        else:
+            cand.append(26)
+        return cand
+
+    def coding_unit(self, x0, y0, log2, depth):
+        c, o, r = self.c, self.off, self.rng
+        size = 1 << log2
+        nxn = 0
+        if log2 == self.min_cb_log2:
+            nxn = int(r.random() < 0.35)
+            c.encode(o["part_mode"], 1 - nxn)                              # bin 1 = PART_2Nx2N
+        parts = [(0, 0), (4, 0), (0, 4), (4, 4)] if nxn else [(0, 0)]
+        pb = size >> nxn
+        prev = [int(r.random() < 0.6) for _ in parts]
+        for f in prev:
+            c.encode(o["prev_intra_luma_pred_mode"], f)
+        modes = []
+        for (dx, dy), f in zip(parts, prev):
+            cand = self.mpm_candidates(x0 + dx, y0 + dy)
+            if f:
+                idx = int(r.integers(0, 3))
+                c.bypass(int(idx > 0))
+                if idx > 0:
+                    c.bypass(int(idx > 1))
+                mode = cand[idx]
+            else:
+                rem = int(r.integers(0, 32))
+                c.bypass_bits(5, rem)
+                mode = rem
+                for cv in sorted(cand):
+                    if mode >= cv:
+                        mode += 1
+            modes.append(int(mode))
+            self.ipm[(y0 + dy) >> 2:(y0 + dy + pb) >> 2, (x0 + dx) >> 2:(x0 + dx + pb) >> 2] = mode
+        cm = int(r.integers(0, 5))                                         # intra_chroma_pred_mode (4 = derived from luma)
+        c.encode(o["intra_chroma_pred_mode"], int(cm != 4))
+        if cm != 4:
+            c.bypass_bits(2, cm)
+        table = [0, 26, 10, 1]
+        mode_c = modes[0] if cm == 4 else (34 if modes[0] == table[cm] else table[cm])
+        self.ct_depth[y0 >> 3:(y0 + size) >> 3, x0 >> 3:(x0 + size) >> 3] = depth
+        self.transform_tree(x0, y0, log2, 0, 0, nxn, modes, mode_c, [0, 0], self.max_th_depth_intra + nxn, modes[0])
+
+    def transform_tree(self, x0, y0, log2, tdepth, blk, nxn, modes, mode_c, parent_cbf_c, max_depth, mode):
+        c, o, r = self.c, self.off, self.rng
+        if nxn and tdepth == 1:
+            mode = modes[blk]                                               # lc->tu.intra_pred_mode of this quadrant (hevc.c:1452)
+        if log2 <= self.max_tb_log2 and log2 > self.min_tb_log2 and tdepth < max_depth and not (nxn and tdepth == 0):
+            split = int(r.random() < 0.3)
+            c.encode(o["split_transform_flag"] + 5 - log2, split)
+        else:
+            split = int(log2 > self.max_tb_log2 or (nxn and tdepth == 0))
+        cbf_c = list(parent_cbf_c)
+        if log2 > 2:
+            for k in range(2):
+                if tdepth == 0 or parent_cbf_c[k]:
+                    cbf_c[k] = int(r.random() < 0.5)
+                    c.encode(o["cbf_cb, cbf_cr"] + tdepth, cbf_c[k])
+                else:
+                    cbf_c[k] = 0
+        if split:
+            h = 1 << (log2 - 1)
+            for i, (dx, dy) in enumerate(((0, 0), (h, 0), (0, h), (h, h))):
+                self.transform_tree(x0 + dx, y0 + dy, log2 - 1, tdepth + 1, i, nxn, modes, mode_c, cbf_c, max_depth, mode)
+            return
+        cbf_luma = int(r.random() < 0.7)
+        c.encode(o["cbf_luma"] + (1 if tdepth == 0 else 0), cbf_luma)
+
+        def scan_of(m, lg):
+            if lg < 4:
+                if 6 <= m <= 14:
+                    return 2
+                if 22 <= m <= 30:
+                    return 1
+            return 0
+        if cbf_luma:
+            self.residual(log2, scan_of(mode, log2) if log2 < 4 else 0, 0)
+        if log2 > 2:
+            for k in range(2):
+                if cbf_c[k]:
+                    self.residual(log2 - 1, scan_of(mode_c, log2) if log2 < 4 else 0, k + 1)
+        elif blk == 3:
+            for k in range(2):
+                if parent_cbf_c[k]:
+                    self.residual(2, scan_of(mode_c, log2), k + 1)
+
+    def residual(self, log2, scan_idx, cidx):
+        c, o, r = self.c, self.off, self.rng
+        n = 1 << log2
+        # random sparse levels, low frequencies more likely
+        lev = np.zeros((n, n), np.int64)
+        yy, xx = np.mgrid[0:n, 0:n]
+        mask = r.random((n, n)) < np.exp(-(xx + yy) / r.uniform(0.7, 0.7 + n / 4.0))
+        mags = np.maximum(1, np.rint(np.abs(r.laplace(0, 2.5, (n, n))))).astype(np.int64)
+        big = r.random((n, n)) < 0.03
+        mags = np.where(big, mags * int(r.integers(5, 60)), mags)
+        lev = np.where(mask, mags * np.where(r.random((n, n)) < 0.5, -1, 1), 0)
+        if not lev.any():
+            lev[0, 0] = int(r.choice([-2, -1, 1, 3]))
+        sb_order, pos_order = scan_tables(log2, scan_idx)
+        # scan position list (sub-block index i, position n) in forward order
+        def coord(i, k):
+            return (sb_order[i][0] << 2) + pos_order[k][0], (sb_order[i][1] << 2) + pos_order[k][1]
+        last_i = last_k = -1
+        for i in range(len(sb_order)):
+            for k in range(16):
+                x, y = coord(i, k)
+                if lev[y, x]:
+                    last_i, last_k = i, k
+        lx, ly = coord(last_i, last_k)
+        if scan_idx == 2:
+            lx, ly = ly, lx                                                # coded swapped for the vertical scan
+        # last_sig_coeff prefix / suffix
+        def prefix_of(v):
+            if v < 4:
+                return v, 0, 0
+            k = v.bit_length() - 1                                          # 1 << k <= v
+            p = 2 * k + (1 if v >= (3 << (k - 1)) else 0)
+            base = (1 << ((p >> 1) - 1)) * (2 + (p & 1))
+            return p, v - base, (p >> 1) - 1
+        if cidx == 0:
+            ctx_off, ctx_shift = 3 * (log2 - 2) + ((log2 - 1) >> 2), (log2 + 1) >> 2
+        else:
+            ctx_off, ctx_shift = 15, log2 - 2
+        maxp = (log2 << 1) - 1
+        px, sx, nsx = prefix_of(lx)
+        py, sy, nsy = prefix_of(ly)
+        for name, p in (("last_significant_coeff_x_prefix", px), ("last_significant_coeff_y_prefix", py)):
+            for i in range(p):
+                c.encode(o[name] + (i >> ctx_shift) + ctx_off, 1)
+            if p < maxp:
+                c.encode(o[name] + (p >> ctx_shift) + ctx_off, 0)
+        if px > 3:
+            c.bypass_bits(nsx, sx)
+        if py > 3:
+            c.bypass_bits(nsy, sy)
+        nsb = 1 << (log2 - 2)
+        csbf = np.zeros((nsb + 1, nsb + 1), np.int32)
+        greater1_ctx = 1
+        for i in range(last_i, -1, -1):
+            xs, ys = sb_order[i]
+            sig = [(k, coord(i, k)) for k in range(16)]
+            nz = [k for k, (x, y) in sig if lev[y, x]]
+            infer_sb = i == last_i or i == 0
+            if not infer_sb:
+                ctxcg = min(int(csbf[ys, xs + 1]) + int(csbf[ys + 1, xs]), 1) + (2 if cidx else 0)
+                c.encode(o["significant_coeff_group_flag"] + ctxcg, int(bool(nz)))
+                csbf[ys, xs] = int(bool(nz))
+            else:
+                csbf[ys, xs] = 1
+            if not csbf[ys, xs]:
+                continue
+            prev_sig = int(csbf[ys, xs + 1]) + 2 * int(csbf[ys + 1, xs])
+            start = last_k - 1 if i == last_i else 15
+            coded = [last_k] if i == last_i else []
+            implicit = (not infer_sb)                                      # sub-block flag was coded as 1: last position may be inferred
+            for k in range(start, -1, -1):
+                xp, yp = pos_order[k]
+                s = int(lev[(ys << 2) + yp, (xs << 2) + xp] != 0)
+                if k == 0 and implicit and not coded:
+                    assert s == 1
+                    coded.append(0)
+                    break
+                # sigCtx (9.3.4.2.5)
+                if log2 == 2:
+                    sc = SIG_CTX_4x4[(yp << 2) + xp]
+                elif xs == 0 and ys == 0 and k == 0 and (xp + yp) == 0:
+                    sc = 0
+                else:
+                    if prev_sig == 0:
+                        sc = 2 if xp + yp == 0 else (1 if xp + yp < 3 else 0)
+                    elif prev_sig == 1:
+                        sc = 2 if yp == 0 else (1 if yp == 1 else 0)
+                    elif prev_sig == 2:
+                        sc = 2 if xp == 0 else (1 if xp == 1 else 0)
+                    else:
+                        sc = 2
+                    if cidx == 0:
+                        if xs > 0 or ys > 0:
+                            sc += 3
+                        sc += (9 if scan_idx == 0 else 15) if log2 == 3 else 21
+                    else:
+                        sc += 9 if log2 == 3 else 12
+                c.encode(o["significant_coeff_flag"] + sc + (27 if cidx else 0), s)
+                if s:
+                    coded.append(k)
+            if not coded:
+                continue
+            # levels of this sub-block, in coding order (high scan position first)
+            ctx_set = 2 if (i > 0 and cidx == 0) else 0
+            if i != last_i and greater1_ctx == 0:
+                ctx_set += 1
+            greater1_ctx = 1
+            vals = []
+            for k in coded:
+                xp, yp = pos_order[k]
+                vals.append(int(lev[(ys << 2) + yp, (xs << 2) + xp]))
+            g1, first_g1 = [], -1
+            for m, v in enumerate(vals[:8]):
+                f = int(abs(v) > 1)
+                c.encode(o["coeff_abs_level_greater1_flag"] + (ctx_set << 2) + greater1_ctx + (16 if cidx else 0), f)
+                g1.append(f)
+                if f:
+                    greater1_ctx = 0
+                    if first_g1 < 0:
+                        first_g1 = m
+                elif 0 < greater1_ctx < 3:
+                    greater1_ctx += 1
+            g2 = 0
+            if first_g1 >= 0:
+                g2 = int(abs(vals[first_g1]) > 2)
+                c.encode(o["coeff_abs_level_greater2_flag"] + ctx_set + (4 if cidx else 0), g2)
+            for v in vals:
+                c.bypass(int(v < 0))
+            rice = 0
+            for m, v in enumerate(vals):
+                base = 1 + (g1[m] if m < 8 else 0) + (g2 if m == first_g1 else 0)
+                thresh = (3 if m == first_g1 else 2) if m < 8 else 1
+                if base == thresh:
+                    rem = abs(v) - base
+                    self.remaining(rem, rice)
+                    if abs(v) > (3 << rice):
+                        rice = min(rice + 1, 4)
+
+    def remaining(self, v, rice):
+        c = self.c
+        if v < (3 << rice):
+            p = v >> rice
+            for _ in range(p):
+                c.bypass(1)
+            c.bypass(0)
+            c.bypass_bits(rice, v & ((1 << rice) - 1))
+        else:
+            p = 0
+            while (((1 << (p + 1)) + 2) << rice) <= v:
+                p += 1
+            for _ in range(p + 3):
+                c.bypass(1)
+            c.bypass(0)
+            c.bypass_bits(p + rice, v - (((1 << p) + 2) << rice))
+
+    def stream(self, frames):
+        out = self.vps() + self.sps() + self.pps()
+        for _ in range(frames):
+            out += self.slice_nal()
+        return out
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("out")
+    ap.add_argument("--width", type=int, default=832)
+    ap.add_argument("--height", type=int, default=480)
+    ap.add_argument("--bit-depth", type=int, default=8)
+    ap.add_argument("--frames", type=int, default=2)
+    ap.add_argument("--seed", type=int, default=1)
+    ap.add_argument("--qp", type=int, default=30)
+    ap.add_argument("--no-sao", action="store_true")
+    a = ap.parse_args()
+    verify_tables_against_reference()
+    g = StreamGen(a.width, a.height, a.bit_depth, a.seed, a.qp, sao=not a.no_sao)
+    data = g.stream(a.frames)
+    open(a.out, "wb").write(data)
+    print(f"wrote {a.out}: {len(data)} bytes, {a.frames} pictures {a.width}x{a.height} {a.bit_depth}-bit")
+
+
+if __name__ == "__main__":
+    main()
