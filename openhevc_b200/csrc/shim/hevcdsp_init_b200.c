@@ -50,6 +50,7 @@ static struct {
     int emu_next;
     int err; char errmsg[256];
     int in_frame;
+    int n_tu, n_intra, n_pu, n_dbk, n_sao, frame_no;   /* B200_SHIM_STATS=1: table calls per picture (stderr) */
 } g;
 
 static void fail(int code, const char *msg)
@@ -119,6 +120,7 @@ static void rec_transform_add(uint8_t *dst, int16_t *coeffs, ptrdiff_t stride, i
     int kind = B200_TU_BYPASS, flags = 0, cl = 0;
     if (g.pend_ptr == coeffs) { kind = g.pend_kind; flags = g.pend_flags; cl = g.pend_col_limit; }
     g.pend_ptr = NULL;
+    g.n_tu++;
     int rc = b200_rec_tu(g.rec, plane, x, y, log2, kind, flags, cl, coeffs, -1);
     if (rc) fail(rc, "b200_rec_tu failed");
 }
@@ -175,6 +177,7 @@ static void mc_emit(B200McRec *m, uint8_t *dst)
     int plane, x, y;
     if (locate_cur(dst, &plane, &x, &y)) return;
     m->plane = (uint8_t)plane; m->x = (uint16_t)x; m->y = (uint16_t)y;
+    g.n_pu++;
     int rc = b200_rec_mc(g.rec, m);
     if (rc) fail(rc, "b200_rec_mc failed");
 }
@@ -236,6 +239,7 @@ static void rec_dbk(uint8_t *pix, int vertical, int beta, int *tc, uint8_t *no_p
 {
     int plane, x, y;
     if (locate_cur(pix, &plane, &x, &y)) return;
+    g.n_dbk++;
     int rc = b200_rec_deblock(g.rec, plane, vertical, x, y, beta, tc, no_p, no_q);
     if (rc) fail(rc, "b200_rec_deblock failed");
 }
@@ -257,6 +261,7 @@ static void rec_sao(uint8_t *dst, SAOParams *sao, int *borders, int c_idx, int t
     if (variant) r.edges = (uint8_t)((ve[0] ? 1 : 0) | (ve[1] ? 2 : 0) | (he[0] ? 4 : 0) | (he[1] ? 8 : 0) | (de[0] ? 16 : 0) | (de[1] ? 32 : 0) | (de[2] ? 64 : 0) | (de[3] ? 128 : 0));
     r.variant = (uint8_t)variant;
     for (int k = 0; k < 5; k++) r.offset_val[k] = sao->offset_val[c_idx][k];
+    g.n_sao++;
     int rc = b200_rec_sao(g.rec, plane, x, y, &r);
     if (rc) fail(rc, "b200_rec_sao failed");
 }
@@ -292,6 +297,7 @@ static void rec_intra(HEVCContext *s, int x0, int y0, int log2_size, int c_idx)
     if (ur && trs <= 0) { flags &= ~B200_INF_UP_RIGHT; if (!(flags & B200_INF_UP)) fail(B200_ENOTSUP, "up-right available with no sample inside the picture"); }
     if (bl && bls <= 0) { flags &= ~B200_INF_BOTTOM_LEFT; if (!(flags & B200_INF_LEFT)) fail(B200_ENOTSUP, "bottom-left available with no sample inside the picture"); }
     const int mode = c_idx ? lc->tu.intra_pred_mode_c : lc->tu.intra_pred_mode;
+    g.n_intra++;
     int rc = b200_rec_intra(g.rec, c_idx, x0 >> hshift, y0 >> vshift, log2_size, mode, flags, trs, bls);
     if (rc) fail(rc, "b200_rec_intra failed");
 }
@@ -389,6 +395,9 @@ int b200_frame_end(HEVCContext *s)
     (void)s;
     if (!g.in_frame) return g.err ? g.err : B200_ESTATE;
     g.in_frame = 0;
+    if (getenv("B200_SHIM_STATS"))
+        fprintf(stderr, "b200 picture %d: intra_pred %d transform_add %d mc %d deblock %d sao %d\n", g.frame_no, g.n_intra, g.n_tu, g.n_pu, g.n_dbk, g.n_sao);
+    g.frame_no++; g.n_tu = g.n_intra = g.n_pu = g.n_dbk = g.n_sao = 0;
     if (g.err) return g.err;
     const void *blob; uint64_t n;
     int rc = b200_rec_set_refs(g.rec, g.ref_slot, g.n_ref);

@@ -190,12 +190,11 @@ def load_contexts():
         off[nme] = o
         o += c
     iv = src[src.index("init_values[3][HEVC_CONTEXTS]"):]
-    first = iv[iv.index("{", iv.index("{") + 1) + 1:]
-    first = first[:first.index("},")]
-    first = re.sub(r"//.*", "", first).replace("CNU", "154")
-    vals = [int(v) for v in re.findall(r"\d+", first)]
-    assert len(vals) == o, (len(vals), o)
-    return off, vals
+    iv = iv[iv.index("{") + 1:iv.index("};")]
+    iv = re.sub(r"//.*", "", iv).replace("CNU", "154")
+    rows = [[int(v) for v in re.findall(r"\d+", grp)] for grp in re.findall(r"\{([^{}]*)\}", iv)]
+    assert len(rows) == 3 and all(len(rw) == o for rw in rows), [len(rw) for rw in rows]
+    return off, rows                                       # rows[init_type], init_type = 2 - slice_type (I -> 0)
 
 
 # ----------------------------------------------------------------------------------------------------------------
@@ -231,10 +230,15 @@ SIG_CTX_4x4 = [0, 1, 4, 5, 2, 3, 4, 5, 6, 6, 8, 8, 7, 7, 8, 8]
 
 
 class StreamGen:
-    def __init__(self, width, height, bit_depth=8, seed=1, qp=30, sao=True, ctb_log2=6):
+    def __init__(self, width, height, bit_depth=8, seed=1, qp=30, sao=True, ctb_log2=6, weighted=False):
         self.W, self.H, self.bd, self.qp, self.sao, self.ctb_log2 = width, height, bit_depth, qp, sao, ctb_log2
+        self.weighted = weighted
+        self.slice_type = 2                                               # 0 B, 1 P, 2 I
+        self.nrefs = [0, 0]
+        self.max_merge = 3
+        self.stats = []
         self.rng = np.random.default_rng(seed)
-        self.off, self.init_vals = load_contexts()
+        self.off, self.init_rows = load_contexts()
         self.min_cb_log2, self.min_tb_log2, self.max_tb_log2 = 3, 2, 5
         self.max_th_depth_intra = 2
 
@@ -298,7 +302,7 @@ class StreamGen:
         w.u(1, 0)                                                          # cu_qp_delta
         w.se(0); w.se(0)                                                   # cb / cr qp offsets
         w.u(1, 0)                                                          # slice chroma qp offsets present
-        w.u(1, 0); w.u(1, 0)                                               # weighted pred / bipred
+        w.u(1, int(self.weighted)); w.u(1, int(self.weighted))             # weighted pred / bipred
         w.u(1, 0)                                                          # transquant bypass
         w.u(1, 0); w.u(1, 0)                                               # tiles, wpp
         w.u(1, 1)                                                          # loop filter across slices
@@ -312,34 +316,77 @@ class StreamGen:
         return nal(34, w.bytes())
 
     # ---- slice ----------------------------------------------------------------------------------------------------
-    def slice_nal(self):
+    def slice_nal(self, pic=0, slice_type=2):
+        """pic: decode-order index (== POC, low-delay); slice_type 2 I (IDR when pic == 0), 1 P, 0 B"""
+        self.slice_type = slice_type
+        idr = pic == 0
+        nref = 0 if slice_type == 2 else min(pic, 2)
+        self.nrefs = [nref, nref if slice_type == 0 else 0]
         w = BitWriter()
         w.u(1, 1)                                                          # first_slice_segment_in_pic
-        w.u(1, 0)                                                          # no_output_of_prior_pics (IRAP)
+        if idr:
+            w.u(1, 0)                                                      # no_output_of_prior_pics (IRAP)
         w.ue(0)                                                            # pps id
-        w.ue(2)                                                            # slice_type I
+        w.ue(slice_type)
+        if not idr:
+            w.u(8, pic & 255)                                              # pic_order_cnt_lsb
+            w.u(1, 0)                                                      # short_term_ref_pic_set_sps_flag
+            nneg = min(pic, 2)
+            w.ue(nneg); w.ue(0)                                            # num_negative_pics, num_positive_pics
+            for _ in range(nneg):
+                w.ue(0); w.u(1, 1)                                         # delta_poc_s0_minus1, used_by_curr_pic
         if self.sao:
             w.u(1, 1); w.u(1, 1)                                           # slice_sao_luma / chroma
+        if slice_type != 2:
+            w.u(1, 1)                                                      # num_ref_idx_active_override_flag
+            w.ue(nref - 1)
+            if slice_type == 0:
+                w.ue(nref - 1)
+                w.u(1, 0)                                                  # mvd_l1_zero_flag
+            if self.weighted:
+                self.pred_weight_table(w)
+            w.ue(5 - self.max_merge)                                       # five_minus_max_num_merge_cand
         w.se(self.qp - 26)                                                 # slice_qp_delta
-        if self.sao or True:
-            w.u(1, 1)                                                      # slice_loop_filter_across_slices_enabled
+        w.u(1, 1)                                                          # slice_loop_filter_across_slices_enabled
         w.bits.append(1)                                                   # byte_alignment()
         while len(w.bits) % 8:
             w.bits.append(0)
-        self.c = Cabac(self.init_vals, self.qp)
+        self.c = Cabac(self.init_rows[2 - slice_type], self.qp)
+        self.cnt = dict(intra_pred=0, transform_add=0, pu=0)
         self.slice_data()
+        self.stats.append(dict(self.cnt))
         body = w.bits + self.c.bits
         while len(body) % 8:
             body.append(0)
         wb = BitWriter()
         wb.bits = body
-        return nal(19, wb.bytes())                                         # IDR_W_RADL
+        return nal(19 if idr else 1, wb.bytes())                           # IDR_W_RADL / TRAIL_R
+
+    def pred_weight_table(self, w):
+        r = self.rng
+        w.ue(int(r.integers(0, 8)))                                        # luma_log2_weight_denom
+        w.se(0)                                                            # delta_chroma_log2_weight_denom
+        for l in range(2 if self.slice_type == 0 else 1):
+            n = self.nrefs[l]
+            lf = [int(r.random() < 0.7) for _ in range(n)]
+            cf = [int(r.random() < 0.7) for _ in range(n)]
+            for f in lf:
+                w.u(1, f)
+            for f in cf:
+                w.u(1, f)
+            for i in range(n):
+                if lf[i]:
+                    w.se(int(r.integers(-20, 21))); w.se(int(r.integers(-10, 11)))
+                if cf[i]:
+                    for _ in range(2):
+                        w.se(int(r.integers(-20, 21))); w.se(int(r.integers(-20, 21)))
 
     def slice_data(self):
         ctb = 1 << self.ctb_log2
         self.cw, self.ch = (self.W + ctb - 1) >> self.ctb_log2, (self.H + ctb - 1) >> self.ctb_log2
         self.ct_depth = np.zeros((self.H >> 3, self.W >> 3), np.int32)
         self.ipm = np.ones((self.H >> 2, self.W >> 2), np.int32)           # INTRA_DC default
+        self.skip = np.zeros((self.H >> 3, self.W >> 3), np.int32)
         n = self.cw * self.ch
         for a in range(n):
             self.rx, self.ry = a % self.cw, a // self.cw
@@ -422,9 +469,122 @@ class StreamGen:
             cand.append(26)
         return cand
 
+    def mvd(self):
+        c, o, r = self.c, self.off, self.rng
+        v = [int(r.choice([0, 1, 2, 3, 5, 9, 17, 40], p=[0.3, 0.2, 0.15, 0.1, 0.1, 0.07, 0.05, 0.03])) for _ in range(2)]
+        for a in v:
+            c.encode(o["abs_mvd_greater0_flag"], int(a > 0))
+        for a in v:
+            if a:
+                c.encode(o["abs_mvd_greater1_flag"] + 1, int(a > 1))
+        for a in v:
+            if a > 1:                                                      # abs_mvd_minus2, EG1
+                t, k = a - 2, 1
+                while t >= (1 << k):
+                    c.bypass(1)
+                    t -= 1 << k
+                    k += 1
+                c.bypass(0)
+                c.bypass_bits(k, t)
+            if a:
+                c.bypass(int(r.integers(0, 2)))                            # mvd_sign_flag
+
+    def prediction_unit(self, w, h, depth, skipped):
+        """syntax of one PU; returns merge_flag"""
+        c, o, r = self.c, self.off, self.rng
+
+        def merge_idx():
+            if self.max_merge > 1:
+                idx = int(r.integers(0, self.max_merge))
+                c.encode(o["merge_idx"], int(idx > 0))
+                if idx > 0:
+                    for k in range(1, self.max_merge - 1):
+                        c.bypass(int(idx > k))
+                        if idx <= k:
+                            break
+        self.cnt["pu"] += 1
+        if skipped:
+            merge_idx()
+            return 1
+        merge = int(r.random() < 0.35)
+        c.encode(o["merge_flag"], merge)
+        if merge:
+            merge_idx()
+            return 1
+        idc = 0                                                            # PRED_L0
+        if self.slice_type == 0:
+            if w + h == 12:
+                idc = int(r.integers(0, 2))
+                c.encode(o["inter_pred_idc"] + 4, idc)
+            else:
+                bi = int(r.random() < 0.55)
+                c.encode(o["inter_pred_idc"] + depth, bi)
+                if bi:
+                    idc = 2
+                else:
+                    idc = int(r.integers(0, 2))
+                    c.encode(o["inter_pred_idc"] + 4, idc)
+        for l in range(2):
+            if (l == 0 and idc == 1) or (l == 1 and idc == 0):
+                continue
+            n = self.nrefs[l]
+            ref = int(r.integers(0, n))
+            mx = n - 1
+            i = 0
+            while i < min(mx, 2):                                          # ref_idx_lX: two context bins, then bypass
+                c.encode(o["ref_idx_l0"] + i, int(ref > i))
+                if ref <= i:
+                    break
+                i += 1
+            if i == 2 and ref >= 2:
+                while i < mx:
+                    c.bypass(int(ref > i))
+                    if ref <= i:
+                        break
+                    i += 1
+            self.mvd()
+            c.encode(o["mvp_lx_flag"], int(r.integers(0, 2)))
+        return 0
+
     def coding_unit(self, x0, y0, log2, depth):
         c, o, r = self.c, self.off, self.rng
         size = 1 << log2
+        if self.slice_type != 2:
+            inc = 0
+            if x0 > 0:
+                inc += int(self.skip[y0 >> 3, (x0 >> 3) - 1] != 0)
+            if y0 > 0:
+                inc += int(self.skip[(y0 >> 3) - 1, x0 >> 3] != 0)
+            skipped = int(r.random() < 0.25)
+            c.encode(o["skip_flag"] + inc, skipped)
+            self.skip[y0 >> 3:(y0 + size) >> 3, x0 >> 3:(x0 + size) >> 3] = skipped
+            self.ct_depth[y0 >> 3:(y0 + size) >> 3, x0 >> 3:(x0 + size) >> 3] = depth
+            if skipped:
+                self.prediction_unit(size, size, depth, True)
+                self.ipm[y0 >> 2:(y0 + size) >> 2, x0 >> 2:(x0 + size) >> 2] = 1
+                return
+            intra = int(r.random() < 0.2)
+            c.encode(o["pred_mode"], intra)
+            if not intra:
+                self.ipm[y0 >> 2:(y0 + size) >> 2, x0 >> 2:(x0 + size) >> 2] = 1
+                u = r.random()
+                part = 0 if u < 0.6 else (1 if u < 0.8 else 2)             # 2Nx2N, 2NxN, Nx2N (amp off, no inter NxN at 8x8)
+                c.encode(o["part_mode"], int(part == 0))
+                if part:
+                    c.encode(o["part_mode"] + 1, int(part == 1))
+                pus = {0: [(size, size)], 1: [(size, size // 2)] * 2, 2: [(size // 2, size)] * 2}[part]
+                merge = 0
+                for (pw_, ph_) in pus:
+                    merge = self.prediction_unit(pw_, ph_, depth, False)
+                root = 1
+                if not (part == 0 and merge):
+                    root = int(r.random() < 0.7)
+                    c.encode(o["no_residual_data_flag"], root)
+                if root:
+                    self.inter = True
+                    self.transform_tree(x0, y0, log2, 0, 0, 0, [1], 1, [0, 0], 2, 1)
+                    self.inter = False
+                return
         nxn = 0
         if log2 == self.min_cb_log2:
             nxn = int(r.random() < 0.35)
@@ -483,16 +643,23 @@ class StreamGen:
             for i, (dx, dy) in enumerate(((0, 0), (h, 0), (0, h), (h, h))):
                 self.transform_tree(x0 + dx, y0 + dy, log2 - 1, tdepth + 1, i, nxn, modes, mode_c, cbf_c, max_depth, mode)
             return
-        cbf_luma = int(r.random() < 0.7)
-        c.encode(o["cbf_luma"] + (1 if tdepth == 0 else 0), cbf_luma)
+        inter = getattr(self, "inter", False)
+        if inter and tdepth == 0 and not cbf_c[0] and not cbf_c[1]:
+            cbf_luma = 1                                                    # inferred (7.3.8.8)
+        else:
+            cbf_luma = int(r.random() < 0.7)
+            c.encode(o["cbf_luma"] + (1 if tdepth == 0 else 0), cbf_luma)
 
         def scan_of(m, lg):
-            if lg < 4:
+            if lg < 4 and not inter:
                 if 6 <= m <= 14:
                     return 2
                 if 22 <= m <= 30:
                     return 1
             return 0
+        if not inter:
+            self.cnt["intra_pred"] += 1 + (2 if (log2 > 2 or blk == 3) else 0)
+        self.cnt["transform_add"] += cbf_luma + ((cbf_c[0] + cbf_c[1]) if log2 > 2 else ((parent_cbf_c[0] + parent_cbf_c[1]) if blk == 3 else 0))
         if cbf_luma:
             self.residual(log2, scan_of(mode, log2) if log2 < 4 else 0, 0)
         if log2 > 2:
@@ -659,10 +826,15 @@ class StreamGen:
             c.bypass(0)
             c.bypass_bits(p + rice, v - (((1 << p) + 2) << rice))
 
-    def stream(self, frames):
+    def stream(self, frames, pattern="I"):
+        """pattern: picture types in decode order after the leading IDR, cycled, e.g. "PB"; "I" = all IDR"""
         out = self.vps() + self.sps() + self.pps()
-        for _ in range(frames):
-            out += self.slice_nal()
+        for k in range(frames):
+            if pattern == "I":
+                out += self.slice_nal(0, 2)
+            else:
+                t = "I" if k == 0 else pattern[(k - 1) % len(pattern)]
+                out += self.slice_nal(k, {"I": 2, "P": 1, "B": 0}[t])
         return out
 
 
@@ -676,12 +848,16 @@ def main():
     ap.add_argument("--seed", type=int, default=1)
     ap.add_argument("--qp", type=int, default=30)
     ap.add_argument("--no-sao", action="store_true")
+    ap.add_argument("--pattern", default="I", help='picture types after the IDR, e.g. "PB" (low-delay, 2 references)')
+    ap.add_argument("--weighted", action="store_true")
     a = ap.parse_args()
     verify_tables_against_reference()
-    g = StreamGen(a.width, a.height, a.bit_depth, a.seed, a.qp, sao=not a.no_sao)
-    data = g.stream(a.frames)
+    g = StreamGen(a.width, a.height, a.bit_depth, a.seed, a.qp, sao=not a.no_sao, weighted=a.weighted)
+    data = g.stream(a.frames, a.pattern)
     open(a.out, "wb").write(data)
     print(f"wrote {a.out}: {len(data)} bytes, {a.frames} pictures {a.width}x{a.height} {a.bit_depth}-bit")
+    for k, st in enumerate(g.stats):
+        print(f"  picture {k}: intra_pred {st['intra_pred']} transform_add {st['transform_add']} prediction units {st['pu']}")
 
 
 if __name__ == "__main__":
