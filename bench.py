@@ -64,7 +64,7 @@ class ClockSampler:
     def __init__(self, index):
         self.rows, self.proc = [], None
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100"],
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "50"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
@@ -81,9 +81,10 @@ class ClockSampler:
         time.sleep(0.15)
         self.proc.terminate()
         sm, mx, reasons = [], [], set()
-        for (t, line) in self.rows:
-            if t < t0 - 0.05 or t > t1 + 0.15:
-                continue
+        inside = [r for r in self.rows if t0 - 0.05 <= r[0] <= t1 + 0.15]
+        if not inside and self.rows:             # timed region shorter than the sampling period: the nearest sample
+            inside = [min(self.rows, key=lambda r: abs(r[0] - 0.5 * (t0 + t1)))]
+        for (t, line) in inside:
             f = [x.strip() for x in line.split(",")]
             try:
                 sm.append(float(f[0])); mx.append(float(f[1]))
@@ -146,8 +147,8 @@ def main():
     os.dup2(2, 1)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=16, help="GOPs (8 pictures) per rank in the timed region")
-    ap.add_argument("--warmup", type=int, default=4)
+    ap.add_argument("--steps", type=int, default=64, help="GOPs (8 pictures) per rank in the timed region")
+    ap.add_argument("--warmup", type=int, default=8)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="c3_4k_main10_ra", choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -171,7 +172,7 @@ def main():
 
     # ---- engine with the DPB inside a torch tensor (so NCCL can address slots) --------------------------------
     lib = _lib.load()
-    cfg = _lib.B200Config(local, wl["width"], wl["height"], wl["cfi"], wl["bit_depth"], 6, FP.N_SLOTS, 16, 0, None, 0)
+    cfg = _lib.B200Config(local, wl["width"], wl["height"], wl["cfi"], wl["bit_depth"], 6, FP.N_SLOTS, 16, 0, None, 0, 0, 0)
     slot_bytes = int(lib.b200_dpb_bytes(cfg)) // FP.N_SLOTS
     dpb = torch.zeros(FP.N_SLOTS * slot_bytes, dtype=torch.uint8, device=f"cuda:{local}")
     eng = FrameEngine(wl["width"], wl["height"], wl["cfi"], wl["bit_depth"], n_slots=FP.N_SLOTS, n_arenas=16, device=local,
@@ -201,6 +202,7 @@ def main():
     t0 = time.time()
     e0.record(backend.compute)
     n_mine = FP.run_schedule(backend, rank, world, args.steps)
+    eng.join()                                   # lane 0 waits for the pictures on every lane, then the end event
     e1.record(backend.compute)
     eng.sync(); torch.cuda.synchronize()
     t1 = time.time()
@@ -251,6 +253,7 @@ def main():
         def __init__(self, *a):
             super().__init__(*a)
             self.k = 0
+            self.inflight = []
 
         def decode(self, pic):
             a = self.k % 16
@@ -258,8 +261,9 @@ def main():
             self.eng.execute(a, pic.cur_slot, pic.ref_slots)
             self.eng.readback(pic.cur_slot, host_out[self.k % 24], sync=False)
             self.k += 1
-            if self.k % 16 == 0:                # bound the run-ahead of the host thread (arenas and host buffers are reused)
-                self.eng.sync()
+            self.inflight.append(pic.cur_slot)
+            if len(self.inflight) > 12:         # bound the run-ahead of the host thread (host buffers are reused after 24): wait for
+                self.eng.wait_readback(self.inflight.pop(0))   # ONE old picture to land, the queue behind it keeps running
 
     be2 = E2E(eng, dpb, slot_bytes, world, list(range(FP.N_BLOBS)))
     e2e_steps = max(2, args.steps // 2)
@@ -301,7 +305,7 @@ def main():
                 "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                 "dtype": "u16" if wl["bit_depth"] > 8 else "u8", "data": "synthetic",
                 "config": {"workload": args.workload, "picture": f"{wl['width']}x{wl['height']} 4:2:0 {wl['bit_depth']}-bit", "gop": "hierarchical-B 8, intra period 32",
-                           "step": "1 GOP (8 pictures) per rank", "parallelism": f"frame-parallel x{world}, anchor broadcast over NCCL" if world > 1 else "single GPU",
+                           "step": "1 GOP (8 pictures) per rank", "lanes": int(os.environ.get("B200_LANES", "4")), "parallelism": f"frame-parallel x{world}, anchor broadcast over NCCL" if world > 1 else "single GPU",
                            "l2": "inputs larger than L2: 9 work lists (%.0f MB) + 23-slot DPB (%.0f MB) cycled" % (sum(b.nbytes for b in blobs) / 1e6, FP.N_SLOTS * slot_bytes / 1e6)},
                 "mpixels_per_s": fps * wl["width"] * wl["height"] / 1e6,
                 "gpu_launches": int(launches), "clocks": clocks,

@@ -45,6 +45,8 @@ typedef struct B200Config {
     uint64_t max_blob_bytes;    /* capacity of one device arena; 0 = worst case for the geometry     */
     void    *ext_frame_mem;     /* optional caller-owned device memory for the DPB (e.g. a torch      */
     uint64_t ext_frame_bytes;   /*   tensor, so that torch.distributed can broadcast slots), else NULL/0 */
+    int32_t n_lanes;            /* pictures executing concurrently (compute streams); 0 = default (8), max 16; env B200_LANES overrides */
+    int32_t reserved0;
 } B200Config;
 
 /* ---- context --------------------------------------------------------------------------------- */
@@ -54,7 +56,14 @@ const char *b200_last_error(const B200Ctx *ctx);          /* ctx may be NULL: er
 uint64_t    b200_dpb_bytes(const B200Config *cfg);         /* device bytes needed for cfg->n_slots slots   */
 uint64_t    b200_slot_bytes(const B200Ctx *ctx);           /* bytes of one slot (3 planes, pitched)        */
 void       *b200_slot_devptr(const B200Ctx *ctx, int slot, int plane, uint64_t *pitch_bytes);
-void       *b200_stream(const B200Ctx *ctx);               /* the compute cudaStream_t, for external event waits */
+void       *b200_stream(const B200Ctx *ctx);               /* cudaStream_t of compute lane 0 (slot uploads / fills run here)  */
+int         b200_join(B200Ctx *ctx);                       /* b200_stream() waits for every picture submitted so far, on all
+                                                              lanes: an event recorded on it afterwards covers them all      */
+/* Caller-owned streams touching a DPB slot (NCCL broadcast of a reference picture, a display kernel ...): bracket the
+ * work with begin/end.  begin makes `stream` wait for the slot's last writer (and, for write != 0, its pending
+ * readers); end publishes the access so that later pictures / read-backs order themselves after it. */
+int         b200_slot_begin_access(B200Ctx *ctx, int slot, void *stream, int write);
+int         b200_slot_end_access(B200Ctx *ctx, int slot, void *stream, int write);
 
 /* ---- pinned host memory for blobs / frames ---------------------------------------------------- */
 void *b200_host_alloc(uint64_t bytes);
@@ -76,7 +85,9 @@ int b200_frame_submit(B200Ctx *ctx, const void *blob, uint64_t nbytes);
  * little-endian uint16 above; strides in bytes.  (libavcodec/hevc_ps.c:1666-1688) */
 int b200_slot_upload(B200Ctx *ctx, int slot, const void *const planes[3], const int64_t strides[3]);
 int b200_slot_readback(B200Ctx *ctx, int slot, void *const planes[3], const int64_t strides[3]); /* async after the slot's last writer */
+int b200_slot_wait_readback(B200Ctx *ctx, int slot);         /* host blocks until the slot's last read-back has landed (not for the whole queue) */
 int b200_slot_fill(B200Ctx *ctx, int slot, int value);    /* generate_missing_ref, hevc_refs.c:538-606 */
+int b200_wait_uploads(B200Ctx *ctx);                       /* wait until submitted blobs have left host memory (not for the kernels) */
 int b200_sync(B200Ctx *ctx);                               /* wait for everything, surface latched errors */
 
 /* ---- measurement ------------------------------------------------------------------------------ */

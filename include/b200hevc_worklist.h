@@ -22,7 +22,7 @@ extern "C" {
 #endif
 
 #define B200_BLOB_MAGIC   0x4C573242u /* "B2WL" */
-#define B200_BLOB_VERSION 2u
+#define B200_BLOB_VERSION 3u
 
 /* blob sections; every section start is 256-byte aligned inside the blob */
 enum {
@@ -59,8 +59,14 @@ typedef struct B200BlobHeader {
                                     RefPicList, hevc_refs.c); B200McRec.ref0/ref1 index this table            */
     uint8_t  n_ref;
     uint8_t  pad[3];
-    uint32_t reserved[64 - 12 - 2 * B200_SEC_COUNT];
+    uint32_t mc_big_count;       /* B200_SEC_MC is ordered: records [0, mc_big_count) are tiles of any legal shape (one warp
+                                    each), the rest are tiles of <= 8x8 samples (four per warp), grouped by
+                                    B200_MC_SMALL_KEY so that the tiles sharing a warp take the same branches            */
+    uint32_t reserved[64 - 13 - 2 * B200_SEC_COUNT];
 } B200BlobHeader;               /* 256 bytes */
+
+#define B200_MC_IS_SMALL(w, h) ((w) <= 8 && (h) <= 8)
+#define B200_MC_SMALL_KEY(flags) ((((flags) & B200_MCF_CHROMA) ? 2 : 0) | (((flags) & B200_MCF_BI) ? 1 : 0))   /* 0..3 */
 
 #define B200_FRAME_HAS_DEBLOCK 1u
 #define B200_FRAME_HAS_SAO     2u

@@ -10,13 +10,14 @@ LIB_PATH = os.path.join(_HERE, "libb200hevc.so")
 class B200Config(C.Structure):
     _fields_ = [("device", C.c_int32), ("width", C.c_int32), ("height", C.c_int32), ("chroma_format_idc", C.c_int32),
                 ("bit_depth", C.c_int32), ("log2_ctb_size", C.c_int32), ("n_slots", C.c_int32), ("n_arenas", C.c_int32),
-                ("max_blob_bytes", C.c_uint64), ("ext_frame_mem", C.c_void_p), ("ext_frame_bytes", C.c_uint64)]
+                ("max_blob_bytes", C.c_uint64), ("ext_frame_mem", C.c_void_p), ("ext_frame_bytes", C.c_uint64),
+                ("n_lanes", C.c_int32), ("reserved0", C.c_int32)]
 
 
 EXPORTS = [  # every symbol include/b200hevc.h declares
     "b200_ctx_create", "b200_ctx_destroy", "b200_last_error", "b200_dpb_bytes", "b200_slot_bytes", "b200_slot_devptr",
-    "b200_stream", "b200_host_alloc", "b200_host_free", "b200_frame_upload", "b200_frame_execute", "b200_frame_execute_ex", "b200_frame_submit",
-    "b200_slot_upload", "b200_slot_readback", "b200_slot_fill", "b200_sync", "b200_set_profiling", "b200_get_stage_ms",
+    "b200_stream", "b200_join", "b200_slot_begin_access", "b200_slot_end_access", "b200_host_alloc", "b200_host_free", "b200_frame_upload", "b200_frame_execute", "b200_frame_execute_ex", "b200_frame_submit",
+    "b200_slot_upload", "b200_slot_readback", "b200_slot_wait_readback", "b200_slot_fill", "b200_wait_uploads", "b200_sync", "b200_set_profiling", "b200_get_stage_ms",
     "b200_launch_count", "b200_rec_create", "b200_rec_destroy", "b200_rec_begin", "b200_rec_set_refs", "b200_rec_tu", "b200_rec_pcm",
     "b200_rec_intra", "b200_rec_mc", "b200_rec_deblock", "b200_rec_sao", "b200_rec_finish", "b200_intra_level_order",
 ]
@@ -36,6 +37,9 @@ def load():
         "b200_slot_bytes": (u64, [vp]),
         "b200_slot_devptr": (vp, [vp, i32, i32, C.POINTER(u64)]),
         "b200_stream": (vp, [vp]),
+        "b200_join": (i32, [vp]),
+        "b200_slot_begin_access": (i32, [vp, i32, vp, i32]),
+        "b200_slot_end_access": (i32, [vp, i32, vp, i32]),
         "b200_host_alloc": (vp, [u64]),
         "b200_host_free": (None, [vp]),
         "b200_frame_upload": (i32, [vp, vp, u64, i32]),
@@ -44,7 +48,9 @@ def load():
         "b200_frame_submit": (i32, [vp, vp, u64]),
         "b200_slot_upload": (i32, [vp, i32, C.POINTER(vp), C.POINTER(i64)]),
         "b200_slot_readback": (i32, [vp, i32, C.POINTER(vp), C.POINTER(i64)]),
+        "b200_slot_wait_readback": (i32, [vp, i32]),
         "b200_slot_fill": (i32, [vp, i32, i32]),
+        "b200_wait_uploads": (i32, [vp]),
         "b200_sync": (i32, [vp]),
         "b200_set_profiling": (i32, [vp, i32]),
         "b200_get_stage_ms": (i32, [vp, C.POINTER(C.c_float)]),

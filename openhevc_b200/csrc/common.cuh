@@ -38,7 +38,7 @@ __device__ __forceinline__ PIX *px_ptr(const PlaneDesc &p, int x, int y)
 }
 
 // launchers (kernels.cu) -- all asynchronous on `st`; return number of kernels launched
-int launch_mc(cudaStream_t st, const B200McRec *recs, int count, const FrameDesc &cur, const FrameDesc *dpb_dev, const RefTable &rt, int bd);
+int launch_mc(cudaStream_t st, const B200McRec *recs, int count, int n_big, const FrameDesc &cur, const FrameDesc *dpb_dev, const RefTable &rt, int bd);
 int launch_residual(cudaStream_t st, const B200TuRec *const recs[4], const int counts[4], const int16_t *pool, int16_t *parked, const FrameDesc &cur, int bd);
 int launch_intra(cudaStream_t st, const B200IntraRec *recs, int count, const int16_t *pool, const FrameDesc &cur, int bd,
                  uint2 *edges[3], const int edge_stride[3], uint32_t *counter);

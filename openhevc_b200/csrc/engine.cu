@@ -1,10 +1,16 @@
 // engine.cu — context, device-resident DPB, upload arenas and the per-frame stage pipeline
 // behind the C ABI of include/b200hevc.h.
 //
-// Streams: `copy` carries the one pinned H2D upload per picture, `compute` runs K1..K5 in
-// submission (= decode) order so inter-picture dependencies are stream order, `down` carries
-// read-backs.  Arenas are double(+)-buffered: the upload of picture k+1 overlaps the kernels
-// of picture k (events ev_uploaded / ev_done per arena).
+// Streams: `copy` carries the one pinned H2D upload per picture, `down` the read-backs, and
+// pictures execute on `n_lanes` compute LANES (stream + private work picture, parked-residual
+// pool, intra edge records).  Pictures are submitted in decode order and placed round-robin on the
+// lanes; what orders them on the device is the data they touch, not the submission order:
+// every DPB slot carries a "written" event and per-lane "read" events, a picture waits for the
+// writers of its reference slots (RAW) and for the readers / previous writer of its own slot
+// (WAR / WAW).  Pictures that do not depend on each other (the B pictures of one hierarchy
+// level, an I picture and the tail of the previous GOP) therefore overlap, which hides the
+// latency-bound intra wavefront (K3) behind the throughput-bound kernels of its neighbours.
+// Arenas are multi-buffered: the upload of picture k+1 overlaps the kernels of picture k.
 #include <cuda_runtime.h>
 #include <stdio.h>
 #include <stdlib.h>
@@ -16,33 +22,55 @@
 
 #define MAX_SLOTS 64
 #define MAX_ARENAS 16
+#define MAX_LANES 16
+#define RD_DOWN MAX_LANES            // reader index of the read-back stream
+#define RD_EXT (MAX_LANES + 1)       // reader index of caller-owned streams (b200_slot_end_access)
+#define N_RD (MAX_LANES + 2)
 
 struct Arena {
     uint8_t *dev = nullptr;
     uint8_t *stage = nullptr;       // pinned staging for blobs that are not in pinned memory
     B200BlobHeader hdr;             // host copy of the resident blob's header
     bool resident = false;
-    cudaEvent_t ev_uploaded = nullptr, ev_done = nullptr;
+    cudaEvent_t ev_uploaded = nullptr;
+    cudaEvent_t ev_done[MAX_LANES] = {};   // last execution of the resident blob on each lane
+    uint32_t done_mask = 0;
+};
+
+struct Lane {
+    cudaStream_t st = nullptr;
+    uint8_t *work = nullptr;            // pre-SAO picture (reconstruct + deblock happen here when the picture has SAO)
+    FrameDesc work_desc;
+    uint2 *flags[3] = { nullptr, nullptr, nullptr };   // intra edge records, 16 B per 4x4 unit
+    uint32_t *counter = nullptr;        // [0] K3 ticket, [1] sticky abort latch
+    int16_t *parked = nullptr;          // residuals of intra TUs (K2 -> K3), indexed like the coefficient pool
+    cudaEvent_t tail = nullptr;         // end of the last picture of this lane
+    bool used = false;
+};
+
+struct SlotState {
+    cudaEvent_t done = nullptr;         // last write of the slot
+    cudaEvent_t rd[N_RD] = {};          // last read per lane / read-back stream / external stream
+    uint32_t readers = 0;               // which rd[] are pending since the last write
+    int writer = -1;                    // lane of the last write (-1: none yet, -2: not a lane)
 };
 
 struct B200Ctx {
     B200Config cfg;
     int pw[3], ph[3], pitch[3];
     size_t plane_off[3], slot_bytes;
-    uint8_t *dpb = nullptr;          // n_slots + 1 frames (last = pre-SAO work picture)
+    uint8_t *dpb = nullptr;          // n_slots frames
     bool own_dpb = false;
-    uint8_t *work = nullptr;
     FrameDesc *dpb_desc_dev = nullptr;
-    FrameDesc slot_desc[MAX_SLOTS + 1];
-    uint2 *flags[3] = { nullptr, nullptr, nullptr };   // intra edge records, 16 B per 4x4 unit
+    FrameDesc slot_desc[MAX_SLOTS];
     int flag_stride[3];
-    uint32_t *counter = nullptr;
-    int16_t *parked = nullptr;       // residuals of intra TUs (K2 -> K3), indexed like the coefficient pool
+    Lane lane[MAX_LANES];
+    int n_lanes = 1, next_lane = 0;
+    SlotState slot[MAX_SLOTS];
     Arena arena[MAX_ARENAS];
     uint64_t arena_bytes = 0;
     int next_arena = 0;
-    cudaStream_t st_copy = nullptr, st_compute = nullptr, st_down = nullptr;
-    cudaEvent_t slot_done[MAX_SLOTS];
+    cudaStream_t st_copy = nullptr, st_compute = nullptr /* == lane[0].st */, st_down = nullptr;
     cudaEvent_t prof[B200_ST_COUNT + 1];
     bool profiling = false, prof_valid = false;
     uint64_t launches = 0;
@@ -138,18 +166,25 @@ extern "C" void b200_ctx_destroy(B200Ctx *ctx)
         if (ctx->arena[i].dev) cudaFree(ctx->arena[i].dev);
         if (ctx->arena[i].stage) cudaFreeHost(ctx->arena[i].stage);
         if (ctx->arena[i].ev_uploaded) cudaEventDestroy(ctx->arena[i].ev_uploaded);
-        if (ctx->arena[i].ev_done) cudaEventDestroy(ctx->arena[i].ev_done);
+        for (int l = 0; l < MAX_LANES; l++) if (ctx->arena[i].ev_done[l]) cudaEventDestroy(ctx->arena[i].ev_done[l]);
     }
-    for (int i = 0; i < MAX_SLOTS; i++) if (ctx->slot_done[i]) cudaEventDestroy(ctx->slot_done[i]);
+    for (int i = 0; i < MAX_SLOTS; i++) {
+        if (ctx->slot[i].done) cudaEventDestroy(ctx->slot[i].done);
+        for (int l = 0; l < N_RD; l++) if (ctx->slot[i].rd[l]) cudaEventDestroy(ctx->slot[i].rd[l]);
+    }
     for (int i = 0; i <= B200_ST_COUNT; i++) if (ctx->prof[i]) cudaEventDestroy(ctx->prof[i]);
     if (ctx->own_dpb && ctx->dpb) cudaFree(ctx->dpb);
-    if (ctx->work) cudaFree(ctx->work);
     if (ctx->dpb_desc_dev) cudaFree(ctx->dpb_desc_dev);
-    for (int p = 0; p < 3; p++) if (ctx->flags[p]) cudaFree(ctx->flags[p]);
-    if (ctx->counter) cudaFree(ctx->counter);
-    if (ctx->parked) cudaFree(ctx->parked);
+    for (int l = 0; l < MAX_LANES; l++) {
+        Lane &L = ctx->lane[l];
+        if (L.work) cudaFree(L.work);
+        for (int p = 0; p < 3; p++) if (L.flags[p]) cudaFree(L.flags[p]);
+        if (L.counter) cudaFree(L.counter);
+        if (L.parked) cudaFree(L.parked);
+        if (L.tail) cudaEventDestroy(L.tail);
+        if (L.st) cudaStreamDestroy(L.st);
+    }
     if (ctx->st_copy) cudaStreamDestroy(ctx->st_copy);
-    if (ctx->st_compute) cudaStreamDestroy(ctx->st_compute);
     if (ctx->st_down) cudaStreamDestroy(ctx->st_down);
     delete ctx;
 }
@@ -172,37 +207,49 @@ static int ctx_init(B200Ctx *ctx)
         ctx->own_dpb = true;
         CU(cudaMemset(ctx->dpb, 0, need));
     }
-    CU(cudaMalloc(&ctx->work, ctx->slot_bytes));
-    CU(cudaMemset(ctx->work, 0, ctx->slot_bytes));
-    for (int s = 0; s <= c.n_slots; s++) {
-        uint8_t *base = s < c.n_slots ? ctx->dpb + (size_t)s * ctx->slot_bytes : ctx->work;
+    auto describe = [&](FrameDesc &fd, uint8_t *base) {
         for (int p = 0; p < 3; p++) {
-            PlaneDesc &d = ctx->slot_desc[s].p[p];
+            PlaneDesc &d = fd.p[p];
             d.base = base + ctx->plane_off[p]; d.pitch = ctx->pitch[p]; d.w = ctx->pw[p]; d.h = ctx->ph[p];
         }
-    }
-    CU(cudaMalloc(&ctx->dpb_desc_dev, sizeof(FrameDesc) * (c.n_slots + 1)));
-    CU(cudaMemcpy(ctx->dpb_desc_dev, ctx->slot_desc, sizeof(FrameDesc) * (c.n_slots + 1), cudaMemcpyHostToDevice));
-    for (int p = 0; p < 3; p++) {
-        ctx->flag_stride[p] = (ctx->pw[p] + 3) / 4 + 1;
-        const size_t n = (size_t)ctx->flag_stride[p] * ((ctx->ph[p] + 3) / 4 + 1);
-        CU(cudaMalloc(&ctx->flags[p], n * 16));
-        CU(cudaMemset(ctx->flags[p], 0, n * 16));
-    }
-    CU(cudaMalloc(&ctx->counter, 256));
-    CU(cudaMemset(ctx->counter, 0, 256));
+    };
+    for (int s = 0; s < c.n_slots; s++) describe(ctx->slot_desc[s], ctx->dpb + (size_t)s * ctx->slot_bytes);
+    CU(cudaMalloc(&ctx->dpb_desc_dev, sizeof(FrameDesc) * c.n_slots));
+    CU(cudaMemcpy(ctx->dpb_desc_dev, ctx->slot_desc, sizeof(FrameDesc) * c.n_slots, cudaMemcpyHostToDevice));
     ctx->arena_bytes = c.max_blob_bytes ? c.max_blob_bytes : worst_blob_bytes(&c);
     ctx->arena_bytes = (ctx->arena_bytes + 4095) & ~(uint64_t)4095;
-    CU(cudaMalloc(&ctx->parked, ctx->arena_bytes));
+    ctx->n_lanes = c.n_lanes > 0 ? c.n_lanes : 8;
+    if (const char *e = getenv("B200_LANES")) if (atoi(e) > 0) ctx->n_lanes = atoi(e);
+    if (ctx->n_lanes > MAX_LANES) ctx->n_lanes = MAX_LANES;
+    for (int p = 0; p < 3; p++) ctx->flag_stride[p] = (ctx->pw[p] + 3) / 4 + 1;
+    for (int l = 0; l < ctx->n_lanes; l++) {
+        Lane &L = ctx->lane[l];
+        CU(cudaStreamCreateWithFlags(&L.st, cudaStreamNonBlocking));
+        CU(cudaMalloc(&L.work, ctx->slot_bytes));
+        CU(cudaMemset(L.work, 0, ctx->slot_bytes));
+        describe(L.work_desc, L.work);
+        for (int p = 0; p < 3; p++) {
+            const size_t n = (size_t)ctx->flag_stride[p] * ((ctx->ph[p] + 3) / 4 + 1);
+            CU(cudaMalloc(&L.flags[p], n * 16));
+            CU(cudaMemset(L.flags[p], 0, n * 16));
+        }
+        CU(cudaMalloc(&L.counter, 256));
+        CU(cudaMemset(L.counter, 0, 256));
+        CU(cudaMalloc(&L.parked, ctx->arena_bytes));
+        CU(cudaEventCreateWithFlags(&L.tail, cudaEventDisableTiming));
+    }
+    ctx->st_compute = ctx->lane[0].st;
     CU(cudaStreamCreateWithFlags(&ctx->st_copy, cudaStreamNonBlocking));
-    CU(cudaStreamCreateWithFlags(&ctx->st_compute, cudaStreamNonBlocking));
     CU(cudaStreamCreateWithFlags(&ctx->st_down, cudaStreamNonBlocking));
     for (int i = 0; i < c.n_arenas; i++) {
         CU(cudaMalloc(&ctx->arena[i].dev, ctx->arena_bytes));
         CU(cudaEventCreateWithFlags(&ctx->arena[i].ev_uploaded, cudaEventDisableTiming));
-        CU(cudaEventCreateWithFlags(&ctx->arena[i].ev_done, cudaEventDisableTiming));
+        for (int l = 0; l < ctx->n_lanes; l++) CU(cudaEventCreateWithFlags(&ctx->arena[i].ev_done[l], cudaEventDisableTiming));
     }
-    for (int i = 0; i < c.n_slots; i++) CU(cudaEventCreateWithFlags(&ctx->slot_done[i], cudaEventDisableTiming));
+    for (int i = 0; i < c.n_slots; i++) {
+        CU(cudaEventCreateWithFlags(&ctx->slot[i].done, cudaEventDisableTiming));
+        for (int l = 0; l < N_RD; l++) if (l < ctx->n_lanes || l >= MAX_LANES) CU(cudaEventCreateWithFlags(&ctx->slot[i].rd[l], cudaEventDisableTiming));
+    }
     for (int i = 0; i <= B200_ST_COUNT; i++) CU(cudaEventCreate(&ctx->prof[i]));
     b200_dbk_layout(c.width, c.height, c.chroma_format_idc, &ctx->dbk);
     ctx->ctb_w = (c.width + (1 << c.log2_ctb_size) - 1) >> c.log2_ctb_size;
@@ -223,7 +270,6 @@ extern "C" int b200_ctx_create(const B200Config *cfg, B200Ctx **out)
     }
     if (cfg->device < 0 || cfg->device >= ndev) return fail(nullptr, B200_EINVAL, "device %d out of range (0..%d)", cfg->device, ndev - 1);
     B200Ctx *ctx = new B200Ctx();
-    memset(ctx->slot_done, 0, sizeof(ctx->slot_done));
     memset(ctx->prof, 0, sizeof(ctx->prof));
     ctx->err[0] = 0;
     ctx->cfg = *cfg;
@@ -251,6 +297,7 @@ static int check_blob(B200Ctx *ctx, const B200BlobHeader *h, uint64_t nbytes)
         const uint64_t end = (uint64_t)h->sec[s].off + (uint64_t)h->sec[s].count * esz[s];
         if (h->sec[s].count && ((h->sec[s].off & 15) || end > nbytes)) return fail(ctx, B200_EINVAL, "section %d out of bounds", s);
     }
+    if (h->mc_big_count > h->sec[B200_SEC_MC].count) return fail(ctx, B200_EINVAL, "mc_big_count %u > %u MC records", h->mc_big_count, h->sec[B200_SEC_MC].count);
     if (h->sec[B200_SEC_DBK].count && h->sec[B200_SEC_DBK].count != ctx->dbk.total) return fail(ctx, B200_EINVAL, "deblock grid size %u != %u", h->sec[B200_SEC_DBK].count, ctx->dbk.total);
     if (h->sec[B200_SEC_SAO].count && h->sec[B200_SEC_SAO].count != (uint32_t)(3 * ctx->ctb_w * ctx->ctb_h)) return fail(ctx, B200_EINVAL, "SAO grid size mismatch");
     return 0;
@@ -291,9 +338,52 @@ static int deep_check(B200Ctx *ctx, const uint8_t *blob)
         if (m.plane > 2 || !m.w || !m.h || m.w > 32 || m.w * m.h > 256 || m.x + m.w > ctx->pw[m.plane] || m.y + m.h > ctx->ph[m.plane] ||
             m.ref0 >= h->n_ref || ((m.flags & B200_MCF_BI) && m.ref1 >= h->n_ref) ||
             (m.frac0 & 15) > maxf || (m.frac0 >> 4) > maxf || (m.frac1 & 15) > maxf || (m.frac1 >> 4) > maxf || m.denom > 7 ||
-            ((m.w > 16) ? m.h > 8 : m.h > 16))
+            ((m.w > 16) ? m.h > 8 : m.h > 16) || (i >= h->mc_big_count && !B200_MC_IS_SMALL(m.w, m.h)))
             return fail(ctx, B200_EINVAL, "MC record %u invalid", i);
     }
+    return 0;
+}
+
+// ---- slot hazards.  All calls come from the (single) submitting thread, in decode order, so "the event as recorded so
+// far" is exactly the set of earlier accesses.  `who`: lane index, RD_DOWN or RD_EXT. ----
+static int slot_acquire(B200Ctx *ctx, int slot, cudaStream_t st, int who, bool write)
+{
+    SlotState &S = ctx->slot[slot];
+    if (S.writer != -1 && S.writer != who) CU(cudaStreamWaitEvent(st, S.done, 0));        // RAW / WAW
+    if (write)
+        for (int l = 0; l < N_RD; l++)
+            if ((S.readers & (1u << l)) && l != who) CU(cudaStreamWaitEvent(st, S.rd[l], 0));   // WAR
+    return 0;
+}
+static int slot_release(B200Ctx *ctx, int slot, cudaStream_t st, int who, bool write)
+{
+    SlotState &S = ctx->slot[slot];
+    if (write) { CU(cudaEventRecord(S.done, st)); S.readers = 0; S.writer = who < MAX_LANES ? who : -2; }
+    else { CU(cudaEventRecord(S.rd[who], st)); S.readers |= 1u << who; }
+    return 0;
+}
+
+extern "C" int b200_slot_begin_access(B200Ctx *ctx, int slot, void *stream, int write)
+{
+    if (!ctx || slot < 0 || slot >= ctx->cfg.n_slots) return B200_EINVAL;
+    CU(cudaSetDevice(ctx->cfg.device));
+    return slot_acquire(ctx, slot, (cudaStream_t)stream, RD_EXT, write != 0);
+}
+extern "C" int b200_slot_end_access(B200Ctx *ctx, int slot, void *stream, int write)
+{
+    if (!ctx || slot < 0 || slot >= ctx->cfg.n_slots) return B200_EINVAL;
+    CU(cudaSetDevice(ctx->cfg.device));
+    return slot_release(ctx, slot, (cudaStream_t)stream, RD_EXT, write != 0);
+}
+
+// b200_stream() (lane 0) waits for everything submitted so far on every lane: an event the caller records on it
+// afterwards marks the completion of all pictures (timing, external consumers)
+extern "C" int b200_join(B200Ctx *ctx)
+{
+    if (!ctx) return B200_EINVAL;
+    CU(cudaSetDevice(ctx->cfg.device));
+    for (int l = 1; l < ctx->n_lanes; l++)
+        if (ctx->lane[l].used) CU(cudaStreamWaitEvent(ctx->lane[0].st, ctx->lane[l].tail, 0));
     return 0;
 }
 
@@ -318,7 +408,9 @@ extern "C" int b200_frame_upload(B200Ctx *ctx, const void *blob, uint64_t nbytes
         memcpy(a.stage, blob, nbytes);
         src = a.stage;
     }
-    if (a.resident) CU(cudaStreamWaitEvent(ctx->st_copy, a.ev_done, 0));   // previous picture of this arena finished
+    for (int l = 0; l < ctx->n_lanes; l++)          // every execution of the arena's previous blob has finished
+        if (a.done_mask & (1u << l)) CU(cudaStreamWaitEvent(ctx->st_copy, a.ev_done[l], 0));
+    a.done_mask = 0;
     CU(cudaMemcpyAsync(a.dev, src, nbytes, cudaMemcpyHostToDevice, ctx->st_copy));
     CU(cudaEventRecord(a.ev_uploaded, ctx->st_copy));
     a.hdr = *h;
@@ -352,26 +444,62 @@ extern "C" int b200_frame_execute_ex(B200Ctx *ctx, int arena, int cur_slot, cons
         rt.w[i >> 3] |= (uint64_t)h.ref_slot[i] << (8 * (i & 7));
     }
     if (h.sec[B200_SEC_MC].count && !h.n_ref) return fail(ctx, B200_EINVAL, "inter records without a reference table");
-    cudaStream_t st = ctx->st_compute;
+    // profiling runs serially on lane 0 (clean stage times).  Otherwise: an idle lane, else the lane that is still writing
+    // one of the picture's references (it would be waited for anyway), else round-robin.  The last lane is kept for
+    // pictures without references: an I picture is one long latency-bound wavefront (K3) that nothing earlier feeds, so
+    // it should start the moment it is submitted -- queued behind inter pictures it would start late and everything
+    // that follows in decode order would then wait for its whole chain.
+    int li = 0;
+    if (ctx->profiling) { int rc = b200_join(ctx); if (rc) return rc; }
+    else {
+        const int nl = ctx->n_lanes, n_gen = nl > 1 ? nl - 1 : 1;
+        const bool intra_only = h.n_ref == 0;
+        auto idle = [&](int l) { return !ctx->lane[l].used || cudaEventQuery(ctx->lane[l].tail) == cudaSuccess; };
+        li = -1;
+        if (intra_only && nl > 1 && idle(nl - 1)) li = nl - 1;
+        const int n_cand = intra_only ? nl : n_gen;
+        for (int i = 0; i < n_cand && li < 0; i++) {
+            const int l = (ctx->next_lane + i) % n_cand;
+            if (idle(l)) li = l;
+        }
+        for (int i = 0; i < h.n_ref && li < 0; i++) {
+            const SlotState &S = ctx->slot[h.ref_slot[i]];
+            if (S.writer >= 0 && S.writer < n_gen && cudaEventQuery(S.done) != cudaSuccess) li = S.writer;
+        }
+        cudaGetLastError();                                  // cudaErrorNotReady is not an error here
+        if (li < 0) li = ctx->next_lane % n_cand;
+        if (li < n_gen) ctx->next_lane = (li + 1) % n_gen;
+    }
+    Lane &L = ctx->lane[li];
+    cudaStream_t st = L.st;
     const int bd = ctx->cfg.bit_depth;
     const bool has_sao = h.sec[B200_SEC_SAO].count != 0;
     const FrameDesc &out = ctx->slot_desc[h.cur_slot];
-    const FrameDesc &cur = has_sao ? ctx->slot_desc[ctx->cfg.n_slots] : out;   // reconstruct + deblock here
+    const FrameDesc &cur = has_sao ? L.work_desc : out;   // reconstruct + deblock here
     const bool pf = ctx->profiling;
+    uint32_t ref_seen[(MAX_SLOTS + 31) / 32] = {};
+    for (int i = 0; i < h.n_ref; i++) {
+        const int r = h.ref_slot[i];
+        if (r == h.cur_slot) return fail(ctx, B200_EINVAL, "reference table entry %d is the picture's own slot %d", i, r);
+        if (ref_seen[r >> 5] & (1u << (r & 31))) continue;
+        ref_seen[r >> 5] |= 1u << (r & 31);
+        int rc = slot_acquire(ctx, r, st, li, false); if (rc) return rc;
+    }
+    { int rc = slot_acquire(ctx, h.cur_slot, st, li, true); if (rc) return rc; }
     CU(cudaStreamWaitEvent(st, a.ev_uploaded, 0));
     if (pf) CU(cudaEventRecord(ctx->prof[0], st));
     // K1 inter
-    ctx->launches += launch_mc(st, (const B200McRec *)(a.dev + h.sec[B200_SEC_MC].off), (int)h.sec[B200_SEC_MC].count, cur, ctx->dpb_desc_dev, rt, bd);
+    ctx->launches += launch_mc(st, (const B200McRec *)(a.dev + h.sec[B200_SEC_MC].off), (int)h.sec[B200_SEC_MC].count, (int)h.mc_big_count, cur, ctx->dpb_desc_dev, rt, bd);
     if (pf) CU(cudaEventRecord(ctx->prof[1], st));
     // K2 residual
     const int16_t *pool = (const int16_t *)(a.dev + h.sec[B200_SEC_COEFF].off);
     const B200TuRec *tu[4]; int ntu[4];
     for (int s = 0; s < 4; s++) { tu[s] = (const B200TuRec *)(a.dev + h.sec[B200_SEC_TU4 + s].off); ntu[s] = (int)h.sec[B200_SEC_TU4 + s].count; }
-    ctx->launches += launch_residual(st, tu, ntu, pool, ctx->parked, cur, bd);
+    ctx->launches += launch_residual(st, tu, ntu, pool, L.parked, cur, bd);
     if (pf) CU(cudaEventRecord(ctx->prof[2], st));
     // K3 intra
-    ctx->launches += launch_intra(st, (const B200IntraRec *)(a.dev + h.sec[B200_SEC_INTRA].off), (int)h.sec[B200_SEC_INTRA].count, ctx->parked, cur, bd,
-                                  ctx->flags, ctx->flag_stride, ctx->counter);
+    ctx->launches += launch_intra(st, (const B200IntraRec *)(a.dev + h.sec[B200_SEC_INTRA].off), (int)h.sec[B200_SEC_INTRA].count, L.parked, cur, bd,
+                                  L.flags, ctx->flag_stride, L.counter);
     if (pf) CU(cudaEventRecord(ctx->prof[3], st));
     // K4 deblock
     if (h.sec[B200_SEC_DBK].count)
@@ -381,8 +509,18 @@ extern "C" int b200_frame_execute_ex(B200Ctx *ctx, int arena, int cur_slot, cons
     if (has_sao)
         ctx->launches += launch_sao(st, (const B200SaoRec *)(a.dev + h.sec[B200_SEC_SAO].off), cur, out, bd, ctx->cfg.log2_ctb_size, ctx->ctb_w, ctx->ctb_h, ctx->cfg.chroma_format_idc);
     if (pf) { CU(cudaEventRecord(ctx->prof[5], st)); ctx->prof_valid = true; }
-    CU(cudaEventRecord(a.ev_done, st));
-    CU(cudaEventRecord(ctx->slot_done[h.cur_slot], st));
+    CU(cudaEventRecord(a.ev_done[li], st));
+    a.done_mask |= 1u << li;
+    { int rc = slot_release(ctx, h.cur_slot, st, li, true); if (rc) return rc; }
+    memset(ref_seen, 0, sizeof(ref_seen));
+    for (int i = 0; i < h.n_ref; i++) {
+        const int r = h.ref_slot[i];
+        if (ref_seen[r >> 5] & (1u << (r & 31))) continue;
+        ref_seen[r >> 5] |= 1u << (r & 31);
+        int rc = slot_release(ctx, r, st, li, false); if (rc) return rc;
+    }
+    CU(cudaEventRecord(L.tail, st));
+    L.used = true;
     CU(cudaGetLastError());
     return 0;
 }
@@ -403,10 +541,10 @@ extern "C" int b200_slot_upload(B200Ctx *ctx, int slot, const void *const planes
     if (ctx->err_code) return ctx->err_code;
     CU(cudaSetDevice(ctx->cfg.device));
     const int B = ctx->cfg.bit_depth > 8 ? 2 : 1;
+    { int rc = slot_acquire(ctx, slot, ctx->st_compute, 0, true); if (rc) return rc; }
     for (int p = 0; p < 3; p++)
         CU(cudaMemcpy2DAsync(ctx->slot_desc[slot].p[p].base, ctx->pitch[p], planes[p], (size_t)strides[p], (size_t)ctx->pw[p] * B, ctx->ph[p], cudaMemcpyHostToDevice, ctx->st_compute));
-    CU(cudaEventRecord(ctx->slot_done[slot], ctx->st_compute));
-    return 0;
+    return slot_release(ctx, slot, ctx->st_compute, 0, true);
 }
 
 extern "C" int b200_slot_readback(B200Ctx *ctx, int slot, void *const planes[3], const int64_t strides[3])
@@ -415,14 +553,22 @@ extern "C" int b200_slot_readback(B200Ctx *ctx, int slot, void *const planes[3],
     if (ctx->err_code) return ctx->err_code;
     CU(cudaSetDevice(ctx->cfg.device));
     const int B = ctx->cfg.bit_depth > 8 ? 2 : 1;
-    CU(cudaStreamWaitEvent(ctx->st_down, ctx->slot_done[slot], 0));
+    { int rc = slot_acquire(ctx, slot, ctx->st_down, RD_DOWN, false); if (rc) return rc; }
     for (int p = 0; p < 3; p++) {
         if (strides[p] == ctx->pitch[p])     // contiguous on both sides: one linear copy
             CU(cudaMemcpyAsync(planes[p], ctx->slot_desc[slot].p[p].base, (size_t)ctx->pitch[p] * ctx->ph[p], cudaMemcpyDeviceToHost, ctx->st_down));
         else
             CU(cudaMemcpy2DAsync(planes[p], (size_t)strides[p], ctx->slot_desc[slot].p[p].base, ctx->pitch[p], (size_t)ctx->pw[p] * B, ctx->ph[p], cudaMemcpyDeviceToHost, ctx->st_down));
     }
-    return 0;
+    return slot_release(ctx, slot, ctx->st_down, RD_DOWN, false);
+}
+
+extern "C" int b200_slot_wait_readback(B200Ctx *ctx, int slot)
+{
+    if (!ctx || slot < 0 || slot >= ctx->cfg.n_slots) return B200_EINVAL;
+    CU(cudaSetDevice(ctx->cfg.device));
+    if (ctx->slot[slot].readers & (1u << RD_DOWN)) CU(cudaEventSynchronize(ctx->slot[slot].rd[RD_DOWN]));
+    return ctx->err_code;
 }
 
 extern "C" int b200_slot_fill(B200Ctx *ctx, int slot, int value)
@@ -430,10 +576,18 @@ extern "C" int b200_slot_fill(B200Ctx *ctx, int slot, int value)
     if (!ctx || slot < 0 || slot >= ctx->cfg.n_slots) return B200_EINVAL;
     if (ctx->err_code) return ctx->err_code;
     CU(cudaSetDevice(ctx->cfg.device));
+    { int rc = slot_acquire(ctx, slot, ctx->st_compute, 0, true); if (rc) return rc; }
     ctx->launches += launch_fill(ctx->st_compute, ctx->slot_desc[slot], ctx->cfg.bit_depth, value);
-    CU(cudaEventRecord(ctx->slot_done[slot], ctx->st_compute));
     CU(cudaGetLastError());
-    return 0;
+    return slot_release(ctx, slot, ctx->st_compute, 0, true);
+}
+
+extern "C" int b200_wait_uploads(B200Ctx *ctx)
+{
+    if (!ctx) return B200_EINVAL;
+    CU(cudaSetDevice(ctx->cfg.device));
+    CU(cudaStreamSynchronize(ctx->st_copy));
+    return ctx->err_code;
 }
 
 extern "C" int b200_sync(B200Ctx *ctx)
@@ -441,11 +595,14 @@ extern "C" int b200_sync(B200Ctx *ctx)
     if (!ctx) return B200_EINVAL;
     CU(cudaSetDevice(ctx->cfg.device));
     CU(cudaStreamSynchronize(ctx->st_copy));
-    CU(cudaStreamSynchronize(ctx->st_compute));
+    for (int l = 0; l < ctx->n_lanes; l++) CU(cudaStreamSynchronize(ctx->lane[l].st));
     CU(cudaStreamSynchronize(ctx->st_down));
-    uint32_t st[2] = { 0, 0 };
-    CU(cudaMemcpy(st, ctx->counter, sizeof(st), cudaMemcpyDeviceToHost));
-    if (st[1]) return fail(ctx, B200_EINVAL, "intra work list is not in decode order (dependency wait timed out)");
+    for (int l = 0; l < ctx->n_lanes; l++) {
+        if (!ctx->lane[l].used) continue;
+        uint32_t st[2] = { 0, 0 };
+        CU(cudaMemcpy(st, ctx->lane[l].counter, sizeof(st), cudaMemcpyDeviceToHost));
+        if (st[1]) return fail(ctx, B200_EINVAL, "intra work list is not in decode order (dependency wait timed out)");
+    }
     return ctx->err_code;
 }
 

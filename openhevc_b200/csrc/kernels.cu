@@ -240,10 +240,15 @@ struct McGeom {
     int wpad, lsh, q;           // stage A: 4 outputs per lane, q quads per row, (1 << lsh) lanes per row
 };
 
+// A tile is processed by a GROUP of GS lanes: GS = 32 (one warp per tile) for the big tiles, GS = 8 (four tiles per
+// warp) for tiles of <= 8x8 samples, which are 3/4 of all tiles in a typical picture but would leave most of a warp
+// idle.  `gl` = lane within the group, `gmask` = the group's lanes: every barrier below is group-local, so the
+// groups of one warp may take different branches (uni/bi, luma/chroma, fractional or not).
+//
 // One reference list of one tile: fills val[j] (j < rows_per) with the 14-bit intermediate of sample
-// (x = lane & (wpw-1), y = part * rows_per + j), exactly the value put_hevc_{q,e}pel* would hold.
-template <typename PIX, int TAPS>
-__device__ __forceinline__ void mc_list(const PlaneDesc &rp, int sx, int sy, int mx, int my, const McGeom &g, int bd, int lane,
+// (x = gl & (wpw-1), y = part * rows_per + j), exactly the value put_hevc_{q,e}pel* would hold.
+template <typename PIX, int TAPS, int GS>
+__device__ __forceinline__ void mc_list(const PlaneDesc &rp, int sx, int sy, int mx, int my, const McGeom &g, int bd, int gl, unsigned gmask,
                                         uint16_t *win, int16_t *tmp, int (&val)[8])
 {
     constexpr int BEFORE = TAPS == 8 ? 3 : 1;
@@ -252,11 +257,11 @@ __device__ __forceinline__ void mc_list(const PlaneDesc &rp, int sx, int sy, int
     const int ox = sx - (mx ? BEFORE : 0), oy = sy - (my ? BEFORE : 0);
     const int skew = ox & 1, ax = ox - skew;               // window origin aligned down to an even sample
     const int np = (C + skew + 1) >> 1, Ws = 2 * np;        // sample pairs per row, shared-memory row stride
-    __syncwarp();
+    __syncwarp(gmask);
     if (ax >= 0 && ax + Ws <= rp.w && oy >= 0 && oy + R <= rp.h) {
         // interior: one 2-sample load per lane, 1 or 2 rows per pass, no clamping
-        const int two = np <= 16;
-        const int pi = two ? (lane & 15) : lane, rsub = two ? (lane >> 4) : 0, rstep = two ? 2 : 1;
+        const int lpr = np <= GS / 2 ? GS / 2 : GS;         // lanes per window row
+        const int pi = gl & (lpr - 1), rsub = gl >= lpr ? 1 : 0, rstep = GS / lpr;
         if (pi < np) {
             const uint8_t *src = rp.base + (size_t)(oy + rsub) * rp.pitch + (size_t)(ax + 2 * pi) * sizeof(PIX);
             uint32_t *dst = reinterpret_cast<uint32_t *>(win) + rsub * np + pi;
@@ -270,24 +275,24 @@ __device__ __forceinline__ void mc_list(const PlaneDesc &rp, int sx, int sy, int
         }
     } else {
         // window hangs over the picture border: clamp sample by sample (== emulated_edge_mc)
-        for (int i = lane; i < R * Ws; i += 32) {
+        for (int i = gl; i < R * Ws; i += GS) {
             const int r = i / Ws, cc = i - r * Ws;
             const int x = clip3i(ax + cc, 0, rp.w - 1), y = clip3i(oy + r, 0, rp.h - 1);
             win[i] = __ldg(px_ptr<PIX>(rp, x, y));
         }
     }
-    __syncwarp();
+    __syncwarp(gmask);
     const int8_t *fxp = TAPS == 8 ? c_qpel[mx] : c_epel[mx];
     const int8_t *fyp = TAPS == 8 ? c_qpel[my] : c_epel[my];
     if (mx) {
-        // stage A: horizontal FIR, 4 outputs per lane, rows_per_pass = 32 >> lsh
+        // stage A: horizontal FIR, 4 outputs per lane, rows per pass = GS >> lsh
         int fx[TAPS];
 #pragma unroll
         for (int k = 0; k < TAPS; k++) fx[k] = fxp[k];
-        const int qi = lane & ((1 << g.lsh) - 1), rstep = 32 >> g.lsh;
+        const int qi = gl & ((1 << g.lsh) - 1), rstep = GS >> g.lsh;
         if (qi < g.q) {
             const int sh = bd - 8;
-            for (int r = lane >> g.lsh; r < R; r += rstep) {
+            for (int r = gl >> g.lsh; r < R; r += rstep) {
                 const uint16_t *s = win + r * Ws + skew + 4 * qi;
                 int p[TAPS + 3];
 #pragma unroll
@@ -305,10 +310,10 @@ __device__ __forceinline__ void mc_list(const PlaneDesc &rp, int sx, int sy, int
                 d[1] = (uint32_t)o[2] | ((uint32_t)o[3] << 16);
             }
         }
-        __syncwarp();
+        __syncwarp(gmask);
     }
     // stage B: vertical FIR (or pass-through), lane = column, up to 8 rows per lane with a register sliding window
-    const int xl = lane & ((1 << g.wsh) - 1), y0 = (lane >> g.wsh) * g.rows_per;
+    const int xl = gl & ((1 << g.wsh) - 1), y0 = (gl >> g.wsh) * g.rows_per;
     const bool act = xl < w && y0 < h;
     int a[8 + TAPS - 1];
     if (mx) {
@@ -339,20 +344,29 @@ __device__ __forceinline__ void mc_list(const PlaneDesc &rp, int sx, int sy, int
     }
 }
 
-template <typename PIX>
+// shared memory per group: window (R x Ws uint16) and horizontal-pass rows (R x wpad int16)
+template <int GS> struct McSmem;
+template <> struct McSmem<32> { static constexpr int WIN = MC_WIN_MAX, TMP = MC_TMP_MAX; };
+template <> struct McSmem<8>  { static constexpr int WIN = 256 /* 15 x 16 */, TMP = 128 /* 15 x 8 */; };
+
+template <typename PIX, int GS>
 __global__ void __launch_bounds__(256) k_mc(const B200McRec *__restrict__ recs, int count, FrameDesc cur, const FrameDesc *__restrict__ dpb, RefTable rt, int bd)
 {
-    __shared__ __align__(16) uint16_t win_s[8][MC_WIN_MAX];
-    __shared__ __align__(16) int16_t tmp_s[8][MC_TMP_MAX];
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int ri = blockIdx.x * 8 + warp;
-    if (ri >= count) return;
+    constexpr int NG = 256 / GS;                           // groups per CTA
+    __shared__ __align__(16) uint16_t win_s[NG][McSmem<GS>::WIN];
+    __shared__ __align__(16) int16_t tmp_s[NG][McSmem<GS>::TMP];
+    const int grp = threadIdx.x / GS, gl = threadIdx.x & (GS - 1);
+    const unsigned gmask = GS == 32 ? 0xffffffffu : (((1u << GS) - 1u) << ((threadIdx.x & 31) & ~(GS - 1)));
+    const int ri = blockIdx.x * NG + grp;
+    if (ri >= count) return;                               // whole groups leave: the barriers are group-local
     const int4 *rp4 = reinterpret_cast<const int4 *>(recs + ri);
     const int4 ra = __ldg(rp4), rb = __ldg(rp4 + 1);
     // B200McRec fields straight from registers
     const int mxy = ra.x, whpf = ra.y;
     const int dx = mxy & 0xffff, dy = (unsigned)mxy >> 16;
-    const int w = whpf & 0xff, h = (whpf >> 8) & 0xff, plane = (whpf >> 16) & 0xff, flags = (unsigned)whpf >> 24;
+    int w = whpf & 0xff, h = (whpf >> 8) & 0xff;
+    if (GS == 8) { w = min(w, 8); h = min(h, 8); }          // the list order guarantees it; never trust it with shared memory
+    const int plane = (whpf >> 16) & 0xff, flags = (unsigned)whpf >> 24;
     const int sx0 = (int16_t)(ra.z & 0xffff), sy0 = (int16_t)((unsigned)ra.z >> 16), sx1 = (int16_t)(ra.w & 0xffff), sy1 = (int16_t)((unsigned)ra.w >> 16);
     const int ref0 = rb.x & 0xff, ref1 = (rb.x >> 8) & 0xff, frac0 = (rb.x >> 16) & 0xff, frac1 = (unsigned)rb.x >> 24;
     const int w0 = (int16_t)(rb.y & 0xffff), w1 = (int16_t)((unsigned)rb.y >> 16), o0 = (int16_t)(rb.z & 0xffff), o1 = (int16_t)((unsigned)rb.z >> 16);
@@ -361,7 +375,7 @@ __global__ void __launch_bounds__(256) k_mc(const B200McRec *__restrict__ recs, 
     McGeom g;
     g.w = w; g.h = h;
     g.wsh = w <= 2 ? 1 : w <= 4 ? 2 : w <= 8 ? 3 : w <= 16 ? 4 : 5;
-    g.parts = 32 >> g.wsh;
+    g.parts = GS >> g.wsh;
     g.rows_per = (h + g.parts - 1) / g.parts;
     g.wpad = (w + 3) & ~3;
     g.q = g.wpad >> 2;
@@ -369,18 +383,18 @@ __global__ void __launch_bounds__(256) k_mc(const B200McRec *__restrict__ recs, 
     int v0[8], v1[8];
     {
         const PlaneDesc rp = dpb[ref_slot_of(rt, ref0)].p[plane];
-        if (chroma) mc_list<PIX, 4>(rp, sx0, sy0, frac0 & 15, frac0 >> 4, g, bd, lane, win_s[warp], tmp_s[warp], v0);
-        else        mc_list<PIX, 8>(rp, sx0, sy0, frac0 & 15, frac0 >> 4, g, bd, lane, win_s[warp], tmp_s[warp], v0);
+        if (chroma) mc_list<PIX, 4, GS>(rp, sx0, sy0, frac0 & 15, frac0 >> 4, g, bd, gl, gmask, win_s[grp], tmp_s[grp], v0);
+        else        mc_list<PIX, 8, GS>(rp, sx0, sy0, frac0 & 15, frac0 >> 4, g, bd, gl, gmask, win_s[grp], tmp_s[grp], v0);
     }
     if (bi) {
         const PlaneDesc rp = dpb[ref_slot_of(rt, ref1)].p[plane];
-        if (chroma) mc_list<PIX, 4>(rp, sx1, sy1, frac1 & 15, frac1 >> 4, g, bd, lane, win_s[warp], tmp_s[warp], v1);
-        else        mc_list<PIX, 8>(rp, sx1, sy1, frac1 & 15, frac1 >> 4, g, bd, lane, win_s[warp], tmp_s[warp], v1);
+        if (chroma) mc_list<PIX, 4, GS>(rp, sx1, sy1, frac1 & 15, frac1 >> 4, g, bd, gl, gmask, win_s[grp], tmp_s[grp], v1);
+        else        mc_list<PIX, 8, GS>(rp, sx1, sy1, frac1 & 15, frac1 >> 4, g, bd, gl, gmask, win_s[grp], tmp_s[grp], v1);
     }
     const PlaneDesc dp = plane_of(cur, plane);
     const int shift = 14 - bd, maxv = (1 << bd) - 1;
     const bool fullpel0 = frac0 == 0;
-    const int xl = lane & ((1 << g.wsh) - 1), y0 = (lane >> g.wsh) * g.rows_per;
+    const int xl = gl & ((1 << g.wsh) - 1), y0 = (gl >> g.wsh) * g.rows_per;
     if (xl >= w) return;
     PIX *d = px_ptr<PIX>(dp, dx + xl, dy + y0);
 #pragma unroll
@@ -1039,13 +1053,24 @@ __global__ void k_fill(FrameDesc f, int value)
 // --------------------------------------------------------------------------------------------
 // launchers
 // --------------------------------------------------------------------------------------------
-int launch_mc(cudaStream_t st, const B200McRec *recs, int count, const FrameDesc &cur, const FrameDesc *dpb_dev, const RefTable &rt, int bd)
+int launch_mc(cudaStream_t st, const B200McRec *recs, int count, int n_big, const FrameDesc &cur, const FrameDesc *dpb_dev, const RefTable &rt, int bd)
 {
     if (!count) return 0;
-    const int grid = (count + 7) / 8;
-    if (bd > 8) k_mc<uint16_t><<<grid, 256, 0, st>>>(recs, count, cur, dpb_dev, rt, bd);
-    else        k_mc<uint8_t><<<grid, 256, 0, st>>>(recs, count, cur, dpb_dev, rt, bd);
-    return 1;
+    int n = 0;
+    const int n_small = count - n_big;
+    if (n_big) {                        // one warp per tile
+        const int grid = (n_big + 7) / 8;
+        if (bd > 8) k_mc<uint16_t, 32><<<grid, 256, 0, st>>>(recs, n_big, cur, dpb_dev, rt, bd);
+        else        k_mc<uint8_t, 32><<<grid, 256, 0, st>>>(recs, n_big, cur, dpb_dev, rt, bd);
+        n++;
+    }
+    if (n_small) {                      // tiles of <= 8x8 samples: four per warp
+        const int grid = (n_small + 31) / 32;
+        if (bd > 8) k_mc<uint16_t, 8><<<grid, 256, 0, st>>>(recs + n_big, n_small, cur, dpb_dev, rt, bd);
+        else        k_mc<uint8_t, 8><<<grid, 256, 0, st>>>(recs + n_big, n_small, cur, dpb_dev, rt, bd);
+        n++;
+    }
+    return n;
 }
 
 template <typename PIX>

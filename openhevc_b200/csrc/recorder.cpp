@@ -304,7 +304,15 @@ extern "C" int b200_rec_finish(B200Rec *r, const void **blob, uint64_t *nbytes)
     }
     o = (o + r->intra.size() * 16 + 255) & ~(uint64_t)255;
     h->sec[B200_SEC_MC].off = (uint32_t)o; h->sec[B200_SEC_MC].count = (uint32_t)r->mc.size();
-    if (!r->mc.empty()) memcpy(r->blob + o, r->mc.data(), r->mc.size() * 32);
+    {   // big tiles first (decode order), then the <= 8x8 tiles bucketed by (chroma, bi): see B200BlobHeader.mc_big_count
+        size_t n[5] = { 0, 0, 0, 0, 0 }, at[5];
+        for (const B200McRec &m : r->mc) n[B200_MC_IS_SMALL(m.w, m.h) ? 1 + B200_MC_SMALL_KEY(m.flags) : 0]++;
+        at[0] = 0;
+        for (int k = 1; k < 5; k++) at[k] = at[k - 1] + n[k - 1];
+        B200McRec *dst = (B200McRec *)(r->blob + o);
+        for (const B200McRec &m : r->mc) dst[at[B200_MC_IS_SMALL(m.w, m.h) ? 1 + B200_MC_SMALL_KEY(m.flags) : 0]++] = m;
+        h->mc_big_count = (uint32_t)n[0];
+    }
     o = (o + r->mc.size() * 32 + 255) & ~(uint64_t)255;
     h->total_bytes = (uint32_t)o;
     r->nbytes = o; r->open = false;

@@ -11,8 +11,9 @@
  * hevcpred.h:32-40, videodsp.h:66-70) and never touches pixels: it maps the pointers it is given
  * back to (DPB slot, plane, x, y) through the planes registered at frame begin and appends one record.
  * Compiled against the reference's headers where they lie (-I/root/reference); it contains no
- * reference code.  Round-1 limits: one decoder instance, threads=1 (state below is process-global),
- * constrained_intra_pred / cross-component prediction / pcm+transquant-bypass SAO restore are
+ * reference code.  Threading: frame threads (-f 1) are supported -- recorder state is thread-local, pictures are
+ * submitted to the GPU in decode order through a ticket; WPP / tile slice threads of ONE picture are not (round 1).
+ * One decoder instance per process.  constrained_intra_pred / cross-component prediction / pcm+transquant-bypass SAO restore are
  * rejected with an error from b200_frame_end.
  */
 #include <stdint.h>
@@ -31,12 +32,26 @@
 
 typedef struct RegPlane { const uint8_t *base; ptrdiff_t linesize; int slot, plane, w, h; } RegPlane;
 
+#include <pthread.h>
+
+/* shared by every decoding thread: the device context, the geometry, and the ticket that keeps pictures in decode
+ * order on the GPU (frame threads reach b200_frame_end out of order; hevc_frame_start is called in decode order) */
 static struct {
     B200Ctx *ctx;
-    B200Rec *rec;
     B200Config cfg;
     int bd, B, cfi;
     int pw[3], ph[3];
+    pthread_mutex_t mu;
+    pthread_cond_t cv;
+    unsigned next_ticket, turn;
+    unsigned gen;                       /* bumped when the context is re-created for a new geometry */
+} G = { .mu = PTHREAD_MUTEX_INITIALIZER, .cv = PTHREAD_COND_INITIALIZER };
+
+/* per decoding thread (frame threads decode one whole picture each on their own HEVCContext copy, pthread_frame.c) */
+static __thread struct {
+    B200Rec *rec;
+    unsigned rec_gen;
+    unsigned ticket;
     RegPlane reg[MAX_REG * 3];
     int n_reg;
     const uint8_t *cur_base[3]; ptrdiff_t cur_ls[3]; int cur_slot;
@@ -57,15 +72,15 @@ static void fail(int code, const char *msg)
 {
     if (!g.err) { g.err = code; snprintf(g.errmsg, sizeof(g.errmsg), "%s", msg); }
 }
-const char *b200_shim_error(void) { return g.err ? g.errmsg : (g.ctx ? b200_last_error(g.ctx) : ""); }
+const char *b200_shim_error(void) { return g.err ? g.errmsg : (G.ctx ? b200_last_error(G.ctx) : ""); }
 
 /* ---- pointer -> (slot, plane, x, y) ---------------------------------------------------------------- */
 static int locate_cur(const uint8_t *p, int *plane, int *x, int *y)
 {
     for (int c = 0; c < 3; c++) {
         ptrdiff_t off = p - g.cur_base[c];
-        if (off >= 0 && off < g.cur_ls[c] * g.ph[c]) {
-            *plane = c; *y = (int)(off / g.cur_ls[c]); *x = (int)(off % g.cur_ls[c]) / g.B;
+        if (off >= 0 && off < g.cur_ls[c] * G.ph[c]) {
+            *plane = c; *y = (int)(off / g.cur_ls[c]); *x = (int)(off % g.cur_ls[c]) / G.B;
             return 0;
         }
     }
@@ -78,14 +93,14 @@ static int locate_ref(const uint8_t *p, int plane_hint, int *slot, int *x, int *
     for (int e = 0; e < 2; e++)          /* source inside an edge-emulation buffer? (hevc.c:1673) */
         if (g.emu[e].buf && p >= g.emu[e].buf && p < g.emu[e].buf + g.emu[e].ls * (MAX_PB_SIZE + 7)) {
             ptrdiff_t off = p - g.emu[e].buf;
-            *slot = g.emu[e].slot; *y = g.emu[e].y + (int)(off / g.emu[e].ls); *x = g.emu[e].x + (int)(off % g.emu[e].ls) / g.B;
+            *slot = g.emu[e].slot; *y = g.emu[e].y + (int)(off / g.emu[e].ls); *x = g.emu[e].x + (int)(off % g.emu[e].ls) / G.B;
             return g.emu[e].plane;
         }
     for (int i = 0; i < g.n_reg; i++) {
         const RegPlane *r = &g.reg[i];
         ptrdiff_t off = p - r->base;
         if (off >= 0 && off < r->linesize * r->h && (plane_hint < 0 || r->plane == plane_hint)) {
-            *slot = r->slot; *y = (int)(off / r->linesize); *x = (int)(off % r->linesize) / g.B;
+            *slot = r->slot; *y = (int)(off / r->linesize); *x = (int)(off % r->linesize) / G.B;
             return r->plane;
         }
     }
@@ -138,7 +153,7 @@ static void rec_put_pcm(uint8_t *dst, ptrdiff_t stride, int width, int height, G
     if (width > 32 || height > 64) { fail(B200_ENOTSUP, "pcm block too large"); return; }
     /* square blocks per plane; 4:2:2 chroma (w x 2w) is recorded as two squares */
     for (int part = 0; part < height / width; part++) {
-        for (int i = 0; i < width * width; i++) smp[i] = (int16_t)(get_bits(gb, pcm_bit_depth) << (g.bd - pcm_bit_depth));
+        for (int i = 0; i < width * width; i++) smp[i] = (int16_t)(get_bits(gb, pcm_bit_depth) << (G.bd - pcm_bit_depth));
         int log2 = 0;
         while ((1 << log2) < width) log2++;
         if (log2 < 2) { fail(B200_ENOTSUP, "pcm block smaller than 4x4"); return; }
@@ -156,7 +171,7 @@ static int mc_fill(B200McRec *m, int list, const uint8_t *src, int mx, int my, i
     (void)chroma_hint;
     const int ri = ref_index(slot);
     /* positions far outside the picture clamp sample by sample: pre-clamp the origin so that it fits int16 */
-    const int pw = g.pw[plane], ph = g.ph[plane];
+    const int pw = G.pw[plane], ph = G.ph[plane];
     if (sx < -80) sx = -80; if (sx > pw + 16) sx = pw + 16;
     if (sy < -80) sy = -80; if (sy > ph + 16) sy = ph + 16;
     if (list == 0) { m->ref0 = (uint8_t)ri; m->sx0 = (int16_t)sx; m->sy0 = (int16_t)sy; m->frac0 = (uint8_t)(mx | (my << 4)); }
@@ -223,7 +238,7 @@ static void rec_emulated_edge_mc(uint8_t *buf, const uint8_t *src, ptrdiff_t buf
                                  int block_w, int block_h, int src_x, int src_y, int w, int h)
 {
     (void)block_w; (void)block_h; (void)w; (void)h;
-    const uint8_t *base = src - ((ptrdiff_t)src_y * src_linesize + (ptrdiff_t)src_x * g.B);
+    const uint8_t *base = src - ((ptrdiff_t)src_y * src_linesize + (ptrdiff_t)src_x * G.B);
     for (int i = 0; i < g.n_reg; i++)
         if (g.reg[i].base == base && g.reg[i].linesize == src_linesize) {
             int e = (g.emu[0].buf == buf) ? 0 : (g.emu[1].buf == buf) ? 1 : (g.emu_next++ & 1);
@@ -346,39 +361,59 @@ void ff_videodsp_init_b200(VideoDSPContext *c, int bpc)
 }
 
 /* ---- frame life cycle ----------------------------------------------------------------------------------------- */
-static int ensure_ctx(const HEVCContext *s)
+static int ensure_ctx(const HEVCContext *s)       /* called with G.mu held */
 {
     const HEVCSPS *sps = s->sps;
-    if (g.ctx && g.cfg.width == sps->width && g.cfg.height == sps->height && g.cfg.bit_depth == sps->bit_depth && g.cfg.chroma_format_idc == sps->chroma_format_idc)
-        return 0;
-    if (g.ctx) { b200_rec_destroy(g.rec); b200_ctx_destroy(g.ctx); g.ctx = NULL; g.rec = NULL; }
-    memset(&g.cfg, 0, sizeof(g.cfg));
-    const char *dev = getenv("B200_DEVICE");
-    g.cfg.device = dev ? atoi(dev) : 0;
-    g.cfg.width = sps->width; g.cfg.height = sps->height; g.cfg.chroma_format_idc = sps->chroma_format_idc;
-    g.cfg.bit_depth = sps->bit_depth; g.cfg.log2_ctb_size = sps->log2_ctb_size;
-    g.cfg.n_slots = 32;                /* == FF_ARRAY_ELEMS(s->DPB), hevc.h:1207 */
-    g.cfg.n_arenas = 2;
-    int rc = b200_ctx_create(&g.cfg, &g.ctx);
-    if (rc) { fail(rc, b200_last_error(NULL)); return rc; }
-    rc = b200_rec_create(&g.cfg, &g.rec);
-    if (rc) { fail(rc, "b200_rec_create failed"); return rc; }
-    g.bd = sps->bit_depth; g.B = g.bd > 8 ? 2 : 1; g.cfi = sps->chroma_format_idc;
-    for (int p = 0; p < 3; p++) b200_plane_dims(sps->width, sps->height, g.cfi, p, &g.pw[p], &g.ph[p]);
+    if (!(G.ctx && G.cfg.width == sps->width && G.cfg.height == sps->height && G.cfg.bit_depth == sps->bit_depth &&
+          G.cfg.chroma_format_idc == sps->chroma_format_idc && G.cfg.log2_ctb_size == (int)sps->log2_ctb_size)) {
+        G.gen++;
+        if (G.ctx) { b200_ctx_destroy(G.ctx); G.ctx = NULL; }
+        memset(&G.cfg, 0, sizeof(G.cfg));
+        const char *dev = getenv("B200_DEVICE");
+        G.cfg.device = dev ? atoi(dev) : 0;
+        G.cfg.width = sps->width; G.cfg.height = sps->height; G.cfg.chroma_format_idc = sps->chroma_format_idc;
+        G.cfg.bit_depth = sps->bit_depth; G.cfg.log2_ctb_size = sps->log2_ctb_size;
+        G.cfg.n_slots = 32;                /* == FF_ARRAY_ELEMS(s->DPB), hevc.h:1207 */
+        G.cfg.n_arenas = 8;
+        int rc = b200_ctx_create(&G.cfg, &G.ctx);
+        if (rc) { fail(rc, b200_last_error(NULL)); return rc; }
+        G.bd = sps->bit_depth; G.B = G.bd > 8 ? 2 : 1; G.cfi = sps->chroma_format_idc;
+        for (int p = 0; p < 3; p++) b200_plane_dims(sps->width, sps->height, G.cfi, p, &G.pw[p], &G.ph[p]);
+    }
+    if (g.rec && g.rec_gen != G.gen) { b200_rec_destroy(g.rec); g.rec = NULL; }
+    if (!g.rec) {
+        g.rec_gen = G.gen;
+        int rc = b200_rec_create(&G.cfg, &g.rec);
+        if (rc) { fail(rc, "b200_rec_create failed"); return rc; }
+    }
     return 0;
+}
+
+static void ticket_release(void)                   /* let the next picture (in decode order) submit */
+{
+    pthread_mutex_lock(&G.mu);
+    while (G.turn != g.ticket) pthread_cond_wait(&G.cv, &G.mu);
+    G.turn++;
+    pthread_cond_broadcast(&G.cv);
+    pthread_mutex_unlock(&G.mu);
 }
 
 int b200_frame_begin(HEVCContext *s)
 {
     if (g.err) return g.err;
-    if (ensure_ctx(s)) return g.err;
+    if (g.in_frame) { g.in_frame = 0; ticket_release(); }      /* previous picture of this thread was abandoned */
+    pthread_mutex_lock(&G.mu);
+    const int erc = ensure_ctx(s);
+    if (!erc) g.ticket = G.next_ticket++;
+    pthread_mutex_unlock(&G.mu);
+    if (erc) return g.err;
     g.n_reg = 0;
     for (int i = 0; i < 32; i++) {
         AVFrame *f = s->DPB[i].frame;
         if (!f || !f->data[0]) continue;
         for (int p = 0; p < 3; p++) {
             RegPlane *r = &g.reg[g.n_reg++];
-            r->base = f->data[p]; r->linesize = f->linesize[p]; r->slot = i; r->plane = p; r->w = g.pw[p]; r->h = g.ph[p];
+            r->base = f->data[p]; r->linesize = f->linesize[p]; r->slot = i; r->plane = p; r->w = G.pw[p]; r->h = G.ph[p];
         }
     }
     g.cur_slot = (int)(s->ref - s->DPB);
@@ -395,16 +430,22 @@ int b200_frame_end(HEVCContext *s)
     (void)s;
     if (!g.in_frame) return g.err ? g.err : B200_ESTATE;
     g.in_frame = 0;
+    if (g.err) { ticket_release(); return g.err; }
     if (getenv("B200_SHIM_STATS"))
         fprintf(stderr, "b200 picture %d: intra_pred %d transform_add %d mc %d deblock %d sao %d\n", g.frame_no, g.n_intra, g.n_tu, g.n_pu, g.n_dbk, g.n_sao);
     g.frame_no++; g.n_tu = g.n_intra = g.n_pu = g.n_dbk = g.n_sao = 0;
-    if (g.err) return g.err;
     const void *blob; uint64_t n;
     int rc = b200_rec_set_refs(g.rec, g.ref_slot, g.n_ref);
     if (!rc) rc = b200_rec_finish(g.rec, &blob, &n);
-    if (!rc) rc = b200_frame_submit(g.ctx, blob, n);
-    if (!rc) rc = b200_sync(g.ctx);          /* the recorder's blob memory is reused by the next picture */
-    if (rc) fail(rc, g.ctx ? b200_last_error(g.ctx) : "frame_end failed");
+    /* pictures enter the compute stream in decode order, whatever order the frame threads finish parsing in */
+    pthread_mutex_lock(&G.mu);
+    while (G.turn != g.ticket) pthread_cond_wait(&G.cv, &G.mu);
+    if (!rc) rc = b200_frame_submit(G.ctx, blob, n);
+    G.turn++;
+    pthread_cond_broadcast(&G.cv);
+    pthread_mutex_unlock(&G.mu);
+    if (!rc) rc = b200_wait_uploads(G.ctx);  /* this thread's recorder memory is reused by its next picture */
+    if (rc) fail(rc, G.ctx ? b200_last_error(G.ctx) : "frame_end failed");
     return rc;
 }
 
@@ -416,30 +457,34 @@ int b200_frame_readback(HEVCContext *s, AVFrame *frame)
     if (slot < 0) { fail(B200_EINVAL, "readback of a frame that is not in the DPB"); return g.err; }
     void *planes[3] = { frame->data[0], frame->data[1], frame->data[2] };
     int64_t strides[3] = { frame->linesize[0], frame->linesize[1], frame->linesize[2] };
-    int rc = b200_slot_readback(g.ctx, slot, planes, strides);
-    if (!rc) rc = b200_sync(g.ctx);
-    if (rc) fail(rc, b200_last_error(g.ctx));
+    int rc = b200_slot_readback(G.ctx, slot, planes, strides);
+    if (!rc) rc = b200_sync(G.ctx);
+    if (rc) fail(rc, b200_last_error(G.ctx));
     return rc;
 }
 
 /* reference pictures that exist only on the host (e.g. produced before the hook was active) */
 int b200_frame_upload_ref(HEVCContext *s, AVFrame *frame)
 {
-    if (ensure_ctx(s)) return g.err;
+    pthread_mutex_lock(&G.mu);
+    const int erc = ensure_ctx(s);
+    pthread_mutex_unlock(&G.mu);
+    if (erc) return g.err;
     int slot = -1;
     for (int i = 0; i < 32; i++) if (s->DPB[i].frame && s->DPB[i].frame->data[0] == frame->data[0]) slot = i;
     if (slot < 0) { fail(B200_EINVAL, "upload of a frame that is not in the DPB"); return g.err; }
     const void *planes[3] = { frame->data[0], frame->data[1], frame->data[2] };
     int64_t strides[3] = { frame->linesize[0], frame->linesize[1], frame->linesize[2] };
-    int rc = b200_slot_upload(g.ctx, slot, planes, strides);
-    if (!rc) rc = b200_sync(g.ctx);
-    if (rc) fail(rc, b200_last_error(g.ctx));
+    int rc = b200_slot_upload(G.ctx, slot, planes, strides);
+    if (!rc) rc = b200_sync(G.ctx);
+    if (rc) fail(rc, b200_last_error(G.ctx));
     return rc;
 }
 
 void b200_shim_close(void)
 {
-    if (g.rec) b200_rec_destroy(g.rec);
-    if (g.ctx) b200_ctx_destroy(g.ctx);
+    if (g.rec) b200_rec_destroy(g.rec);      /* recorders of other threads die with their threads' process */
+    if (G.ctx) b200_ctx_destroy(G.ctx);
+    G.ctx = NULL; G.next_ticket = G.turn = 0;
     memset(&g, 0, sizeof(g));
 }

@@ -43,10 +43,10 @@ class PinnedBuffer:
 
 class FrameEngine:
     def __init__(self, width, height, chroma_format_idc=1, bit_depth=8, log2_ctb_size=6, n_slots=6, n_arenas=2,
-                 device=0, max_blob_bytes=0, ext_frame_mem=None, ext_frame_bytes=0):
+                 device=0, max_blob_bytes=0, ext_frame_mem=None, ext_frame_bytes=0, n_lanes=0):
         self.lib = _lib.load()
         self.cfg = _lib.B200Config(device, width, height, chroma_format_idc, bit_depth, log2_ctb_size, n_slots, n_arenas,
-                                   max_blob_bytes, ext_frame_mem, ext_frame_bytes)
+                                   max_blob_bytes, ext_frame_mem, ext_frame_bytes, n_lanes, 0)
         self.width, self.height, self.cfi, self.bit_depth, self.n_slots = width, height, chroma_format_idc, bit_depth, n_slots
         self.dtype = np.uint16 if bit_depth > 8 else np.uint8
         h = C.c_void_p()
@@ -124,8 +124,22 @@ class FrameEngine:
             self.sync()
         return out
 
+    def wait_readback(self, slot):
+        """block until the last read-back of `slot` has landed in host memory (the queue keeps running)"""
+        self._chk(self.lib.b200_slot_wait_readback(self.h, slot))
+
     def sync(self):
         self._chk(self.lib.b200_sync(self.h))
+
+    def join(self):
+        """b200_stream() (lane 0) waits for every picture submitted so far; record timing events on it afterwards"""
+        self._chk(self.lib.b200_join(self.h))
+
+    def slot_begin_access(self, slot, stream, write):
+        self._chk(self.lib.b200_slot_begin_access(self.h, slot, C.c_void_p(stream), int(write)))
+
+    def slot_end_access(self, slot, stream, write):
+        self._chk(self.lib.b200_slot_end_access(self.h, slot, C.c_void_p(stream), int(write)))
 
     def decode(self, blob, out=None):
         """submit + readback of the picture's DPB slot (blocking): what a caller of the reference's

@@ -85,7 +85,10 @@ def run_schedule(backend, rank, world, n_gops_per_rank):
 
 
 class GpuBackend:
-    """libb200hevc engine + NCCL.  The DPB lives in a torch tensor so that torch.distributed can address slots."""
+    """libb200hevc engine + NCCL.  The DPB lives in a torch tensor so that torch.distributed can address slots.
+    Ordering on the device is the engine's slot-hazard tracking (include/b200hevc.h: b200_slot_begin/end_access):
+    the broadcast is a reader of the anchor's slot on its owner and a writer of the slot everywhere else, on the
+    communication stream, so it overlaps the B pictures of the previous GOP on the compute lanes."""
 
     def __init__(self, engine, dpb_tensor, slot_bytes, world, arenas_of_blob):
         import torch
@@ -94,43 +97,27 @@ class GpuBackend:
         self.arena = arenas_of_blob
         self.compute = torch.cuda.ExternalStream(engine.lib.b200_stream(engine.h))
         self.comm = torch.cuda.Stream() if world > 1 else None
-        self.ev_anchor, self.ev_ready, self.ev_gop = {}, {}, {}
         self.bcast_bytes = 0
 
     def decode(self, pic):
         self.eng.execute(self.arena[pic.blob], pic.cur_slot, pic.ref_slots)
 
     def anchor_decoded(self, g):
-        ev = self.torch.cuda.Event()
-        ev.record(self.compute)
-        self.ev_anchor[g] = ev
-        if self.world == 1:
-            self.ev_ready[g] = ev
+        pass                                           # the engine recorded the slot's "written" event
 
     def wait_anchor(self, g):
-        ev = self.ev_ready.get(g)
-        if ev is not None:
-            self.compute.wait_event(ev)
+        pass                                           # pictures wait for the writers of their reference slots
 
     def broadcast_anchor(self, g, slot, owner):
         torch = self.torch
         import torch.distributed as dist
         t = self.dpb[slot * self.slot_bytes:(slot + 1) * self.slot_bytes]
+        write = dist.get_rank() != owner
         with torch.cuda.stream(self.comm):
-            if g in self.ev_anchor:                    # owner: the picture must be complete before it is sent
-                self.comm.wait_event(self.ev_anchor[g])
-            old = self.ev_gop.get(g - N_ANCHOR_SLOTS + 1) or self.ev_gop.get(g - N_ANCHOR_SLOTS)
-            if old is not None:                        # WAR: last local readers of the slot's previous content
-                self.comm.wait_event(old)
+            self.eng.slot_begin_access(slot, self.comm.cuda_stream, write)
             dist.broadcast(t, src=owner)
-            ev = torch.cuda.Event()
-            ev.record(self.comm)
-        self.ev_ready[g] = ev
+            self.eng.slot_end_access(slot, self.comm.cuda_stream, write)
         self.bcast_bytes += self.slot_bytes
-        for k in [k for k in self.ev_ready if k < g - 2 * N_ANCHOR_SLOTS]:
-            self.ev_ready.pop(k, None); self.ev_anchor.pop(k, None); self.ev_gop.pop(k, None)
 
     def gop_done(self, g):
-        ev = self.torch.cuda.Event()
-        ev.record(self.compute)
-        self.ev_gop[g] = ev
+        pass

@@ -1,4 +1,4 @@
-"""numpy mirror of include/b200hevc_worklist.h (blob v1) — builder and parser.
+"""numpy mirror of include/b200hevc_worklist.h (blob v3) — builder and parser.
 
 Host-side only.  The structured dtypes below are byte-for-byte the C structs; a blob built here
 is what the C recorder (csrc/recorder.cpp) produces for the same table calls.
@@ -6,7 +6,7 @@ is what the C recorder (csrc/recorder.cpp) produces for the same table calls.
 import numpy as np
 
 MAGIC = 0x4C573242
-VERSION = 2
+VERSION = 3
 TU_DENSE = 0xFFFF
 (SEC_COEFF, SEC_TU4, SEC_TU8, SEC_TU16, SEC_TU32, SEC_INTRA, SEC_MC, SEC_DBK, SEC_SAO, SEC_COUNT) = range(10)
 
@@ -24,7 +24,7 @@ header_dt = np.dtype([
     ("width", "<u2"), ("height", "<u2"), ("chroma_format_idc", "u1"), ("bit_depth", "u1"),
     ("log2_ctb_size", "u1"), ("cur_slot", "u1"), ("flags", "<u4"),
     ("sec", section_dt, (SEC_COUNT,)), ("ref_slot", "u1", (16,)), ("n_ref", "u1"), ("pad", "u1", (3,)),
-    ("reserved", "<u4", (64 - 12 - 2 * SEC_COUNT,)),
+    ("mc_big_count", "<u4"), ("reserved", "<u4", (64 - 13 - 2 * SEC_COUNT,)),
 ])
 tu_dt = np.dtype([("x", "<u2"), ("y", "<u2"), ("plane", "u1"), ("log2", "u1"), ("kind", "u1"), ("flags", "u1"),
                   ("col_limit", "u1"), ("pad", "u1"), ("nnz", "<u2"), ("coeff_off", "<u4")])
@@ -93,6 +93,15 @@ def split_mc_tiles(recs):
     return np.concatenate(out)
 
 
+def order_mc(recs):
+    """B200_SEC_MC order (B200BlobHeader.mc_big_count): big tiles in the given order, then the <= 8x8 tiles bucketed by
+    (chroma, bi) -- same stable bucketing as b200_rec_finish().  Returns (ordered records, mc_big_count)."""
+    recs = np.ascontiguousarray(recs, mc_dt)
+    small = (recs["w"] <= 8) & (recs["h"] <= 8)
+    key = np.where(small, 1 + np.where(recs["flags"] & MCF_CHROMA, 2, 0) + np.where(recs["flags"] & MCF_BI, 1, 0), 0)
+    return recs[np.argsort(key, kind="stable")], int((~small).sum())
+
+
 def tu_dense(t, pool):
     """(dense NxN coefficients, parked-pool index or None) of one TU record -- mirror of b200_tu_data / b200_tu_expand"""
     n2 = 1 << (2 * int(t["log2"]))
@@ -133,7 +142,7 @@ def build_blob(width, height, cfi, bit_depth, log2_ctb, cur_slot, poc=0, coeff=N
     for k in range(4):
         parts[SEC_TU4 + k] = np.ascontiguousarray(tu.get(k + 2, np.zeros(0, tu_dt)), tu_dt)
     parts[SEC_INTRA] = np.ascontiguousarray(intra if intra is not None else np.zeros(0, intra_dt), intra_dt)
-    parts[SEC_MC] = np.ascontiguousarray(mc if mc is not None else np.zeros(0, mc_dt), mc_dt)
+    parts[SEC_MC], mc_big = order_mc(mc if mc is not None else np.zeros(0, mc_dt))
     parts[SEC_DBK] = np.ascontiguousarray(dbk if dbk is not None else np.zeros(0, np.uint16), np.uint16)
     parts[SEC_SAO] = np.ascontiguousarray(sao if sao is not None else np.zeros(0, sao_dt), sao_dt)
     hdr = np.zeros(1, header_dt)
@@ -142,6 +151,7 @@ def build_blob(width, height, cfi, bit_depth, log2_ctb, cur_slot, poc=0, coeff=N
     hdr["log2_ctb_size"], hdr["cur_slot"] = log2_ctb, cur_slot
     assert len(ref_slots) <= 16
     hdr["n_ref"] = len(ref_slots)
+    hdr["mc_big_count"] = mc_big
     hdr["ref_slot"][0][:len(ref_slots)] = list(ref_slots)
     hdr["flags"] = (FRAME_HAS_DEBLOCK if len(parts[SEC_DBK]) else 0) | (FRAME_HAS_SAO if len(parts[SEC_SAO]) else 0)
     off = 256

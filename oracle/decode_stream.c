@@ -26,9 +26,10 @@ static void plane_md5(const uint8_t *p, int pitch, int w_bytes, int h, char *hex
 
 int main(int argc, char **argv)
 {
-    if (argc < 2) { fprintf(stderr, "usage: %s stream.hevc [quiet]\n", argv[0]); return 2; }
-    const int quiet = argc > 2;
-    OpenHevc_Handle h = libOpenHevcInit(1, 1);
+    if (argc < 2) { fprintf(stderr, "usage: %s stream.hevc [threads [quiet]]   (threads > 1: frame threads, like hevc -p N -f 1)\n", argv[0]); return 2; }
+    const int threads = argc > 2 ? atoi(argv[2]) : 1;
+    const int quiet = argc > 3;
+    OpenHevc_Handle h = libOpenHevcInit(threads > 0 ? threads : 1, 1 /* frame */);
     if (!h) return 3;
     libOpenHevcSetCheckMD5(h, 0);
     av_register_all();

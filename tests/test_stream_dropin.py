@@ -2,7 +2,7 @@
  (a) the UNMODIFIED reference (oracle/_ref/decode_ref -> libohevc_ref.so) and
  (b) the reference carrying the three table hooks + three frame hooks of INTEGRATION.md
      (oracle/_ref/decode_b200 -> libohevc_b200.so -> libb200hevc_shim.so -> GPU),
-both through the public libOpenHevc* API, single thread.  Per-picture plane MD5s must be identical
+both through the public libOpenHevc* API, single thread and with frame threads (hevc -p 4 -f 1).  Per-picture plane MD5s must be identical
 (BASELINE config 1: 832x480 8-bit, I pictures, bit-exact gate)."""
 import glob
 import os
@@ -15,8 +15,8 @@ REFDIR = os.path.join(os.path.dirname(HERE), "oracle", "_ref")
 STREAMS = sorted(glob.glob(os.path.join(HERE, "golden", "streams", "*.hevc")))
 
 
-def run(binary, stream):
-    out = subprocess.run([os.path.join(REFDIR, binary), stream], capture_output=True, text=True, timeout=600)
+def run(binary, stream, threads=1):
+    out = subprocess.run([os.path.join(REFDIR, binary), stream, str(threads)], capture_output=True, text=True, timeout=600)
     assert out.returncode == 0, out.stderr[-2000:]
     return [l for l in out.stdout.splitlines() if l.startswith("frame ")]
 
@@ -44,3 +44,28 @@ def test_hooked_decoder_is_bit_exact_on_the_same_stream(stream):
     assert len(got) == len(want)
     for g, w in zip(got, want):
         assert g == w, f"picture differs:\n got {g}\nwant {w}"
+
+
+@pytest.mark.parametrize("stream", [s for s in STREAMS if "/b_" in s or "/p_" in s], ids=os.path.basename)
+def test_reference_decoder_frame_threads(stream):
+    """CPU: the reference's frame threading is deterministic on these streams (precondition of the GPU test below)"""
+    if not os.path.exists(os.path.join(REFDIR, "decode_ref")):
+        pytest.skip("oracle/_ref/decode_ref not built")
+    assert run("decode_ref", stream, threads=4) == open(stream[:-5] + ".md5").read().splitlines()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("stream", STREAMS, ids=os.path.basename)
+def test_hooked_decoder_with_frame_threads(stream):
+    """4 frame threads: thread-local recorders, pictures reach the GPU in decode order through the shim's ticket.
+    The arbiter is the unmodified reference run with the same thread count (on streams shorter than the thread
+    count its own flush logic, main_hm/main.c:283, drops the delayed pictures -- the drop-in must behave the same)."""
+    if not os.path.exists(os.path.join(REFDIR, "decode_b200")) or not os.path.exists(os.path.join(REFDIR, "decode_ref")):
+        pytest.skip("oracle/_ref/decode_ref / decode_b200 not built")
+    want = run("decode_ref", stream, threads=4)
+    committed = open(stream[:-5] + ".md5").read().splitlines()
+    assert [l.split()[2:] for l in want] == [l.split()[2:] for l in committed[:len(want)]]
+    if "/b_" in stream or "/p_" in stream:
+        assert want == committed
+    for rep in range(2):
+        assert run("decode_b200", stream, threads=4) == want
