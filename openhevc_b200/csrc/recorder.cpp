@@ -222,9 +222,11 @@ extern "C" int b200_rec_mc(B200Rec *r, const B200McRec *b)
 {
     if (!r || !r->open || !b || b->plane > 2 || !b->w || !b->h || b->w > 64 || b->h > 64) return B200_EINVAL;
     if (b->x + b->w > r->pw[b->plane] || b->y + b->h > r->ph[b->plane]) return B200_EINVAL;
-    // split into tiles of <= 32 x 8 or <= 16 x 16 samples: one warp each on the device
+    // split into tiles of <= 16 x 16 samples (blocks taller than 8 rows: the squarer tile has the smaller filter
+    // halo) or <= 32 x 8: one warp each on the device, tiles of <= 8 x 8 four per warp
+    const int twmax = b->h > 8 ? 16 : 32;
     for (int tx = 0; tx < b->w;) {
-        const int tw = b->w - tx > 32 ? 32 : b->w - tx;
+        const int tw = b->w - tx > twmax ? twmax : b->w - tx;
         const int maxh = tw > 16 ? 8 : 16;
         for (int ty = 0; ty < b->h; ty += maxh) {
             const int th = b->h - ty > maxh ? maxh : b->h - ty;

@@ -71,7 +71,7 @@ class DbkLayout:
 
 
 def split_mc_tiles(recs):
-    """Same tiling as b200_rec_mc(): every block becomes tiles of <= 32x8 or <= 16x16 samples (vectorised per block shape)."""
+    """Same tiling as b200_rec_mc(): every block becomes tiles of <= 16x16 (blocks taller than 8) or <= 32x8 samples (vectorised per block shape)."""
     if len(recs) == 0:
         return np.zeros(0, mc_dt)
     out = []
@@ -80,8 +80,9 @@ def split_mc_tiles(recs):
         w, h = int(w), int(h)
         sel = recs[(recs["w"] == w) & (recs["h"] == h)]
         tiles, tx = [], 0
+        twmax = 16 if h > 8 else 32
         while tx < w:
-            tw = min(32, w - tx)
+            tw = min(twmax, w - tx)
             maxh = 8 if tw > 16 else 16
             tiles += [(tx, ty, tw, min(maxh, h - ty)) for ty in range(0, h, maxh)]
             tx += tw
