@@ -120,6 +120,7 @@ int  b200_rec_sao(B200Rec *r, int plane, int x, int y, const B200SaoRec *params)
  * intra records by dependency level (stable); returns the number of levels (>= 0) or a negative error */
 int  b200_intra_level_order(const B200IntraRec *recs, uint32_t n, int width, int height, int chroma_format_idc, uint32_t *perm);
 /* finish: returns the blob (pinned memory owned by the recorder, valid until the next begin) */
+int b200_rec_merge(B200Rec *dst, B200Rec *src);           /* fold the lists of a worker thread of the SAME picture into dst (WPP / tiles / slices) */
 int  b200_rec_finish(B200Rec *r, const void **blob, uint64_t *nbytes);
 
 #ifdef __cplusplus

@@ -5,6 +5,7 @@
 // recording) | TU4 | TU8 | TU16 | TU32 | INTRA | MC   (lists appended by b200_rec_finish).
 #include <stdlib.h>
 #include <string.h>
+#include <algorithm>
 #include <vector>
 #include "../../include/b200hevc.h"
 
@@ -24,6 +25,7 @@ struct B200Rec {
     std::vector<B200McRec> mc;
     int last_intra[3];
     bool any_dbk = false, any_sao = false, open = false;
+    bool merged = false;         // holds lists of several recording threads: intra records need re-ordering at finish
     int cur_slot = 0, poc = 0;
     uint8_t ref_slot[16];
     int n_ref = 0;
@@ -134,7 +136,7 @@ extern "C" int b200_rec_begin(B200Rec *r, int cur_slot, int poc)
     r->intra.clear(); r->mc.clear();
     r->ncoef = 0; r->npark = 0; r->any_dbk = r->any_sao = false;
     r->last_intra[0] = r->last_intra[1] = r->last_intra[2] = -1;
-    r->cur_slot = cur_slot; r->poc = poc; r->open = true; r->nbytes = 0; r->n_ref = 0;
+    r->cur_slot = cur_slot; r->poc = poc; r->open = true; r->nbytes = 0; r->n_ref = 0; r->merged = false;
     return 0;
 }
 
@@ -241,6 +243,68 @@ extern "C" int b200_rec_mc(B200Rec *r, const B200McRec *b)
     return 0;
 }
 
+// Slice / WPP / tile worker threads of ONE picture record into their own B200Rec (lock-free appends);
+// at frame end the owner folds them into its recorder.  `s` must have its reference table set (b200_rec_set_refs);
+// indices are re-mapped into d's table, pool offsets relocated.  s is closed afterwards.
+extern "C" int b200_rec_merge(B200Rec *d, B200Rec *s)
+{
+    if (!d || !s || d == s || !d->open || !s->open) return B200_EINVAL;
+    if (d->cfg.width != s->cfg.width || d->cfg.height != s->cfg.height || d->cfg.chroma_format_idc != s->cfg.chroma_format_idc ||
+        d->cfg.bit_depth != s->cfg.bit_depth || d->cfg.log2_ctb_size != s->cfg.log2_ctb_size || d->cur_slot != s->cur_slot)
+        return B200_EINVAL;
+    uint8_t map[16];
+    for (int i = 0; i < s->n_ref; i++) {
+        int j = 0;
+        while (j < d->n_ref && d->ref_slot[j] != s->ref_slot[i]) j++;
+        if (j == d->n_ref) {
+            if (d->n_ref == 16) return B200_ENOTSUP;
+            d->ref_slot[d->n_ref++] = s->ref_slot[i];
+        }
+        map[i] = (uint8_t)j;
+    }
+    const uint32_t base = (d->ncoef + 7) & ~7u, pbase = (d->npark + 7) & ~7u;
+    if ((uint64_t)d->off_pool + ((uint64_t)base + s->ncoef) * 2 + (1u << 16) > d->cap) return B200_ENOMEM;
+    int16_t *dp = (int16_t *)(d->blob + d->off_pool);
+    if (s->ncoef) memcpy(dp + base, s->blob + s->off_pool, (size_t)s->ncoef * 2);
+    d->ncoef = base + s->ncoef;
+    d->npark = pbase + s->npark;
+    for (int k = 0; k < 4; k++)
+        for (B200TuRec t : s->tu[k]) {
+            t.coeff_off += base;
+            if (t.flags & B200_TUF_PARK) {
+                const uint32_t po = ((uint32_t)(uint16_t)dp[t.coeff_off] | ((uint32_t)(uint16_t)dp[t.coeff_off + 1] << 16)) + pbase;
+                dp[t.coeff_off] = (int16_t)(po & 0xffff); dp[t.coeff_off + 1] = (int16_t)(po >> 16);
+            }
+            d->tu[k].push_back(t);
+        }
+    for (B200IntraRec ir : s->intra) {
+        if (ir.resid_off != B200_NO_RESID) ir.resid_off += pbase;
+        d->intra.push_back(ir);
+    }
+    for (B200McRec m : s->mc) {
+        if (m.ref0 >= s->n_ref || ((m.flags & B200_MCF_BI) && m.ref1 >= s->n_ref)) return B200_EINVAL;
+        m.ref0 = map[m.ref0];
+        if (m.flags & B200_MCF_BI) m.ref1 = map[m.ref1];
+        d->mc.push_back(m);
+    }
+    if (s->any_dbk) {
+        uint16_t *dg = (uint16_t *)(d->blob + d->off_dbk);
+        const uint16_t *sg = (const uint16_t *)(s->blob + s->off_dbk);
+        for (uint32_t i = 0; i < d->dbk.total; i++) if (sg[i]) dg[i] = sg[i];
+        d->any_dbk = true;
+    }
+    if (s->any_sao) {
+        uint64_t *dg = (uint64_t *)(d->blob + d->off_sao);
+        const uint64_t *sg = (const uint64_t *)(s->blob + s->off_sao);
+        for (int i = 0; i < 3 * d->ctb_w * d->ctb_h; i++) if (sg[2 * i] | sg[2 * i + 1]) { dg[2 * i] = sg[2 * i]; dg[2 * i + 1] = sg[2 * i + 1]; }
+        d->any_sao = true;
+    }
+    d->last_intra[0] = d->last_intra[1] = d->last_intra[2] = -1;
+    d->merged = true;
+    s->open = false;
+    return 0;
+}
+
 extern "C" int b200_rec_deblock(B200Rec *r, int plane, int vertical, int x, int y, int beta, const int tc[2],
                                 const uint8_t no_p[2], const uint8_t no_q[2])
 {
@@ -298,6 +362,16 @@ extern "C" int b200_rec_finish(B200Rec *r, const void **blob, uint64_t *nbytes)
         o = (o + r->tu[s].size() * 16 + 255) & ~(uint64_t)255;
     }
     h->sec[B200_SEC_INTRA].off = (uint32_t)o; h->sec[B200_SEC_INTRA].count = (uint32_t)r->intra.size();
+    if (r->merged) {
+        // each CTB was recorded by one thread in decode order; CTB raster order between them is a topological order of
+        // the intra dependencies (they reach up / left / up-right CTBs only), which is all the level sort needs
+        const int lc = r->cfg.log2_ctb_size, cfi = r->cfg.chroma_format_idc, cw = r->ctb_w;
+        auto key = [&](const B200IntraRec &a) {
+            const int hs = a.plane && cfi != 3, vs = a.plane && cfi == 1;
+            return (((int)a.y << vs) >> lc) * cw + (((int)a.x << hs) >> lc);
+        };
+        std::stable_sort(r->intra.begin(), r->intra.end(), [&](const B200IntraRec &a, const B200IntraRec &b) { return key(a) < key(b); });
+    }
     if (!r->intra.empty()) {
         std::vector<uint32_t> perm(r->intra.size());
         b200_intra_level_order(r->intra.data(), (uint32_t)r->intra.size(), r->cfg.width, r->cfg.height, r->cfg.chroma_format_idc, perm.data());

@@ -11,9 +11,12 @@
  * hevcpred.h:32-40, videodsp.h:66-70) and never touches pixels: it maps the pointers it is given
  * back to (DPB slot, plane, x, y) through the planes registered at frame begin and appends one record.
  * Compiled against the reference's headers where they lie (-I/root/reference); it contains no
- * reference code.  Threading: frame threads (-f 1) are supported -- recorder state is thread-local, pictures are
- * submitted to the GPU in decode order through a ticket; WPP / tile slice threads of ONE picture are not (round 1).
- * One decoder instance per process.  constrained_intra_pred / cross-component prediction / pcm+transquant-bypass SAO restore are
+ * reference code.  Threading: recorder state is thread-local.  Frame threads (-f 1): every thread owns
+ * the picture it decodes, pictures are submitted to the GPU in decode order through a ticket.  Slice / WPP / tile worker
+ * threads of ONE picture (-f 2, execute2 jobs, hevc.c:3082): a worker attaches itself to the picture in progress on its
+ * first table call, records into its own B200Rec, and b200_frame_end folds the workers into the owner's recorder
+ * (b200_rec_merge).  Frame and slice threads combined (-f 4) are rejected: a table call carries no context, so a worker
+ * cannot tell which of several pictures in progress it belongs to.  One decoder instance per process.  constrained_intra_pred / cross-component prediction / pcm+transquant-bypass SAO restore are
  * rejected with an error from b200_frame_end.
  */
 #include <stdint.h>
@@ -29,6 +32,8 @@
 #include "b200hevc_tables.h"
 
 #define MAX_REG 33
+#define MAX_WORKERS 64
+#define MAX_ACTIVE 64
 
 typedef struct RegPlane { const uint8_t *base; ptrdiff_t linesize; int slot, plane, w, h; } RegPlane;
 
@@ -45,10 +50,13 @@ static struct {
     pthread_cond_t cv;
     unsigned next_ticket, turn;
     unsigned gen;                       /* bumped when the context is re-created for a new geometry */
+    struct ShimThread *active[MAX_ACTIVE];   /* owners of the pictures between b200_frame_begin and b200_frame_end */
+    int n_active;
 } G = { .mu = PTHREAD_MUTEX_INITIALIZER, .cv = PTHREAD_COND_INITIALIZER };
 
-/* per decoding thread (frame threads decode one whole picture each on their own HEVCContext copy, pthread_frame.c) */
-static __thread struct {
+/* per thread: the owner of a picture (the thread that runs hevc_frame_start .. the end of decode_nal_unit for it; with
+ * frame threads one per picture in flight, pthread_frame.c) or a slice / WPP worker attached to an owner's picture */
+typedef struct ShimThread {
     B200Rec *rec;
     unsigned rec_gen;
     unsigned ticket;
@@ -64,9 +72,14 @@ static __thread struct {
     struct { const uint8_t *buf; ptrdiff_t ls; int slot, plane, x, y; } emu[2];
     int emu_next;
     int err; char errmsg[256];
-    int in_frame;
+    int in_frame;                                        /* 0 no picture, 1 owner of the picture in progress, 2 attached worker */
+    int poc;
+    unsigned frame_seq;                                  /* owner: bumped by every b200_frame_begin */
+    struct ShimThread *workers[MAX_WORKERS]; int n_workers;   /* owner: workers that recorded part of this picture */
+    struct ShimThread *att; unsigned att_seq;            /* worker: the owner it is attached to */
     int n_tu, n_intra, n_pu, n_dbk, n_sao, frame_no;   /* B200_SHIM_STATS=1: table calls per picture (stderr) */
-} g;
+} ShimThread;
+static __thread ShimThread g;
 
 static void fail(int code, const char *msg)
 {
@@ -74,9 +87,49 @@ static void fail(int code, const char *msg)
 }
 const char *b200_shim_error(void) { return g.err ? g.errmsg : (G.ctx ? b200_last_error(G.ctx) : ""); }
 
+/* A table call on a thread that owns no picture: a slice / WPP / tile worker (execute2 job).  Attach it to the picture
+ * in progress: own recorder, own reference table, a copy of the owner's plane registry. */
+static int attach_slow(void)
+{
+    pthread_mutex_lock(&G.mu);
+    int rc = 0;
+    if (G.n_active != 1) {
+        fail(B200_ENOTSUP, G.n_active ? "table call from a worker thread with several pictures in progress (frame + slice threads combined)"
+                                      : "table call outside b200_frame_begin / b200_frame_end");
+        rc = -1;
+    } else {
+        ShimThread *o = G.active[0];
+        if (g.rec && g.rec_gen != G.gen) { b200_rec_destroy(g.rec); g.rec = NULL; }
+        if (!g.rec) {
+            g.rec_gen = G.gen;
+            if (b200_rec_create(&G.cfg, &g.rec)) { fail(B200_ENOMEM, "b200_rec_create failed (worker)"); rc = -1; }
+        }
+        if (!rc && o->n_workers == MAX_WORKERS) { fail(B200_ENOTSUP, "too many worker threads"); rc = -1; }
+        if (!rc) {
+            memcpy(g.reg, o->reg, sizeof(g.reg)); g.n_reg = o->n_reg;
+            for (int p = 0; p < 3; p++) { g.cur_base[p] = o->cur_base[p]; g.cur_ls[p] = o->cur_ls[p]; }
+            g.cur_slot = o->cur_slot; g.poc = o->poc;
+            g.n_ref = 0; g.pend_ptr = NULL; g.first_tmp = NULL; g.emu[0].buf = g.emu[1].buf = NULL;
+            g.n_tu = g.n_intra = g.n_pu = g.n_dbk = g.n_sao = 0;
+            if (b200_rec_begin(g.rec, g.cur_slot, g.poc)) { fail(B200_ESTATE, "b200_rec_begin failed (worker)"); rc = -1; }
+            else { o->workers[o->n_workers++] = &g; g.att = o; g.att_seq = o->frame_seq; g.in_frame = 2; }
+        }
+    }
+    pthread_mutex_unlock(&G.mu);
+    return rc;
+}
+static inline int attached(void)
+{
+    if (g.in_frame == 1) return 1;
+    if (g.err) return 0;
+    if (g.in_frame == 2 && g.att->in_frame == 1 && g.att->frame_seq == g.att_seq) return 1;
+    return attach_slow() == 0;
+}
+
 /* ---- pointer -> (slot, plane, x, y) ---------------------------------------------------------------- */
 static int locate_cur(const uint8_t *p, int *plane, int *x, int *y)
 {
+    if (!attached()) return -1;
     for (int c = 0; c < 3; c++) {
         ptrdiff_t off = p - g.cur_base[c];
         if (off >= 0 && off < g.cur_ls[c] * G.ph[c]) {
@@ -90,6 +143,7 @@ static int locate_cur(const uint8_t *p, int *plane, int *x, int *y)
 
 static int locate_ref(const uint8_t *p, int plane_hint, int *slot, int *x, int *y)
 {
+    if (!attached()) return -1;
     for (int e = 0; e < 2; e++)          /* source inside an edge-emulation buffer? (hevc.c:1673) */
         if (g.emu[e].buf && p >= g.emu[e].buf && p < g.emu[e].buf + g.emu[e].ls * (MAX_PB_SIZE + 7)) {
             ptrdiff_t off = p - g.emu[e].buf;
@@ -238,6 +292,7 @@ static void rec_emulated_edge_mc(uint8_t *buf, const uint8_t *src, ptrdiff_t buf
                                  int block_w, int block_h, int src_x, int src_y, int w, int h)
 {
     (void)block_w; (void)block_h; (void)w; (void)h;
+    if (!attached()) return;
     const uint8_t *base = src - ((ptrdiff_t)src_y * src_linesize + (ptrdiff_t)src_x * G.B);
     for (int i = 0; i < g.n_reg; i++)
         if (g.reg[i].base == base && g.reg[i].linesize == src_linesize) {
@@ -292,6 +347,7 @@ static void rec_intra(HEVCContext *s, int x0, int y0, int log2_size, int c_idx)
 {
     HEVCLocalContext *lc = s->HEVClc;
     const HEVCSPS *sps = s->sps;
+    if (!attached()) return;
     if (s->pps->constrained_intra_pred_flag) { fail(B200_ENOTSUP, "constrained_intra_pred is not supported by the B200 path yet"); return; }
     const int hshift = sps->hshift[c_idx], vshift = sps->vshift[c_idx];
     const int size = 1 << log2_size;
@@ -398,10 +454,20 @@ static void ticket_release(void)                   /* let the next picture (in d
     pthread_mutex_unlock(&G.mu);
 }
 
+static void deactivate(void)                       /* the picture is no longer open for worker threads */
+{
+    pthread_mutex_lock(&G.mu);
+    g.in_frame = 0;
+    for (int i = 0; i < G.n_active; i++)
+        if (G.active[i] == &g) { G.active[i] = G.active[--G.n_active]; break; }
+    pthread_mutex_unlock(&G.mu);
+}
+
 int b200_frame_begin(HEVCContext *s)
 {
     if (g.err) return g.err;
-    if (g.in_frame) { g.in_frame = 0; ticket_release(); }      /* previous picture of this thread was abandoned */
+    if (g.in_frame == 1) { deactivate(); ticket_release(); }   /* previous picture of this thread was abandoned */
+    g.in_frame = 0;
     pthread_mutex_lock(&G.mu);
     const int erc = ensure_ctx(s);
     if (!erc) g.ticket = G.next_ticket++;
@@ -419,24 +485,39 @@ int b200_frame_begin(HEVCContext *s)
     g.cur_slot = (int)(s->ref - s->DPB);
     for (int p = 0; p < 3; p++) { g.cur_base[p] = s->frame->data[p]; g.cur_ls[p] = s->frame->linesize[p]; }
     g.n_ref = 0; g.pend_ptr = NULL; g.first_tmp = NULL; g.emu[0].buf = g.emu[1].buf = NULL;
+    g.poc = s->poc; g.n_workers = 0;
     int rc = b200_rec_begin(g.rec, g.cur_slot, s->poc);
-    if (rc) { fail(rc, "b200_rec_begin failed"); return rc; }
+    if (rc) { fail(rc, "b200_rec_begin failed"); ticket_release(); return rc; }
+    pthread_mutex_lock(&G.mu);
+    g.frame_seq++;
     g.in_frame = 1;
+    if (G.n_active < MAX_ACTIVE) G.active[G.n_active++] = &g;
+    pthread_mutex_unlock(&G.mu);
     return 0;
 }
+
 
 int b200_frame_end(HEVCContext *s)
 {
     (void)s;
-    if (!g.in_frame) return g.err ? g.err : B200_ESTATE;
-    g.in_frame = 0;
+    if (g.in_frame != 1) return g.err ? g.err : B200_ESTATE;
+    deactivate();                                   /* all execute2 jobs of the picture have returned (hevc.c:3087) */
+    int mrc = b200_rec_set_refs(g.rec, g.ref_slot, g.n_ref);
+    for (int i = 0; i < g.n_workers; i++) {         /* fold the slice / WPP workers' lists into this recorder */
+        ShimThread *w = g.workers[i];
+        if (w->err) { fail(w->err, w->errmsg); w->err = 0; }
+        if (!mrc) mrc = b200_rec_set_refs(w->rec, w->ref_slot, w->n_ref);
+        if (!mrc) mrc = b200_rec_merge(g.rec, w->rec);
+        g.n_tu += w->n_tu; g.n_intra += w->n_intra; g.n_pu += w->n_pu; g.n_dbk += w->n_dbk; g.n_sao += w->n_sao;
+        w->in_frame = 0;
+    }
+    if (mrc) fail(mrc, "merging the worker threads' work lists failed");
     if (g.err) { ticket_release(); return g.err; }
     if (getenv("B200_SHIM_STATS"))
         fprintf(stderr, "b200 picture %d: intra_pred %d transform_add %d mc %d deblock %d sao %d\n", g.frame_no, g.n_intra, g.n_tu, g.n_pu, g.n_dbk, g.n_sao);
     g.frame_no++; g.n_tu = g.n_intra = g.n_pu = g.n_dbk = g.n_sao = 0;
     const void *blob; uint64_t n;
-    int rc = b200_rec_set_refs(g.rec, g.ref_slot, g.n_ref);
-    if (!rc) rc = b200_rec_finish(g.rec, &blob, &n);
+    int rc = b200_rec_finish(g.rec, &blob, &n);
     /* pictures enter the compute stream in decode order, whatever order the frame threads finish parsing in */
     pthread_mutex_lock(&G.mu);
     while (G.turn != g.ticket) pthread_cond_wait(&G.cv, &G.mu);

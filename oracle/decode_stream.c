@@ -26,10 +26,11 @@ static void plane_md5(const uint8_t *p, int pitch, int w_bytes, int h, char *hex
 
 int main(int argc, char **argv)
 {
-    if (argc < 2) { fprintf(stderr, "usage: %s stream.hevc [threads [quiet]]   (threads > 1: frame threads, like hevc -p N -f 1)\n", argv[0]); return 2; }
+    if (argc < 2) { fprintf(stderr, "usage: %s stream.hevc [threads[w] [quiet]]   (N: frame threads, hevc -p N -f 1; Nw: slice / WPP threads, -f 2)\n", argv[0]); return 2; }
     const int threads = argc > 2 ? atoi(argv[2]) : 1;
+    const int slice_threads = argc > 2 && strchr(argv[2], 'w') != NULL;
     const int quiet = argc > 3;
-    OpenHevc_Handle h = libOpenHevcInit(threads > 0 ? threads : 1, 1 /* frame */);
+    OpenHevc_Handle h = libOpenHevcInit(threads > 0 ? threads : 1, slice_threads ? 2 /* slice */ : 1 /* frame */);
     if (!h) return 3;
     libOpenHevcSetCheckMD5(h, 0);
     av_register_all();

@@ -103,19 +103,25 @@ def test_no_gpu_means_loud_failure_not_fallback(built):
         FrameEngine(64, 64)
 
 
-def test_recorder_matches_numpy_builder(built):
-    """the C recorder (host-only code path of libb200hevc.so) and the numpy builder produce equivalent blobs"""
+def replay_through_recorders(lib, blob, geom, n_workers):
+    """Replays a blob's records through the C recorder the way the decoder's table calls would arrive.  With
+    n_workers > 1 the calls of CTB row k go to recorder k % n_workers (WPP / slice threads: every worker has its own
+    B200Rec and its own, lazily built reference table) and the workers are folded into recorder 0 with b200_rec_merge."""
     from openhevc_b200 import _lib
-    lib = _lib.load()
-    w, h, cfi, bd = 128, 64, 1, 8
-    s = FrameSynth(w, h, cfi=cfi, bit_depth=bd, seed=11, refs=[1, 2], cur_slot=3, exotic=0.05)
-    blob, _ = s.generate()
+    w, h, cfi, bd = geom
     hdr, secs = W.parse_blob(blob)
     cfg = _lib.B200Config(0, w, h, cfi, bd, 6, 6, 2, 0, None, 0)
-    r = C.c_void_p()
-    assert lib.b200_rec_create(C.byref(cfg), C.byref(r)) == 0
-    assert lib.b200_rec_begin(r, 3, 0) == 0
-    assert lib.b200_rec_set_refs(r, bytes(hdr["ref_slot"][:int(hdr["n_ref"])]), int(hdr["n_ref"])) == 0
+    recs, tables = [], []
+    for k in range(n_workers):
+        r = C.c_void_p()
+        assert lib.b200_rec_create(C.byref(cfg), C.byref(r)) == 0
+        assert lib.b200_rec_begin(r, int(hdr["cur_slot"]), 0) == 0
+        recs.append(r); tables.append([])
+
+    def who(plane, y):
+        vs = 1 if (plane and cfi == 1) else 0
+        return ((int(y) << vs) >> 6) % n_workers
+
     pool = secs[W.SEC_COEFF]
     # replay in an order the decoder could have used: intra pred call immediately followed by its residual
     parked = {}
@@ -124,6 +130,7 @@ def test_recorder_matches_numpy_builder(built):
             if t["flags"] & W.TUF_PARK:
                 parked[W.tu_dense(t, pool)[1]] = t
     for ir in secs[W.SEC_INTRA]:
+        r = recs[who(ir["plane"], ir["y"])]
         assert lib.b200_rec_intra(r, int(ir["plane"]), int(ir["x"]), int(ir["y"]), int(ir["log2"]), int(ir["mode"]), int(ir["flags"]),
                                   int(ir["top_right_size"]), int(ir["bottom_left_size"])) == 0
         if ir["resid_off"] != W.NO_RESID:
@@ -135,10 +142,17 @@ def test_recorder_matches_numpy_builder(built):
             if t["flags"] & W.TUF_PARK:
                 continue
             c = np.ascontiguousarray(W.tu_dense(t, pool)[0])
-            assert lib.b200_rec_tu(r, int(t["plane"]), int(t["x"]), int(t["y"]), int(t["log2"]), int(t["kind"]), int(t["flags"]), int(t["col_limit"]), c.ctypes.data, -1) == 0
+            assert lib.b200_rec_tu(recs[who(t["plane"], t["y"])], int(t["plane"]), int(t["x"]), int(t["y"]), int(t["log2"]), int(t["kind"]), int(t["flags"]), int(t["col_limit"]), c.ctypes.data, -1) == 0
+    ref_slots = [int(v) for v in hdr["ref_slot"][:int(hdr["n_ref"])]]
     for m in secs[W.SEC_MC]:
+        k = who(m["plane"], m["y"])
         mm = np.array([m])
-        assert lib.b200_rec_mc(r, mm.ctypes.data) == 0
+        for f in ("ref0", "ref1") if m["flags"] & W.MCF_BI else ("ref0",):     # the worker's own table, in order of first use
+            slot = ref_slots[int(m[f])]
+            if slot not in tables[k]:
+                tables[k].append(slot)
+            mm[f] = tables[k].index(slot)
+        assert lib.b200_rec_mc(recs[k], mm.ctypes.data) == 0
     L = W.DbkLayout(w, h, cfi)
     grid = secs[W.SEC_DBK]
     for p in range(3):
@@ -156,20 +170,37 @@ def test_recorder_matches_numpy_builder(built):
                 tc = (C.c_int * 2)(*[e & 63 for e in ent])
                 nop = (C.c_uint8 * 2)(*[(e >> 13) & 1 for e in ent]); noq = (C.c_uint8 * 2)(*[(e >> 14) & 1 for e in ent])
                 beta = max((e >> 6) & 127 for e in ent)
-                assert lib.b200_rec_deblock(r, p, 1 - d, x0, y0, beta, tc, nop, noq) == 0
+                assert lib.b200_rec_deblock(recs[who(p, y0)], p, 1 - d, x0, y0, beta, tc, nop, noq) == 0
     sg = secs[W.SEC_SAO]
     nctb = len(sg) // 3
     cw = (w + 63) // 64
     for p in range(3):
-        hs, vs = (1, 1) if p else (0, 0)
+        hs, vs = ((1 if cfi != 3 else 0), (1 if cfi == 1 else 0)) if p else (0, 0)
         for i in range(nctb):
             e = np.array([sg[p * nctb + i]])
-            assert lib.b200_rec_sao(r, p, ((i % cw) * 64) >> hs, ((i // cw) * 64) >> vs, e.ctypes.data) == 0
+            assert lib.b200_rec_sao(recs[(i // cw) % n_workers], p, ((i % cw) * 64) >> hs, ((i // cw) * 64) >> vs, e.ctypes.data) == 0
+    for k in range(n_workers):
+        tab = tables[k]
+        assert lib.b200_rec_set_refs(recs[k], bytes(tab), len(tab)) == 0
+    for k in range(1, n_workers):
+        assert lib.b200_rec_merge(recs[0], recs[k]) == 0
     bp, nb = C.c_void_p(), C.c_uint64()
-    assert lib.b200_rec_finish(r, C.byref(bp), C.byref(nb)) == 0
+    assert lib.b200_rec_finish(recs[0], C.byref(bp), C.byref(nb)) == 0
     rblob = np.ctypeslib.as_array(C.cast(bp, C.POINTER(C.c_uint8)), shape=(nb.value,)).copy()
+    for r in recs:
+        lib.b200_rec_destroy(r)
+    return rblob
 
-    lib.b200_rec_destroy(r)
+
+def test_recorder_matches_numpy_builder(built):
+    """the C recorder (host-only code path of libb200hevc.so) and the numpy builder produce equivalent blobs"""
+    from openhevc_b200 import _lib
+    lib = _lib.load()
+    w, h, cfi, bd = 128, 64, 1, 8
+    s = FrameSynth(w, h, cfi=cfi, bit_depth=bd, seed=11, refs=[1, 2], cur_slot=3, exotic=0.05)
+    blob, _ = s.generate()
+    hdr, secs = W.parse_blob(blob)
+    rblob = replay_through_recorders(lib, blob, (w, h, cfi, bd), 1)
     # same picture on the oracle from both blobs
     dpb = [smooth_frame(w, h, cfi, bd, 50 + k) for k in range(4)]
     a = oracle_lib.execute(blob, dpb)
@@ -177,3 +208,21 @@ def test_recorder_matches_numpy_builder(built):
     assert all((x == y).all() for x, y in zip(a, b))
     rh, rs = W.parse_blob(rblob)
     assert len(rs[W.SEC_MC]) == len(secs[W.SEC_MC]) and len(rs[W.SEC_INTRA]) == len(secs[W.SEC_INTRA])
+
+
+@pytest.mark.parametrize("n_workers,cfi,refs", [(2, 1, [1, 2]), (3, 1, []), (3, 2, [2, 1])])
+def test_recorder_merge_of_worker_threads(built, n_workers, cfi, refs):
+    """WPP / slice threads: per-worker recorders (CTB rows interleaved) merged at frame end give the same picture,
+    and the merged intra list is still in a valid dependency order"""
+    from openhevc_b200 import _lib
+    lib = _lib.load()
+    w, h, bd = 192, 320, 10
+    blob, _ = FrameSynth(w, h, cfi=cfi, bit_depth=bd, seed=77 + n_workers, refs=refs, cur_slot=3, exotic=0.05, p_intra=0.3 if refs else 1.0).generate()
+    rblob = replay_through_recorders(lib, blob, (w, h, cfi, bd), n_workers)
+    oracle_lib.check_decode_order(rblob)
+    dpb = [smooth_frame(w, h, cfi, bd, 60 + k) for k in range(4)]
+    a = oracle_lib.execute(blob, dpb)
+    b = oracle_lib.execute(rblob, dpb)
+    assert all((x == y).all() for x, y in zip(a, b))
+    rh, rs = W.parse_blob(rblob)
+    assert sorted(int(v) for v in rh["ref_slot"][:int(rh["n_ref"])]) == sorted(refs)

@@ -15,10 +15,16 @@ REFDIR = os.path.join(os.path.dirname(HERE), "oracle", "_ref")
 STREAMS = sorted(glob.glob(os.path.join(HERE, "golden", "streams", "*.hevc")))
 
 
-def run(binary, stream, threads=1):
-    out = subprocess.run([os.path.join(REFDIR, binary), stream, str(threads)], capture_output=True, text=True, timeout=600)
+def run(binary, stream, threads=1, env=None, want_stderr=False):
+    """threads: N = frame threads (hevc -p N -f 1), "Nw" = slice / WPP threads (-f 2)"""
+    out = subprocess.run([os.path.join(REFDIR, binary), stream, str(threads)], capture_output=True, text=True, timeout=600,
+                         env=dict(os.environ, **(env or {})))
     assert out.returncode == 0, out.stderr[-2000:]
-    return [l for l in out.stdout.splitlines() if l.startswith("frame ")]
+    frames = [l for l in out.stdout.splitlines() if l.startswith("frame ")]
+    return (frames, out.stderr) if want_stderr else frames
+
+
+WPP_STREAMS = [s for s in STREAMS if os.path.basename(s).startswith("wpp_")]
 
 
 def test_streams_committed():
@@ -69,3 +75,43 @@ def test_hooked_decoder_with_frame_threads(stream):
         assert want == committed
     for rep in range(2):
         assert run("decode_b200", stream, threads=4) == want
+
+
+@pytest.mark.parametrize("stream", WPP_STREAMS, ids=os.path.basename)
+def test_reference_decoder_wpp_threads(stream):
+    """CPU: entropy_coding_sync streams (one CABAC substream per CTB row + entry points) decode identically with the
+    reference's WPP worker threads (hls_slice_data_wpp, hevc.c:3082) -- pins the entry points the generator writes"""
+    if not os.path.exists(os.path.join(REFDIR, "decode_ref")):
+        pytest.skip("oracle/_ref/decode_ref not built")
+    assert len(WPP_STREAMS) >= 3
+    assert run("decode_ref", stream, threads="4w") == open(stream[:-5] + ".md5").read().splitlines()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("stream", WPP_STREAMS, ids=os.path.basename)
+def test_hooked_decoder_with_wpp_threads(stream):
+    """4 WPP worker threads record ONE picture concurrently into their own recorders; b200_frame_end merges them"""
+    if not os.path.exists(os.path.join(REFDIR, "decode_b200")):
+        pytest.skip("oracle/_ref/decode_b200 not built")
+    want = open(stream[:-5] + ".md5").read().splitlines()
+    for rep in range(2):
+        assert run("decode_b200", stream, threads="4w") == want
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("stream", [s for s in STREAMS if os.path.exists(s[:-5] + ".gen.txt")], ids=os.path.basename)
+@pytest.mark.parametrize("threads", [1, "4w"])
+def test_table_calls_equal_what_the_generator_wrote(stream, threads):
+    """B200_SHIM_STATS: the table calls the decoder made per picture == the syntax elements the generator wrote
+    (the decoder parses the stream as written, also when the calls come from worker threads)"""
+    import re
+    if not os.path.exists(os.path.join(REFDIR, "decode_b200")):
+        pytest.skip("oracle/_ref/decode_b200 not built")
+    if threads != 1 and stream not in WPP_STREAMS:
+        pytest.skip("no entry points: slice threads fall back to one thread")
+    gen = [tuple(int(v) for v in m.groups()) for m in re.finditer(r"intra_pred (\d+) transform_add (\d+) prediction units (\d+)", open(stream[:-5] + ".gen.txt").read())]
+    _, err = run("decode_b200", stream, threads=threads, env={"B200_SHIM_STATS": "1"}, want_stderr=True)
+    got = [tuple(int(v) for v in m.groups()) for m in re.finditer(r"b200 picture \d+: intra_pred (\d+) transform_add (\d+) mc (\d+)", err)]
+    assert len(got) == len(gen)
+    for (gi, gt, gm), (wi, wt, wp) in zip(got, gen):
+        assert (gi, gt) == (wi, wt) and gm == 3 * wp

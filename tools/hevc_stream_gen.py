@@ -230,9 +230,10 @@ SIG_CTX_4x4 = [0, 1, 4, 5, 2, 3, 4, 5, 6, 6, 8, 8, 7, 7, 8, 8]
 
 
 class StreamGen:
-    def __init__(self, width, height, bit_depth=8, seed=1, qp=30, sao=True, ctb_log2=6, weighted=False):
+    def __init__(self, width, height, bit_depth=8, seed=1, qp=30, sao=True, ctb_log2=6, weighted=False, wpp=False):
         self.W, self.H, self.bd, self.qp, self.sao, self.ctb_log2 = width, height, bit_depth, qp, sao, ctb_log2
         self.weighted = weighted
+        self.wpp = wpp                                                    # entropy_coding_sync: one CABAC substream per CTB row
         self.slice_type = 2                                               # 0 B, 1 P, 2 I
         self.nrefs = [0, 0]
         self.max_merge = 3
@@ -304,7 +305,7 @@ class StreamGen:
         w.u(1, 0)                                                          # slice chroma qp offsets present
         w.u(1, int(self.weighted)); w.u(1, int(self.weighted))             # weighted pred / bipred
         w.u(1, 0)                                                          # transquant bypass
-        w.u(1, 0); w.u(1, 0)                                               # tiles, wpp
+        w.u(1, 0); w.u(1, int(self.wpp))                                   # tiles, entropy_coding_sync (WPP)
         w.u(1, 1)                                                          # loop filter across slices
         w.u(1, 0)                                                          # deblocking filter control present
         w.u(1, 0)                                                          # scaling list data
@@ -348,19 +349,39 @@ class StreamGen:
             w.ue(5 - self.max_merge)                                       # five_minus_max_num_merge_cand
         w.se(self.qp - 26)                                                 # slice_qp_delta
         w.u(1, 1)                                                          # slice_loop_filter_across_slices_enabled
+        self.c = Cabac(self.init_rows[2 - slice_type], self.qp)
+        self.cnt = dict(intra_pred=0, transform_add=0, pu=0)
+        self.substreams = []
+        self.slice_data()
+        self.stats.append(dict(self.cnt))
+        self.substreams.append(self.c.bits)
+        data = bytearray()
+        ends = []
+        for bits in self.substreams:                                       # every substream ends byte aligned (9.3.2.5 / 7.3.8.1)
+            bits = bits + [0] * (-len(bits) % 8)
+            wb = BitWriter(); wb.bits = bits
+            data += wb.bytes()
+            ends.append(len(data))
+        if self.wpp:
+            # entry points count the bytes of the NAL unit INCLUDING emulation prevention bytes (7.4.7.1); the header
+            # ends in a non-zero byte (alignment bit), so the zero run restarts at the first byte of the slice data
+            pos, zeros, n = [0], 0, 0
+            for b in data:
+                if zeros >= 2 and b <= 3:
+                    n += 1; zeros = 0
+                n += 1
+                zeros = zeros + 1 if b == 0 else 0
+                pos.append(n)
+            sizes = [pos[e] - pos[st] for st, e in zip([0] + ends[:-1], ends)]
+            w.ue(len(sizes) - 1)                                           # num_entry_point_offsets
+            if len(sizes) > 1:
+                w.ue(31)                                                   # offset_len_minus1
+                for sz in sizes[:-1]:
+                    w.u(32, sz - 1)                                        # entry_point_offset_minus1
         w.bits.append(1)                                                   # byte_alignment()
         while len(w.bits) % 8:
             w.bits.append(0)
-        self.c = Cabac(self.init_rows[2 - slice_type], self.qp)
-        self.cnt = dict(intra_pred=0, transform_add=0, pu=0)
-        self.slice_data()
-        self.stats.append(dict(self.cnt))
-        body = w.bits + self.c.bits
-        while len(body) % 8:
-            body.append(0)
-        wb = BitWriter()
-        wb.bits = body
-        return nal(19 if idr else 1, wb.bytes())                           # IDR_W_RADL / TRAIL_R
+        return nal(19 if idr else 1, w.bytes() + bytes(data))              # IDR_W_RADL / TRAIL_R
 
     def pred_weight_table(self, w):
         r = self.rng
@@ -388,12 +409,26 @@ class StreamGen:
         self.ipm = np.ones((self.H >> 2, self.W >> 2), np.int32)           # INTRA_DC default
         self.skip = np.zeros((self.H >> 3, self.W >> 3), np.int32)
         n = self.cw * self.ch
+        saved = None
         for a in range(n):
             self.rx, self.ry = a % self.cw, a // self.cw
+            if self.wpp and self.rx == 0 and a:
+                # new substream: arithmetic coder restarts, contexts come from the state stored after the 2nd CTB of the
+                # row above (9.3.1: synchronization; a picture one CTB wide re-initialises instead)
+                self.substreams.append(self.c.bits)
+                fresh = Cabac(self.init_rows[2 - self.slice_type], self.qp)
+                if self.cw > 1:
+                    fresh.state = [list(st) for st in saved]
+                self.c = fresh
             if self.sao:
                 self.sao_syntax()
             self.quadtree(self.rx << self.ctb_log2, self.ry << self.ctb_log2, self.ctb_log2, 0)
             self.c.terminate(1 if a == n - 1 else 0)                       # end_of_slice_segment_flag
+            if self.wpp:
+                if self.rx == 1 or (self.cw == 1):
+                    saved = [list(st) for st in self.c.state]              # storage process after the 2nd CTB of a row
+                if self.rx == self.cw - 1 and a != n - 1:
+                    self.c.terminate(1)                                    # end_of_subset_one_bit, then byte_alignment()
 
     def sao_syntax(self):
         c, r, o = self.c, self.rng, self.off
@@ -850,9 +885,10 @@ def main():
     ap.add_argument("--no-sao", action="store_true")
     ap.add_argument("--pattern", default="I", help='picture types after the IDR, e.g. "PB" (low-delay, 2 references)')
     ap.add_argument("--weighted", action="store_true")
+    ap.add_argument("--wpp", action="store_true", help="entropy_coding_sync_enabled_flag: one substream per CTB row + entry points")
     a = ap.parse_args()
     verify_tables_against_reference()
-    g = StreamGen(a.width, a.height, a.bit_depth, a.seed, a.qp, sao=not a.no_sao, weighted=a.weighted)
+    g = StreamGen(a.width, a.height, a.bit_depth, a.seed, a.qp, sao=not a.no_sao, weighted=a.weighted, wpp=a.wpp)
     data = g.stream(a.frames, a.pattern)
     open(a.out, "wb").write(data)
     print(f"wrote {a.out}: {len(data)} bytes, {a.frames} pictures {a.width}x{a.height} {a.bit_depth}-bit")
