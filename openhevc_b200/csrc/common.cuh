@@ -16,12 +16,75 @@ struct RefTable {
     uint64_t w[2];      // B200BlobHeader.ref_slot[16] packed little-endian (possibly overridden at execute time)
 };
 
-__device__ __forceinline__ int clip3i(int v, int lo, int hi) { return min(max(v, lo), hi); }
-__device__ __forceinline__ int clip16i(int v) { return min(max(v, -32768), 32767); }
+// HD: code that is also compiled for the host so that tests/ can run the very same per-thread code on the CPU
+// (csrc/emul.cu, test infrastructure; the product library never executes it on the host)
+#define HD __host__ __device__ __forceinline__
+HD int clip3i(int v, int lo, int hi) { return v < lo ? lo : v > hi ? hi : v; }
+HD int clip16i(int v) { return v < -32768 ? -32768 : v > 32767 ? 32767 : v; }
+HD int imin(int a, int b) { return a < b ? a : b; }
+HD int imax(int a, int b) { return a > b ? a : b; }
+
+// ---- 16x2 SIMD integer helpers: the sm_100a instructions (VIADD.16x2, VIADDMNMX.S16x2.RELU, VIMNMX.U16x2, PRMT, SHF)
+// on the device, their definition in plain C on the host ----
+HD uint32_t prmt32(uint32_t a, uint32_t b, uint32_t sel)          // prmt.b32, generic mode, selectors 0..7 only
+{
+#ifdef __CUDA_ARCH__
+    uint32_t r;
+    asm("prmt.b32 %0, %1, %2, %3;" : "=r"(r) : "r"(a), "r"(b), "r"(sel));
+    return r;
+#else
+    const uint64_t src = ((uint64_t)b << 32) | a;
+    uint32_t r = 0;
+    for (int i = 0; i < 4; i++) r |= (uint32_t)((src >> (8 * ((sel >> (4 * i)) & 7))) & 0xff) << (8 * i);
+    return r;
+#endif
+}
+HD uint32_t vadd2(uint32_t a, uint32_t b)                         // per-half wrapping add
+{
+#ifdef __CUDA_ARCH__
+    return __vadd2(a, b);
+#else
+    return ((a + b) & 0xffffu) | ((((a >> 16) + (b >> 16)) & 0xffffu) << 16);
+#endif
+}
+HD uint32_t viaddmin_s16x2_relu(uint32_t a, uint32_t b, uint32_t c)   // per half: max(min(s16(a + b), s16(c)), 0)
+{
+#ifdef __CUDA_ARCH__
+    return __viaddmin_s16x2_relu(a, b, c);
+#else
+    uint32_t r = 0;
+    for (int h = 0; h < 2; h++) {
+        const int s = (int16_t)(uint16_t)(((a >> (16 * h)) + (b >> (16 * h))) & 0xffff), m = (int16_t)(uint16_t)((c >> (16 * h)) & 0xffff);
+        int v = s < m ? s : m;
+        if (v < 0) v = 0;
+        r |= (uint32_t)(v & 0xffff) << (16 * h);
+    }
+    return r;
+#endif
+}
+HD uint32_t vminu2(uint32_t a, uint32_t b)                        // per-half unsigned minimum
+{
+#ifdef __CUDA_ARCH__
+    return __vminu2(a, b);
+#else
+    const uint32_t lo = (a & 0xffff) < (b & 0xffff) ? (a & 0xffff) : (b & 0xffff), hi = (a >> 16) < (b >> 16) ? (a >> 16) : (b >> 16);
+    return lo | (hi << 16);
+#endif
+}
+HD uint4 LDG128(const void *p)                                     // read-only 16-byte load
+{
+#ifdef __CUDA_ARCH__
+    return __ldg(reinterpret_cast<const uint4 *>(p));
+#else
+    return *reinterpret_cast<const uint4 *>(p);
+#endif
+}
+HD uint32_t fsl16(uint32_t lo, uint32_t hi) { return (hi << 16) | (lo >> 16); }   // funnel shift left by 16 of hi:lo, upper word
+HD uint32_t fsr16(uint32_t lo, uint32_t hi) { return (lo >> 16) | (hi << 16); }   // funnel shift right by 16 of hi:lo, lower word
 
 // plane descriptor of a kernel-parameter FrameDesc by register selects: indexing the parameter struct with a runtime
 // plane number would make the compiler copy it to local memory (an L2 round trip per access for a cold warp)
-__device__ __forceinline__ PlaneDesc plane_of(const FrameDesc &f, int plane)
+HD PlaneDesc plane_of(const FrameDesc &f, int plane)
 {
     PlaneDesc d;
     d.base = plane == 0 ? f.p[0].base : plane == 1 ? f.p[1].base : f.p[2].base;
@@ -32,7 +95,7 @@ __device__ __forceinline__ PlaneDesc plane_of(const FrameDesc &f, int plane)
 }
 
 template <typename PIX>
-__device__ __forceinline__ PIX *px_ptr(const PlaneDesc &p, int x, int y)
+HD PIX *px_ptr(const PlaneDesc &p, int x, int y)
 {
     return reinterpret_cast<PIX *>(p.base + (size_t)y * p.pitch) + x;
 }

@@ -974,132 +974,30 @@ __global__ void __launch_bounds__(256) k_deblock(const uint16_t *__restrict__ gr
 }
 
 // --------------------------------------------------------------------------------------------
-// K5: SAO.  One CTA per CTB-plane tile; source = deblocked picture (never modified), destination
-// = DPB slot, so the reference's sao_frame copy / SAO_APPLIED bookkeeping (hevc_filter.c:267-319)
-// has no equivalent here.  CTBs without SAO are copied through.
+// K5: SAO.  Source = deblocked picture (never modified), destination = DPB slot, so the reference's
+// sao_frame copy / SAO_APPLIED bookkeeping (hevc_filter.c:267-319) has no equivalent here.  CTBs
+// without SAO are copied through.
+//
+// The stage is issue-bound, not bandwidth-bound, so the kernel is written around the instruction count:
+//  * samples stay packed two per 32-bit register (16-bit halves; 8-bit pictures are widened on load) and are
+//    classified with the 16x2 SIMD integer instructions of sm_100a (VIADD.16x2, VIADDMNMX.S16x2.RELU):
+//    sign(c - a) + 1 = relu(min(c + (1 - a), 2)) is ONE instruction for two samples;
+//  * the offset is fetched with a byte permute (PRMT) from a 5-entry table held in two registers (offsets biased by
+//    128: |offset| <= 124 for every legal stream up to 12 bits, hevc_cabac.c:684-692 / hevc.c:1178);
+//  * one thread owns 8 samples x SAO_R rows, so rows are loaded once and reused as neighbours, and the CTB record is
+//    decoded once per 8 x SAO_R samples; a warp never spans more than one CTB horizontally (no class divergence
+//    inside a row of lanes).
+// Picture-border rows / columns ("offset 0", hevcdsp_template.c:433-471) and the not-across-boundary restore of
+// sao_edge_filter_1 (:533-566) touch only the outermost rows / columns of a CTB: those rows take sao_row_exact(),
+// the scalar statement of the reference rules; everything else takes the packed path.
 // --------------------------------------------------------------------------------------------
-// 8 consecutive samples (x multiple of 8: 16-byte / 8-byte aligned; rows are padded to the pitch, so a vector that
-// starts inside the plane may be read whole)
-template <typename PIX> __device__ __forceinline__ void load8(const PlaneDesc &pd, int x, int y, int (&v)[8])
-{
-    const PIX *s = px_ptr<PIX>(pd, x, y);
-    if (sizeof(PIX) == 2) {
-        const uint4 q = *reinterpret_cast<const uint4 *>(s);
-        v[0] = q.x & 0xffff; v[1] = q.x >> 16; v[2] = q.y & 0xffff; v[3] = q.y >> 16; v[4] = q.z & 0xffff; v[5] = q.z >> 16; v[6] = q.w & 0xffff; v[7] = q.w >> 16;
-    } else {
-        const uint2 q = *reinterpret_cast<const uint2 *>(s);
-        v[0] = q.x & 0xff; v[1] = (q.x >> 8) & 0xff; v[2] = (q.x >> 16) & 0xff; v[3] = q.x >> 24; v[4] = q.y & 0xff; v[5] = (q.y >> 8) & 0xff; v[6] = (q.y >> 16) & 0xff; v[7] = q.y >> 24;
-    }
-}
-template <typename PIX> __device__ __forceinline__ void store8(const PlaneDesc &pd, int x, int y, const int (&v)[8], int nvalid)
-{
-    PIX *d = px_ptr<PIX>(pd, x, y);
-    if (sizeof(PIX) == 2) {
-        const uint2 lo = make_uint2((uint32_t)v[0] | ((uint32_t)v[1] << 16), (uint32_t)v[2] | ((uint32_t)v[3] << 16));
-        if (nvalid == 8) *reinterpret_cast<uint4 *>(d) = make_uint4(lo.x, lo.y, (uint32_t)v[4] | ((uint32_t)v[5] << 16), (uint32_t)v[6] | ((uint32_t)v[7] << 16));
-        else *reinterpret_cast<uint2 *>(d) = lo;            // plane widths are multiples of 4
-    } else {
-        const uint32_t lo = (uint32_t)v[0] | ((uint32_t)v[1] << 8) | ((uint32_t)v[2] << 16) | ((uint32_t)v[3] << 24);
-        if (nvalid == 8) *reinterpret_cast<uint2 *>(d) = make_uint2(lo, (uint32_t)v[4] | ((uint32_t)v[5] << 8) | ((uint32_t)v[6] << 16) | ((uint32_t)v[7] << 24));
-        else *reinterpret_cast<uint32_t *>(d) = lo;
-    }
-}
+#include "k_sao.cuh"
 
-// One thread = 8 consecutive samples of one row (always inside one CTB: CTBs are >= 8 samples wide in every plane).
-// The neighbours an edge class needs are the rows above / below as vectors plus one scalar on either side; all of it
-// comes through L1/L2, DRAM sees every sample once.
 template <typename PIX>
-__global__ void __launch_bounds__(256) k_sao(const B200SaoRec *__restrict__ grid, FrameDesc src, FrameDesc dst, int bd,
-                                             int log2_ctb, int ctb_w, int ctb_h, int cfi)
+__global__ void __launch_bounds__(256, 2) k_sao(const B200SaoRec *__restrict__ grid, FrameDesc src, FrameDesc dst, int bd,
+                                                int log2_ctb, int ctb_w, int ctb_h, int cfi, int4 tile_base, int3 tiles_x)
 {
-    const int plane = blockIdx.z;
-    const PlaneDesc sp = plane_of(src, plane), dp = plane_of(dst, plane);
-    const int gx = (blockIdx.x * 32 + threadIdx.x) * 8, gy = blockIdx.y * 8 + threadIdx.y;
-    if (gx >= sp.w || gy >= sp.h) return;
-    const int hs = plane && cfi != 3, vs = plane && cfi == 1;
-    const int lw = log2_ctb - hs, lh = log2_ctb - vs;
-    const int cx = gx >> lw, cy = gy >> lh;
-    const uint4 rq = __ldg(reinterpret_cast<const uint4 *>(grid + (plane * ctb_h + cy) * ctb_w + cx));
-    const int type = rq.x & 0xff, param = (rq.x >> 8) & 0xff, borders = (rq.x >> 16) & 0xff, edges = rq.x >> 24, variant = rq.y & 0xff;
-    int off[5];
-    off[0] = (int16_t)(rq.y >> 16); off[1] = (int16_t)(rq.z & 0xffff); off[2] = (int16_t)(rq.z >> 16); off[3] = (int16_t)(rq.w & 0xffff); off[4] = (int16_t)(rq.w >> 16);
-    const int nvalid = min(8, sp.w - gx);
-    int c[8], out[8];
-    load8<PIX>(sp, gx, gy, c);
-    if (nvalid < 8) c[4] = c[5] = c[6] = c[7] = c[3];       // beyond the plane: replicate, like the clamped addressing of the scalars
-#pragma unroll
-    for (int i = 0; i < 8; i++) out[i] = c[i];
-    const int maxv = (1 << bd) - 1;
-    if (type == B200_SAO_BAND) {
-#pragma unroll
-        for (int i = 0; i < 8; i++) {
-            const int k = ((c[i] >> (bd - 5)) - param) & 31;
-            if (k < 4) out[i] = clip3i(c[i] + (k == 0 ? off[1] : k == 1 ? off[2] : k == 2 ? off[3] : off[4]), 0, maxv);
-        }
-    } else if (type == B200_SAO_EDGE) {
-        const int cls = param;
-        const int x0 = cx << lw, y0 = cy << lh;
-        const int w = min(1 << lw, sp.w - x0), h = min(1 << lh, sp.h - y0);
-        const int xs = gx - x0, y = gy - y0;
-        const bool b_l = borders & 1, b_t = borders & 2, b_r = borders & 4, b_b = borders & 8;
-        // neighbours: a = sample at (+dx0, +dy0), b = the opposite one; positions outside the picture are clamped
-        // (they are only ever used by samples that take the `zero` path)
-        int A[8], Bq[8];
-        const int yu = max(gy - 1, 0), yd = min(gy + 1, sp.h - 1), xl = max(gx - 1, 0), xr = min(gx + 8, sp.w - 1);
-        if (cls == 0) {
-            const int l = *px_ptr<PIX>(sp, xl, gy), r = *px_ptr<PIX>(sp, xr, gy);
-#pragma unroll
-            for (int i = 0; i < 8; i++) { A[i] = i ? c[i - 1] : l; Bq[i] = i < 7 ? c[i + 1] : r; }
-        } else {
-            int U[8], D[8];
-            load8<PIX>(sp, gx, yu, U);
-            load8<PIX>(sp, gx, yd, D);
-            if (nvalid < 8) { U[4] = U[5] = U[6] = U[7] = U[3]; D[4] = D[5] = D[6] = D[7] = D[3]; }
-            if (cls == 1) {
-#pragma unroll
-                for (int i = 0; i < 8; i++) { A[i] = U[i]; Bq[i] = D[i]; }
-            } else if (cls == 2) {      // 135 degrees: a = up-left, b = down-right
-                const int ul = *px_ptr<PIX>(sp, xl, yu), dr = *px_ptr<PIX>(sp, xr, yd);
-#pragma unroll
-                for (int i = 0; i < 8; i++) { A[i] = i ? U[i - 1] : ul; Bq[i] = i < 7 ? D[i + 1] : dr; }
-            } else {                    // 45 degrees: a = up-right, b = down-left
-                const int ur = *px_ptr<PIX>(sp, xr, yu), dl = *px_ptr<PIX>(sp, xl, yd);
-#pragma unroll
-                for (int i = 0; i < 8; i++) { A[i] = i < 7 ? U[i + 1] : ur; Bq[i] = i ? D[i - 1] : dl; }
-            }
-        }
-        const bool zrow = cls != 0 && ((b_t && y == 0) || (b_b && y == h - 1));
-#pragma unroll
-        for (int i = 0; i < 8; i++) {
-            const int x = xs + i, v = c[i];
-            const bool zero = zrow || (cls != 1 && ((b_l && x == 0) || (b_r && x == w - 1)));
-            const int e = (v > A[i]) - (v < A[i]) + (v > Bq[i]) - (v < Bq[i]);      // -2..2
-            const int o = zero ? off[0] : e == -2 ? off[1] : e == -1 ? off[2] : e == 0 ? off[0] : e == 1 ? off[3] : off[4];   // edge_idx[] = {1,2,0,3,4}
-            out[i] = clip3i(v + o, 0, maxv);
-        }
-        if (variant) {   // not-across-boundary restore, hevcdsp_template.c:533-566 (2 = SAO_EO_135D, 3 = SAO_EO_45D)
-            const int init_x = (cls != 1 && b_l) ? 1 : 0, wid = (cls != 1 && b_r) ? w - 1 : w, hei = (cls != 0 && b_b) ? h - 1 : h;
-            const bool ve0 = edges & 1, ve1 = edges & 2, he0 = edges & 4, he1 = edges & 8;
-            const bool de0 = edges & 16, de1 = edges & 32, de2 = edges & 64, de3 = edges & 128;
-            const int sul = !de0 && cls == 2 && !b_l && !b_t, sur = !de1 && cls == 3 && !b_t && !b_r;
-            const int slr = !de2 && cls == 2 && !b_r && !b_b, sll = !de3 && cls == 3 && !b_l && !b_b;
-#pragma unroll
-            for (int i = 0; i < 8; i++) {
-                const int x = xs + i;
-                bool rs = false;
-                rs |= ve0 && cls != 1 && x == 0 && y >= sul && y < hei - sll;
-                rs |= ve1 && cls != 1 && x == wid - 1 && y >= sur && y < hei - slr;
-                rs |= he0 && cls != 0 && y == 0 && x >= init_x + sul && x < wid - sur;
-                rs |= he1 && cls != 0 && y == hei - 1 && x >= init_x + sll && x < wid - slr;
-                rs |= de0 && cls == 2 && x == 0 && y == 0;
-                rs |= de1 && cls == 3 && x == wid - 1 && y == 0;
-                rs |= de2 && cls == 2 && x == wid - 1 && y == hei - 1;
-                rs |= de3 && cls == 3 && x == 0 && y == hei - 1;
-                if (rs) out[i] = c[i];
-            }
-        }
-    }
-    store8<PIX>(dp, gx, gy, out, nvalid);
+    sao_thread<PIX>(grid, src, dst, bd, log2_ctb, ctb_w, ctb_h, cfi, tile_base, tiles_x, blockIdx.x * 8 + (threadIdx.x >> 5), threadIdx.x & 31);
 }
 
 template <typename PIX>
@@ -1181,9 +1079,20 @@ int launch_deblock(cudaStream_t st, const uint16_t *grid, const B200DbkLayout &L
 int launch_sao(cudaStream_t st, const B200SaoRec *grid, const FrameDesc &src, const FrameDesc &dst, int bd,
                int log2_ctb, int ctb_w, int ctb_h, int cfi)
 {
-    const dim3 g((src.p[0].w + 255) / 256, (src.p[0].h + 7) / 8, 3), b(32, 8);
-    if (bd > 8) k_sao<uint16_t><<<g, b, 0, st>>>(grid, src, dst, bd, log2_ctb, ctb_w, ctb_h, cfi);
-    else        k_sao<uint8_t><<<g, b, 0, st>>>(grid, src, dst, bd, log2_ctb, ctb_w, ctb_h, cfi);
+    // warp tiles: (CTB width, at most 64) x (32 / strips x SAO_R) samples, all planes in one linear index
+    int base[4] = { 0, 0, 0, 0 }, ntx[3];
+    for (int p = 0; p < 3; p++) {
+        const int hs = p && cfi != 3;
+        const int lS = (log2_ctb - hs - 3) < 3 ? (log2_ctb - hs - 3) : 3;
+        const int tw = 8 << lS, th = (32 >> lS) * SAO_R;
+        ntx[p] = (src.p[p].w + tw - 1) / tw;
+        base[p + 1] = base[p] + ntx[p] * ((src.p[p].h + th - 1) / th);
+    }
+    const int blocks = (base[3] + 7) / 8;
+    const int4 tb = make_int4(base[0], base[1], base[2], base[3]);
+    const int3 tx = make_int3(ntx[0], ntx[1], ntx[2]);
+    if (bd > 8) k_sao<uint16_t><<<blocks, 256, 0, st>>>(grid, src, dst, bd, log2_ctb, ctb_w, ctb_h, cfi, tb, tx);
+    else        k_sao<uint8_t><<<blocks, 256, 0, st>>>(grid, src, dst, bd, log2_ctb, ctb_w, ctb_h, cfi, tb, tx);
     return 1;
 }
 

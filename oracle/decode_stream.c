@@ -26,10 +26,11 @@ static void plane_md5(const uint8_t *p, int pitch, int w_bytes, int h, char *hex
 
 int main(int argc, char **argv)
 {
-    if (argc < 2) { fprintf(stderr, "usage: %s stream.hevc [threads[w] [quiet]]   (N: frame threads, hevc -p N -f 1; Nw: slice / WPP threads, -f 2)\n", argv[0]); return 2; }
+    if (argc < 2) { fprintf(stderr, "usage: %s stream.hevc [threads[w] [quiet|time]]   (N: frame threads, hevc -p N -f 1; Nw: slice / WPP threads, -f 2)\n", argv[0]); return 2; }
     const int threads = argc > 2 ? atoi(argv[2]) : 1;
     const int slice_threads = argc > 2 && strchr(argv[2], 'w') != NULL;
     const int quiet = argc > 3;
+    const int timing = argc > 3 && !strcmp(argv[3], "time");    /* fps run: no MD5 work inside the timed loop */
     OpenHevc_Handle h = libOpenHevcInit(threads > 0 ? threads : 1, slice_threads ? 2 /* slice */ : 1 /* frame */);
     if (!h) return 3;
     libOpenHevcSetCheckMD5(h, 0);
@@ -58,10 +59,12 @@ int main(int argc, char **argv)
                 const int cw = f.frameInfo.chromat_format == YUV444 ? f.frameInfo.nWidth : f.frameInfo.nWidth / 2;
                 const int ch = f.frameInfo.chromat_format == YUV420 ? f.frameInfo.nHeight / 2 : f.frameInfo.nHeight;
                 char a[33], b[33], c[33];
+                if (!timing) {
                 plane_md5((const uint8_t *)f.pvY, f.frameInfo.nYPitch, f.frameInfo.nWidth * B, f.frameInfo.nHeight, a);
                 plane_md5((const uint8_t *)f.pvU, f.frameInfo.nUPitch, cw * B, ch, b);
                 plane_md5((const uint8_t *)f.pvV, f.frameInfo.nVPitch, cw * B, ch, c);
                 if (!quiet) printf("frame %d %dx%d bd%d %s %s %s\n", nframes, f.frameInfo.nWidth, f.frameInfo.nHeight, f.frameInfo.nBitDepth, a, b, c);
+                }
                 nframes++;
             } else if (stop_dec) stop = 1;
         }

@@ -1,0 +1,41 @@
+// kernel_emul.cu — TEST INFRASTRUCTURE.  Runs the per-thread code of the CUDA kernels (the __host__ __device__ functions
+// of openhevc_b200/csrc/k_*.cuh, the very source the GPU executes) on the CPU, one "thread" after the other, on host
+// memory.  tests/test_kernel_emul_cpu.py compares the result with the oracle: arithmetic identities of the packed
+// 16x2 paths, tile / lane geometry and border rules are checked here, without a GPU.  Nothing in the product links this.
+#include "../../openhevc_b200/csrc/k_sao.cuh"
+#include <vector>
+
+static void describe(FrameDesc &f, uint8_t *const planes[3], const int pitch[3], int width, int height, int cfi)
+{
+    for (int p = 0; p < 3; p++) {
+        const int hs = p && cfi != 3, vs = p && cfi == 1;
+        f.p[p].base = planes[p]; f.p[p].pitch = pitch[p]; f.p[p].w = width >> hs; f.p[p].h = height >> vs;
+    }
+}
+
+// same geometry as launch_sao() in kernels.cu
+extern "C" int emul_sao(const B200SaoRec *grid, uint8_t *const src_planes[3], uint8_t *const dst_planes[3], const int pitch[3],
+                        int width, int height, int cfi, int bd, int log2_ctb)
+{
+    FrameDesc src, dst;
+    describe(src, src_planes, pitch, width, height, cfi);
+    describe(dst, dst_planes, pitch, width, height, cfi);
+    const int ctb_w = (width + (1 << log2_ctb) - 1) >> log2_ctb, ctb_h = (height + (1 << log2_ctb) - 1) >> log2_ctb;
+    int base[4] = { 0, 0, 0, 0 }, ntx[3];
+    for (int p = 0; p < 3; p++) {
+        const int hs = p && cfi != 3;
+        const int lS = (log2_ctb - hs - 3) < 3 ? (log2_ctb - hs - 3) : 3;
+        const int tw = 8 << lS, th = (32 >> lS) * SAO_R;
+        ntx[p] = (src.p[p].w + tw - 1) / tw;
+        base[p + 1] = base[p] + ntx[p] * ((src.p[p].h + th - 1) / th);
+    }
+    const int blocks = (base[3] + 7) / 8;
+    const int4 tb = make_int4(base[0], base[1], base[2], base[3]);
+    const int3 tx = make_int3(ntx[0], ntx[1], ntx[2]);
+    for (int warp = 0; warp < blocks * 8; warp++)
+        for (int lane = 0; lane < 32; lane++) {
+            if (bd > 8) sao_thread<uint16_t>(grid, src, dst, bd, log2_ctb, ctb_w, ctb_h, cfi, tb, tx, warp, lane);
+            else        sao_thread<uint8_t>(grid, src, dst, bd, log2_ctb, ctb_w, ctb_h, cfi, tb, tx, warp, lane);
+        }
+    return 0;
+}

@@ -1,0 +1,109 @@
+"""CPU suite: the per-thread code of the CUDA kernels (openhevc_b200/csrc/k_*.cuh, compiled for the host by
+tests/emul/kernel_emul.cu) against the oracle.  This is the same source the GPU runs, executed thread by thread, so the
+packed 16x2 arithmetic, the tile / lane geometry and the border rules are checked without a GPU.  TEST INFRASTRUCTURE:
+the product library never runs this code on the host."""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+import oracle_lib
+from openhevc_b200 import worklist as W
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+EMUL_SO = os.path.join(ROOT, "oracle", "_ref", "libkernel_emul.so")
+EMUL_SRC = os.path.join(ROOT, "tests", "emul", "kernel_emul.cu")
+
+
+@pytest.fixture(scope="module")
+def emul():
+    if not os.path.exists(EMUL_SO):
+        if not os.path.exists("/usr/local/cuda/bin/nvcc"):
+            pytest.skip("kernel emulation library not built and nvcc not available")
+        subprocess.run(["make", "-C", os.path.join(ROOT, "tests", "emul")], check=True, capture_output=True)
+    lib = C.CDLL(EMUL_SO)
+    lib.emul_sao.restype = C.c_int
+    return lib
+
+
+def noisy_planes(w, h, cfi, bd, rng, flat):
+    """small-amplitude noise on a ramp: plenty of equal neighbours (edge index 0) and of both signs"""
+    planes = []
+    for p in range(3):
+        pw, ph = W.plane_dims(w, h, cfi, p)
+        yy, xx = np.mgrid[0:ph, 0:pw]
+        base = ((xx * 3 + yy * 5) % (1 << bd)) if not flat else np.full((ph, pw), (1 << bd) - 3)
+        v = np.clip(base + rng.integers(-3, 4, (ph, pw)), 0, (1 << bd) - 1)
+        planes.append(v.astype(np.uint16))
+    return planes
+
+
+def random_sao_grid(w, h, bd, log2_ctb, rng, restore, big_offsets):
+    ctb = 1 << log2_ctb
+    cw, ch = (w + ctb - 1) // ctb, (h + ctb - 1) // ctb
+    n = 3 * cw * ch
+    g = np.zeros(n, W.sao_dt)
+    u = rng.random(n)
+    g["type"] = np.where(u < 0.15, W.SAO_NONE, np.where(u < 0.4, W.SAO_BAND, W.SAO_EDGE))
+    edge = g["type"] == W.SAO_EDGE
+    g["param"] = np.where(edge, rng.integers(0, 4, n), rng.integers(0, 32, n))
+    maxo = 31 << max(0, bd - 10)
+    off = rng.integers(-maxo, maxo + 1, (n, 5))
+    off[:, 0] = 0
+    if big_offsets:
+        big = rng.random(n) < 0.3
+        off[big] = rng.integers(-600, 601, (int(big.sum()), 5))
+        off[rng.random(n) < 0.1, 0] = 5          # a non-zero entry 0: never produced by the parser, legal in the wire format
+    g["offset_val"] = off
+    cx = np.tile(np.arange(cw), ch); cy = np.repeat(np.arange(ch), cw)
+    at_edge = (cx == 0) * 1 | (cy == 0) * 2 | (cx == cw - 1) * 4 | (cy == ch - 1) * 8     # hevc_filter.c:207-253: always set there
+    g["borders"] = np.tile(at_edge, 3) | rng.integers(0, 16, n) * (rng.random(n) < 0.2)    # ... and the kernels must obey any other
+    if restore:
+        g["variant"] = rng.random(n) < 0.6
+        g["edges"] = rng.integers(0, 256, n) * g["variant"]
+    return g
+
+
+CASES = [
+    # w, h, cfi, bd, log2_ctb, restore, big
+    (256, 128, 1, 8, 6, False, False),
+    (256, 128, 1, 10, 6, True, False),
+    (200, 104, 1, 10, 6, True, False),      # widths / heights that end inside a CTB and inside an 8-sample strip
+    (136, 72, 1, 8, 4, True, False),        # 16x16 CTBs: 8-sample chroma CTBs
+    (192, 128, 2, 10, 5, True, False),      # 4:2:2
+    (192, 128, 3, 8, 6, True, False),       # 4:4:4
+    (320, 192, 1, 12, 6, True, True),       # 12 bit, offsets beyond the packed table
+    (72, 40, 1, 10, 5, True, True),
+]
+
+
+@pytest.mark.parametrize("w,h,cfi,bd,log2_ctb,restore,big", CASES)
+def test_sao_thread_code_equals_oracle(emul, w, h, cfi, bd, log2_ctb, restore, big):
+    for seed in range(3):
+        rng = np.random.default_rng(1000 * seed + w + bd)
+        grid = random_sao_grid(w, h, bd, log2_ctb, rng, restore, big)
+        src = noisy_planes(w, h, cfi, bd, rng, flat=(seed == 2))
+        blob = W.build_blob(w, h, cfi, bd, log2_ctb, 0, sao=grid)
+        want = oracle_lib.execute(blob, [src])
+        dt = np.uint16 if bd > 8 else np.uint8
+        B = np.dtype(dt).itemsize
+        pitches, s_bufs, d_bufs = [], [], []
+        for p in range(3):
+            pw, ph = W.plane_dims(w, h, cfi, p)
+            pitch = (pw * B + 255) // 256 * 256
+            sb = np.full((ph, pitch // B), 0x5a5a if bd > 8 else 0x5a, dt)     # garbage in the row padding, as on the device
+            sb[:, :pw] = src[p]
+            db = np.zeros_like(sb)
+            pitches.append(pitch); s_bufs.append(sb); d_bufs.append(db)
+        sp = (C.c_void_p * 3)(*[b.ctypes.data for b in s_bufs])
+        dp = (C.c_void_p * 3)(*[b.ctypes.data for b in d_bufs])
+        rc = emul.emul_sao(grid.ctypes.data_as(C.c_void_p), sp, dp, (C.c_int * 3)(*pitches), w, h, cfi, bd, log2_ctb)
+        assert rc == 0
+        for p in range(3):
+            pw, ph = W.plane_dims(w, h, cfi, p)
+            got = d_bufs[p][:, :pw].astype(np.uint16)
+            bad = np.argwhere(got != want[p])
+            assert len(bad) == 0, (f"seed {seed} plane {p}: {len(bad)} samples differ, first at (y,x)={tuple(bad[0])} "
+                                   f"got {got[tuple(bad[0])]} want {want[p][tuple(bad[0])]}")

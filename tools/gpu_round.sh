@@ -1,0 +1,19 @@
+#!/bin/bash
+# One GPU visit: parity suite, bench (4K + 1080p), the real decoder side by side, launch list.  Run through gpurun:
+#   gpurun --timeout 1500 -- 'bash tools/gpu_round.sh [tag]'
+tag=${1:-r}
+mkdir -p gpurun_out
+nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm --format=csv,noheader > gpurun_out/${tag}_gpu.txt 2>&1
+( time timeout 900 python -m pytest tests -m gpu -x -q --durations=8 ) > gpurun_out/${tag}_pytest.log 2>&1
+tail -15 gpurun_out/${tag}_pytest.log
+timeout 600 python bench.py > gpurun_out/${tag}_bench.json 2> gpurun_out/${tag}_bench.err
+cat gpurun_out/${tag}_bench.json
+timeout 300 python bench.py --workload c2_1080p_main_ra --no-cpu-baseline > gpurun_out/${tag}_bench_1080p.json 2>> gpurun_out/${tag}_bench.err
+cat gpurun_out/${tag}_bench_1080p.json
+if [ -z "$SKIP_DECODE" ]; then
+  timeout 600 python tools/decode_bench.py --repeat 1 > gpurun_out/${tag}_decode.json 2> gpurun_out/${tag}_decode.err
+  cat gpurun_out/${tag}_decode.json
+fi
+if [ -n "$WITH_NCU" ]; then
+  timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 1500 --csv --log-file gpurun_out/${tag}_launches.csv python bench.py --steps 2 --warmup 3 --no-cpu-baseline > gpurun_out/${tag}_ncu_bench.log 2>&1
+fi
