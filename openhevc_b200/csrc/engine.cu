@@ -16,6 +16,10 @@
 #include <stdlib.h>
 #include <string.h>
 #include <stdarg.h>
+#include <ctype.h>
+#include <sched.h>
+#include <unistd.h>
+#include <sys/syscall.h>
 #include <mutex>
 #include "../../include/b200hevc.h"
 #include "common.cuh"
@@ -149,10 +153,65 @@ extern "C" void *b200_slot_devptr(const B200Ctx *ctx, int slot, int plane, uint6
     return ctx->slot_desc[slot].p[plane].base;
 }
 
+// Pinned staging memory on the NUMA node the GPU hangs off: on a two-socket host a buffer on the far node halves the
+// PCIe rate both ways (every transfer crosses the socket interconnect).  Pages are placed at allocation time (the driver
+// faults them in to pin them), so the calling thread is moved onto the GPU's node -- CPU affinity, plus a preferred-node
+// memory policy where the container allows the syscall -- for the duration of the cudaHostAlloc only.  Best effort:
+// any failure leaves the default placement.  B200_NUMA=0 disables it.
+static int gpu_numa_node(int device, cpu_set_t *cpus)
+{
+    char bus[32] = { 0 }, path[128], buf[4096];
+    if (cudaDeviceGetPCIBusId(bus, sizeof(bus), device) != cudaSuccess) { cudaGetLastError(); return -1; }
+    for (char *c = bus; *c; c++) *c = (char)tolower(*c);
+    snprintf(path, sizeof(path), "/sys/bus/pci/devices/%s/numa_node", bus);
+    FILE *f = fopen(path, "r");
+    int node = -1;
+    if (f) { if (fscanf(f, "%d", &node) != 1) node = -1; fclose(f); }
+    if (node < 0) return -1;
+    snprintf(path, sizeof(path), "/sys/devices/system/node/node%d/cpulist", node);
+    f = fopen(path, "r");
+    if (!f) return -1;
+    const bool ok = fgets(buf, sizeof(buf), f) != nullptr;
+    fclose(f);
+    if (!ok) return -1;
+    CPU_ZERO(cpus);
+    for (char *t = strtok(buf, ",\n"); t; t = strtok(nullptr, ",\n")) {       // "0-31,64-95"
+        int a, b;
+        const int n = sscanf(t, "%d-%d", &a, &b);
+        if (n == 1) b = a;
+        if (n >= 1) for (int c = a; c <= b && c < CPU_SETSIZE; c++) CPU_SET(c, cpus);
+    }
+    return node;
+}
+
+static cudaError_t host_alloc_near_gpu(void **p, size_t bytes)
+{
+    static const bool enabled = !getenv("B200_NUMA") || atoi(getenv("B200_NUMA"));
+    int dev = 0;
+    cpu_set_t local, saved;
+    int node = -1;
+    bool moved = false, policy = false;
+    if (enabled && cudaGetDevice(&dev) == cudaSuccess && (node = gpu_numa_node(dev, &local)) >= 0 && node < 64) {
+        if (sched_getaffinity(0, sizeof(saved), &saved) == 0) {
+            cpu_set_t want;
+            CPU_AND(&want, &local, &saved);                      // stay inside the cpuset the container was given
+            if (CPU_COUNT(&want) > 0 && sched_setaffinity(0, sizeof(want), &want) == 0) moved = true;
+        }
+        unsigned long mask = 1ul << node;
+        policy = syscall(SYS_set_mempolicy, 1 /* MPOL_PREFERRED */, &mask, 65ul) == 0;
+    }
+    const cudaError_t rc = cudaHostAlloc(p, bytes, cudaHostAllocDefault);
+    if (policy) syscall(SYS_set_mempolicy, 0 /* MPOL_DEFAULT */, nullptr, 0ul);
+    if (moved) sched_setaffinity(0, sizeof(saved), &saved);
+    static const bool verbose = getenv("B200_VERBOSE") != nullptr;
+    if (verbose) fprintf(stderr, "b200: pinned %zu bytes, GPU %d on NUMA node %d (affinity %s, mempolicy %s)\n", bytes, dev, node, moved ? "set" : "-", policy ? "set" : "-");
+    return rc;
+}
+
 extern "C" void *b200_host_alloc(uint64_t bytes)
 {
     void *p = nullptr;
-    if (cudaHostAlloc(&p, bytes, cudaHostAllocDefault) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+    if (host_alloc_near_gpu(&p, bytes) != cudaSuccess) { cudaGetLastError(); return nullptr; }
     return p;
 }
 extern "C" void b200_host_free(void *p) { if (p) cudaFreeHost(p); }
@@ -403,7 +462,7 @@ extern "C" int b200_frame_upload(B200Ctx *ctx, const void *blob, uint64_t nbytes
     bool pinned = cudaPointerGetAttributes(&at, blob) == cudaSuccess && at.type == cudaMemoryTypeHost;
     cudaGetLastError();
     if (!pinned) {   // stage through pinned memory so the copy stays asynchronous w.r.t. compute
-        if (!a.stage) CU(cudaHostAlloc(&a.stage, ctx->arena_bytes, cudaHostAllocDefault));
+        if (!a.stage) CU(host_alloc_near_gpu((void **)&a.stage, ctx->arena_bytes));
         if (a.resident) CU(cudaEventSynchronize(a.ev_uploaded));
         memcpy(a.stage, blob, nbytes);
         src = a.stage;

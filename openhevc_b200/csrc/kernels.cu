@@ -846,131 +846,25 @@ __global__ void __launch_bounds__(128) k_intra(const B200IntraRec *__restrict__ 
 }
 
 // --------------------------------------------------------------------------------------------
-// K4: deblocking, both directions in ONE pass.  Tiles are offset by (-4,-4) from the 8x8 edge
-// grid, so every sample an edge reads or writes (<= 4 each side) belongs to exactly one tile:
-// load tile -> all vertical edges -> all horizontal edges -> store, no halo, in place.
+// K4: deblocking, both directions in ONE pass (k_deblock.cuh: one thread per 4-line edge segment).
 // --------------------------------------------------------------------------------------------
-#define DBK_TW 64
-#define DBK_TH 32
-#define DBK_PITCH 66
-
-__device__ __forceinline__ void dbk_luma_line(int (&p)[8], int beta, int tc, bool no_p, bool no_q, int bd, int lane)
-{
-    // p[0..3] = P3..P0, p[4..7] = Q0..Q3.  Decisions use lines 0 and 3 of the 4-line segment (quad of lanes).
-    const int base = lane & ~3;
-    const int dp = abs(p[1] - 2 * p[2] + p[3]), dq = abs(p[6] - 2 * p[5] + p[4]);
-    const int sa = abs(p[0] - p[3]) + abs(p[7] - p[4]), sb = abs(p[3] - p[4]);
-    const int dp0 = __shfl_sync(0xffffffffu, dp, base), dp3 = __shfl_sync(0xffffffffu, dp, base + 3);
-    const int dq0 = __shfl_sync(0xffffffffu, dq, base), dq3 = __shfl_sync(0xffffffffu, dq, base + 3);
-    const int sa0 = __shfl_sync(0xffffffffu, sa, base), sa3 = __shfl_sync(0xffffffffu, sa, base + 3);
-    const int sb0 = __shfl_sync(0xffffffffu, sb, base), sb3 = __shfl_sync(0xffffffffu, sb, base + 3);
-    beta <<= bd - 8; tc <<= bd - 8;
-    const int d0 = dp0 + dq0, d3 = dp3 + dq3;
-    if (d0 + d3 >= beta) return;
-    const int tc25 = (tc * 5 + 1) >> 1, maxv = (1 << bd) - 1;
-    const bool strong = sa0 < (beta >> 3) && sb0 < tc25 && sa3 < (beta >> 3) && sb3 < tc25 && (d0 << 1) < (beta >> 2) && (d3 << 1) < (beta >> 2);
-    const int p3 = p[0], p2 = p[1], p1 = p[2], p0 = p[3], q0 = p[4], q1 = p[5], q2 = p[6], q3 = p[7];
-    if (strong) {
-        const int t2 = tc << 1;
-        if (!no_p) {
-            p[3] = p0 + clip3i(((p2 + 2 * p1 + 2 * p0 + 2 * q0 + q1 + 4) >> 3) - p0, -t2, t2);
-            p[2] = p1 + clip3i(((p2 + p1 + p0 + q0 + 2) >> 2) - p1, -t2, t2);
-            p[1] = p2 + clip3i(((2 * p3 + 3 * p2 + p1 + p0 + q0 + 4) >> 3) - p2, -t2, t2);
-        }
-        if (!no_q) {
-            p[4] = q0 + clip3i(((p1 + 2 * p0 + 2 * q0 + 2 * q1 + q2 + 4) >> 3) - q0, -t2, t2);
-            p[5] = q1 + clip3i(((p0 + q0 + q1 + q2 + 2) >> 2) - q1, -t2, t2);
-            p[6] = q2 + clip3i(((2 * q3 + 3 * q2 + q1 + q0 + p0 + 4) >> 3) - q2, -t2, t2);
-        }
-    } else {
-        int delta = (9 * (q0 - p0) - 3 * (q1 - p1) + 8) >> 4;
-        if (abs(delta) < 10 * tc) {
-            const int th = tc >> 1, side = (beta + (beta >> 1)) >> 3;
-            delta = clip3i(delta, -tc, tc);
-            if (!no_p) p[3] = clip3i(p0 + delta, 0, maxv);
-            if (!no_q) p[4] = clip3i(q0 - delta, 0, maxv);
-            if (!no_p && dp0 + dp3 < side) p[2] = clip3i(p1 + clip3i((((p2 + p0 + 1) >> 1) - p1 + delta) >> 1, -th, th), 0, maxv);
-            if (!no_q && dq0 + dq3 < side) p[5] = clip3i(q1 + clip3i((((q2 + q0 + 1) >> 1) - q1 - delta) >> 1, -th, th), 0, maxv);
-        }
-    }
-}
-
-__device__ __forceinline__ void dbk_chroma_line(int (&p)[8], int tc, bool no_p, bool no_q, int bd)
-{
-    tc <<= bd - 8;
-    if (tc <= 0) return;
-    const int maxv = (1 << bd) - 1;
-    const int p1 = p[2], p0 = p[3], q0 = p[4], q1 = p[5];
-    const int delta = clip3i((((q0 - p0) * 4) + p1 - q1 + 4) >> 3, -tc, tc);
-    if (!no_p) p[3] = clip3i(p0 + delta, 0, maxv);
-    if (!no_q) p[4] = clip3i(q0 - delta, 0, maxv);
-}
+#include "k_deblock.cuh"
 
 template <typename PIX>
-__global__ void __launch_bounds__(256) k_deblock(const uint16_t *__restrict__ grid, B200DbkLayout L, FrameDesc f, int bd)
+__global__ void __launch_bounds__(DBK_THREADS, 3) k_deblock(const uint16_t *__restrict__ grid, B200DbkLayout L, FrameDesc f, int bd)
 {
     const int plane = blockIdx.z;
     const PlaneDesc pd = plane_of(f, plane);
-    const int gx0 = DBK_TW * blockIdx.x - 4, gy0 = DBK_TH * blockIdx.y - 4;
-    if (gx0 >= pd.w || gy0 >= pd.h) return;
-    __shared__ uint16_t t[DBK_TH][DBK_PITCH];
-    const int tid = threadIdx.x, lane = tid & 31;
-    // ---- load (units of 4 samples; plane widths are multiples of 4) ----
-    for (int u = tid; u < DBK_TH * (DBK_TW / 4); u += 256) {
-        const int row = u / (DBK_TW / 4), ux = u % (DBK_TW / 4), gx = gx0 + 4 * ux, gy = gy0 + row;
-        uint16_t a = 0, b = 0, c = 0, d = 0;
-        if (gx >= 0 && gx < pd.w && gy >= 0 && gy < pd.h) {
-            const PIX *s = px_ptr<PIX>(pd, gx, gy);
-            if (sizeof(PIX) == 2) { const uint2 q = *reinterpret_cast<const uint2 *>(s); a = q.x & 0xffff; b = q.x >> 16; c = q.y & 0xffff; d = q.y >> 16; }
-            else { const uint32_t q = *reinterpret_cast<const uint32_t *>(s); a = q & 0xff; b = (q >> 8) & 0xff; c = (q >> 16) & 0xff; d = q >> 24; }
-        }
-        t[row][4 * ux] = a; t[row][4 * ux + 1] = b; t[row][4 * ux + 2] = c; t[row][4 * ux + 3] = d;
-    }
+    if (DBK_TW * (int)blockIdx.x - 4 >= pd.w || DBK_TH * (int)blockIdx.y - 4 >= pd.h) return;
+    __shared__ __align__(16) uint16_t t[DBK_TH * DBK_PITCH];
+    const int tid = threadIdx.x;
+    dbk_load<PIX>(t, pd, blockIdx.x, blockIdx.y, tid);
     __syncthreads();
-    // ---- vertical edges: thread = (edge column e, row) ----
-    {
-        const int e = tid >> 5, row = tid & 31, gxe = DBK_TW * blockIdx.x + 8 * e, gy = gy0 + row;
-        const bool valid = gxe > 0 && gxe < pd.w && gy >= 0 && gy < pd.h;
-        const uint16_t en = valid ? __ldg(grid + L.off[plane][0] + (gy >> 2) * L.stride[plane][0] + (gxe >> 3)) : 0;
-        int p[8];
-#pragma unroll
-        for (int i = 0; i < 8; i++) p[i] = t[row][8 * e + i];
-        const bool on = en & B200_DBK_PRESENT;
-        if (plane == 0) dbk_luma_line(p, on ? B200_DBK_BETA(en) : 0, on ? B200_DBK_TC(en) : 0, B200_DBK_NOP(en), B200_DBK_NOQ(en), bd, lane);
-        else if (on) dbk_chroma_line(p, B200_DBK_TC(en), B200_DBK_NOP(en), B200_DBK_NOQ(en), bd);
-        if (on) {
-#pragma unroll
-            for (int i = 1; i < 7; i++) t[row][8 * e + i] = (uint16_t)p[i];
-        }
-    }
+    dbk_vertical(t, grid, L, pd, plane, blockIdx.x, blockIdx.y, tid, bd);
     __syncthreads();
-    // ---- horizontal edges: thread = (edge row f, column) ----
-    {
-        const int fr = tid >> 6, col = tid & 63, gye = DBK_TH * blockIdx.y + 8 * fr, gx = gx0 + col;
-        const bool valid = gye > 0 && gye < pd.h && gx >= 0 && gx < pd.w;
-        const uint16_t en = valid ? __ldg(grid + L.off[plane][1] + (gye >> 3) * L.stride[plane][1] + (gx >> 2)) : 0;
-        int p[8];
-#pragma unroll
-        for (int i = 0; i < 8; i++) p[i] = t[8 * fr + i][col];
-        const bool on = en & B200_DBK_PRESENT;
-        if (plane == 0) dbk_luma_line(p, on ? B200_DBK_BETA(en) : 0, on ? B200_DBK_TC(en) : 0, B200_DBK_NOP(en), B200_DBK_NOQ(en), bd, lane);
-        else if (on) dbk_chroma_line(p, B200_DBK_TC(en), B200_DBK_NOP(en), B200_DBK_NOQ(en), bd);
-        if (on) {
-#pragma unroll
-            for (int i = 1; i < 7; i++) t[8 * fr + i][col] = (uint16_t)p[i];
-        }
-    }
+    dbk_horizontal(t, grid, L, pd, plane, blockIdx.x, blockIdx.y, tid, bd);
     __syncthreads();
-    // ---- store ----
-    for (int u = tid; u < DBK_TH * (DBK_TW / 4); u += 256) {
-        const int row = u / (DBK_TW / 4), ux = u % (DBK_TW / 4), gx = gx0 + 4 * ux, gy = gy0 + row;
-        if (gx >= 0 && gx < pd.w && gy >= 0 && gy < pd.h) {
-            PIX *s = px_ptr<PIX>(pd, gx, gy);
-            const uint32_t a = t[row][4 * ux], b = t[row][4 * ux + 1], c = t[row][4 * ux + 2], d = t[row][4 * ux + 3];
-            if (sizeof(PIX) == 2) *reinterpret_cast<uint2 *>(s) = make_uint2(a | (b << 16), c | (d << 16));
-            else *reinterpret_cast<uint32_t *>(s) = a | (b << 8) | (c << 16) | (d << 24);
-        }
-    }
+    dbk_store<PIX>(t, pd, blockIdx.x, blockIdx.y, tid);
 }
 
 // --------------------------------------------------------------------------------------------
@@ -1071,8 +965,8 @@ int launch_intra(cudaStream_t st, const B200IntraRec *recs, int count, const int
 int launch_deblock(cudaStream_t st, const uint16_t *grid, const B200DbkLayout &L, const FrameDesc &cur, int bd)
 {
     const dim3 g((cur.p[0].w + 4 + DBK_TW - 1) / DBK_TW, (cur.p[0].h + 4 + DBK_TH - 1) / DBK_TH, 3);
-    if (bd > 8) k_deblock<uint16_t><<<g, 256, 0, st>>>(grid, L, cur, bd);
-    else        k_deblock<uint8_t><<<g, 256, 0, st>>>(grid, L, cur, bd);
+    if (bd > 8) k_deblock<uint16_t><<<g, DBK_THREADS, 0, st>>>(grid, L, cur, bd);
+    else        k_deblock<uint8_t><<<g, DBK_THREADS, 0, st>>>(grid, L, cur, bd);
     return 1;
 }
 

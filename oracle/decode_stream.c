@@ -26,10 +26,13 @@ static void plane_md5(const uint8_t *p, int pitch, int w_bytes, int h, char *hex
 
 int main(int argc, char **argv)
 {
-    if (argc < 2) { fprintf(stderr, "usage: %s stream.hevc [threads[w] [quiet|time]]   (N: frame threads, hevc -p N -f 1; Nw: slice / WPP threads, -f 2)\n", argv[0]); return 2; }
+    if (argc < 2) { fprintf(stderr, "usage: %s stream.hevc [threads[w] [quiet|time [passes]]]   (N: frame threads, hevc -p N -f 1; Nw: slice / WPP threads, -f 2)\n", argv[0]); return 2; }
     const int threads = argc > 2 ? atoi(argv[2]) : 1;
     const int slice_threads = argc > 2 && strchr(argv[2], 'w') != NULL;
-    const int quiet = argc > 3;
+    const int quiet = argc > 3 && strcmp(argv[3], "md5");      /* "md5": print the per-picture lines even with a pass count */
+    const int loops = argc > 4 ? atoi(argv[4]) : 1;             /* decode the file this many times back to back (the stream
+                                                                   starts with parameter sets + IDR, so the concatenation is a valid
+                                                                   stream); the steady-state fps excludes the first pass (start-up) */
     const int timing = argc > 3 && !strcmp(argv[3], "time");    /* fps run: no MD5 work inside the timed loop */
     OpenHevc_Handle h = libOpenHevcInit(threads > 0 ? threads : 1, slice_threads ? 2 /* slice */ : 1 /* frame */);
     if (!h) return 3;
@@ -45,11 +48,20 @@ int main(int argc, char **argv)
     libOpenHevcSetActiveDecoders(h, 0);
     libOpenHevcSetViewLayers(h, 0);
     AVPacket pkt;
-    int stop = 0, stop_dec = 0, nframes = 0;
-    struct timespec t0, t1;
+    int stop = 0, stop_dec = 0, nframes = 0, pass = 0;
+    static struct timespec stamp[1 << 16];
+    struct timespec t0, t1, tf;
     clock_gettime(CLOCK_MONOTONIC, &t0);
     while (!stop) {
-        if (!stop_dec && av_read_frame(fmt, &pkt) < 0) stop_dec = 1;
+        if (!stop_dec && av_read_frame(fmt, &pkt) < 0) {
+            if (++pass < loops) {                                 /* next pass: reopen the file, keep the decoder running */
+                avformat_close_input(&fmt);
+                fmt = avformat_alloc_context();
+                if (avformat_open_input(&fmt, argv[1], NULL, NULL) != 0) return 4;
+                continue;
+            }
+            stop_dec = 1;
+        }
         if (stop_dec || pkt.stream_index == vs) {
             int got = libOpenHevcDecode(h, stop_dec ? NULL : pkt.data, stop_dec ? 0 : pkt.size, stop_dec ? 0 : pkt.pts);
             if (got > 0) {
@@ -65,6 +77,7 @@ int main(int argc, char **argv)
                 plane_md5((const uint8_t *)f.pvV, f.frameInfo.nVPitch, cw * B, ch, c);
                 if (!quiet) printf("frame %d %dx%d bd%d %s %s %s\n", nframes, f.frameInfo.nWidth, f.frameInfo.nHeight, f.frameInfo.nBitDepth, a, b, c);
                 }
+                if (nframes < (1 << 16)) clock_gettime(CLOCK_MONOTONIC, &stamp[nframes]);
                 nframes++;
             } else if (stop_dec) stop = 1;
         }
@@ -72,7 +85,12 @@ int main(int argc, char **argv)
     }
     clock_gettime(CLOCK_MONOTONIC, &t1);
     double sec = (t1.tv_sec - t0.tv_sec) + 1e-9 * (t1.tv_nsec - t0.tv_nsec);
-    printf("frames %d time %.3f fps %.2f\n", nframes, sec, nframes / (sec > 0 ? sec : 1));
+    /* steady state: everything after the last picture of the first pass came out (one pass when there is only one) */
+    const int n1 = loops > 1 ? nframes / loops : 1;
+    tf = stamp[n1 > 0 && n1 <= (1 << 16) ? n1 - 1 : 0];
+    double steady = (t1.tv_sec - tf.tv_sec) + 1e-9 * (t1.tv_nsec - tf.tv_nsec);
+    printf("frames %d time %.3f fps %.2f first_frame_s %.3f steady_fps %.2f\n", nframes, sec, nframes / (sec > 0 ? sec : 1),
+           nframes ? sec - steady : 0.0, nframes > n1 && steady > 0 ? (nframes - n1) / steady : 0.0);
     libOpenHevcClose(h);
     return 0;
 }

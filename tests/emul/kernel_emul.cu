@@ -3,6 +3,7 @@
 // memory.  tests/test_kernel_emul_cpu.py compares the result with the oracle: arithmetic identities of the packed
 // 16x2 paths, tile / lane geometry and border rules are checked here, without a GPU.  Nothing in the product links this.
 #include "../../openhevc_b200/csrc/k_sao.cuh"
+#include "../../openhevc_b200/csrc/k_deblock.cuh"
 #include <vector>
 
 static void describe(FrameDesc &f, uint8_t *const planes[3], const int pitch[3], int width, int height, int cfi)
@@ -37,5 +38,28 @@ extern "C" int emul_sao(const B200SaoRec *grid, uint8_t *const src_planes[3], ui
             if (bd > 8) sao_thread<uint16_t>(grid, src, dst, bd, log2_ctb, ctb_w, ctb_h, cfi, tb, tx, warp, lane);
             else        sao_thread<uint8_t>(grid, src, dst, bd, log2_ctb, ctb_w, ctb_h, cfi, tb, tx, warp, lane);
         }
+    return 0;
+}
+
+// same geometry as launch_deblock() / k_deblock in kernels.cu: phases separated by __syncthreads() there, by loops here
+extern "C" int emul_deblock(const uint16_t *grid, uint8_t *const planes[3], const int pitch[3], int width, int height, int cfi, int bd)
+{
+    FrameDesc f;
+    describe(f, planes, pitch, width, height, cfi);
+    B200DbkLayout L;
+    b200_dbk_layout(width, height, cfi, &L);
+    std::vector<uint16_t> tile(DBK_TH * DBK_PITCH + 8);
+    uint16_t *t = (uint16_t *)(((uintptr_t)tile.data() + 15) & ~(uintptr_t)15);
+    const int gx = (f.p[0].w + 4 + DBK_TW - 1) / DBK_TW, gy = (f.p[0].h + 4 + DBK_TH - 1) / DBK_TH;
+    for (int plane = 0; plane < 3; plane++)
+        for (int by = 0; by < gy; by++)
+            for (int bx = 0; bx < gx; bx++) {
+                const PlaneDesc pd = plane_of(f, plane);
+                if (DBK_TW * bx - 4 >= pd.w || DBK_TH * by - 4 >= pd.h) continue;
+                for (int tid = 0; tid < DBK_THREADS; tid++) { if (bd > 8) dbk_load<uint16_t>(t, pd, bx, by, tid); else dbk_load<uint8_t>(t, pd, bx, by, tid); }
+                for (int tid = 0; tid < DBK_THREADS; tid++) dbk_vertical(t, grid, L, pd, plane, bx, by, tid, bd);
+                for (int tid = 0; tid < DBK_THREADS; tid++) dbk_horizontal(t, grid, L, pd, plane, bx, by, tid, bd);
+                for (int tid = 0; tid < DBK_THREADS; tid++) { if (bd > 8) dbk_store<uint16_t>(t, pd, bx, by, tid); else dbk_store<uint8_t>(t, pd, bx, by, tid); }
+            }
     return 0;
 }

@@ -107,3 +107,55 @@ def test_sao_thread_code_equals_oracle(emul, w, h, cfi, bd, log2_ctb, restore, b
             bad = np.argwhere(got != want[p])
             assert len(bad) == 0, (f"seed {seed} plane {p}: {len(bad)} samples differ, first at (y,x)={tuple(bad[0])} "
                                    f"got {got[tuple(bad[0])]} want {want[p][tuple(bad[0])]}")
+
+
+def run_emul_planes(fn, planes, w, h, cfi, bd, *args):
+    """copies the planes into pitched native-type buffers (garbage in the padding), runs fn in place, returns uint16 planes"""
+    dt = np.uint16 if bd > 8 else np.uint8
+    B = np.dtype(dt).itemsize
+    pitches, bufs = [], []
+    for p in range(3):
+        pw, ph = W.plane_dims(w, h, cfi, p)
+        pitch = (pw * B + 255) // 256 * 256
+        b = np.full((ph, pitch // B), 0x5a5a if bd > 8 else 0x5a, dt)
+        b[:, :pw] = planes[p]
+        pitches.append(pitch); bufs.append(b)
+    ptrs = (C.c_void_p * 3)(*[b.ctypes.data for b in bufs])
+    assert fn(*args, ptrs, (C.c_int * 3)(*pitches), w, h, cfi, bd) == 0
+    return [bufs[p][:, :W.plane_dims(w, h, cfi, p)[0]].astype(np.uint16) for p in range(3)]
+
+
+def random_dbk_grid(w, h, cfi, rng, density):
+    L = W.DbkLayout(w, h, cfi)
+    g = np.zeros(L.total, np.uint16)
+    for p in range(3):
+        for d in range(2):
+            v = L.view(g, p, d)
+            n = v.shape
+            tc = rng.integers(0, 25, n); beta = rng.integers(0, 65, n)
+            nop = rng.random(n) < 0.1; noq = rng.random(n) < 0.1
+            e = W.DBK_PRESENT | tc | (beta << 6) | (nop.astype(np.int64) << 13) | (noq.astype(np.int64) << 14)
+            v[...] = np.where(rng.random(n) < density, e, 0).astype(np.uint16)
+    return g
+
+
+DBK_CASES = [(256, 128, 1, 8), (256, 128, 1, 10), (200, 104, 1, 10), (136, 72, 1, 8), (192, 128, 2, 10), (192, 136, 3, 8), (320, 192, 1, 12), (520, 264, 1, 10)]
+
+
+@pytest.mark.parametrize("w,h,cfi,bd", DBK_CASES)
+def test_deblock_thread_code_equals_oracle(emul, w, h, cfi, bd):
+    from openhevc_b200.synth import smooth_frame
+    for seed in range(3):
+        rng = np.random.default_rng(77 * seed + w + bd)
+        grid = random_dbk_grid(w, h, cfi, rng, density=(0.9, 0.5, 0.1)[seed])
+        # smooth pictures with small steps at the block edges: all three branches (none / normal / strong) are taken
+        src = [np.clip(p.astype(np.int64) + rng.integers(-2, 3, p.shape) + 6 * ((np.indices(p.shape)[0] // 8 + np.indices(p.shape)[1] // 8) % 2),
+                       0, (1 << bd) - 1).astype(np.uint16) for p in smooth_frame(w, h, cfi, bd, seed)]
+        blob = W.build_blob(w, h, cfi, bd, 6, 0, dbk=grid)
+        want = oracle_lib.execute(blob, [src])
+        assert any((want[p] != src[p]).any() for p in range(3)), "the test picture was not filtered at all"
+        got = run_emul_planes(emul.emul_deblock, src, w, h, cfi, bd, grid.ctypes.data_as(C.c_void_p))
+        for p in range(3):
+            bad = np.argwhere(got[p] != want[p])
+            assert len(bad) == 0, (f"seed {seed} plane {p}: {len(bad)} samples differ, first at (y,x)={tuple(bad[0])} "
+                                   f"got {got[p][tuple(bad[0])]} want {want[p][tuple(bad[0])]}")

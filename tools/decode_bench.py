@@ -22,16 +22,16 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 REF = os.path.join(ROOT, "oracle", "_ref")
 
 
-def run(binary, stream, threads, repeat):
+def run(binary, stream, threads, repeat, passes):
     best = None
     for _ in range(repeat):
-        r = subprocess.run([os.path.join(REF, binary), stream, str(threads), "time"], capture_output=True, text=True, timeout=1800)
-        m = re.search(r"frames (\d+) time ([\d.]+) fps ([\d.]+)", r.stdout)
+        r = subprocess.run([os.path.join(REF, binary), stream, str(threads), "time", str(passes)], capture_output=True, text=True, timeout=1800)
+        m = re.search(r"frames (\d+) time ([\d.]+) fps ([\d.]+) first_frame_s ([\d.]+) steady_fps ([\d.]+)", r.stdout)
         if r.returncode or not m:
             return {"error": (r.stderr or r.stdout)[-300:], "rc": r.returncode}
         frames, sec = int(m.group(1)), float(m.group(2))
         if best is None or sec < best["sec"]:
-            best = {"frames": frames, "sec": sec, "fps": frames / sec}
+            best = {"frames": frames, "sec": sec, "fps": frames / sec, "first_frame_s": float(m.group(4)), "steady_fps": float(m.group(5))}
     return best
 
 
@@ -40,18 +40,19 @@ def main():
     ap.add_argument("stream", nargs="?", default=os.path.join(REF, "streams", "c3_4k_33.hevc"))
     ap.add_argument("--threads", default="1,%d" % min(os.cpu_count() or 1, 16))
     ap.add_argument("--repeat", type=int, default=2)
+    ap.add_argument("--passes", type=int, default=3, help="decode the file this many times back to back; steady_fps excludes the first pass")
     ap.add_argument("--only", default="", help="ref | b200")
     a = ap.parse_args()
     if not os.path.exists(a.stream):
         a.stream = os.path.join(ROOT, "tests", "golden", "streams", "c3_3840x2160_10b_lowdelay.hevc")
-    out = {"stream": os.path.basename(a.stream), "bytes": os.path.getsize(a.stream), "host_cores": os.cpu_count(), "runs": []}
+    out = {"stream": os.path.basename(a.stream), "bytes": os.path.getsize(a.stream), "host_cores": os.cpu_count(), "passes": a.passes, "runs": []}
     for t in [int(x) for x in a.threads.split(",")]:
         for arm, binary in (("reference", "decode_ref"), ("b200", "decode_b200")):
             if a.only and not arm.startswith(a.only):
                 continue
             if not os.path.exists(os.path.join(REF, binary)):
                 continue
-            r = run(binary, a.stream, t, a.repeat)
+            r = run(binary, a.stream, t, a.repeat, a.passes)
             r.update(arm=arm, frame_threads=t)
             out["runs"].append(r)
     print(json.dumps(out))

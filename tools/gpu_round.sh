@@ -11,9 +11,13 @@ cat gpurun_out/${tag}_bench.json
 timeout 300 python bench.py --workload c2_1080p_main_ra --no-cpu-baseline > gpurun_out/${tag}_bench_1080p.json 2>> gpurun_out/${tag}_bench.err
 cat gpurun_out/${tag}_bench_1080p.json
 if [ -z "$SKIP_DECODE" ]; then
-  timeout 600 python tools/decode_bench.py --repeat 1 > gpurun_out/${tag}_decode.json 2> gpurun_out/${tag}_decode.err
+  timeout 900 python tools/decode_bench.py --repeat 1 --passes 3 > gpurun_out/${tag}_decode.json 2> gpurun_out/${tag}_decode.err
   cat gpurun_out/${tag}_decode.json
 fi
 if [ -n "$WITH_NCU" ]; then
   timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 1500 --csv --log-file gpurun_out/${tag}_launches.csv python bench.py --steps 2 --warmup 3 --no-cpu-baseline > gpurun_out/${tag}_ncu_bench.log 2>&1
 fi
+if [ -n "$WITH_NCU_FULL" ]; then   # one B picture (blob 4), second repetition: every kernel of the picture with the full set
+  timeout 600 ncu --set full --clock-control none --import-source on -c 26 -o gpurun_out/${tag}_bpic python tools/run_pictures.py --only 4 --reps 2 > gpurun_out/${tag}_ncu_full.log 2>&1
+fi
+if [ -n "$WITH_PCIE" ]; then B200_VERBOSE=1 python tools/pcie_probe.py > gpurun_out/${tag}_pcie.txt 2>&1; cat gpurun_out/${tag}_pcie.txt; cat /sys/fs/cgroup/cpu.max >> gpurun_out/${tag}_pcie.txt 2>&1; nproc >> gpurun_out/${tag}_pcie.txt; fi

@@ -37,4 +37,12 @@ def both():
     d2h(); h2d()
 
 
-print("D2H %.1f GB/s  H2D %.1f GB/s  both: %.1f GB/s each direction" % (t(d2h), t(h2d), t(both)))
+print("torch pin_memory():   D2H %.1f GB/s  H2D %.1f GB/s  both: %.1f GB/s each direction" % (t(d2h), t(h2d), t(both)))
+
+# the same with the library's own staging allocator (b200_host_alloc: placed on the GPU's NUMA node)
+import os, sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from openhevc_b200 import engine as E, _lib   # noqa: E402
+_b1, _b2 = E.PinnedBuffer(_lib.load(), n), E.PinnedBuffer(_lib.load(), n)
+h1, h2 = torch.from_numpy(_b1.array), torch.from_numpy(_b2.array)
+print("b200_host_alloc():    D2H %.1f GB/s  H2D %.1f GB/s  both: %.1f GB/s each direction" % (t(d2h), t(h2d), t(both)))
