@@ -31,6 +31,28 @@ WORKLOADS = {
 METRIC, UNIT = "decoded_frames_per_sec", "frames/s"
 
 
+def usable_cpus():
+    """host threads this process can really run at once: the affinity mask, capped by the cgroup CPU quota
+    (os.cpu_count() reports the machine, not the container)"""
+    try:
+        n = len(os.sched_getaffinity(0))
+    except Exception:
+        n = os.cpu_count() or 1
+    for path in ("/sys/fs/cgroup/cpu.max", "/sys/fs/cgroup/cpu/cpu.cfs_quota_us"):
+        try:
+            f = open(path).read().split()
+            if path.endswith("cpu.max"):
+                quota, period = f[0], float(f[1])
+            else:
+                quota, period = f[0], float(open("/sys/fs/cgroup/cpu/cpu.cfs_period_us").read())
+            if quota not in ("max", "-1"):
+                n = max(1, min(n, int(float(quota) / period + 0.5)))
+            break
+        except Exception:
+            continue
+    return n
+
+
 def make_blobs(wl, out_alloc=None):
     """the 9 distinct pictures of the periodic stream; symbolic reference table [0, 1], cur_slot 2"""
     from openhevc_b200.synth import FrameSynth
@@ -114,8 +136,7 @@ def run_reference(args, wl, rank):
     rng = np.random.default_rng(1)
     seq = [seq[i] for i in rng.permutation(len(seq))]
     dpb = [smooth_frame(wl["width"], wl["height"], wl["cfi"], wl["bit_depth"], 7 + k) for k in range(3)]
-    threads = os.cpu_count() or 1
-    threads = min(threads, 256)
+    threads = min(usable_cpus(), 256)
 
     def iters_for(gops):
         return max(1, -(-gops * 8 // threads))
@@ -292,7 +313,7 @@ def main():
                 seq = [np.array(blobs[b]) for b, n in sorted(mix.items()) for _ in range(n)]
                 seq = [seq[i] for i in rng.permutation(len(seq))]
                 cdpb = [smooth_frame(wl["width"], wl["height"], wl["cfi"], wl["bit_depth"], 7 + k) for k in range(3)]
-                threads = min(os.cpu_count() or 1, 256)
+                threads = min(usable_cpus(), 256)
                 it = 2 if wl["width"] >= 3840 else 8
                 sec = oracle_lib.ref_bench(seq, cdpb, threads, it)
                 cpu = {"value": threads * it / sec, "unit": UNIT, "cores": threads, "kind": "reference",

@@ -116,6 +116,10 @@ int  b200_rec_mc(B200Rec *r, const B200McRec *whole_block /* w,h up to 64 */);
 int  b200_rec_deblock(B200Rec *r, int plane, int vertical, int x, int y, int beta, const int tc[2],
                       const uint8_t no_p[2], const uint8_t no_q[2]);
 int  b200_rec_sao(B200Rec *r, int plane, int x, int y, const B200SaoRec *params);
+/* pps->constrained_intra_pred_flag pictures: which min-PUs are intra coded (one byte per PU, row-major, non-zero = intra:
+ * MvField.pred_flag == PF_INTRA of s->ref->tab_mvf, hevc.h:1032-1041), once all CTBs are parsed.  B200IntraRec.flags of
+ * such a picture are the availability BEFORE the constrained-intra rule (hevcpred_template.c:116-163) */
+int  b200_rec_set_cip(B200Rec *r, int log2_min_pu_size, int min_pu_width, int min_pu_height, const uint8_t *is_intra);
 /* host helper shared by the recorder and by external blob builders: permutation (perm[new] = old) that sorts decode-order
  * intra records by dependency level (stable); returns the number of levels (>= 0) or a negative error */
 int  b200_intra_level_order(const B200IntraRec *recs, uint32_t n, int width, int height, int chroma_format_idc, uint32_t *perm);

@@ -62,14 +62,28 @@ typedef struct B200BlobHeader {
     uint32_t mc_big_count;       /* B200_SEC_MC is ordered: records [0, mc_big_count) are tiles of any legal shape (one warp
                                     each), the rest are tiles of <= 8x8 samples (four per warp), grouped by
                                     B200_MC_SMALL_KEY so that the tiles sharing a warp take the same branches            */
-    uint32_t reserved[64 - 13 - 2 * B200_SEC_COUNT];
+    B200Section cip;             /* constrained_intra_pred pictures only (else count = 0): uint32 words, B200CipHeader followed by
+                                    one bit per min-PU, row-major, bit set = the PU is intra coded (MvField.pred_flag == PF_INTRA,
+                                    hevc.h:1032-1041, read by hevcpred_template.c:39-40).  Carved out of the reserved words of blob v3:
+                                    older blobs read as "no CIP"                                                                      */
+    uint32_t reserved[64 - 15 - 2 * B200_SEC_COUNT];
 } B200BlobHeader;               /* 256 bytes */
+
+typedef struct B200CipHeader {   /* first 4 words of the CIP section */
+    uint32_t log2_min_pu_size;   /* sps->log2_min_pu_size */
+    uint32_t min_pu_width;       /* sps->min_pu_width  (bitmap row length in bits) */
+    uint32_t min_pu_height;
+    uint32_t reserved;
+} B200CipHeader;
+#define B200_CIP_WORDS(pw, ph) (4u + (((uint32_t)(pw) * (uint32_t)(ph) + 31u) >> 5))
 
 #define B200_MC_IS_SMALL(w, h) ((w) <= 8 && (h) <= 8)
 #define B200_MC_SMALL_KEY(flags) ((((flags) & B200_MCF_CHROMA) ? 2 : 0) | (((flags) & B200_MCF_BI) ? 1 : 0))   /* 0..3 */
 
 #define B200_FRAME_HAS_DEBLOCK 1u
 #define B200_FRAME_HAS_SAO     2u
+#define B200_FRAME_CIP         4u   /* pps->constrained_intra_pred_flag: B200IntraRec.flags hold the availability BEFORE the
+                                       CIP rules; the device applies hevcpred_template.c:116-163 and :185-249 with the bitmap */
 
 /* ---- residual stage (K2) ------------------------------------------------------------- */
 enum {

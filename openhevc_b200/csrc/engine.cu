@@ -34,6 +34,7 @@
 struct Arena {
     uint8_t *dev = nullptr;
     uint8_t *stage = nullptr;       // pinned staging for blobs that are not in pinned memory
+    B200CipHeader cip_hdr = {};     // host copy of the resident blob's CIP section header (constrained_intra_pred pictures)
     B200BlobHeader hdr;             // host copy of the resident blob's header
     bool resident = false;
     cudaEvent_t ev_uploaded = nullptr;
@@ -46,7 +47,7 @@ struct Lane {
     uint8_t *work = nullptr;            // pre-SAO picture (reconstruct + deblock happen here when the picture has SAO)
     FrameDesc work_desc;
     uint2 *flags[3] = { nullptr, nullptr, nullptr };   // intra edge records, 16 B per 4x4 unit
-    uint32_t *counter = nullptr;        // [0] K3 ticket, [1] sticky abort latch
+    uint32_t *counter = nullptr;        // [0] K3 ticket, [1] validation gate of the picture in progress, [2] K3 time-out latch, [3] validation latch
     int16_t *parked = nullptr;          // residuals of intra TUs (K2 -> K3), indexed like the coefficient pool
     cudaEvent_t tail = nullptr;         // end of the last picture of this lane
     bool used = false;
@@ -356,13 +357,28 @@ static int check_blob(B200Ctx *ctx, const B200BlobHeader *h, uint64_t nbytes)
         const uint64_t end = (uint64_t)h->sec[s].off + (uint64_t)h->sec[s].count * esz[s];
         if (h->sec[s].count && ((h->sec[s].off & 15) || end > nbytes)) return fail(ctx, B200_EINVAL, "section %d out of bounds", s);
     }
+    if (h->cip.count || (h->flags & B200_FRAME_CIP)) {          // constrained_intra_pred: bitmap of the min-PUs
+        const uint64_t end = (uint64_t)h->cip.off + 4ull * h->cip.count;
+        if (!(h->flags & B200_FRAME_CIP) || h->cip.count < 4 || (h->cip.off & 15) || end > nbytes) return fail(ctx, B200_EINVAL, "CIP section out of bounds");
+        const B200CipHeader *ch = (const B200CipHeader *)((const uint8_t *)h + h->cip.off);
+        if (ch->log2_min_pu_size < 2 || ch->log2_min_pu_size > 5 || ch->min_pu_width != ((uint32_t)c.width >> ch->log2_min_pu_size) ||
+            ch->min_pu_height != ((uint32_t)c.height >> ch->log2_min_pu_size) || h->cip.count < B200_CIP_WORDS(ch->min_pu_width, ch->min_pu_height))
+            return fail(ctx, B200_EINVAL, "CIP section does not match the picture geometry");
+    }
     if (h->mc_big_count > h->sec[B200_SEC_MC].count) return fail(ctx, B200_EINVAL, "mc_big_count %u > %u MC records", h->mc_big_count, h->sec[B200_SEC_MC].count);
     if (h->sec[B200_SEC_DBK].count && h->sec[B200_SEC_DBK].count != ctx->dbk.total) return fail(ctx, B200_EINVAL, "deblock grid size %u != %u", h->sec[B200_SEC_DBK].count, ctx->dbk.total);
     if (h->sec[B200_SEC_SAO].count && h->sec[B200_SEC_SAO].count != (uint32_t)(3 * ctx->ctb_w * ctx->ctb_h)) return fail(ctx, B200_EINVAL, "SAO grid size mismatch");
     return 0;
 }
 
-// deep validation (every record in range), ~1 ms of host time for a 4K picture; B200_VALIDATE=0 turns it off
+static int validate_mode()
+{
+    static const int mode = getenv("B200_VALIDATE") ? atoi(getenv("B200_VALIDATE")) : 1;   // 0 off, 1 device (default), 2 host
+    return mode;
+}
+
+// host-side validation (every record in range), ~1 ms of host time for a 4K picture: B200_VALIDATE=2.  The default is the
+// same set of checks on the device (k_validate in kernels.cu) -- keep the two in step.
 static int deep_check(B200Ctx *ctx, const uint8_t *blob)
 {
     const B200BlobHeader *h = (const B200BlobHeader *)blob;
@@ -453,8 +469,10 @@ extern "C" int b200_frame_upload(B200Ctx *ctx, const void *blob, uint64_t nbytes
     const B200BlobHeader *h = (const B200BlobHeader *)blob;
     int rc = check_blob(ctx, h, nbytes);
     if (rc) { ctx->err_code = 0; return rc; }
-    static const bool deep = !getenv("B200_VALIDATE") || atoi(getenv("B200_VALIDATE"));   // on unless B200_VALIDATE=0
-    if (deep && (rc = deep_check(ctx, (const uint8_t *)blob))) { ctx->err_code = 0; return rc; }
+    // every record is validated before it is used: by default on the device, in front of the picture's kernels
+    // (k_validate, a few microseconds; errors surface from b200_sync like the other device-side errors);
+    // B200_VALIDATE=2 checks on the host instead (synchronous error from this call, ~1 ms per 4K picture), 0 = off
+    if (validate_mode() == 2 && (rc = deep_check(ctx, (const uint8_t *)blob))) { ctx->err_code = 0; return rc; }
     CU(cudaSetDevice(ctx->cfg.device));
     Arena &a = ctx->arena[arena];
     const void *src = blob;
@@ -473,6 +491,7 @@ extern "C" int b200_frame_upload(B200Ctx *ctx, const void *blob, uint64_t nbytes
     CU(cudaMemcpyAsync(a.dev, src, nbytes, cudaMemcpyHostToDevice, ctx->st_copy));
     CU(cudaEventRecord(a.ev_uploaded, ctx->st_copy));
     a.hdr = *h;
+    if (h->cip.count) a.cip_hdr = *(const B200CipHeader *)((const uint8_t *)blob + h->cip.off);
     a.resident = true;
     return 0;
 }
@@ -546,19 +565,22 @@ extern "C" int b200_frame_execute_ex(B200Ctx *ctx, int arena, int cur_slot, cons
     }
     { int rc = slot_acquire(ctx, h.cur_slot, st, li, true); if (rc) return rc; }
     CU(cudaStreamWaitEvent(st, a.ev_uploaded, 0));
+    CU(cudaMemsetAsync(L.counter, 0, 2 * sizeof(uint32_t), st));          // K3 ticket + this picture's validation gate
+    if (validate_mode() == 1) ctx->launches += launch_validate(st, a.dev, h, ctx->pw, ctx->ph, ctx->arena_bytes, L.counter);
     if (pf) CU(cudaEventRecord(ctx->prof[0], st));
     // K1 inter
-    ctx->launches += launch_mc(st, (const B200McRec *)(a.dev + h.sec[B200_SEC_MC].off), (int)h.sec[B200_SEC_MC].count, (int)h.mc_big_count, cur, ctx->dpb_desc_dev, rt, bd);
+    ctx->launches += launch_mc(st, (const B200McRec *)(a.dev + h.sec[B200_SEC_MC].off), (int)h.sec[B200_SEC_MC].count, (int)h.mc_big_count, cur, ctx->dpb_desc_dev, rt, bd, L.counter);
     if (pf) CU(cudaEventRecord(ctx->prof[1], st));
     // K2 residual
     const int16_t *pool = (const int16_t *)(a.dev + h.sec[B200_SEC_COEFF].off);
     const B200TuRec *tu[4]; int ntu[4];
     for (int s = 0; s < 4; s++) { tu[s] = (const B200TuRec *)(a.dev + h.sec[B200_SEC_TU4 + s].off); ntu[s] = (int)h.sec[B200_SEC_TU4 + s].count; }
-    ctx->launches += launch_residual(st, tu, ntu, pool, L.parked, cur, bd);
+    ctx->launches += launch_residual(st, tu, ntu, pool, L.parked, cur, bd, L.counter);
     if (pf) CU(cudaEventRecord(ctx->prof[2], st));
     // K3 intra
     ctx->launches += launch_intra(st, (const B200IntraRec *)(a.dev + h.sec[B200_SEC_INTRA].off), (int)h.sec[B200_SEC_INTRA].count, L.parked, cur, bd,
-                                  L.flags, ctx->flag_stride, L.counter);
+                                  L.flags, ctx->flag_stride, L.counter,
+                                  (h.flags & B200_FRAME_CIP) && h.cip.count ? (const uint32_t *)(a.dev + h.cip.off) : nullptr, &a.cip_hdr, ctx->cfg.chroma_format_idc);
     if (pf) CU(cudaEventRecord(ctx->prof[3], st));
     // K4 deblock
     if (h.sec[B200_SEC_DBK].count)
@@ -658,9 +680,15 @@ extern "C" int b200_sync(B200Ctx *ctx)
     CU(cudaStreamSynchronize(ctx->st_down));
     for (int l = 0; l < ctx->n_lanes; l++) {
         if (!ctx->lane[l].used) continue;
-        uint32_t st[2] = { 0, 0 };
+        uint32_t st[4] = { 0, 0, 0, 0 };
         CU(cudaMemcpy(st, ctx->lane[l].counter, sizeof(st), cudaMemcpyDeviceToHost));
-        if (st[1]) return fail(ctx, B200_EINVAL, "intra work list is not in decode order (dependency wait timed out)");
+        if (st[2]) return fail(ctx, B200_EINVAL, "intra work list is not in decode order (dependency wait timed out)");
+        if (st[3]) {                                     // k_validate closed the gate of a picture on this lane: it was not executed
+            CU(cudaMemset(ctx->lane[l].counter + 3, 0, sizeof(uint32_t)));
+            int rc = fail(ctx, B200_EINVAL, "work list rejected on the device: invalid record in section mask 0x%x (picture not executed)", st[3]);
+            ctx->err_code = 0;                           // the context stays usable, like after a rejected upload
+            return rc;
+        }
     }
     return ctx->err_code;
 }

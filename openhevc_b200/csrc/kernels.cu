@@ -39,6 +39,88 @@ __host__ __device__ constexpr int hevc_T(int k, int n)
 }
 
 // --------------------------------------------------------------------------------------------
+// K0: work-list validation.  A record is an index into device memory (picture, coefficient pool, reference table):
+// none of them is trusted.  Checking ~300 k records costs the submitting host thread about a millisecond per 4K
+// picture -- more than everything else it does -- and a few microseconds here, one record per thread.  A bad record
+// closes the picture's GATE (gate[1]): every kernel that consumes records returns at once, so a malformed list is
+// rejected, not executed; gate[3] latches the failing sections until b200_sync() reports them.
+// gate layout (uint32, one per compute lane): [0] K3 ticket, [1] gate of the picture in progress, [2] K3 time-out latch,
+// [3] validation latch.
+// --------------------------------------------------------------------------------------------
+struct ValidateArgs {
+    const uint8_t *blob;                 // device copy of the blob
+    B200Section sec[B200_SEC_COUNT];
+    int pw[3], ph[3];
+    uint32_t ncoef, mc_big, n_ref;
+    unsigned long long arena_bytes;
+};
+
+__global__ void __launch_bounds__(256) k_validate(ValidateArgs a, uint32_t *gate)
+{
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    uint32_t bad = 0;
+#pragma unroll
+    for (int s = B200_SEC_TU4; s <= B200_SEC_TU32; s++) {
+        if (i >= a.sec[s].count) continue;
+        const int4 raw = __ldg(reinterpret_cast<const int4 *>(a.blob + a.sec[s].off) + i);
+        B200TuRec t;
+        memcpy(&t, &raw, 16);
+        const int n = 4 << (s - B200_SEC_TU4);
+        const int pl = t.plane > 2 ? 0 : t.plane;
+        const int pw = pl == 0 ? a.pw[0] : pl == 1 ? a.pw[1] : a.pw[2], ph = pl == 0 ? a.ph[0] : pl == 1 ? a.ph[1] : a.ph[2];
+        const unsigned long long need = (unsigned long long)t.coeff_off + ((t.flags & B200_TUF_PARK) ? 2 : 0) + (t.nnz == B200_TU_DENSE ? n * n : 2ull * t.nnz);
+        if (t.plane > 2 || (1 << t.log2) != n || t.x + n > pw || t.y + n > ph || need > a.ncoef ||
+            (t.nnz != B200_TU_DENSE && (int)t.nnz > n * n) || (t.kind == B200_TU_PCM && t.nnz != B200_TU_DENSE) ||
+            t.kind > B200_TU_PCM || (t.kind == B200_TU_DST && n != 4))
+            bad |= 1u << s;
+    }
+    if (i < a.sec[B200_SEC_INTRA].count) {
+        const int4 raw = __ldg(reinterpret_cast<const int4 *>(a.blob + a.sec[B200_SEC_INTRA].off) + i);
+        B200IntraRec r;
+        memcpy(&r, &raw, 16);
+        const int n = 1 << (r.log2 & 7);
+        const int pl = r.plane > 2 ? 0 : r.plane;
+        const int pw = pl == 0 ? a.pw[0] : pl == 1 ? a.pw[1] : a.pw[2], ph = pl == 0 ? a.ph[0] : pl == 1 ? a.ph[1] : a.ph[2];
+        if (r.plane > 2 || r.log2 < 2 || r.log2 > 5 || r.mode > 34 || (r.x & 3) || (r.y & 3) || r.x + n > pw || r.y + n > ph ||
+            (r.resid_off != B200_NO_RESID && ((unsigned long long)r.resid_off + n * n) * 2 > a.arena_bytes) ||
+            ((r.flags & B200_INF_UP_RIGHT) && (r.top_right_size < 1 || r.top_right_size > n || r.x + n + r.top_right_size > pw)) ||
+            ((r.flags & B200_INF_BOTTOM_LEFT) && (r.bottom_left_size < 1 || r.bottom_left_size > n || r.y + n + r.bottom_left_size > ph)) ||
+            ((r.flags & (B200_INF_UP | B200_INF_UP_RIGHT | B200_INF_UP_LEFT)) && r.y == 0) ||
+            ((r.flags & (B200_INF_LEFT | B200_INF_BOTTOM_LEFT | B200_INF_UP_LEFT)) && r.x == 0))
+            bad |= 1u << B200_SEC_INTRA;
+    }
+    if (i < a.sec[B200_SEC_MC].count) {
+        const int4 *p = reinterpret_cast<const int4 *>(a.blob + a.sec[B200_SEC_MC].off) + 2 * (size_t)i;
+        const int4 ra = __ldg(p), rb = __ldg(p + 1);
+        B200McRec m;
+        memcpy(&m, &ra, 16);
+        memcpy(reinterpret_cast<uint8_t *>(&m) + 16, &rb, 16);
+        const int maxf = (m.flags & B200_MCF_CHROMA) ? 7 : 3;
+        const int pl = m.plane > 2 ? 0 : m.plane;
+        const int pw = pl == 0 ? a.pw[0] : pl == 1 ? a.pw[1] : a.pw[2], ph = pl == 0 ? a.ph[0] : pl == 1 ? a.ph[1] : a.ph[2];
+        if (m.plane > 2 || !m.w || !m.h || m.w > 32 || m.w * m.h > 256 || m.x + m.w > pw || m.y + m.h > ph ||
+            m.ref0 >= a.n_ref || ((m.flags & B200_MCF_BI) && m.ref1 >= a.n_ref) ||
+            (m.frac0 & 15) > maxf || (m.frac0 >> 4) > maxf || (m.frac1 & 15) > maxf || (m.frac1 >> 4) > maxf || m.denom > 7 ||
+            ((m.w > 16) ? m.h > 8 : m.h > 16) || (i >= a.mc_big && !B200_MC_IS_SMALL(m.w, m.h)))
+            bad |= 1u << B200_SEC_MC;
+    }
+    if (bad) { gate[1] = 1u; atomicOr(gate + 3, bad); }
+}
+
+int launch_validate(cudaStream_t st, const uint8_t *blob_dev, const B200BlobHeader &h, const int pw[3], const int ph[3], unsigned long long arena_bytes, uint32_t *gate)
+{
+    ValidateArgs a;
+    a.blob = blob_dev;
+    uint32_t most = 0;
+    for (int s = 0; s < B200_SEC_COUNT; s++) { a.sec[s] = h.sec[s]; if (s >= B200_SEC_TU4 && s <= B200_SEC_MC && h.sec[s].count > most) most = h.sec[s].count; }
+    for (int p = 0; p < 3; p++) { a.pw[p] = pw[p]; a.ph[p] = ph[p]; }
+    a.ncoef = h.sec[B200_SEC_COEFF].count; a.mc_big = h.mc_big_count; a.n_ref = h.n_ref; a.arena_bytes = arena_bytes;
+    if (!most) return 0;
+    k_validate<<<(most + 255) / 256, 256, 0, st>>>(a, gate);
+    return 1;
+}
+
+// --------------------------------------------------------------------------------------------
 // K2: residual.  N lanes per TU (one column, then one row each); 32/N TUs per warp.
 // 1-D inverse DCT as register butterflies (even/odd decomposition), transposition through
 // a padded shared tile.  The int16 clip between the two stages is kept (Appendix A.2).
@@ -93,8 +175,9 @@ template <int N> __device__ __forceinline__ void dst4_1d(const int (&v)[N], int 
 
 template <typename PIX, int N>
 __global__ void __launch_bounds__(128) k_residual(const B200TuRec *__restrict__ recs, int count, const int16_t *__restrict__ pool,
-                                                  int16_t *__restrict__ parked, FrameDesc f, int bd)
+                                                  int16_t *__restrict__ parked, FrameDesc f, int bd, const uint32_t *__restrict__ gate)
 {
+    if (__ldg(gate + 1)) return;         // the picture's work list failed validation (k_validate)
     constexpr int G = 32 / N;            // TUs per warp
     constexpr int TS = N * (N + 1);      // padded tile
     __shared__ int tile_s[4][G * TS];
@@ -351,8 +434,10 @@ template <> struct McSmem<32> { static constexpr int WIN = MC_WIN_MAX, TMP = MC_
 template <> struct McSmem<8>  { static constexpr int WIN = 256 /* 15 x 16 */, TMP = 128 /* 15 x 8 */; };
 
 template <typename PIX, int GS>
-__global__ void __launch_bounds__(256) k_mc(const B200McRec *__restrict__ recs, int count, FrameDesc cur, const FrameDesc *__restrict__ dpb, RefTable rt, int bd)
+__global__ void __launch_bounds__(256) k_mc(const B200McRec *__restrict__ recs, int count, FrameDesc cur, const FrameDesc *__restrict__ dpb, RefTable rt, int bd,
+                                            const uint32_t *__restrict__ gate)
 {
+    if (__ldg(gate + 1)) return;         // the picture's work list failed validation (k_validate)
     constexpr int NG = 256 / GS;                           // groups per CTA
     __shared__ __align__(16) uint16_t win_s[NG][McSmem<GS>::WIN];
     __shared__ __align__(16) int16_t tmp_s[NG][McSmem<GS>::TMP];
@@ -477,6 +562,8 @@ __device__ __forceinline__ B200IntraRec decode_intra(const int4 raw)
     return r;
 }
 
+#include "k_intra_cip.cuh"
+
 struct IntraEdges {
     uint2 *e[3];        // per plane: [2 * unit] = bottom row of the 4x4 unit, [2 * unit + 1] = its right column
     int stride[3];      // units per row
@@ -500,8 +587,9 @@ __global__ void k_intra_edges_init(FrameDesc f, IntraEdges ed)
 }
 
 // units an intra TU of this picture will write: not valid yet
-__global__ void k_intra_prepass(const B200IntraRec *__restrict__ recs, int count, IntraEdges ed)
+__global__ void k_intra_prepass(const B200IntraRec *__restrict__ recs, int count, IntraEdges ed, const uint32_t *__restrict__ gate)
 {
+    if (__ldg(gate + 1)) return;
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= count) return;
     const B200IntraRec r = decode_intra(__ldg(reinterpret_cast<const int4 *>(recs + i)));
@@ -515,7 +603,7 @@ __global__ void k_intra_prepass(const B200IntraRec *__restrict__ recs, int count
 // Poll until every lane of the warp has its record(s).  Executed by all 32 lanes with a uniform (vote) exit so the
 // warp leaves the loop CONVERGED -- a per-lane `while (!valid)` lets lanes leave one by one and the rest of the TU
 // then runs as diverged fragments (measured 5100 vs ~700 cycles for a 4x4 TU).  A malformed list (dependency cycle)
-// must not hang the GPU: give up after ~0.3 s and latch an error in counter[1].
+// must not hang the GPU: give up after ~0.3 s and latch an error in counter[2].
 // `pa_alt`: alternative source of record a (the up-left corner sample is the last element of BOTH halves of its unit,
 // and depending on the neighbour's geometry only the bottom row or only the right column of that unit is published).
 __device__ __forceinline__ void fetch_edges(const uint2 *pa, const uint2 *pa_alt, uint2 &va, const uint2 *pb, uint2 &vb, uint32_t *counter)
@@ -532,8 +620,8 @@ __device__ __forceinline__ void fetch_edges(const uint2 *pa, const uint2 *pa_alt
         if (__all_sync(0xffffffffu, ha && hb)) break;
         __nanosleep(20);
         if ((++spins & 1023) == 0) {
-            const bool abort = spins > (1u << 21) || ld_relaxed(counter + 1) != 0;
-            if (__any_sync(0xffffffffu, abort)) { st_relaxed(counter + 1, 1u); break; }
+            const bool abort = spins > (1u << 21) || ld_relaxed(counter + 2) != 0;
+            if (__any_sync(0xffffffffu, abort)) { st_relaxed(counter + 2, 1u); break; }
         }
     }
 }
@@ -673,8 +761,10 @@ __device__ __forceinline__ void intra_small(const B200IntraRec &r, const int16_t
 
 template <typename PIX>
 __global__ void __launch_bounds__(128) k_intra(const B200IntraRec *__restrict__ recs, int count, const int16_t *__restrict__ pool,
-                                               FrameDesc f, int bd, IntraEdges ed, uint32_t *counter)
+                                               FrameDesc f, int bd, IntraEdges ed, uint32_t *counter, CipDesc cipd)
 {
+    if (ld_relaxed(counter + 1)) return;               // the picture's work list failed validation (k_validate)
+    const bool cip = cipd.bits != nullptr;             // constrained_intra_pred picture (rare): every TU takes the general path
     __shared__ int s_g[4][2][66];     // gathered   [0]=top [1]=left, element [k] holds index k-1
     __shared__ int s_f[4][2][66];     // substituted
     __shared__ int s_ff[4][2][66];    // smoothed
@@ -689,7 +779,7 @@ __global__ void __launch_bounds__(128) k_intra(const B200IntraRec *__restrict__ 
         const B200IntraRec r = decode_intra(__ldg(reinterpret_cast<const int4 *>(recs + idx)));
         uint2 *e = edges_of(ed, r.plane);
         const int fs = estride_of(ed, r.plane);
-        if (r.log2 <= 3) {
+        if (r.log2 <= 3 && !cip) {
             unsigned long long *tr = g_intra_trace ? g_intra_trace + 8ull * idx : nullptr;
             TRACE(0);
             intra_small<PIX>(r, pool, plane_of(f, r.plane), bd, e, fs, counter, lane, &s_st[warp][0][0], tr);
@@ -697,8 +787,19 @@ __global__ void __launch_bounds__(128) k_intra(const B200IntraRec *__restrict__ 
         }
         const int n = 1 << r.log2, n2 = 2 * n, x0 = r.x, y0 = r.y;
         const PlaneDesc pd = plane_of(f, r.plane);
-        const bool ul = r.flags & B200_INF_UP_LEFT, up = r.flags & B200_INF_UP, ur = r.flags & B200_INF_UP_RIGHT;
-        const bool lf = r.flags & B200_INF_LEFT, bl = r.flags & B200_INF_BOTTOM_LEFT;
+        // availability: final in the record, except under constrained_intra_pred, where the record holds the flags BEFORE
+        // the rule and lane 0 applies hevcpred_template.c:116-163 with the picture's intra bitmap
+        int aflags = r.flags;
+        CipBlock cb;
+        if (cip) {
+            const int hs = r.plane ? cipd.hs_c : 0, vs = r.plane ? cipd.vs_c : 0;
+            cb.x0 = x0 << hs; cb.y0 = y0 << vs; cb.hs = hs; cb.vs = vs; cb.n = n;
+            int fl = 0;
+            if (lane == 0) fl = cip_flags(cipd, cb, r.flags);
+            aflags = __shfl_sync(0xffffffffu, fl, 0);
+        }
+        const bool ul = aflags & B200_INF_UP_LEFT, up = aflags & B200_INF_UP, ur = aflags & B200_INF_UP_RIGHT;
+        const bool lf = aflags & B200_INF_LEFT, bl = aflags & B200_INF_BOTTOM_LEFT;
         const int trs = r.top_right_size, bls = r.bottom_left_size;
         uint16_t *stg_t = s_st[warp][0], *stg_l = s_st[warp][1];
         // ---- neighbours: lane k fetches the bottom row of top unit k (4 samples), lane k the right column of left unit k;
@@ -724,10 +825,11 @@ __global__ void __launch_bounds__(128) k_intra(const B200IntraRec *__restrict__ 
         __syncwarp();
         // ---- the reference arrays, with the replication of the last in-picture sample (hevcpred_template.c:170-183) ----
         int *gt = s_g[warp][0], *gl = s_g[warp][1];
+        const int nofill = cip ? cip_fill_value(bd) : 0;       // what the reference leaves in samples nobody copied (:159-161)
         for (int k = lane; k <= n2; k += 32) {
             const int t = k - 1;
-            int tv = 0, lv = 0;
-            if (t < 0) { if (ul) tv = lv = g_corner; }
+            int tv = nofill, lv = nofill;
+            if (t < 0) { tv = lv = cip ? 128 : 0; if (ul) tv = lv = g_corner; }
             else {
                 if (t < n ? up : ur) tv = stg_t[t < n ? t : min(t, n + trs - 1)];
                 if (t < n ? lf : bl) lv = stg_l[t < n ? t : min(t, n + bls - 1)];
@@ -735,6 +837,10 @@ __global__ void __launch_bounds__(128) k_intra(const B200IntraRec *__restrict__ 
             gt[k] = tv; gl[k] = lv;
         }
         __syncwarp();
+        if (cip) {                                               // :185-249, a sequential scan: one lane
+            if (lane == 0) cip_substitute(cipd, cb, aflags, bls, gt + 1, gl + 1);
+            __syncwarp();
+        }
         // ---- substitution (hevcpred_template.c:250-286) in closed form ----
         int *ft = s_f[warp][0], *fleft = s_f[warp][1];
         {
@@ -906,59 +1012,66 @@ __global__ void k_fill(FrameDesc f, int value)
 // --------------------------------------------------------------------------------------------
 // launchers
 // --------------------------------------------------------------------------------------------
-int launch_mc(cudaStream_t st, const B200McRec *recs, int count, int n_big, const FrameDesc &cur, const FrameDesc *dpb_dev, const RefTable &rt, int bd)
+int launch_mc(cudaStream_t st, const B200McRec *recs, int count, int n_big, const FrameDesc &cur, const FrameDesc *dpb_dev, const RefTable &rt, int bd, const uint32_t *gate)
 {
     if (!count) return 0;
     int n = 0;
     const int n_small = count - n_big;
     if (n_big) {                        // one warp per tile
         const int grid = (n_big + 7) / 8;
-        if (bd > 8) k_mc<uint16_t, 32><<<grid, 256, 0, st>>>(recs, n_big, cur, dpb_dev, rt, bd);
-        else        k_mc<uint8_t, 32><<<grid, 256, 0, st>>>(recs, n_big, cur, dpb_dev, rt, bd);
+        if (bd > 8) k_mc<uint16_t, 32><<<grid, 256, 0, st>>>(recs, n_big, cur, dpb_dev, rt, bd, gate);
+        else        k_mc<uint8_t, 32><<<grid, 256, 0, st>>>(recs, n_big, cur, dpb_dev, rt, bd, gate);
         n++;
     }
     if (n_small) {                      // tiles of <= 8x8 samples: four per warp
         const int grid = (n_small + 31) / 32;
-        if (bd > 8) k_mc<uint16_t, 8><<<grid, 256, 0, st>>>(recs + n_big, n_small, cur, dpb_dev, rt, bd);
-        else        k_mc<uint8_t, 8><<<grid, 256, 0, st>>>(recs + n_big, n_small, cur, dpb_dev, rt, bd);
+        if (bd > 8) k_mc<uint16_t, 8><<<grid, 256, 0, st>>>(recs + n_big, n_small, cur, dpb_dev, rt, bd, gate);
+        else        k_mc<uint8_t, 8><<<grid, 256, 0, st>>>(recs + n_big, n_small, cur, dpb_dev, rt, bd, gate);
         n++;
     }
     return n;
 }
 
 template <typename PIX>
-static int launch_residual_t(cudaStream_t st, const B200TuRec *const recs[4], const int counts[4], const int16_t *pool, int16_t *parked, const FrameDesc &cur, int bd)
+static int launch_residual_t(cudaStream_t st, const B200TuRec *const recs[4], const int counts[4], const int16_t *pool, int16_t *parked, const FrameDesc &cur, int bd, const uint32_t *gate)
 {
     int n = 0;
-    if (counts[0]) { k_residual<PIX, 4><<<(counts[0] + 31) / 32, 128, 0, st>>>(recs[0], counts[0], pool, parked, cur, bd); n++; }
-    if (counts[1]) { k_residual<PIX, 8><<<(counts[1] + 15) / 16, 128, 0, st>>>(recs[1], counts[1], pool, parked, cur, bd); n++; }
-    if (counts[2]) { k_residual<PIX, 16><<<(counts[2] + 7) / 8, 128, 0, st>>>(recs[2], counts[2], pool, parked, cur, bd); n++; }
-    if (counts[3]) { k_residual<PIX, 32><<<(counts[3] + 3) / 4, 128, 0, st>>>(recs[3], counts[3], pool, parked, cur, bd); n++; }
+    if (counts[0]) { k_residual<PIX, 4><<<(counts[0] + 31) / 32, 128, 0, st>>>(recs[0], counts[0], pool, parked, cur, bd, gate); n++; }
+    if (counts[1]) { k_residual<PIX, 8><<<(counts[1] + 15) / 16, 128, 0, st>>>(recs[1], counts[1], pool, parked, cur, bd, gate); n++; }
+    if (counts[2]) { k_residual<PIX, 16><<<(counts[2] + 7) / 8, 128, 0, st>>>(recs[2], counts[2], pool, parked, cur, bd, gate); n++; }
+    if (counts[3]) { k_residual<PIX, 32><<<(counts[3] + 3) / 4, 128, 0, st>>>(recs[3], counts[3], pool, parked, cur, bd, gate); n++; }
     return n;
 }
-int launch_residual(cudaStream_t st, const B200TuRec *const recs[4], const int counts[4], const int16_t *pool, int16_t *parked, const FrameDesc &cur, int bd)
+int launch_residual(cudaStream_t st, const B200TuRec *const recs[4], const int counts[4], const int16_t *pool, int16_t *parked, const FrameDesc &cur, int bd, const uint32_t *gate)
 {
-    return bd > 8 ? launch_residual_t<uint16_t>(st, recs, counts, pool, parked, cur, bd) : launch_residual_t<uint8_t>(st, recs, counts, pool, parked, cur, bd);
+    return bd > 8 ? launch_residual_t<uint16_t>(st, recs, counts, pool, parked, cur, bd, gate) : launch_residual_t<uint8_t>(st, recs, counts, pool, parked, cur, bd, gate);
 }
 
 int launch_intra(cudaStream_t st, const B200IntraRec *recs, int count, const int16_t *pool, const FrameDesc &cur, int bd,
-                 uint2 *edges[3], const int edge_stride[3], uint32_t *counter)
+                 uint2 *edges[3], const int edge_stride[3], uint32_t *counter, const uint32_t *cip_words, const B200CipHeader *cip_hdr, int cfi)
 {
     if (!count) return 0;
     IntraEdges ed;
     for (int p = 0; p < 3; p++) { ed.e[p] = edges[p]; ed.stride[p] = edge_stride[p]; }
-    cudaMemsetAsync(counter, 0, sizeof(uint32_t), st);   // counter[1] = sticky abort flag, cleared at context creation
+    // counter[0] (ticket) and counter[1] (gate) were cleared when the picture entered its lane (engine.cu)
     const dim3 gi((cur.p[0].w / 4 + 127) / 128, cur.p[0].h / 4, 3);
     if (bd > 8) k_intra_edges_init<uint16_t><<<gi, 128, 0, st>>>(cur, ed);
     else        k_intra_edges_init<uint8_t><<<gi, 128, 0, st>>>(cur, ed);
-    k_intra_prepass<<<(count + 255) / 256, 256, 0, st>>>(recs, count, ed);
+    k_intra_prepass<<<(count + 255) / 256, 256, 0, st>>>(recs, count, ed, counter);
     int grid = (count + 3) / 4;
     // persistent warps.  The list is sorted by dependency level, so the TUs that can run together are adjacent and a
     // small window exposes all the parallelism there is; more waiting warps would only add polling traffic on L2.
     static const int max_ctas = getenv("B200_INTRA_CTAS") ? atoi(getenv("B200_INTRA_CTAS")) : 148 * 2;
     if (grid > max_ctas) grid = max_ctas;
-    if (bd > 8) k_intra<uint16_t><<<grid, 128, 0, st>>>(recs, count, pool, cur, bd, ed, counter);
-    else        k_intra<uint8_t><<<grid, 128, 0, st>>>(recs, count, pool, cur, bd, ed, counter);
+    CipDesc cd;
+    memset(&cd, 0, sizeof(cd));
+    if (cip_words && cip_hdr) {                        // device pointer to the blob's CIP section (B200CipHeader, then the bitmap) + host copy of the header
+        const B200CipHeader &ch = *cip_hdr;
+        cd.bits = cip_words + 4; cd.log2_pu = (int)ch.log2_min_pu_size; cd.pu_w = (int)ch.min_pu_width; cd.pu_h = (int)ch.min_pu_height;
+        cd.pic_w = cur.p[0].w; cd.pic_h = cur.p[0].h; cd.hs_c = cfi != 3; cd.vs_c = cfi == 1;
+    }
+    if (bd > 8) k_intra<uint16_t><<<grid, 128, 0, st>>>(recs, count, pool, cur, bd, ed, counter, cd);
+    else        k_intra<uint8_t><<<grid, 128, 0, st>>>(recs, count, pool, cur, bd, ed, counter, cd);
     return 3;
 }
 

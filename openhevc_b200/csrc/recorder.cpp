@@ -23,6 +23,7 @@ struct B200Rec {
     std::vector<B200TuRec> tu[4];
     std::vector<B200IntraRec> intra;
     std::vector<B200McRec> mc;
+    std::vector<uint32_t> cip;   // B200CipHeader + bitmap of a constrained_intra_pred picture (b200_rec_set_cip), else empty
     int last_intra[3];
     bool any_dbk = false, any_sao = false, open = false;
     bool merged = false;         // holds lists of several recording threads: intra records need re-ordering at finish
@@ -133,7 +134,7 @@ extern "C" int b200_rec_begin(B200Rec *r, int cur_slot, int poc)
     if (!r || cur_slot < 0 || cur_slot > 255) return B200_EINVAL;
     memset(r->blob + r->off_dbk, 0, r->off_pool - r->off_dbk);
     for (int s = 0; s < 4; s++) r->tu[s].clear();
-    r->intra.clear(); r->mc.clear();
+    r->intra.clear(); r->mc.clear(); r->cip.clear();
     r->ncoef = 0; r->npark = 0; r->any_dbk = r->any_sao = false;
     r->last_intra[0] = r->last_intra[1] = r->last_intra[2] = -1;
     r->cur_slot = cur_slot; r->poc = poc; r->open = true; r->nbytes = 0; r->n_ref = 0; r->merged = false;
@@ -335,6 +336,20 @@ extern "C" int b200_rec_sao(B200Rec *r, int plane, int x, int y, const B200SaoRe
     return 0;
 }
 
+// pps->constrained_intra_pred_flag: the PU types of the picture (MvField.pred_flag == PF_INTRA, one byte per min-PU,
+// row-major), as they stand when every CTB has been parsed
+extern "C" int b200_rec_set_cip(B200Rec *r, int log2_min_pu_size, int min_pu_width, int min_pu_height, const uint8_t *is_intra)
+{
+    if (!r || !r->open || !is_intra || log2_min_pu_size < 2 || log2_min_pu_size > 5 || min_pu_width <= 0 || min_pu_height <= 0 ||
+        min_pu_width != (r->cfg.width >> log2_min_pu_size) || min_pu_height != (r->cfg.height >> log2_min_pu_size)) return B200_EINVAL;
+    r->cip.assign(B200_CIP_WORDS(min_pu_width, min_pu_height), 0u);
+    r->cip[0] = (uint32_t)log2_min_pu_size; r->cip[1] = (uint32_t)min_pu_width; r->cip[2] = (uint32_t)min_pu_height;
+    for (int y = 0; y < min_pu_height; y++)
+        for (int x = 0; x < min_pu_width; x++)
+            if (is_intra[(size_t)y * min_pu_width + x]) { const size_t i = (size_t)y * min_pu_width + x; r->cip[4 + (i >> 5)] |= 1u << (i & 31); }
+    return 0;
+}
+
 extern "C" int b200_rec_finish(B200Rec *r, const void **blob, uint64_t *nbytes)
 {
     if (!r || !r->open || !blob || !nbytes) return B200_EINVAL;
@@ -390,6 +405,13 @@ extern "C" int b200_rec_finish(B200Rec *r, const void **blob, uint64_t *nbytes)
         h->mc_big_count = (uint32_t)n[0];
     }
     o = (o + r->mc.size() * 32 + 255) & ~(uint64_t)255;
+    if (!r->cip.empty()) {                                   // constrained_intra_pred picture: B200CipHeader + intra bitmap
+        if (o + r->cip.size() * 4 + 256 > r->cap) return B200_ENOMEM;
+        h->cip.off = (uint32_t)o; h->cip.count = (uint32_t)r->cip.size();
+        h->flags |= B200_FRAME_CIP;
+        memcpy(r->blob + o, r->cip.data(), r->cip.size() * 4);
+        o = (o + r->cip.size() * 4 + 255) & ~(uint64_t)255;
+    }
     h->total_bytes = (uint32_t)o;
     r->nbytes = o; r->open = false;
     *blob = r->blob; *nbytes = o;

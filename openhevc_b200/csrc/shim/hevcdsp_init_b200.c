@@ -16,7 +16,7 @@
  * threads of ONE picture (-f 2, execute2 jobs, hevc.c:3082): a worker attaches itself to the picture in progress on its
  * first table call, records into its own B200Rec, and b200_frame_end folds the workers into the owner's recorder
  * (b200_rec_merge).  Frame and slice threads combined (-f 4) are rejected: a table call carries no context, so a worker
- * cannot tell which of several pictures in progress it belongs to.  One decoder instance per process.  constrained_intra_pred / cross-component prediction / pcm+transquant-bypass SAO restore are
+ * cannot tell which of several pictures in progress it belongs to.  One decoder instance per process.  cross-component prediction / pcm+transquant-bypass SAO restore are
  * rejected with an error from b200_frame_end.
  */
 #include <stdint.h>
@@ -348,7 +348,6 @@ static void rec_intra(HEVCContext *s, int x0, int y0, int log2_size, int c_idx)
     HEVCLocalContext *lc = s->HEVClc;
     const HEVCSPS *sps = s->sps;
     if (!attached()) return;
-    if (s->pps->constrained_intra_pred_flag) { fail(B200_ENOTSUP, "constrained_intra_pred is not supported by the B200 path yet"); return; }
     const int hshift = sps->hshift[c_idx], vshift = sps->vshift[c_idx];
     const int size = 1 << log2_size;
     const int size_l_h = size << hshift, size_l_v = size << vshift;
@@ -499,7 +498,6 @@ int b200_frame_begin(HEVCContext *s)
 
 int b200_frame_end(HEVCContext *s)
 {
-    (void)s;
     if (g.in_frame != 1) return g.err ? g.err : B200_ESTATE;
     deactivate();                                   /* all execute2 jobs of the picture have returned (hevc.c:3087) */
     int mrc = b200_rec_set_refs(g.rec, g.ref_slot, g.n_ref);
@@ -512,6 +510,18 @@ int b200_frame_end(HEVCContext *s)
         w->in_frame = 0;
     }
     if (mrc) fail(mrc, "merging the worker threads' work lists failed");
+    if (!g.err && s->pps && s->pps->constrained_intra_pred_flag && s->ref && s->ref->tab_mvf) {
+        /* the device applies the constrained-intra rules itself (hevcpred_template.c:116-249): hand it the PU types */
+        const int pw = s->sps->min_pu_width, ph = s->sps->min_pu_height;
+        uint8_t *map = malloc((size_t)pw * ph);
+        if (!map) fail(B200_ENOMEM, "constrained_intra_pred map");
+        else {
+            for (int i = 0; i < pw * ph; i++) map[i] = s->ref->tab_mvf[i].pred_flag == PF_INTRA;
+            int crc = b200_rec_set_cip(g.rec, s->sps->log2_min_pu_size, pw, ph, map);
+            if (crc) fail(crc, "b200_rec_set_cip failed");
+            free(map);
+        }
+    }
     if (g.err) { ticket_release(); return g.err; }
     if (getenv("B200_SHIM_STATS"))
         fprintf(stderr, "b200 picture %d: intra_pred %d transform_add %d mc %d deblock %d sao %d\n", g.frame_no, g.n_intra, g.n_tu, g.n_pu, g.n_dbk, g.n_sao);

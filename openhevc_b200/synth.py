@@ -31,13 +31,14 @@ class FrameSynth:
 
     def __init__(self, width, height, cfi=1, bit_depth=8, log2_ctb=6, seed=0, refs=(), cur_slot=0, poc=0,
                  p_intra=0.12, coded_frac=0.7, weighted=False, deblock=True, sao=True, sao_restore=False,
-                 exotic=0.0, max_mv=64, split_bias=1.0, qp=32, bi_frac=0.6):
+                 exotic=0.0, max_mv=64, split_bias=1.0, qp=32, bi_frac=0.6, cip=False):
         self.W, self.H, self.cfi, self.bd, self.log2_ctb = width, height, cfi, bit_depth, log2_ctb
         self.rng = np.random.default_rng(seed)
         self.refs, self.cur_slot, self.poc = list(refs), cur_slot, poc
         self.p_intra, self.coded_frac, self.weighted = p_intra, coded_frac, weighted
         self.deblock, self.sao, self.sao_restore, self.exotic = deblock, sao, sao_restore, exotic
         self.max_mv, self.split_bias, self.qp, self.bi_frac = max_mv, split_bias, qp, bi_frac
+        self.cip = cip                                # constrained_intra_pred: the blob carries the intra bitmap of the min-PUs (4x4 luma)
         self.hs = 1 if cfi != 3 else 0
         self.vs = 1 if cfi == 1 else 0
         self.ctb = 1 << log2_ctb
@@ -442,7 +443,7 @@ class FrameSynth:
         dbk = self._deblock_grid() if self.deblock else None
         sao = self._sao_grid() if self.sao else None
         blob = W.build_blob(self.W, self.H, self.cfi, self.bd, self.log2_ctb, self.cur_slot, self.poc, pool, tu, intra, mc, dbk, sao, out=out,
-                            ref_slots=self.refs)
+                            ref_slots=self.refs, cip=(2, self.is_intra) if self.cip else None)
         B = 2 if self.bd > 8 else 1
         S = sum(np.prod(W.plane_dims(self.W, self.H, self.cfi, p)) for p in range(3))
         st = self.stats

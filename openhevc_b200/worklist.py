@@ -16,7 +16,7 @@ INF_UP_LEFT, INF_UP, INF_UP_RIGHT, INF_LEFT, INF_BOTTOM_LEFT, INF_FILTER, INF_ST
 MCF_BI, MCF_WEIGHTED, MCF_CHROMA = 1, 2, 4
 SAO_NONE, SAO_BAND, SAO_EDGE = 0, 1, 2
 NO_RESID = 0xFFFFFFFF
-FRAME_HAS_DEBLOCK, FRAME_HAS_SAO = 1, 2
+FRAME_HAS_DEBLOCK, FRAME_HAS_SAO, FRAME_CIP = 1, 2, 4
 
 section_dt = np.dtype([("off", "<u4"), ("count", "<u4")])
 header_dt = np.dtype([
@@ -24,7 +24,7 @@ header_dt = np.dtype([
     ("width", "<u2"), ("height", "<u2"), ("chroma_format_idc", "u1"), ("bit_depth", "u1"),
     ("log2_ctb_size", "u1"), ("cur_slot", "u1"), ("flags", "<u4"),
     ("sec", section_dt, (SEC_COUNT,)), ("ref_slot", "u1", (16,)), ("n_ref", "u1"), ("pad", "u1", (3,)),
-    ("mc_big_count", "<u4"), ("reserved", "<u4", (64 - 13 - 2 * SEC_COUNT,)),
+    ("mc_big_count", "<u4"), ("cip", section_dt), ("reserved", "<u4", (64 - 15 - 2 * SEC_COUNT,)),
 ])
 tu_dt = np.dtype([("x", "<u2"), ("y", "<u2"), ("plane", "u1"), ("log2", "u1"), ("kind", "u1"), ("flags", "u1"),
                   ("col_limit", "u1"), ("pad", "u1"), ("nnz", "<u2"), ("coeff_off", "<u4")])
@@ -133,9 +133,10 @@ def level_order(intra, width, height, cfi):
 
 
 def build_blob(width, height, cfi, bit_depth, log2_ctb, cur_slot, poc=0, coeff=None, tu=None, intra=None, mc=None,
-               dbk=None, sao=None, out=None, ref_slots=()):
+               dbk=None, sao=None, out=None, ref_slots=(), cip=None):
     """Assemble a blob.  tu: dict {2,3,4,5 -> tu_dt array}; dbk: uint16 array (DbkLayout.total) or None;
-    sao: sao_dt array [3*ctb_count] or None.  `out`: optional uint8 buffer (e.g. pinned) to build into."""
+    sao: sao_dt array [3*ctb_count] or None.  `out`: optional uint8 buffer (e.g. pinned) to build into.
+    cip: None, or (log2_min_pu, bool array [min_pu_height, min_pu_width], True = intra PU) for a constrained_intra_pred picture."""
     coeff = np.zeros(0, np.int16) if coeff is None else np.ascontiguousarray(coeff, np.int16)
     tu = tu or {}
     parts = [None] * SEC_COUNT
@@ -159,6 +160,16 @@ def build_blob(width, height, cfi, bit_depth, log2_ctb, cur_slot, poc=0, coeff=N
     for s, p in enumerate(parts):
         hdr["sec"][0][s] = (off, len(p))
         off = (off + p.nbytes + 255) // 256 * 256
+    cip_words = None
+    if cip is not None:
+        log2_pu, bitmap = cip
+        bitmap = np.ascontiguousarray(bitmap, bool)
+        bits = np.packbits(bitmap.reshape(-1), bitorder="little")
+        bits = np.concatenate([bits, np.zeros(-len(bits) % 4, np.uint8)]).view("<u4")
+        cip_words = np.concatenate([np.array([log2_pu, bitmap.shape[1], bitmap.shape[0], 0], "<u4"), bits])
+        hdr["cip"][0] = (off, len(cip_words))
+        hdr["flags"] |= FRAME_CIP
+        off = (off + cip_words.nbytes + 255) // 256 * 256
     hdr["total_bytes"] = off
     if out is None:
         out = np.zeros(off, np.uint8)
@@ -169,6 +180,9 @@ def build_blob(width, height, cfi, bit_depth, log2_ctb, cur_slot, poc=0, coeff=N
     for s, p in enumerate(parts):
         o = int(hdr["sec"][0][s]["off"])
         out[o:o + p.nbytes] = p.view(np.uint8).reshape(-1)
+    if cip_words is not None:
+        o = int(hdr["cip"][0]["off"])
+        out[o:o + cip_words.nbytes] = cip_words.view(np.uint8)
     return out
 
 

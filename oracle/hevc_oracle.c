@@ -238,24 +238,148 @@ void orc_mc_rec(const B200McRec *m, pix_t *dst, int dst_stride, const pix_t *ref
 
 /* ------------------------------------------------------------------------------------------
  * Intra prediction.  Reference: hevcpred_template.c:30-344 (neighbour gathering, substitution,
- * smoothing), :359-384 planar, :388-417 DC, :419-538 angular.  constrained_intra_pred is
- * resolved on the host (flags in the record are final); the CIP substitution chain itself
- * (:116-249) is not restated (out of scope for the gate configurations).
+ * smoothing), :359-384 planar, :388-417 DC, :419-538 angular.  constrained_intra_pred
+ * (:116-163 candidate flags from the PU types, :185-249 substitution of the samples of inter
+ * neighbours) is restated in orc_cip_flags() / orc_cip_substitute(); the record's flags are the
+ * availability BEFORE those rules, the intra bitmap travels in the blob (B200BlobHeader.cip).
  * ---------------------------------------------------------------------------------------- */
+typedef struct OrcCip {          /* NULL pointer = picture without constrained_intra_pred */
+    int log2_min_pu, pu_w, pu_h;
+    const uint32_t *bits;        /* one bit per min-PU, row-major: MvField.pred_flag == PF_INTRA */
+    int hs, vs;                  /* chroma shifts of the plane the record is in */
+    int pic_w, pic_h;            /* luma size (sps->width / height) */
+} OrcCip;
+
+static int cip_pu_intra(const OrcCip *c, int px, int py)                   /* MVF(x, y).pred_flag == PF_INTRA (:35-36) */
+{
+    const long i = (long)px + (long)py * c->pu_w;                          /* the reference indexes the array linearly */
+    if (i < 0 || i >= (long)c->pu_w * c->pu_h) return 0;                   /* never reached by a legal stream */
+    return (c->bits[i >> 5] >> (i & 31)) & 1;
+}
+/* IS_INTRA(x, y) (:37-40): x, y = sample offsets from the block origin, in samples of the block's plane */
+static int cip_is_intra(const OrcCip *c, int x0, int y0, int x, int y)
+{
+    return cip_pu_intra(c, (x0 + x * (1 << c->hs)) >> c->log2_min_pu, (y0 + y * (1 << c->vs)) >> c->log2_min_pu);
+}
+
+/* :116-163 -- a neighbour stays a candidate only if one of its PUs (every second one is looked at) is intra */
+static void orc_cip_flags(const B200IntraRec *r, const OrcCip *c, int *up_left, int *up, int *up_right, int *lft, int *bottom_left)
+{
+    const int n = 1 << r->log2, pu = c->log2_min_pu;
+    const int x0 = r->x << c->hs, y0 = r->y << c->vs, sl_h = n << c->hs, sl_v = n << c->vs;
+    const int pv = sl_v >> pu;
+    int ph = sl_h >> pu;
+    const int on_x = !(x0 & ((1 << pu) - 1)), on_y = !(y0 & ((1 << pu) - 1));
+    if (!ph) ph++;                                                          /* only the horizontal count is bumped (:121-122) */
+    if (*bottom_left && on_x) {
+        const int xl = (x0 - 1) >> pu, yb = (y0 + sl_v) >> pu;
+        int max = pv < c->pu_h - yb ? pv : c->pu_h - yb, any = 0;
+        for (int i = 0; i < max; i += 2) any |= cip_pu_intra(c, xl, yb + i);
+        *bottom_left = any;
+    }
+    if (*lft && on_x) {
+        const int xl = (x0 - 1) >> pu, yl = y0 >> pu;
+        int max = pv < c->pu_h - yl ? pv : c->pu_h - yl, any = 0;
+        for (int i = 0; i < max; i += 2) any |= cip_pu_intra(c, xl, yl + i);
+        *lft = any;
+    }
+    if (*up_left) *up_left = cip_pu_intra(c, (x0 - 1) >> pu, (y0 - 1) >> pu);
+    if (*up && on_y) {
+        const int xt = x0 >> pu, yt = (y0 - 1) >> pu;
+        int max = ph < c->pu_w - xt ? ph : c->pu_w - xt, any = 0;
+        for (int i = 0; i < max; i += 2) any |= cip_pu_intra(c, xt + i, yt);
+        *up = any;
+    }
+    if (*up_right && on_y) {
+        const int yt = (y0 - 1) >> pu, xr = (x0 + sl_h) >> pu;
+        int max = ph < c->pu_w - xr ? ph : c->pu_w - xr, any = 0;
+        for (int i = 0; i < max; i += 2) any |= cip_pu_intra(c, xr + i, yt);
+        *up_right = any;
+    }
+}
+
+static void put4(int *p, int v) { p[0] = p[1] = p[2] = p[3] = v; }         /* AV_WN4P of a splatted pixel */
+
+/* :185-249 -- runs after the candidate samples were copied: samples of inter-coded neighbours are replaced by
+ * propagating the nearest intra-coded ones, in groups of four like the reference's 4-pixel stores */
+static void orc_cip_substitute(const B200IntraRec *r, const OrcCip *c, int *left, int *top,
+                               int up_left, int up, int up_right, int lft, int bottom_left)
+{
+    if (!(bottom_left || lft || up_left || up || up_right)) return;
+    const int n = 1 << r->log2;
+    const int x0 = r->x << c->hs, y0 = r->y << c->vs;
+#define ISI(x, y) cip_is_intra(c, x0, y0, (x), (y))
+    int smx = x0 + ((2 * n) << c->hs) < c->pic_w ? 2 * n : (c->pic_w - x0) >> c->hs;
+    int smy = y0 + ((2 * n) << c->vs) < c->pic_h ? 2 * n : (c->pic_h - y0) >> c->vs;
+    int j = n + (bottom_left ? r->bottom_left_size : 0) - 1, i, a;
+    if (!up_right)    smx = x0 + (n << c->hs) < c->pic_w ? n : (c->pic_w - x0) >> c->hs;
+    if (!bottom_left) smy = y0 + (n << c->vs) < c->pic_h ? n : (c->pic_h - y0) >> c->vs;
+    if (bottom_left || lft || up_left) {
+        while (j > -1 && !ISI(-1, j)) j--;                                  /* lowest intra sample of the left column */
+        if (!ISI(-1, j)) {                                                   /* none, not even the corner: take the first intra sample of the top row */
+            j = 0;
+            while (j < smx && !ISI(j, -1)) j++;
+            for (i = j; i > -1; i--) if (!ISI(i - 1, -1)) top[i - 1] = top[i];      /* EXTEND_LEFT_CIP(top, j, j + 1) */
+            left[-1] = top[-1];
+        }
+    } else {
+        j = 0;
+        while (j < smx && !ISI(j, -1)) j++;
+        if (j > 0) {
+            if (x0 > 0) { for (i = j; i > -1; i--) if (!ISI(i - 1, -1)) top[i - 1] = top[i]; }
+            else { for (i = j; i > 0; i--) if (!ISI(i - 1, -1)) top[i - 1] = top[i]; top[-1] = top[0]; }
+        }
+        left[-1] = top[-1];
+    }
+    left[-1] = top[-1];
+    if (bottom_left || lft) {                                                /* EXTEND_DOWN_CIP(left, 0, smy) */
+        a = left[-1];
+        for (i = 0; i < smy; i += 4) { if (!ISI(-1, i)) put4(left + i, a); else a = left[i + 3]; }
+    }
+    if (!lft) for (i = 0; i < n; i += 4) put4(left + i, left[-1]);
+    if (!bottom_left) { const int v = left[n - 1]; for (i = 0; i < n; i += 4) put4(left + n + i, v); }
+    if (x0 != 0 && y0 != 0) {
+        a = left[smy - 1];
+        for (i = smy - 1; i > -1; i -= 4) { if (!ISI(-1, i - 3)) put4(left + i - 3, a); else a = left[i - 3]; }   /* EXTEND_UP_CIP */
+        if (!ISI(-1, -1)) left[-1] = left[0];
+    } else if (x0 == 0) {
+        for (i = 0; i < smy; i += 4) put4(left + i, 0);
+    } else {
+        a = left[smy - 1];
+        for (i = smy - 1; i > -1; i -= 4) { if (!ISI(-1, i - 3)) put4(left + i - 3, a); else a = left[i - 3]; }
+    }
+    top[-1] = left[-1];
+    if (y0 != 0) {                                                           /* EXTEND_RIGHT_CIP(top, 0, smx) */
+        a = left[-1];
+        for (i = 0; i < smx; i += 4) { if (!ISI(i, -1)) put4(top + i, a); else a = top[i + 3]; }
+    }
+#undef ISI
+}
+
 static const int8_t k_intra_angle[33] = { 32, 26, 21, 17, 13, 9, 5, 2, 0, -2, -5, -9, -13, -17, -21, -26, -32,
                                           -26, -21, -17, -13, -9, -5, -2, 0, 2, 5, 9, 13, 17, 21, 26, 32 };
 static const int16_t k_inv_angle[15] = { -4096, -1638, -910, -630, -482, -390, -315, -256, -315, -390, -482, -630, -910, -1638, -4096 };
 
-void orc_intra_rec(const B200IntraRec *r, pix_t *plane, int stride, int bd)
+static void orc_intra_rec_cip(const B200IntraRec *r, pix_t *plane, int stride, int bd, const OrcCip *cip);
+static int *g_cap_top, *g_cap_left, *g_cap_flags;      /* test hook, see orc_debug_cip_refs() */
+void orc_intra_rec(const B200IntraRec *r, pix_t *plane, int stride, int bd) { orc_intra_rec_cip(r, plane, stride, bd, NULL); }
+
+static void orc_intra_rec_cip(const B200IntraRec *r, pix_t *plane, int stride, int bd, const OrcCip *cip)
 {
     const int n = 1 << r->log2, n2 = 2 * n;
     pix_t *src = plane + r->y * stride + r->x;
-    int lbuf[2][65], tbuf[2][65];          /* index 0 holds [-1] */
-    int *left = lbuf[0] + 1, *top = tbuf[0] + 1;
+    int lbuf[2][8 + 65 + 8], tbuf[2][8 + 65 + 8];          /* index 8 holds [-1]; slack for the 4-sample stores of the CIP rules */
+    int *left = lbuf[0] + 9, *top = tbuf[0] + 9;
     int up_left = !!(r->flags & B200_INF_UP_LEFT), up = !!(r->flags & B200_INF_UP), up_right = !!(r->flags & B200_INF_UP_RIGHT);
     int lft = !!(r->flags & B200_INF_LEFT), bottom_left = !!(r->flags & B200_INF_BOTTOM_LEFT);
     int i;
     for (i = -1; i < n2; i++) left[i] = top[i] = 0;
+    if (cip) {
+        /* :116-163, then memset(left / top, 128, ...) of `pixel`s (:159-161): 0x80 or 0x8080 per sample, top[-1] = 128 */
+        orc_cip_flags(r, cip, &up_left, &up, &up_right, &lft, &bottom_left);
+        for (i = 0; i < 64; i++) left[i] = top[i] = bd > 8 ? 0x8080 : 0x80;
+        left[-1] = top[-1] = 128;
+    }
 
     /* gather what exists (:164-183) */
     if (up_left) left[-1] = top[-1] = src[-stride - 1];
@@ -268,6 +392,13 @@ void orc_intra_rec(const B200IntraRec *r, pix_t *plane, int stride, int bd)
     if (bottom_left) {
         for (i = 0; i < r->bottom_left_size; i++) left[n + i] = src[(n + i) * stride - 1];
         for (; i < n; i++) left[n + i] = src[(n + r->bottom_left_size - 1) * stride - 1];
+    }
+    if (cip) orc_cip_substitute(r, cip, left, top, up_left, up, up_right, lft, bottom_left);
+    if (g_cap_top) {                 /* orc_debug_cip_refs(): hand out the arrays as they stand here, predict nothing */
+        for (i = -1; i < 64; i++) { g_cap_top[i + 1] = top[i]; g_cap_left[i + 1] = left[i]; }
+        *g_cap_flags = (up_left ? B200_INF_UP_LEFT : 0) | (up ? B200_INF_UP : 0) | (up_right ? B200_INF_UP_RIGHT : 0) |
+                       (lft ? B200_INF_LEFT : 0) | (bottom_left ? B200_INF_BOTTOM_LEFT : 0);
+        return;
     }
     /* substitution chain (:250-286) */
     if (!bottom_left) {
@@ -296,7 +427,7 @@ void orc_intra_rec(const B200IntraRec *r, pix_t *plane, int stride, int bd)
         static const int thresh[3] = { 7, 1, 0 };
         int d26 = iabs(mode - 26), d10 = iabs(mode - 10), dist = d26 < d10 ? d26 : d10;
         if (dist > thresh[r->log2 - 3]) {
-            int *fl = lbuf[1] + 1, *ft = tbuf[1] + 1;
+            int *fl = lbuf[1] + 9, *ft = tbuf[1] + 9;
             if ((r->flags & B200_INF_STRONG) && r->plane == 0 && r->log2 == 5 &&
                 iabs(top[-1] + top[63] - 2 * top[31]) < (1 << (bd - 5)) &&
                 iabs(left[-1] + left[63] - 2 * left[31]) < (1 << (bd - 5))) {
@@ -557,10 +688,19 @@ int orc_execute_blob(const uint8_t *blob, uint16_t **planes, int n_slots)
     }
     /* K3 intra, decode order */
     const B200IntraRec *ir = (const B200IntraRec *)(blob + h->sec[B200_SEC_INTRA].off);
+    OrcCip cip;
+    const int has_cip = (h->flags & B200_FRAME_CIP) && h->cip.count >= 4;
+    if (has_cip) {
+        const uint32_t *cw = (const uint32_t *)(blob + h->cip.off);
+        cip.log2_min_pu = (int)cw[0]; cip.pu_w = (int)cw[1]; cip.pu_h = (int)cw[2]; cip.bits = cw + 4;
+        cip.pic_w = h->width; cip.pic_h = h->height;
+        if (h->cip.count < B200_CIP_WORDS(cip.pu_w, cip.pu_h)) { free(parked); return -4; }
+    }
     for (uint32_t i = 0; i < h->sec[B200_SEC_INTRA].count; i++) {
         const B200IntraRec *r = &ir[i];
         const int p = r->plane;
-        orc_intra_rec(r, cur[p], pw[p], bd);
+        if (has_cip) { cip.hs = p && cfi != 3; cip.vs = p && cfi == 1; }
+        orc_intra_rec_cip(r, cur[p], pw[p], bd, has_cip ? &cip : NULL);
         if (r->resid_off != B200_NO_RESID)
             orc_add_residual(cur[p] + r->y * pw[p] + r->x, pw[p], parked + r->resid_off, 1 << r->log2, bd);
     }
@@ -595,5 +735,24 @@ int orc_execute_blob(const uint8_t *blob, uint16_t **planes, int n_slots)
             free(copy);
         }
     }
+    return 0;
+}
+
+/* Test hook for tests/test_kernel_emul_cpu.py: the reference arrays of intra record `rec_index` of a constrained_intra_pred
+ * blob after the CIP rules (:116-249), before the ordinary substitution -- neighbours are read from `planes` (the
+ * picture of the current slot) as they are.  top65 / left65: index 0 holds [-1].  Not thread safe. */
+int orc_debug_cip_refs(const uint8_t *blob, uint16_t **planes, int rec_index, int *top65, int *left65, int *flags_out)
+{
+    const B200BlobHeader *h = (const B200BlobHeader *)blob;
+    if (h->magic != B200_BLOB_MAGIC || !(h->flags & B200_FRAME_CIP) || h->cip.count < 4 || rec_index < 0 || (uint32_t)rec_index >= h->sec[B200_SEC_INTRA].count) return -1;
+    const uint32_t *cw = (const uint32_t *)(blob + h->cip.off);
+    const B200IntraRec *r = (const B200IntraRec *)(blob + h->sec[B200_SEC_INTRA].off) + rec_index;
+    const int cfi = h->chroma_format_idc, p = r->plane;
+    OrcCip cip = { (int)cw[0], (int)cw[1], (int)cw[2], cw + 4, p && cfi != 3, p && cfi == 1, h->width, h->height };
+    int pw, ph;
+    b200_plane_dims(h->width, h->height, cfi, p, &pw, &ph);
+    g_cap_top = top65; g_cap_left = left65; g_cap_flags = flags_out;
+    orc_intra_rec_cip(r, planes[p], pw, h->bit_depth, &cip);
+    g_cap_top = g_cap_left = g_cap_flags = NULL;
     return 0;
 }

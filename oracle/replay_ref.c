@@ -36,6 +36,8 @@ typedef struct RefCtx {
     int *zs;
     int bd, B, cfi, W, H;
     int pw[3], ph[3];
+    HEVCFrame refframe;          /* s->ref of a constrained_intra_pred picture: only tab_mvf[].pred_flag is read (hevcpred_template.c:35-40) */
+    MvField *mvf;
 } RefCtx;
 
 static RefCtx *ref_ctx_new(const B200BlobHeader *h)
@@ -64,7 +66,7 @@ static RefCtx *ref_ctx_new(const B200BlobHeader *h)
 }
 static void ref_ctx_free(RefCtx *c)
 {
-    free(c->zs); free(c->fr); free(c->lc); free(c->pps); free(c->sps); free(c->s); free(c);
+    free(c->mvf); free(c->zs); free(c->fr); free(c->lc); free(c->pps); free(c->sps); free(c->s); free(c);
 }
 
 typedef struct HostFrame { uint8_t *p[3]; int stride[3]; } HostFrame;
@@ -175,6 +177,20 @@ static int execute(RefCtx *c, const uint8_t *blob, uint8_t **planes, const int64
     for (int s = 0; s < n_slots; s++) for (int p = 0; p < 3; p++) { dpb[s].p[p] = planes[3 * s + p]; dpb[s].stride[p] = (int)strides[3 * s + p]; }
     HostFrame *cur = &dpb[h->cur_slot];
     for (int p = 0; p < 3; p++) { c->fr->data[p] = cur->p[p]; c->fr->linesize[p] = cur->stride[p]; }
+    /* constrained_intra_pred: the motion field the reference looks the PU types up in, from the blob's bitmap */
+    c->pps->constrained_intra_pred_flag = 0;
+    if ((h->flags & B200_FRAME_CIP) && h->cip.count >= 4) {
+        const uint32_t *cw = (const uint32_t *)(blob + h->cip.off);
+        const int pw_ = (int)cw[1], ph_ = (int)cw[2];
+        if (h->cip.count < B200_CIP_WORDS(pw_, ph_)) return -6;
+        c->sps->log2_min_pu_size = cw[0]; c->sps->min_pu_width = pw_; c->sps->min_pu_height = ph_;
+        free(c->mvf);
+        c->mvf = calloc((size_t)pw_ * ph_ + 1, sizeof(MvField));
+        for (int i = 0; i < pw_ * ph_; i++) c->mvf[i].pred_flag = ((cw[4 + (i >> 5)] >> (i & 31)) & 1) ? PF_INTRA : PF_L0;
+        if (!c->s->ref) c->s->ref = &c->refframe;       /* the drop-in run has s->ref = its DPB entry already */
+        c->s->ref->tab_mvf = c->mvf;
+        c->pps->constrained_intra_pred_flag = 1;
+    }
 
     const B200McRec *mc = (const B200McRec *)(blob + h->sec[B200_SEC_MC].off);
     for (uint32_t i = 0; i < h->sec[B200_SEC_MC].count; i++) replay_mc(c, h, &mc[i], cur, dpb);

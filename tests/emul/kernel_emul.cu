@@ -4,6 +4,7 @@
 // 16x2 paths, tile / lane geometry and border rules are checked here, without a GPU.  Nothing in the product links this.
 #include "../../openhevc_b200/csrc/k_sao.cuh"
 #include "../../openhevc_b200/csrc/k_deblock.cuh"
+#include "../../openhevc_b200/csrc/k_intra_cip.cuh"
 #include <vector>
 
 static void describe(FrameDesc &f, uint8_t *const planes[3], const int pitch[3], int width, int height, int cfi)
@@ -61,5 +62,33 @@ extern "C" int emul_deblock(const uint16_t *grid, uint8_t *const planes[3], cons
                 for (int tid = 0; tid < DBK_THREADS; tid++) dbk_horizontal(t, grid, L, pd, plane, bx, by, tid, bd);
                 for (int tid = 0; tid < DBK_THREADS; tid++) { if (bd > 8) dbk_store<uint16_t>(t, pd, bx, by, tid); else dbk_store<uint8_t>(t, pd, bx, by, tid); }
             }
+    return 0;
+}
+
+// constrained_intra_pred: cip_flags() + the gather k_intra performs with those flags (restated here with plain loops: the
+// kernel's gather is warp-cooperative and goes through the edge records) + cip_substitute().  Output like
+// orc_debug_cip_refs(): index 0 holds [-1].
+extern "C" int emul_cip_refs(const uint32_t *cip_words, const B200IntraRec *r, const uint16_t *plane, int stride, int pic_w, int pic_h, int cfi, int bd,
+                             int *top65, int *left65, int *flags_out)
+{
+    CipDesc cd;
+    cd.bits = cip_words + 4; cd.log2_pu = (int)cip_words[0]; cd.pu_w = (int)cip_words[1]; cd.pu_h = (int)cip_words[2];
+    cd.pic_w = pic_w; cd.pic_h = pic_h; cd.hs_c = cfi != 3; cd.vs_c = cfi == 1;
+    CipBlock cb;
+    cb.hs = r->plane ? cd.hs_c : 0; cb.vs = r->plane ? cd.vs_c : 0;
+    cb.x0 = r->x << cb.hs; cb.y0 = r->y << cb.vs; cb.n = 1 << r->log2;
+    const int n = cb.n, fl = cip_flags(cd, cb, r->flags);
+    int tbuf[8 + 66 + 8], lbuf[8 + 66 + 8];
+    int *top = tbuf + 9, *left = lbuf + 9;
+    for (int i = -1; i < 64; i++) top[i] = left[i] = i < 0 ? 128 : cip_fill_value(bd);
+    const uint16_t *src = plane + (size_t)r->y * stride + r->x;
+    if (fl & B200_INF_UP_LEFT) top[-1] = left[-1] = src[-stride - 1];
+    if (fl & B200_INF_UP) for (int i = 0; i < n; i++) top[i] = src[-stride + i];
+    if (fl & B200_INF_UP_RIGHT) for (int i = 0; i < n; i++) top[n + i] = src[-stride + n + imin(i, r->top_right_size - 1)];
+    if (fl & B200_INF_LEFT) for (int i = 0; i < n; i++) left[i] = src[(size_t)i * stride - 1];
+    if (fl & B200_INF_BOTTOM_LEFT) for (int i = 0; i < n; i++) left[n + i] = src[(size_t)(n + imin(i, r->bottom_left_size - 1)) * stride - 1];
+    cip_substitute(cd, cb, fl, r->bottom_left_size, top, left);
+    for (int i = -1; i < 64; i++) { top65[i + 1] = top[i]; left65[i + 1] = left[i]; }
+    *flags_out = fl & 31;
     return 0;
 }

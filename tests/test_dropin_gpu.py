@@ -20,6 +20,8 @@ pytestmark = pytest.mark.gpu
     (192, 128, 2, 10, [2], {}),
     (192, 128, 3, 8, [1, 2], dict(sao_restore=True)),
     (832, 480, 1, 8, [], {}),
+    (256, 128, 1, 10, [1, 2], dict(cip=True, p_intra=0.4)),       # constrained_intra_pred: the shim hands the PU types over at frame end
+    (192, 128, 2, 8, [1], dict(cip=True, p_intra=0.6)),
 ])
 def test_tables_through_shim_equal_reference_tables(w, h, cfi, bd, refs, kw):
     if oracle_lib.ref_lib() is None or not os.path.exists(oracle_lib.SHIM_SO):

@@ -159,3 +159,34 @@ def test_deblock_thread_code_equals_oracle(emul, w, h, cfi, bd):
             bad = np.argwhere(got[p] != want[p])
             assert len(bad) == 0, (f"seed {seed} plane {p}: {len(bad)} samples differ, first at (y,x)={tuple(bad[0])} "
                                    f"got {got[p][tuple(bad[0])]} want {want[p][tuple(bad[0])]}")
+
+
+@pytest.mark.parametrize("cfi,bd,p_intra,split", [(1, 8, 0.12, 1.0), (1, 10, 0.45, 1.0), (2, 10, 0.3, 2.0), (3, 8, 0.6, 0.5), (1, 12, 0.8, 2.0)])
+def test_constrained_intra_rules_equal_oracle(emul, cfi, bd, p_intra, split):
+    """cip_flags() / cip_substitute() (k_intra_cip.cuh, run by lane 0 of k_intra) against the oracle's restatement of
+    hevcpred_template.c:116-249, for every intra TU of synthetic inter pictures"""
+    from openhevc_b200.synth import FrameSynth, smooth_frame
+    w, h = 320, 192
+    blob, st = FrameSynth(w, h, cfi=cfi, bit_depth=bd, seed=500 + cfi + bd, refs=[1], cur_slot=0, cip=True, p_intra=p_intra, split_bias=split).generate()
+    hdr, secs = W.parse_blob(blob)
+    assert int(hdr["flags"]) & W.FRAME_CIP
+    rng = np.random.default_rng(9)
+    planes = [rng.integers(0, 1 << bd, W.plane_dims(w, h, cfi, p)[::-1]).astype(np.uint16) for p in range(3)]     # noise: any mix-up of two samples shows
+    cip_words = np.ascontiguousarray(blob[int(hdr["cip"]["off"]):int(hdr["cip"]["off"]) + 4 * int(hdr["cip"]["count"])]).view("<u4")
+    o = oracle_lib.lib()
+    pp = (C.c_void_p * 3)(*[p.ctypes.data for p in planes])
+    recs = secs[W.SEC_INTRA]
+    changed = 0
+    for i in range(len(recs)):
+        ot, ol, of = (C.c_int * 65)(), (C.c_int * 65)(), C.c_int()
+        et, el, ef = (C.c_int * 65)(), (C.c_int * 65)(), C.c_int()
+        assert o.orc_debug_cip_refs(np.ascontiguousarray(blob).ctypes.data_as(C.c_void_p), pp, i, ot, ol, C.byref(of)) == 0
+        r = recs[i:i + 1]
+        pl = int(r["plane"][0])
+        assert emul.emul_cip_refs(cip_words.ctypes.data_as(C.c_void_p), r.ctypes.data_as(C.c_void_p), planes[pl].ctypes.data_as(C.c_void_p),
+                                  planes[pl].shape[1], w, h, cfi, bd, et, el, C.byref(ef)) == 0
+        n2 = 2 << int(r["log2"][0])
+        assert of.value == ef.value, f"record {i}: flags {ef.value:#x} != oracle {of.value:#x}"
+        assert list(ot)[:n2 + 1] == list(et)[:n2 + 1] and list(ol)[:n2 + 1] == list(el)[:n2 + 1], f"record {i}: reference arrays differ"
+        changed += of.value != (int(r["flags"][0]) & 31)
+    assert changed > 10, "the constrained-intra rule never removed a candidate: the test picture does not exercise it"

@@ -47,7 +47,10 @@ def test_synth_is_in_decode_order_and_oracle_runs(cfi, bd, refs):
     assert all((a == b).all() for a, b in zip(out, out2))
 
 
-@pytest.mark.parametrize("cfi,bd,refs,kw", [(1, 8, [], {}), (1, 10, [1, 2], dict(weighted=True)), (2, 10, [1, 2], {}), (3, 8, [2], dict(sao_restore=True)), (1, 12, [1], {})])
+@pytest.mark.parametrize("cfi,bd,refs,kw", [(1, 8, [], {}), (1, 10, [1, 2], dict(weighted=True)), (2, 10, [1, 2], {}), (3, 8, [2], dict(sao_restore=True)), (1, 12, [1], {}),
+                                            # constrained_intra_pred (hevcpred_template.c:116-249): inter pictures with 12 % / 45 % intra CUs
+                                            (1, 8, [1, 2], dict(cip=True)), (1, 10, [1], dict(cip=True, p_intra=0.45)), (2, 10, [1, 2], dict(cip=True, p_intra=0.3)),
+                                            (3, 8, [2], dict(cip=True, p_intra=0.3, split_bias=2.0))])
 def test_oracle_equals_reference_at_picture_level(built, cfi, bd, refs, kw):
     """whole synthetic pictures: restatement (oracle/hevc_oracle.c) == the reference's own table functions
     driven by oracle/replay_ref.c -- MC incl. emulated edges, all transforms, intra_pred(), deblock, SAO."""

@@ -40,6 +40,15 @@ def test_weighted_prediction_and_sao_restore():
     run_sequence(256, 192, 1, 10, seeds=[21, 22, 23], weighted=True, sao_restore=True)
 
 
+def test_constrained_intra_pred():
+    """pps->constrained_intra_pred_flag: inter pictures whose intra TUs may only use intra-coded neighbours; the device
+    applies hevcpred_template.c:116-249 itself from the picture's intra bitmap (B200BlobHeader.cip)"""
+    run_sequence(256, 192, 1, 10, seeds=[61, 62, 63], cip=True, p_intra=0.4)
+    run_sequence(256, 128, 1, 8, seeds=[64, 65], cip=True, p_intra=0.15, split_bias=2.0)
+    run_sequence(192, 128, 2, 10, seeds=[66, 67], cip=True, p_intra=0.5)
+    run_sequence(192, 128, 3, 8, seeds=[68, 69], cip=True, p_intra=0.7, split_bias=0.4)
+
+
 def test_intra_only_small_blocks():
     """all-intra with a deep quadtree: the TU-granular wavefront and every predictor / smoothing branch"""
     run_sequence(256, 256, 1, 8, seeds=[31], split_bias=2.0)
@@ -123,6 +132,39 @@ def test_malformed_blobs_are_rejected_not_executed():
         with pytest.raises(B200Error):
             eng.submit(blob[:1000])
         eng.decode(blob)                                        # context still usable
+        # a record that points outside the picture / the coefficient pool / the reference table: caught by the
+        # validation kernel in front of the picture's kernels (k_validate); the picture is not executed
+        hdr, secs = W.parse_blob(blob)
+        for sec, field, value in ((W.SEC_TU8, "x", 124), (W.SEC_TU4, "coeff_off", 0x7fffffff), (W.SEC_INTRA, "mode", 77), (W.SEC_INTRA, "y", 62)):
+            bad = blob.copy()
+            _, bsecs = W.parse_blob(bad)
+            if len(bsecs[sec]) == 0:
+                continue
+            bsecs[sec][field][len(bsecs[sec]) // 2] = value
+            before = eng.decode(blob)
+            with pytest.raises(B200Error, match="rejected on the device"):
+                eng.decode(bad)
+            after = eng.decode(blob)                            # context still usable, and the good picture unchanged
+            assert all((a == b).all() for a, b in zip(before, after))
+    finally:
+        eng.close()
+
+
+def test_malformed_inter_records_are_rejected_on_the_device():
+    w, h = 128, 64
+    eng = FrameEngine(w, h, 1, 8, n_slots=3)
+    try:
+        eng.upload_slot(1, smooth_frame(w, h, 1, 8, 3))
+        blob, _ = FrameSynth(w, h, 1, 8, seed=6, refs=[1], cur_slot=0).generate()
+        good = eng.decode(blob)
+        for field, value in (("ref0", 9), ("w", 40), ("x", 120), ("frac0", 0x7f)):
+            bad = blob.copy()
+            _, bsecs = W.parse_blob(bad)
+            bsecs[W.SEC_MC][field][3] = value
+            with pytest.raises(B200Error, match="rejected on the device"):
+                eng.decode(bad)
+        again = eng.decode(blob)
+        assert all((a == b).all() for a, b in zip(good, again))
     finally:
         eng.close()
 

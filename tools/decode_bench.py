@@ -38,7 +38,7 @@ def run(binary, stream, threads, repeat, passes):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("stream", nargs="?", default=os.path.join(REF, "streams", "c3_4k_33.hevc"))
-    ap.add_argument("--threads", default="1,%d" % min(os.cpu_count() or 1, 16))
+    ap.add_argument("--threads", default="1,%d" % min(len(os.sched_getaffinity(0)), 16))
     ap.add_argument("--repeat", type=int, default=2)
     ap.add_argument("--passes", type=int, default=3, help="decode the file this many times back to back; steady_fps excludes the first pass")
     ap.add_argument("--only", default="", help="ref | b200")

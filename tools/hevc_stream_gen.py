@@ -230,9 +230,10 @@ SIG_CTX_4x4 = [0, 1, 4, 5, 2, 3, 4, 5, 6, 6, 8, 8, 7, 7, 8, 8]
 
 
 class StreamGen:
-    def __init__(self, width, height, bit_depth=8, seed=1, qp=30, sao=True, ctb_log2=6, weighted=False, wpp=False):
+    def __init__(self, width, height, bit_depth=8, seed=1, qp=30, sao=True, ctb_log2=6, weighted=False, wpp=False, cip=False):
         self.W, self.H, self.bd, self.qp, self.sao, self.ctb_log2 = width, height, bit_depth, qp, sao, ctb_log2
         self.weighted = weighted
+        self.cip = cip                      # pps constrained_intra_pred_flag (hevcpred_template.c:116-249)
         self.wpp = wpp                                                    # entropy_coding_sync: one CABAC substream per CTB row
         self.slice_type = 2                                               # 0 B, 1 P, 2 I
         self.nrefs = [0, 0]
@@ -298,7 +299,7 @@ class StreamGen:
         w.u(1, 0)                                                          # cabac_init_present
         w.ue(0); w.ue(0)
         w.se(0)                                                            # init_qp_minus26
-        w.u(1, 0)                                                          # constrained intra pred
+        w.u(1, int(self.cip))                                              # constrained intra pred
         w.u(1, 0)                                                          # transform skip
         w.u(1, 0)                                                          # cu_qp_delta
         w.se(0); w.se(0)                                                   # cb / cr qp offsets
@@ -885,10 +886,11 @@ def main():
     ap.add_argument("--no-sao", action="store_true")
     ap.add_argument("--pattern", default="I", help='picture types after the IDR, e.g. "PB" (low-delay, 2 references)')
     ap.add_argument("--weighted", action="store_true")
+    ap.add_argument("--cip", action="store_true", help="constrained_intra_pred_flag")
     ap.add_argument("--wpp", action="store_true", help="entropy_coding_sync_enabled_flag: one substream per CTB row + entry points")
     a = ap.parse_args()
     verify_tables_against_reference()
-    g = StreamGen(a.width, a.height, a.bit_depth, a.seed, a.qp, sao=not a.no_sao, weighted=a.weighted, wpp=a.wpp)
+    g = StreamGen(a.width, a.height, a.bit_depth, a.seed, a.qp, sao=not a.no_sao, weighted=a.weighted, wpp=a.wpp, cip=a.cip)
     data = g.stream(a.frames, a.pattern)
     open(a.out, "wb").write(data)
     print(f"wrote {a.out}: {len(data)} bytes, {a.frames} pictures {a.width}x{a.height} {a.bit_depth}-bit")
