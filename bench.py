@@ -97,6 +97,12 @@ class ClockSampler:
         for line in self.proc.stdout:
             self.rows.append((time.time(), line.strip()))
 
+    def wait_first(self, timeout=8.0):
+        """nvidia-smi needs up to a few seconds before its first line: the timed region must not start before it"""
+        t_end = time.time() + timeout
+        while self.proc and not self.rows and time.time() < t_end:
+            time.sleep(0.05)
+
     def stop(self, t0, t1):
         if not self.proc:
             return None
@@ -168,7 +174,7 @@ def main():
     os.dup2(2, 1)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=64, help="GOPs (8 pictures) per rank in the timed region")
+    ap.add_argument("--steps", type=int, default=256, help="GOPs (8 pictures) per rank in the timed region")
     ap.add_argument("--warmup", type=int, default=8)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="c3_4k_main10_ra", choices=sorted(WORKLOADS))
@@ -215,9 +221,11 @@ def main():
         torch.cuda.synchronize()
 
     # ---- value: device-resident work lists ----------------------------------------------------------------------
-    FP.run_schedule(backend, rank, world, args.warmup)
-    eng.sync(); barrier()
     sampler = ClockSampler(local) if rank == 0 else None
+    FP.run_schedule(backend, rank, world, args.warmup)
+    if sampler:
+        sampler.wait_first()
+    eng.sync(); barrier()
     l0 = eng.launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     t0 = time.time()

@@ -21,6 +21,7 @@
 #include <unistd.h>
 #include <sys/syscall.h>
 #include <mutex>
+#include <vector>
 #include "../../include/b200hevc.h"
 #include "common.cuh"
 
@@ -83,6 +84,11 @@ struct B200Ctx {
     int ctb_w, ctb_h;
     char err[512];
     int err_code = 0;
+    // B200_TRACE=<file>: timeline of the pictures as they really ran on the lanes (events at the stage boundaries of every
+    // picture, written as CSV when the context is destroyed) -- the overlap between pictures is invisible to per-kernel tools
+    struct TraceRec { cudaEvent_t ev[7]; int lane, arena, poc, n_ref; };
+    std::vector<TraceRec> trace;
+    const char *trace_path = nullptr;
 };
 
 static char g_create_err[512];
@@ -222,6 +228,22 @@ extern "C" void b200_ctx_destroy(B200Ctx *ctx)
     if (!ctx) return;
     cudaSetDevice(ctx->cfg.device);
     cudaDeviceSynchronize();
+    if (ctx->trace_path && !ctx->trace.empty()) {
+        FILE *f = fopen(ctx->trace_path, "w");
+        if (f) {
+            fprintf(f, "picture,lane,arena,poc,n_ref,start_us,mc_us,residual_us,intra_us,deblock_us,sao_us\n");
+            for (size_t i = 0; i < ctx->trace.size(); i++) {
+                const B200Ctx::TraceRec &t = ctx->trace[i];
+                float t0 = 0, d[5] = { 0, 0, 0, 0, 0 };
+                cudaEventElapsedTime(&t0, ctx->trace[0].ev[0], t.ev[0]);
+                for (int k = 0; k < 5; k++) cudaEventElapsedTime(&d[k], t.ev[0], t.ev[k + 1]);
+                fprintf(f, "%zu,%d,%d,%d,%d,%.1f,%.1f,%.1f,%.1f,%.1f,%.1f\n", i, t.lane, t.arena, t.poc, t.n_ref, 1e3 * t0, 1e3 * d[0], 1e3 * d[1], 1e3 * d[2], 1e3 * d[3], 1e3 * d[4]);
+            }
+            fclose(f);
+        }
+        cudaGetLastError();
+    }
+    for (auto &t : ctx->trace) for (int k = 0; k < 6; k++) if (t.ev[k]) cudaEventDestroy(t.ev[k]);
     for (int i = 0; i < MAX_ARENAS; i++) {
         if (ctx->arena[i].dev) cudaFree(ctx->arena[i].dev);
         if (ctx->arena[i].stage) cudaFreeHost(ctx->arena[i].stage);
@@ -281,6 +303,8 @@ static int ctx_init(B200Ctx *ctx)
     ctx->n_lanes = c.n_lanes > 0 ? c.n_lanes : 8;
     if (const char *e = getenv("B200_LANES")) if (atoi(e) > 0) ctx->n_lanes = atoi(e);
     if (ctx->n_lanes > MAX_LANES) ctx->n_lanes = MAX_LANES;
+    ctx->trace_path = getenv("B200_TRACE");
+    if (ctx->trace_path) ctx->trace.reserve(4096);      // TraceRec pointers stay valid while a picture is being submitted
     for (int p = 0; p < 3; p++) ctx->flag_stride[p] = (ctx->pw[p] + 3) / 4 + 1;
     for (int l = 0; l < ctx->n_lanes; l++) {
         Lane &L = ctx->lane[l];
@@ -567,29 +591,43 @@ extern "C" int b200_frame_execute_ex(B200Ctx *ctx, int arena, int cur_slot, cons
     CU(cudaStreamWaitEvent(st, a.ev_uploaded, 0));
     CU(cudaMemsetAsync(L.counter, 0, 2 * sizeof(uint32_t), st));          // K3 ticket + this picture's validation gate
     if (validate_mode() == 1) ctx->launches += launch_validate(st, a.dev, h, ctx->pw, ctx->ph, ctx->arena_bytes, L.counter);
+    B200Ctx::TraceRec *tr = nullptr;
+    if (ctx->trace_path && ctx->trace.size() < 4096) {
+        ctx->trace.emplace_back();
+        tr = &ctx->trace.back();
+        tr->lane = li; tr->arena = arena; tr->poc = h.poc; tr->n_ref = h.n_ref;
+        for (int k = 0; k < 7; k++) tr->ev[k] = nullptr;
+        for (int k = 0; k < 6; k++) CU(cudaEventCreate(&tr->ev[k]));
+        CU(cudaEventRecord(tr->ev[0], st));
+    }
     if (pf) CU(cudaEventRecord(ctx->prof[0], st));
     // K1 inter
     ctx->launches += launch_mc(st, (const B200McRec *)(a.dev + h.sec[B200_SEC_MC].off), (int)h.sec[B200_SEC_MC].count, (int)h.mc_big_count, cur, ctx->dpb_desc_dev, rt, bd, L.counter);
     if (pf) CU(cudaEventRecord(ctx->prof[1], st));
+    if (tr) CU(cudaEventRecord(tr->ev[1], st));
     // K2 residual
     const int16_t *pool = (const int16_t *)(a.dev + h.sec[B200_SEC_COEFF].off);
     const B200TuRec *tu[4]; int ntu[4];
     for (int s = 0; s < 4; s++) { tu[s] = (const B200TuRec *)(a.dev + h.sec[B200_SEC_TU4 + s].off); ntu[s] = (int)h.sec[B200_SEC_TU4 + s].count; }
     ctx->launches += launch_residual(st, tu, ntu, pool, L.parked, cur, bd, L.counter);
     if (pf) CU(cudaEventRecord(ctx->prof[2], st));
+    if (tr) CU(cudaEventRecord(tr->ev[2], st));
     // K3 intra
     ctx->launches += launch_intra(st, (const B200IntraRec *)(a.dev + h.sec[B200_SEC_INTRA].off), (int)h.sec[B200_SEC_INTRA].count, L.parked, cur, bd,
                                   L.flags, ctx->flag_stride, L.counter,
                                   (h.flags & B200_FRAME_CIP) && h.cip.count ? (const uint32_t *)(a.dev + h.cip.off) : nullptr, &a.cip_hdr, ctx->cfg.chroma_format_idc);
     if (pf) CU(cudaEventRecord(ctx->prof[3], st));
+    if (tr) CU(cudaEventRecord(tr->ev[3], st));
     // K4 deblock
     if (h.sec[B200_SEC_DBK].count)
         ctx->launches += launch_deblock(st, (const uint16_t *)(a.dev + h.sec[B200_SEC_DBK].off), ctx->dbk, cur, bd);
     if (pf) CU(cudaEventRecord(ctx->prof[4], st));
+    if (tr) CU(cudaEventRecord(tr->ev[4], st));
     // K5 SAO
     if (has_sao)
         ctx->launches += launch_sao(st, (const B200SaoRec *)(a.dev + h.sec[B200_SEC_SAO].off), cur, out, bd, ctx->cfg.log2_ctb_size, ctx->ctb_w, ctx->ctb_h, ctx->cfg.chroma_format_idc);
     if (pf) { CU(cudaEventRecord(ctx->prof[5], st)); ctx->prof_valid = true; }
+    if (tr) CU(cudaEventRecord(tr->ev[5], st));
     CU(cudaEventRecord(a.ev_done[li], st));
     a.done_mask |= 1u << li;
     { int rc = slot_release(ctx, h.cur_slot, st, li, true); if (rc) return rc; }

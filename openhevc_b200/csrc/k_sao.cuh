@@ -37,12 +37,23 @@ struct SaoCtb {                 // one decoded B200SaoRec + the geometry of its 
     int off[5];
     int x0, y0, w, h;           // CTB origin and (picture-clipped) size in samples of the plane
 };
+HD SaoCtb sao_decode(const uint4 rq, const PlaneDesc &sp, int cx, int cy, int lw, int lh)
+{
+    SaoCtb t;
+    t.type = rq.x & 0xff; t.cls = (rq.x >> 8) & 0xff; t.borders = (rq.x >> 16) & 0xff; t.edges = rq.x >> 24; t.variant = rq.y & 0xff;
+    t.off[0] = (int16_t)(rq.y >> 16); t.off[1] = (int16_t)(rq.z & 0xffff); t.off[2] = (int16_t)(rq.z >> 16); t.off[3] = (int16_t)(rq.w & 0xffff); t.off[4] = (int16_t)(rq.w >> 16);
+    t.x0 = cx << lw; t.y0 = cy << lh;
+    t.w = imin(1 << lw, sp.w - t.x0); t.h = imin(1 << lh, sp.h - t.y0);
+    return t;
+}
 
 // The reference rules for one row of 8 samples, sample by sample (edge offset only): used for the outermost rows /
-// columns of CTBs that carry border or restore flags, and for CTBs whose offsets do not fit the packed table.
+// columns of CTBs that carry border or restore flags, and for CTBs whose offsets do not fit the packed table.  Rare, and
+// deliberately self-contained (it reads the record again) so that the packed path carries none of its state in registers.
 template <typename PIX>
-__host__ __device__ __noinline__ void sao_row_exact(const PlaneDesc &sp, const SaoCtb &t, int gx, int gy, int maxv, uint32_t (&outp)[4])
+__host__ __device__ __noinline__ void sao_row_exact(const PlaneDesc &sp, const B200SaoRec *rec, int cx, int cy, int lwlh, int gx, int gy, int maxv, uint32_t (&outp)[4])
 {
+    const SaoCtb t = sao_decode(LDG128(rec), sp, cx, cy, lwlh & 0xff, lwlh >> 8);
     int c[8], out[8];
     const int yu = imax(gy - 1, 0), yd = imin(gy + 1, sp.h - 1);
     int A[8], Bq[8];
@@ -104,45 +115,27 @@ HD uint32_t sao_apply2(uint32_t c, uint32_t X, uint32_t tab_lo, uint32_t tab_hi,
 // Edge offset of class CLS for the 8 x SAO_R samples of one thread.  a / b = the two neighbours of the class
 // (hevcdsp_template.c:372-431: pos[][] = {{-1,0},{1,0}}, {{0,-1},{0,1}}, {{-1,-1},{1,1}}, {{1,-1},{-1,1}}).
 template <typename PIX, int CLS>
-HD void sao_edge_rows(const PlaneDesc &sp, const PlaneDesc &dp, const SaoCtb &t, int gx, int gy0, int nvalid, int nrows, int maxv, bool fits)
+HD void sao_edge_rows(const PlaneDesc &sp, const PlaneDesc &dp, const B200SaoRec *rec, int cx, int cy, int lwlh, int gx, int gy0, int nvalid, int nrows,
+                      int maxv, uint32_t tab_lo, uint32_t tab_hi, int exact_rows,
+                      const uint32_t (&c)[SAO_R + 2][4], const uint32_t (&sl)[SAO_R + 2], const uint32_t (&sr)[SAO_R + 2])
 {
-    const int xs = gx - t.x0, ys = gy0 - t.y0;
     const uint32_t maxv2 = (uint32_t)maxv * 0x10001u;
-    // rows / columns the border rule ("offset 0") or the restore rule can touch: x == 0, x >= w - 2, y == 0, y >= h - 2
-    const bool b_l = t.borders & 1, b_t = t.borders & 2, b_r = t.borders & 4, b_b = t.borders & 8, var = t.variant != 0;
-    const bool col_exact = !fits || (((b_l && CLS != 1) || var) && xs == 0) || (((b_r && CLS != 1) || var) && xs + 8 >= t.w - 1);
-    const bool top_exact = (b_t && CLS != 0) || var, bot_exact = (b_b && CLS != 0) || var;
     constexpr int JLO = CLS == 0 ? 1 : 0, JHI = CLS == 0 ? SAO_R : SAO_R + 1;
-    uint32_t c[SAO_R + 2][4], m[SAO_R + 2][4];
-    uint32_t mL[SAO_R + 2], mR[SAO_R + 2];
-    const int xl = imax(gx - 1, 0), xr = imin(gx + 8, sp.w - 1);
+    uint32_t m[SAO_R + 2][4], mL[SAO_R + 2], mR[SAO_R + 2];
 #pragma unroll
     for (int j = JLO; j <= JHI; j++) {
-        const int yy = imin(imax(gy0 + j - 1, 0), sp.h - 1);
-        load8p<PIX>(sp, gx, yy, c[j]);
-        // the row serves as `a` row (for the row below it / itself) and / or as `b` row (for the row above it / itself)
-        const bool is_a = CLS == 0 ? true : j <= SAO_R - 1, is_b = CLS == 0 ? true : j >= 2;
-        const bool need_l = (CLS == 0) || (CLS == 2 && is_a) || (CLS == 3 && is_b);
-        const bool need_r = (CLS == 0) || (CLS == 2 && is_b) || (CLS == 3 && is_a);
-        if (need_l) mL[j] = (2u + ~(uint32_t)*px_ptr<PIX>(sp, xl, yy)) << 16;     // 1 - left neighbour, in the high half
-        if (need_r) mR[j] = 2u + ~(uint32_t)*px_ptr<PIX>(sp, xr, yy);               // 1 - right neighbour (only the low half is used)
-    }
-#pragma unroll
-    for (int j = JLO; j <= JHI; j++) {
-        if (nvalid < 8) c[j][2] = c[j][3] = prmt32(c[j][1], 0, 0x3232);       // beyond the plane: replicate, like clamped addressing
 #pragma unroll
         for (int k = 0; k < 4; k++) m[j][k] = vadd2(~c[j][k], 0x00020002u);   // 1 - sample, per half
+        mL[j] = (2u + ~sl[j]) << 16;                                           // 1 - left neighbour, in the high half
+        mR[j] = 2u + ~sr[j];                                                   // 1 - right neighbour (only the low half is used)
     }
-    const uint32_t tab_lo = (uint32_t)((t.off[1] + 128) & 0xff) | ((uint32_t)((t.off[2] + 128) & 0xff) << 8) |
-                            ((uint32_t)((t.off[0] + 128) & 0xff) << 16) | ((uint32_t)((t.off[3] + 128) & 0xff) << 24);
-    const uint32_t tab_hi = (uint32_t)((t.off[4] + 128) & 0xff);              // edge_idx[] = {1,2,0,3,4}
 #pragma unroll
     for (int r = 0; r < SAO_R; r++) {
         if (r < nrows) {
-            const int j = r + 1, y = ys + r;
+            const int j = r + 1;
             uint32_t o[4];
-            if (col_exact || (top_exact && y == 0) || (bot_exact && y >= t.h - 2)) {
-                sao_row_exact<PIX>(sp, t, gx, gy0 + r, maxv, o);
+            if ((exact_rows >> r) & 1) {
+                sao_row_exact<PIX>(sp, rec, cx, cy, lwlh, gx, gy0 + r, maxv, o);
             } else {
                 uint32_t A[4], Bn[4];
                 const int ja = CLS == 0 ? j : j - 1, jb = CLS == 0 ? j : j + 1;     // compile-time after unrolling
@@ -188,26 +181,36 @@ HD void sao_thread(const B200SaoRec *__restrict__ grid, const FrameDesc &src, co
     const int gx = ((tx << lS) + (lane & ((1 << lS) - 1))) * 8;
     const int gy0 = ((ty << (5 - lS)) + (lane >> lS)) * SAO_R;
     if (gx >= sp.w || gy0 >= sp.h) return;
-    SaoCtb t;
     const int cx = gx >> lw, cy = gy0 >> lh;
-    {
-        const uint4 rq = LDG128(grid + (plane * ctb_h + cy) * ctb_w + cx);
-        t.type = rq.x & 0xff; t.cls = (rq.x >> 8) & 0xff; t.borders = (rq.x >> 16) & 0xff; t.edges = rq.x >> 24; t.variant = rq.y & 0xff;
-        t.off[0] = (int16_t)(rq.y >> 16); t.off[1] = (int16_t)(rq.z & 0xffff); t.off[2] = (int16_t)(rq.z >> 16); t.off[3] = (int16_t)(rq.w & 0xffff); t.off[4] = (int16_t)(rq.w >> 16);
-        t.x0 = cx << lw; t.y0 = cy << lh;
-        t.w = imin(1 << lw, sp.w - t.x0); t.h = imin(1 << lh, sp.h - t.y0);
-    }
+    const B200SaoRec *rec = grid + (plane * ctb_h + cy) * ctb_w + cx;
+    const uint4 rq = LDG128(rec);
+    // The rows are fetched BEFORE the record is looked at: whatever the CTB's SAO type, the SAO_R rows are needed (even
+    // "off" copies them), and the row above / below and the two outer columns are needed by 3 of the 4 edge classes --
+    // issuing them now puts ONE memory latency on the thread's critical path instead of two (record, then rows).
     const int nvalid = imin(8, sp.w - gx);
+    uint32_t c[SAO_R + 2][4], sl[SAO_R + 2], sr[SAO_R + 2];
+    {
+        const int xl = imax(gx - 1, 0), xr = imin(gx + 8, sp.w - 1);
+#pragma unroll
+        for (int j = 0; j <= SAO_R + 1; j++) {
+            const int yy = imin(imax(gy0 + j - 1, 0), sp.h - 1);
+            load8p<PIX>(sp, gx, yy, c[j]);
+            sl[j] = *px_ptr<PIX>(sp, xl, yy);
+            sr[j] = *px_ptr<PIX>(sp, xr, yy);
+        }
+        if (nvalid < 8) {                          // beyond the plane: replicate, like clamped addressing
+#pragma unroll
+            for (int j = 0; j <= SAO_R + 1; j++) c[j][2] = c[j][3] = prmt32(c[j][1], 0, 0x3232);
+        }
+    }
+    const SaoCtb t = sao_decode(rq, sp, cx, cy, lw, lh);
     const int nrows = imin(SAO_R, sp.h - gy0);
     const int maxv = (1 << bd) - 1;
     const uint32_t maxv2 = (uint32_t)maxv * 0x10001u;
 
     if (t.type != B200_SAO_BAND && t.type != B200_SAO_EDGE) {           // no SAO in this CTB: copy through
-        for (int r = 0; r < nrows; r++) {
-            uint32_t c[4];
-            load8p<PIX>(sp, gx, gy0 + r, c);
-            store8p<PIX>(dp, gx, gy0 + r, c, nvalid);
-        }
+#pragma unroll
+        for (int r = 0; r < SAO_R; r++) if (r < nrows) store8p<PIX>(dp, gx, gy0 + r, c[r + 1], nvalid);
         return;
     }
     bool fits = true;                                                   // offsets representable in the packed table?
@@ -221,27 +224,29 @@ HD void sao_thread(const B200SaoRec *__restrict__ grid, const FrameDesc &src, co
                                     ((uint32_t)((t.off[3] + 128) & 0xff) << 16) | ((uint32_t)((t.off[4] + 128) & 0xff) << 24);
             const uint32_t tab_hi = 128u;                                   // entry 4: no offset
             const uint32_t nb = (uint32_t)((32 - t.cls) & 31) * 0x10001u;   // t.cls = band_position for band CTBs
-            for (int r = 0; r < nrows; r++) {
-                uint32_t c[4], o[4];
-                load8p<PIX>(sp, gx, gy0 + r, c);
+#pragma unroll
+            for (int r = 0; r < SAO_R; r++) {
+                if (r >= nrows) break;
+                uint32_t o[4];
 #pragma unroll
                 for (int k = 0; k < 4; k++) {
-                    const uint32_t band = (c[k] >> sh) & 0x001f001fu;
+                    const uint32_t band = (c[r + 1][k] >> sh) & 0x001f001fu;
                     const uint32_t kk = vminu2((band + nb) & 0x001f001fu, 0x00040004u);      // (band - position) & 31, 4 = outside
-                    o[k] = sao_apply2(c[k], kk, tab_lo, tab_hi, maxv2);
+                    o[k] = sao_apply2(c[r + 1][k], kk, tab_lo, tab_hi, maxv2);
                 }
                 store8p<PIX>(dp, gx, gy0 + r, o, nvalid);
             }
         } else {
-            for (int r = 0; r < nrows; r++) {
-                uint32_t c[4], o[4];
-                load8p<PIX>(sp, gx, gy0 + r, c);
+#pragma unroll
+            for (int r = 0; r < SAO_R; r++) {
+                if (r >= nrows) break;
+                uint32_t o[4];
 #pragma unroll
                 for (int k = 0; k < 4; k++) {
                     uint32_t res = 0;
 #pragma unroll
                     for (int hlf = 0; hlf < 2; hlf++) {
-                        const int v = (c[k] >> (16 * hlf)) & 0xffff;
+                        const int v = (c[r + 1][k] >> (16 * hlf)) & 0xffff;
                         const int kk = ((v >> sh) - t.cls) & 31;
                         const int ov = kk < 4 ? clip3i(v + (kk == 0 ? t.off[1] : kk == 1 ? t.off[2] : kk == 2 ? t.off[3] : t.off[4]), 0, maxv) : v;
                         res |= (uint32_t)ov << (16 * hlf);
@@ -255,11 +260,26 @@ HD void sao_thread(const B200SaoRec *__restrict__ grid, const FrameDesc &src, co
     }
 
     // ---- edge offset ----
+    // rows / columns the border rule ("offset 0") or the restore rule can touch: x == 0, x >= w - 2, y == 0, y >= h - 2
+    int exact_rows;
+    {
+        const int cls = t.cls, xs = gx - t.x0, ys = gy0 - t.y0;
+        const bool b_l = t.borders & 1, b_t = t.borders & 2, b_r = t.borders & 4, b_b = t.borders & 8, var = t.variant != 0;
+        const bool col_exact = !fits || (((b_l && cls != 1) || var) && xs == 0) || (((b_r && cls != 1) || var) && xs + 8 >= t.w - 1);
+        const bool top_exact = (b_t && cls != 0) || var, bot_exact = (b_b && cls != 0) || var;
+        exact_rows = col_exact ? (1 << SAO_R) - 1 : 0;
+#pragma unroll
+        for (int r = 0; r < SAO_R; r++) if ((top_exact && ys + r == 0) || (bot_exact && ys + r >= t.h - 2)) exact_rows |= 1 << r;
+    }
+    const uint32_t tab_lo = (uint32_t)((t.off[1] + 128) & 0xff) | ((uint32_t)((t.off[2] + 128) & 0xff) << 8) |
+                            ((uint32_t)((t.off[0] + 128) & 0xff) << 16) | ((uint32_t)((t.off[3] + 128) & 0xff) << 24);
+    const uint32_t tab_hi = (uint32_t)((t.off[4] + 128) & 0xff);        // edge_idx[] = {1,2,0,3,4}
+    const int lwlh = lw | (lh << 8);
     switch (t.cls) {
-    case 0:  sao_edge_rows<PIX, 0>(sp, dp, t, gx, gy0, nvalid, nrows, maxv, fits); break;
-    case 1:  sao_edge_rows<PIX, 1>(sp, dp, t, gx, gy0, nvalid, nrows, maxv, fits); break;
-    case 2:  sao_edge_rows<PIX, 2>(sp, dp, t, gx, gy0, nvalid, nrows, maxv, fits); break;
-    default: sao_edge_rows<PIX, 3>(sp, dp, t, gx, gy0, nvalid, nrows, maxv, fits); break;
+    case 0:  sao_edge_rows<PIX, 0>(sp, dp, rec, cx, cy, lwlh, gx, gy0, nvalid, nrows, maxv, tab_lo, tab_hi, exact_rows, c, sl, sr); break;
+    case 1:  sao_edge_rows<PIX, 1>(sp, dp, rec, cx, cy, lwlh, gx, gy0, nvalid, nrows, maxv, tab_lo, tab_hi, exact_rows, c, sl, sr); break;
+    case 2:  sao_edge_rows<PIX, 2>(sp, dp, rec, cx, cy, lwlh, gx, gy0, nvalid, nrows, maxv, tab_lo, tab_hi, exact_rows, c, sl, sr); break;
+    default: sao_edge_rows<PIX, 3>(sp, dp, rec, cx, cy, lwlh, gx, gy0, nvalid, nrows, maxv, tab_lo, tab_hi, exact_rows, c, sl, sr); break;
     }
 }
 

@@ -157,7 +157,7 @@ def test_malformed_inter_records_are_rejected_on_the_device():
         eng.upload_slot(1, smooth_frame(w, h, 1, 8, 3))
         blob, _ = FrameSynth(w, h, 1, 8, seed=6, refs=[1], cur_slot=0).generate()
         good = eng.decode(blob)
-        for field, value in (("ref0", 9), ("w", 40), ("x", 120), ("frac0", 0x7f)):
+        for field, value in (("ref0", 9), ("w", 40), ("x", 127), ("frac0", 0x7f)):
             bad = blob.copy()
             _, bsecs = W.parse_blob(bad)
             bsecs[W.SEC_MC][field][3] = value

@@ -21,3 +21,7 @@ if [ -n "$WITH_NCU_FULL" ]; then   # one B picture (blob 4), second repetition: 
   timeout 600 ncu --set full --clock-control none --import-source on -c 26 -o gpurun_out/${tag}_bpic python tools/run_pictures.py --only 4 --reps 2 > gpurun_out/${tag}_ncu_full.log 2>&1
 fi
 if [ -n "$WITH_PCIE" ]; then B200_VERBOSE=1 python tools/pcie_probe.py > gpurun_out/${tag}_pcie.txt 2>&1; cat gpurun_out/${tag}_pcie.txt; cat /sys/fs/cgroup/cpu.max >> gpurun_out/${tag}_pcie.txt 2>&1; nproc >> gpurun_out/${tag}_pcie.txt; fi
+if [ -n "$WITH_TRACE" ]; then
+  B200_TRACE=gpurun_out/${tag}_trace.csv timeout 300 python bench.py --steps 24 --warmup 4 --no-cpu-baseline > gpurun_out/${tag}_trace_bench.json 2>> gpurun_out/${tag}_bench.err
+  python tools/timeline.py gpurun_out/${tag}_trace.csv --from 64 --to 224 | tee gpurun_out/${tag}_timeline.txt
+fi
