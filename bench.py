@@ -335,7 +335,7 @@ def main():
                 "dtype": "u16" if wl["bit_depth"] > 8 else "u8", "data": "synthetic",
                 "config": {"workload": args.workload, "picture": f"{wl['width']}x{wl['height']} 4:2:0 {wl['bit_depth']}-bit", "gop": "hierarchical-B 8, intra period 32",
                            "step": "1 GOP (8 pictures) per rank", "lanes": int(os.environ.get("B200_LANES", "8")), "parallelism": f"frame-parallel x{world}, anchor broadcast over NCCL" if world > 1 else "single GPU",
-                           "l2": "inputs larger than L2: 9 work lists (%.0f MB) + 23-slot DPB (%.0f MB) cycled" % (sum(b.nbytes for b in blobs) / 1e6, FP.N_SLOTS * slot_bytes / 1e6)},
+                           "l2": "inputs larger than L2: 9 work lists (%.0f MB) + %d-slot DPB (%.0f MB) cycled" % (sum(b.nbytes for b in blobs) / 1e6, FP.N_SLOTS, FP.N_SLOTS * slot_bytes / 1e6)},
                 "mpixels_per_s": fps * wl["width"] * wl["height"] / 1e6,
                 "gpu_launches": int(launches), "clocks": clocks,
                 "e2e": {"value": e2e_fps, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h), "steps": e2e_steps,

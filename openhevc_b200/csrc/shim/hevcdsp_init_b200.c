@@ -467,6 +467,15 @@ int b200_frame_begin(HEVCContext *s)
     if (g.err) return g.err;
     if (g.in_frame == 1) { deactivate(); ticket_release(); }   /* previous picture of this thread was abandoned */
     g.in_frame = 0;
+    /* tools whose pixel work bypasses the tables and is not done on the device yet: refuse, never guess */
+    if (s->sps->chroma_array_type == 3 && s->pps->cross_component_prediction_enabled_flag) {
+        fail(B200_ENOTSUP, "cross_component_prediction (4:4:4, hevc.c:1325-1327) is not supported by the B200 path");
+        return g.err;
+    }
+    if (s->sps->sao_enabled && (s->pps->transquant_bypass_enable_flag || (s->sps->pcm.loop_filter_disable_flag && s->sps->pcm_enabled_flag))) {
+        fail(B200_ENOTSUP, "SAO together with transquant_bypass / pcm_loop_filter_disabled (restore_tqb_pixels, hevc_filter.c:163-193) is not supported by the B200 path");
+        return g.err;
+    }
     pthread_mutex_lock(&G.mu);
     const int erc = ensure_ctx(s);
     if (!erc) g.ticket = G.next_ticket++;

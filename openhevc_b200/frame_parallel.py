@@ -17,7 +17,7 @@ from dataclasses import dataclass
 from typing import List
 
 N_ANCHOR_SLOTS = 16            # anchors rotate through slots 0..15: a slot is reused 16 GOPs later
-N_B_SLOTS = 7
+N_B_SLOTS = 14                 # two sets of seven: consecutive GOPs do not wait for each other's B pictures (WAR on the slots)
 N_SLOTS = N_ANCHOR_SLOTS + N_B_SLOTS
 INTRA_PERIOD_GOPS = 4          # every 4th anchor is an I picture (intra period 32 pictures)
 
@@ -41,7 +41,7 @@ def anchor_slot(g):
 def gop_pictures(g):
     """decode-order pictures of GOP g (POC order 8g+{8,4,2,6,1,3,5,7}) with their DPB placement"""
     a_prev, a_cur = anchor_slot(g - 1), anchor_slot(g)
-    b = [N_ANCHOR_SLOTS + k for k in range(N_B_SLOTS)]     # b4, b2, b6, b1, b3, b5, b7
+    b = [N_ANCHOR_SLOTS + 7 * (g & 1) + k for k in range(7)]     # b4, b2, b6, b1, b3, b5, b7
     intra = g % INTRA_PERIOD_GOPS == 0
     return [
         Picture(BLOB_ANCHOR_I if intra else BLOB_ANCHOR_P, a_cur, [] if intra else [a_prev], True),

@@ -4,7 +4,7 @@
 tag=${1:-r}
 mkdir -p gpurun_out
 nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm --format=csv,noheader > gpurun_out/${tag}_gpu.txt 2>&1
-( time timeout 900 python -m pytest tests -m gpu -x -q --durations=8 ) > gpurun_out/${tag}_pytest.log 2>&1
+( time timeout 900 python -m pytest tests -m gpu -x -q --durations=8 ${PYTEST_K:+-k "$PYTEST_K"} ) > gpurun_out/${tag}_pytest.log 2>&1
 tail -15 gpurun_out/${tag}_pytest.log
 timeout 600 python bench.py > gpurun_out/${tag}_bench.json 2> gpurun_out/${tag}_bench.err
 cat gpurun_out/${tag}_bench.json
