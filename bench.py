@@ -269,9 +269,20 @@ def main():
     stages = {k: {"ms": stage_ms[k], "algorithmic_bytes": abytes[k], "gbps": abytes[k] / (stage_ms[k] * 1e-3) / 1e9 if stage_ms[k] > 0 else None}
               for k in abytes}
     dom = max(abytes, key=lambda k: stage_ms[k])
+    # DRAM traffic of the dominant kernel from the committed ncu capture (profiles/ncu_traffic.json: one B picture, per launch)
+    traffic, traffic_note = None, None
+    try:
+        tj = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))
+        kname = {"mc": "k_mc<unsigned short, 32>", "residual": "k_residual<unsigned short, 16>", "intra": "k_intra<unsigned short>",
+                 "deblock": "k_deblock<unsigned short>", "sao": "k_sao<unsigned short>"}[dom]
+        if wl["bit_depth"] > 8 and wl["width"] == 3840 and kname in tj["kernels"]:
+            traffic = tj["kernels"][kname]["dram_bytes_per_launch"]
+            traffic_note = "dram read+write bytes per launch of " + kname + " on a 4K B picture, " + tj["source"]
+    except Exception:
+        pass
     roofline = {"bound": "hbm", "kernel": {"mc": "k_mc", "residual": "k_residual", "intra": "k_intra", "deblock": "k_deblock", "sao": "k_sao"}[dom],
                 "achieved": stages[dom]["gbps"], "peak": peak, "unit": "GB/s", "frac": stages[dom]["gbps"] / peak, "peak_source": peak_src,
-                "traffic": None, "share_of_step": stage_ms[dom] / stage_ms["total"], "stages": stages,
+                "traffic": traffic, "traffic_note": traffic_note, "share_of_step": stage_ms[dom] / stage_ms["total"], "stages": stages,
                 "whole_picture": {"algorithmic_bytes": sum(abytes.values()), "ms": stage_ms["total"],
                                   "gbps": sum(abytes.values()) / (stage_ms["total"] * 1e-3) / 1e9}}
 

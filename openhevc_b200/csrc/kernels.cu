@@ -173,19 +173,21 @@ template <int N> __device__ __forceinline__ void dst4_1d(const int (&v)[N], int 
     }
 }
 
+#define RESID_TILE_INTS (32 * 33)      // per warp: the largest padded tile (one 32x32 TU)
+
+// One warp's share of the TUs of size N: `blk` = index of the 4-warp block within the list of this size.
 template <typename PIX, int N>
-__global__ void __launch_bounds__(128) k_residual(const B200TuRec *__restrict__ recs, int count, const int16_t *__restrict__ pool,
-                                                  int16_t *__restrict__ parked, FrameDesc f, int bd, const uint32_t *__restrict__ gate)
+__device__ __forceinline__ void residual_warp(const B200TuRec *__restrict__ recs, int count, const int16_t *__restrict__ pool,
+                                              int16_t *__restrict__ parked, const FrameDesc &f, int bd, int *tile_w, int blk)
 {
-    if (__ldg(gate + 1)) return;         // the picture's work list failed validation (k_validate)
     constexpr int G = 32 / N;            // TUs per warp
     constexpr int TS = N * (N + 1);      // padded tile
-    __shared__ int tile_s[4][G * TS];
+    static_assert(G * TS <= RESID_TILE_INTS, "tile buffer too small");
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int g = lane / N, col = lane % N;
-    const int ti = (blockIdx.x * 4 + warp) * G + g;
+    const int ti = (blk * 4 + warp) * G + g;
     const bool active = ti < count;
-    int *tile = tile_s[warp] + g * TS;
+    int *tile = tile_w + g * TS;
 
     B200TuRec rec;
     if (active) {
@@ -302,6 +304,33 @@ __global__ void __launch_bounds__(128) k_residual(const B200TuRec *__restrict__ 
         }
     }
 }
+
+// All four TU sizes in ONE launch: separate launches ran back to back although none of them fills the machine (the
+// 32x32 list is a few hundred CTAs at 14 % occupancy for 23 us).  Largest TUs first, so that the long-running warps
+// start first and the small ones fill in behind them.
+struct ResidualLists {
+    const B200TuRec *recs[4];            // 4x4, 8x8, 16x16, 32x32
+    int count[4];
+    int nblk[4];                         // CTAs of 4 warps per list
+};
+
+template <typename PIX>
+__global__ void __launch_bounds__(128) k_residual(ResidualLists L, const int16_t *__restrict__ pool, int16_t *__restrict__ parked, FrameDesc f, int bd,
+                                                  const uint32_t *__restrict__ gate)
+{
+    if (__ldg(gate + 1)) return;         // the picture's work list failed validation (k_validate)
+    __shared__ int tile_s[4][RESID_TILE_INTS];
+    int *tile_w = tile_s[threadIdx.x >> 5];
+    int b = blockIdx.x;
+    if (b < L.nblk[3]) { residual_warp<PIX, 32>(L.recs[3], L.count[3], pool, parked, f, bd, tile_w, b); return; }
+    b -= L.nblk[3];
+    if (b < L.nblk[2]) { residual_warp<PIX, 16>(L.recs[2], L.count[2], pool, parked, f, bd, tile_w, b); return; }
+    b -= L.nblk[2];
+    if (b < L.nblk[1]) { residual_warp<PIX, 8>(L.recs[1], L.count[1], pool, parked, f, bd, tile_w, b); return; }
+    b -= L.nblk[1];
+    residual_warp<PIX, 4>(L.recs[0], L.count[0], pool, parked, f, bd, tile_w, b);
+}
+
 
 // --------------------------------------------------------------------------------------------
 // K1: inter prediction.  One warp per tile record (<= 256 samples, <= 32 wide).
@@ -1035,12 +1064,16 @@ int launch_mc(cudaStream_t st, const B200McRec *recs, int count, int n_big, cons
 template <typename PIX>
 static int launch_residual_t(cudaStream_t st, const B200TuRec *const recs[4], const int counts[4], const int16_t *pool, int16_t *parked, const FrameDesc &cur, int bd, const uint32_t *gate)
 {
-    int n = 0;
-    if (counts[0]) { k_residual<PIX, 4><<<(counts[0] + 31) / 32, 128, 0, st>>>(recs[0], counts[0], pool, parked, cur, bd, gate); n++; }
-    if (counts[1]) { k_residual<PIX, 8><<<(counts[1] + 15) / 16, 128, 0, st>>>(recs[1], counts[1], pool, parked, cur, bd, gate); n++; }
-    if (counts[2]) { k_residual<PIX, 16><<<(counts[2] + 7) / 8, 128, 0, st>>>(recs[2], counts[2], pool, parked, cur, bd, gate); n++; }
-    if (counts[3]) { k_residual<PIX, 32><<<(counts[3] + 3) / 4, 128, 0, st>>>(recs[3], counts[3], pool, parked, cur, bd, gate); n++; }
-    return n;
+    ResidualLists L;
+    int total = 0;
+    for (int k = 0; k < 4; k++) {
+        const int per_cta = 4 * (32 >> (k + 2));         // 4 warps x (32 / N) TUs
+        L.recs[k] = recs[k]; L.count[k] = counts[k]; L.nblk[k] = (counts[k] + per_cta - 1) / per_cta;
+        total += L.nblk[k];
+    }
+    if (!total) return 0;
+    k_residual<PIX><<<total, 128, 0, st>>>(L, pool, parked, cur, bd, gate);
+    return 1;
 }
 int launch_residual(cudaStream_t st, const B200TuRec *const recs[4], const int counts[4], const int16_t *pool, int16_t *parked, const FrameDesc &cur, int bd, const uint32_t *gate)
 {

@@ -36,7 +36,7 @@ def full(rep, out, keys):
                     f.write(f"{k} [{rows[1][i]}] = {r[i]}\n")
 
 
-KEYS = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum", "dram__throughput.avg.pct_of_peak", "gpu__dram_throughput", "lts__t_bytes.sum", "lts__t_sector_hit_rate",
+KEYS = ["gpu__time_duration.sum", "smsp__issue_active.avg.pct", "sm__pipe_alu_cycles_active.avg.pct", "sm__pipe_fma_cycles_active.avg.pct", "dram__bytes_read.sum", "dram__bytes_write.sum", "dram__throughput.avg.pct_of_peak", "gpu__dram_throughput", "lts__t_bytes.sum", "lts__t_sector_hit_rate",
         "launch__registers_per_thread", "launch__occupancy_limit", "sm__warps_active.avg.pct_of_peak", "sm__throughput.avg.pct", "smsp__inst_executed.sum", "sm__inst_executed_pipe_lsu",
         "l1tex__t_sector_hit_rate", "smsp__cycles_active.avg", "sm__pipe_tensor_cycles_active", "launch__shared_mem_per_block", "smsp__warp_issue_stalled"]
 if __name__ == "__main__":
