@@ -337,8 +337,7 @@ __global__ void __launch_bounds__(128) k_residual(ResidualLists L, const int16_t
 // Reference window staged in shared memory with clamped addressing (== emulated_edge_mc),
 // separable FIR with the 14-bit intermediate of the reference.
 // --------------------------------------------------------------------------------------------
-#define MC_WIN_MAX 640      // (32+7+1) x 15 = 600, (16+7+1) x 23 = 552, + slack for padded reads
-#define MC_TMP_MAX 512      // 15 x 32, 23 x 16
+#include "k_mc.cuh"
 
 __device__ __forceinline__ int ref_slot_of(const RefTable &rt, int i)
 {
@@ -457,13 +456,9 @@ __device__ __forceinline__ void mc_list(const PlaneDesc &rp, int sx, int sy, int
     }
 }
 
-// shared memory per group: window (R x Ws uint16) and horizontal-pass rows (R x wpad int16)
-template <int GS> struct McSmem;
-template <> struct McSmem<32> { static constexpr int WIN = MC_WIN_MAX, TMP = MC_TMP_MAX; };
-template <> struct McSmem<8>  { static constexpr int WIN = 256 /* 15 x 16 */, TMP = 128 /* 15 x 8 */; };
-
+// ---- the first version of K1 (scalar FIRs: one IMAD per tap), kept selectable with B200_MC=1 ----
 template <typename PIX, int GS>
-__global__ void __launch_bounds__(256) k_mc(const B200McRec *__restrict__ recs, int count, FrameDesc cur, const FrameDesc *__restrict__ dpb, RefTable rt, int bd,
+__global__ void __launch_bounds__(256) k_mc_v1(const B200McRec *__restrict__ recs, int count, FrameDesc cur, const FrameDesc *__restrict__ dpb, RefTable rt, int bd,
                                             const uint32_t *__restrict__ gate)
 {
     if (__ldg(gate + 1)) return;         // the picture's work list failed validation (k_validate)
@@ -533,6 +528,44 @@ __global__ void __launch_bounds__(256) k_mc(const B200McRec *__restrict__ recs, 
         *d = (PIX)out;
         d = reinterpret_cast<PIX *>(reinterpret_cast<uint8_t *>(d) + dp.pitch);
     }
+}
+
+
+// K1, current version: the phases of k_mc.cuh (IDP.2A FIRs on packed sample pairs) with group-local barriers between them
+template <typename PIX, int GS>
+__global__ void __launch_bounds__(256, 4) k_mc(const B200McRec *__restrict__ recs, int count, FrameDesc cur, const FrameDesc *__restrict__ dpb, RefTable rt, int bd,
+                                            const uint32_t *__restrict__ gate)
+{
+    if (__ldg(gate + 1)) return;         // the picture's work list failed validation (k_validate)
+    constexpr int NG = 256 / GS;                           // groups per CTA
+    __shared__ __align__(16) uint16_t win_s[NG][McSmem<GS>::WIN];
+    __shared__ __align__(16) int16_t tmp_s[NG][McSmem<GS>::TMP];
+    const int grp = threadIdx.x / GS, gl = threadIdx.x & (GS - 1);
+    const unsigned gmask = GS == 32 ? 0xffffffffu : (((1u << GS) - 1u) << ((threadIdx.x & 31) & ~(GS - 1)));
+    const int ri = blockIdx.x * NG + grp;
+    if (ri >= count) return;                               // whole groups leave: the barriers are group-local
+    const int4 *rp4 = reinterpret_cast<const int4 *>(recs + ri);
+    const McTile t = mc_decode<GS>(__ldg(rp4), __ldg(rp4 + 1));
+    const bool chroma = t.flags & B200_MCF_CHROMA, bi = t.flags & B200_MCF_BI;
+    uint16_t *win = win_s[grp];
+    int16_t *tmp = tmp_s[grp];
+    int v0[8], v1[8];
+#pragma unroll
+    for (int list = 0; list < 2; list++) {
+        if (list && !bi) break;
+        const PlaneDesc rp = dpb[ref_slot_of(rt, list ? t.ref1 : t.ref0)].p[t.plane];
+        const int sx = list ? t.sx1 : t.sx0, sy = list ? t.sy1 : t.sy0, fr = list ? t.frac1 : t.frac0, mx = fr & 15, my = fr >> 4;
+        int (&v)[8] = list ? v1 : v0;
+        __syncwarp(gmask);                                 // the previous list's readers are done with win / tmp
+        if (chroma) mc_load_window<PIX, 4, GS>(rp, t, sx, sy, mx, my, gl, win); else mc_load_window<PIX, 8, GS>(rp, t, sx, sy, mx, my, gl, win);
+        __syncwarp(gmask);
+        if (mx) {
+            if (chroma) mc_stage_a<4, GS>(t, sx, sy, mx, my, bd, gl, win, tmp); else mc_stage_a<8, GS>(t, sx, sy, mx, my, bd, gl, win, tmp);
+            __syncwarp(gmask);
+        }
+        if (chroma) mc_stage_b<4, GS>(t, sx, sy, mx, my, bd, gl, win, tmp, v); else mc_stage_b<8, GS>(t, sx, sy, mx, my, bd, gl, win, tmp, v);
+    }
+    mc_store<PIX>(t, plane_of(cur, t.plane), bd, gl, v0, v1);
 }
 
 // --------------------------------------------------------------------------------------------
@@ -1044,18 +1077,29 @@ __global__ void k_fill(FrameDesc f, int value)
 int launch_mc(cudaStream_t st, const B200McRec *recs, int count, int n_big, const FrameDesc &cur, const FrameDesc *dpb_dev, const RefTable &rt, int bd, const uint32_t *gate)
 {
     if (!count) return 0;
+    static const int version = getenv("B200_MC") ? atoi(getenv("B200_MC")) : 2;     // 1 = scalar FIRs (first version), 2 = IDP.2A
     int n = 0;
     const int n_small = count - n_big;
     if (n_big) {                        // one warp per tile
         const int grid = (n_big + 7) / 8;
-        if (bd > 8) k_mc<uint16_t, 32><<<grid, 256, 0, st>>>(recs, n_big, cur, dpb_dev, rt, bd, gate);
-        else        k_mc<uint8_t, 32><<<grid, 256, 0, st>>>(recs, n_big, cur, dpb_dev, rt, bd, gate);
+        if (version == 1) {
+            if (bd > 8) k_mc_v1<uint16_t, 32><<<grid, 256, 0, st>>>(recs, n_big, cur, dpb_dev, rt, bd, gate);
+            else        k_mc_v1<uint8_t, 32><<<grid, 256, 0, st>>>(recs, n_big, cur, dpb_dev, rt, bd, gate);
+        } else {
+            if (bd > 8) k_mc<uint16_t, 32><<<grid, 256, 0, st>>>(recs, n_big, cur, dpb_dev, rt, bd, gate);
+            else        k_mc<uint8_t, 32><<<grid, 256, 0, st>>>(recs, n_big, cur, dpb_dev, rt, bd, gate);
+        }
         n++;
     }
     if (n_small) {                      // tiles of <= 8x8 samples: four per warp
         const int grid = (n_small + 31) / 32;
-        if (bd > 8) k_mc<uint16_t, 8><<<grid, 256, 0, st>>>(recs + n_big, n_small, cur, dpb_dev, rt, bd, gate);
-        else        k_mc<uint8_t, 8><<<grid, 256, 0, st>>>(recs + n_big, n_small, cur, dpb_dev, rt, bd, gate);
+        if (version == 1) {
+            if (bd > 8) k_mc_v1<uint16_t, 8><<<grid, 256, 0, st>>>(recs + n_big, n_small, cur, dpb_dev, rt, bd, gate);
+            else        k_mc_v1<uint8_t, 8><<<grid, 256, 0, st>>>(recs + n_big, n_small, cur, dpb_dev, rt, bd, gate);
+        } else {
+            if (bd > 8) k_mc<uint16_t, 8><<<grid, 256, 0, st>>>(recs + n_big, n_small, cur, dpb_dev, rt, bd, gate);
+            else        k_mc<uint8_t, 8><<<grid, 256, 0, st>>>(recs + n_big, n_small, cur, dpb_dev, rt, bd, gate);
+        }
         n++;
     }
     return n;

@@ -190,3 +190,54 @@ def test_constrained_intra_rules_equal_oracle(emul, cfi, bd, p_intra, split):
         assert list(ot)[:n2 + 1] == list(et)[:n2 + 1] and list(ol)[:n2 + 1] == list(el)[:n2 + 1], f"record {i}: reference arrays differ"
         changed += of.value != (int(r["flags"][0]) & 31)
     assert changed > 10, "the constrained-intra rule never removed a candidate: the test picture does not exercise it"
+
+
+MC_CASES = [  # w, h, cfi, bd, kw
+    (256, 128, 1, 8, {}),
+    (256, 128, 1, 10, dict(weighted=True)),
+    (320, 192, 1, 10, dict(max_mv=150)),               # windows far outside the picture: clamped loads
+    (192, 128, 2, 10, {}),
+    (192, 128, 3, 8, dict(weighted=True)),
+    (320, 192, 1, 12, dict(split_bias=2.5)),           # many small blocks
+    (256, 192, 1, 10, dict(split_bias=0.3, bi_frac=0.2)),
+]
+
+
+@pytest.mark.parametrize("w,h,cfi,bd,kw", MC_CASES)
+def test_mc_phase_code_equals_oracle(emul, w, h, cfi, bd, kw):
+    """K1: the phases of k_mc.cuh (IDP.2A FIRs on packed pairs, interleaved row pairs between the passes) executed lane after
+    lane, against the oracle on pure inter pictures (every PU shape of the synthetic quadtrees, all 16 / 64 phases, uni / bi /
+    weighted, luma and chroma, windows hanging over the picture border)"""
+    from openhevc_b200.synth import FrameSynth, smooth_frame
+    for seed in range(2):
+        blob, st = FrameSynth(w, h, cfi=cfi, bit_depth=bd, seed=800 + 10 * seed + bd + cfi, refs=[1, 2], cur_slot=0, p_intra=0.0, coded_frac=0.0,
+                              deblock=False, sao=False, **kw).generate()
+        hdr, secs = W.parse_blob(blob)
+        assert len(secs[W.SEC_INTRA]) == 0 and sum(len(secs[k]) for k in (W.SEC_TU4, W.SEC_TU8, W.SEC_TU16, W.SEC_TU32)) == 0
+        dpb = [smooth_frame(w, h, cfi, bd, 300 + k) for k in range(3)]
+        want = oracle_lib.execute(blob, dpb)
+        dt = np.uint16 if bd > 8 else np.uint8
+        B = np.dtype(dt).itemsize
+        pitches, bufs = [], []
+        for slot in range(3):
+            for p in range(3):
+                pw, ph = W.plane_dims(w, h, cfi, p)
+                pitch = (pw * B + 255) // 256 * 256
+                b = np.full((ph, pitch // B), 0x5a5a if bd > 8 else 0x5a, dt)
+                b[:, :pw] = dpb[slot][p] if slot else 0
+                bufs.append(b)
+                if slot == 0:
+                    pitches.append(pitch)
+        ptrs = (C.c_void_p * 9)(*[b.ctypes.data for b in bufs])
+        cur = (C.c_void_p * 3)(*[b.ctypes.data for b in bufs[:3]])
+        mc = np.ascontiguousarray(secs[W.SEC_MC])
+        ref_slot = np.ascontiguousarray(hdr["ref_slot"])
+        rc = emul.emul_mc(mc.ctypes.data_as(C.c_void_p), len(mc), int(hdr["mc_big_count"]), cur, ptrs, 3, (C.c_int * 3)(*pitches), w, h, cfi, bd,
+                          ref_slot.ctypes.data_as(C.c_void_p))
+        assert rc == 0
+        for p in range(3):
+            pw, ph = W.plane_dims(w, h, cfi, p)
+            got = bufs[p][:, :pw].astype(np.uint16)
+            bad = np.argwhere(got != want[p])
+            assert len(bad) == 0, (f"seed {seed} plane {p}: {len(bad)} samples differ, first at (y,x)={tuple(bad[0])} "
+                                   f"got {got[tuple(bad[0])]} want {want[p][tuple(bad[0])]}")
