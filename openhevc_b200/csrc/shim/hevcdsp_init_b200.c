@@ -52,6 +52,11 @@ static struct {
     unsigned gen;                       /* bumped when the context is re-created for a new geometry */
     struct ShimThread *active[MAX_ACTIVE];   /* owners of the pictures between b200_frame_begin and b200_frame_end */
     int n_active;
+    /* B200_SHIM_DUMP=<dir>: record only.  Every picture's work list is written to <dir>/pic_NNNNN.blob (decode order) and
+     * nothing is sent to a GPU -- no device is needed, the decoder's output pictures stay untouched.  tests/ replay the dumps
+     * through the CPU oracle and compare with the unmodified decoder: the recorder + wire format + oracle, end to end. */
+    const char *dump_dir;
+    int dump_no, configured;
 } G = { .mu = PTHREAD_MUTEX_INITIALIZER, .cv = PTHREAD_COND_INITIALIZER };
 
 /* per thread: the owner of a picture (the thread that runs hevc_frame_start .. the end of decode_nal_unit for it; with
@@ -419,7 +424,8 @@ void ff_videodsp_init_b200(VideoDSPContext *c, int bpc)
 static int ensure_ctx(const HEVCContext *s)       /* called with G.mu held */
 {
     const HEVCSPS *sps = s->sps;
-    if (!(G.ctx && G.cfg.width == sps->width && G.cfg.height == sps->height && G.cfg.bit_depth == sps->bit_depth &&
+    G.dump_dir = getenv("B200_SHIM_DUMP");
+    if (!((G.ctx || (G.dump_dir && G.configured)) && G.cfg.width == sps->width && G.cfg.height == sps->height && G.cfg.bit_depth == sps->bit_depth &&
           G.cfg.chroma_format_idc == sps->chroma_format_idc && G.cfg.log2_ctb_size == (int)sps->log2_ctb_size)) {
         G.gen++;
         if (G.ctx) { b200_ctx_destroy(G.ctx); G.ctx = NULL; }
@@ -430,8 +436,11 @@ static int ensure_ctx(const HEVCContext *s)       /* called with G.mu held */
         G.cfg.bit_depth = sps->bit_depth; G.cfg.log2_ctb_size = sps->log2_ctb_size;
         G.cfg.n_slots = 32;                /* == FF_ARRAY_ELEMS(s->DPB), hevc.h:1207 */
         G.cfg.n_arenas = 8;
-        int rc = b200_ctx_create(&G.cfg, &G.ctx);
-        if (rc) { fail(rc, b200_last_error(NULL)); return rc; }
+        if (!G.dump_dir) {
+            int rc = b200_ctx_create(&G.cfg, &G.ctx);
+            if (rc) { fail(rc, b200_last_error(NULL)); return rc; }
+        }
+        G.configured = 1;
         G.bd = sps->bit_depth; G.B = G.bd > 8 ? 2 : 1; G.cfi = sps->chroma_format_idc;
         for (int p = 0; p < 3; p++) b200_plane_dims(sps->width, sps->height, G.cfi, p, &G.pw[p], &G.ph[p]);
     }
@@ -540,11 +549,17 @@ int b200_frame_end(HEVCContext *s)
     /* pictures enter the compute stream in decode order, whatever order the frame threads finish parsing in */
     pthread_mutex_lock(&G.mu);
     while (G.turn != g.ticket) pthread_cond_wait(&G.cv, &G.mu);
-    if (!rc) rc = b200_frame_submit(G.ctx, blob, n);
+    if (!rc && G.dump_dir) {
+        char path[1024];
+        snprintf(path, sizeof(path), "%s/pic_%05d.blob", G.dump_dir, G.dump_no++);
+        FILE *f = fopen(path, "wb");
+        if (!f || fwrite(blob, 1, (size_t)n, f) != (size_t)n) { fail(B200_EINVAL, "B200_SHIM_DUMP: cannot write the work list"); rc = B200_EINVAL; }
+        if (f) fclose(f);
+    } else if (!rc) rc = b200_frame_submit(G.ctx, blob, n);
     G.turn++;
     pthread_cond_broadcast(&G.cv);
     pthread_mutex_unlock(&G.mu);
-    if (!rc) rc = b200_wait_uploads(G.ctx);  /* this thread's recorder memory is reused by its next picture */
+    if (!rc && !G.dump_dir) rc = b200_wait_uploads(G.ctx);  /* this thread's recorder memory is reused by its next picture */
     if (rc) fail(rc, G.ctx ? b200_last_error(G.ctx) : "frame_end failed");
     return rc;
 }
@@ -552,6 +567,7 @@ int b200_frame_end(HEVCContext *s)
 int b200_frame_readback(HEVCContext *s, AVFrame *frame)
 {
     if (g.err) return g.err;
+    if (G.dump_dir) return 0;                 /* record-only run: there is no device picture */
     int slot = -1;
     for (int i = 0; i < 32; i++) if (s->DPB[i].frame && s->DPB[i].frame->data[0] == frame->data[0]) slot = i;
     if (slot < 0) { fail(B200_EINVAL, "readback of a frame that is not in the DPB"); return g.err; }
@@ -570,6 +586,7 @@ int b200_frame_upload_ref(HEVCContext *s, AVFrame *frame)
     const int erc = ensure_ctx(s);
     pthread_mutex_unlock(&G.mu);
     if (erc) return g.err;
+    if (G.dump_dir) return 0;
     int slot = -1;
     for (int i = 0; i < 32; i++) if (s->DPB[i].frame && s->DPB[i].frame->data[0] == frame->data[0]) slot = i;
     if (slot < 0) { fail(B200_EINVAL, "upload of a frame that is not in the DPB"); return g.err; }

@@ -1,0 +1,56 @@
+"""CPU suite, end to end without a GPU: the REAL decoder (reference + the hooks of INTEGRATION.md) parses the committed
+Annex-B streams with the B200 tables installed in record-only mode (B200_SHIM_DUMP: every picture's work list is written
+to a file, nothing is sent to a device); the CPU oracle executes the dumped work lists picture after picture on its own
+DPB; the per-plane MD5s must equal those of the UNMODIFIED reference decoder committed next to the streams.
+
+What this pins: the shim's pointer -> (slot, plane, x, y) mapping, the recorder and the wire format (incl. sparse
+coefficients, MC tile splitting, intra level ordering, deblock / SAO grids, constrained_intra_pred bitmap), and the
+oracle itself against the reference decoder on real syntax -- the GPU suite then only has to show kernel == oracle."""
+import ctypes as C
+import glob
+import hashlib
+import os
+import subprocess
+import tempfile
+
+import numpy as np
+import pytest
+
+import oracle_lib
+from openhevc_b200 import worklist as W
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+REFDIR = os.path.join(os.path.dirname(HERE), "oracle", "_ref")
+STREAMS = sorted(glob.glob(os.path.join(HERE, "golden", "streams", "*.hevc")))
+SMALL = [s for s in STREAMS if os.path.getsize(s) < 400_000]          # the 1080p / 4K streams run in the GPU suite
+
+
+@pytest.mark.parametrize("stream", SMALL, ids=[os.path.basename(s) for s in SMALL])
+def test_recorded_work_lists_through_the_oracle_equal_the_reference_decoder(stream):
+    binary = os.path.join(REFDIR, "decode_b200")
+    if not os.path.exists(binary):
+        pytest.skip("oracle/_ref/decode_b200 not built (needs /root/reference)")
+    want = open(stream[:-5] + ".md5").read().splitlines()
+    with tempfile.TemporaryDirectory() as d:
+        r = subprocess.run([binary, stream, "1", "quiet"], capture_output=True, text=True, timeout=600, env=dict(os.environ, B200_SHIM_DUMP=d))
+        assert r.returncode == 0, r.stderr[-2000:]
+        blobs = sorted(glob.glob(os.path.join(d, "pic_*.blob")))
+        assert len(blobs) == len(want), f"{len(blobs)} work lists for {len(want)} pictures"
+        lib = oracle_lib.lib()
+        slots = {}
+        dummy = np.zeros(1, np.uint16)
+        for k, path in enumerate(blobs):
+            blob = np.fromfile(path, np.uint8)
+            hdr, _ = W.parse_blob(blob)
+            w, h, cfi, bd = int(hdr["width"]), int(hdr["height"]), int(hdr["chroma_format_idc"]), int(hdr["bit_depth"])
+            cur = int(hdr["cur_slot"])
+            # a new picture in a slot starts from the decoder's fresh frame; the oracle overwrites every sample anyway
+            slots[cur] = [np.zeros(W.plane_dims(w, h, cfi, p)[::-1], np.uint16) for p in range(3)]
+            for i in range(int(hdr["n_ref"])):
+                assert int(hdr["ref_slot"][i]) in slots, f"picture {k} references an empty DPB slot"
+            n_slots = 32
+            flat = [slots[s][p] if s in slots else dummy for s in range(n_slots) for p in range(3)]
+            ptrs = (C.c_void_p * len(flat))(*[a.ctypes.data for a in flat])
+            assert lib.orc_execute_blob(blob.ctypes.data_as(C.c_void_p), ptrs, n_slots) == 0
+            md5 = [hashlib.md5((pl.astype(np.uint8) if bd == 8 else pl.astype("<u2")).tobytes()).hexdigest() for pl in slots[cur]]
+            assert f"frame {k} {w}x{h} bd{bd} " + " ".join(md5) == want[k], f"picture {k} of {os.path.basename(stream)}"
