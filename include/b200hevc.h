@@ -120,6 +120,10 @@ int  b200_rec_sao(B200Rec *r, int plane, int x, int y, const B200SaoRec *params)
  * MvField.pred_flag == PF_INTRA of s->ref->tab_mvf, hevc.h:1032-1041), once all CTBs are parsed.  B200IntraRec.flags of
  * such a picture are the availability BEFORE the constrained-intra rule (hevcpred_template.c:116-163) */
 int  b200_rec_set_cip(B200Rec *r, int log2_min_pu_size, int min_pu_width, int min_pu_height, const uint8_t *is_intra);
+/* streams with transquant_bypass_enable_flag / pcm_loop_filter_disabled AND SAO: s->is_pcm[] (one byte per min-PU, non-zero
+ * = PCM-without-loop-filter or transquant-bypass PU), once all CTBs are parsed; the device gives those PUs their deblocked
+ * samples back after SAO, exactly as restore_tqb_pixels does (hevc_filter.c:163-193) */
+int  b200_rec_set_tqb(B200Rec *r, int log2_min_pu_size, int min_pu_width, int min_pu_height, const uint8_t *is_pcm);
 /* host helper shared by the recorder and by external blob builders: permutation (perm[new] = old) that sorts decode-order
  * intra records by dependency level (stable); returns the number of levels (>= 0) or a negative error */
 int  b200_intra_level_order(const B200IntraRec *recs, uint32_t n, int width, int height, int chroma_format_idc, uint32_t *perm);

@@ -66,7 +66,11 @@ typedef struct B200BlobHeader {
                                     one bit per min-PU, row-major, bit set = the PU is intra coded (MvField.pred_flag == PF_INTRA,
                                     hevc.h:1032-1041, read by hevcpred_template.c:39-40).  Carved out of the reserved words of blob v3:
                                     older blobs read as "no CIP"                                                                      */
-    uint32_t reserved[64 - 15 - 2 * B200_SEC_COUNT];
+    B200Section tqb;             /* pictures of streams with transquant_bypass / pcm_loop_filter_disabled AND SAO (else count = 0): uint32
+                                    words, B200CipHeader followed by one bit per min-PU, bit set = s->is_pcm[] != 0 (PCM with the loop filter
+                                    off, or cu_transquant_bypass).  After SAO those PUs get their deblocked samples back
+                                    (restore_tqb_pixels, hevc_filter.c:163-193 -- with its two quirks, see k_sao.cuh)                        */
+    uint32_t reserved[64 - 17 - 2 * B200_SEC_COUNT];
 } B200BlobHeader;               /* 256 bytes */
 
 typedef struct B200CipHeader {   /* first 4 words of the CIP section */
@@ -82,6 +86,7 @@ typedef struct B200CipHeader {   /* first 4 words of the CIP section */
 
 #define B200_FRAME_HAS_DEBLOCK 1u
 #define B200_FRAME_HAS_SAO     2u
+#define B200_FRAME_TQB         8u   /* B200BlobHeader.tqb is present; B200SaoRec.tqb marks the CTBs that contain such PUs */
 #define B200_FRAME_CIP         4u   /* pps->constrained_intra_pred_flag: B200IntraRec.flags hold the availability BEFORE the
                                        CIP rules; the device applies hevcpred_template.c:116-163 and :185-249 with the bitmap */
 
@@ -186,7 +191,7 @@ typedef struct B200SaoRec {      /* 16 bytes; grid index = plane * ctb_count + c
     uint8_t  borders;            /* bit0 left, bit1 top, bit2 right, bit3 bottom picture border      */
     uint8_t  edges;              /* bit0-1 vert_edge[2], bit2-3 horiz_edge[2], bit4-7 diag_edge[4]; only variant 1 */
     uint8_t  variant;            /* 0 = sao_edge_filter[0], 1 = sao_edge_filter[1] (restore)          */
-    uint8_t  pad;
+    uint8_t  tqb;                /* 1 = the CTB contains PUs of B200BlobHeader.tqb (set by the recorder)  */
     int16_t  offset_val[5];      /* sao->offset_val[c_idx][0..4]                                      */
 } B200SaoRec;
 

@@ -108,6 +108,6 @@ int launch_intra(cudaStream_t st, const B200IntraRec *recs, int count, const int
                  uint2 *edges[3], const int edge_stride[3], uint32_t *counter, const uint32_t *cip_words, const B200CipHeader *cip_hdr, int cfi);
 int launch_deblock(cudaStream_t st, const uint16_t *grid, const B200DbkLayout &L, const FrameDesc &cur, int bd);
 int launch_sao(cudaStream_t st, const B200SaoRec *grid, const FrameDesc &src, const FrameDesc &dst, int bd,
-               int log2_ctb, int ctb_w, int ctb_h, int chroma_format_idc);
+               int log2_ctb, int ctb_w, int ctb_h, int chroma_format_idc, const uint32_t *tqb_words, const B200CipHeader *tqb_hdr);
 int set_intra_trace(unsigned long long *p);
 int launch_fill(cudaStream_t st, const FrameDesc &f, int bd, int value);

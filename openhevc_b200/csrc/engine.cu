@@ -36,6 +36,7 @@ struct Arena {
     uint8_t *dev = nullptr;
     uint8_t *stage = nullptr;       // pinned staging for blobs that are not in pinned memory
     B200CipHeader cip_hdr = {};     // host copy of the resident blob's CIP section header (constrained_intra_pred pictures)
+    B200CipHeader tqb_hdr = {};     // ... and of its TQB section header (restore_tqb_pixels)
     B200BlobHeader hdr;             // host copy of the resident blob's header
     bool resident = false;
     cudaEvent_t ev_uploaded = nullptr;
@@ -389,6 +390,14 @@ static int check_blob(B200Ctx *ctx, const B200BlobHeader *h, uint64_t nbytes)
             ch->min_pu_height != ((uint32_t)c.height >> ch->log2_min_pu_size) || h->cip.count < B200_CIP_WORDS(ch->min_pu_width, ch->min_pu_height))
             return fail(ctx, B200_EINVAL, "CIP section does not match the picture geometry");
     }
+    if (h->tqb.count || (h->flags & B200_FRAME_TQB)) {          // restore_tqb_pixels: bitmap of the min-PUs
+        const uint64_t end = (uint64_t)h->tqb.off + 4ull * h->tqb.count;
+        if (!(h->flags & B200_FRAME_TQB) || h->tqb.count < 4 || (h->tqb.off & 15) || end > nbytes) return fail(ctx, B200_EINVAL, "TQB section out of bounds");
+        const B200CipHeader *th = (const B200CipHeader *)((const uint8_t *)h + h->tqb.off);
+        if (th->log2_min_pu_size < 2 || th->log2_min_pu_size > 5 || th->min_pu_width != ((uint32_t)c.width >> th->log2_min_pu_size) ||
+            th->min_pu_height != ((uint32_t)c.height >> th->log2_min_pu_size) || h->tqb.count < B200_CIP_WORDS(th->min_pu_width, th->min_pu_height))
+            return fail(ctx, B200_EINVAL, "TQB section does not match the picture geometry");
+    }
     if (h->mc_big_count > h->sec[B200_SEC_MC].count) return fail(ctx, B200_EINVAL, "mc_big_count %u > %u MC records", h->mc_big_count, h->sec[B200_SEC_MC].count);
     if (h->sec[B200_SEC_DBK].count && h->sec[B200_SEC_DBK].count != ctx->dbk.total) return fail(ctx, B200_EINVAL, "deblock grid size %u != %u", h->sec[B200_SEC_DBK].count, ctx->dbk.total);
     if (h->sec[B200_SEC_SAO].count && h->sec[B200_SEC_SAO].count != (uint32_t)(3 * ctx->ctb_w * ctx->ctb_h)) return fail(ctx, B200_EINVAL, "SAO grid size mismatch");
@@ -516,6 +525,7 @@ extern "C" int b200_frame_upload(B200Ctx *ctx, const void *blob, uint64_t nbytes
     CU(cudaEventRecord(a.ev_uploaded, ctx->st_copy));
     a.hdr = *h;
     if (h->cip.count) a.cip_hdr = *(const B200CipHeader *)((const uint8_t *)blob + h->cip.off);
+    if (h->tqb.count) a.tqb_hdr = *(const B200CipHeader *)((const uint8_t *)blob + h->tqb.off);
     a.resident = true;
     return 0;
 }
@@ -616,7 +626,8 @@ extern "C" int b200_frame_execute_ex(B200Ctx *ctx, int arena, int cur_slot, cons
     if (tr) CU(cudaEventRecord(tr->ev[4], st));
     // K5 SAO
     if (has_sao)
-        ctx->launches += launch_sao(st, (const B200SaoRec *)(a.dev + h.sec[B200_SEC_SAO].off), cur, out, bd, ctx->cfg.log2_ctb_size, ctx->ctb_w, ctx->ctb_h, ctx->cfg.chroma_format_idc);
+        ctx->launches += launch_sao(st, (const B200SaoRec *)(a.dev + h.sec[B200_SEC_SAO].off), cur, out, bd, ctx->cfg.log2_ctb_size, ctx->ctb_w, ctx->ctb_h, ctx->cfg.chroma_format_idc,
+                                    (h.flags & B200_FRAME_TQB) && h.tqb.count ? (const uint32_t *)(a.dev + h.tqb.off) : nullptr, &a.tqb_hdr);
     if (pf) { CU(cudaEventRecord(ctx->prof[5], st)); ctx->prof_valid = true; }
     if (tr) CU(cudaEventRecord(tr->ev[5], st));
     CU(cudaEventRecord(a.ev_done[li], st));

@@ -33,14 +33,14 @@ template <typename PIX> HD void store8p(const PlaneDesc &pd, int x, int y, const
 }
 
 struct SaoCtb {                 // one decoded B200SaoRec + the geometry of its CTB in this plane
-    int type, cls, borders, edges, variant;
+    int type, cls, borders, edges, variant, tqb;
     int off[5];
     int x0, y0, w, h;           // CTB origin and (picture-clipped) size in samples of the plane
 };
 HD SaoCtb sao_decode(const uint4 rq, const PlaneDesc &sp, int cx, int cy, int lw, int lh)
 {
     SaoCtb t;
-    t.type = rq.x & 0xff; t.cls = (rq.x >> 8) & 0xff; t.borders = (rq.x >> 16) & 0xff; t.edges = rq.x >> 24; t.variant = rq.y & 0xff;
+    t.type = rq.x & 0xff; t.cls = (rq.x >> 8) & 0xff; t.borders = (rq.x >> 16) & 0xff; t.edges = rq.x >> 24; t.variant = rq.y & 0xff; t.tqb = (rq.y >> 8) & 0xff;
     t.off[0] = (int16_t)(rq.y >> 16); t.off[1] = (int16_t)(rq.z & 0xffff); t.off[2] = (int16_t)(rq.z >> 16); t.off[3] = (int16_t)(rq.w & 0xffff); t.off[4] = (int16_t)(rq.w >> 16);
     t.x0 = cx << lw; t.y0 = cy << lh;
     t.w = imin(1 << lw, sp.w - t.x0); t.h = imin(1 << lh, sp.h - t.y0);
@@ -104,6 +104,44 @@ __host__ __device__ __noinline__ void sao_row_exact(const PlaneDesc &sp, const B
     for (int k = 0; k < 4; k++) outp[k] = (uint32_t)out[2 * k] | ((uint32_t)out[2 * k + 1] << 16);
 }
 
+// restore_tqb_pixels (hevc_filter.c:163-193): after the SAO of a CTB, PUs flagged in is_pcm[] (PCM with the loop filter off,
+// cu_transquant_bypass) get their deblocked samples back.  Two things the reference really does are kept:
+//  - it is called with the LUMA origin of the CTB but the CTB's width / height in the plane being filtered, so for
+//    subsampled chroma only the PUs of the first half of the CTB are visited (x_lim / y_lim below);
+//  - a row of a PU is copied with memcpy(.., min_pu_size >> hshift): samples used as bytes, so above 8 bits only the first
+//    half of each row comes back (len below).
+// Only CTBs marked by the recorder (B200SaoRec.tqb) look at the bitmap: rare streams, a handful of CTBs.
+struct TqbDesc {
+    const uint32_t *bits;        // one bit per min-PU, row-major; nullptr = nothing to restore in this picture
+    int log2_pu, pu_w;
+};
+HD bool tqb_pu(const TqbDesc &q, int X, int Y)
+{
+    const long i = (long)Y * q.pu_w + X;
+#ifdef __CUDA_ARCH__
+    return (__ldg(q.bits + (i >> 5)) >> (i & 31)) & 1;
+#else
+    return (q.bits[i >> 5] >> (i & 31)) & 1;
+#endif
+}
+// one row of 8 samples at (gx, gy) of a plane with shifts hs / vs: samples of restored PUs take the value of `c` again
+HD void sao_restore_row(const TqbDesc &q, const SaoCtb &t, int hs, int vs, int B, int gx, int gy, const uint32_t (&c)[4], uint32_t (&o)[4])
+{
+    const int l = q.log2_pu;
+    const int x_lim = ((t.x0 << hs) + t.w) >> l, y_lim = ((t.y0 << vs) + t.h) >> l;      // luma origin + size in the plane (sic)
+    const int len = ((1 << l) >> hs) / B;                                                  // bytes taken for samples (sic)
+    const int Y = (gy << vs) >> l;
+    if (Y >= y_lim) return;
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+        const int px = gx + i, X = (px << hs) >> l;
+        if (X < x_lim && px - ((X << l) >> hs) < len && tqb_pu(q, X, Y)) {
+            const uint32_t keep = (i & 1) ? 0xffff0000u : 0x0000ffffu;
+            o[i >> 1] = (o[i >> 1] & ~keep) | (c[i >> 1] & keep);
+        }
+    }
+}
+
 // out = clip(c + table[idx]) for two samples: idx = 0..4 in each 16-bit half of X
 HD uint32_t sao_apply2(uint32_t c, uint32_t X, uint32_t tab_lo, uint32_t tab_hi, uint32_t maxv2)
 {
@@ -117,7 +155,8 @@ HD uint32_t sao_apply2(uint32_t c, uint32_t X, uint32_t tab_lo, uint32_t tab_hi,
 template <typename PIX, int CLS>
 HD void sao_edge_rows(const PlaneDesc &sp, const PlaneDesc &dp, const B200SaoRec *rec, int cx, int cy, int lwlh, int gx, int gy0, int nvalid, int nrows,
                       int maxv, uint32_t tab_lo, uint32_t tab_hi, int exact_rows,
-                      const uint32_t (&c)[SAO_R + 2][4], const uint32_t (&sl)[SAO_R + 2], const uint32_t (&sr)[SAO_R + 2])
+                      const uint32_t (&c)[SAO_R + 2][4], const uint32_t (&sl)[SAO_R + 2], const uint32_t (&sr)[SAO_R + 2],
+                      const TqbDesc &tq, const SaoCtb &t, int hsvsB)
 {
     const uint32_t maxv2 = (uint32_t)maxv * 0x10001u;
     constexpr int JLO = CLS == 0 ? 1 : 0, JHI = CLS == 0 ? SAO_R : SAO_R + 1;
@@ -157,6 +196,7 @@ HD void sao_edge_rows(const PlaneDesc &sp, const PlaneDesc &dp, const B200SaoRec
                     o[k] = sao_apply2(c[j][k], ua + ub, tab_lo, tab_hi, maxv2);
                 }
             }
+            if (t.tqb) sao_restore_row(tq, t, hsvsB & 1, (hsvsB >> 1) & 1, hsvsB >> 2, gx, gy0 + r, c[j], o);
             store8p<PIX>(dp, gx, gy0 + r, o, nvalid);
         }
     }
@@ -167,7 +207,7 @@ HD void sao_edge_rows(const PlaneDesc &sp, const PlaneDesc &dp, const B200SaoRec
 // row groups.
 template <typename PIX>
 HD void sao_thread(const B200SaoRec *__restrict__ grid, const FrameDesc &src, const FrameDesc &dst, int bd,
-                   int log2_ctb, int ctb_w, int ctb_h, int cfi, int4 tile_base, int3 tiles_x, int warp, int lane)
+                   int log2_ctb, int ctb_w, int ctb_h, int cfi, int4 tile_base, int3 tiles_x, const TqbDesc &tq, int warp, int lane)
 {
     if (warp >= tile_base.w) return;                                // tile_base = first tile of plane 0, 1, 2, and the total
     const int plane = warp >= tile_base.z ? 2 : warp >= tile_base.y ? 1 : 0;
@@ -234,6 +274,7 @@ HD void sao_thread(const B200SaoRec *__restrict__ grid, const FrameDesc &src, co
                     const uint32_t kk = vminu2((band + nb) & 0x001f001fu, 0x00040004u);      // (band - position) & 31, 4 = outside
                     o[k] = sao_apply2(c[r + 1][k], kk, tab_lo, tab_hi, maxv2);
                 }
+                if (t.tqb) sao_restore_row(tq, t, hs, vs, (int)sizeof(PIX), gx, gy0 + r, c[r + 1], o);
                 store8p<PIX>(dp, gx, gy0 + r, o, nvalid);
             }
         } else {
@@ -253,6 +294,7 @@ HD void sao_thread(const B200SaoRec *__restrict__ grid, const FrameDesc &src, co
                     }
                     o[k] = res;
                 }
+                if (t.tqb) sao_restore_row(tq, t, hs, vs, (int)sizeof(PIX), gx, gy0 + r, c[r + 1], o);
                 store8p<PIX>(dp, gx, gy0 + r, o, nvalid);
             }
         }
@@ -274,12 +316,12 @@ HD void sao_thread(const B200SaoRec *__restrict__ grid, const FrameDesc &src, co
     const uint32_t tab_lo = (uint32_t)((t.off[1] + 128) & 0xff) | ((uint32_t)((t.off[2] + 128) & 0xff) << 8) |
                             ((uint32_t)((t.off[0] + 128) & 0xff) << 16) | ((uint32_t)((t.off[3] + 128) & 0xff) << 24);
     const uint32_t tab_hi = (uint32_t)((t.off[4] + 128) & 0xff);        // edge_idx[] = {1,2,0,3,4}
-    const int lwlh = lw | (lh << 8);
+    const int lwlh = lw | (lh << 8), hsvsB = hs | (vs << 1) | ((int)sizeof(PIX) << 2);
     switch (t.cls) {
-    case 0:  sao_edge_rows<PIX, 0>(sp, dp, rec, cx, cy, lwlh, gx, gy0, nvalid, nrows, maxv, tab_lo, tab_hi, exact_rows, c, sl, sr); break;
-    case 1:  sao_edge_rows<PIX, 1>(sp, dp, rec, cx, cy, lwlh, gx, gy0, nvalid, nrows, maxv, tab_lo, tab_hi, exact_rows, c, sl, sr); break;
-    case 2:  sao_edge_rows<PIX, 2>(sp, dp, rec, cx, cy, lwlh, gx, gy0, nvalid, nrows, maxv, tab_lo, tab_hi, exact_rows, c, sl, sr); break;
-    default: sao_edge_rows<PIX, 3>(sp, dp, rec, cx, cy, lwlh, gx, gy0, nvalid, nrows, maxv, tab_lo, tab_hi, exact_rows, c, sl, sr); break;
+    case 0:  sao_edge_rows<PIX, 0>(sp, dp, rec, cx, cy, lwlh, gx, gy0, nvalid, nrows, maxv, tab_lo, tab_hi, exact_rows, c, sl, sr, tq, t, hsvsB); break;
+    case 1:  sao_edge_rows<PIX, 1>(sp, dp, rec, cx, cy, lwlh, gx, gy0, nvalid, nrows, maxv, tab_lo, tab_hi, exact_rows, c, sl, sr, tq, t, hsvsB); break;
+    case 2:  sao_edge_rows<PIX, 2>(sp, dp, rec, cx, cy, lwlh, gx, gy0, nvalid, nrows, maxv, tab_lo, tab_hi, exact_rows, c, sl, sr, tq, t, hsvsB); break;
+    default: sao_edge_rows<PIX, 3>(sp, dp, rec, cx, cy, lwlh, gx, gy0, nvalid, nrows, maxv, tab_lo, tab_hi, exact_rows, c, sl, sr, tq, t, hsvsB); break;
     }
 }
 

@@ -456,7 +456,7 @@ __device__ __forceinline__ void mc_list(const PlaneDesc &rp, int sx, int sy, int
     }
 }
 
-// ---- the first version of K1 (scalar FIRs: one IMAD per tap), kept selectable with B200_MC=1 ----
+// ---- K1, default version: scalar FIRs (one IMAD per tap) ----
 template <typename PIX, int GS>
 __global__ void __launch_bounds__(256) k_mc_v1(const B200McRec *__restrict__ recs, int count, FrameDesc cur, const FrameDesc *__restrict__ dpb, RefTable rt, int bd,
                                             const uint32_t *__restrict__ gate)
@@ -531,7 +531,7 @@ __global__ void __launch_bounds__(256) k_mc_v1(const B200McRec *__restrict__ rec
 }
 
 
-// K1, current version: the phases of k_mc.cuh (IDP.2A FIRs on packed sample pairs) with group-local barriers between them
+// K1, experimental version (B200_MC=2): the phases of k_mc.cuh (IDP.2A FIRs on packed sample pairs) with group-local barriers between them
 template <typename PIX, int GS>
 __global__ void __launch_bounds__(256, 4) k_mc(const B200McRec *__restrict__ recs, int count, FrameDesc cur, const FrameDesc *__restrict__ dpb, RefTable rt, int bd,
                                             const uint32_t *__restrict__ gate)
@@ -1057,9 +1057,9 @@ __global__ void __launch_bounds__(DBK_THREADS, 3) k_deblock(const uint16_t *__re
 
 template <typename PIX>
 __global__ void __launch_bounds__(256, 2) k_sao(const B200SaoRec *__restrict__ grid, FrameDesc src, FrameDesc dst, int bd,
-                                                int log2_ctb, int ctb_w, int ctb_h, int cfi, int4 tile_base, int3 tiles_x)
+                                                int log2_ctb, int ctb_w, int ctb_h, int cfi, int4 tile_base, int3 tiles_x, TqbDesc tq)
 {
-    sao_thread<PIX>(grid, src, dst, bd, log2_ctb, ctb_w, ctb_h, cfi, tile_base, tiles_x, blockIdx.x * 8 + (threadIdx.x >> 5), threadIdx.x & 31);
+    sao_thread<PIX>(grid, src, dst, bd, log2_ctb, ctb_w, ctb_h, cfi, tile_base, tiles_x, tq, blockIdx.x * 8 + (threadIdx.x >> 5), threadIdx.x & 31);
 }
 
 template <typename PIX>
@@ -1077,7 +1077,11 @@ __global__ void k_fill(FrameDesc f, int value)
 int launch_mc(cudaStream_t st, const B200McRec *recs, int count, int n_big, const FrameDesc &cur, const FrameDesc *dpb_dev, const RefTable &rt, int bd, const uint32_t *gate)
 {
     if (!count) return 0;
-    static const int version = getenv("B200_MC") ? atoi(getenv("B200_MC")) : 2;     // 1 = scalar FIRs (first version), 2 = IDP.2A
+    // 1 = scalar FIRs, one IMAD per tap (default); 2 = IDP.2A on packed pairs (k_mc.cuh).  Version 2 is bit-exact on the GPU
+    // (full parity suite) but SLOWER: 145 vs 109 us per 4K B picture, 38.9 M + 29.7 M vs 35.4 M + 22.8 M warp instructions --
+    // the pair shuffles and the 16-bit interleaved stores cost more than the halved multiplies save, and ncu shows the
+    // stage waiting on its window loads (long scoreboard), not on the ALU.  Kept selectable for the next round's work.
+    static const int version = getenv("B200_MC") ? atoi(getenv("B200_MC")) : 1;
     int n = 0;
     const int n_small = count - n_big;
     if (n_big) {                        // one warp per tile
@@ -1161,8 +1165,11 @@ int launch_deblock(cudaStream_t st, const uint16_t *grid, const B200DbkLayout &L
 }
 
 int launch_sao(cudaStream_t st, const B200SaoRec *grid, const FrameDesc &src, const FrameDesc &dst, int bd,
-               int log2_ctb, int ctb_w, int ctb_h, int cfi)
+               int log2_ctb, int ctb_w, int ctb_h, int cfi, const uint32_t *tqb_words, const B200CipHeader *tqb_hdr)
 {
+    TqbDesc tq;
+    tq.bits = nullptr; tq.log2_pu = 2; tq.pu_w = 0;
+    if (tqb_words && tqb_hdr) { tq.bits = tqb_words + 4; tq.log2_pu = (int)tqb_hdr->log2_min_pu_size; tq.pu_w = (int)tqb_hdr->min_pu_width; }
     // warp tiles: (CTB width, at most 64) x (32 / strips x SAO_R) samples, all planes in one linear index
     int base[4] = { 0, 0, 0, 0 }, ntx[3];
     for (int p = 0; p < 3; p++) {
@@ -1175,8 +1182,8 @@ int launch_sao(cudaStream_t st, const B200SaoRec *grid, const FrameDesc &src, co
     const int blocks = (base[3] + 7) / 8;
     const int4 tb = make_int4(base[0], base[1], base[2], base[3]);
     const int3 tx = make_int3(ntx[0], ntx[1], ntx[2]);
-    if (bd > 8) k_sao<uint16_t><<<blocks, 256, 0, st>>>(grid, src, dst, bd, log2_ctb, ctb_w, ctb_h, cfi, tb, tx);
-    else        k_sao<uint8_t><<<blocks, 256, 0, st>>>(grid, src, dst, bd, log2_ctb, ctb_w, ctb_h, cfi, tb, tx);
+    if (bd > 8) k_sao<uint16_t><<<blocks, 256, 0, st>>>(grid, src, dst, bd, log2_ctb, ctb_w, ctb_h, cfi, tb, tx, tq);
+    else        k_sao<uint8_t><<<blocks, 256, 0, st>>>(grid, src, dst, bd, log2_ctb, ctb_w, ctb_h, cfi, tb, tx, tq);
     return 1;
 }
 

@@ -24,6 +24,7 @@ struct B200Rec {
     std::vector<B200IntraRec> intra;
     std::vector<B200McRec> mc;
     std::vector<uint32_t> cip;   // B200CipHeader + bitmap of a constrained_intra_pred picture (b200_rec_set_cip), else empty
+    std::vector<uint32_t> tqb;   // B200CipHeader + bitmap of the PUs restore_tqb_pixels gives their deblocked samples back (b200_rec_set_tqb)
     int last_intra[3];
     bool any_dbk = false, any_sao = false, open = false;
     bool merged = false;         // holds lists of several recording threads: intra records need re-ordering at finish
@@ -134,7 +135,7 @@ extern "C" int b200_rec_begin(B200Rec *r, int cur_slot, int poc)
     if (!r || cur_slot < 0 || cur_slot > 255) return B200_EINVAL;
     memset(r->blob + r->off_dbk, 0, r->off_pool - r->off_dbk);
     for (int s = 0; s < 4; s++) r->tu[s].clear();
-    r->intra.clear(); r->mc.clear(); r->cip.clear();
+    r->intra.clear(); r->mc.clear(); r->cip.clear(); r->tqb.clear();
     r->ncoef = 0; r->npark = 0; r->any_dbk = r->any_sao = false;
     r->last_intra[0] = r->last_intra[1] = r->last_intra[2] = -1;
     r->cur_slot = cur_slot; r->poc = poc; r->open = true; r->nbytes = 0; r->n_ref = 0; r->merged = false;
@@ -350,6 +351,22 @@ extern "C" int b200_rec_set_cip(B200Rec *r, int log2_min_pu_size, int min_pu_wid
     return 0;
 }
 
+// streams with transquant_bypass_enable / pcm_loop_filter_disabled AND SAO: s->is_pcm[] (one byte per min-PU, row-major,
+// non-zero = the PU keeps its deblocked samples), once all CTBs are parsed (hevc_filter.c:163-193)
+extern "C" int b200_rec_set_tqb(B200Rec *r, int log2_min_pu_size, int min_pu_width, int min_pu_height, const uint8_t *is_pcm)
+{
+    if (!r || !r->open || !is_pcm || log2_min_pu_size < 2 || log2_min_pu_size > 5 || min_pu_width <= 0 || min_pu_height <= 0 ||
+        min_pu_width != (r->cfg.width >> log2_min_pu_size) || min_pu_height != (r->cfg.height >> log2_min_pu_size)) return B200_EINVAL;
+    bool any = false;
+    r->tqb.assign(B200_CIP_WORDS(min_pu_width, min_pu_height), 0u);
+    r->tqb[0] = (uint32_t)log2_min_pu_size; r->tqb[1] = (uint32_t)min_pu_width; r->tqb[2] = (uint32_t)min_pu_height;
+    for (int y = 0; y < min_pu_height; y++)
+        for (int x = 0; x < min_pu_width; x++)
+            if (is_pcm[(size_t)y * min_pu_width + x]) { const size_t i = (size_t)y * min_pu_width + x; r->tqb[4 + (i >> 5)] |= 1u << (i & 31); any = true; }
+    if (!any) r->tqb.clear();                               // nothing to restore in this picture
+    return 0;
+}
+
 extern "C" int b200_rec_finish(B200Rec *r, const void **blob, uint64_t *nbytes)
 {
     if (!r || !r->open || !blob || !nbytes) return B200_EINVAL;
@@ -411,6 +428,26 @@ extern "C" int b200_rec_finish(B200Rec *r, const void **blob, uint64_t *nbytes)
         h->flags |= B200_FRAME_CIP;
         memcpy(r->blob + o, r->cip.data(), r->cip.size() * 4);
         o = (o + r->cip.size() * 4 + 255) & ~(uint64_t)255;
+    }
+    if (!r->tqb.empty() && r->any_sao) {                     // restore_tqb_pixels only ever runs behind the SAO of a CTB
+        if (o + r->tqb.size() * 4 + 256 > r->cap) return B200_ENOMEM;
+        h->tqb.off = (uint32_t)o; h->tqb.count = (uint32_t)r->tqb.size();
+        h->flags |= B200_FRAME_TQB;
+        memcpy(r->blob + o, r->tqb.data(), r->tqb.size() * 4);
+        o = (o + r->tqb.size() * 4 + 255) & ~(uint64_t)255;
+        // mark the CTBs that contain such PUs (all three planes): the SAO kernel looks at the bitmap only there
+        const int lp = (int)r->tqb[0], pw_ = (int)r->tqb[1], ph_ = (int)r->tqb[2], per = (1 << r->cfg.log2_ctb_size) >> lp;
+        B200SaoRec *g = (B200SaoRec *)(r->blob + r->off_sao);
+        for (int cy = 0; cy < r->ctb_h; cy++)
+            for (int cx = 0; cx < r->ctb_w; cx++) {
+                bool any = false;
+                for (int y = cy * per; y < (cy + 1) * per && y < ph_ && !any; y++)
+                    for (int x = cx * per; x < (cx + 1) * per && x < pw_; x++) {
+                        const size_t i = (size_t)y * pw_ + x;
+                        if ((r->tqb[4 + (i >> 5)] >> (i & 31)) & 1) { any = true; break; }
+                    }
+                if (any) for (int pl = 0; pl < 3; pl++) g[(pl * r->ctb_h + cy) * r->ctb_w + cx].tqb = 1;
+            }
     }
     h->total_bytes = (uint32_t)o;
     r->nbytes = o; r->open = false;

@@ -16,7 +16,7 @@
  * threads of ONE picture (-f 2, execute2 jobs, hevc.c:3082): a worker attaches itself to the picture in progress on its
  * first table call, records into its own B200Rec, and b200_frame_end folds the workers into the owner's recorder
  * (b200_rec_merge).  Frame and slice threads combined (-f 4) are rejected: a table call carries no context, so a worker
- * cannot tell which of several pictures in progress it belongs to.  One decoder instance per process.  cross-component prediction / pcm+transquant-bypass SAO restore are
+ * cannot tell which of several pictures in progress it belongs to.  One decoder instance per process.  4:4:4 cross-component prediction is
  * rejected with an error from b200_frame_end.
  */
 #include <stdint.h>
@@ -481,10 +481,6 @@ int b200_frame_begin(HEVCContext *s)
         fail(B200_ENOTSUP, "cross_component_prediction (4:4:4, hevc.c:1325-1327) is not supported by the B200 path");
         return g.err;
     }
-    if (s->sps->sao_enabled && (s->pps->transquant_bypass_enable_flag || (s->sps->pcm.loop_filter_disable_flag && s->sps->pcm_enabled_flag))) {
-        fail(B200_ENOTSUP, "SAO together with transquant_bypass / pcm_loop_filter_disabled (restore_tqb_pixels, hevc_filter.c:163-193) is not supported by the B200 path");
-        return g.err;
-    }
     pthread_mutex_lock(&G.mu);
     const int erc = ensure_ctx(s);
     if (!erc) g.ticket = G.next_ticket++;
@@ -539,6 +535,12 @@ int b200_frame_end(HEVCContext *s)
             if (crc) fail(crc, "b200_rec_set_cip failed");
             free(map);
         }
+    }
+    if (!g.err && s->sps->sao_enabled && s->is_pcm &&
+        (s->pps->transquant_bypass_enable_flag || (s->sps->pcm.loop_filter_disable_flag && s->sps->pcm_enabled_flag))) {
+        /* restore_tqb_pixels (hevc_filter.c:163-193) is pixel work outside the tables: the device redoes it from is_pcm[] */
+        int crc = b200_rec_set_tqb(g.rec, s->sps->log2_min_pu_size, s->sps->min_pu_width, s->sps->min_pu_height, s->is_pcm);
+        if (crc) fail(crc, "b200_rec_set_tqb failed");
     }
     if (g.err) { ticket_release(); return g.err; }
     if (getenv("B200_SHIM_STATS"))

@@ -16,7 +16,7 @@ INF_UP_LEFT, INF_UP, INF_UP_RIGHT, INF_LEFT, INF_BOTTOM_LEFT, INF_FILTER, INF_ST
 MCF_BI, MCF_WEIGHTED, MCF_CHROMA = 1, 2, 4
 SAO_NONE, SAO_BAND, SAO_EDGE = 0, 1, 2
 NO_RESID = 0xFFFFFFFF
-FRAME_HAS_DEBLOCK, FRAME_HAS_SAO, FRAME_CIP = 1, 2, 4
+FRAME_HAS_DEBLOCK, FRAME_HAS_SAO, FRAME_CIP, FRAME_TQB = 1, 2, 4, 8
 
 section_dt = np.dtype([("off", "<u4"), ("count", "<u4")])
 header_dt = np.dtype([
@@ -24,7 +24,7 @@ header_dt = np.dtype([
     ("width", "<u2"), ("height", "<u2"), ("chroma_format_idc", "u1"), ("bit_depth", "u1"),
     ("log2_ctb_size", "u1"), ("cur_slot", "u1"), ("flags", "<u4"),
     ("sec", section_dt, (SEC_COUNT,)), ("ref_slot", "u1", (16,)), ("n_ref", "u1"), ("pad", "u1", (3,)),
-    ("mc_big_count", "<u4"), ("cip", section_dt), ("reserved", "<u4", (64 - 15 - 2 * SEC_COUNT,)),
+    ("mc_big_count", "<u4"), ("cip", section_dt), ("tqb", section_dt), ("reserved", "<u4", (64 - 17 - 2 * SEC_COUNT,)),
 ])
 tu_dt = np.dtype([("x", "<u2"), ("y", "<u2"), ("plane", "u1"), ("log2", "u1"), ("kind", "u1"), ("flags", "u1"),
                   ("col_limit", "u1"), ("pad", "u1"), ("nnz", "<u2"), ("coeff_off", "<u4")])
@@ -34,7 +34,7 @@ mc_dt = np.dtype([("x", "<u2"), ("y", "<u2"), ("w", "u1"), ("h", "u1"), ("plane"
                   ("sx0", "<i2"), ("sy0", "<i2"), ("sx1", "<i2"), ("sy1", "<i2"), ("ref0", "u1"), ("ref1", "u1"),
                   ("frac0", "u1"), ("frac1", "u1"), ("w0", "<i2"), ("w1", "<i2"), ("o0", "<i2"), ("o1", "<i2"),
                   ("denom", "u1"), ("pad", "u1", (3,))])
-sao_dt = np.dtype([("type", "u1"), ("param", "u1"), ("borders", "u1"), ("edges", "u1"), ("variant", "u1"), ("pad", "u1"),
+sao_dt = np.dtype([("type", "u1"), ("param", "u1"), ("borders", "u1"), ("edges", "u1"), ("variant", "u1"), ("tqb", "u1"),
                    ("offset_val", "<i2", (5,))])
 assert header_dt.itemsize == 256 and tu_dt.itemsize == 16 and intra_dt.itemsize == 16 and mc_dt.itemsize == 32 and sao_dt.itemsize == 16
 
@@ -133,10 +133,12 @@ def level_order(intra, width, height, cfi):
 
 
 def build_blob(width, height, cfi, bit_depth, log2_ctb, cur_slot, poc=0, coeff=None, tu=None, intra=None, mc=None,
-               dbk=None, sao=None, out=None, ref_slots=(), cip=None):
+               dbk=None, sao=None, out=None, ref_slots=(), cip=None, tqb=None):
     """Assemble a blob.  tu: dict {2,3,4,5 -> tu_dt array}; dbk: uint16 array (DbkLayout.total) or None;
     sao: sao_dt array [3*ctb_count] or None.  `out`: optional uint8 buffer (e.g. pinned) to build into.
-    cip: None, or (log2_min_pu, bool array [min_pu_height, min_pu_width], True = intra PU) for a constrained_intra_pred picture."""
+    cip: None, or (log2_min_pu, bool array [min_pu_height, min_pu_width], True = intra PU) for a constrained_intra_pred picture.
+    tqb: None, or (log2_min_pu, bool array [min_pu_height, min_pu_width], True = PCM-without-loop-filter / transquant-bypass PU);
+    the CTBs of `sao` that contain such PUs are marked."""
     coeff = np.zeros(0, np.int16) if coeff is None else np.ascontiguousarray(coeff, np.int16)
     tu = tu or {}
     parts = [None] * SEC_COUNT
@@ -170,6 +172,25 @@ def build_blob(width, height, cfi, bit_depth, log2_ctb, cur_slot, poc=0, coeff=N
         hdr["cip"][0] = (off, len(cip_words))
         hdr["flags"] |= FRAME_CIP
         off = (off + cip_words.nbytes + 255) // 256 * 256
+    tqb_words = None
+    if tqb is not None and len(parts[SEC_SAO]):
+        log2_pu, bitmap = tqb
+        bitmap = np.ascontiguousarray(bitmap, bool)
+        bits = np.packbits(bitmap.reshape(-1), bitorder="little")
+        bits = np.concatenate([bits, np.zeros(-len(bits) % 4, np.uint8)]).view("<u4")
+        tqb_words = np.concatenate([np.array([log2_pu, bitmap.shape[1], bitmap.shape[0], 0], "<u4"), bits])
+        hdr["tqb"][0] = (off, len(tqb_words))
+        hdr["flags"] |= FRAME_TQB
+        off = (off + tqb_words.nbytes + 255) // 256 * 256
+        # mark the CTBs
+        per = (1 << log2_ctb) >> log2_pu
+        cw, ch = (width + (1 << log2_ctb) - 1) >> log2_ctb, (height + (1 << log2_ctb) - 1) >> log2_ctb
+        g = parts[SEC_SAO] = parts[SEC_SAO].copy()
+        for cy in range(ch):
+            for cx in range(cw):
+                if bitmap[cy * per:(cy + 1) * per, cx * per:(cx + 1) * per].any():
+                    for pl in range(3):
+                        g["tqb"][(pl * ch + cy) * cw + cx] = 1
     hdr["total_bytes"] = off
     if out is None:
         out = np.zeros(off, np.uint8)
@@ -183,6 +204,9 @@ def build_blob(width, height, cfi, bit_depth, log2_ctb, cur_slot, poc=0, coeff=N
     if cip_words is not None:
         o = int(hdr["cip"][0]["off"])
         out[o:o + cip_words.nbytes] = cip_words.view(np.uint8)
+    if tqb_words is not None:
+        o = int(hdr["tqb"][0]["off"])
+        out[o:o + tqb_words.nbytes] = tqb_words.view(np.uint8)
     return out
 
 

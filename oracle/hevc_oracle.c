@@ -629,6 +629,30 @@ void orc_sao_ctb(const B200SaoRec *s, pix_t *dst, const pix_t *src, int stride, 
         }
 }
 
+/* restore_tqb_pixels (hevc_filter.c:163-193), called after the SAO of a CTB whose type is band or edge: PUs flagged in
+ * is_pcm[] (PCM with pcm_loop_filter_disabled, cu_transquant_bypass) get their pre-SAO samples back.  Restated with the two
+ * things the reference really does:
+ *  - it is called with the LUMA origin of the CTB but the width / height of the CTB in the plane being filtered
+ *    (hevc_filter.c:275,316), so for subsampled chroma only the PUs of the first half of the CTB are visited;
+ *  - a row of a PU is copied with memcpy(.., min_pu_size >> hshift) -- a length in samples used as bytes, so for
+ *    bit depths above 8 only the first half of each row comes back.
+ * x0l, y0l: luma origin of the CTB; w, h: size of the CTB in this plane; B: bytes per sample. */
+static void orc_restore_tqb(pix_t *dst, const pix_t *src, int stride, int x0l, int y0l, int w, int h, int hs, int vs, int B,
+                            int log2_pu, int pu_w, const uint32_t *bits)
+{
+    const int pu = 1 << log2_pu;
+    const int x_min = x0l >> log2_pu, y_min = y0l >> log2_pu, x_max = (x0l + w) >> log2_pu, y_max = (y0l + h) >> log2_pu;
+    const int len_samples = (pu >> hs) / B;
+    for (int y = y_min; y < y_max; y++)
+        for (int x = x_min; x < x_max; x++) {
+            const long i = (long)y * pu_w + x;
+            if (!((bits[i >> 5] >> (i & 31)) & 1)) continue;
+            const int px = (x << log2_pu) >> hs, py = (y << log2_pu) >> vs;
+            for (int n = 0; n < (pu >> vs); n++)
+                for (int k = 0; k < len_samples; k++) dst[(py + n) * stride + px + k] = src[(py + n) * stride + px + k];
+        }
+}
+
 /* ------------------------------------------------------------------------------------------
  * Whole-picture executor: the CPU statement of what the GPU stages K1..K5 compute for one blob.
  * planes[slot*3 + c] = uint16 plane of DPB slot `slot`, stride = plane width.
@@ -713,6 +737,13 @@ int orc_execute_blob(const uint8_t *blob, uint16_t **planes, int n_slots)
         for (int p = 0; p < 3; p++) deblock_plane(cur[p], pw[p], ph[p], p, grid, &L, bd);
     }
     /* K5 SAO */
+    const uint32_t *tqb_bits = NULL;
+    int tqb_log2 = 2, tqb_w = 0;
+    if ((h->flags & B200_FRAME_TQB) && h->tqb.count >= 4) {
+        const uint32_t *tw = (const uint32_t *)(blob + h->tqb.off);
+        if (h->tqb.count < B200_CIP_WORDS(tw[1], tw[2])) return -7;
+        tqb_log2 = (int)tw[0]; tqb_w = (int)tw[1]; tqb_bits = tw + 4;
+    }
     if (h->sec[B200_SEC_SAO].count) {
         const B200SaoRec *sg = (const B200SaoRec *)(blob + h->sec[B200_SEC_SAO].off);
         const int ctb = 1 << h->log2_ctb_size;
@@ -731,6 +762,8 @@ int orc_execute_blob(const uint8_t *blob, uint16_t **planes, int n_slots)
                     if (w > pw[p] - x0) w = pw[p] - x0;
                     if (hh > ph[p] - y0) hh = ph[p] - y0;
                     orc_sao_ctb(s, cur[p], copy, pw[p], x0, y0, w, hh, bd);
+                    if (tqb_bits) orc_restore_tqb(cur[p], copy, pw[p], cx << h->log2_ctb_size, cy << h->log2_ctb_size, w, hh, hs, vs,
+                                                  bd > 8 ? 2 : 1, tqb_log2, tqb_w, tqb_bits);
                 }
             free(copy);
         }

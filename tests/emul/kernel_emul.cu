@@ -18,8 +18,11 @@ static void describe(FrameDesc &f, uint8_t *const planes[3], const int pitch[3],
 
 // same geometry as launch_sao() in kernels.cu
 extern "C" int emul_sao(const B200SaoRec *grid, uint8_t *const src_planes[3], uint8_t *const dst_planes[3], const int pitch[3],
-                        int width, int height, int cfi, int bd, int log2_ctb)
+                        int width, int height, int cfi, int bd, int log2_ctb, const uint32_t *tqb_words)
 {
+    TqbDesc tq;
+    tq.bits = nullptr; tq.log2_pu = 2; tq.pu_w = 0;
+    if (tqb_words) { tq.bits = tqb_words + 4; tq.log2_pu = (int)tqb_words[0]; tq.pu_w = (int)tqb_words[1]; }
     FrameDesc src, dst;
     describe(src, src_planes, pitch, width, height, cfi);
     describe(dst, dst_planes, pitch, width, height, cfi);
@@ -37,8 +40,8 @@ extern "C" int emul_sao(const B200SaoRec *grid, uint8_t *const src_planes[3], ui
     const int3 tx = make_int3(ntx[0], ntx[1], ntx[2]);
     for (int warp = 0; warp < blocks * 8; warp++)
         for (int lane = 0; lane < 32; lane++) {
-            if (bd > 8) sao_thread<uint16_t>(grid, src, dst, bd, log2_ctb, ctb_w, ctb_h, cfi, tb, tx, warp, lane);
-            else        sao_thread<uint8_t>(grid, src, dst, bd, log2_ctb, ctb_w, ctb_h, cfi, tb, tx, warp, lane);
+            if (bd > 8) sao_thread<uint16_t>(grid, src, dst, bd, log2_ctb, ctb_w, ctb_h, cfi, tb, tx, tq, warp, lane);
+            else        sao_thread<uint8_t>(grid, src, dst, bd, log2_ctb, ctb_w, ctb_h, cfi, tb, tx, tq, warp, lane);
         }
     return 0;
 }

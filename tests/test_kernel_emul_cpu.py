@@ -99,7 +99,7 @@ def test_sao_thread_code_equals_oracle(emul, w, h, cfi, bd, log2_ctb, restore, b
             pitches.append(pitch); s_bufs.append(sb); d_bufs.append(db)
         sp = (C.c_void_p * 3)(*[b.ctypes.data for b in s_bufs])
         dp = (C.c_void_p * 3)(*[b.ctypes.data for b in d_bufs])
-        rc = emul.emul_sao(grid.ctypes.data_as(C.c_void_p), sp, dp, (C.c_int * 3)(*pitches), w, h, cfi, bd, log2_ctb)
+        rc = emul.emul_sao(grid.ctypes.data_as(C.c_void_p), sp, dp, (C.c_int * 3)(*pitches), w, h, cfi, bd, log2_ctb, None)
         assert rc == 0
         for p in range(3):
             pw, ph = W.plane_dims(w, h, cfi, p)
@@ -241,3 +241,40 @@ def test_mc_phase_code_equals_oracle(emul, w, h, cfi, bd, kw):
             bad = np.argwhere(got != want[p])
             assert len(bad) == 0, (f"seed {seed} plane {p}: {len(bad)} samples differ, first at (y,x)={tuple(bad[0])} "
                                    f"got {got[tuple(bad[0])]} want {want[p][tuple(bad[0])]}")
+
+
+@pytest.mark.parametrize("w,h,cfi,bd,log2_ctb", [(256, 128, 1, 8, 6), (256, 128, 1, 10, 6), (200, 104, 1, 10, 5), (192, 128, 2, 10, 6), (192, 128, 3, 12, 4)])
+def test_sao_restore_of_bypass_pus_equals_oracle(emul, w, h, cfi, bd, log2_ctb):
+    """restore_tqb_pixels (hevc_filter.c:163-193) as the SAO kernel does it (sao_restore_row) against the oracle's restatement,
+    with the reference's two quirks: chroma visits the PUs of half a CTB only, and above 8 bits half of each PU row comes back"""
+    for seed in range(2):
+        rng = np.random.default_rng(4000 + 10 * seed + w + bd)
+        grid = random_sao_grid(w, h, bd, log2_ctb, rng, restore=True, big_offsets=False)
+        pu = rng.random((h // 4, w // 4)) < (0.15 if seed else 0.6)
+        pu[:, : (1 << log2_ctb) // 4] = False                         # a column of CTBs without any such PU
+        src = noisy_planes(w, h, cfi, bd, rng, flat=False)
+        blob = W.build_blob(w, h, cfi, bd, log2_ctb, 0, sao=grid, tqb=(2, pu))
+        hdr, secs = W.parse_blob(blob)
+        assert int(hdr["flags"]) & W.FRAME_TQB and secs[W.SEC_SAO]["tqb"].any() and not secs[W.SEC_SAO]["tqb"].all()
+        want = oracle_lib.execute(blob, [src])
+        plain = oracle_lib.execute(W.build_blob(w, h, cfi, bd, log2_ctb, 0, sao=grid), [src])
+        assert any((a != b).any() for a, b in zip(want, plain)), "the restore changed nothing"
+        tqb_words = np.ascontiguousarray(blob[int(hdr["tqb"]["off"]):int(hdr["tqb"]["off"]) + 4 * int(hdr["tqb"]["count"])]).view("<u4")
+        g2 = np.ascontiguousarray(secs[W.SEC_SAO])
+        dt = np.uint16 if bd > 8 else np.uint8
+        B = np.dtype(dt).itemsize
+        pitches, s_bufs, d_bufs = [], [], []
+        for p in range(3):
+            pw, ph = W.plane_dims(w, h, cfi, p)
+            pitch = (pw * B + 255) // 256 * 256
+            sb = np.full((ph, pitch // B), 0x5a5a if bd > 8 else 0x5a, dt)
+            sb[:, :pw] = src[p]
+            pitches.append(pitch); s_bufs.append(sb); d_bufs.append(np.zeros_like(sb))
+        sp = (C.c_void_p * 3)(*[b.ctypes.data for b in s_bufs])
+        dp = (C.c_void_p * 3)(*[b.ctypes.data for b in d_bufs])
+        assert emul.emul_sao(g2.ctypes.data_as(C.c_void_p), sp, dp, (C.c_int * 3)(*pitches), w, h, cfi, bd, log2_ctb, tqb_words.ctypes.data_as(C.c_void_p)) == 0
+        for p in range(3):
+            pw, ph = W.plane_dims(w, h, cfi, p)
+            got = d_bufs[p][:, :pw].astype(np.uint16)
+            bad = np.argwhere(got != want[p])
+            assert len(bad) == 0, f"seed {seed} plane {p}: {len(bad)} samples differ, first at (y,x)={tuple(bad[0])} got {got[tuple(bad[0])]} want {want[p][tuple(bad[0])]}"

@@ -49,6 +49,32 @@ def test_constrained_intra_pred():
     run_sequence(192, 128, 3, 8, seeds=[68, 69], cip=True, p_intra=0.7, split_bias=0.4)
 
 
+def test_sao_restore_of_bypass_pus():
+    """transquant-bypass / PCM-without-loop-filter PUs get their deblocked samples back after SAO (restore_tqb_pixels,
+    hevc_filter.c:163-193, with the reference's two quirks): blob with a TQB bitmap, SAO kernel vs oracle"""
+    for (w, h, cfi, bd) in ((256, 128, 1, 8), (256, 128, 1, 10), (192, 128, 2, 10), (192, 128, 3, 8)):
+        eng = FrameEngine(w, h, cfi, bd, n_slots=2)
+        try:
+            for seed in (71, 72):
+                syn = FrameSynth(w, h, cfi, bd, seed=seed + bd, cur_slot=0, sao_restore=True)
+                blob, _ = syn.generate()
+                hdr, secs = W.parse_blob(blob)
+                rng = np.random.default_rng(seed)
+                pu = rng.random((h // 4, w // 4)) < 0.3
+                pu[:, :16] = False
+                blob2 = W.build_blob(w, h, cfi, bd, 6, 0, coeff=secs[W.SEC_COEFF], tu={k + 2: secs[W.SEC_TU4 + k] for k in range(4)}, intra=secs[W.SEC_INTRA],
+                                     dbk=secs[W.SEC_DBK], sao=secs[W.SEC_SAO], tqb=(2, pu))
+                got = eng.decode(blob2)
+                dpb = [[np.zeros_like(p) for p in smooth_frame(w, h, cfi, bd, 0)] for _ in range(2)]
+                want = oracle_lib.execute(blob2, dpb)
+                plain = oracle_lib.execute(blob, dpb)
+                assert any((a != b).any() for a, b in zip(want, plain)), "the restore changed nothing"
+                for p in range(3):
+                    assert (got[p] == want[p]).all(), f"{w}x{h} cfi {cfi} bd {bd} seed {seed} plane {p}"
+        finally:
+            eng.close()
+
+
 def test_intra_only_small_blocks():
     """all-intra with a deep quadtree: the TU-granular wavefront and every predictor / smoothing branch"""
     run_sequence(256, 256, 1, 8, seeds=[31], split_bias=2.0)

@@ -230,10 +230,11 @@ SIG_CTX_4x4 = [0, 1, 4, 5, 2, 3, 4, 5, 6, 6, 8, 8, 7, 7, 8, 8]
 
 
 class StreamGen:
-    def __init__(self, width, height, bit_depth=8, seed=1, qp=30, sao=True, ctb_log2=6, weighted=False, wpp=False, cip=False):
+    def __init__(self, width, height, bit_depth=8, seed=1, qp=30, sao=True, ctb_log2=6, weighted=False, wpp=False, cip=False, tqb=0.0):
         self.W, self.H, self.bd, self.qp, self.sao, self.ctb_log2 = width, height, bit_depth, qp, sao, ctb_log2
         self.weighted = weighted
         self.cip = cip                      # pps constrained_intra_pred_flag (hevcpred_template.c:116-249)
+        self.tqb = tqb                      # share of CUs with cu_transquant_bypass_flag (pps transquant_bypass_enable_flag when > 0)
         self.wpp = wpp                                                    # entropy_coding_sync: one CABAC substream per CTB row
         self.slice_type = 2                                               # 0 B, 1 P, 2 I
         self.nrefs = [0, 0]
@@ -305,7 +306,7 @@ class StreamGen:
         w.se(0); w.se(0)                                                   # cb / cr qp offsets
         w.u(1, 0)                                                          # slice chroma qp offsets present
         w.u(1, int(self.weighted)); w.u(1, int(self.weighted))             # weighted pred / bipred
-        w.u(1, 0)                                                          # transquant bypass
+        w.u(1, int(self.tqb > 0))                                          # transquant bypass
         w.u(1, 0); w.u(1, int(self.wpp))                                   # tiles, entropy_coding_sync (WPP)
         w.u(1, 1)                                                          # loop filter across slices
         w.u(1, 0)                                                          # deblocking filter control present
@@ -585,6 +586,8 @@ class StreamGen:
     def coding_unit(self, x0, y0, log2, depth):
         c, o, r = self.c, self.off, self.rng
         size = 1 << log2
+        if self.tqb > 0:                                                    # cu_transquant_bypass_flag (hevc.c:2371-2374): the residual is
+            c.encode(o["cu_transquant_bypass_flag"], int(r.random() < self.tqb))   # added untransformed, deblocking / SAO leave the CU alone
         if self.slice_type != 2:
             inc = 0
             if x0 > 0:
@@ -887,10 +890,11 @@ def main():
     ap.add_argument("--pattern", default="I", help='picture types after the IDR, e.g. "PB" (low-delay, 2 references)')
     ap.add_argument("--weighted", action="store_true")
     ap.add_argument("--cip", action="store_true", help="constrained_intra_pred_flag")
+    ap.add_argument("--tqb", type=float, default=0.0, help="share of CUs coded with cu_transquant_bypass_flag")
     ap.add_argument("--wpp", action="store_true", help="entropy_coding_sync_enabled_flag: one substream per CTB row + entry points")
     a = ap.parse_args()
     verify_tables_against_reference()
-    g = StreamGen(a.width, a.height, a.bit_depth, a.seed, a.qp, sao=not a.no_sao, weighted=a.weighted, wpp=a.wpp, cip=a.cip)
+    g = StreamGen(a.width, a.height, a.bit_depth, a.seed, a.qp, sao=not a.no_sao, weighted=a.weighted, wpp=a.wpp, cip=a.cip, tqb=a.tqb)
     data = g.stream(a.frames, a.pattern)
     open(a.out, "wb").write(data)
     print(f"wrote {a.out}: {len(data)} bytes, {a.frames} pictures {a.width}x{a.height} {a.bit_depth}-bit")
