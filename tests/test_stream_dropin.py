@@ -70,7 +70,10 @@ def test_hooked_decoder_with_frame_threads(stream):
         pytest.skip("oracle/_ref/decode_ref / decode_b200 not built")
     want = run("decode_ref", stream, threads=4)
     committed = open(stream[:-5] + ".md5").read().splitlines()
-    assert [l.split()[2:] for l in want] == [l.split()[2:] for l in committed[:len(want)]]
+    if not os.path.basename(stream).startswith("tqb_"):
+        # (transquant-bypass streams: the reference never clears s->is_pcm between pictures, hevc.c:147, so its own output
+        #  depends on the thread count there; the drop-in reads the same array and must follow the reference run the same way)
+        assert [l.split()[2:] for l in want] == [l.split()[2:] for l in committed[:len(want)]]
     if "/b_" in stream or "/p_" in stream:
         assert want == committed
     for rep in range(2):

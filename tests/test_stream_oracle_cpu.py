@@ -25,17 +25,41 @@ STREAMS = sorted(glob.glob(os.path.join(HERE, "golden", "streams", "*.hevc")))
 SMALL = [s for s in STREAMS if os.path.getsize(s) < 400_000]          # the 1080p / 4K streams run in the GPU suite
 
 
+@pytest.mark.parametrize("threads", ["1", "4", "4w"])
 @pytest.mark.parametrize("stream", SMALL, ids=[os.path.basename(s) for s in SMALL])
-def test_recorded_work_lists_through_the_oracle_equal_the_reference_decoder(stream):
+def test_recorded_work_lists_through_the_oracle_equal_the_reference_decoder(stream, threads):
+    """threads: "1"; "4" = four frame threads (pictures recorded concurrently, dumped in decode order by the shim's ticket);
+    "4w" = four WPP workers recording one picture together (merged by b200_rec_merge) -- streams with entry points only"""
     binary = os.path.join(REFDIR, "decode_b200")
     if not os.path.exists(binary):
         pytest.skip("oracle/_ref/decode_b200 not built (needs /root/reference)")
-    want = open(stream[:-5] + ".md5").read().splitlines()
+    if threads == "4w" and not os.path.basename(stream).startswith("wpp_"):
+        pytest.skip("no entry points: slice threads fall back to one thread")
+    # the arbiter is the UNMODIFIED decoder run the same way.  Single thread: that is the committed MD5 file.  With threads
+    # the reference may differ from itself: it never clears s->is_pcm between pictures (hevc.c:147, only allocated zeroed), so
+    # on transquant-bypass streams the flags a context sees depend on which pictures it decoded before -- i.e. on the
+    # thread count.  The drop-in reads the same array and must reproduce whatever the reference does with it.  (On streams
+    # shorter than the thread count the reference's flush logic, main_hm/main.c:283, also drops the delayed pictures.)
+    ref = subprocess.run([os.path.join(REFDIR, "decode_ref"), stream, threads], capture_output=True, text=True, timeout=600)
+    want = [l for l in ref.stdout.splitlines() if l.startswith("frame ")]
+    if threads == "1":
+        assert want == open(stream[:-5] + ".md5").read().splitlines()
+    if not want:
+        pytest.skip("the reference outputs no picture of this stream with that many threads")
     with tempfile.TemporaryDirectory() as d:
-        r = subprocess.run([binary, stream, "1", "quiet"], capture_output=True, text=True, timeout=600, env=dict(os.environ, B200_SHIM_DUMP=d))
+        r = subprocess.run([binary, stream, threads, "quiet"], capture_output=True, text=True, timeout=600,
+                           env=dict(os.environ, B200_SHIM_DUMP=d, B200_SHIM_STATS="1"))
         assert r.returncode == 0, r.stderr[-2000:]
+        gen_path = stream[:-5] + ".gen.txt"
+        if os.path.exists(gen_path) and threads != "4":      # B200_SHIM_STATS: the table calls per picture == what the generator wrote
+            import re                                        # (with frame threads the lines come in completion order)
+            gen = [tuple(int(v) for v in m.groups()) for m in re.finditer(r"intra_pred (\d+) transform_add (\d+) prediction units (\d+)", open(gen_path).read())]
+            got = [tuple(int(v) for v in m.groups()) for m in re.finditer(r"b200 picture \d+: intra_pred (\d+) transform_add (\d+) mc (\d+)", r.stderr)]
+            assert len(got) == len(gen)
+            for (gi, gt, gm), (wi, wt, wp) in zip(got, gen):
+                assert (gi, gt) == (wi, wt) and gm == 3 * wp
         blobs = sorted(glob.glob(os.path.join(d, "pic_*.blob")))
-        assert len(blobs) == len(want), f"{len(blobs)} work lists for {len(want)} pictures"
+        assert len(blobs) >= len(want), f"{len(blobs)} work lists for {len(want)} pictures"
         lib = oracle_lib.lib()
         slots = {}
         dummy = np.zeros(1, np.uint16)
@@ -52,5 +76,7 @@ def test_recorded_work_lists_through_the_oracle_equal_the_reference_decoder(stre
             flat = [slots[s][p] if s in slots else dummy for s in range(n_slots) for p in range(3)]
             ptrs = (C.c_void_p * len(flat))(*[a.ctypes.data for a in flat])
             assert lib.orc_execute_blob(blob.ctypes.data_as(C.c_void_p), ptrs, n_slots) == 0
+            if k >= len(want):
+                continue
             md5 = [hashlib.md5((pl.astype(np.uint8) if bd == 8 else pl.astype("<u2")).tobytes()).hexdigest() for pl in slots[cur]]
             assert f"frame {k} {w}x{h} bd{bd} " + " ".join(md5) == want[k], f"picture {k} of {os.path.basename(stream)}"
