@@ -333,7 +333,7 @@ def main():
                 seq = [seq[i] for i in rng.permutation(len(seq))]
                 cdpb = [smooth_frame(wl["width"], wl["height"], wl["cfi"], wl["bit_depth"], 7 + k) for k in range(3)]
                 threads = min(usable_cpus(), 256)
-                it = 2 if wl["width"] >= 3840 else 8
+                it = 6 if wl["width"] >= 3840 else 24       # ~20-30 s of CPU work (threads x it pictures)
                 sec = oracle_lib.ref_bench(seq, cdpb, threads, it)
                 cpu = {"value": threads * it / sec, "unit": UNIT, "cores": threads, "kind": "reference",
                        "sample": f"{threads * it} pictures of the same stream mix ({threads} threads x {it}), reference C tables via oracle/replay_ref.c, {sec:.1f} s"}

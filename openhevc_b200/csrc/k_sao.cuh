@@ -243,7 +243,8 @@ HD void sao_thread(const B200SaoRec *__restrict__ grid, const FrameDesc &src, co
             for (int j = 0; j <= SAO_R + 1; j++) c[j][2] = c[j][3] = prmt32(c[j][1], 0, 0x3232);
         }
     }
-    const SaoCtb t = sao_decode(rq, sp, cx, cy, lw, lh);
+    SaoCtb t = sao_decode(rq, sp, cx, cy, lw, lh);
+    if (!tq.bits) t.tqb = 0;                                        // a mark without a bitmap means nothing
     const int nrows = imin(SAO_R, sp.h - gy0);
     const int maxv = (1 << bd) - 1;
     const uint32_t maxv2 = (uint32_t)maxv * 0x10001u;
