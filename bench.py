@@ -152,12 +152,17 @@ def run_reference(args, wl, rank):
     sec = oracle_lib.ref_bench(seq, dpb, threads, it)
     n = threads * it
     fps = n / sec
+    try:
+        stages = {k: {"ms_per_picture_one_core": 1e3 * v / n} for k, v in oracle_lib.ref_bench_stages().items()}
+    except Exception:
+        stages = None
     line = {"metric": METRIC, "value": fps, "unit": UNIT, "impl": "reference", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": 1e3 * sec / max(1, n / 8), "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u16" if wl["bit_depth"] > 8 else "u8",
             "data": "synthetic", "config": {"workload": args.workload, "gop": "hierarchical-B 8, intra period 32", "pictures_timed": n},
             "mpixels_per_s": fps * wl["width"] * wl["height"] / 1e6,
             "cpu_baseline": {"value": fps, "unit": UNIT, "cores": threads, "kind": "reference",
-                             "sample": f"{n} pictures of the bench stream mix, {threads} threads x {it} pictures, reference C tables (-O3 -fno-tree-vectorize, no asm)"},
+                             "sample": f"{n} pictures of the bench stream mix, {threads} threads x {it} pictures, reference C tables (-O3 -fno-tree-vectorize, no asm)",
+                             "stages": stages},
             "e2e": {"value": fps, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), file=_REAL_STDOUT, flush=True)
 
@@ -337,6 +342,14 @@ def main():
                 sec = oracle_lib.ref_bench(seq, cdpb, threads, it)
                 cpu = {"value": threads * it / sec, "unit": UNIT, "cores": threads, "kind": "reference",
                        "sample": f"{threads * it} pictures of the same stream mix ({threads} threads x {it}), reference C tables via oracle/replay_ref.c, {sec:.1f} s"}
+                try:                             # the same work lists, per stage, on the host cores beside each GPU kernel
+                    st = oracle_lib.ref_bench_stages()
+                    S = sum(int(np.prod(eng.plane_shape(p))) for p in range(3))
+                    cpu["stages"] = {k: {"ms_per_picture_one_core": 1e3 * v / (threads * it),
+                                         "gpu_stage_speedup_vs_one_core": (v / (threads * it)) / (stage_ms[k] * 1e-3) if stage_ms.get(k) else None} for k, v in st.items()}
+                    cpu["msamples_per_s_one_core"] = S * threads * it / sum(st.values()) / 1e6
+                except Exception:
+                    pass
         except Exception as ex:                  # the baseline is a report, never a reason to lose the bench line
             cpu = {"value": None, "unit": UNIT, "cores": 0, "kind": "reference", "sample": f"failed: {ex}"}
 

@@ -36,6 +36,7 @@ typedef struct RefCtx {
     int *zs;
     int bd, B, cfi, W, H;
     int pw[3], ph[3];
+    uint64_t stage_ns[5];        /* time spent in the table calls of each stage: MC, residual, intra (+ its residuals), deblock, SAO */
     HEVCFrame refframe;          /* s->ref of a constrained_intra_pred picture: only tab_mvf[].pred_flag is read (hevcpred_template.c:35-40) */
     MvField *mvf;
 } RefCtx;
@@ -70,6 +71,8 @@ static void ref_ctx_free(RefCtx *c)
 }
 
 typedef struct HostFrame { uint8_t *p[3]; int stride[3]; } HostFrame;
+
+static uint64_t now_ns(void) { struct timespec t; clock_gettime(CLOCK_MONOTONIC, &t); return (uint64_t)t.tv_sec * 1000000000ull + (uint64_t)t.tv_nsec; }
 
 typedef struct Parked { uint32_t off; const B200TuRec *t; } Parked;
 static int cmp_park(const void *a, const void *b)
@@ -192,8 +195,11 @@ static int execute(RefCtx *c, const uint8_t *blob, uint8_t **planes, const int64
         c->pps->constrained_intra_pred_flag = 1;
     }
 
+    uint64_t tick = now_ns(), tock;
+#define STAGE_END(k) do { tock = now_ns(); c->stage_ns[k] += tock - tick; tick = tock; } while (0)
     const B200McRec *mc = (const B200McRec *)(blob + h->sec[B200_SEC_MC].off);
     for (uint32_t i = 0; i < h->sec[B200_SEC_MC].count; i++) replay_mc(c, h, &mc[i], cur, dpb);
+    STAGE_END(0);
 
     const int16_t *pool = (const int16_t *)(blob + h->sec[B200_SEC_COEFF].off);
     DECLARE_ALIGNED(32, int16_t, coeffs[32 * 32]);
@@ -232,6 +238,7 @@ static int execute(RefCtx *c, const uint8_t *blob, uint8_t **planes, const int64
         }
     }
     qsort(park, npark, sizeof(*park), cmp_park);
+    STAGE_END(1);
     const B200IntraRec *ir = (const B200IntraRec *)(blob + h->sec[B200_SEC_INTRA].off);
     for (uint32_t i = 0; i < h->sec[B200_SEC_INTRA].count; i++) {
         const B200IntraRec *r = &ir[i];
@@ -248,6 +255,7 @@ static int execute(RefCtx *c, const uint8_t *blob, uint8_t **planes, const int64
         }
     }
     free(park);
+    STAGE_END(2);
 
     if (h->sec[B200_SEC_DBK].count) {              /* every vertical edge of the picture, then every horizontal one */
         B200DbkLayout L;
@@ -274,6 +282,7 @@ static int execute(RefCtx *c, const uint8_t *blob, uint8_t **planes, const int64
                     }
             }
     }
+    STAGE_END(3);
     if (h->sec[B200_SEC_SAO].count) {              /* hevc_filter.c:255-319 with a whole-picture copy as sao_frame */
         const B200SaoRec *sg = (const B200SaoRec *)(blob + h->sec[B200_SEC_SAO].off);
         const int ctb = 1 << h->log2_ctb_size, cw = (c->W + ctb - 1) >> h->log2_ctb_size, ch = (c->H + ctb - 1) >> h->log2_ctb_size;
@@ -302,6 +311,8 @@ static int execute(RefCtx *c, const uint8_t *blob, uint8_t **planes, const int64
         }
         frame_free(c, &cp, 1);
     }
+    STAGE_END(4);
+#undef STAGE_END
     return 0;
 }
 
@@ -361,6 +372,10 @@ int ref_execute_blob_b200(const uint8_t *blob, uint8_t **planes, const int64_t *
 }
 
 /* ---- CPU baseline: `iters` pictures per thread, frame-parallel like the reference's frame threads --------- */
+static uint64_t g_stage_ns[5];                   /* thread-time per stage of the last ref_bench() run, summed over the threads */
+static pthread_mutex_t g_stage_mu = PTHREAD_MUTEX_INITIALIZER;
+void ref_bench_stage_seconds(double out[5]) { for (int k = 0; k < 5; k++) out[k] = 1e-9 * (double)g_stage_ns[k]; }
+
 typedef struct Job { const uint8_t *const *blobs; int n_blobs; uint8_t **planes; const int64_t *strides; int n_slots; int iters; int tid; int rc; pthread_barrier_t *bar; } Job;
 
 static void *worker(void *arg)
@@ -382,6 +397,9 @@ static void *worker(void *arg)
     pthread_barrier_wait(j->bar);               /* setup (private DPB copies) is outside the timed region */
     for (int i = 0; i < j->iters && !j->rc; i++) j->rc = execute(c, j->blobs[(i + j->tid) % j->n_blobs], pl, st, j->n_slots);
     for (int s = 0; s < j->n_slots; s++) frame_free(c, &own[s], 0);
+    pthread_mutex_lock(&g_stage_mu);
+    for (int k = 0; k < 5; k++) g_stage_ns[k] += c->stage_ns[k];
+    pthread_mutex_unlock(&g_stage_mu);
     ref_ctx_free(c);
     return NULL;
 }
@@ -390,6 +408,7 @@ static void *worker(void *arg)
 double ref_bench(const uint8_t *const *blobs, int n_blobs, uint8_t **planes, const int64_t *strides, int n_slots, int n_threads, int iters)
 {
     if (n_threads < 1 || n_threads > 256) return -1;
+    memset(g_stage_ns, 0, sizeof(g_stage_ns));
     pthread_t th[256]; Job jobs[256];
     struct timespec t0, t1;
     pthread_barrier_t bar;

@@ -61,6 +61,9 @@ def ref_lib():
         _ref.ref_execute_blob.argtypes = [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_int64), C.c_int]
         _ref.ref_bench.restype = C.c_double
         _ref.ref_bench.argtypes = [C.POINTER(C.c_void_p), C.c_int, C.POINTER(C.c_void_p), C.POINTER(C.c_int64), C.c_int, C.c_int, C.c_int]
+        if hasattr(_ref, "ref_bench_stage_seconds"):
+            _ref.ref_bench_stage_seconds.restype = None
+            _ref.ref_bench_stage_seconds.argtypes = [C.POINTER(C.c_double)]
     return _ref
 
 
@@ -110,6 +113,13 @@ def ref_bench(blobs, dpb, n_threads, iters):
     if t < 0:
         raise RuntimeError(f"ref_bench failed: {t}")
     return t
+
+
+def ref_bench_stages():
+    """thread-seconds the last ref_bench() run spent in the table calls of each stage (summed over its threads)"""
+    out = (C.c_double * 5)()
+    ref_lib().ref_bench_stage_seconds(out)
+    return dict(zip(("mc", "residual", "intra", "deblock", "sao"), [float(v) for v in out]))
 
 
 def check_decode_order(blob):
