@@ -41,7 +41,9 @@ struct B200Rec {
 extern "C" int b200_intra_level_order(const B200IntraRec *recs, uint32_t n, int width, int height, int cfi, uint32_t *perm)
 {
     if (!recs || !perm) return B200_EINVAL;
-    std::vector<uint32_t> lvl[3];
+    // scratch kept per thread: a picture needs ~3 MB of unit maps, and fresh vectors would be mmap'ed, faulted in and
+    // unmapped again for every picture (this runs on the decoding thread, between two pictures)
+    static thread_local std::vector<uint32_t> lvl[3], level, start;
     int fs[3];
     for (int p = 0; p < 3; p++) {
         int pw, ph;
@@ -49,7 +51,7 @@ extern "C" int b200_intra_level_order(const B200IntraRec *recs, uint32_t n, int 
         fs[p] = pw / 4 + 2;
         lvl[p].assign((size_t)fs[p] * (ph / 4 + 2), 0);
     }
-    std::vector<uint32_t> level(n);
+    level.assign(n, 0);
     uint32_t maxl = 0;
     for (uint32_t i = 0; i < n; i++) {
         const B200IntraRec &r = recs[i];
@@ -74,7 +76,7 @@ extern "C" int b200_intra_level_order(const B200IntraRec *recs, uint32_t n, int 
         if (level[i] > maxl) maxl = level[i];
         for (int y = 0; y < u; y++) for (int x = 0; x < u; x++) L[(size_t)(uy + y) * s + ux + x] = m + 1;
     }
-    std::vector<uint32_t> start(maxl + 2, 0);
+    start.assign(maxl + 2, 0);
     for (uint32_t i = 0; i < n; i++) start[level[i] + 1]++;
     for (uint32_t k = 0; k <= maxl; k++) start[k + 1] += start[k];
     for (uint32_t i = 0; i < n; i++) perm[start[level[i]]++] = i;
@@ -166,13 +168,35 @@ extern "C" int b200_rec_tu(B200Rec *r, int plane, int x, int y, int log2, int ki
         link = ir.x == x && ir.y == y && ir.log2 == log2 && ir.resid_off == B200_NO_RESID;
         if (intra_linked == 0) link = false;
     }
-    // sparse transport: most dequantised coefficients are zero, send (position, value) pairs
-    int nnz = 0;
-    for (int i = 0; i < n * n; i++) nnz += coeffs[i] != 0;
-    const bool sparse = kind != B200_TU_PCM && 2 * nnz < n * n;
+    // sparse transport: most dequantised coefficients are zero, send (position, value) pairs.
+    // One pass, four coefficients per test (the block is 8-byte aligned scratch of the decoder, hevc.h:1063): pairs are
+    // written straight into the pool while they stay below the size of a dense block, else the block is copied whole.
+    const int nn = n * n;
     uint32_t off;
-    int16_t *dst = pool_take(r, (link ? 2 : 0) + (sparse ? 2 * nnz : n * n), &off);
+    int16_t *dst = pool_take(r, (link ? 2 : 0) + nn, &off);           // room for either form; the unused tail is given back
     if (!dst) return B200_ENOMEM;
+    int16_t *pairs = dst + (link ? 2 : 0);
+    int nnz = 0;
+    bool sparse = kind != B200_TU_PCM;
+    if (sparse) {
+        const int limit = (nn - 1) / 2;                                // sparse iff 2 * nnz < nn
+        if (((uintptr_t)coeffs & 7) == 0) {
+            const uint64_t *w = (const uint64_t *)coeffs;
+            for (int q = 0; q < nn / 4 && nnz <= limit; q++) {
+                const uint64_t v = w[q];
+                if (!v) continue;
+                for (int k = 0; k < 4; k++) {
+                    const int16_t c = (int16_t)(v >> (16 * k));
+                    if (c) { if (nnz < limit) { pairs[2 * nnz] = (int16_t)(4 * q + k); pairs[2 * nnz + 1] = c; } nnz++; }
+                }
+            }
+        } else {
+            for (int i = 0; i < nn && nnz <= limit; i++)
+                if (coeffs[i]) { if (nnz < limit) { pairs[2 * nnz] = (int16_t)i; pairs[2 * nnz + 1] = coeffs[i]; } nnz++; }
+        }
+        sparse = nnz <= limit && 2 * nnz < nn;
+    }
+    r->ncoef = off + (link ? 2 : 0) + (sparse ? 2 * nnz : nn);        // give the unused tail back
     B200TuRec t;
     memset(&t, 0, sizeof(t));
     if (link) {
@@ -183,12 +207,9 @@ extern "C" int b200_rec_tu(B200Rec *r, int plane, int x, int y, int log2, int ki
         r->intra[li].resid_off = po;
         t.flags |= B200_TUF_PARK;
     }
-    if (sparse) {
-        for (int i = 0, e = 0; i < n * n; i++)
-            if (coeffs[i]) { dst[2 * e] = (int16_t)i; dst[2 * e + 1] = coeffs[i]; e++; }
-        t.nnz = (uint16_t)nnz;
-    } else {
-        memcpy(dst, coeffs, (size_t)n * n * 2);
+    if (sparse) t.nnz = (uint16_t)nnz;                                 // the pairs are in place
+    else {
+        memcpy(dst, coeffs, (size_t)nn * 2);
         t.nnz = B200_TU_DENSE;
     }
     t.x = (uint16_t)x; t.y = (uint16_t)y; t.plane = (uint8_t)plane; t.log2 = (uint8_t)log2; t.kind = (uint8_t)kind;
@@ -405,7 +426,8 @@ extern "C" int b200_rec_finish(B200Rec *r, const void **blob, uint64_t *nbytes)
         std::stable_sort(r->intra.begin(), r->intra.end(), [&](const B200IntraRec &a, const B200IntraRec &b) { return key(a) < key(b); });
     }
     if (!r->intra.empty()) {
-        std::vector<uint32_t> perm(r->intra.size());
+        static thread_local std::vector<uint32_t> perm;
+        perm.resize(r->intra.size());
         b200_intra_level_order(r->intra.data(), (uint32_t)r->intra.size(), r->cfg.width, r->cfg.height, r->cfg.chroma_format_idc, perm.data());
         B200IntraRec *dst = (B200IntraRec *)(r->blob + o);
         for (size_t i = 0; i < perm.size(); i++) dst[i] = r->intra[perm[i]];
