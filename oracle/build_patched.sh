@@ -24,7 +24,7 @@ sed -i -e "0,/^#include/s//$inc\n#include/" \
 # frame life cycle (hevc.c:3271 / 3446 / 4145)
 sed -i -e "0,/^#include/s//$inc\n#include/" \
        -e 's/^\(\s*\)ff_thread_finish_setup(s->avctx);/\1if ((ret = b200_frame_begin(s)) < 0) goto fail;\n&/' \
-       -e 's/^\(\s*\)s->is_decoded = 1;/&\n\1if ((ret = b200_frame_end(s)) < 0) goto fail;/' \
+       -e '/^\s*s->is_decoded = 1;/,/tiles_filters(s);/ s/^\(\s*\)tiles_filters(s);/&\n\1if ((ret = b200_frame_end(s)) < 0) goto fail;   \/* after the filters of tile threads *\//' \
        -e 's|^\(\s*\)/\* verify the SEI checksum \*/|\1if (s->is_decoded \&\& s->ref) b200_frame_readback(s, s->ref->frame);\n&|' "$P/hevc.c"
 for pat in ff_hevcdsp_init_b200 ff_hevcpred_init_b200 ff_videodsp_init_b200 b200_frame_begin b200_frame_end b200_frame_readback; do
   grep -q "$pat" "$P"/*.c || { echo "hook $pat was not inserted" >&2; exit 1; }

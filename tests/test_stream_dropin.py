@@ -24,7 +24,7 @@ def run(binary, stream, threads=1, env=None, want_stderr=False):
     return (frames, out.stderr) if want_stderr else frames
 
 
-WPP_STREAMS = [s for s in STREAMS if os.path.basename(s).startswith("wpp_")]
+WPP_STREAMS = [s for s in STREAMS if os.path.basename(s).startswith(("wpp_", "tiles_"))]      # streams with entry points: slice threads really run
 
 
 def test_streams_committed():

@@ -29,11 +29,12 @@ SMALL = [s for s in STREAMS if os.path.getsize(s) < 400_000]          # the 1080
 @pytest.mark.parametrize("stream", SMALL, ids=[os.path.basename(s) for s in SMALL])
 def test_recorded_work_lists_through_the_oracle_equal_the_reference_decoder(stream, threads):
     """threads: "1"; "4" = four frame threads (pictures recorded concurrently, dumped in decode order by the shim's ticket);
-    "4w" = four WPP workers recording one picture together (merged by b200_rec_merge) -- streams with entry points only"""
+    "4w" = four slice-thread workers (WPP rows, or tiles) recording one picture together (merged by b200_rec_merge) -- streams with
+    entry points only"""
     binary = os.path.join(REFDIR, "decode_b200")
     if not os.path.exists(binary):
         pytest.skip("oracle/_ref/decode_b200 not built (needs /root/reference)")
-    if threads == "4w" and not os.path.basename(stream).startswith("wpp_"):
+    if threads == "4w" and not os.path.basename(stream).startswith(("wpp_", "tiles_")):
         pytest.skip("no entry points: slice threads fall back to one thread")
     # the arbiter is the UNMODIFIED decoder run the same way.  Single thread: that is the committed MD5 file.  With threads
     # the reference may differ from itself: it never clears s->is_pcm between pictures (hevc.c:147, only allocated zeroed), so

@@ -230,11 +230,14 @@ SIG_CTX_4x4 = [0, 1, 4, 5, 2, 3, 4, 5, 6, 6, 8, 8, 7, 7, 8, 8]
 
 
 class StreamGen:
-    def __init__(self, width, height, bit_depth=8, seed=1, qp=30, sao=True, ctb_log2=6, weighted=False, wpp=False, cip=False, tqb=0.0):
+    def __init__(self, width, height, bit_depth=8, seed=1, qp=30, sao=True, ctb_log2=6, weighted=False, wpp=False, cip=False, tqb=0.0, tiles=None, lf_across_tiles=True):
         self.W, self.H, self.bd, self.qp, self.sao, self.ctb_log2 = width, height, bit_depth, qp, sao, ctb_log2
         self.weighted = weighted
         self.cip = cip                      # pps constrained_intra_pred_flag (hevcpred_template.c:116-249)
         self.tqb = tqb                      # share of CUs with cu_transquant_bypass_flag (pps transquant_bypass_enable_flag when > 0)
+        self.tiles = tiles                  # (columns, rows), uniform spacing: one CABAC substream + entry point per tile, tile scan
+        self.lf_across_tiles = lf_across_tiles
+        assert not (tiles and wpp), "WPP inside tiles is not generated"
         self.wpp = wpp                                                    # entropy_coding_sync: one CABAC substream per CTB row
         self.slice_type = 2                                               # 0 B, 1 P, 2 I
         self.nrefs = [0, 0]
@@ -307,7 +310,11 @@ class StreamGen:
         w.u(1, 0)                                                          # slice chroma qp offsets present
         w.u(1, int(self.weighted)); w.u(1, int(self.weighted))             # weighted pred / bipred
         w.u(1, int(self.tqb > 0))                                          # transquant bypass
-        w.u(1, 0); w.u(1, int(self.wpp))                                   # tiles, entropy_coding_sync (WPP)
+        w.u(1, int(bool(self.tiles))); w.u(1, int(self.wpp))               # tiles, entropy_coding_sync (WPP)
+        if self.tiles:
+            w.ue(self.tiles[0] - 1); w.ue(self.tiles[1] - 1)               # num_tile_columns_minus1, num_tile_rows_minus1
+            w.u(1, 1)                                                      # uniform_spacing_flag
+            w.u(1, int(self.lf_across_tiles))                              # loop_filter_across_tiles_enabled_flag
         w.u(1, 1)                                                          # loop filter across slices
         w.u(1, 0)                                                          # deblocking filter control present
         w.u(1, 0)                                                          # scaling list data
@@ -364,7 +371,7 @@ class StreamGen:
             wb = BitWriter(); wb.bits = bits
             data += wb.bytes()
             ends.append(len(data))
-        if self.wpp:
+        if self.wpp or self.tiles:
             # entry points count the bytes of the NAL unit INCLUDING emulation prevention bytes (7.4.7.1); the header
             # ends in a non-zero byte (alignment bit), so the zero run restarts at the first byte of the slice data
             pos, zeros, n = [0], 0, 0
@@ -412,8 +419,21 @@ class StreamGen:
         self.skip = np.zeros((self.H >> 3, self.W >> 3), np.int32)
         n = self.cw * self.ch
         saved = None
+        # CTB order: raster, or tile scan (6.5.1) with uniformly spaced tiles; tile_x0 / tile_y0 = first CTB column / row of the
+        # tile a CTB belongs to (neighbours outside the tile are unavailable, 6.4.1)
+        if self.tiles:
+            ncol, nrow = self.tiles
+            cb = [(i * self.cw) // ncol for i in range(ncol + 1)]
+            rb = [(j * self.ch) // nrow for j in range(nrow + 1)]
+            order = [(x, y, cb[i], rb[j]) for j in range(nrow) for i in range(ncol) for y in range(rb[j], rb[j + 1]) for x in range(cb[i], cb[i + 1])]
+        else:
+            order = [(a % self.cw, a // self.cw, 0, 0) for a in range(n)]
         for a in range(n):
-            self.rx, self.ry = a % self.cw, a // self.cw
+            self.rx, self.ry, self.tile_x0, self.tile_y0 = order[a]
+            if self.tiles and a and (self.rx, self.ry) == (self.tile_x0, self.tile_y0):
+                # first CTB of a tile: new substream, the arithmetic coder and the contexts start afresh (9.3.1)
+                self.substreams.append(self.c.bits)
+                self.c = Cabac(self.init_rows[2 - self.slice_type], self.qp)
             if self.wpp and self.rx == 0 and a:
                 # new substream: arithmetic coder restarts, contexts come from the state stored after the 2nd CTB of the
                 # row above (9.3.1: synchronization; a picture one CTB wide re-initialises instead)
@@ -431,15 +451,24 @@ class StreamGen:
                     saved = [list(st) for st in self.c.state]              # storage process after the 2nd CTB of a row
                 if self.rx == self.cw - 1 and a != n - 1:
                     self.c.terminate(1)                                    # end_of_subset_one_bit, then byte_alignment()
+            if self.tiles and a != n - 1 and order[a + 1][:2] == order[a + 1][2:]:
+                self.c.terminate(1)                                        # last CTB of a tile: end_of_subset_one_bit
+
+    def left_ok(self, x0):
+        """is the block to the left of luma column x0 available (same tile; one slice per picture)?  lc->ctb_left_flag || x0b"""
+        return (x0 & ((1 << self.ctb_log2) - 1)) != 0 or self.rx > getattr(self, "tile_x0", 0)
+
+    def up_ok(self, y0):
+        return (y0 & ((1 << self.ctb_log2) - 1)) != 0 or self.ry > getattr(self, "tile_y0", 0)
 
     def sao_syntax(self):
         c, r, o = self.c, self.rng, self.off
-        if self.rx > 0:
+        if self.rx > self.tile_x0:
             m = int(r.random() < 0.2)
             c.encode(o["sao_merge_flag"], m)
             if m:
                 return
-        if self.ry > 0:
+        if self.ry > self.tile_y0:
             m = int(r.random() < 0.2)
             c.encode(o["sao_merge_flag"], m)
             if m:
@@ -473,9 +502,9 @@ class StreamGen:
         size = 1 << log2
         if x0 + size <= self.W and y0 + size <= self.H and log2 > self.min_cb_log2:
             inc = 0
-            if x0 > 0:
+            if self.left_ok(x0):
                 inc += int(self.ct_depth[y0 >> 3, (x0 >> 3) - 1] > depth)
-            if y0 > 0:
+            if self.up_ok(y0):
                 inc += int(self.ct_depth[(y0 >> 3) - 1, x0 >> 3] > depth)
             split = int(self.rng.random() < {6: 0.9, 5: 0.65, 4: 0.45}[log2])
             c.encode(o["split_coding_unit_flag"] + inc, split)
@@ -491,7 +520,7 @@ class StreamGen:
 
     def mpm_candidates(self, x0, y0):
         ctb = 1 << self.ctb_log2
-        left = self.ipm[y0 >> 2, (x0 >> 2) - 1] if x0 > 0 else 1
+        left = self.ipm[y0 >> 2, (x0 >> 2) - 1] if self.left_ok(x0) else 1
         up = self.ipm[(y0 >> 2) - 1, x0 >> 2] if (y0 > 0 and (y0 - 1) >= (y0 // ctb) * ctb) else 1
         if left == up:
             if left < 2:
@@ -590,9 +619,9 @@ class StreamGen:
             c.encode(o["cu_transquant_bypass_flag"], int(r.random() < self.tqb))   # added untransformed, deblocking / SAO leave the CU alone
         if self.slice_type != 2:
             inc = 0
-            if x0 > 0:
+            if self.left_ok(x0):
                 inc += int(self.skip[y0 >> 3, (x0 >> 3) - 1] != 0)
-            if y0 > 0:
+            if self.up_ok(y0):
                 inc += int(self.skip[(y0 >> 3) - 1, x0 >> 3] != 0)
             skipped = int(r.random() < 0.25)
             c.encode(o["skip_flag"] + inc, skipped)
@@ -891,10 +920,13 @@ def main():
     ap.add_argument("--weighted", action="store_true")
     ap.add_argument("--cip", action="store_true", help="constrained_intra_pred_flag")
     ap.add_argument("--tqb", type=float, default=0.0, help="share of CUs coded with cu_transquant_bypass_flag")
+    ap.add_argument("--tiles", default="", help="COLSxROWS uniformly spaced tiles, e.g. 3x2")
+    ap.add_argument("--no-lf-across-tiles", action="store_true", help="loop_filter_across_tiles_enabled_flag = 0")
     ap.add_argument("--wpp", action="store_true", help="entropy_coding_sync_enabled_flag: one substream per CTB row + entry points")
     a = ap.parse_args()
     verify_tables_against_reference()
-    g = StreamGen(a.width, a.height, a.bit_depth, a.seed, a.qp, sao=not a.no_sao, weighted=a.weighted, wpp=a.wpp, cip=a.cip, tqb=a.tqb)
+    g = StreamGen(a.width, a.height, a.bit_depth, a.seed, a.qp, sao=not a.no_sao, weighted=a.weighted, wpp=a.wpp, cip=a.cip, tqb=a.tqb,
+                  tiles=tuple(int(v) for v in a.tiles.split("x")) if a.tiles else None, lf_across_tiles=not a.no_lf_across_tiles)
     data = g.stream(a.frames, a.pattern)
     open(a.out, "wb").write(data)
     print(f"wrote {a.out}: {len(data)} bytes, {a.frames} pictures {a.width}x{a.height} {a.bit_depth}-bit")
