@@ -230,11 +230,13 @@ SIG_CTX_4x4 = [0, 1, 4, 5, 2, 3, 4, 5, 6, 6, 8, 8, 7, 7, 8, 8]
 
 
 class StreamGen:
-    def __init__(self, width, height, bit_depth=8, seed=1, qp=30, sao=True, ctb_log2=6, weighted=False, wpp=False, cip=False, tqb=0.0, tiles=None, lf_across_tiles=True):
+    def __init__(self, width, height, bit_depth=8, seed=1, qp=30, sao=True, ctb_log2=6, weighted=False, wpp=False, cip=False, tqb=0.0, tiles=None, lf_across_tiles=True, tskip=0.0):
         self.W, self.H, self.bd, self.qp, self.sao, self.ctb_log2 = width, height, bit_depth, qp, sao, ctb_log2
         self.weighted = weighted
         self.cip = cip                      # pps constrained_intra_pred_flag (hevcpred_template.c:116-249)
         self.tqb = tqb                      # share of CUs with cu_transquant_bypass_flag (pps transquant_bypass_enable_flag when > 0)
+        self.tskip = tskip                  # share of 4x4 TUs with transform_skip_flag (pps transform_skip_enabled_flag when > 0)
+        self.cu_bypass = 0
         self.tiles = tiles                  # (columns, rows), uniform spacing: one CABAC substream + entry point per tile, tile scan
         self.lf_across_tiles = lf_across_tiles
         assert not (tiles and wpp), "WPP inside tiles is not generated"
@@ -304,7 +306,7 @@ class StreamGen:
         w.ue(0); w.ue(0)
         w.se(0)                                                            # init_qp_minus26
         w.u(1, int(self.cip))                                              # constrained intra pred
-        w.u(1, 0)                                                          # transform skip
+        w.u(1, int(self.tskip > 0))                                        # transform skip (log2_max_transform_skip_block_size = 2)
         w.u(1, 0)                                                          # cu_qp_delta
         w.se(0); w.se(0)                                                   # cb / cr qp offsets
         w.u(1, 0)                                                          # slice chroma qp offsets present
@@ -615,8 +617,10 @@ class StreamGen:
     def coding_unit(self, x0, y0, log2, depth):
         c, o, r = self.c, self.off, self.rng
         size = 1 << log2
+        self.cu_bypass = 0
         if self.tqb > 0:                                                    # cu_transquant_bypass_flag (hevc.c:2371-2374): the residual is
-            c.encode(o["cu_transquant_bypass_flag"], int(r.random() < self.tqb))   # added untransformed, deblocking / SAO leave the CU alone
+            self.cu_bypass = int(r.random() < self.tqb)                    # added untransformed, deblocking / SAO leave the CU alone
+            c.encode(o["cu_transquant_bypass_flag"], self.cu_bypass)
         if self.slice_type != 2:
             inc = 0
             if self.left_ok(x0):
@@ -752,6 +756,8 @@ class StreamGen:
         lev = np.where(mask, mags * np.where(r.random((n, n)) < 0.5, -1, 1), 0)
         if not lev.any():
             lev[0, 0] = int(r.choice([-2, -1, 1, 3]))
+        if self.tskip > 0 and log2 == 2 and not self.cu_bypass:            # transform_skip_flag (hevc_cabac.c:1443-1446): first element of
+            c.encode(o["transform_skip_flag[][]"] + (1 if cidx else 0), int(r.random() < self.tskip))   # residual_coding()
         sb_order, pos_order = scan_tables(log2, scan_idx)
         # scan position list (sub-block index i, position n) in forward order
         def coord(i, k):
@@ -920,12 +926,13 @@ def main():
     ap.add_argument("--weighted", action="store_true")
     ap.add_argument("--cip", action="store_true", help="constrained_intra_pred_flag")
     ap.add_argument("--tqb", type=float, default=0.0, help="share of CUs coded with cu_transquant_bypass_flag")
+    ap.add_argument("--tskip", type=float, default=0.0, help="share of 4x4 TUs coded with transform_skip_flag")
     ap.add_argument("--tiles", default="", help="COLSxROWS uniformly spaced tiles, e.g. 3x2")
     ap.add_argument("--no-lf-across-tiles", action="store_true", help="loop_filter_across_tiles_enabled_flag = 0")
     ap.add_argument("--wpp", action="store_true", help="entropy_coding_sync_enabled_flag: one substream per CTB row + entry points")
     a = ap.parse_args()
     verify_tables_against_reference()
-    g = StreamGen(a.width, a.height, a.bit_depth, a.seed, a.qp, sao=not a.no_sao, weighted=a.weighted, wpp=a.wpp, cip=a.cip, tqb=a.tqb,
+    g = StreamGen(a.width, a.height, a.bit_depth, a.seed, a.qp, sao=not a.no_sao, weighted=a.weighted, wpp=a.wpp, cip=a.cip, tqb=a.tqb, tskip=a.tskip,
                   tiles=tuple(int(v) for v in a.tiles.split("x")) if a.tiles else None, lf_across_tiles=not a.no_lf_across_tiles)
     data = g.stream(a.frames, a.pattern)
     open(a.out, "wb").write(data)
