@@ -230,11 +230,12 @@ SIG_CTX_4x4 = [0, 1, 4, 5, 2, 3, 4, 5, 6, 6, 8, 8, 7, 7, 8, 8]
 
 
 class StreamGen:
-    def __init__(self, width, height, bit_depth=8, seed=1, qp=30, sao=True, ctb_log2=6, weighted=False, wpp=False, cip=False, tqb=0.0, tiles=None, lf_across_tiles=True, tskip=0.0):
+    def __init__(self, width, height, bit_depth=8, seed=1, qp=30, sao=True, ctb_log2=6, weighted=False, wpp=False, cip=False, tqb=0.0, tiles=None, lf_across_tiles=True, tskip=0.0, pcm=0.0, pcm_lf_off=False):
         self.W, self.H, self.bd, self.qp, self.sao, self.ctb_log2 = width, height, bit_depth, qp, sao, ctb_log2
         self.weighted = weighted
         self.cip = cip                      # pps constrained_intra_pred_flag (hevcpred_template.c:116-249)
         self.tqb = tqb                      # share of CUs with cu_transquant_bypass_flag (pps transquant_bypass_enable_flag when > 0)
+        self.pcm, self.pcm_lf_off = pcm, pcm_lf_off   # share of 2Nx2N intra CUs (8x8 .. 32x32) coded as PCM; pcm_loop_filter_disabled_flag
         self.tskip = tskip                  # share of 4x4 TUs with transform_skip_flag (pps transform_skip_enabled_flag when > 0)
         self.cu_bypass = 0
         self.tiles = tiles                  # (columns, rows), uniform spacing: one CABAC substream + entry point per tile, tile scan
@@ -287,7 +288,11 @@ class StreamGen:
         w.u(1, 0)                                                          # scaling lists
         w.u(1, 0)                                                          # amp
         w.u(1, 1 if self.sao else 0)                                       # sample_adaptive_offset_enabled
-        w.u(1, 0)                                                          # pcm
+        w.u(1, int(self.pcm > 0))                                          # pcm_enabled_flag
+        if self.pcm > 0:
+            w.u(4, self.bd - 1); w.u(4, self.bd - 1)                       # pcm sample bit depth luma / chroma (minus 1): full depth
+            w.ue(0); w.ue(2)                                               # log2_min_pcm_cb_size - 3 (8), log2_diff_max_min (.. 32)
+            w.u(1, int(self.pcm_lf_off))                                   # pcm_loop_filter_disabled_flag
         w.ue(0)                                                            # num_short_term_ref_pic_sets
         w.u(1, 0)                                                          # long term refs
         w.u(1, 0)                                                          # temporal mvp
@@ -661,6 +666,21 @@ class StreamGen:
         if log2 == self.min_cb_log2:
             nxn = int(r.random() < 0.35)
             c.encode(o["part_mode"], 1 - nxn)                              # bin 1 = PART_2Nx2N
+        if self.pcm > 0 and not nxn and 3 <= log2 <= 5:
+            # pcm_flag is a terminate bin (hevc.c:2406-2411); when set: the arithmetic codeword is flushed, the stream is byte
+            # aligned, the samples follow raw (luma, Cb, Cr; hls_pcm_sample, hevc.c:1587-1623), and the arithmetic engine --
+            # not the contexts -- starts afresh (9.3.2.5)
+            is_pcm = int(r.random() < self.pcm)
+            c.terminate(is_pcm)
+            if is_pcm:
+                c.bits += [0] * (-len(c.bits) % 8)                         # pcm_alignment_zero_bit
+                for npix in (size * size, (size >> 1) ** 2, (size >> 1) ** 2):
+                    for v in r.integers(0, 1 << self.bd, npix):
+                        c.bits += [(int(v) >> k) & 1 for k in range(self.bd - 1, -1, -1)]
+                c.low, c.range, c.outstanding, c.first = 0, 510, 0, True
+                self.ipm[y0 >> 2:(y0 + size) >> 2, x0 >> 2:(x0 + size) >> 2] = 1          # INTRA_DC for the neighbours' candidates
+                self.ct_depth[y0 >> 3:(y0 + size) >> 3, x0 >> 3:(x0 + size) >> 3] = depth
+                return
         parts = [(0, 0), (4, 0), (0, 4), (4, 4)] if nxn else [(0, 0)]
         pb = size >> nxn
         prev = [int(r.random() < 0.6) for _ in parts]
@@ -926,13 +946,15 @@ def main():
     ap.add_argument("--weighted", action="store_true")
     ap.add_argument("--cip", action="store_true", help="constrained_intra_pred_flag")
     ap.add_argument("--tqb", type=float, default=0.0, help="share of CUs coded with cu_transquant_bypass_flag")
+    ap.add_argument("--pcm", type=float, default=0.0, help="share of 2Nx2N intra CUs coded as PCM")
+    ap.add_argument("--pcm-lf-off", action="store_true", help="pcm_loop_filter_disabled_flag")
     ap.add_argument("--tskip", type=float, default=0.0, help="share of 4x4 TUs coded with transform_skip_flag")
     ap.add_argument("--tiles", default="", help="COLSxROWS uniformly spaced tiles, e.g. 3x2")
     ap.add_argument("--no-lf-across-tiles", action="store_true", help="loop_filter_across_tiles_enabled_flag = 0")
     ap.add_argument("--wpp", action="store_true", help="entropy_coding_sync_enabled_flag: one substream per CTB row + entry points")
     a = ap.parse_args()
     verify_tables_against_reference()
-    g = StreamGen(a.width, a.height, a.bit_depth, a.seed, a.qp, sao=not a.no_sao, weighted=a.weighted, wpp=a.wpp, cip=a.cip, tqb=a.tqb, tskip=a.tskip,
+    g = StreamGen(a.width, a.height, a.bit_depth, a.seed, a.qp, sao=not a.no_sao, weighted=a.weighted, wpp=a.wpp, cip=a.cip, tqb=a.tqb, tskip=a.tskip, pcm=a.pcm, pcm_lf_off=a.pcm_lf_off,
                   tiles=tuple(int(v) for v in a.tiles.split("x")) if a.tiles else None, lf_across_tiles=not a.no_lf_across_tiles)
     data = g.stream(a.frames, a.pattern)
     open(a.out, "wb").write(data)
