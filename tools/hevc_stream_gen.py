@@ -230,11 +230,13 @@ SIG_CTX_4x4 = [0, 1, 4, 5, 2, 3, 4, 5, 6, 6, 8, 8, 7, 7, 8, 8]
 
 
 class StreamGen:
-    def __init__(self, width, height, bit_depth=8, seed=1, qp=30, sao=True, ctb_log2=6, weighted=False, wpp=False, cip=False, tqb=0.0, tiles=None, lf_across_tiles=True, tskip=0.0, pcm=0.0, pcm_lf_off=False):
+    def __init__(self, width, height, bit_depth=8, seed=1, qp=30, sao=True, ctb_log2=6, weighted=False, wpp=False, cip=False, tqb=0.0, tiles=None, lf_across_tiles=True, tskip=0.0, pcm=0.0, pcm_lf_off=False, slices=1, lf_across_slices=True):
         self.W, self.H, self.bd, self.qp, self.sao, self.ctb_log2 = width, height, bit_depth, qp, sao, ctb_log2
         self.weighted = weighted
         self.cip = cip                      # pps constrained_intra_pred_flag (hevcpred_template.c:116-249)
         self.tqb = tqb                      # share of CUs with cu_transquant_bypass_flag (pps transquant_bypass_enable_flag when > 0)
+        self.slices, self.lf_across_slices = slices, lf_across_slices   # independent slices per picture, each starting a CTB row
+        assert slices == 1 or not (tiles or wpp), "several slices are generated without tiles / WPP only"
         self.pcm, self.pcm_lf_off = pcm, pcm_lf_off   # share of 2Nx2N intra CUs (8x8 .. 32x32) coded as PCM; pcm_loop_filter_disabled_flag
         self.tskip = tskip                  # share of 4x4 TUs with transform_skip_flag (pps transform_skip_enabled_flag when > 0)
         self.cu_bypass = 0
@@ -334,16 +336,34 @@ class StreamGen:
 
     # ---- slice ----------------------------------------------------------------------------------------------------
     def slice_nal(self, pic=0, slice_type=2):
-        """pic: decode-order index (== POC, low-delay); slice_type 2 I (IDR when pic == 0), 1 P, 0 B"""
+        """all slices of one picture.  pic: decode-order index (== POC, low-delay); slice_type 2 I (IDR when pic == 0), 1 P, 0 B"""
+        ctb = 1 << self.ctb_log2
+        self.cw, self.ch = (self.W + ctb - 1) >> self.ctb_log2, (self.H + ctb - 1) >> self.ctb_log2
+        self.ct_depth = np.zeros((self.H >> 3, self.W >> 3), np.int32)
+        self.ipm = np.ones((self.H >> 2, self.W >> 2), np.int32)           # INTRA_DC default
+        self.skip = np.zeros((self.H >> 3, self.W >> 3), np.int32)
+        self.cnt = dict(intra_pred=0, transform_add=0, pu=0)
+        nsl = max(1, min(self.slices, self.ch))
+        rows = [(j * self.ch) // nsl for j in range(nsl + 1)]             # slice j covers CTB rows rows[j] .. rows[j + 1] - 1
+        out = b""
+        for j in range(nsl):
+            out += self.one_slice(pic, slice_type, rows[j] * self.cw, rows[j + 1] * self.cw)
+        self.stats.append(dict(self.cnt))
+        return out
+
+    def one_slice(self, pic, slice_type, ctb_start, ctb_end):
         self.slice_type = slice_type
+        self.slice_start = ctb_start
         idr = pic == 0
         nref = 0 if slice_type == 2 else min(pic, 2)
         self.nrefs = [nref, nref if slice_type == 0 else 0]
         w = BitWriter()
-        w.u(1, 1)                                                          # first_slice_segment_in_pic
+        w.u(1, int(ctb_start == 0))                                        # first_slice_segment_in_pic
         if idr:
             w.u(1, 0)                                                      # no_output_of_prior_pics (IRAP)
         w.ue(0)                                                            # pps id
+        if ctb_start:
+            w.u(max(1, (self.cw * self.ch - 1).bit_length()), ctb_start)   # slice_segment_address, Ceil(Log2(PicSizeInCtbsY)) bits
         w.ue(slice_type)
         if not idr:
             w.u(8, pic & 255)                                              # pic_order_cnt_lsb
@@ -364,12 +384,10 @@ class StreamGen:
                 self.pred_weight_table(w)
             w.ue(5 - self.max_merge)                                       # five_minus_max_num_merge_cand
         w.se(self.qp - 26)                                                 # slice_qp_delta
-        w.u(1, 1)                                                          # slice_loop_filter_across_slices_enabled
+        w.u(1, int(self.lf_across_slices))                                 # slice_loop_filter_across_slices_enabled
         self.c = Cabac(self.init_rows[2 - slice_type], self.qp)
-        self.cnt = dict(intra_pred=0, transform_add=0, pu=0)
         self.substreams = []
-        self.slice_data()
-        self.stats.append(dict(self.cnt))
+        self.slice_data(ctb_start, ctb_end)
         self.substreams.append(self.c.bits)
         data = bytearray()
         ends = []
@@ -418,13 +436,9 @@ class StreamGen:
                     for _ in range(2):
                         w.se(int(r.integers(-20, 21))); w.se(int(r.integers(-20, 21)))
 
-    def slice_data(self):
-        ctb = 1 << self.ctb_log2
-        self.cw, self.ch = (self.W + ctb - 1) >> self.ctb_log2, (self.H + ctb - 1) >> self.ctb_log2
-        self.ct_depth = np.zeros((self.H >> 3, self.W >> 3), np.int32)
-        self.ipm = np.ones((self.H >> 2, self.W >> 2), np.int32)           # INTRA_DC default
-        self.skip = np.zeros((self.H >> 3, self.W >> 3), np.int32)
+    def slice_data(self, ctb_start=0, ctb_end=None):
         n = self.cw * self.ch
+        ctb_end = n if ctb_end is None else ctb_end
         saved = None
         # CTB order: raster, or tile scan (6.5.1) with uniformly spaced tiles; tile_x0 / tile_y0 = first CTB column / row of the
         # tile a CTB belongs to (neighbours outside the tile are unavailable, 6.4.1)
@@ -435,7 +449,7 @@ class StreamGen:
             order = [(x, y, cb[i], rb[j]) for j in range(nrow) for i in range(ncol) for y in range(rb[j], rb[j + 1]) for x in range(cb[i], cb[i + 1])]
         else:
             order = [(a % self.cw, a // self.cw, 0, 0) for a in range(n)]
-        for a in range(n):
+        for a in range(ctb_start, ctb_end):
             self.rx, self.ry, self.tile_x0, self.tile_y0 = order[a]
             if self.tiles and a and (self.rx, self.ry) == (self.tile_x0, self.tile_y0):
                 # first CTB of a tile: new substream, the arithmetic coder and the contexts start afresh (9.3.1)
@@ -452,30 +466,37 @@ class StreamGen:
             if self.sao:
                 self.sao_syntax()
             self.quadtree(self.rx << self.ctb_log2, self.ry << self.ctb_log2, self.ctb_log2, 0)
-            self.c.terminate(1 if a == n - 1 else 0)                       # end_of_slice_segment_flag
+            self.c.terminate(1 if a == ctb_end - 1 else 0)                 # end_of_slice_segment_flag
             if self.wpp:
                 if self.rx == 1 or (self.cw == 1):
                     saved = [list(st) for st in self.c.state]              # storage process after the 2nd CTB of a row
-                if self.rx == self.cw - 1 and a != n - 1:
+                if self.rx == self.cw - 1 and a != ctb_end - 1:
                     self.c.terminate(1)                                    # end_of_subset_one_bit, then byte_alignment()
-            if self.tiles and a != n - 1 and order[a + 1][:2] == order[a + 1][2:]:
+            if self.tiles and a != ctb_end - 1 and order[a + 1][:2] == order[a + 1][2:]:
                 self.c.terminate(1)                                        # last CTB of a tile: end_of_subset_one_bit
 
     def left_ok(self, x0):
         """is the block to the left of luma column x0 available (same tile; one slice per picture)?  lc->ctb_left_flag || x0b"""
-        return (x0 & ((1 << self.ctb_log2) - 1)) != 0 or self.rx > getattr(self, "tile_x0", 0)
+        return (x0 & ((1 << self.ctb_log2) - 1)) != 0 or self.ctb_left_ok()
 
     def up_ok(self, y0):
-        return (y0 & ((1 << self.ctb_log2) - 1)) != 0 or self.ry > getattr(self, "tile_y0", 0)
+        return (y0 & ((1 << self.ctb_log2) - 1)) != 0 or self.ctb_up_ok()
+
+    def ctb_left_ok(self):
+        """lc->ctb_left_flag (hls_decode_neighbour, hevc.c): the CTB to the left exists, in this tile and in this slice"""
+        return self.rx > self.tile_x0 and self.ry * self.cw + self.rx - 1 >= self.slice_start
+
+    def ctb_up_ok(self):
+        return self.ry > self.tile_y0 and (self.ry - 1) * self.cw + self.rx >= self.slice_start
 
     def sao_syntax(self):
         c, r, o = self.c, self.rng, self.off
-        if self.rx > self.tile_x0:
+        if self.ctb_left_ok():
             m = int(r.random() < 0.2)
             c.encode(o["sao_merge_flag"], m)
             if m:
                 return
-        if self.ry > self.tile_y0:
+        if self.ctb_up_ok():
             m = int(r.random() < 0.2)
             c.encode(o["sao_merge_flag"], m)
             if m:
@@ -948,13 +969,15 @@ def main():
     ap.add_argument("--tqb", type=float, default=0.0, help="share of CUs coded with cu_transquant_bypass_flag")
     ap.add_argument("--pcm", type=float, default=0.0, help="share of 2Nx2N intra CUs coded as PCM")
     ap.add_argument("--pcm-lf-off", action="store_true", help="pcm_loop_filter_disabled_flag")
+    ap.add_argument("--slices", type=int, default=1, help="independent slices per picture (each starts a CTB row)")
+    ap.add_argument("--no-lf-across-slices", action="store_true", help="slice_loop_filter_across_slices_enabled_flag = 0")
     ap.add_argument("--tskip", type=float, default=0.0, help="share of 4x4 TUs coded with transform_skip_flag")
     ap.add_argument("--tiles", default="", help="COLSxROWS uniformly spaced tiles, e.g. 3x2")
     ap.add_argument("--no-lf-across-tiles", action="store_true", help="loop_filter_across_tiles_enabled_flag = 0")
     ap.add_argument("--wpp", action="store_true", help="entropy_coding_sync_enabled_flag: one substream per CTB row + entry points")
     a = ap.parse_args()
     verify_tables_against_reference()
-    g = StreamGen(a.width, a.height, a.bit_depth, a.seed, a.qp, sao=not a.no_sao, weighted=a.weighted, wpp=a.wpp, cip=a.cip, tqb=a.tqb, tskip=a.tskip, pcm=a.pcm, pcm_lf_off=a.pcm_lf_off,
+    g = StreamGen(a.width, a.height, a.bit_depth, a.seed, a.qp, sao=not a.no_sao, weighted=a.weighted, wpp=a.wpp, cip=a.cip, tqb=a.tqb, tskip=a.tskip, pcm=a.pcm, pcm_lf_off=a.pcm_lf_off, slices=a.slices, lf_across_slices=not a.no_lf_across_slices,
                   tiles=tuple(int(v) for v in a.tiles.split("x")) if a.tiles else None, lf_across_tiles=not a.no_lf_across_tiles)
     data = g.stream(a.frames, a.pattern)
     open(a.out, "wb").write(data)
