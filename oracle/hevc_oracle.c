@@ -13,7 +13,11 @@
  * Parity pinning: the reference ships no golden vectors, so this file is
  * pinned against the reference's own C tables compiled from /root/reference into
  * oracle/_ref/libohevc_ref.so (oracle/build_ref.sh) by oracle/kat_ref.c, function by
- * function, and against committed fixtures in tests/golden/ produced by that harness.
+ * function, against committed fixtures in tests/golden/ produced by that harness, at picture
+ * level by oracle/replay_ref.c (the reference's functions in the decoder's call order), and at
+ * stream level: the real decoder parses the committed Annex-B streams with the recording tables
+ * installed (B200_SHIM_DUMP), this file executes the recorded work lists, and the per-plane MD5s
+ * must equal those of the unmodified decoder (tests/test_stream_oracle_cpu.py).
  */
 #include <stdint.h>
 #include <stdlib.h>
