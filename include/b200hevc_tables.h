@@ -8,8 +8,9 @@
  *   ff_hevcpred_init_b200  like ff_hevcpred_init_x86 (libavcodec/hevcpred.c:84, hevcpred.h:44)
  *   ff_videodsp_init_b200  like ff_videodsp_init_x86 (libavcodec/videodsp.c:51-58, videodsp.h:94-97)
  *   b200_frame_begin       after hevc_frame_start() has chosen the DPB slot      (libavcodec/hevc.c:3245)
- *   b200_frame_end         when every CTB of the picture has been parsed          (libavcodec/hevc.c:3446)
+ *   b200_frame_end         when every CTB of the picture has been parsed and filtered (libavcodec/hevc.c:3447-3449, after tiles_filters)
  *   b200_frame_readback    before the picture is hashed or output                 (libavcodec/hevc.c:4145, 4178)
+ *   b200_frame_fill        when generate_missing_ref() has filled a grey reference  (libavcodec/hevc_refs.c:538-606)
  *
  * The structs are the reference's own (opaque here); the implementation
  * (openhevc_b200/csrc/shim/hevcdsp_init_b200.c) is compiled against the reference headers.
@@ -29,6 +30,7 @@ struct HEVCPredContext;
 struct VideoDSPContext;
 struct HEVCContext;
 struct AVFrame;
+struct HEVCFrame;
 
 void ff_hevcdsp_init_b200(struct HEVCDSPContext *c, const int bit_depth);
 void ff_hevcpred_init_b200(struct HEVCPredContext *c, const int bit_depth);
@@ -37,6 +39,7 @@ void ff_videodsp_init_b200(struct VideoDSPContext *c, int bpc);
 int  b200_frame_begin(struct HEVCContext *s);
 int  b200_frame_end(struct HEVCContext *s);
 int  b200_frame_readback(struct HEVCContext *s, struct AVFrame *frame);
+int  b200_frame_fill(struct HEVCContext *s, struct HEVCFrame *frame);       /* grey reference picture (generate_missing_ref) */
 int  b200_frame_upload_ref(struct HEVCContext *s, struct AVFrame *frame);   /* host-only reference picture -> device slot */
 void b200_shim_close(void);
 const char *b200_shim_error(void);

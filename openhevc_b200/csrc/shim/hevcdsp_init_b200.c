@@ -83,6 +83,7 @@ typedef struct ShimThread {
     struct ShimThread *workers[MAX_WORKERS]; int n_workers;   /* owner: workers that recorded part of this picture */
     struct ShimThread *att; unsigned att_seq;            /* worker: the owner it is attached to */
     int n_tu, n_intra, n_pu, n_dbk, n_sao, frame_no;   /* B200_SHIM_STATS=1: table calls per picture (stderr) */
+    uint8_t fill_slot[16]; int n_fill;                  /* generate_missing_ref (hevc_refs.c:538): grey references this picture needs */
 } ShimThread;
 static __thread ShimThread g;
 
@@ -551,6 +552,16 @@ int b200_frame_end(HEVCContext *s)
     /* pictures enter the compute stream in decode order, whatever order the frame threads finish parsing in */
     pthread_mutex_lock(&G.mu);
     while (G.turn != g.ticket) pthread_cond_wait(&G.cv, &G.mu);
+    for (int i = 0; i < g.n_fill && !rc; i++) {      /* grey reference pictures, in decode order with everything else */
+        const int grey = 1 << (G.bd - 1);
+        if (G.dump_dir) {
+            char path[1024];
+            snprintf(path, sizeof(path), "%s/pic_%05d.fill", G.dump_dir, G.dump_no);
+            FILE *f = fopen(path, "a");
+            if (f) { fprintf(f, "%d %d\n", g.fill_slot[i], grey); fclose(f); } else rc = B200_EINVAL;
+        } else rc = b200_slot_fill(G.ctx, g.fill_slot[i], grey);
+    }
+    g.n_fill = 0;
     if (!rc && G.dump_dir) {
         char path[1024];
         snprintf(path, sizeof(path), "%s/pic_%05d.blob", G.dump_dir, G.dump_no++);
@@ -564,6 +575,19 @@ int b200_frame_end(HEVCContext *s)
     if (!rc && !G.dump_dir) rc = b200_wait_uploads(G.ctx);  /* this thread's recorder memory is reused by its next picture */
     if (rc) fail(rc, G.ctx ? b200_last_error(G.ctx) : "frame_end failed");
     return rc;
+}
+
+/* hevc_refs.c:538-606 generate_missing_ref: a reference the stream does not contain is replaced by a grey picture the host
+ * fills with memset; the device slot must hold the same.  Called while the RPS of the NEXT picture of this thread is set up
+ * (before its b200_frame_begin), executed in decode order at that picture's b200_frame_end. */
+int b200_frame_fill(HEVCContext *s, HEVCFrame *frame)
+{
+    if (g.err) return g.err;
+    const int slot = (int)(frame - s->DPB);
+    if (slot < 0 || slot >= 32) { fail(B200_EINVAL, "generate_missing_ref: frame is not in the DPB"); return g.err; }
+    if (g.n_fill == 16) { fail(B200_ENOTSUP, "more than 16 missing reference pictures"); return g.err; }
+    g.fill_slot[g.n_fill++] = (uint8_t)slot;
+    return 0;
 }
 
 int b200_frame_readback(HEVCContext *s, AVFrame *frame)

@@ -69,6 +69,11 @@ def test_recorded_work_lists_through_the_oracle_equal_the_reference_decoder(stre
             hdr, _ = W.parse_blob(blob)
             w, h, cfi, bd = int(hdr["width"]), int(hdr["height"]), int(hdr["chroma_format_idc"]), int(hdr["bit_depth"])
             cur = int(hdr["cur_slot"])
+            # grey reference pictures the decoder generated for this picture (generate_missing_ref -> b200_frame_fill)
+            if os.path.exists(path[:-5] + ".fill"):
+                for line in open(path[:-5] + ".fill"):
+                    sl, val = [int(v) for v in line.split()]
+                    slots[sl] = [np.full(W.plane_dims(w, h, cfi, p)[::-1], val, np.uint16) for p in range(3)]
             # a new picture in a slot starts from the decoder's fresh frame; the oracle overwrites every sample anyway
             slots[cur] = [np.zeros(W.plane_dims(w, h, cfi, p)[::-1], np.uint16) for p in range(3)]
             for i in range(int(hdr["n_ref"])):
