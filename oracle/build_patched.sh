@@ -1,6 +1,6 @@
 #!/bin/bash
 # TEST INFRASTRUCTURE — builds the reference decoder WITH the B200 hooks of INTEGRATION.md into
-# oracle/_ref/libohevc_b200.so: the four files that receive a hook are copied to oracle/_ref/patched/ (git-ignored),
+# oracle/_ref/libohevc_b200.so: the five files that receive a hook are copied to oracle/_ref/patched/ (git-ignored),
 # the hook lines are inserted with sed, every other object is reused from the plain reference build.
 # Needs /root/reference; on the GPU box the prebuilt library is used.
 set -euo pipefail

@@ -1,6 +1,6 @@
 """The real decoder, end to end: committed synthetic Annex-B streams (tools/hevc_stream_gen.py) decoded by
  (a) the UNMODIFIED reference (oracle/_ref/decode_ref -> libohevc_ref.so) and
- (b) the reference carrying the three table hooks + three frame hooks of INTEGRATION.md
+ (b) the reference carrying the three table hooks + four frame hooks of INTEGRATION.md
      (oracle/_ref/decode_b200 -> libohevc_b200.so -> libb200hevc_shim.so -> GPU),
 both through the public libOpenHevc* API, single thread and with frame threads (hevc -p 4 -f 1).  Per-picture plane MD5s must be identical
 (BASELINE config 1: 832x480 8-bit, I pictures, bit-exact gate)."""
