@@ -246,6 +246,8 @@ class StreamGen:
         self.wpp = wpp                                                    # entropy_coding_sync: one CABAC substream per CTB row
         self.slice_type = 2                                               # 0 B, 1 P, 2 I
         self.nrefs = [0, 0]
+        self.reorder = 0                    # sps_max_num_reorder_pics: 2 for the hierarchical-B plan of stream(pattern="RA")
+        self.plan = None
         self.max_merge = 3
         self.stats = []
         self.rng = np.random.default_rng(seed)
@@ -266,7 +268,7 @@ class StreamGen:
         w = BitWriter()
         w.u(4, 0); w.u(2, 3); w.u(6, 0); w.u(3, 0); w.u(1, 1); w.u(16, 0xFFFF)
         self.ptl(w)
-        w.u(1, 1); w.ue(4); w.ue(0); w.ue(0)                              # sub_layer_ordering_info, dpb 5, reorder 0, latency
+        w.u(1, 1); w.ue(4); w.ue(self.reorder); w.ue(0)                   # sub_layer_ordering_info, dpb 5, reorder, latency
         w.u(6, 0); w.ue(0)                                                 # max_layer_id, num_layer_sets_minus1
         w.u(1, 0)                                                          # timing info
         w.u(1, 0)                                                          # extension
@@ -283,7 +285,7 @@ class StreamGen:
         w.u(1, 0)                                                          # conformance window
         w.ue(self.bd - 8); w.ue(self.bd - 8)
         w.ue(4)                                                            # log2_max_poc_lsb - 4
-        w.u(1, 1); w.ue(4); w.ue(0); w.ue(0)
+        w.u(1, 1); w.ue(4); w.ue(self.reorder); w.ue(0)                   # sub_layer_ordering_info: dpb 5, num_reorder, latency
         w.ue(self.min_cb_log2 - 3); w.ue(self.ctb_log2 - self.min_cb_log2)
         w.ue(self.min_tb_log2 - 2); w.ue(self.max_tb_log2 - self.min_tb_log2)
         w.ue(2); w.ue(self.max_th_depth_intra)                             # max_transform_hierarchy_depth inter / intra
@@ -355,7 +357,13 @@ class StreamGen:
         self.slice_type = slice_type
         self.slice_start = ctb_start
         idr = pic == 0
-        nref = 0 if slice_type == 2 else min(pic, 2)
+        plan = self.plan[pic] if self.plan else None       # random access: POC and reference picture set from the GOP plan
+        poc = plan["poc"] if plan else pic
+        if plan and not idr:
+            ntot = len(plan["neg"]) + len(plan["pos"])
+            nref = min(ntot, 2)
+        else:
+            nref = 0 if slice_type == 2 else min(pic, 2)
         self.nrefs = [nref, nref if slice_type == 0 else 0]
         w = BitWriter()
         w.u(1, int(ctb_start == 0))                                        # first_slice_segment_in_pic
@@ -366,12 +374,21 @@ class StreamGen:
             w.u(max(1, (self.cw * self.ch - 1).bit_length()), ctb_start)   # slice_segment_address, Ceil(Log2(PicSizeInCtbsY)) bits
         w.ue(slice_type)
         if not idr:
-            w.u(8, pic & 255)                                              # pic_order_cnt_lsb
+            w.u(8, poc & 255)                                              # pic_order_cnt_lsb
             w.u(1, 0)                                                      # short_term_ref_pic_set_sps_flag
-            nneg = min(pic, 2)
-            w.ue(nneg); w.ue(0)                                            # num_negative_pics, num_positive_pics
-            for _ in range(nneg):
-                w.ue(0); w.u(1, 1)                                         # delta_poc_s0_minus1, used_by_curr_pic
+            if plan:
+                w.ue(len(plan["neg"])); w.ue(len(plan["pos"]))             # num_negative_pics, num_positive_pics
+                prev = poc
+                for q in plan["neg"]:                                      # closest first
+                    w.ue(prev - q - 1); w.u(1, 1); prev = q                # delta_poc_s0_minus1, used_by_curr_pic_s0
+                prev = poc
+                for q in plan["pos"]:
+                    w.ue(q - prev - 1); w.u(1, 1); prev = q                # delta_poc_s1_minus1, used_by_curr_pic_s1
+            else:
+                nneg = min(pic, 2)
+                w.ue(nneg); w.ue(0)                                        # num_negative_pics, num_positive_pics
+                for _ in range(nneg):
+                    w.ue(0); w.u(1, 1)                                     # delta_poc_s0_minus1, used_by_curr_pic
         if self.sao:
             w.u(1, 1); w.u(1, 1)                                           # slice_sao_luma / chroma
         if slice_type != 2:
@@ -942,7 +959,23 @@ class StreamGen:
             c.bypass_bits(p + rice, v - (((1 << p) + 2) << rice))
 
     def stream(self, frames, pattern="I"):
-        """pattern: picture types in decode order after the leading IDR, cycled, e.g. "PB"; "I" = all IDR"""
+        """pattern: picture types in decode order after the leading IDR, cycled, e.g. "PB"; "I" = all IDR;
+        "RA" = random access: hierarchical-B GOPs of 4 (decode order I0 P4 B2 B1 B3 P8 B6 B5 B7 ..., output in POC order)"""
+        if pattern == "RA":
+            self.reorder = 2
+            self.plan = [dict(poc=0, type=2, neg=[], pos=[])]
+            a = 4
+            while len(self.plan) < frames:
+                self.plan += [dict(poc=a, type=1, neg=[a - 4], pos=[]),
+                              dict(poc=a - 2, type=0, neg=[a - 4], pos=[a]),
+                              dict(poc=a - 3, type=0, neg=[a - 4], pos=[a - 2, a]),
+                              dict(poc=a - 1, type=0, neg=[a - 2], pos=[a])]
+                a += 4
+            self.plan = self.plan[:frames]
+            out = self.vps() + self.sps() + self.pps()
+            for k, pl in enumerate(self.plan):
+                out += self.slice_nal(k, pl["type"])
+            return out
         out = self.vps() + self.sps() + self.pps()
         for k in range(frames):
             if pattern == "I":
@@ -963,7 +996,7 @@ def main():
     ap.add_argument("--seed", type=int, default=1)
     ap.add_argument("--qp", type=int, default=30)
     ap.add_argument("--no-sao", action="store_true")
-    ap.add_argument("--pattern", default="I", help='picture types after the IDR, e.g. "PB" (low-delay, 2 references)')
+    ap.add_argument("--pattern", default="I", help='"RA" = random access (hierarchical-B GOP 4); else picture types after the IDR, e.g. "PB" (low-delay, 2 references)')
     ap.add_argument("--weighted", action="store_true")
     ap.add_argument("--cip", action="store_true", help="constrained_intra_pred_flag")
     ap.add_argument("--tqb", type=float, default=0.0, help="share of CUs coded with cu_transquant_bypass_flag")
