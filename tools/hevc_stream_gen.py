@@ -230,11 +230,13 @@ SIG_CTX_4x4 = [0, 1, 4, 5, 2, 3, 4, 5, 6, 6, 8, 8, 7, 7, 8, 8]
 
 
 class StreamGen:
-    def __init__(self, width, height, bit_depth=8, seed=1, qp=30, sao=True, ctb_log2=6, weighted=False, wpp=False, cip=False, tqb=0.0, tiles=None, lf_across_tiles=True, tskip=0.0, pcm=0.0, pcm_lf_off=False, slices=1, lf_across_slices=True):
+    def __init__(self, width, height, bit_depth=8, seed=1, qp=30, sao=True, ctb_log2=6, weighted=False, wpp=False, cip=False, tqb=0.0, tiles=None, lf_across_tiles=True, tskip=0.0, pcm=0.0, pcm_lf_off=False, slices=1, lf_across_slices=True, cfi=1):
         self.W, self.H, self.bd, self.qp, self.sao, self.ctb_log2 = width, height, bit_depth, qp, sao, ctb_log2
         self.weighted = weighted
         self.cip = cip                      # pps constrained_intra_pred_flag (hevcpred_template.c:116-249)
         self.tqb = tqb                      # share of CUs with cu_transquant_bypass_flag (pps transquant_bypass_enable_flag when > 0)
+        self.cfi = cfi                      # chroma_format_idc: 1 = 4:2:0, 2 = 4:2:2 (two stacked chroma blocks per TU, RExt)
+        assert cfi in (1, 2) and not (cfi == 2 and pcm > 0)
         self.slices, self.lf_across_slices = slices, lf_across_slices   # independent slices per picture, each starting a CTB row
         assert slices == 1 or not (tiles or wpp), "several slices are generated without tiles / WPP only"
         self.pcm, self.pcm_lf_off = pcm, pcm_lf_off   # share of 2Nx2N intra CUs (8x8 .. 32x32) coded as PCM; pcm_loop_filter_disabled_flag
@@ -252,14 +254,19 @@ class StreamGen:
         self.stats = []
         self.rng = np.random.default_rng(seed)
         self.off, self.init_rows = load_contexts()
+        src = open(os.path.join(REF, "libavcodec", "hevc.c")).read()      # 4:2:2 chroma mode mapping (8.4.3), from the decoder's own table
+        body = src[src.index("tab_mode_idx[]"):]
+        self.tab_mode_idx = [int(v) for v in re.findall(r"\d+", body[body.index("{") + 1:body.index("}")])]
+        assert len(self.tab_mode_idx) == 35
         self.min_cb_log2, self.min_tb_log2, self.max_tb_log2 = 3, 2, 5
         self.max_th_depth_intra = 2
 
     # ---- parameter sets -------------------------------------------------------------------------------------
     def ptl(self, w):
-        w.u(2, 0); w.u(1, 0); w.u(5, 2 if self.bd > 8 else 1)            # profile space, tier, profile idc
+        prof = 4 if getattr(self, "cfi", 1) == 2 else (2 if self.bd > 8 else 1)   # Main / Main10 / format range extensions
+        w.u(2, 0); w.u(1, 0); w.u(5, prof)                                 # profile space, tier, profile idc
         for i in range(32):
-            w.u(1, 1 if i in (1, 2) else 0)
+            w.u(1, 1 if (i in (1, 2) and prof != 4) or (i == 4 and prof == 4) else 0)
         w.u(1, 1); w.u(1, 0); w.u(1, 0); w.u(1, 1)                        # progressive, interlaced, non-packed, frame-only
         w.u(16, 0); w.u(16, 0); w.u(12, 0)
         w.u(8, 153)                                                        # level 5.1
@@ -280,7 +287,7 @@ class StreamGen:
         w.u(4, 0); w.u(3, 0); w.u(1, 1)
         self.ptl(w)
         w.ue(0)                                                            # sps id
-        w.ue(1)                                                            # chroma_format_idc 4:2:0
+        w.ue(self.cfi)                                                     # chroma_format_idc
         w.ue(self.W); w.ue(self.H)
         w.u(1, 0)                                                          # conformance window
         w.ue(self.bd - 8); w.ue(self.bd - 8)
@@ -748,6 +755,8 @@ class StreamGen:
             c.bypass_bits(2, cm)
         table = [0, 26, 10, 1]
         mode_c = modes[0] if cm == 4 else (34 if modes[0] == table[cm] else table[cm])
+        if self.cfi == 2:
+            mode_c = self.tab_mode_idx[mode_c]                              # 4:2:2: process of 8.4.3, table read from hevc.c:2252
         self.ct_depth[y0 >> 3:(y0 + size) >> 3, x0 >> 3:(x0 + size) >> 3] = depth
         self.transform_tree(x0, y0, log2, 0, 0, nxn, modes, mode_c, [0, 0], self.max_th_depth_intra + nxn, modes[0])
 
@@ -760,21 +769,27 @@ class StreamGen:
             c.encode(o["split_transform_flag"] + 5 - log2, split)
         else:
             split = int(log2 > self.max_tb_log2 or (nxn and tdepth == 0))
-        cbf_c = list(parent_cbf_c)
+        # cbf_cb / cbf_cr (hevc.c:1491-1513): one flag per component, two at 4:2:2 (upper / lower square) unless the node splits
+        # further above 8x8; a node is only asked when its parent's first flag was set
+        nblk = 2 if self.cfi == 2 else 1
+        if tdepth == 0 and not isinstance(parent_cbf_c[0], list):
+            parent_cbf_c = [[0, 0], [0, 0]]
+        cbf_c = [list(parent_cbf_c[0]), list(parent_cbf_c[1])]
         if log2 > 2:
             for k in range(2):
-                if tdepth == 0 or parent_cbf_c[k]:
-                    cbf_c[k] = int(r.random() < 0.5)
-                    c.encode(o["cbf_cb, cbf_cr"] + tdepth, cbf_c[k])
-                else:
-                    cbf_c[k] = 0
+                if tdepth == 0 or parent_cbf_c[k][0]:
+                    cbf_c[k][0] = int(r.random() < 0.5)
+                    c.encode(o["cbf_cb, cbf_cr"] + tdepth, cbf_c[k][0])
+                    if self.cfi == 2 and (not split or log2 == 3):
+                        cbf_c[k][1] = int(r.random() < 0.5)
+                        c.encode(o["cbf_cb, cbf_cr"] + tdepth, cbf_c[k][1])
         if split:
             h = 1 << (log2 - 1)
             for i, (dx, dy) in enumerate(((0, 0), (h, 0), (0, h), (h, h))):
                 self.transform_tree(x0 + dx, y0 + dy, log2 - 1, tdepth + 1, i, nxn, modes, mode_c, cbf_c, max_depth, mode)
             return
         inter = getattr(self, "inter", False)
-        if inter and tdepth == 0 and not cbf_c[0] and not cbf_c[1]:
+        if inter and tdepth == 0 and not any(cbf_c[0][:nblk] + cbf_c[1][:nblk]):
             cbf_luma = 1                                                    # inferred (7.3.8.8)
         else:
             cbf_luma = int(r.random() < 0.7)
@@ -787,19 +802,19 @@ class StreamGen:
                 if 22 <= m <= 30:
                     return 1
             return 0
+        chroma_here = log2 > 2 or blk == 3                                  # 4x4 luma: the chroma of the 8x8 parent comes with block 3
+        flags = cbf_c if log2 > 2 else parent_cbf_c
         if not inter:
-            self.cnt["intra_pred"] += 1 + (2 if (log2 > 2 or blk == 3) else 0)
-        self.cnt["transform_add"] += cbf_luma + ((cbf_c[0] + cbf_c[1]) if log2 > 2 else ((parent_cbf_c[0] + parent_cbf_c[1]) if blk == 3 else 0))
+            self.cnt["intra_pred"] += 1 + (2 * nblk if chroma_here else 0)
+        self.cnt["transform_add"] += cbf_luma + (sum(flags[0][:nblk]) + sum(flags[1][:nblk]) if chroma_here else 0)
         if cbf_luma:
             self.residual(log2, scan_of(mode, log2) if log2 < 4 else 0, 0)
-        if log2 > 2:
-            for k in range(2):
-                if cbf_c[k]:
-                    self.residual(log2 - 1, scan_of(mode_c, log2) if log2 < 4 else 0, k + 1)
-        elif blk == 3:
-            for k in range(2):
-                if parent_cbf_c[k]:
-                    self.residual(2, scan_of(mode_c, log2), k + 1)
+        if chroma_here:
+            log2_c = log2 - 1 if log2 > 2 else 2
+            for k in range(2):                                              # Cb blocks, then Cr blocks (hevc.c:1302-1362)
+                for i in range(nblk):
+                    if flags[k][i]:
+                        self.residual(log2_c, scan_of(mode_c, log2) if log2 < 4 else 0, k + 1)
 
     def residual(self, log2, scan_idx, cidx):
         c, o, r = self.c, self.off, self.rng
@@ -1002,6 +1017,7 @@ def main():
     ap.add_argument("--tqb", type=float, default=0.0, help="share of CUs coded with cu_transquant_bypass_flag")
     ap.add_argument("--pcm", type=float, default=0.0, help="share of 2Nx2N intra CUs coded as PCM")
     ap.add_argument("--pcm-lf-off", action="store_true", help="pcm_loop_filter_disabled_flag")
+    ap.add_argument("--cfi", type=int, default=1, help="chroma_format_idc: 1 = 4:2:0, 2 = 4:2:2")
     ap.add_argument("--slices", type=int, default=1, help="independent slices per picture (each starts a CTB row)")
     ap.add_argument("--no-lf-across-slices", action="store_true", help="slice_loop_filter_across_slices_enabled_flag = 0")
     ap.add_argument("--tskip", type=float, default=0.0, help="share of 4x4 TUs coded with transform_skip_flag")
@@ -1010,7 +1026,7 @@ def main():
     ap.add_argument("--wpp", action="store_true", help="entropy_coding_sync_enabled_flag: one substream per CTB row + entry points")
     a = ap.parse_args()
     verify_tables_against_reference()
-    g = StreamGen(a.width, a.height, a.bit_depth, a.seed, a.qp, sao=not a.no_sao, weighted=a.weighted, wpp=a.wpp, cip=a.cip, tqb=a.tqb, tskip=a.tskip, pcm=a.pcm, pcm_lf_off=a.pcm_lf_off, slices=a.slices, lf_across_slices=not a.no_lf_across_slices,
+    g = StreamGen(a.width, a.height, a.bit_depth, a.seed, a.qp, sao=not a.no_sao, weighted=a.weighted, wpp=a.wpp, cip=a.cip, tqb=a.tqb, tskip=a.tskip, pcm=a.pcm, pcm_lf_off=a.pcm_lf_off, slices=a.slices, lf_across_slices=not a.no_lf_across_slices, cfi=a.cfi,
                   tiles=tuple(int(v) for v in a.tiles.split("x")) if a.tiles else None, lf_across_tiles=not a.no_lf_across_tiles)
     data = g.stream(a.frames, a.pattern)
     open(a.out, "wb").write(data)
