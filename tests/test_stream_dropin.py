@@ -28,6 +28,7 @@ def run(binary, stream, threads=1, env=None, want_stderr=False):
 # array between pictures (hevc.c:147), so its own output depends on which pictures a context decoded before, i.e. on the
 # number of frame threads; the arbiter for such runs is the reference run the same way, not the committed single-thread MD5
 IS_PCM_STREAMS = ("tqb_", "pcm_416x240_10b_lfoff", "tskip_416x240_8b")
+REPEATED = [s for s in STREAMS if os.path.basename(s).startswith(("b_", "p_", "wpp_416", "tiles_416", "cip_416", "ra_416"))]
 WPP_STREAMS = [s for s in STREAMS if os.path.basename(s).startswith(("wpp_", "tiles_"))]      # streams with entry points: slice threads really run
 
 
@@ -80,7 +81,7 @@ def test_hooked_decoder_with_frame_threads(stream):
         assert [l.split()[2:] for l in want] == [l.split()[2:] for l in committed[:len(want)]]
     if "/b_" in stream or "/p_" in stream:
         assert want == committed
-    for rep in range(2):
+    for rep in range(2 if stream in REPEATED else 1):     # a second run catches state left behind by the first (a subset: every run starts a process + CUDA context)
         assert run("decode_b200", stream, threads=4) == want
 
 
@@ -101,7 +102,7 @@ def test_hooked_decoder_with_wpp_threads(stream):
     if not os.path.exists(os.path.join(REFDIR, "decode_b200")):
         pytest.skip("oracle/_ref/decode_b200 not built")
     want = open(stream[:-5] + ".md5").read().splitlines()
-    for rep in range(2):
+    for rep in range(2 if stream in REPEATED else 1):
         assert run("decode_b200", stream, threads="4w") == want
 
 
