@@ -603,7 +603,8 @@ extern "C" int b200_frame_execute_ex(B200Ctx *ctx, int arena, int cur_slot, cons
     }
     if (pf) CU(cudaEventRecord(ctx->prof[0], st));
     // K1 inter
-    ctx->launches += launch_mc(st, (const B200McRec *)(a.dev + h.sec[B200_SEC_MC].off), (int)h.sec[B200_SEC_MC].count, (int)h.mc_big_count, cur, ctx->dpb_desc_dev, rt, bd, L.counter);
+    ctx->launches += launch_mc(st, (const B200McRec *)(a.dev + h.sec[B200_SEC_MC].off), (int)h.sec[B200_SEC_MC].count, (int)h.mc_big_count, cur, ctx->dpb_desc_dev, rt, bd, L.counter,
+                               ctx->slot_desc[0], (unsigned long long)ctx->slot_bytes);
     if (pf) CU(cudaEventRecord(ctx->prof[1], st));
     if (tr) CU(cudaEventRecord(tr->ev[1], st));
     // K2 residual

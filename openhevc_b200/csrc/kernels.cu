@@ -345,6 +345,22 @@ __device__ __forceinline__ int ref_slot_of(const RefTable &rt, int i)
     return (int)((w >> (8 * (i & 7))) & 0xff);
 }
 
+
+// The DPB is one regular allocation (engine.cu: slot s starts at dpb + s * slot_bytes, same plane offsets in every slot), so a
+// reference plane can be described from kernel parameters instead of being loaded from the descriptor table in global
+// memory -- one dependent memory latency less per list and tile.  `slot_bytes` == 0 selects the table (B200_MC_DESC=0).
+struct DpbLayout {
+    FrameDesc slot0;
+    unsigned long long slot_bytes;
+};
+__device__ __forceinline__ PlaneDesc ref_plane(const DpbLayout &L, const FrameDesc *__restrict__ dpb, int slot, int plane)
+{
+    if (!L.slot_bytes) return dpb[slot].p[plane];
+    PlaneDesc d = plane_of(L.slot0, plane);
+    d.base += (size_t)slot * L.slot_bytes;
+    return d;
+}
+
 struct McGeom {
     int w, h;
     int wsh, parts, rows_per;   // stage B: lane = column (1 << wsh per row group), `parts` row groups of rows_per rows
@@ -459,7 +475,7 @@ __device__ __forceinline__ void mc_list(const PlaneDesc &rp, int sx, int sy, int
 // ---- K1, default version: scalar FIRs (one IMAD per tap) ----
 template <typename PIX, int GS>
 __global__ void __launch_bounds__(256) k_mc_v1(const B200McRec *__restrict__ recs, int count, FrameDesc cur, const FrameDesc *__restrict__ dpb, RefTable rt, int bd,
-                                            const uint32_t *__restrict__ gate)
+                                            const uint32_t *__restrict__ gate, DpbLayout lay)
 {
     if (__ldg(gate + 1)) return;         // the picture's work list failed validation (k_validate)
     constexpr int NG = 256 / GS;                           // groups per CTA
@@ -492,12 +508,12 @@ __global__ void __launch_bounds__(256) k_mc_v1(const B200McRec *__restrict__ rec
     g.lsh = g.q <= 1 ? 0 : g.q <= 2 ? 1 : g.q <= 4 ? 2 : 3;
     int v0[8], v1[8];
     {
-        const PlaneDesc rp = dpb[ref_slot_of(rt, ref0)].p[plane];
+        const PlaneDesc rp = ref_plane(lay, dpb, ref_slot_of(rt, ref0), plane);
         if (chroma) mc_list<PIX, 4, GS>(rp, sx0, sy0, frac0 & 15, frac0 >> 4, g, bd, gl, gmask, win_s[grp], tmp_s[grp], v0);
         else        mc_list<PIX, 8, GS>(rp, sx0, sy0, frac0 & 15, frac0 >> 4, g, bd, gl, gmask, win_s[grp], tmp_s[grp], v0);
     }
     if (bi) {
-        const PlaneDesc rp = dpb[ref_slot_of(rt, ref1)].p[plane];
+        const PlaneDesc rp = ref_plane(lay, dpb, ref_slot_of(rt, ref1), plane);
         if (chroma) mc_list<PIX, 4, GS>(rp, sx1, sy1, frac1 & 15, frac1 >> 4, g, bd, gl, gmask, win_s[grp], tmp_s[grp], v1);
         else        mc_list<PIX, 8, GS>(rp, sx1, sy1, frac1 & 15, frac1 >> 4, g, bd, gl, gmask, win_s[grp], tmp_s[grp], v1);
     }
@@ -534,7 +550,7 @@ __global__ void __launch_bounds__(256) k_mc_v1(const B200McRec *__restrict__ rec
 // K1, experimental version (B200_MC=2): the phases of k_mc.cuh (IDP.2A FIRs on packed sample pairs) with group-local barriers between them
 template <typename PIX, int GS>
 __global__ void __launch_bounds__(256, 4) k_mc(const B200McRec *__restrict__ recs, int count, FrameDesc cur, const FrameDesc *__restrict__ dpb, RefTable rt, int bd,
-                                            const uint32_t *__restrict__ gate)
+                                            const uint32_t *__restrict__ gate, DpbLayout lay)
 {
     if (__ldg(gate + 1)) return;         // the picture's work list failed validation (k_validate)
     constexpr int NG = 256 / GS;                           // groups per CTA
@@ -553,7 +569,7 @@ __global__ void __launch_bounds__(256, 4) k_mc(const B200McRec *__restrict__ rec
 #pragma unroll
     for (int list = 0; list < 2; list++) {
         if (list && !bi) break;
-        const PlaneDesc rp = dpb[ref_slot_of(rt, list ? t.ref1 : t.ref0)].p[t.plane];
+        const PlaneDesc rp = ref_plane(lay, dpb, ref_slot_of(rt, list ? t.ref1 : t.ref0), t.plane);
         const int sx = list ? t.sx1 : t.sx0, sy = list ? t.sy1 : t.sy0, fr = list ? t.frac1 : t.frac0, mx = fr & 15, my = fr >> 4;
         int (&v)[8] = list ? v1 : v0;
         __syncwarp(gmask);                                 // the previous list's readers are done with win / tmp
@@ -646,6 +662,32 @@ __global__ void k_intra_edges_init(FrameDesc f, IntraEdges ed)
     const uint2 bot = edge_pack(b[0], b[1], b[2], b[3]), rgt = edge_pack(r0, r1, r2, b[3]);
     uint4 *dst = reinterpret_cast<uint4 *>(edges_of(ed, plane) + 2 * ((size_t)uy * estride_of(ed, plane) + ux));
     *dst = make_uint4(bot.x, bot.y, rgt.x, rgt.y);
+}
+
+// The same, driven by the intra records: only the units an intra TU can read (the row above from the up-left corner to the
+// end of the up-right block, the column to the left down to the end of the bottom-left block) are initialised -- a B
+// picture with 8 % intra blocks touches a few per cent of the picture instead of reading all of it (25 MB, 11 us at 4K).
+// One warp per record, lane k = unit k of the 4u + 1 neighbours.  Units that belong to another intra TU get a record from
+// the picture as well; k_intra_prepass, which runs after this kernel, marks them "not valid yet" again.
+template <typename PIX>
+__global__ void k_intra_edges_init_sparse(const B200IntraRec *__restrict__ recs, int count, FrameDesc f, IntraEdges ed, const uint32_t *__restrict__ gate)
+{
+    if (__ldg(gate + 1)) return;
+    const int i = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (i >= count) return;
+    const B200IntraRec r = decode_intra(__ldg(reinterpret_cast<const int4 *>(recs + i)));
+    const PlaneDesc pd = plane_of(f, r.plane);
+    const int u = 1 << (r.log2 - 2), ux0 = r.x >> 2, uy0 = r.y >> 2;
+    for (int k = lane; k < 4 * u + 1; k += 32) {
+        // k = 0 .. 2u: row above, from the corner; k = 2u + 1 .. 4u: column to the left, top down
+        const int ux = k <= 2 * u ? ux0 - 1 + k : ux0 - 1, uy = k <= 2 * u ? uy0 - 1 : uy0 + (k - 2 * u - 1);
+        if (ux < 0 || uy < 0 || 4 * ux >= pd.w || 4 * uy >= pd.h) continue;
+        const PIX *b = px_ptr<PIX>(pd, 4 * ux, 4 * uy + 3);
+        const int r0 = *px_ptr<PIX>(pd, 4 * ux + 3, 4 * uy), r1 = *px_ptr<PIX>(pd, 4 * ux + 3, 4 * uy + 1), r2 = *px_ptr<PIX>(pd, 4 * ux + 3, 4 * uy + 2);
+        const uint2 bot = edge_pack(b[0], b[1], b[2], b[3]), rgt = edge_pack(r0, r1, r2, b[3]);
+        uint4 *dst = reinterpret_cast<uint4 *>(edges_of(ed, r.plane) + 2 * ((size_t)uy * estride_of(ed, r.plane) + ux));
+        *dst = make_uint4(bot.x, bot.y, rgt.x, rgt.y);
+    }
 }
 
 // units an intra TU of this picture will write: not valid yet
@@ -1074,9 +1116,15 @@ __global__ void k_fill(FrameDesc f, int value)
 // --------------------------------------------------------------------------------------------
 // launchers
 // --------------------------------------------------------------------------------------------
-int launch_mc(cudaStream_t st, const B200McRec *recs, int count, int n_big, const FrameDesc &cur, const FrameDesc *dpb_dev, const RefTable &rt, int bd, const uint32_t *gate)
+int launch_mc(cudaStream_t st, const B200McRec *recs, int count, int n_big, const FrameDesc &cur, const FrameDesc *dpb_dev, const RefTable &rt, int bd, const uint32_t *gate,
+              const FrameDesc &slot0, unsigned long long slot_bytes)
 {
     if (!count) return 0;
+    // B200_MC_DESC=1: reference planes described from kernel parameters (see DpbLayout); default 0 = descriptor table, the
+    // path every GPU run of round 1 used -- the switch exists so that the next GPU visit can measure the difference at once
+    static const bool by_param = getenv("B200_MC_DESC") && atoi(getenv("B200_MC_DESC"));
+    DpbLayout lay;
+    lay.slot0 = slot0; lay.slot_bytes = by_param ? slot_bytes : 0ull;
     // 1 = scalar FIRs, one IMAD per tap (default); 2 = IDP.2A on packed pairs (k_mc.cuh).  Version 2 is bit-exact on the GPU
     // (full parity suite) but SLOWER: 145 vs 109 us per 4K B picture, 38.9 M + 29.7 M vs 35.4 M + 22.8 M warp instructions --
     // the pair shuffles and the 16-bit interleaved stores cost more than the halved multiplies save, and ncu shows the
@@ -1087,22 +1135,22 @@ int launch_mc(cudaStream_t st, const B200McRec *recs, int count, int n_big, cons
     if (n_big) {                        // one warp per tile
         const int grid = (n_big + 7) / 8;
         if (version == 1) {
-            if (bd > 8) k_mc_v1<uint16_t, 32><<<grid, 256, 0, st>>>(recs, n_big, cur, dpb_dev, rt, bd, gate);
-            else        k_mc_v1<uint8_t, 32><<<grid, 256, 0, st>>>(recs, n_big, cur, dpb_dev, rt, bd, gate);
+            if (bd > 8) k_mc_v1<uint16_t, 32><<<grid, 256, 0, st>>>(recs, n_big, cur, dpb_dev, rt, bd, gate, lay);
+            else        k_mc_v1<uint8_t, 32><<<grid, 256, 0, st>>>(recs, n_big, cur, dpb_dev, rt, bd, gate, lay);
         } else {
-            if (bd > 8) k_mc<uint16_t, 32><<<grid, 256, 0, st>>>(recs, n_big, cur, dpb_dev, rt, bd, gate);
-            else        k_mc<uint8_t, 32><<<grid, 256, 0, st>>>(recs, n_big, cur, dpb_dev, rt, bd, gate);
+            if (bd > 8) k_mc<uint16_t, 32><<<grid, 256, 0, st>>>(recs, n_big, cur, dpb_dev, rt, bd, gate, lay);
+            else        k_mc<uint8_t, 32><<<grid, 256, 0, st>>>(recs, n_big, cur, dpb_dev, rt, bd, gate, lay);
         }
         n++;
     }
     if (n_small) {                      // tiles of <= 8x8 samples: four per warp
         const int grid = (n_small + 31) / 32;
         if (version == 1) {
-            if (bd > 8) k_mc_v1<uint16_t, 8><<<grid, 256, 0, st>>>(recs + n_big, n_small, cur, dpb_dev, rt, bd, gate);
-            else        k_mc_v1<uint8_t, 8><<<grid, 256, 0, st>>>(recs + n_big, n_small, cur, dpb_dev, rt, bd, gate);
+            if (bd > 8) k_mc_v1<uint16_t, 8><<<grid, 256, 0, st>>>(recs + n_big, n_small, cur, dpb_dev, rt, bd, gate, lay);
+            else        k_mc_v1<uint8_t, 8><<<grid, 256, 0, st>>>(recs + n_big, n_small, cur, dpb_dev, rt, bd, gate, lay);
         } else {
-            if (bd > 8) k_mc<uint16_t, 8><<<grid, 256, 0, st>>>(recs + n_big, n_small, cur, dpb_dev, rt, bd, gate);
-            else        k_mc<uint8_t, 8><<<grid, 256, 0, st>>>(recs + n_big, n_small, cur, dpb_dev, rt, bd, gate);
+            if (bd > 8) k_mc<uint16_t, 8><<<grid, 256, 0, st>>>(recs + n_big, n_small, cur, dpb_dev, rt, bd, gate, lay);
+            else        k_mc<uint8_t, 8><<<grid, 256, 0, st>>>(recs + n_big, n_small, cur, dpb_dev, rt, bd, gate, lay);
         }
         n++;
     }
@@ -1135,9 +1183,18 @@ int launch_intra(cudaStream_t st, const B200IntraRec *recs, int count, const int
     IntraEdges ed;
     for (int p = 0; p < 3; p++) { ed.e[p] = edges[p]; ed.stride[p] = edge_stride[p]; }
     // counter[0] (ticket) and counter[1] (gate) were cleared when the picture entered its lane (engine.cu)
-    const dim3 gi((cur.p[0].w / 4 + 127) / 128, cur.p[0].h / 4, 3);
-    if (bd > 8) k_intra_edges_init<uint16_t><<<gi, 128, 0, st>>>(cur, ed);
-    else        k_intra_edges_init<uint8_t><<<gi, 128, 0, st>>>(cur, ed);
+    // B200_EDGES_SPARSE=1: initialise only the edge records intra TUs can read (record-driven) when the picture is mostly inter;
+    // default 0 = every unit of the picture, the path every GPU run of round 1 used (switch for the next GPU visit)
+    static const bool sparse_ok = getenv("B200_EDGES_SPARSE") && atoi(getenv("B200_EDGES_SPARSE"));
+    const long units = (long)(cur.p[0].w / 4) * (cur.p[0].h / 4) + 2l * (cur.p[1].w / 4) * (cur.p[1].h / 4);
+    if (sparse_ok && (long)count * 16 < units) {
+        if (bd > 8) k_intra_edges_init_sparse<uint16_t><<<(count + 3) / 4, 128, 0, st>>>(recs, count, cur, ed, counter);
+        else        k_intra_edges_init_sparse<uint8_t><<<(count + 3) / 4, 128, 0, st>>>(recs, count, cur, ed, counter);
+    } else {
+        const dim3 gi((cur.p[0].w / 4 + 127) / 128, cur.p[0].h / 4, 3);
+        if (bd > 8) k_intra_edges_init<uint16_t><<<gi, 128, 0, st>>>(cur, ed);
+        else        k_intra_edges_init<uint8_t><<<gi, 128, 0, st>>>(cur, ed);
+    }
     k_intra_prepass<<<(count + 255) / 256, 256, 0, st>>>(recs, count, ed, counter);
     int grid = (count + 3) / 4;
     // persistent warps.  The list is sorted by dependency level, so the TUs that can run together are adjacent and a
