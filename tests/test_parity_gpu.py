@@ -49,6 +49,7 @@ def test_constrained_intra_pred():
     run_sequence(192, 128, 3, 8, seeds=[68, 69], cip=True, p_intra=0.7, split_bias=0.4)
 
 
+@pytest.mark.late
 def test_sao_restore_of_bypass_pus():
     """transquant-bypass / PCM-without-loop-filter PUs get their deblocked samples back after SAO (restore_tqb_pixels,
     hevc_filter.c:163-193, with the reference's two quirks): blob with a TQB bitmap, SAO kernel vs oracle"""
@@ -176,6 +177,7 @@ def test_malformed_blobs_are_rejected_not_executed():
         eng.close()
 
 
+@pytest.mark.late
 def test_malformed_inter_records_are_rejected_on_the_device():
     w, h = 128, 64
     eng = FrameEngine(w, h, 1, 8, n_slots=3)

@@ -12,7 +12,7 @@ import pytest
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 REFDIR = os.path.join(os.path.dirname(HERE), "oracle", "_ref")
-STREAMS = sorted(glob.glob(os.path.join(HERE, "golden", "streams", "*.hevc")))
+STREAMS = sorted(glob.glob(os.path.join(HERE, "golden", "streams", "*.hevc")))      # run order: tests/conftest.py
 
 
 def run(binary, stream, threads=1, env=None, want_stderr=False):
