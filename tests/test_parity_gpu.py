@@ -197,6 +197,29 @@ def test_malformed_inter_records_are_rejected_on_the_device():
         eng.close()
 
 
+@pytest.mark.late
+@pytest.mark.parametrize("cfi,bd", [(1, 8), (2, 10)])
+def test_grey_reference_fill(cfi, bd):
+    """generate_missing_ref (hevc_refs.c:538): a reference the stream lost is a picture of 1 << (bit_depth - 1); the
+    drop-in fills the slot on the device (b200_slot_fill) and the next picture predicts from it"""
+    w, h, grey = 192, 128, 1 << (bd - 1)
+    eng = FrameEngine(w, h, cfi, bd, n_slots=3)
+    try:
+        eng.upload_slot(1, smooth_frame(w, h, cfi, bd, 5))       # something else first: the fill must overwrite every sample
+        eng.fill_slot(1, grey)
+        got = eng.readback(1)
+        dpb = [[np.zeros_like(p) for p in got] for _ in range(3)]
+        for p in range(3):
+            assert got[p].shape == eng.plane_shape(p) and (got[p] == grey).all()
+            dpb[1][p][:] = grey
+        blob, _ = FrameSynth(w, h, cfi, bd, seed=41, refs=[1], cur_slot=0, poc=1).generate()
+        pic, want = eng.decode(blob), oracle_lib.execute(blob, dpb)
+        for p in range(3):
+            assert np.array_equal(pic[p], want[p])
+    finally:
+        eng.close()
+
+
 def test_cyclic_intra_dependencies_time_out_instead_of_hanging():
     """a work list whose intra TUs wait on each other (cannot come from a real decode order) must not hang the device"""
     w, h = 128, 64
