@@ -7,6 +7,9 @@
 #include <string.h>
 #include <algorithm>
 #include <vector>
+#if defined(__SSE2__)
+#include <emmintrin.h>
+#endif
 #include "../../include/b200hevc.h"
 
 struct B200Rec {
@@ -180,6 +183,21 @@ extern "C" int b200_rec_tu(B200Rec *r, int plane, int x, int y, int log2, int ki
     bool sparse = kind != B200_TU_PCM;
     if (sparse) {
         const int limit = (nn - 1) / 2;                                // sparse iff 2 * nnz < nn
+#if defined(__SSE2__)
+        {   // eight coefficients per test; the decoder's scratch is mostly zeros
+            const __m128i zero = _mm_setzero_si128();
+            for (int q = 0; q < nn / 8 && nnz <= limit; q++) {
+                const __m128i v = _mm_loadu_si128((const __m128i *)(coeffs + 8 * q));
+                unsigned m = 0xffffu & ~(unsigned)_mm_movemask_epi8(_mm_cmpeq_epi16(v, zero));     // two bits per non-zero coefficient
+                while (m) {
+                    const int k = __builtin_ctz(m) >> 1;
+                    m &= ~(3u << (2 * k));
+                    if (nnz < limit) { pairs[2 * nnz] = (int16_t)(8 * q + k); pairs[2 * nnz + 1] = coeffs[8 * q + k]; }
+                    nnz++;
+                }
+            }
+        }
+#else
         if (((uintptr_t)coeffs & 7) == 0) {
             const uint64_t *w = (const uint64_t *)coeffs;
             for (int q = 0; q < nn / 4 && nnz <= limit; q++) {
@@ -194,6 +212,7 @@ extern "C" int b200_rec_tu(B200Rec *r, int plane, int x, int y, int log2, int ki
             for (int i = 0; i < nn && nnz <= limit; i++)
                 if (coeffs[i]) { if (nnz < limit) { pairs[2 * nnz] = (int16_t)i; pairs[2 * nnz + 1] = coeffs[i]; } nnz++; }
         }
+#endif
         sparse = nnz <= limit && 2 * nnz < nn;
     }
     r->ncoef = off + (link ? 2 : 0) + (sparse ? 2 * nnz : nn);        // give the unused tail back

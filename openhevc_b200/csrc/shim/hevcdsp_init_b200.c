@@ -35,7 +35,7 @@
 #define MAX_WORKERS 64
 #define MAX_ACTIVE 64
 
-typedef struct RegPlane { const uint8_t *base; ptrdiff_t linesize; int slot, plane, w, h; } RegPlane;
+typedef struct RegPlane { const uint8_t *base; ptrdiff_t linesize, size; uint64_t inv; int slot, plane, w, h; } RegPlane;
 
 #include <pthread.h>
 
@@ -66,8 +66,8 @@ typedef struct ShimThread {
     unsigned rec_gen;
     unsigned ticket;
     RegPlane reg[MAX_REG * 3];
-    int n_reg;
-    const uint8_t *cur_base[3]; ptrdiff_t cur_ls[3]; int cur_slot;
+    int n_reg, reg_hit;
+    const uint8_t *cur_base[3]; ptrdiff_t cur_ls[3], cur_size[3]; uint64_t cur_inv[3]; int cur_slot;
     uint8_t ref_slot[16]; int n_ref;
     /* pending in-place transform on the per-thread coefficient scratch (hevc.h:1063) */
     const int16_t *pend_ptr; int pend_kind, pend_flags, pend_col_limit;
@@ -85,7 +85,46 @@ typedef struct ShimThread {
     int n_tu, n_intra, n_pu, n_dbk, n_sao, frame_no;   /* B200_SHIM_STATS=1: table calls per picture (stderr) */
     uint8_t fill_slot[16]; int n_fill;                  /* generate_missing_ref (hevc_refs.c:538): grey references this picture needs */
 } ShimThread;
-static __thread ShimThread g;
+/* One heap block per thread, reached through an 8-byte initial-exec TLS pointer: a plain `static __thread ShimThread` in a
+ * shared library costs a __tls_get_addr call per table call (2.4% of the hooked decoder's CPU time plus the PLT), and the
+ * struct itself is too large for the static TLS surplus if libOpenHevc is dlopen()ed.  Blocks of threads that exited are
+ * recycled, never freed: workers keep pointers to their owner's block (att), and frame_seq must stay monotonic. */
+static __thread struct ShimThread *g_self __attribute__((tls_model("initial-exec")));
+static pthread_key_t g_key;
+static pthread_once_t g_key_once = PTHREAD_ONCE_INIT;
+static pthread_mutex_t g_pool_mu = PTHREAD_MUTEX_INITIALIZER;
+static ShimThread *g_pool[256]; static int g_pool_n;
+static ShimThread g_oom = { .err = B200_ENOMEM, .errmsg = "out of memory (per-thread state of the B200 shim)" };
+
+static void shim_thread_exit(void *p)
+{
+    ShimThread *t = p;
+    if (t == &g_oom) return;
+    pthread_mutex_lock(&g_pool_mu);
+    t->in_frame = 0;
+    if (g_pool_n < 256) g_pool[g_pool_n++] = t;         /* else: leaked, 256 exited threads are already parked */
+    pthread_mutex_unlock(&g_pool_mu);
+}
+static void shim_key_make(void) { pthread_key_create(&g_key, shim_thread_exit); }
+static __attribute__((noinline)) ShimThread *shim_self_slow(void)
+{
+    pthread_once(&g_key_once, shim_key_make);
+    pthread_mutex_lock(&g_pool_mu);
+    ShimThread *t = g_pool_n ? g_pool[--g_pool_n] : NULL;
+    pthread_mutex_unlock(&g_pool_mu);
+    if (t) { t->err = 0; t->n_fill = 0; t->n_workers = 0; t->att = NULL; }
+    else t = calloc(1, sizeof(*t));
+    if (!t) t = &g_oom;
+    g_self = t;
+    pthread_setspecific(g_key, t);
+    return t;
+}
+static inline ShimThread *shim_self(void)
+{
+    ShimThread *t = g_self;
+    return __builtin_expect(t != NULL, 1) ? t : shim_self_slow();
+}
+#define g (*shim_self())
 
 static void fail(int code, const char *msg)
 {
@@ -113,7 +152,7 @@ static int attach_slow(void)
         if (!rc && o->n_workers == MAX_WORKERS) { fail(B200_ENOTSUP, "too many worker threads"); rc = -1; }
         if (!rc) {
             memcpy(g.reg, o->reg, sizeof(g.reg)); g.n_reg = o->n_reg;
-            for (int p = 0; p < 3; p++) { g.cur_base[p] = o->cur_base[p]; g.cur_ls[p] = o->cur_ls[p]; }
+            for (int p = 0; p < 3; p++) { g.cur_base[p] = o->cur_base[p]; g.cur_ls[p] = o->cur_ls[p]; g.cur_size[p] = o->cur_size[p]; g.cur_inv[p] = o->cur_inv[p]; }
             g.cur_slot = o->cur_slot; g.poc = o->poc;
             g.n_ref = 0; g.pend_ptr = NULL; g.first_tmp = NULL; g.emu[0].buf = g.emu[1].buf = NULL;
             g.n_tu = g.n_intra = g.n_pu = g.n_dbk = g.n_sao = 0;
@@ -133,14 +172,22 @@ static inline int attached(void)
 }
 
 /* ---- pointer -> (slot, plane, x, y) ---------------------------------------------------------------- */
+/* offset / linesize without a division (several hundred thousand calls per 4K picture): inv = floor(2^48 / ls) + 1 is exact
+ * for off * ls < 2^48, i.e. any plane below 4 GB with a line below 64 KB; inv == 0 (odd geometry) falls back to dividing */
+static inline uint64_t row_inverse(ptrdiff_t ls) { return ls > 0 && ls < 65536 ? (1ull << 48) / (uint64_t)ls + 1 : 0; }
+static inline uint32_t row_of(uint32_t off, uint32_t ls, uint64_t inv)
+{
+    return inv ? (uint32_t)(((unsigned __int128)off * inv) >> 48) : off / ls;
+}
+
 static int locate_cur(const uint8_t *p, int *plane, int *x, int *y)
 {
     if (!attached()) return -1;
+    ShimThread *t = &g;
     for (int c = 0; c < 3; c++) {
-        const ptrdiff_t off = p - g.cur_base[c];
-        if (off >= 0 && off < g.cur_ls[c] * G.ph[c]) {
-            /* ~4 million calls per 4K picture: one 32-bit division (a plane is far below 4 GB), the remainder by multiplication */
-            const uint32_t o = (uint32_t)off, ls = (uint32_t)g.cur_ls[c], row = o / ls;
+        const ptrdiff_t off = p - t->cur_base[c];
+        if (off >= 0 && off < t->cur_size[c]) {
+            const uint32_t o = (uint32_t)off, ls = (uint32_t)t->cur_ls[c], row = row_of(o, ls, t->cur_inv[c]);
             *plane = c; *y = (int)row; *x = (int)((o - row * ls) >> (G.B - 1));
             return 0;
         }
@@ -152,18 +199,23 @@ static int locate_cur(const uint8_t *p, int *plane, int *x, int *y)
 static int locate_ref(const uint8_t *p, int plane_hint, int *slot, int *x, int *y)
 {
     if (!attached()) return -1;
+    ShimThread *t = &g;
     for (int e = 0; e < 2; e++)          /* source inside an edge-emulation buffer? (hevc.c:1673) */
-        if (g.emu[e].buf && p >= g.emu[e].buf && p < g.emu[e].buf + g.emu[e].ls * (MAX_PB_SIZE + 7)) {
-            ptrdiff_t off = p - g.emu[e].buf;
-            *slot = g.emu[e].slot; *y = g.emu[e].y + (int)(off / g.emu[e].ls); *x = g.emu[e].x + (int)(off % g.emu[e].ls) / G.B;
-            return g.emu[e].plane;
+        if (t->emu[e].buf && p >= t->emu[e].buf && p < t->emu[e].buf + t->emu[e].ls * (MAX_PB_SIZE + 7)) {
+            ptrdiff_t off = p - t->emu[e].buf;
+            *slot = t->emu[e].slot; *y = t->emu[e].y + (int)(off / t->emu[e].ls); *x = t->emu[e].x + (int)(off % t->emu[e].ls) / G.B;
+            return t->emu[e].plane;
         }
-    for (int i = 0; i < g.n_reg; i++) {
-        const RegPlane *r = &g.reg[i];
+    /* the plane of the previous hit first: consecutive blocks mostly read the same reference picture */
+    for (int k = -1; k < t->n_reg; k++) {
+        const int i = k < 0 ? t->reg_hit : k;
+        if (i >= t->n_reg) continue;
+        const RegPlane *r = &t->reg[i];
         ptrdiff_t off = p - r->base;
-        if (off >= 0 && off < r->linesize * r->h && (plane_hint < 0 || r->plane == plane_hint)) {
-            const uint32_t o = (uint32_t)off, ls = (uint32_t)r->linesize, row = o / ls;
+        if (off >= 0 && off < r->size && (plane_hint < 0 || r->plane == plane_hint)) {
+            const uint32_t o = (uint32_t)off, ls = (uint32_t)r->linesize, row = row_of(o, ls, r->inv);
             *slot = r->slot; *y = (int)row; *x = (int)((o - row * ls) >> (G.B - 1));
+            t->reg_hit = i;
             return r->plane;
         }
     }
@@ -497,10 +549,14 @@ int b200_frame_begin(HEVCContext *s)
         for (int p = 0; p < 3; p++) {
             RegPlane *r = &g.reg[g.n_reg++];
             r->base = f->data[p]; r->linesize = f->linesize[p]; r->slot = i; r->plane = p; r->w = G.pw[p]; r->h = G.ph[p];
+            r->size = r->linesize * r->h; r->inv = row_inverse(r->linesize);
         }
     }
     g.cur_slot = (int)(s->ref - s->DPB);
-    for (int p = 0; p < 3; p++) { g.cur_base[p] = s->frame->data[p]; g.cur_ls[p] = s->frame->linesize[p]; }
+    for (int p = 0; p < 3; p++) {
+        g.cur_base[p] = s->frame->data[p]; g.cur_ls[p] = s->frame->linesize[p];
+        g.cur_size[p] = g.cur_ls[p] * G.ph[p]; g.cur_inv[p] = row_inverse(g.cur_ls[p]);
+    }
     g.n_ref = 0; g.pend_ptr = NULL; g.first_tmp = NULL; g.emu[0].buf = g.emu[1].buf = NULL;
     g.poc = s->poc; g.n_workers = 0;
     int rc = b200_rec_begin(g.rec, g.cur_slot, s->poc);
@@ -557,6 +613,7 @@ int b200_frame_end(HEVCContext *s)
     while (G.turn != g.ticket) pthread_cond_wait(&G.cv, &G.mu);
     for (int i = 0; i < g.n_fill && !rc; i++) {      /* grey reference pictures, in decode order with everything else */
         const int grey = 1 << (G.bd - 1);
+        if (G.dump_dir && !strcmp(G.dump_dir, "-")) continue;
         if (G.dump_dir) {
             char path[1024];
             snprintf(path, sizeof(path), "%s/pic_%05d.fill", G.dump_dir, G.dump_no);
@@ -565,7 +622,8 @@ int b200_frame_end(HEVCContext *s)
         } else rc = b200_slot_fill(G.ctx, g.fill_slot[i], grey);
     }
     g.n_fill = 0;
-    if (!rc && G.dump_dir) {
+    if (!rc && G.dump_dir && !strcmp(G.dump_dir, "-")) G.dump_no++;     /* "-": record and drop (host-side timing without a device) */
+    else if (!rc && G.dump_dir) {
         char path[1024];
         snprintf(path, sizeof(path), "%s/pic_%05d.blob", G.dump_dir, G.dump_no++);
         FILE *f = fopen(path, "wb");
@@ -632,5 +690,6 @@ void b200_shim_close(void)
     if (g.rec) b200_rec_destroy(g.rec);      /* recorders of other threads die with their threads' process */
     if (G.ctx) b200_ctx_destroy(G.ctx);
     G.ctx = NULL; G.next_ticket = G.turn = 0;
-    memset(&g, 0, sizeof(g));
+    ShimThread *t = &g;
+    if (t != &g_oom) { const unsigned seq = t->frame_seq; memset(t, 0, sizeof(*t)); t->frame_seq = seq; }   /* workers compare (att, att_seq) */
 }
