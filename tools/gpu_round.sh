@@ -13,6 +13,10 @@ cat gpurun_out/${tag}_bench_1080p.json
 if [ -z "$SKIP_DECODE" ]; then
   timeout 900 python tools/decode_bench.py --repeat 1 --passes 3 > gpurun_out/${tag}_decode.json 2> gpurun_out/${tag}_decode.err
   cat gpurun_out/${tag}_decode.json
+  if [ -f oracle/_ref/streams/c3_4k_calm_17.hevc ]; then    # lightly coded 4K stream (tools/make_bench_streams.sh): the bit rate of real content
+    timeout 600 python tools/decode_bench.py oracle/_ref/streams/c3_4k_calm_17.hevc --repeat 1 --passes 4 > gpurun_out/${tag}_decode_calm.json 2>> gpurun_out/${tag}_decode.err
+    cat gpurun_out/${tag}_decode_calm.json
+  fi
 fi
 if [ -n "$WITH_NCU" ]; then
   timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 1500 --csv --log-file gpurun_out/${tag}_launches.csv python bench.py --steps 2 --warmup 3 --no-cpu-baseline > gpurun_out/${tag}_ncu_bench.log 2>&1

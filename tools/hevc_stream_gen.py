@@ -230,7 +230,7 @@ SIG_CTX_4x4 = [0, 1, 4, 5, 2, 3, 4, 5, 6, 6, 8, 8, 7, 7, 8, 8]
 
 
 class StreamGen:
-    def __init__(self, width, height, bit_depth=8, seed=1, qp=30, sao=True, ctb_log2=6, weighted=False, wpp=False, cip=False, tqb=0.0, tiles=None, lf_across_tiles=True, tskip=0.0, pcm=0.0, pcm_lf_off=False, slices=1, lf_across_slices=True, cfi=1):
+    def __init__(self, width, height, bit_depth=8, seed=1, qp=30, sao=True, ctb_log2=6, weighted=False, wpp=False, cip=False, tqb=0.0, tiles=None, lf_across_tiles=True, tskip=0.0, pcm=0.0, pcm_lf_off=False, slices=1, lf_across_slices=True, cfi=1, calm=0.0):
         self.W, self.H, self.bd, self.qp, self.sao, self.ctb_log2 = width, height, bit_depth, qp, sao, ctb_log2
         self.weighted = weighted
         self.cip = cip                      # pps constrained_intra_pred_flag (hevcpred_template.c:116-249)
@@ -240,6 +240,7 @@ class StreamGen:
         self.slices, self.lf_across_slices = slices, lf_across_slices   # independent slices per picture, each starting a CTB row
         assert slices == 1 or not (tiles or wpp), "several slices are generated without tiles / WPP only"
         self.pcm, self.pcm_lf_off = pcm, pcm_lf_off   # share of 2Nx2N intra CUs (8x8 .. 32x32) coded as PCM; pcm_loop_filter_disabled_flag
+        self.calm = calm                    # 0 = densely coded random content (default), 1 = lightly coded: more skipped / larger CUs, fewer and sparser residual blocks
         self.tskip = tskip                  # share of 4x4 TUs with transform_skip_flag (pps transform_skip_enabled_flag when > 0)
         self.cu_bypass = 0
         self.tiles = tiles                  # (columns, rows), uniform spacing: one CABAC substream + entry point per tile, tile scan
@@ -558,7 +559,7 @@ class StreamGen:
                 inc += int(self.ct_depth[y0 >> 3, (x0 >> 3) - 1] > depth)
             if self.up_ok(y0):
                 inc += int(self.ct_depth[(y0 >> 3) - 1, x0 >> 3] > depth)
-            split = int(self.rng.random() < {6: 0.9, 5: 0.65, 4: 0.45}[log2])
+            split = int(self.rng.random() < {6: 0.9, 5: 0.65, 4: 0.45}[log2] * (1 - 0.45 * self.calm))
             c.encode(o["split_coding_unit_flag"] + inc, split)
         else:
             split = int(log2 > self.min_cb_log2)
@@ -677,7 +678,7 @@ class StreamGen:
                 inc += int(self.skip[y0 >> 3, (x0 >> 3) - 1] != 0)
             if self.up_ok(y0):
                 inc += int(self.skip[(y0 >> 3) - 1, x0 >> 3] != 0)
-            skipped = int(r.random() < 0.25)
+            skipped = int(r.random() < 0.25 + 0.5 * self.calm)
             c.encode(o["skip_flag"] + inc, skipped)
             self.skip[y0 >> 3:(y0 + size) >> 3, x0 >> 3:(x0 + size) >> 3] = skipped
             self.ct_depth[y0 >> 3:(y0 + size) >> 3, x0 >> 3:(x0 + size) >> 3] = depth
@@ -685,7 +686,7 @@ class StreamGen:
                 self.prediction_unit(size, size, depth, True)
                 self.ipm[y0 >> 2:(y0 + size) >> 2, x0 >> 2:(x0 + size) >> 2] = 1
                 return
-            intra = int(r.random() < 0.2)
+            intra = int(r.random() < 0.2 - 0.15 * self.calm)
             c.encode(o["pred_mode"], intra)
             if not intra:
                 self.ipm[y0 >> 2:(y0 + size) >> 2, x0 >> 2:(x0 + size) >> 2] = 1
@@ -700,7 +701,7 @@ class StreamGen:
                     merge = self.prediction_unit(pw_, ph_, depth, False)
                 root = 1
                 if not (part == 0 and merge):
-                    root = int(r.random() < 0.7)
+                    root = int(r.random() < 0.7 - 0.35 * self.calm)
                     c.encode(o["no_residual_data_flag"], root)
                 if root:
                     self.inter = True
@@ -778,10 +779,10 @@ class StreamGen:
         if log2 > 2:
             for k in range(2):
                 if tdepth == 0 or parent_cbf_c[k][0]:
-                    cbf_c[k][0] = int(r.random() < 0.5)
+                    cbf_c[k][0] = int(r.random() < 0.5 - 0.3 * self.calm)
                     c.encode(o["cbf_cb, cbf_cr"] + tdepth, cbf_c[k][0])
                     if self.cfi == 2 and (not split or log2 == 3):
-                        cbf_c[k][1] = int(r.random() < 0.5)
+                        cbf_c[k][1] = int(r.random() < 0.5 - 0.3 * self.calm)
                         c.encode(o["cbf_cb, cbf_cr"] + tdepth, cbf_c[k][1])
         if split:
             h = 1 << (log2 - 1)
@@ -792,7 +793,7 @@ class StreamGen:
         if inter and tdepth == 0 and not any(cbf_c[0][:nblk] + cbf_c[1][:nblk]):
             cbf_luma = 1                                                    # inferred (7.3.8.8)
         else:
-            cbf_luma = int(r.random() < 0.7)
+            cbf_luma = int(r.random() < 0.7 - 0.3 * self.calm)
             c.encode(o["cbf_luma"] + (1 if tdepth == 0 else 0), cbf_luma)
 
         def scan_of(m, lg):
@@ -822,7 +823,7 @@ class StreamGen:
         # random sparse levels, low frequencies more likely
         lev = np.zeros((n, n), np.int64)
         yy, xx = np.mgrid[0:n, 0:n]
-        mask = r.random((n, n)) < np.exp(-(xx + yy) / r.uniform(0.7, 0.7 + n / 4.0))
+        mask = r.random((n, n)) < np.exp(-(xx + yy) / (r.uniform(0.7, 0.7 + n / 4.0) * (1 - 0.7 * self.calm)))
         mags = np.maximum(1, np.rint(np.abs(r.laplace(0, 2.5, (n, n))))).astype(np.int64)
         big = r.random((n, n)) < 0.03
         mags = np.where(big, mags * int(r.integers(5, 60)), mags)
@@ -1023,10 +1024,11 @@ def main():
     ap.add_argument("--tskip", type=float, default=0.0, help="share of 4x4 TUs coded with transform_skip_flag")
     ap.add_argument("--tiles", default="", help="COLSxROWS uniformly spaced tiles, e.g. 3x2")
     ap.add_argument("--no-lf-across-tiles", action="store_true", help="loop_filter_across_tiles_enabled_flag = 0")
+    ap.add_argument("--calm", type=float, default=0.0, help="0 = dense random content (default) .. 1 = lightly coded (more skip, larger CUs, sparse residuals)")
     ap.add_argument("--wpp", action="store_true", help="entropy_coding_sync_enabled_flag: one substream per CTB row + entry points")
     a = ap.parse_args()
     verify_tables_against_reference()
-    g = StreamGen(a.width, a.height, a.bit_depth, a.seed, a.qp, sao=not a.no_sao, weighted=a.weighted, wpp=a.wpp, cip=a.cip, tqb=a.tqb, tskip=a.tskip, pcm=a.pcm, pcm_lf_off=a.pcm_lf_off, slices=a.slices, lf_across_slices=not a.no_lf_across_slices, cfi=a.cfi,
+    g = StreamGen(a.width, a.height, a.bit_depth, a.seed, a.qp, sao=not a.no_sao, weighted=a.weighted, wpp=a.wpp, cip=a.cip, tqb=a.tqb, tskip=a.tskip, pcm=a.pcm, pcm_lf_off=a.pcm_lf_off, slices=a.slices, lf_across_slices=not a.no_lf_across_slices, cfi=a.cfi, calm=a.calm,
                   tiles=tuple(int(v) for v in a.tiles.split("x")) if a.tiles else None, lf_across_tiles=not a.no_lf_across_tiles)
     data = g.stream(a.frames, a.pattern)
     open(a.out, "wb").write(data)
