@@ -11,6 +11,9 @@
  *   b200_frame_end         when every CTB of the picture has been parsed and filtered (libavcodec/hevc.c:3447-3449, after tiles_filters)
  *   b200_frame_readback    before the picture is hashed or output                 (libavcodec/hevc.c:4145, 4178)
  *   b200_frame_fill        when generate_missing_ref() has filled a grey reference  (libavcodec/hevc_refs.c:538-606)
+ *   b200_host_pixels_unused  OPTIONAL, performance only: guard at the top of copy_CTB()  (libavcodec/hevc_filter.c:151-161) --
+ *                          sao_filter_CTB copies every CTB between the host frame and sao_frame before it calls the SAO
+ *                          tables; with the tables on the device nobody reads those host pixels
  *
  * The structs are the reference's own (opaque here); the implementation
  * (openhevc_b200/csrc/shim/hevcdsp_init_b200.c) is compiled against the reference headers.
@@ -41,6 +44,7 @@ int  b200_frame_end(struct HEVCContext *s);
 int  b200_frame_readback(struct HEVCContext *s, struct AVFrame *frame);
 int  b200_frame_fill(struct HEVCContext *s, struct HEVCFrame *frame);       /* grey reference picture (generate_missing_ref) */
 int  b200_frame_upload_ref(struct HEVCContext *s, struct AVFrame *frame);   /* host-only reference picture -> device slot */
+int  b200_host_pixels_unused(void);                                         /* 1 once the B200 tables are installed */
 void b200_shim_close(void);
 const char *b200_shim_error(void);
 

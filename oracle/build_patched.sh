@@ -1,6 +1,6 @@
 #!/bin/bash
 # TEST INFRASTRUCTURE — builds the reference decoder WITH the B200 hooks of INTEGRATION.md into
-# oracle/_ref/libohevc_b200.so: the five files that receive a hook are copied to oracle/_ref/patched/ (git-ignored),
+# oracle/_ref/libohevc_b200.so: the six files that receive a hook are copied to oracle/_ref/patched/ (git-ignored),
 # the hook lines are inserted with sed, every other object is reused from the plain reference build.
 # Needs /root/reference; on the GPU box the prebuilt library is used.
 set -euo pipefail
@@ -12,7 +12,7 @@ if [ ! -d "$REF/libavcodec" ]; then echo "build_patched: $REF not present - keep
 [ -f "$OUT/libohevc_ref.so" ] || "$HERE/build_ref.sh"
 P=$OUT/patched/libavcodec
 mkdir -p "$P" "$OUT/obj_b200"
-for f in hevc.c hevcdsp.c hevcpred.c videodsp.c hevc_refs.c; do cp "$REF/libavcodec/$f" "$P/$f"; done
+for f in hevc.c hevcdsp.c hevcpred.c videodsp.c hevc_refs.c hevc_filter.c; do cp "$REF/libavcodec/$f" "$P/$f"; done
 inc='#include "b200hevc_tables.h"'
 # table hooks: one more arch-init call, exactly where the x86 / arm ones are (hevcdsp.c:1326-1327, hevcpred.c:84, videodsp.c:57-58)
 sed -i -e "0,/^#include/s//$inc\n#include/" \
@@ -29,15 +29,22 @@ sed -i -e "0,/^#include/s//$inc\n#include/" \
 # a reference picture the stream does not contain (hevc_refs.c:538-606 fills a grey frame on the host): the device slot gets the same fill
 sed -i -e "0,/^#include/s//$inc\n#include/" \
        -e '/^static HEVCFrame \*generate_missing_ref/,/^}/ s/^    return frame;/    b200_frame_fill(s, frame);\n&/' "$P/hevc_refs.c"
+# optional, performance only (B200_NO_COPY_GUARD=1 builds without it): sao_filter_CTB's CTB copies between the host frame and
+# sao_frame feed nothing once the SAO tables record (hevc_filter.c:151-161)
+if [ -z "${B200_NO_COPY_GUARD:-}" ]; then
+  sed -i -e "0,/^#include/s//$inc\n#include/" \
+         -e '/^static void copy_CTB/,/^}/ s/^    int i;/&\n    if (b200_host_pixels_unused()) return;/' "$P/hevc_filter.c"
+  grep -q "b200_host_pixels_unused" "$P/hevc_filter.c" || { echo "hook b200_host_pixels_unused was not inserted" >&2; exit 1; }
+fi
 for pat in ff_hevcdsp_init_b200 ff_hevcpred_init_b200 ff_videodsp_init_b200 b200_frame_begin b200_frame_end b200_frame_readback b200_frame_fill; do
   grep -q "$pat" "$P"/*.c || { echo "hook $pat was not inserted" >&2; exit 1; }
 done
 CFLAGS=$(cat "$OUT/cflags.txt")
-for f in hevc hevcdsp hevcpred videodsp hevc_refs; do
+for f in hevc hevcdsp hevcpred videodsp hevc_refs hevc_filter; do
   gcc $CFLAGS -fPIC -std=gnu99 -w -DPIC -I"$OUT/gen" -I"$REF/libavcodec" -I"$REF" -I"$REF/gpac/modules/openhevc_dec" -I"$ROOT/include" \
       -c "$P/$f.c" -o "$OUT/obj_b200/libavcodec_$f.o"
 done
-objs=$(ls "$OUT"/obj/*.o | grep -v -e 'libavcodec_hevc\.o' -e 'libavcodec_hevcdsp\.o' -e 'libavcodec_hevcpred\.o' -e 'libavcodec_videodsp\.o' -e 'libavcodec_hevc_refs\.o')
+objs=$(ls "$OUT"/obj/*.o | grep -v -e 'libavcodec_hevc\.o' -e 'libavcodec_hevcdsp\.o' -e 'libavcodec_hevcpred\.o' -e 'libavcodec_videodsp\.o' -e 'libavcodec_hevc_refs\.o' -e 'libavcodec_hevc_filter\.o')
 gcc -shared -o "$OUT/libohevc_b200.so" $objs "$OUT"/obj_b200/*.o -L"$ROOT/openhevc_b200" -lb200hevc_shim -lb200hevc \
     -Wl,-rpath,'$ORIGIN/../../openhevc_b200' -lm -lpthread
 echo "built $OUT/libohevc_b200.so"
