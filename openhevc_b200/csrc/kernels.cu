@@ -13,6 +13,12 @@
 #include "common.cuh"
 #include <stdlib.h>
 
+// Kernel launches go through one macro so that tests/emul/ can compile this very file for the CPU (warp-lockstep fibers,
+// -DB200_EMUL) and run whole pictures through the same launchers; for nvcc it is the plain launch syntax.
+#ifndef B200_EMUL
+#define B200_LAUNCH(grid, block, smem, stream, ...) __VA_ARGS__<<<grid, block, smem, stream>>>
+#endif
+
 // --------------------------------------------------------------------------------------------
 // constants
 // --------------------------------------------------------------------------------------------
@@ -116,7 +122,7 @@ int launch_validate(cudaStream_t st, const uint8_t *blob_dev, const B200BlobHead
     for (int p = 0; p < 3; p++) { a.pw[p] = pw[p]; a.ph[p] = ph[p]; }
     a.ncoef = h.sec[B200_SEC_COEFF].count; a.mc_big = h.mc_big_count; a.n_ref = h.n_ref; a.arena_bytes = arena_bytes;
     if (!most) return 0;
-    k_validate<<<(most + 255) / 256, 256, 0, st>>>(a, gate);
+    B200_LAUNCH((most + 255) / 256, 256, 0, st, k_validate)(a, gate);
     return 1;
 }
 
@@ -594,10 +600,16 @@ __global__ void __launch_bounds__(256, 4) k_mc(const B200McRec *__restrict__ rec
 // --------------------------------------------------------------------------------------------
 // debug: per-TU timestamps (ns, %globaltimer) [grab, -, neighbours in, predicted, -, published]; null = off
 __device__ unsigned long long *g_intra_trace = nullptr;
+#ifndef B200_EMUL
 __device__ __forceinline__ unsigned long long gtime() { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; }
+#endif
 #define TRACE(slot) do { if (tr && lane == 0) tr[slot] = gtime(); } while (0)
 int set_intra_trace(unsigned long long *p) { return (int)cudaMemcpyToSymbol(g_intra_trace, &p, sizeof(p)); }
 
+// relaxed, GPU-scope accesses for the flags and edge records other warps poll.  8-byte edge words: naturally aligned 64-bit
+// accesses are single-copy atomic, so a reader sees a whole record or none.  (tests/emul/ supplies CPU versions of the four:
+// plain accesses, the loads also yield to the other emulated warps.)
+#ifndef B200_EMUL
 __device__ __forceinline__ uint32_t ld_relaxed(const uint32_t *p)
 {
     uint32_t v;
@@ -608,7 +620,6 @@ __device__ __forceinline__ void st_relaxed(uint32_t *p, uint32_t v)
 {
     asm volatile("st.relaxed.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
-// 8-byte edge words: naturally aligned 64-bit accesses are single-copy atomic, so a reader sees a whole record or none
 __device__ __forceinline__ uint2 ld_edge(const uint2 *p)
 {
     uint2 v;
@@ -619,6 +630,7 @@ __device__ __forceinline__ void st_edge(uint2 *p, uint2 v)
 {
     asm volatile("st.relaxed.gpu.global.v2.u32 [%0], {%1, %2};" ::"l"(p), "r"(v.x), "r"(v.y) : "memory");
 }
+#endif
 #define EDGE_VALID 0x8000u
 __device__ __forceinline__ uint2 edge_pack(int a, int b, int c, int d)
 {
@@ -1135,22 +1147,22 @@ int launch_mc(cudaStream_t st, const B200McRec *recs, int count, int n_big, cons
     if (n_big) {                        // one warp per tile
         const int grid = (n_big + 7) / 8;
         if (version == 1) {
-            if (bd > 8) k_mc_v1<uint16_t, 32><<<grid, 256, 0, st>>>(recs, n_big, cur, dpb_dev, rt, bd, gate, lay);
-            else        k_mc_v1<uint8_t, 32><<<grid, 256, 0, st>>>(recs, n_big, cur, dpb_dev, rt, bd, gate, lay);
+            if (bd > 8) B200_LAUNCH(grid, 256, 0, st, k_mc_v1<uint16_t, 32>)(recs, n_big, cur, dpb_dev, rt, bd, gate, lay);
+            else        B200_LAUNCH(grid, 256, 0, st, k_mc_v1<uint8_t, 32>)(recs, n_big, cur, dpb_dev, rt, bd, gate, lay);
         } else {
-            if (bd > 8) k_mc<uint16_t, 32><<<grid, 256, 0, st>>>(recs, n_big, cur, dpb_dev, rt, bd, gate, lay);
-            else        k_mc<uint8_t, 32><<<grid, 256, 0, st>>>(recs, n_big, cur, dpb_dev, rt, bd, gate, lay);
+            if (bd > 8) B200_LAUNCH(grid, 256, 0, st, k_mc<uint16_t, 32>)(recs, n_big, cur, dpb_dev, rt, bd, gate, lay);
+            else        B200_LAUNCH(grid, 256, 0, st, k_mc<uint8_t, 32>)(recs, n_big, cur, dpb_dev, rt, bd, gate, lay);
         }
         n++;
     }
     if (n_small) {                      // tiles of <= 8x8 samples: four per warp
         const int grid = (n_small + 31) / 32;
         if (version == 1) {
-            if (bd > 8) k_mc_v1<uint16_t, 8><<<grid, 256, 0, st>>>(recs + n_big, n_small, cur, dpb_dev, rt, bd, gate, lay);
-            else        k_mc_v1<uint8_t, 8><<<grid, 256, 0, st>>>(recs + n_big, n_small, cur, dpb_dev, rt, bd, gate, lay);
+            if (bd > 8) B200_LAUNCH(grid, 256, 0, st, k_mc_v1<uint16_t, 8>)(recs + n_big, n_small, cur, dpb_dev, rt, bd, gate, lay);
+            else        B200_LAUNCH(grid, 256, 0, st, k_mc_v1<uint8_t, 8>)(recs + n_big, n_small, cur, dpb_dev, rt, bd, gate, lay);
         } else {
-            if (bd > 8) k_mc<uint16_t, 8><<<grid, 256, 0, st>>>(recs + n_big, n_small, cur, dpb_dev, rt, bd, gate, lay);
-            else        k_mc<uint8_t, 8><<<grid, 256, 0, st>>>(recs + n_big, n_small, cur, dpb_dev, rt, bd, gate, lay);
+            if (bd > 8) B200_LAUNCH(grid, 256, 0, st, k_mc<uint16_t, 8>)(recs + n_big, n_small, cur, dpb_dev, rt, bd, gate, lay);
+            else        B200_LAUNCH(grid, 256, 0, st, k_mc<uint8_t, 8>)(recs + n_big, n_small, cur, dpb_dev, rt, bd, gate, lay);
         }
         n++;
     }
@@ -1168,7 +1180,7 @@ static int launch_residual_t(cudaStream_t st, const B200TuRec *const recs[4], co
         total += L.nblk[k];
     }
     if (!total) return 0;
-    k_residual<PIX><<<total, 128, 0, st>>>(L, pool, parked, cur, bd, gate);
+    B200_LAUNCH(total, 128, 0, st, k_residual<PIX>)(L, pool, parked, cur, bd, gate);
     return 1;
 }
 int launch_residual(cudaStream_t st, const B200TuRec *const recs[4], const int counts[4], const int16_t *pool, int16_t *parked, const FrameDesc &cur, int bd, const uint32_t *gate)
@@ -1188,14 +1200,14 @@ int launch_intra(cudaStream_t st, const B200IntraRec *recs, int count, const int
     static const bool sparse_ok = getenv("B200_EDGES_SPARSE") && atoi(getenv("B200_EDGES_SPARSE"));
     const long units = (long)(cur.p[0].w / 4) * (cur.p[0].h / 4) + 2l * (cur.p[1].w / 4) * (cur.p[1].h / 4);
     if (sparse_ok && (long)count * 16 < units) {
-        if (bd > 8) k_intra_edges_init_sparse<uint16_t><<<(count + 3) / 4, 128, 0, st>>>(recs, count, cur, ed, counter);
-        else        k_intra_edges_init_sparse<uint8_t><<<(count + 3) / 4, 128, 0, st>>>(recs, count, cur, ed, counter);
+        if (bd > 8) B200_LAUNCH((count + 3) / 4, 128, 0, st, k_intra_edges_init_sparse<uint16_t>)(recs, count, cur, ed, counter);
+        else        B200_LAUNCH((count + 3) / 4, 128, 0, st, k_intra_edges_init_sparse<uint8_t>)(recs, count, cur, ed, counter);
     } else {
         const dim3 gi((cur.p[0].w / 4 + 127) / 128, cur.p[0].h / 4, 3);
-        if (bd > 8) k_intra_edges_init<uint16_t><<<gi, 128, 0, st>>>(cur, ed);
-        else        k_intra_edges_init<uint8_t><<<gi, 128, 0, st>>>(cur, ed);
+        if (bd > 8) B200_LAUNCH(gi, 128, 0, st, k_intra_edges_init<uint16_t>)(cur, ed);
+        else        B200_LAUNCH(gi, 128, 0, st, k_intra_edges_init<uint8_t>)(cur, ed);
     }
-    k_intra_prepass<<<(count + 255) / 256, 256, 0, st>>>(recs, count, ed, counter);
+    B200_LAUNCH((count + 255) / 256, 256, 0, st, k_intra_prepass)(recs, count, ed, counter);
     int grid = (count + 3) / 4;
     // persistent warps.  The list is sorted by dependency level, so the TUs that can run together are adjacent and a
     // small window exposes all the parallelism there is; more waiting warps would only add polling traffic on L2.
@@ -1208,16 +1220,16 @@ int launch_intra(cudaStream_t st, const B200IntraRec *recs, int count, const int
         cd.bits = cip_words + 4; cd.log2_pu = (int)ch.log2_min_pu_size; cd.pu_w = (int)ch.min_pu_width; cd.pu_h = (int)ch.min_pu_height;
         cd.pic_w = cur.p[0].w; cd.pic_h = cur.p[0].h; cd.hs_c = cfi != 3; cd.vs_c = cfi == 1;
     }
-    if (bd > 8) k_intra<uint16_t><<<grid, 128, 0, st>>>(recs, count, pool, cur, bd, ed, counter, cd);
-    else        k_intra<uint8_t><<<grid, 128, 0, st>>>(recs, count, pool, cur, bd, ed, counter, cd);
+    if (bd > 8) B200_LAUNCH(grid, 128, 0, st, k_intra<uint16_t>)(recs, count, pool, cur, bd, ed, counter, cd);
+    else        B200_LAUNCH(grid, 128, 0, st, k_intra<uint8_t>)(recs, count, pool, cur, bd, ed, counter, cd);
     return 3;
 }
 
 int launch_deblock(cudaStream_t st, const uint16_t *grid, const B200DbkLayout &L, const FrameDesc &cur, int bd)
 {
     const dim3 g((cur.p[0].w + 4 + DBK_TW - 1) / DBK_TW, (cur.p[0].h + 4 + DBK_TH - 1) / DBK_TH, 3);
-    if (bd > 8) k_deblock<uint16_t><<<g, DBK_THREADS, 0, st>>>(grid, L, cur, bd);
-    else        k_deblock<uint8_t><<<g, DBK_THREADS, 0, st>>>(grid, L, cur, bd);
+    if (bd > 8) B200_LAUNCH(g, DBK_THREADS, 0, st, k_deblock<uint16_t>)(grid, L, cur, bd);
+    else        B200_LAUNCH(g, DBK_THREADS, 0, st, k_deblock<uint8_t>)(grid, L, cur, bd);
     return 1;
 }
 
@@ -1239,15 +1251,15 @@ int launch_sao(cudaStream_t st, const B200SaoRec *grid, const FrameDesc &src, co
     const int blocks = (base[3] + 7) / 8;
     const int4 tb = make_int4(base[0], base[1], base[2], base[3]);
     const int3 tx = make_int3(ntx[0], ntx[1], ntx[2]);
-    if (bd > 8) k_sao<uint16_t><<<blocks, 256, 0, st>>>(grid, src, dst, bd, log2_ctb, ctb_w, ctb_h, cfi, tb, tx, tq);
-    else        k_sao<uint8_t><<<blocks, 256, 0, st>>>(grid, src, dst, bd, log2_ctb, ctb_w, ctb_h, cfi, tb, tx, tq);
+    if (bd > 8) B200_LAUNCH(blocks, 256, 0, st, k_sao<uint16_t>)(grid, src, dst, bd, log2_ctb, ctb_w, ctb_h, cfi, tb, tx, tq);
+    else        B200_LAUNCH(blocks, 256, 0, st, k_sao<uint8_t>)(grid, src, dst, bd, log2_ctb, ctb_w, ctb_h, cfi, tb, tx, tq);
     return 1;
 }
 
 int launch_fill(cudaStream_t st, const FrameDesc &f, int bd, int value)
 {
     const dim3 g((f.p[0].w + 255) / 256, f.p[0].h, 3);
-    if (bd > 8) k_fill<uint16_t><<<g, 256, 0, st>>>(f, value);
-    else        k_fill<uint8_t><<<g, 256, 0, st>>>(f, value);
+    if (bd > 8) B200_LAUNCH(g, 256, 0, st, k_fill<uint16_t>)(f, value);
+    else        B200_LAUNCH(g, 256, 0, st, k_fill<uint8_t>)(f, value);
     return 1;
 }

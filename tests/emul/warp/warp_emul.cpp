@@ -1,0 +1,220 @@
+// TEST INFRASTRUCTURE -- the scheduler behind tests/emul/warp/cuda_runtime.h: one fiber per CUDA thread, blocks one after
+// another, lanes of a warp in lock-step at every *_sync collective.  Single OS thread; not re-entrant (a global lock
+// serialises kernel launches of different host threads).
+#include <cuda_runtime.h>
+#include <stdio.h>
+#include <sys/mman.h>
+#include <ucontext.h>
+#include <mutex>
+#include <vector>
+
+EmuThread *emu_self;
+uint3 emu_block_idx;
+dim3 emu_block_dim, emu_grid_dim;
+
+void emu_recheck(int warp);
+
+namespace {
+
+struct Collective {
+    unsigned mask = 0, arrived = 0;
+    int op = 0, width = 32;
+    uint32_t val[32];
+    int arg[32];
+};
+struct Fiber : EmuThread {
+    ucontext_t ctx;
+    char *stack = nullptr;
+    bool done = false, waiting = false;      // waiting: parked in a collective or the block barrier until released
+    uint32_t result = 0;
+    int warp = 0, lane = 0;
+};
+struct Warp {
+    unsigned exited = 0;
+    std::vector<Collective> open;            // collectives in progress, keyed by mask (disjoint lane groups sync independently)
+};
+
+constexpr size_t STACK = 256 << 10;
+std::mutex g_launch;
+std::vector<Fiber> g_fib;
+std::vector<Warp> g_warp;
+ucontext_t g_sched;
+Fiber *g_cur;
+const std::function<void()> *g_body;
+const char *g_name;
+int g_barrier_arrived, g_alive;
+unsigned long g_switches;
+
+void to_scheduler() { swapcontext(&g_cur->ctx, &g_sched); }
+
+void fiber_main()
+{
+    (*g_body)();
+    Fiber *f = g_cur;
+    f->done = true;
+    g_alive--;
+    Warp &w = g_warp[f->warp];
+    w.exited |= 1u << f->lane;
+    // a lane that leaves may complete a collective the others are parked in (they only wait for lanes still alive)
+    emu_recheck(f->warp);
+    if (g_barrier_arrived && g_barrier_arrived == g_alive) {          // ... or the block barrier
+        for (Fiber &o : g_fib) o.waiting = false;
+        g_barrier_arrived = 0;
+    }
+    to_scheduler();
+}
+
+uint32_t resolve(const Collective &c, int lane)
+{
+    const int seg = lane & ~(c.width - 1), end = seg + c.width - 1;
+    int src = lane;
+    switch (c.op) {
+    case EMU_SYNCWARP: return 0;
+    case EMU_SHFL_IDX: src = seg | (c.arg[lane] & (c.width - 1)); break;
+    case EMU_SHFL_XOR: src = lane ^ c.arg[lane]; if (src > end || src < seg) src = lane; break;
+    case EMU_SHFL_UP: src = lane - c.arg[lane]; if (src < seg) src = lane; break;
+    case EMU_SHFL_DOWN: src = lane + c.arg[lane]; if (src > end) src = lane; break;
+    case EMU_ANY: case EMU_ALL: case EMU_BALLOT: {
+        unsigned b = 0;
+        for (int l = 0; l < 32; l++) if ((c.arrived >> l & 1) && c.val[l]) b |= 1u << l;
+        return c.op == EMU_ANY ? b != 0 : c.op == EMU_ALL ? b == c.arrived : b;
+    }
+    }
+    return (c.arrived >> src & 1) ? c.val[src] : c.val[lane];          // reading a lane that does not take part is undefined on the device
+}
+
+bool try_complete(int warp, size_t k)
+{
+    Warp &w = g_warp[warp];
+    Collective &c = w.open[k];
+    if (c.arrived != (c.mask & ~w.exited)) return false;
+    for (int l = 0; l < 32; l++)
+        if (c.arrived >> l & 1) {
+            Fiber &f = g_fib[warp * 32 + l];
+            f.result = resolve(c, l);
+            f.waiting = false;
+        }
+    w.open.erase(w.open.begin() + k);
+    return true;
+}
+
+}  // namespace
+
+void emu_recheck(int warp)
+{
+    for (size_t k = 0; k < g_warp[warp].open.size();)
+        if (!try_complete(warp, k)) k++;
+}
+
+uint32_t emu_collective(unsigned mask, int op, uint32_t value, int arg, int width)
+{
+    Fiber *f = g_cur;
+    Warp &w = g_warp[f->warp];
+    if (!(mask >> f->lane & 1)) { fprintf(stderr, "emu: %s: lane %d calls a collective whose mask %08x excludes it\n", g_name, f->lane, mask); abort(); }
+    size_t k = 0;
+    while (k < w.open.size() && !(w.open[k].mask == mask && !(w.open[k].arrived >> f->lane & 1))) k++;
+    if (k == w.open.size()) { w.open.emplace_back(); w.open[k].mask = mask; w.open[k].op = op; w.open[k].width = width; }
+    Collective &c = w.open[k];
+    if (c.op != op || c.width != width) { fprintf(stderr, "emu: %s: lanes of one warp meet in different collectives (mask %08x: op %d vs %d)\n", g_name, mask, c.op, op); abort(); }
+    c.arrived |= 1u << f->lane;
+    c.val[f->lane] = value;
+    c.arg[f->lane] = arg;
+    f->waiting = true;
+    if (!try_complete(f->warp, k)) to_scheduler();
+    return f->result;
+}
+
+void emu_syncthreads()
+{
+    Fiber *f = g_cur;
+    g_barrier_arrived++;
+    if (g_barrier_arrived == g_alive) {
+        for (Fiber &o : g_fib) o.waiting = false;
+        g_barrier_arrived = 0;
+        return;
+    }
+    f->waiting = true;
+    to_scheduler();
+}
+
+void emu_yield() { if (g_cur) to_scheduler(); }
+
+void emu_run_grid(dim3 grid, dim3 block, const std::function<void()> &body, const char *name)
+{
+    std::lock_guard<std::mutex> lock(g_launch);
+    const unsigned n = block.x * block.y * block.z;
+    if (n == 0 || grid.x == 0 || grid.y == 0 || grid.z == 0) return;
+    if (g_fib.size() < n) {
+        const size_t old = g_fib.size();
+        g_fib.resize(n);
+        for (size_t i = old; i < n; i++) {
+            g_fib[i].stack = (char *)mmap(nullptr, STACK, PROT_READ | PROT_WRITE, MAP_PRIVATE | MAP_ANONYMOUS | MAP_NORESERVE, -1, 0);
+            if (g_fib[i].stack == MAP_FAILED) { perror("emu: fiber stack"); abort(); }
+        }
+    }
+    g_body = &body;
+    g_name = name;
+    emu_block_dim = block;
+    emu_grid_dim = grid;
+    for (unsigned bz = 0; bz < grid.z; bz++)
+        for (unsigned by = 0; by < grid.y; by++)
+            for (unsigned bx = 0; bx < grid.x; bx++) {
+                emu_block_idx = uint3{ bx, by, bz };
+                g_warp.assign((n + 31) / 32, Warp());
+                if (n & 31) g_warp.back().exited = ~0u << (n & 31);       // lanes that do not exist
+                g_alive = (int)n;
+                g_barrier_arrived = 0;
+                for (unsigned t = 0; t < n; t++) {
+                    Fiber &f = g_fib[t];
+                    f.tid = uint3{ t % block.x, t / block.x % block.y, t / (block.x * block.y) };
+                    f.done = f.waiting = false;
+                    f.warp = (int)t / 32;
+                    f.lane = (int)t & 31;
+                    getcontext(&f.ctx);
+                    f.ctx.uc_stack.ss_sp = f.stack;
+                    f.ctx.uc_stack.ss_size = STACK;
+                    f.ctx.uc_link = nullptr;
+                    makecontext(&f.ctx, fiber_main, 0);
+                }
+                for (int left = (int)n; left;) {
+                    bool ran = false;
+                    for (unsigned t = 0; t < n; t++) {
+                        Fiber &f = g_fib[t];
+                        if (f.done || f.waiting) continue;
+                        g_cur = &f;
+                        emu_self = &f;
+                        g_switches++;
+                        swapcontext(&g_sched, &f.ctx);
+                        ran = true;
+                        if (f.done) left--;
+                    }
+                    if (!ran && left) {
+                        fprintf(stderr, "emu: %s: block (%u,%u,%u) is stuck: %d threads wait in collectives nobody completes\n", name, bx, by, bz, left);
+                        for (size_t wi = 0; wi < g_warp.size(); wi++)
+                            for (const Collective &c : g_warp[wi].open)
+                                fprintf(stderr, "  warp %zu: op %d mask %08x arrived %08x exited %08x\n", wi, c.op, c.mask, c.arrived, g_warp[wi].exited);
+                        abort();
+                    }
+                }
+            }
+    g_cur = nullptr;
+    emu_self = nullptr;
+}
+
+// ---- runtime API stubs that own memory -------------------------------------------------------------------------------------
+cudaError_t cudaMalloc(void **p, size_t n)
+{
+    if (posix_memalign(p, 256, n ? n : 1)) return cudaErrorInvalidValue;     // exactly n bytes: an address sanitizer build sees every overrun
+    memset(*p, 0xA5, n);                       // device memory comes uninitialised: make reads of it show
+    return cudaSuccess;
+}
+cudaError_t cudaFree(void *p) { free(p); return cudaSuccess; }
+cudaError_t cudaHostAlloc(void **p, size_t n, unsigned) { return posix_memalign(p, 4096, n ? n : 1) ? cudaErrorInvalidValue : cudaSuccess; }
+cudaError_t cudaFreeHost(void *p) { free(p); return cudaSuccess; }
+cudaError_t cudaPointerGetAttributes(cudaPointerAttributes *a, const void *) { memset(a, 0, sizeof(*a)); a->type = cudaMemoryTypeUnregistered; return cudaSuccess; }
+struct EmuStream { int unused; };
+struct EmuEvent { int unused; };
+cudaError_t cudaStreamCreateWithFlags(cudaStream_t *s, unsigned) { *s = new EmuStream(); return cudaSuccess; }
+cudaError_t cudaStreamDestroy(cudaStream_t s) { delete s; return cudaSuccess; }
+cudaError_t cudaEventCreateWithFlags(cudaEvent_t *e, unsigned) { *e = new EmuEvent(); return cudaSuccess; }
+cudaError_t cudaEventDestroy(cudaEvent_t e) { delete e; return cudaSuccess; }

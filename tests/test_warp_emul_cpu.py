@@ -1,0 +1,167 @@
+"""CPU suite: the CUDA kernels' own source on the CPU.
+
+tests/emul/ compiles openhevc_b200/csrc/kernels.cu + engine.cu + recorder.cpp UNCHANGED with g++ against a stand-in
+<cuda_runtime.h> (tests/emul/warp/): every CUDA thread is a fiber, the lanes of a warp meet in lock-step at each
+__shfl_*_sync / __syncwarp / vote / __syncthreads, kernel launches, copies and events complete at once.  The result,
+oracle/_ref/libb200hevc_emul.so, has the C ABI of libb200hevc.so.  These tests load it IN PLACE of the CUDA library -- only
+here, the product never does -- and run
+
+ * the GPU parity tests (tests/test_parity_gpu.py, same functions, same seeds) against the oracle, and
+ * the real decoder with the B200 hooks on the committed streams (decode_b200, the emulated library pre-loaded) against
+   the MD5s of the unmodified reference decoder,
+
+so a kernel or engine change is checked bit-exactly before a GPU is spent on it.  Not shown by this: memory-model races,
+stream / event ordering, anything about speed -- that stays with `-m gpu`."""
+import glob
+import os
+import subprocess
+import sys
+
+import pytest
+
+import oracle_lib
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+REFDIR = os.path.join(ROOT, "oracle", "_ref")
+EMUL = os.path.join(REFDIR, "libb200hevc_emul.so")
+STREAMS = sorted(glob.glob(os.path.join(HERE, "golden", "streams", "*.hevc")))
+SMALL = [s for s in STREAMS if "416x240" in s or "256x128" in s]
+
+needs_emul = pytest.mark.skipif(not os.path.exists(EMUL), reason="oracle/_ref/libb200hevc_emul.so not built (make -C tests/emul)")
+
+
+@pytest.fixture
+def emulated(monkeypatch):
+    """FrameEngine loads the emulated library instead of libb200hevc.so for the duration of one test"""
+    from openhevc_b200 import _lib
+    monkeypatch.setattr(_lib, "LIB_PATH", EMUL)
+    return True
+
+
+@needs_emul
+def test_emulated_library_has_the_product_abi():
+    import ctypes
+    from openhevc_b200 import _lib
+    lib = ctypes.CDLL(EMUL)
+    for name in _lib.EXPORTS:
+        assert hasattr(lib, name), name
+
+
+PARITY = ["test_weighted_prediction_and_sao_restore", "test_constrained_intra_pred", "test_sao_restore_of_bypass_pus", "test_intra_only_small_blocks",
+          "test_stages_individually", "test_far_out_of_picture_motion", "test_pcm_and_exotic_transform_paths", "test_malformed_blobs_are_rejected_not_executed",
+          "test_malformed_inter_records_are_rejected_on_the_device"]
+
+
+@needs_emul
+@pytest.mark.parametrize("name", PARITY)
+def test_gpu_parity_test_on_the_emulated_kernels(emulated, name):
+    import test_parity_gpu
+    getattr(test_parity_gpu, name)()
+
+
+@needs_emul
+@pytest.mark.parametrize("w,h,cfi,bd", [(256, 128, 1, 8), (256, 128, 1, 10), (192, 128, 2, 10), (192, 128, 3, 8), (320, 192, 1, 12)])
+def test_sequence_all_stages_on_the_emulated_kernels(emulated, w, h, cfi, bd):
+    import test_parity_gpu
+    test_parity_gpu.test_sequence_all_stages(w, h, cfi, bd)
+
+
+@needs_emul
+@pytest.mark.parametrize("cfi,bd", [(1, 8), (2, 10)])
+def test_grey_reference_fill_on_the_emulated_kernels(emulated, cfi, bd):
+    import test_parity_gpu
+    test_parity_gpu.test_grey_reference_fill(cfi, bd)
+
+
+@needs_emul
+def test_golden_fixtures_on_the_emulated_kernels(emulated):
+    import test_golden
+    for path in test_golden.FIXTURES:
+        test_golden.test_cuda_reproduces_reference_golden(path)
+
+
+# the experiments behind environment switches (read once per process, hence a child process each): bit-exact or not worth a GPU visit
+VARIANTS = [dict(B200_MC="2"), dict(B200_MC_DESC="1"), dict(B200_EDGES_SPARSE="1"), dict(B200_VALIDATE="2"), dict(B200_LANES="1")]
+
+
+@needs_emul
+@pytest.mark.parametrize("env", VARIANTS, ids=lambda e: ",".join(f"{k}={v}" for k, v in e.items()))
+def test_switch_variants_on_the_emulated_kernels(env):
+    code = ("import sys; sys.path[:0] = [%r, %r]\n"
+            "from openhevc_b200 import _lib; _lib.LIB_PATH = %r\n"
+            "import test_parity_gpu as T\n"
+            "T.run_sequence(256, 128, 1, 10, seeds=[11, 12, 13], exotic=0.04)\n"
+            "T.run_sequence(192, 128, 2, 8, seeds=[14, 15], p_intra=0.05)\n"
+            "T.run_sequence(192, 128, 1, 8, seeds=[16, 17, 18], weighted=True)\n" % (ROOT, HERE, EMUL))
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=900, env=dict(os.environ, **env))
+    assert r.returncode == 0, r.stderr[-3000:]
+
+
+def test_address_sanitizer_sees_no_out_of_bounds_access_in_the_kernels():
+    """the emulated library built with -fsanitize=address: device allocations are exact-size heap blocks and shared memory is
+    static storage, so a kernel reading or writing one element too far -- which a GPU run forgives silently -- aborts here.
+    Includes the malformed work lists that the device-side validation must reject before any kernel trusts them."""
+    asan_lib = os.path.join(REFDIR, "libb200hevc_emul_asan.so")
+    rt = subprocess.run(["gcc", "-print-file-name=libasan.so"], capture_output=True, text=True).stdout.strip()
+    if not os.path.exists(asan_lib) or not os.path.isabs(rt) or not os.path.exists(rt):
+        pytest.skip("no address sanitizer build / runtime")
+    code = ("import sys; sys.path[:0] = [%r, %r]\n"
+            "from openhevc_b200 import _lib; _lib.LIB_PATH = %r\n"
+            "import test_parity_gpu as T\n"
+            "T.run_sequence(256, 128, 1, 10, seeds=[11, 12, 13], exotic=0.04)\n"
+            "T.run_sequence(192, 128, 2, 8, seeds=[66, 67], cip=True, p_intra=0.5)\n"
+            "T.test_far_out_of_picture_motion()\n"
+            "T.test_malformed_blobs_are_rejected_not_executed()\n"
+            "T.test_malformed_inter_records_are_rejected_on_the_device()\n" % (ROOT, HERE, asan_lib))
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=1800,
+                       env=dict(os.environ, LD_PRELOAD=rt, ASAN_OPTIONS="detect_leaks=0:detect_stack_use_after_return=0"))
+    assert r.returncode == 0 and "ERROR: AddressSanitizer" not in r.stderr, r.stderr[-4000:]
+
+
+def decode_emulated(stream, threads):
+    out = subprocess.run([os.path.join(REFDIR, "decode_b200"), stream, threads], capture_output=True, text=True, timeout=900,
+                         env=dict(os.environ, LD_PRELOAD=EMUL))
+    assert out.returncode == 0, out.stderr[-2000:]
+    return [l for l in out.stdout.splitlines() if l.startswith("frame ")]
+
+
+@needs_emul
+@pytest.mark.parametrize("stream", SMALL, ids=os.path.basename)
+def test_hooked_decoder_on_the_emulated_kernels(stream):
+    """real decoder -> shim -> recorder -> engine -> emulated K0..K5 -> read-back == unmodified reference decoder"""
+    if not os.path.exists(os.path.join(REFDIR, "decode_b200")):
+        pytest.skip("oracle/_ref/decode_b200 not built (needs /root/reference)")
+    want = open(stream[:-5] + ".md5").read().splitlines()
+    assert decode_emulated(stream, "1") == want
+
+
+@needs_emul
+@pytest.mark.parametrize("stream", [s for s in SMALL if os.path.basename(s).startswith(("b_", "ra_416", "wpp_416", "tiles_416x240_10b", "cip_416"))], ids=os.path.basename)
+@pytest.mark.parametrize("threads", ["4", "4w"])
+def test_hooked_decoder_with_threads_on_the_emulated_kernels(stream, threads):
+    if not os.path.exists(os.path.join(REFDIR, "decode_b200")):
+        pytest.skip("oracle/_ref/decode_b200 not built (needs /root/reference)")
+    if threads == "4w" and not os.path.basename(stream).startswith(("wpp_", "tiles_")):
+        pytest.skip("no entry points: slice threads fall back to one thread")
+    ref = subprocess.run([os.path.join(REFDIR, "decode_ref"), stream, threads], capture_output=True, text=True, timeout=600)
+    want = [l for l in ref.stdout.splitlines() if l.startswith("frame ")]
+    if not want:
+        pytest.skip("the reference outputs no picture of this stream with that many threads")
+    assert decode_emulated(stream, threads) == want
+
+
+@needs_emul
+def test_tables_through_shim_on_the_emulated_kernels():
+    """tests/test_dropin_gpu.py's comparison (reference call sequence through the reference's C tables vs through the shim) with the
+    emulated device behind the shim; child process, the emulated library pre-loaded"""
+    if oracle_lib.ref_lib() is None or not os.path.exists(oracle_lib.SHIM_SO):
+        pytest.skip("prebuilt oracle/_ref/libreplay_ref.so or libb200hevc_shim.so missing")
+    code = ("import sys; sys.path[:0] = [%r, %r]\n"
+            "import test_dropin_gpu as T\n"
+            "T.test_tables_through_shim_equal_reference_tables(256, 128, 1, 10, [1, 2], dict(weighted=True))\n"
+            "T.test_tables_through_shim_equal_reference_tables(192, 128, 2, 10, [2], {})\n"
+            "T.test_tables_through_shim_equal_reference_tables(192, 128, 3, 8, [1, 2], dict(sao_restore=True))\n"
+            "T.test_tables_through_shim_equal_reference_tables(192, 128, 2, 8, [1], dict(cip=True, p_intra=0.6))\n" % (ROOT, HERE))
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=900, env=dict(os.environ, LD_PRELOAD=EMUL))
+    assert r.returncode == 0, r.stderr[-3000:]
