@@ -380,18 +380,59 @@ struct McGeom {
 //
 // One reference list of one tile: fills val[j] (j < rows_per) with the 14-bit intermediate of sample
 // (x = gl & (wpw-1), y = part * rows_per + j), exactly the value put_hevc_{q,e}pel* would hold.
+// the window of reference samples one list of one tile needs, as it lies in shared memory
+struct McWin1 {
+    int R;                      // rows
+    int ox, oy;                 // picture position of its first sample (before the even alignment)
+    int skew, ax;               // origin aligned down to an even sample: ax = ox - skew
+    int np, Ws;                 // sample pairs per row, shared-memory row stride (samples)
+};
+template <int TAPS>
+__device__ __forceinline__ McWin1 mc_win1(int sx, int sy, int mx, int my, const McGeom &g)
+{
+    constexpr int BEFORE = TAPS == 8 ? 3 : 1;
+    McWin1 m;
+    const int C = g.w + (mx ? TAPS - 1 : 0);
+    m.R = g.h + (my ? TAPS - 1 : 0);
+    m.ox = sx - (mx ? BEFORE : 0); m.oy = sy - (my ? BEFORE : 0);
+    m.skew = m.ox & 1; m.ax = m.ox - m.skew;
+    m.np = (C + m.skew + 1) >> 1; m.Ws = 2 * m.np;
+    return m;
+}
+__device__ __forceinline__ bool mc_win1_interior(const McWin1 &m, const PlaneDesc &rp)
+{
+    return m.ax >= 0 && m.ax + m.Ws <= rp.w && m.oy >= 0 && m.oy + m.R <= rp.h;
+}
+// window hangs over the picture border: clamp sample by sample (== emulated_edge_mc)
+template <typename PIX, int GS>
+__device__ __forceinline__ void mc_win1_clamped(const McWin1 &m, const PlaneDesc &rp, int gl, uint16_t *win)
+{
+    for (int i = gl; i < m.R * m.Ws; i += GS) {
+        const int r = i / m.Ws, cc = i - r * m.Ws;
+        const int x = clip3i(m.ax + cc, 0, rp.w - 1), y = clip3i(m.oy + r, 0, rp.h - 1);
+        win[i] = __ldg(px_ptr<PIX>(rp, x, y));
+    }
+}
+template <typename PIX>
+__device__ __forceinline__ uint32_t mc_ld_pair(const uint8_t *src)          // two neighbouring samples as two 16-bit halves
+{
+    if (sizeof(PIX) == 2) return __ldg(reinterpret_cast<const uint32_t *>(src));
+    const uint32_t t = __ldg(reinterpret_cast<const uint16_t *>(src));
+    return (t & 0xff) | ((t & 0xff00) << 8);
+}
+
+template <int TAPS, int GS>
+__device__ __forceinline__ void mc_list_fir(const McWin1 &m, int mx, int my, const McGeom &g, int bd, int gl, unsigned gmask,
+                                            const uint16_t *win, int16_t *tmp, int (&val)[8]);
+
 template <typename PIX, int TAPS, int GS>
 __device__ __forceinline__ void mc_list(const PlaneDesc &rp, int sx, int sy, int mx, int my, const McGeom &g, int bd, int gl, unsigned gmask,
                                         uint16_t *win, int16_t *tmp, int (&val)[8])
 {
-    constexpr int BEFORE = TAPS == 8 ? 3 : 1;
-    const int w = g.w, h = g.h;
-    const int C = w + (mx ? TAPS - 1 : 0), R = h + (my ? TAPS - 1 : 0);
-    const int ox = sx - (mx ? BEFORE : 0), oy = sy - (my ? BEFORE : 0);
-    const int skew = ox & 1, ax = ox - skew;               // window origin aligned down to an even sample
-    const int np = (C + skew + 1) >> 1, Ws = 2 * np;        // sample pairs per row, shared-memory row stride
+    const McWin1 m = mc_win1<TAPS>(sx, sy, mx, my, g);
+    const int R = m.R, np = m.np, ax = m.ax, oy = m.oy;
     __syncwarp(gmask);
-    if (ax >= 0 && ax + Ws <= rp.w && oy >= 0 && oy + R <= rp.h) {
+    if (mc_win1_interior(m, rp)) {
         // interior: one 2-sample load per lane, 1 or 2 rows per pass, no clamping
         const int lpr = np <= GS / 2 ? GS / 2 : GS;         // lanes per window row
         const int pi = gl & (lpr - 1), rsub = gl >= lpr ? 1 : 0, rstep = GS / lpr;
@@ -399,22 +440,21 @@ __device__ __forceinline__ void mc_list(const PlaneDesc &rp, int sx, int sy, int
             const uint8_t *src = rp.base + (size_t)(oy + rsub) * rp.pitch + (size_t)(ax + 2 * pi) * sizeof(PIX);
             uint32_t *dst = reinterpret_cast<uint32_t *>(win) + rsub * np + pi;
             for (int r = rsub; r < R; r += rstep) {
-                uint32_t v;
-                if (sizeof(PIX) == 2) v = __ldg(reinterpret_cast<const uint32_t *>(src));
-                else { const uint32_t t = __ldg(reinterpret_cast<const uint16_t *>(src)); v = (t & 0xff) | ((t & 0xff00) << 8); }
-                *dst = v;
+                *dst = mc_ld_pair<PIX>(src);
                 src += (size_t)rstep * rp.pitch; dst += rstep * np;
             }
         }
-    } else {
-        // window hangs over the picture border: clamp sample by sample (== emulated_edge_mc)
-        for (int i = gl; i < R * Ws; i += GS) {
-            const int r = i / Ws, cc = i - r * Ws;
-            const int x = clip3i(ax + cc, 0, rp.w - 1), y = clip3i(oy + r, 0, rp.h - 1);
-            win[i] = __ldg(px_ptr<PIX>(rp, x, y));
-        }
-    }
+    } else mc_win1_clamped<PIX, GS>(m, rp, gl, win);
     __syncwarp(gmask);
+    mc_list_fir<TAPS, GS>(m, mx, my, g, bd, gl, gmask, win, tmp, val);
+}
+
+// the FIRs of one list on a window that is complete in shared memory
+template <int TAPS, int GS>
+__device__ __forceinline__ void mc_list_fir(const McWin1 &m, int mx, int my, const McGeom &g, int bd, int gl, unsigned gmask,
+                                            const uint16_t *win, int16_t *tmp, int (&val)[8])
+{
+    const int R = m.R, Ws = m.Ws, skew = m.skew;
     const int8_t *fxp = TAPS == 8 ? c_qpel[mx] : c_epel[mx];
     const int8_t *fyp = TAPS == 8 ? c_qpel[my] : c_epel[my];
     if (mx) {
@@ -479,31 +519,28 @@ __device__ __forceinline__ void mc_list(const PlaneDesc &rp, int sx, int sy, int
 }
 
 // ---- K1, default version: scalar FIRs (one IMAD per tap) ----
-template <typename PIX, int GS>
-__global__ void __launch_bounds__(256) k_mc_v1(const B200McRec *__restrict__ recs, int count, FrameDesc cur, const FrameDesc *__restrict__ dpb, RefTable rt, int bd,
-                                            const uint32_t *__restrict__ gate, DpbLayout lay)
+// B200McRec fields straight from the two 16-byte halves of the record
+struct McRec1 {
+    int dx, dy, w, h, plane, flags, sx0, sy0, sx1, sy1, ref0, ref1, frac0, frac1, w0, w1, o0, o1, denom;
+};
+template <int GS>
+__device__ __forceinline__ McRec1 mc_rec1(const int4 ra, const int4 rb)
 {
-    if (__ldg(gate + 1)) return;         // the picture's work list failed validation (k_validate)
-    constexpr int NG = 256 / GS;                           // groups per CTA
-    __shared__ __align__(16) uint16_t win_s[NG][McSmem<GS>::WIN];
-    __shared__ __align__(16) int16_t tmp_s[NG][McSmem<GS>::TMP];
-    const int grp = threadIdx.x / GS, gl = threadIdx.x & (GS - 1);
-    const unsigned gmask = GS == 32 ? 0xffffffffu : (((1u << GS) - 1u) << ((threadIdx.x & 31) & ~(GS - 1)));
-    const int ri = blockIdx.x * NG + grp;
-    if (ri >= count) return;                               // whole groups leave: the barriers are group-local
-    const int4 *rp4 = reinterpret_cast<const int4 *>(recs + ri);
-    const int4 ra = __ldg(rp4), rb = __ldg(rp4 + 1);
-    // B200McRec fields straight from registers
+    McRec1 t;
     const int mxy = ra.x, whpf = ra.y;
-    const int dx = mxy & 0xffff, dy = (unsigned)mxy >> 16;
-    int w = whpf & 0xff, h = (whpf >> 8) & 0xff;
-    if (GS == 8) { w = min(w, 8); h = min(h, 8); }          // the list order guarantees it; never trust it with shared memory
-    const int plane = (whpf >> 16) & 0xff, flags = (unsigned)whpf >> 24;
-    const int sx0 = (int16_t)(ra.z & 0xffff), sy0 = (int16_t)((unsigned)ra.z >> 16), sx1 = (int16_t)(ra.w & 0xffff), sy1 = (int16_t)((unsigned)ra.w >> 16);
-    const int ref0 = rb.x & 0xff, ref1 = (rb.x >> 8) & 0xff, frac0 = (rb.x >> 16) & 0xff, frac1 = (unsigned)rb.x >> 24;
-    const int w0 = (int16_t)(rb.y & 0xffff), w1 = (int16_t)((unsigned)rb.y >> 16), o0 = (int16_t)(rb.z & 0xffff), o1 = (int16_t)((unsigned)rb.z >> 16);
-    const int denom = rb.w & 0xff;
-    const bool chroma = flags & B200_MCF_CHROMA, bi = flags & B200_MCF_BI, weighted = flags & B200_MCF_WEIGHTED;
+    t.dx = mxy & 0xffff; t.dy = (unsigned)mxy >> 16;
+    t.w = whpf & 0xff; t.h = (whpf >> 8) & 0xff;
+    if (GS == 8) { t.w = min(t.w, 8); t.h = min(t.h, 8); }          // the list order guarantees it; never trust it with shared memory
+    t.plane = (whpf >> 16) & 0xff; t.flags = (unsigned)whpf >> 24;
+    t.sx0 = (int16_t)(ra.z & 0xffff); t.sy0 = (int16_t)((unsigned)ra.z >> 16); t.sx1 = (int16_t)(ra.w & 0xffff); t.sy1 = (int16_t)((unsigned)ra.w >> 16);
+    t.ref0 = rb.x & 0xff; t.ref1 = (rb.x >> 8) & 0xff; t.frac0 = (rb.x >> 16) & 0xff; t.frac1 = (unsigned)rb.x >> 24;
+    t.w0 = (int16_t)(rb.y & 0xffff); t.w1 = (int16_t)((unsigned)rb.y >> 16); t.o0 = (int16_t)(rb.z & 0xffff); t.o1 = (int16_t)((unsigned)rb.z >> 16);
+    t.denom = rb.w & 0xff;
+    return t;
+}
+template <int GS>
+__device__ __forceinline__ McGeom mc_geom1(int w, int h)
+{
     McGeom g;
     g.w = w; g.h = h;
     g.wsh = w <= 2 ? 1 : w <= 4 ? 2 : w <= 8 ? 3 : w <= 16 ? 4 : 5;
@@ -512,23 +549,19 @@ __global__ void __launch_bounds__(256) k_mc_v1(const B200McRec *__restrict__ rec
     g.wpad = (w + 3) & ~3;
     g.q = g.wpad >> 2;
     g.lsh = g.q <= 1 ? 0 : g.q <= 2 ? 1 : g.q <= 4 ? 2 : 3;
-    int v0[8], v1[8];
-    {
-        const PlaneDesc rp = ref_plane(lay, dpb, ref_slot_of(rt, ref0), plane);
-        if (chroma) mc_list<PIX, 4, GS>(rp, sx0, sy0, frac0 & 15, frac0 >> 4, g, bd, gl, gmask, win_s[grp], tmp_s[grp], v0);
-        else        mc_list<PIX, 8, GS>(rp, sx0, sy0, frac0 & 15, frac0 >> 4, g, bd, gl, gmask, win_s[grp], tmp_s[grp], v0);
-    }
-    if (bi) {
-        const PlaneDesc rp = ref_plane(lay, dpb, ref_slot_of(rt, ref1), plane);
-        if (chroma) mc_list<PIX, 4, GS>(rp, sx1, sy1, frac1 & 15, frac1 >> 4, g, bd, gl, gmask, win_s[grp], tmp_s[grp], v1);
-        else        mc_list<PIX, 8, GS>(rp, sx1, sy1, frac1 & 15, frac1 >> 4, g, bd, gl, gmask, win_s[grp], tmp_s[grp], v1);
-    }
-    const PlaneDesc dp = plane_of(cur, plane);
+    return g;
+}
+// combine the lists' 14-bit intermediates (hevcdsp_template.c put_hevc_*_uni / _bi / _w) and store the tile
+template <typename PIX>
+__device__ __forceinline__ void mc_store1(const McRec1 &t, const McGeom &g, const PlaneDesc &dp, int bd, int gl, const int (&v0)[8], const int (&v1)[8])
+{
+    const bool bi = t.flags & B200_MCF_BI, weighted = t.flags & B200_MCF_WEIGHTED;
+    const int w = t.w, h = t.h, w0 = t.w0, w1 = t.w1, o0 = t.o0, o1 = t.o1, denom = t.denom;
     const int shift = 14 - bd, maxv = (1 << bd) - 1;
-    const bool fullpel0 = frac0 == 0;
+    const bool fullpel0 = t.frac0 == 0;
     const int xl = gl & ((1 << g.wsh) - 1), y0 = (gl >> g.wsh) * g.rows_per;
     if (xl >= w) return;
-    PIX *d = px_ptr<PIX>(dp, dx + xl, dy + y0);
+    PIX *d = px_ptr<PIX>(dp, t.dx + xl, t.dy + y0);
 #pragma unroll
     for (int j = 0; j < 8; j++) {
         if (j >= g.rows_per || y0 + j >= h) break;
@@ -550,6 +583,112 @@ __global__ void __launch_bounds__(256) k_mc_v1(const B200McRec *__restrict__ rec
         *d = (PIX)out;
         d = reinterpret_cast<PIX *>(reinterpret_cast<uint8_t *>(d) + dp.pitch);
     }
+}
+
+template <typename PIX, int GS>
+__global__ void __launch_bounds__(256) k_mc_v1(const B200McRec *__restrict__ recs, int count, FrameDesc cur, const FrameDesc *__restrict__ dpb, RefTable rt, int bd,
+                                            const uint32_t *__restrict__ gate, DpbLayout lay)
+{
+    if (__ldg(gate + 1)) return;         // the picture's work list failed validation (k_validate)
+    constexpr int NG = 256 / GS;                           // groups per CTA
+    __shared__ __align__(16) uint16_t win_s[NG][McSmem<GS>::WIN];
+    __shared__ __align__(16) int16_t tmp_s[NG][McSmem<GS>::TMP];
+    const int grp = threadIdx.x / GS, gl = threadIdx.x & (GS - 1);
+    const unsigned gmask = GS == 32 ? 0xffffffffu : (((1u << GS) - 1u) << ((threadIdx.x & 31) & ~(GS - 1)));
+    const int ri = blockIdx.x * NG + grp;
+    if (ri >= count) return;                               // whole groups leave: the barriers are group-local
+    const int4 *rp4 = reinterpret_cast<const int4 *>(recs + ri);
+    const McRec1 t = mc_rec1<GS>(__ldg(rp4), __ldg(rp4 + 1));
+    const bool chroma = t.flags & B200_MCF_CHROMA, bi = t.flags & B200_MCF_BI;
+    const McGeom g = mc_geom1<GS>(t.w, t.h);
+    int v0[8], v1[8];
+    {
+        const PlaneDesc rp = ref_plane(lay, dpb, ref_slot_of(rt, t.ref0), t.plane);
+        if (chroma) mc_list<PIX, 4, GS>(rp, t.sx0, t.sy0, t.frac0 & 15, t.frac0 >> 4, g, bd, gl, gmask, win_s[grp], tmp_s[grp], v0);
+        else        mc_list<PIX, 8, GS>(rp, t.sx0, t.sy0, t.frac0 & 15, t.frac0 >> 4, g, bd, gl, gmask, win_s[grp], tmp_s[grp], v0);
+    }
+    if (bi) {
+        const PlaneDesc rp = ref_plane(lay, dpb, ref_slot_of(rt, t.ref1), t.plane);
+        if (chroma) mc_list<PIX, 4, GS>(rp, t.sx1, t.sy1, t.frac1 & 15, t.frac1 >> 4, g, bd, gl, gmask, win_s[grp], tmp_s[grp], v1);
+        else        mc_list<PIX, 8, GS>(rp, t.sx1, t.sy1, t.frac1 & 15, t.frac1 >> 4, g, bd, gl, gmask, win_s[grp], tmp_s[grp], v1);
+    }
+    mc_store1<PIX>(t, g, plane_of(cur, t.plane), bd, gl, v0, v1);
+}
+
+// ---- K1, version 3 (B200_MC=3): the arithmetic of the default version, but the window loads of BOTH lists are issued before
+// anything waits for them.  The default version fetches a window in passes of four 4-byte loads per lane (the compiler's
+// unrolling of the row loop) and the second list only after the first has been filtered: six dependent round trips to L2 /
+// HBM per bi-predicted tile in a kernel that ncu shows waiting on exactly those loads (long scoreboard, DRAM at 10 %).
+// Here a lane issues up to 2 x 15 loads back to back into registers, then commits them to the two shared-memory windows.
+#define MC3_PASSES 15          // 32x8 tiles: 15 rows, one per pass; 16x16 tiles: 23 rows, two per pass; 8-lane groups: <= 15 rows
+template <typename PIX, int GS>
+__device__ __forceinline__ void mc3_issue(const McWin1 &m, const PlaneDesc &rp, int gl, uint32_t (&v)[MC3_PASSES])
+{
+    const int np = m.np;
+    const int lpr = np <= GS / 2 ? GS / 2 : GS;         // lanes per window row
+    const int pi = min(gl & (lpr - 1), np - 1), rsub = gl >= lpr ? 1 : 0, rstep = GS / lpr;
+    // unconditional loads: lanes and passes beyond the window re-read its last pair / last row (never committed), so the
+    // loop is straight-line code and every load is in flight before the first one is needed
+    const uint8_t *src = rp.base + (size_t)m.oy * rp.pitch + (size_t)(m.ax + 2 * pi) * sizeof(PIX);
+#pragma unroll
+    for (int i = 0; i < MC3_PASSES; i++) v[i] = mc_ld_pair<PIX>(src + (size_t)min(rsub + i * rstep, m.R - 1) * rp.pitch);
+}
+template <typename PIX, int GS>
+__device__ __forceinline__ void mc3_commit(const McWin1 &m, const PlaneDesc &rp, int gl, const uint32_t (&v)[MC3_PASSES], uint16_t *win)
+{
+    const int np = m.np;
+    const int lpr = np <= GS / 2 ? GS / 2 : GS;
+    const int pi = gl & (lpr - 1), rsub = gl >= lpr ? 1 : 0, rstep = GS / lpr;
+    if (pi >= np) return;
+    uint32_t *dst = reinterpret_cast<uint32_t *>(win) + rsub * np + pi;
+#pragma unroll
+    for (int i = 0; i < MC3_PASSES; i++)
+        if (rsub + i * rstep < m.R) dst[i * rstep * np] = v[i];
+    // taller windows than any valid tile produces (the validation kernel bounds w and h): finish row by row
+    for (int r = rsub + MC3_PASSES * rstep; r < m.R; r += rstep)
+        dst[(r - rsub) * np] = mc_ld_pair<PIX>(rp.base + (size_t)(m.oy + r) * rp.pitch + (size_t)(m.ax + 2 * pi) * sizeof(PIX));
+}
+
+template <typename PIX, int GS>
+__global__ void __launch_bounds__(256, 3) k_mc_v3(const B200McRec *__restrict__ recs, int count, FrameDesc cur, const FrameDesc *__restrict__ dpb, RefTable rt, int bd,
+                                            const uint32_t *__restrict__ gate, DpbLayout lay)
+{
+    if (__ldg(gate + 1)) return;         // the picture's work list failed validation (k_validate)
+    constexpr int NG = 256 / GS;                           // groups per CTA
+    __shared__ __align__(16) uint16_t win_s[NG][2][McSmem<GS>::WIN];
+    __shared__ __align__(16) int16_t tmp_s[NG][McSmem<GS>::TMP];
+    const int grp = threadIdx.x / GS, gl = threadIdx.x & (GS - 1);
+    const unsigned gmask = GS == 32 ? 0xffffffffu : (((1u << GS) - 1u) << ((threadIdx.x & 31) & ~(GS - 1)));
+    const int ri = blockIdx.x * NG + grp;
+    if (ri >= count) return;                               // whole groups leave: the barriers are group-local
+    const int4 *rp4 = reinterpret_cast<const int4 *>(recs + ri);
+    const McRec1 t = mc_rec1<GS>(__ldg(rp4), __ldg(rp4 + 1));
+    const bool chroma = t.flags & B200_MCF_CHROMA, bi = t.flags & B200_MCF_BI;
+    const McGeom g = mc_geom1<GS>(t.w, t.h);
+    const int mx0 = t.frac0 & 15, my0 = t.frac0 >> 4, mx1 = t.frac1 & 15, my1 = t.frac1 >> 4;
+    const PlaneDesc rp0 = ref_plane(lay, dpb, ref_slot_of(rt, t.ref0), t.plane);
+    const PlaneDesc rp1 = bi ? ref_plane(lay, dpb, ref_slot_of(rt, t.ref1), t.plane) : rp0;
+    const McWin1 m0 = chroma ? mc_win1<4>(t.sx0, t.sy0, mx0, my0, g) : mc_win1<8>(t.sx0, t.sy0, mx0, my0, g);
+    const McWin1 m1 = chroma ? mc_win1<4>(t.sx1, t.sy1, mx1, my1, g) : mc_win1<8>(t.sx1, t.sy1, mx1, my1, g);
+    const bool in0 = mc_win1_interior(m0, rp0), in1 = bi && mc_win1_interior(m1, rp1);      // uniform over the group
+    uint16_t *win0 = win_s[grp][0], *win1 = win_s[grp][1];
+    uint32_t r0[MC3_PASSES], r1[MC3_PASSES];
+    if (in0) mc3_issue<PIX, GS>(m0, rp0, gl, r0);
+    if (in1) mc3_issue<PIX, GS>(m1, rp1, gl, r1);
+    if (!in0) mc_win1_clamped<PIX, GS>(m0, rp0, gl, win0);
+    if (bi && !in1) mc_win1_clamped<PIX, GS>(m1, rp1, gl, win1);
+    if (in0) mc3_commit<PIX, GS>(m0, rp0, gl, r0, win0);
+    if (in1) mc3_commit<PIX, GS>(m1, rp1, gl, r1, win1);
+    __syncwarp(gmask);
+    int v0[8], v1[8];
+    if (chroma) mc_list_fir<4, GS>(m0, mx0, my0, g, bd, gl, gmask, win0, tmp_s[grp], v0);
+    else        mc_list_fir<8, GS>(m0, mx0, my0, g, bd, gl, gmask, win0, tmp_s[grp], v0);
+    if (bi) {
+        __syncwarp(gmask);                                 // list 0's stage B has read tmp
+        if (chroma) mc_list_fir<4, GS>(m1, mx1, my1, g, bd, gl, gmask, win1, tmp_s[grp], v1);
+        else        mc_list_fir<8, GS>(m1, mx1, my1, g, bd, gl, gmask, win1, tmp_s[grp], v1);
+    }
+    mc_store1<PIX>(t, g, plane_of(cur, t.plane), bd, gl, v0, v1);
 }
 
 
@@ -1141,6 +1280,8 @@ int launch_mc(cudaStream_t st, const B200McRec *recs, int count, int n_big, cons
     // (full parity suite) but SLOWER: 145 vs 109 us per 4K B picture, 38.9 M + 29.7 M vs 35.4 M + 22.8 M warp instructions --
     // the pair shuffles and the 16-bit interleaved stores cost more than the halved multiplies save, and ncu shows the
     // stage waiting on its window loads (long scoreboard), not on the ALU.  Kept selectable for the next round's work.
+    // 3 = version 1's arithmetic with the window loads of both lists issued back to back (k_mc_v3): written after the last GPU
+    // visit of round 1, bit-exact in the warp emulation (tests/test_warp_emul_cpu.py), 80 registers / 3 CTAs per SM; not yet timed.
     static const int version = getenv("B200_MC") ? atoi(getenv("B200_MC")) : 1;
     int n = 0;
     const int n_small = count - n_big;
@@ -1149,6 +1290,9 @@ int launch_mc(cudaStream_t st, const B200McRec *recs, int count, int n_big, cons
         if (version == 1) {
             if (bd > 8) B200_LAUNCH(grid, 256, 0, st, k_mc_v1<uint16_t, 32>)(recs, n_big, cur, dpb_dev, rt, bd, gate, lay);
             else        B200_LAUNCH(grid, 256, 0, st, k_mc_v1<uint8_t, 32>)(recs, n_big, cur, dpb_dev, rt, bd, gate, lay);
+        } else if (version == 3) {
+            if (bd > 8) B200_LAUNCH(grid, 256, 0, st, k_mc_v3<uint16_t, 32>)(recs, n_big, cur, dpb_dev, rt, bd, gate, lay);
+            else        B200_LAUNCH(grid, 256, 0, st, k_mc_v3<uint8_t, 32>)(recs, n_big, cur, dpb_dev, rt, bd, gate, lay);
         } else {
             if (bd > 8) B200_LAUNCH(grid, 256, 0, st, k_mc<uint16_t, 32>)(recs, n_big, cur, dpb_dev, rt, bd, gate, lay);
             else        B200_LAUNCH(grid, 256, 0, st, k_mc<uint8_t, 32>)(recs, n_big, cur, dpb_dev, rt, bd, gate, lay);
@@ -1160,6 +1304,9 @@ int launch_mc(cudaStream_t st, const B200McRec *recs, int count, int n_big, cons
         if (version == 1) {
             if (bd > 8) B200_LAUNCH(grid, 256, 0, st, k_mc_v1<uint16_t, 8>)(recs + n_big, n_small, cur, dpb_dev, rt, bd, gate, lay);
             else        B200_LAUNCH(grid, 256, 0, st, k_mc_v1<uint8_t, 8>)(recs + n_big, n_small, cur, dpb_dev, rt, bd, gate, lay);
+        } else if (version == 3) {
+            if (bd > 8) B200_LAUNCH(grid, 256, 0, st, k_mc_v3<uint16_t, 8>)(recs + n_big, n_small, cur, dpb_dev, rt, bd, gate, lay);
+            else        B200_LAUNCH(grid, 256, 0, st, k_mc_v3<uint8_t, 8>)(recs + n_big, n_small, cur, dpb_dev, rt, bd, gate, lay);
         } else {
             if (bd > 8) B200_LAUNCH(grid, 256, 0, st, k_mc<uint16_t, 8>)(recs + n_big, n_small, cur, dpb_dev, rt, bd, gate, lay);
             else        B200_LAUNCH(grid, 256, 0, st, k_mc<uint8_t, 8>)(recs + n_big, n_small, cur, dpb_dev, rt, bd, gate, lay);

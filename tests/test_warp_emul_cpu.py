@@ -82,7 +82,7 @@ def test_golden_fixtures_on_the_emulated_kernels(emulated):
 
 
 # the experiments behind environment switches (read once per process, hence a child process each): bit-exact or not worth a GPU visit
-VARIANTS = [dict(B200_MC="2"), dict(B200_MC_DESC="1"), dict(B200_EDGES_SPARSE="1"), dict(B200_VALIDATE="2"), dict(B200_LANES="1")]
+VARIANTS = [dict(B200_MC="2"), dict(B200_MC="3"), dict(B200_MC_DESC="1"), dict(B200_EDGES_SPARSE="1"), dict(B200_VALIDATE="2"), dict(B200_LANES="1")]
 
 
 @needs_emul
