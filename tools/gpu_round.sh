@@ -29,3 +29,11 @@ if [ -n "$WITH_TRACE" ]; then
   B200_TRACE=gpurun_out/${tag}_trace.csv timeout 300 python bench.py --steps 24 --warmup 4 --no-cpu-baseline > gpurun_out/${tag}_trace_bench.json 2>> gpurun_out/${tag}_bench.err
   python tools/timeline.py gpurun_out/${tag}_trace.csv --from 64 --to 224 | tee gpurun_out/${tag}_timeline.txt
 fi
+if [ -n "$WITH_VARIANTS" ]; then   # the switches prepared without a GPU: parity subset + bench line each
+  for v in "B200_MC=3" "B200_MC=3 B200_MC_DESC=1" "B200_MC_DESC=1" "B200_EDGES_SPARSE=1" "B200_MC=3 B200_MC_DESC=1 B200_EDGES_SPARSE=1"; do
+    name=$(echo "$v" | tr ' =' '__')
+    ( env $v timeout 600 python -m pytest tests/test_parity_gpu.py tests/test_golden.py -m gpu -x -q 2>&1 | tail -2 ) > gpurun_out/${tag}_var_${name}_pytest.log
+    env $v timeout 300 python bench.py --no-cpu-baseline > gpurun_out/${tag}_var_${name}_bench.json 2>> gpurun_out/${tag}_bench.err
+    echo "$v: $(cat gpurun_out/${tag}_var_${name}_pytest.log | tail -1) $(cat gpurun_out/${tag}_var_${name}_bench.json | cut -c1-200)"
+  done
+fi
