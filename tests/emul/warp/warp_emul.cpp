@@ -44,6 +44,8 @@ const std::function<void()> *g_body;
 const char *g_name;
 int g_barrier_arrived, g_alive;
 unsigned long g_switches;
+std::vector<unsigned> g_order;
+int g_order_kind = -1;
 
 void to_scheduler() { swapcontext(&g_cur->ctx, &g_sched); }
 
@@ -152,6 +154,22 @@ void emu_run_grid(dim3 grid, dim3 block, const std::function<void()> &body, cons
             if (g_fib[i].stack == MAP_FAILED) { perror("emu: fiber stack"); abort(); }
         }
     }
+    // The order in which runnable fibers get the CPU between two collectives.  Correct kernels do not care; one that reads what
+    // a neighbouring lane wrote without a barrier in between passes in one order and fails in another.  B200_EMUL_ORDER =
+    // "reverse" or "random[:seed]" (default: ascending thread index).
+    if (g_order.size() != n || g_order_kind < 0) {
+        const char *e = getenv("B200_EMUL_ORDER");
+        g_order_kind = !e ? 0 : !strncmp(e, "reverse", 7) ? 1 : !strncmp(e, "random", 6) ? 2 : 0;
+        g_order.resize(n);
+        for (unsigned t = 0; t < n; t++) g_order[t] = g_order_kind == 1 ? n - 1 - t : t;
+        if (g_order_kind == 2) {
+            uint64_t x = 0x9e3779b97f4a7c15ull ^ (e[6] == ':' ? strtoull(e + 7, nullptr, 0) : 1);
+            for (unsigned t = n - 1; t > 0; t--) {
+                x ^= x << 13; x ^= x >> 7; x ^= x << 17;
+                std::swap(g_order[t], g_order[x % (t + 1)]);
+            }
+        }
+    }
     g_body = &body;
     g_name = name;
     emu_block_dim = block;
@@ -178,8 +196,8 @@ void emu_run_grid(dim3 grid, dim3 block, const std::function<void()> &body, cons
                 }
                 for (int left = (int)n; left;) {
                     bool ran = false;
-                    for (unsigned t = 0; t < n; t++) {
-                        Fiber &f = g_fib[t];
+                    for (unsigned k = 0; k < n; k++) {
+                        Fiber &f = g_fib[g_order[k]];
                         if (f.done || f.waiting) continue;
                         g_cur = &f;
                         emu_self = &f;

@@ -81,8 +81,11 @@ def test_golden_fixtures_on_the_emulated_kernels(emulated):
         test_golden.test_cuda_reproduces_reference_golden(path)
 
 
-# the experiments behind environment switches (read once per process, hence a child process each): bit-exact or not worth a GPU visit
-VARIANTS = [dict(B200_MC="2"), dict(B200_MC="3"), dict(B200_MC_DESC="1"), dict(B200_EDGES_SPARSE="1"), dict(B200_VALIDATE="2"), dict(B200_LANES="1")]
+# the experiments behind environment switches (read once per process, hence a child process each): bit-exact or not worth a GPU
+# visit.  B200_EMUL_ORDER changes the order in which the emulator runs the lanes between two collectives (reverse / shuffled):
+# a kernel that needs a barrier it does not have passes in one order and fails in another.
+VARIANTS = [dict(B200_EMUL_ORDER="reverse"), dict(B200_EMUL_ORDER="random:7"), dict(B200_MC="2", B200_EMUL_ORDER="reverse"), dict(B200_MC="3", B200_EMUL_ORDER="random:3"),
+            dict(B200_MC="2"), dict(B200_MC="3"), dict(B200_MC_DESC="1"), dict(B200_EDGES_SPARSE="1"), dict(B200_VALIDATE="2"), dict(B200_LANES="1")]
 
 
 @needs_emul
@@ -96,6 +99,13 @@ def test_switch_variants_on_the_emulated_kernels(env):
             "T.run_sequence(192, 128, 1, 8, seeds=[16, 17, 18], weighted=True)\n" % (ROOT, HERE, EMUL))
     r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=900, env=dict(os.environ, **env))
     assert r.returncode == 0, r.stderr[-3000:]
+
+
+@needs_emul
+def test_smoke_on_the_emulated_kernels(emulated, capsys):
+    import __graft_entry__
+    __graft_entry__.smoke()
+    assert "smoke ok" in capsys.readouterr().out
 
 
 def test_address_sanitizer_sees_no_out_of_bounds_access_in_the_kernels():
