@@ -220,6 +220,30 @@ def test_grey_reference_fill(cfi, bd):
         eng.close()
 
 
+@pytest.mark.late
+def test_empty_work_list_and_smallest_pictures():
+    """a work list without a single record leaves the picture as it was (and says so through the same path as any other); the
+    smallest geometry the context accepts (16x16) and sizes that are no multiple of any CTB size; smaller ones are refused"""
+    w, h, cfi, bd = 64, 48, 1, 10
+    eng = FrameEngine(w, h, cfi, bd, n_slots=2)
+    try:
+        before = smooth_frame(w, h, cfi, bd, 9)
+        eng.upload_slot(0, before)
+        blob = W.build_blob(w, h, cfi, bd, 6, 0)
+        got = eng.decode(blob)
+        want = oracle_lib.execute(blob, [[p.copy() for p in before], [np.zeros_like(p) for p in before]])
+        for p in range(3):
+            assert np.array_equal(got[p], want[p]) and np.array_equal(got[p], before[p])
+    finally:
+        eng.close()
+    for (w, h, cfi, bd) in ((16, 16, 1, 8), (16, 16, 3, 10), (24, 40, 2, 10), (72, 24, 1, 12)):
+        run_sequence(w, h, cfi, bd, seeds=[5, 6, 7], exotic=0.1)
+    with pytest.raises(B200Error):
+        FrameEngine(8, 8, 1, 8)
+    with pytest.raises(B200Error):
+        FrameEngine(20, 16, 1, 8)                         # not a multiple of the minimum coding block
+
+
 def test_cyclic_intra_dependencies_time_out_instead_of_hanging():
     """a work list whose intra TUs wait on each other (cannot come from a real decode order) must not hang the device"""
     w, h = 128, 64

@@ -50,7 +50,7 @@ def test_emulated_library_has_the_product_abi():
 
 PARITY = ["test_weighted_prediction_and_sao_restore", "test_constrained_intra_pred", "test_sao_restore_of_bypass_pus", "test_intra_only_small_blocks",
           "test_stages_individually", "test_far_out_of_picture_motion", "test_pcm_and_exotic_transform_paths", "test_malformed_blobs_are_rejected_not_executed",
-          "test_malformed_inter_records_are_rejected_on_the_device"]
+          "test_malformed_inter_records_are_rejected_on_the_device", "test_empty_work_list_and_smallest_pictures"]
 
 
 @needs_emul
