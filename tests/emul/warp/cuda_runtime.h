@@ -84,18 +84,25 @@ template <typename T> static inline T __shfl_down_sync(unsigned mask, T v, unsig
 
 // ---- memory, atomics, time -------------------------------------------------------------------------------------------
 template <typename T> static inline T __ldg(const T *p) { return *p; }
-static inline unsigned atomicAdd(unsigned *p, unsigned v) { const unsigned o = *p; *p = o + v; return o; }
-static inline int atomicAdd(int *p, int v) { const int o = *p; *p = o + v; return o; }
-static inline unsigned atomicOr(unsigned *p, unsigned v) { const unsigned o = *p; *p = o | v; return o; }
-static inline unsigned atomicMax(unsigned *p, unsigned v) { const unsigned o = *p; if (v > o) *p = v; return o; }
+// atomics and the relaxed GPU-scope accessors of kernels.cu (inline PTX there) are compiler atomics, so that a thread-sanitizer
+// build of the emulation knows them from plain accesses; a polling load is also where a waiting warp yields
+static inline unsigned atomicAdd(unsigned *p, unsigned v) { return __atomic_fetch_add(p, v, __ATOMIC_RELAXED); }
+static inline int atomicAdd(int *p, int v) { return __atomic_fetch_add(p, v, __ATOMIC_RELAXED); }
+static inline unsigned atomicOr(unsigned *p, unsigned v) { return __atomic_fetch_or(p, v, __ATOMIC_RELAXED); }
+static inline unsigned atomicMax(unsigned *p, unsigned v) { unsigned o = __atomic_load_n(p, __ATOMIC_RELAXED); while (v > o && !__atomic_compare_exchange_n(p, &o, v, false, __ATOMIC_RELAXED, __ATOMIC_RELAXED)) {} return o; }
 static inline void __nanosleep(unsigned) { emu_yield(); }
-static inline void __threadfence() {}
-// the four relaxed GPU-scope accessors of kernels.cu (inline PTX there): plain accesses; a load is where a polling warp waits
+static inline void __threadfence() { __atomic_thread_fence(__ATOMIC_SEQ_CST); }
 static inline unsigned long long gtime() { return 0; }
-static inline uint32_t ld_relaxed(const uint32_t *p) { emu_yield(); return *(const volatile uint32_t *)p; }
-static inline void st_relaxed(uint32_t *p, uint32_t v) { *(volatile uint32_t *)p = v; }
-static inline uint2 ld_edge(const uint2 *p) { emu_yield(); uint2 v; v.x = ((const volatile unsigned *)p)[0]; v.y = ((const volatile unsigned *)p)[1]; return v; }
-static inline void st_edge(uint2 *p, uint2 v) { ((volatile unsigned *)p)[0] = v.x; ((volatile unsigned *)p)[1] = v.y; }
+static inline uint32_t ld_relaxed(const uint32_t *p) { emu_yield(); return __atomic_load_n(p, __ATOMIC_RELAXED); }
+static inline void st_relaxed(uint32_t *p, uint32_t v) { __atomic_store_n(p, v, __ATOMIC_RELAXED); }
+static inline uint2 ld_edge(const uint2 *p)
+{
+    emu_yield();
+    const uint64_t w = __atomic_load_n(reinterpret_cast<const uint64_t *>(p), __ATOMIC_RELAXED);      // one 8-byte access, as on the device
+    uint2 v; v.x = (unsigned)w; v.y = (unsigned)(w >> 32);
+    return v;
+}
+static inline void st_edge(uint2 *p, uint2 v) { __atomic_store_n(reinterpret_cast<uint64_t *>(p), (uint64_t)v.x | ((uint64_t)v.y << 32), __ATOMIC_RELAXED); }
 
 // integer min / max with the device's overload set (the kernels mix int and unsigned like CUDA allows)
 static inline int min(int a, int b) { return a < b ? a : b; }

@@ -8,6 +8,21 @@
 #include <mutex>
 #include <vector>
 
+// Thread-sanitizer build (kernels.cu / engine.cu with -fsanitize=thread, this file with -DEMU_TSAN but NOT instrumented: the
+// scheduler's own bookkeeping is shared between fibers by design): every fiber is a TSan fiber, switches carry NO synchronisation, and the only
+// happens-before edges are the ones the CUDA model gives: a completed warp collective orders its participants, __syncthreads
+// the block, block / kernel boundaries everything (blocks run one after another here, so races BETWEEN blocks are not looked
+// for).  Two lanes touching the same shared or global word without a collective in between are reported as a data race --
+// what compute-sanitizer racecheck looks for, on the CPU.
+#if defined(EMU_TSAN)
+#include <sanitizer/tsan_interface.h>
+#define TSAN_RELEASE(p) __tsan_release(p)
+#define TSAN_ACQUIRE(p) __tsan_acquire(p)
+#else
+#define TSAN_RELEASE(p) ((void)0)
+#define TSAN_ACQUIRE(p) ((void)0)
+#endif
+
 EmuThread *emu_self;
 uint3 emu_block_idx;
 dim3 emu_block_dim, emu_grid_dim;
@@ -28,10 +43,14 @@ struct Fiber : EmuThread {
     bool done = false, waiting = false;      // waiting: parked in a collective or the block barrier until released
     uint32_t result = 0;
     int warp = 0, lane = 0;
+    void *tsan = nullptr;                    // TSan fiber context
+    void *acquire = nullptr;                 // sync object to acquire when the fiber resumes after a collective / barrier
 };
 struct Warp {
     unsigned exited = 0;
-    std::vector<Collective> open;            // collectives in progress, keyed by mask (disjoint lane groups sync independently)
+    char sync[32];                           // TSan sync objects of the collectives, one per lowest lane of the mask
+    Collective open[8];                      // collectives in progress, keyed by mask (disjoint lane groups sync independently);
+                                             // mask == 0 = free slot (fixed slots, no copies: a sanitizer build intercepts memmove)
 };
 
 constexpr size_t STACK = 256 << 10;
@@ -43,16 +62,28 @@ Fiber *g_cur;
 const std::function<void()> *g_body;
 const char *g_name;
 int g_barrier_arrived, g_alive;
+char g_sync_block, g_sync_grid;              // TSan sync objects: __syncthreads, block / kernel boundaries
+void *g_tsan_sched;
 unsigned long g_switches;
 std::vector<unsigned> g_order;
 int g_order_kind = -1;
 
-void to_scheduler() { swapcontext(&g_cur->ctx, &g_sched); }
+void to_scheduler()
+{
+#if defined(EMU_TSAN)
+    __tsan_switch_to_fiber(g_tsan_sched, __tsan_switch_to_fiber_no_sync);
+#endif
+    Fiber *f = g_cur;
+    swapcontext(&f->ctx, &g_sched);
+    if (f->acquire) { TSAN_ACQUIRE(f->acquire); f->acquire = nullptr; }
+}
 
 void fiber_main()
 {
+    TSAN_ACQUIRE(&g_sync_grid);              // everything before this block (host copies, earlier kernels and blocks)
     (*g_body)();
     Fiber *f = g_cur;
+    TSAN_RELEASE(&g_sync_grid);
     f->done = true;
     g_alive--;
     Warp &w = g_warp[f->warp];
@@ -89,14 +120,14 @@ bool try_complete(int warp, size_t k)
 {
     Warp &w = g_warp[warp];
     Collective &c = w.open[k];
-    if (c.arrived != (c.mask & ~w.exited)) return false;
+    if (!c.mask || c.arrived != (c.mask & ~w.exited)) return false;
     for (int l = 0; l < 32; l++)
         if (c.arrived >> l & 1) {
             Fiber &f = g_fib[warp * 32 + l];
             f.result = resolve(c, l);
             f.waiting = false;
         }
-    w.open.erase(w.open.begin() + k);
+    c.mask = c.arrived = 0;
     return true;
 }
 
@@ -104,8 +135,7 @@ bool try_complete(int warp, size_t k)
 
 void emu_recheck(int warp)
 {
-    for (size_t k = 0; k < g_warp[warp].open.size();)
-        if (!try_complete(warp, k)) k++;
+    for (size_t k = 0; k < 8; k++) try_complete(warp, k);
 }
 
 uint32_t emu_collective(unsigned mask, int op, uint32_t value, int arg, int width)
@@ -114,15 +144,22 @@ uint32_t emu_collective(unsigned mask, int op, uint32_t value, int arg, int widt
     Warp &w = g_warp[f->warp];
     if (!(mask >> f->lane & 1)) { fprintf(stderr, "emu: %s: lane %d calls a collective whose mask %08x excludes it\n", g_name, f->lane, mask); abort(); }
     size_t k = 0;
-    while (k < w.open.size() && !(w.open[k].mask == mask && !(w.open[k].arrived >> f->lane & 1))) k++;
-    if (k == w.open.size()) { w.open.emplace_back(); w.open[k].mask = mask; w.open[k].op = op; w.open[k].width = width; }
+    while (k < 8 && !(w.open[k].mask == mask && !(w.open[k].arrived >> f->lane & 1))) k++;
+    if (k == 8) {
+        for (k = 0; k < 8 && w.open[k].mask; k++) {}
+        if (k == 8) { fprintf(stderr, "emu: %s: more than 8 collectives in progress in one warp\n", g_name); abort(); }
+        w.open[k].mask = mask; w.open[k].arrived = 0; w.open[k].op = op; w.open[k].width = width;
+    }
     Collective &c = w.open[k];
     if (c.op != op || c.width != width) { fprintf(stderr, "emu: %s: lanes of one warp meet in different collectives (mask %08x: op %d vs %d)\n", g_name, mask, c.op, op); abort(); }
     c.arrived |= 1u << f->lane;
     c.val[f->lane] = value;
     c.arg[f->lane] = arg;
     f->waiting = true;
-    if (!try_complete(f->warp, k)) to_scheduler();
+    void *sync = &w.sync[__builtin_ctz(mask)];
+    TSAN_RELEASE(sync);                      // every participant releases on arrival and acquires when it goes on: all-to-all order
+    if (!try_complete(f->warp, k)) { f->acquire = sync; to_scheduler(); }
+    else TSAN_ACQUIRE(sync);
     return f->result;
 }
 
@@ -130,12 +167,15 @@ void emu_syncthreads()
 {
     Fiber *f = g_cur;
     g_barrier_arrived++;
+    TSAN_RELEASE(&g_sync_block);
     if (g_barrier_arrived == g_alive) {
         for (Fiber &o : g_fib) o.waiting = false;
         g_barrier_arrived = 0;
+        TSAN_ACQUIRE(&g_sync_block);
         return;
     }
     f->waiting = true;
+    f->acquire = &g_sync_block;
     to_scheduler();
 }
 
@@ -170,6 +210,9 @@ void emu_run_grid(dim3 grid, dim3 block, const std::function<void()> &body, cons
             }
         }
     }
+#if defined(EMU_TSAN)
+    g_tsan_sched = __tsan_get_current_fiber();
+#endif
     g_body = &body;
     g_name = name;
     emu_block_dim = block;
@@ -182,10 +225,15 @@ void emu_run_grid(dim3 grid, dim3 block, const std::function<void()> &body, cons
                 if (n & 31) g_warp.back().exited = ~0u << (n & 31);       // lanes that do not exist
                 g_alive = (int)n;
                 g_barrier_arrived = 0;
+                TSAN_RELEASE(&g_sync_grid);
                 for (unsigned t = 0; t < n; t++) {
                     Fiber &f = g_fib[t];
                     f.tid = uint3{ t % block.x, t / block.x % block.y, t / (block.x * block.y) };
                     f.done = f.waiting = false;
+                    f.acquire = nullptr;
+#if defined(EMU_TSAN)
+                    if (!f.tsan) f.tsan = __tsan_create_fiber(0);     // reused by later blocks: creating one costs milliseconds
+#endif
                     f.warp = (int)t / 32;
                     f.lane = (int)t & 31;
                     getcontext(&f.ctx);
@@ -202,6 +250,9 @@ void emu_run_grid(dim3 grid, dim3 block, const std::function<void()> &body, cons
                         g_cur = &f;
                         emu_self = &f;
                         g_switches++;
+#if defined(EMU_TSAN)
+                        __tsan_switch_to_fiber(f.tsan, __tsan_switch_to_fiber_no_sync);
+#endif
                         swapcontext(&g_sched, &f.ctx);
                         ran = true;
                         if (f.done) left--;
@@ -210,11 +261,12 @@ void emu_run_grid(dim3 grid, dim3 block, const std::function<void()> &body, cons
                         fprintf(stderr, "emu: %s: block (%u,%u,%u) is stuck: %d threads wait in collectives nobody completes\n", name, bx, by, bz, left);
                         for (size_t wi = 0; wi < g_warp.size(); wi++)
                             for (const Collective &c : g_warp[wi].open)
-                                fprintf(stderr, "  warp %zu: op %d mask %08x arrived %08x exited %08x\n", wi, c.op, c.mask, c.arrived, g_warp[wi].exited);
+                                if (c.mask) fprintf(stderr, "  warp %zu: op %d mask %08x arrived %08x exited %08x\n", wi, c.op, c.mask, c.arrived, g_warp[wi].exited);
                         abort();
                     }
                 }
             }
+    TSAN_ACQUIRE(&g_sync_grid);
     g_cur = nullptr;
     emu_self = nullptr;
 }

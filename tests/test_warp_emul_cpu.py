@@ -129,6 +129,26 @@ def test_address_sanitizer_sees_no_out_of_bounds_access_in_the_kernels():
     assert r.returncode == 0 and "ERROR: AddressSanitizer" not in r.stderr, r.stderr[-4000:]
 
 
+@pytest.mark.parametrize("stream", [s for s in SMALL if os.path.basename(s).startswith(("b_416", "cip_416x240_8b", "tqb_416x240_10b", "i_256", "ra_416", "c422_416"))], ids=os.path.basename)
+def test_thread_sanitizer_sees_no_data_race_in_the_kernels(stream):
+    """the emulated library built with -fsanitize=thread: every CUDA thread is a TSan fiber, and the only happens-before edges
+    are the ones the CUDA model gives -- a completed warp collective among its participants, __syncthreads in the block, block
+    and kernel boundaries.  Two lanes touching the same shared-memory or global word without such an edge in between is a
+    reported race (what compute-sanitizer racecheck looks for; a removed __syncwarp gives eight reports on one P picture).
+    Real decoder, hooks, emulated device: pictures must still be right, and the sanitizer must stay silent."""
+    tsan_lib = os.path.join(REFDIR, "libb200hevc_emul_tsan.so")
+    rt = subprocess.run(["gcc", "-print-file-name=libtsan.so"], capture_output=True, text=True).stdout.strip()
+    if not os.path.exists(tsan_lib) or not os.path.isabs(rt) or not os.path.exists(rt) or not os.path.exists(os.path.join(REFDIR, "decode_b200")):
+        pytest.skip("no thread sanitizer build / runtime / hooked decoder")
+    out = subprocess.run([os.path.join(REFDIR, "decode_b200"), stream, "1"], capture_output=True, text=True, timeout=1800,
+                         env=dict(os.environ, LD_PRELOAD=rt + " " + tsan_lib, TSAN_OPTIONS="halt_on_error=0 report_signal_unsafe=0"))
+    if "FATAL: ThreadSanitizer" in out.stderr and "unexpected memory mapping" in out.stderr:
+        pytest.skip("thread sanitizer cannot map its shadow memory in this environment")
+    assert "WARNING: ThreadSanitizer" not in out.stderr, out.stderr[:6000]
+    assert out.returncode == 0, out.stderr[-2000:]
+    assert [l for l in out.stdout.splitlines() if l.startswith("frame ")] == open(stream[:-5] + ".md5").read().splitlines()
+
+
 def decode_emulated(stream, threads):
     out = subprocess.run([os.path.join(REFDIR, "decode_b200"), stream, threads], capture_output=True, text=True, timeout=900,
                          env=dict(os.environ, LD_PRELOAD=EMUL))
