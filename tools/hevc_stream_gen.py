@@ -235,8 +235,8 @@ class StreamGen:
         self.weighted = weighted
         self.cip = cip                      # pps constrained_intra_pred_flag (hevcpred_template.c:116-249)
         self.tqb = tqb                      # share of CUs with cu_transquant_bypass_flag (pps transquant_bypass_enable_flag when > 0)
-        self.cfi = cfi                      # chroma_format_idc: 1 = 4:2:0, 2 = 4:2:2 (two stacked chroma blocks per TU, RExt)
-        assert cfi in (1, 2) and not (cfi == 2 and pcm > 0)
+        self.cfi = cfi                      # chroma_format_idc: 1 = 4:2:0, 2 = 4:2:2 (two stacked chroma blocks per TU, RExt), 3 = 4:4:4 (chroma like luma, RExt)
+        assert cfi in (1, 2, 3) and not (cfi != 1 and pcm > 0)
         self.slices, self.lf_across_slices = slices, lf_across_slices   # independent slices per picture, each starting a CTB row
         assert slices == 1 or not (tiles or wpp), "several slices are generated without tiles / WPP only"
         self.pcm, self.pcm_lf_off = pcm, pcm_lf_off   # share of 2Nx2N intra CUs (8x8 .. 32x32) coded as PCM; pcm_loop_filter_disabled_flag
@@ -264,7 +264,7 @@ class StreamGen:
 
     # ---- parameter sets -------------------------------------------------------------------------------------
     def ptl(self, w):
-        prof = 4 if getattr(self, "cfi", 1) == 2 else (2 if self.bd > 8 else 1)   # Main / Main10 / format range extensions
+        prof = 4 if getattr(self, "cfi", 1) >= 2 else (2 if self.bd > 8 else 1)   # Main / Main10 / format range extensions
         w.u(2, 0); w.u(1, 0); w.u(5, prof)                                 # profile space, tier, profile idc
         for i in range(32):
             w.u(1, 1 if (i in (1, 2) and prof != 4) or (i == 4 and prof == 4) else 0)
@@ -289,6 +289,8 @@ class StreamGen:
         self.ptl(w)
         w.ue(0)                                                            # sps id
         w.ue(self.cfi)                                                     # chroma_format_idc
+        if self.cfi == 3:
+            w.u(1, 0)                                                      # separate_colour_plane_flag (hevc_ps.c:1597)
         w.ue(self.W); w.ue(self.H)
         w.u(1, 0)                                                          # conformance window
         w.ue(self.bd - 8); w.ue(self.bd - 8)
@@ -750,14 +752,18 @@ class StreamGen:
                         mode += 1
             modes.append(int(mode))
             self.ipm[(y0 + dy) >> 2:(y0 + dy + pb) >> 2, (x0 + dx) >> 2:(x0 + dx + pb) >> 2] = mode
-        cm = int(r.integers(0, 5))                                         # intra_chroma_pred_mode (4 = derived from luma)
-        c.encode(o["intra_chroma_pred_mode"], int(cm != 4))
-        if cm != 4:
-            c.bypass_bits(2, cm)
         table = [0, 26, 10, 1]
-        mode_c = modes[0] if cm == 4 else (34 if modes[0] == table[cm] else table[cm])
+        modes_c = []
+        for m in (modes if self.cfi == 3 else modes[:1]):                   # 4:4:4: one intra_chroma_pred_mode per luma block (hevc.c:2270-2283)
+            cm = int(r.integers(0, 5))                                     # intra_chroma_pred_mode (4 = derived from luma)
+            c.encode(o["intra_chroma_pred_mode"], int(cm != 4))
+            if cm != 4:
+                c.bypass_bits(2, cm)
+            modes_c.append(m if cm == 4 else (34 if m == table[cm] else table[cm]))
+        mode_c = modes_c[0]
         if self.cfi == 2:
             mode_c = self.tab_mode_idx[mode_c]                              # 4:2:2: process of 8.4.3, table read from hevc.c:2252
+        self.modes_c = modes_c
         self.ct_depth[y0 >> 3:(y0 + size) >> 3, x0 >> 3:(x0 + size) >> 3] = depth
         self.transform_tree(x0, y0, log2, 0, 0, nxn, modes, mode_c, [0, 0], self.max_th_depth_intra + nxn, modes[0])
 
@@ -765,6 +771,8 @@ class StreamGen:
         c, o, r = self.c, self.off, self.rng
         if nxn and tdepth == 1:
             mode = modes[blk]                                               # lc->tu.intra_pred_mode of this quadrant (hevc.c:1452)
+            if self.cfi == 3:
+                mode_c = self.modes_c[blk]                                  # ... and its own chroma mode at 4:4:4 (hevc.c:1463-1465)
         if log2 <= self.max_tb_log2 and log2 > self.min_tb_log2 and tdepth < max_depth and not (nxn and tdepth == 0):
             split = int(r.random() < 0.3)
             c.encode(o["split_transform_flag"] + 5 - log2, split)
@@ -776,7 +784,7 @@ class StreamGen:
         if tdepth == 0 and not isinstance(parent_cbf_c[0], list):
             parent_cbf_c = [[0, 0], [0, 0]]
         cbf_c = [list(parent_cbf_c[0]), list(parent_cbf_c[1])]
-        if log2 > 2:
+        if log2 > 2 or self.cfi == 3:                                       # hevc.c:1493
             for k in range(2):
                 if tdepth == 0 or parent_cbf_c[k][0]:
                     cbf_c[k][0] = int(r.random() < 0.5 - 0.3 * self.calm)
@@ -803,15 +811,15 @@ class StreamGen:
                 if 22 <= m <= 30:
                     return 1
             return 0
-        chroma_here = log2 > 2 or blk == 3                                  # 4x4 luma: the chroma of the 8x8 parent comes with block 3
-        flags = cbf_c if log2 > 2 else parent_cbf_c
+        chroma_here = log2 > 2 or blk == 3 or self.cfi == 3                 # 4x4 luma: the chroma of the 8x8 parent comes with block 3 (not at 4:4:4)
+        flags = cbf_c if (log2 > 2 or self.cfi == 3) else parent_cbf_c
         if not inter:
             self.cnt["intra_pred"] += 1 + (2 * nblk if chroma_here else 0)
         self.cnt["transform_add"] += cbf_luma + (sum(flags[0][:nblk]) + sum(flags[1][:nblk]) if chroma_here else 0)
         if cbf_luma:
             self.residual(log2, scan_of(mode, log2) if log2 < 4 else 0, 0)
         if chroma_here:
-            log2_c = log2 - 1 if log2 > 2 else 2
+            log2_c = log2 if self.cfi == 3 else (log2 - 1 if log2 > 2 else 2)
             for k in range(2):                                              # Cb blocks, then Cr blocks (hevc.c:1302-1362)
                 for i in range(nblk):
                     if flags[k][i]:
@@ -1018,7 +1026,7 @@ def main():
     ap.add_argument("--tqb", type=float, default=0.0, help="share of CUs coded with cu_transquant_bypass_flag")
     ap.add_argument("--pcm", type=float, default=0.0, help="share of 2Nx2N intra CUs coded as PCM")
     ap.add_argument("--pcm-lf-off", action="store_true", help="pcm_loop_filter_disabled_flag")
-    ap.add_argument("--cfi", type=int, default=1, help="chroma_format_idc: 1 = 4:2:0, 2 = 4:2:2")
+    ap.add_argument("--cfi", type=int, default=1, help="chroma_format_idc: 1 = 4:2:0, 2 = 4:2:2, 3 = 4:4:4")
     ap.add_argument("--slices", type=int, default=1, help="independent slices per picture (each starts a CTB row)")
     ap.add_argument("--no-lf-across-slices", action="store_true", help="slice_loop_filter_across_slices_enabled_flag = 0")
     ap.add_argument("--tskip", type=float, default=0.0, help="share of 4x4 TUs coded with transform_skip_flag")
