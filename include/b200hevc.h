@@ -124,6 +124,13 @@ int  b200_rec_set_cip(B200Rec *r, int log2_min_pu_size, int min_pu_width, int mi
  * = PCM-without-loop-filter or transquant-bypass PU), once all CTBs are parsed; the device gives those PUs their deblocked
  * samples back after SAO, exactly as restore_tqb_pixels does (hevc_filter.c:163-193) */
 int  b200_rec_set_tqb(B200Rec *r, int log2_min_pu_size, int min_pu_width, int min_pu_height, const uint8_t *is_pcm);
+/* cross-component prediction (4:4:4, hevc.c:1295-1360): b200_rec_tu_parked records a transform block whose residual is only
+ * PARKED (not added to the picture, not linked to an intra record) and returns where; b200_rec_ccp records
+ * "block of `plane` += (scale * parked luma residual) >> 3 [+ its own parked residual]" -- added to the picture after the
+ * residual stage, or handed to the intra stage when the block is intra predicted (decided like b200_rec_tu does). */
+int  b200_rec_tu_parked(B200Rec *r, int plane, int x, int y, int log2, int kind, int flags, int col_limit, const int16_t *coeffs,
+                        uint32_t *park_off);
+int  b200_rec_ccp(B200Rec *r, int plane, int x, int y, int log2, int scale, uint32_t off_y, int has_c, uint32_t off_c);
 /* host helper shared by the recorder and by external blob builders: permutation (perm[new] = old) that sorts decode-order
  * intra records by dependency level (stable); returns the number of levels (>= 0) or a negative error */
 int  b200_intra_level_order(const B200IntraRec *recs, uint32_t n, int width, int height, int chroma_format_idc, uint32_t *perm);

@@ -70,7 +70,9 @@ typedef struct B200BlobHeader {
                                     words, B200CipHeader followed by one bit per min-PU, bit set = s->is_pcm[] != 0 (PCM with the loop filter
                                     off, or cu_transquant_bypass).  After SAO those PUs get their deblocked samples back
                                     (restore_tqb_pixels, hevc_filter.c:163-193 -- with its two quirks, see k_sao.cuh)                        */
-    uint32_t reserved[64 - 17 - 2 * B200_SEC_COUNT];
+    B200Section ccp;             /* 4:4:4 pictures of streams with cross_component_prediction_enabled_flag (else count = 0): B200CcpRec[count],
+                                    executed between the residual stage and the intra stage                                            */
+    uint32_t reserved[64 - 19 - 2 * B200_SEC_COUNT];
 } B200BlobHeader;               /* 256 bytes */
 
 typedef struct B200CipHeader {   /* first 4 words of the CIP section */
@@ -87,6 +89,7 @@ typedef struct B200CipHeader {   /* first 4 words of the CIP section */
 #define B200_FRAME_HAS_DEBLOCK 1u
 #define B200_FRAME_HAS_SAO     2u
 #define B200_FRAME_TQB         8u   /* B200BlobHeader.tqb is present; B200SaoRec.tqb marks the CTBs that contain such PUs */
+#define B200_FRAME_CCP         16u  /* B200BlobHeader.ccp is present */
 #define B200_FRAME_CIP         4u   /* pps->constrained_intra_pred_flag: B200IntraRec.flags hold the availability BEFORE the
                                        CIP rules; the device applies hevcpred_template.c:116-163 and :185-249 with the bitmap */
 
@@ -125,6 +128,25 @@ typedef struct B200TuRec {       /* 16 bytes */
 #define B200_INF_BOTTOM_LEFT 16u
 #define B200_INF_FILTER      32u /* !intra_smoothing_disabled && (c_idx==0 || chroma_array_type==3)  :288 */
 #define B200_INF_STRONG      64u /* sps_strong_intra_smoothing_enable_flag                           :296 */
+
+/* ---- cross-component prediction (range extensions, 4:4:4; hevc.c:1186-1197, 1295-1360, hevc_cabac.c:1942-1948) ----------
+ * chroma residual += (res_scale_val * luma residual) >> 3, in int16 like the reference's coefficient arrays.  The reference
+ * computes it on the host from the luma block it has just transformed in place; with the transforms on the device the
+ * luma residual only exists there, so the recorder has the residual stage PARK it (a second, unlinked record of the luma TU)
+ * next to the chroma block's own residual (when it has coefficients), and this record combines them.                      */
+#define B200_CCPF_HAS_C   1u /* the chroma block has its own residual, parked at off_c                                 */
+#define B200_CCPF_TO_PARK 2u /* intra TU: the result goes to parked[off_out] (B200IntraRec.resid_off), else it is added to the picture */
+typedef struct B200CcpRec {      /* 32 bytes */
+    uint16_t x, y;               /* block origin in its plane                                     */
+    uint8_t  plane;              /* 1 = Cb, 2 = Cr                                                */
+    uint8_t  log2;               /* 2..5                                                          */
+    int8_t   scale;              /* lc->tu.res_scale_val: +-1, +-2, +-4, +-8                      */
+    uint8_t  flags;              /* B200_CCPF_*                                                   */
+    uint32_t off_y;              /* parked luma residual, int16 units                             */
+    uint32_t off_c;              /* parked chroma residual (B200_CCPF_HAS_C)                      */
+    uint32_t off_out;            /* destination in the parked pool (B200_CCPF_TO_PARK)            */
+    uint32_t pad[3];
+} B200CcpRec;
 
 typedef struct B200IntraRec {    /* 16 bytes */
     uint16_t x, y;               /* top-left sample in its plane */

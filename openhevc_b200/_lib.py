@@ -19,7 +19,7 @@ EXPORTS = [  # every symbol include/b200hevc.h declares
     "b200_stream", "b200_join", "b200_slot_begin_access", "b200_slot_end_access", "b200_host_alloc", "b200_host_free", "b200_frame_upload", "b200_frame_execute", "b200_frame_execute_ex", "b200_frame_submit",
     "b200_slot_upload", "b200_slot_readback", "b200_slot_wait_readback", "b200_slot_fill", "b200_wait_uploads", "b200_sync", "b200_set_profiling", "b200_get_stage_ms",
     "b200_launch_count", "b200_rec_create", "b200_rec_destroy", "b200_rec_begin", "b200_rec_set_refs", "b200_rec_tu", "b200_rec_pcm",
-    "b200_rec_intra", "b200_rec_mc", "b200_rec_deblock", "b200_rec_sao", "b200_rec_set_cip", "b200_rec_set_tqb", "b200_rec_merge", "b200_rec_finish", "b200_intra_level_order",
+    "b200_rec_intra", "b200_rec_mc", "b200_rec_deblock", "b200_rec_sao", "b200_rec_set_cip", "b200_rec_set_tqb", "b200_rec_tu_parked", "b200_rec_ccp", "b200_rec_merge", "b200_rec_finish", "b200_intra_level_order",
 ]
 
 
@@ -67,6 +67,8 @@ def load():
         "b200_rec_sao": (i32, [vp, i32, i32, i32, vp]),
         "b200_rec_set_cip": (i32, [vp, i32, i32, i32, vp]),
         "b200_rec_set_tqb": (i32, [vp, i32, i32, i32, vp]),
+        "b200_rec_tu_parked": (i32, [vp, i32, i32, i32, i32, i32, i32, i32, vp, C.POINTER(C.c_uint32)]),
+        "b200_rec_ccp": (i32, [vp, i32, i32, i32, i32, i32, C.c_uint32, i32, C.c_uint32]),
         "b200_rec_merge": (i32, [vp, vp]),
         "b200_rec_finish": (i32, [vp, C.POINTER(vp), C.POINTER(u64)]),
         "b200_intra_level_order": (i32, [vp, C.c_uint32, i32, i32, i32, vp]),

@@ -398,6 +398,11 @@ static int check_blob(B200Ctx *ctx, const B200BlobHeader *h, uint64_t nbytes)
             th->min_pu_height != ((uint32_t)c.height >> th->log2_min_pu_size) || h->tqb.count < B200_CIP_WORDS(th->min_pu_width, th->min_pu_height))
             return fail(ctx, B200_EINVAL, "TQB section does not match the picture geometry");
     }
+    if (h->ccp.count || (h->flags & B200_FRAME_CCP)) {          // cross-component prediction records (validated record by record on the device)
+        const uint64_t end = (uint64_t)h->ccp.off + (uint64_t)sizeof(B200CcpRec) * h->ccp.count;
+        if (!(h->flags & B200_FRAME_CCP) || !h->ccp.count || (h->ccp.off & 15) || end > nbytes || c.chroma_format_idc != 3)
+            return fail(ctx, B200_EINVAL, "CCP section out of bounds (or not a 4:4:4 picture)");
+    }
     if (h->mc_big_count > h->sec[B200_SEC_MC].count) return fail(ctx, B200_EINVAL, "mc_big_count %u > %u MC records", h->mc_big_count, h->sec[B200_SEC_MC].count);
     if (h->sec[B200_SEC_DBK].count && h->sec[B200_SEC_DBK].count != ctx->dbk.total) return fail(ctx, B200_EINVAL, "deblock grid size %u != %u", h->sec[B200_SEC_DBK].count, ctx->dbk.total);
     if (h->sec[B200_SEC_SAO].count && h->sec[B200_SEC_SAO].count != (uint32_t)(3 * ctx->ctb_w * ctx->ctb_h)) return fail(ctx, B200_EINVAL, "SAO grid size mismatch");
@@ -612,6 +617,8 @@ extern "C" int b200_frame_execute_ex(B200Ctx *ctx, int arena, int cur_slot, cons
     const B200TuRec *tu[4]; int ntu[4];
     for (int s = 0; s < 4; s++) { tu[s] = (const B200TuRec *)(a.dev + h.sec[B200_SEC_TU4 + s].off); ntu[s] = (int)h.sec[B200_SEC_TU4 + s].count; }
     ctx->launches += launch_residual(st, tu, ntu, pool, L.parked, cur, bd, L.counter);
+    if (h.flags & B200_FRAME_CCP)                       // 4:4:4 cross-component prediction: combine the parked luma / chroma residuals
+        ctx->launches += launch_ccp(st, (const B200CcpRec *)(a.dev + h.ccp.off), (int)h.ccp.count, L.parked, cur, bd, L.counter, ctx->arena_bytes);
     if (pf) CU(cudaEventRecord(ctx->prof[2], st));
     if (tr) CU(cudaEventRecord(tr->ev[2], st));
     // K3 intra

@@ -339,6 +339,46 @@ __global__ void __launch_bounds__(128) k_residual(ResidualLists L, const int16_t
 
 
 // --------------------------------------------------------------------------------------------
+// K2b: cross-component prediction (4:4:4 range extension; hevc.c:1295-1360, hevc_cabac.c:1942-1948), only launched for pictures
+// that carry B200CcpRec records.  chroma residual = own residual (parked by K2, if the block has coefficients) +
+// (res_scale_val * luma residual) >> 3 (the luma block parked by K2 through a second, unlinked record), in int16 like the
+// reference's coefficient arrays; added to the picture like transform_add, or parked again for the intra stage.
+// The records are validated here (one CTA per record): a bad one closes the picture's gate like K0 does.
+// --------------------------------------------------------------------------------------------
+template <typename PIX>
+__global__ void __launch_bounds__(128) k_ccp(const B200CcpRec *__restrict__ recs, int count, int16_t *__restrict__ parked, FrameDesc f, int bd,
+                                             uint32_t *gate, unsigned long long arena_bytes)
+{
+    if (__ldg(gate + 1)) return;
+    const int i = blockIdx.x;
+    if (i >= count) return;
+    const int4 *rp = reinterpret_cast<const int4 *>(recs + i);
+    const int4 ra = __ldg(rp);
+    const int x = ra.x & 0xffff, y = (unsigned)ra.x >> 16;
+    const int plane = ra.y & 0xff, log2 = (ra.y >> 8) & 0xff, scale = (int8_t)((ra.y >> 16) & 0xff), flags = (unsigned)ra.y >> 24;
+    const uint32_t off_y = (uint32_t)ra.z, off_c = (uint32_t)ra.w, off_out = (uint32_t)__ldg(reinterpret_cast<const int *>(rp + 1));
+    const int n = 1 << (log2 & 7), nn = n * n;
+    const int pl = plane == 2 ? 2 : 1;
+    const PlaneDesc pd = plane_of(f, pl);
+    const unsigned long long cap = arena_bytes / 2;                           // int16 entries of the parked pool
+    if ((plane != 1 && plane != 2) || log2 < 2 || log2 > 5 || x + n > pd.w || y + n > pd.h || (unsigned long long)off_y + nn > cap ||
+        ((flags & B200_CCPF_HAS_C) && (unsigned long long)off_c + nn > cap) || ((flags & B200_CCPF_TO_PARK) && (unsigned long long)off_out + nn > cap)) {
+        if (threadIdx.x == 0) { gate[1] = 1u; atomicOr(gate + 3, 1u << B200_SEC_COUNT); }
+        return;
+    }
+    const int maxv = (1 << bd) - 1;
+    for (int k = threadIdx.x; k < nn; k += 128) {
+        const int own = (flags & B200_CCPF_HAS_C) ? parked[off_c + k] : 0;
+        const int r = (int16_t)(own + ((scale * (int)parked[off_y + k]) >> 3));
+        if (flags & B200_CCPF_TO_PARK) parked[off_out + k] = (int16_t)r;
+        else {
+            PIX *d = px_ptr<PIX>(pd, x + (k & (n - 1)), y + (k >> log2));
+            *d = (PIX)clip3i((int)*d + r, 0, maxv);
+        }
+    }
+}
+
+// --------------------------------------------------------------------------------------------
 // K1: inter prediction.  One warp per tile record (<= 256 samples, <= 32 wide).
 // Reference window staged in shared memory with clamped addressing (== emulated_edge_mc),
 // separable FIR with the 14-bit intermediate of the reference.
@@ -1333,6 +1373,14 @@ static int launch_residual_t(cudaStream_t st, const B200TuRec *const recs[4], co
 int launch_residual(cudaStream_t st, const B200TuRec *const recs[4], const int counts[4], const int16_t *pool, int16_t *parked, const FrameDesc &cur, int bd, const uint32_t *gate)
 {
     return bd > 8 ? launch_residual_t<uint16_t>(st, recs, counts, pool, parked, cur, bd, gate) : launch_residual_t<uint8_t>(st, recs, counts, pool, parked, cur, bd, gate);
+}
+
+int launch_ccp(cudaStream_t st, const B200CcpRec *recs, int count, int16_t *parked, const FrameDesc &cur, int bd, uint32_t *gate, unsigned long long arena_bytes)
+{
+    if (!count) return 0;
+    if (bd > 8) B200_LAUNCH(count, 128, 0, st, k_ccp<uint16_t>)(recs, count, parked, cur, bd, gate, arena_bytes);
+    else        B200_LAUNCH(count, 128, 0, st, k_ccp<uint8_t>)(recs, count, parked, cur, bd, gate, arena_bytes);
+    return 1;
 }
 
 int launch_intra(cudaStream_t st, const B200IntraRec *recs, int count, const int16_t *pool, const FrameDesc &cur, int bd,

@@ -27,6 +27,7 @@ struct B200Rec {
     std::vector<B200IntraRec> intra;
     std::vector<B200McRec> mc;
     std::vector<uint32_t> cip;   // B200CipHeader + bitmap of a constrained_intra_pred picture (b200_rec_set_cip), else empty
+    std::vector<B200CcpRec> ccp; // cross-component prediction records (b200_rec_ccp), executed between the residual and the intra stage
     std::vector<uint32_t> tqb;   // B200CipHeader + bitmap of the PUs restore_tqb_pixels gives their deblocked samples back (b200_rec_set_tqb)
     int last_intra[3];
     bool any_dbk = false, any_sao = false, open = false;
@@ -140,7 +141,7 @@ extern "C" int b200_rec_begin(B200Rec *r, int cur_slot, int poc)
     if (!r || cur_slot < 0 || cur_slot > 255) return B200_EINVAL;
     memset(r->blob + r->off_dbk, 0, r->off_pool - r->off_dbk);
     for (int s = 0; s < 4; s++) r->tu[s].clear();
-    r->intra.clear(); r->mc.clear(); r->cip.clear(); r->tqb.clear();
+    r->intra.clear(); r->mc.clear(); r->cip.clear(); r->tqb.clear(); r->ccp.clear();
     r->ncoef = 0; r->npark = 0; r->any_dbk = r->any_sao = false;
     r->last_intra[0] = r->last_intra[1] = r->last_intra[2] = -1;
     r->cur_slot = cur_slot; r->poc = poc; r->open = true; r->nbytes = 0; r->n_ref = 0; r->merged = false;
@@ -156,8 +157,10 @@ static int16_t *pool_take(B200Rec *r, int n, uint32_t *off)
     return (int16_t *)(r->blob + r->off_pool) + o;
 }
 
-extern "C" int b200_rec_tu(B200Rec *r, int plane, int x, int y, int log2, int kind, int flags, int col_limit,
-                           const int16_t *coeffs, int intra_linked)
+// intra_linked: -1 = link to the preceding intra record of the plane if it matches (the normal case), 0 = never, 1 = must;
+// 2 = PARK the residual without linking it to anything (cross-component prediction), park offset returned in *park_out
+static int rec_tu_impl(B200Rec *r, int plane, int x, int y, int log2, int kind, int flags, int col_limit,
+                       const int16_t *coeffs, int intra_linked, uint32_t *park_out)
 {
     if (!r || !r->open || !coeffs || plane < 0 || plane > 2 || log2 < 2 || log2 > 5 || kind < 0 || kind > B200_TU_PCM) return B200_EINVAL;
     const int n = 1 << log2;
@@ -169,16 +172,19 @@ extern "C" int b200_rec_tu(B200Rec *r, int plane, int x, int y, int log2, int ki
     if (li >= 0 && kind != B200_TU_PCM) {
         const B200IntraRec &ir = r->intra[li];
         link = ir.x == x && ir.y == y && ir.log2 == log2 && ir.resid_off == B200_NO_RESID;
-        if (intra_linked == 0) link = false;
+        if (intra_linked == 0 || intra_linked == 2) link = false;
     }
+    const bool park_only = intra_linked == 2 && kind != B200_TU_PCM;
+    if (intra_linked == 2 && !park_only) return B200_EINVAL;
+    const bool parked = link || park_only;
     // sparse transport: most dequantised coefficients are zero, send (position, value) pairs.
     // One pass, four coefficients per test (the block is 8-byte aligned scratch of the decoder, hevc.h:1063): pairs are
     // written straight into the pool while they stay below the size of a dense block, else the block is copied whole.
     const int nn = n * n;
     uint32_t off;
-    int16_t *dst = pool_take(r, (link ? 2 : 0) + nn, &off);           // room for either form; the unused tail is given back
+    int16_t *dst = pool_take(r, (parked ? 2 : 0) + nn, &off);         // room for either form; the unused tail is given back
     if (!dst) return B200_ENOMEM;
-    int16_t *pairs = dst + (link ? 2 : 0);
+    int16_t *pairs = dst + (parked ? 2 : 0);
     int nnz = 0;
     bool sparse = kind != B200_TU_PCM;
     if (sparse) {
@@ -215,15 +221,16 @@ extern "C" int b200_rec_tu(B200Rec *r, int plane, int x, int y, int log2, int ki
 #endif
         sparse = nnz <= limit && 2 * nnz < nn;
     }
-    r->ncoef = off + (link ? 2 : 0) + (sparse ? 2 * nnz : nn);        // give the unused tail back
+    r->ncoef = off + (parked ? 2 : 0) + (sparse ? 2 * nnz : nn);      // give the unused tail back
     B200TuRec t;
     memset(&t, 0, sizeof(t));
-    if (link) {
+    if (parked) {
         const uint32_t po = (r->npark + 7) & ~7u;
         r->npark = po + n * n;
         dst[0] = (int16_t)(po & 0xffff); dst[1] = (int16_t)(po >> 16);
         dst += 2;
-        r->intra[li].resid_off = po;
+        if (link) r->intra[li].resid_off = po;
+        if (park_out) *park_out = po;
         t.flags |= B200_TUF_PARK;
     }
     if (sparse) t.nnz = (uint16_t)nnz;                                 // the pairs are in place
@@ -237,6 +244,47 @@ extern "C" int b200_rec_tu(B200Rec *r, int plane, int x, int y, int log2, int ki
     t.coeff_off = off;
     if (intra_linked == 1 && !link) return B200_ESTATE;
     r->tu[log2 - 2].push_back(t);
+    return 0;
+}
+
+extern "C" int b200_rec_tu(B200Rec *r, int plane, int x, int y, int log2, int kind, int flags, int col_limit,
+                           const int16_t *coeffs, int intra_linked)
+{
+    if (intra_linked < -1 || intra_linked > 1) return B200_EINVAL;
+    return rec_tu_impl(r, plane, x, y, log2, kind, flags, col_limit, coeffs, intra_linked, nullptr);
+}
+
+extern "C" int b200_rec_tu_parked(B200Rec *r, int plane, int x, int y, int log2, int kind, int flags, int col_limit, const int16_t *coeffs,
+                                  uint32_t *park_off)
+{
+    if (!park_off) return B200_EINVAL;
+    return rec_tu_impl(r, plane, x, y, log2, kind, flags, col_limit, coeffs, 2, park_off);
+}
+
+// cross-component prediction of one chroma block (hevc.c:1295-1360): see B200CcpRec
+extern "C" int b200_rec_ccp(B200Rec *r, int plane, int x, int y, int log2, int scale, uint32_t off_y, int has_c, uint32_t off_c)
+{
+    if (!r || !r->open || plane < 1 || plane > 2 || log2 < 2 || log2 > 5 || r->cfg.chroma_format_idc != 3) return B200_EINVAL;
+    const int n = 1 << log2, as = scale < 0 ? -scale : scale;
+    if (x < 0 || y < 0 || x + n > r->pw[plane] || y + n > r->ph[plane] || (as != 1 && as != 2 && as != 4 && as != 8)) return B200_EINVAL;
+    if ((uint64_t)off_y + n * n > r->npark || (has_c && (uint64_t)off_c + n * n > r->npark)) return B200_EINVAL;
+    B200CcpRec c;
+    memset(&c, 0, sizeof(c));
+    c.x = (uint16_t)x; c.y = (uint16_t)y; c.plane = (uint8_t)plane; c.log2 = (uint8_t)log2; c.scale = (int8_t)scale;
+    c.off_y = off_y; c.off_c = has_c ? off_c : 0;
+    c.flags = has_c ? B200_CCPF_HAS_C : 0;
+    const int li = r->last_intra[plane];
+    if (li >= 0) {                                  // intra predicted block: the intra stage adds the combined residual after predicting
+        B200IntraRec &ir = r->intra[li];
+        if (ir.x == x && ir.y == y && ir.log2 == log2 && ir.resid_off == B200_NO_RESID) {
+            const uint32_t po = (r->npark + 7) & ~7u;
+            r->npark = po + n * n;
+            ir.resid_off = po;
+            c.off_out = po;
+            c.flags |= B200_CCPF_TO_PARK;
+        }
+    }
+    r->ccp.push_back(c);
     return 0;
 }
 
@@ -319,6 +367,12 @@ extern "C" int b200_rec_merge(B200Rec *d, B200Rec *s)
             }
             d->tu[k].push_back(t);
         }
+    for (B200CcpRec c : s->ccp) {
+        c.off_y += pbase;
+        if (c.flags & B200_CCPF_HAS_C) c.off_c += pbase;
+        if (c.flags & B200_CCPF_TO_PARK) c.off_out += pbase;
+        d->ccp.push_back(c);
+    }
     for (B200IntraRec ir : s->intra) {
         if (ir.resid_off != B200_NO_RESID) ir.resid_off += pbase;
         d->intra.push_back(ir);
@@ -469,6 +523,13 @@ extern "C" int b200_rec_finish(B200Rec *r, const void **blob, uint64_t *nbytes)
         h->flags |= B200_FRAME_CIP;
         memcpy(r->blob + o, r->cip.data(), r->cip.size() * 4);
         o = (o + r->cip.size() * 4 + 255) & ~(uint64_t)255;
+    }
+    if (!r->ccp.empty()) {                                   // cross-component prediction records
+        if (o + r->ccp.size() * sizeof(B200CcpRec) + 256 > r->cap) return B200_ENOMEM;
+        h->ccp.off = (uint32_t)o; h->ccp.count = (uint32_t)r->ccp.size();
+        h->flags |= B200_FRAME_CCP;
+        memcpy(r->blob + o, r->ccp.data(), r->ccp.size() * sizeof(B200CcpRec));
+        o = (o + r->ccp.size() * sizeof(B200CcpRec) + 255) & ~(uint64_t)255;
     }
     if (!r->tqb.empty() && r->any_sao) {                     // restore_tqb_pixels only ever runs behind the SAO of a CTB
         if (o + r->tqb.size() * 4 + 256 > r->cap) return B200_ENOMEM;

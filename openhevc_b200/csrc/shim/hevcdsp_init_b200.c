@@ -83,6 +83,10 @@ typedef struct ShimThread {
     struct ShimThread *workers[MAX_WORKERS]; int n_workers;   /* owner: workers that recorded part of this picture */
     struct ShimThread *att; unsigned att_seq;            /* worker: the owner it is attached to */
     int n_tu, n_intra, n_pu, n_dbk, n_sao, frame_no;   /* B200_SHIM_STATS=1: table calls per picture (stderr) */
+    /* cross-component prediction (4:4:4 range extension): the owner's decoder context, this thread's local context (found by
+     * the coefficient pointer), and the luma transform block the chroma blocks of the same TU refer to */
+    HEVCContext *s; int ccp; HEVCLocalContext *lc;
+    struct { int x, y, log2, kind, flags, cl, parked; uint32_t park; } last_y;
     uint8_t fill_slot[16]; int n_fill;                  /* generate_missing_ref (hevc_refs.c:538): grey references this picture needs */
 } ShimThread;
 /* One heap block per thread, reached through an 8-byte initial-exec TLS pointer: a plain `static __thread ShimThread` in a
@@ -154,6 +158,7 @@ static int attach_slow(void)
             memcpy(g.reg, o->reg, sizeof(g.reg)); g.n_reg = o->n_reg;
             for (int p = 0; p < 3; p++) { g.cur_base[p] = o->cur_base[p]; g.cur_ls[p] = o->cur_ls[p]; g.cur_size[p] = o->cur_size[p]; g.cur_inv[p] = o->cur_inv[p]; }
             g.cur_slot = o->cur_slot; g.poc = o->poc;
+            g.s = o->s; g.ccp = o->ccp; g.lc = NULL; g.last_y.log2 = 0;
             g.n_ref = 0; g.pend_ptr = NULL; g.first_tmp = NULL; g.emu[0].buf = g.emu[1].buf = NULL;
             g.n_tu = g.n_intra = g.n_pu = g.n_dbk = g.n_sao = 0;
             if (b200_rec_begin(g.rec, g.cur_slot, g.poc)) { fail(B200_ESTATE, "b200_rec_begin failed (worker)"); rc = -1; }
@@ -242,15 +247,65 @@ static void rec_transform_rdpcm(int16_t *c, int16_t log2_size, int mode)
     if (g.pend_ptr != c) { g.pend_ptr = c; g.pend_kind = B200_TU_BYPASS; g.pend_col_limit = 0; }
     g.pend_flags = B200_TUF_RDPCM | (mode ? B200_TUF_RDPCM_VERT : 0);
 }
+/* Cross-component prediction (hevc.c:1295-1360, hevc_cabac.c:1942-1948).  Between the chroma block's idct() call and its
+ * transform_add() call the reference adds (res_scale_val * luma residual) >> 3 to the chroma coefficients ON THE HOST, reading
+ * the luma block it has transformed in place -- which, with the transforms recorded instead of executed, still holds the
+ * dequantised luma COEFFICIENTS.  The term it added is therefore known exactly (same arrays, same arithmetic) and is taken
+ * out again; the device gets the chroma block as the decoder parsed it, the luma block a second time (parked only), and a
+ * record that combines the two residuals there.  The local context (res_scale_val, cross_pf, the luma array) is found through
+ * the coefficient pointer: the tables carry no context argument. */
+static HEVCLocalContext *local_context_of(const int16_t *coeffs)
+{
+    ShimThread *t = &g;
+    if (t->lc && coeffs >= t->lc->tu.coeffs[0] && coeffs < t->lc->tu.coeffs[0] + 2 * MAX_TB_SIZE * MAX_TB_SIZE) return t->lc;
+    HEVCContext *s = t->s;
+    for (int i = -1; s && i < MAX_NB_THREADS; i++) {
+        HEVCLocalContext *lc = i < 0 ? s->HEVClc : s->HEVClcList[i];
+        if (lc && coeffs >= lc->tu.coeffs[0] && coeffs < lc->tu.coeffs[0] + 2 * MAX_TB_SIZE * MAX_TB_SIZE) return t->lc = lc;
+    }
+    return NULL;
+}
+static int rec_cross_component(int plane, int x, int y, int log2, int16_t *coeffs, int kind, int flags, int cl, int pending)
+{
+    ShimThread *t = &g;
+    HEVCLocalContext *lc = local_context_of(coeffs);
+    if (!lc) { fail(B200_EINVAL, "cross_component_prediction: coefficient block outside every local context"); return -1; }
+    if (!lc->tu.cross_pf || !lc->tu.res_scale_val) return 0;                 /* nothing was added on the host */
+    if (t->last_y.log2 != log2 || t->last_y.x != x || t->last_y.y != y) { fail(B200_ESTATE, "cross_component_prediction without the luma block of the same TU"); return -1; }
+    const int16_t *cy = lc->tu.coeffs[0];
+    const int scale = lc->tu.res_scale_val, nn = 1 << (2 * log2);
+    int16_t own[MAX_TB_SIZE * MAX_TB_SIZE];
+    int has_c = pending;
+    for (int i = 0; i < nn; i++) {
+        own[i] = (int16_t)(coeffs[i] - ((scale * cy[i]) >> 3));
+        has_c |= own[i] != 0;
+    }
+    int rc = 0;
+    uint32_t off_c = 0;
+    if (!t->last_y.parked) {
+        rc = b200_rec_tu_parked(t->rec, 0, x, y, log2, t->last_y.kind, t->last_y.flags, t->last_y.cl, cy, &t->last_y.park);
+        t->last_y.parked = 1;
+    }
+    if (!rc && has_c) rc = b200_rec_tu_parked(t->rec, plane, x, y, log2, kind, flags, cl, own, &off_c);
+    if (!rc) rc = b200_rec_ccp(t->rec, plane, x, y, log2, scale, t->last_y.park, has_c, off_c);
+    if (rc) { fail(rc, "recording a cross-component prediction block failed"); return -1; }
+    return 1;
+}
+
 static void rec_transform_add(uint8_t *dst, int16_t *coeffs, ptrdiff_t stride, int log2)
 {
     int plane, x, y;
     (void)stride;
     if (locate_cur(dst, &plane, &x, &y)) return;
     int kind = B200_TU_BYPASS, flags = 0, cl = 0;
-    if (g.pend_ptr == coeffs) { kind = g.pend_kind; flags = g.pend_flags; cl = g.pend_col_limit; }
+    const int pending = g.pend_ptr == coeffs;
+    if (pending) { kind = g.pend_kind; flags = g.pend_flags; cl = g.pend_col_limit; }
     g.pend_ptr = NULL;
     g.n_tu++;
+    if (g.ccp) {
+        if (plane == 0) { g.last_y.x = x; g.last_y.y = y; g.last_y.log2 = log2; g.last_y.kind = kind; g.last_y.flags = flags; g.last_y.cl = cl; g.last_y.parked = 0; }
+        else if (rec_cross_component(plane, x, y, log2, coeffs, kind, flags, cl, pending)) return;
+    }
     int rc = b200_rec_tu(g.rec, plane, x, y, log2, kind, flags, cl, coeffs, -1);
     if (rc) fail(rc, "b200_rec_tu failed");
 }
@@ -539,11 +594,9 @@ int b200_frame_begin(HEVCContext *s)
     if (g.err) return g.err;
     if (g.in_frame == 1) { deactivate(); ticket_release(); }   /* previous picture of this thread was abandoned */
     g.in_frame = 0;
-    /* tools whose pixel work bypasses the tables and is not done on the device yet: refuse, never guess */
-    if (s->sps->chroma_array_type == 3 && s->pps->cross_component_prediction_enabled_flag) {
-        fail(B200_ENOTSUP, "cross_component_prediction (4:4:4, hevc.c:1325-1327) is not supported by the B200 path");
-        return g.err;
-    }
+    /* cross-component prediction (4:4:4): host arithmetic between two table calls, undone and redone on the device (rec_cross_component) */
+    g.s = s; g.lc = NULL; g.last_y.log2 = 0;
+    g.ccp = s->sps->chroma_array_type == 3 && s->pps->cross_component_prediction_enabled_flag;
     pthread_mutex_lock(&G.mu);
     const int erc = ensure_ctx(s);
     if (!erc) g.ticket = G.next_ticket++;

@@ -24,7 +24,7 @@ header_dt = np.dtype([
     ("width", "<u2"), ("height", "<u2"), ("chroma_format_idc", "u1"), ("bit_depth", "u1"),
     ("log2_ctb_size", "u1"), ("cur_slot", "u1"), ("flags", "<u4"),
     ("sec", section_dt, (SEC_COUNT,)), ("ref_slot", "u1", (16,)), ("n_ref", "u1"), ("pad", "u1", (3,)),
-    ("mc_big_count", "<u4"), ("cip", section_dt), ("tqb", section_dt), ("reserved", "<u4", (64 - 17 - 2 * SEC_COUNT,)),
+    ("mc_big_count", "<u4"), ("cip", section_dt), ("tqb", section_dt), ("ccp", section_dt), ("reserved", "<u4", (64 - 19 - 2 * SEC_COUNT,)),
 ])
 tu_dt = np.dtype([("x", "<u2"), ("y", "<u2"), ("plane", "u1"), ("log2", "u1"), ("kind", "u1"), ("flags", "u1"),
                   ("col_limit", "u1"), ("pad", "u1"), ("nnz", "<u2"), ("coeff_off", "<u4")])

@@ -684,6 +684,12 @@ int orc_execute_blob(const uint8_t *blob, uint16_t **planes, int n_slots)
                 if ((size_t)po + (1u << (2 * tu[i].log2)) > park_len) park_len = (size_t)po + (1u << (2 * tu[i].log2));
             }
     }
+    const B200CcpRec *ccp = (const B200CcpRec *)(blob + h->ccp.off);
+    const uint32_t n_ccp = (h->flags & B200_FRAME_CCP) ? h->ccp.count : 0;
+    for (uint32_t i = 0; i < n_ccp; i++) {
+        const size_t nn = (size_t)1 << (2 * ccp[i].log2);
+        if ((ccp[i].flags & B200_CCPF_TO_PARK) && ccp[i].off_out + nn > park_len) park_len = ccp[i].off_out + nn;
+    }
     int16_t *parked = (int16_t *)calloc(park_len, sizeof(int16_t));
     if (!parked) return -3;
 
@@ -713,6 +719,22 @@ int orc_execute_blob(const uint8_t *blob, uint16_t **planes, int n_slots)
             if (t->flags & B200_TUF_PARK) memcpy(parked + po, c, (size_t)n * n * sizeof(int16_t));
             else orc_add_residual(cur[p] + t->y * pw[p] + t->x, pw[p], c, n, bd);
         }
+    }
+    /* cross-component prediction (4:4:4 range extension): chroma residual = own residual + (res_scale_val * luma residual) >> 3,
+     * in int16 like the reference's coefficient arrays (hevc.c:1325-1327, 1358-1360, hevc_cabac.c:1942-1948), then
+     * transform_add -- or, for an intra block, the intra stage below adds it after predicting */
+    for (uint32_t i = 0; i < n_ccp; i++) {
+        const B200CcpRec *c = &ccp[i];
+        const int n = 1 << c->log2, p = c->plane;
+        if (p < 1 || p > 2 || c->x + n > pw[p] || c->y + n > ph[p] || c->off_y + (size_t)n * n > park_len ||
+            ((c->flags & B200_CCPF_HAS_C) && c->off_c + (size_t)n * n > park_len)) { free(parked); return -8; }
+        int16_t r[32 * 32];
+        for (int k = 0; k < n * n; k++) {
+            const int16_t own = (c->flags & B200_CCPF_HAS_C) ? parked[c->off_c + k] : 0;
+            r[k] = (int16_t)(own + ((c->scale * parked[c->off_y + k]) >> 3));
+        }
+        if (c->flags & B200_CCPF_TO_PARK) memcpy(parked + c->off_out, r, (size_t)n * n * sizeof(int16_t));
+        else orc_add_residual(cur[p] + c->y * pw[p] + c->x, pw[p], r, n, bd);
     }
     /* K3 intra, decode order */
     const B200IntraRec *ir = (const B200IntraRec *)(blob + h->sec[B200_SEC_INTRA].off);

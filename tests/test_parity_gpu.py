@@ -244,6 +244,82 @@ def test_empty_work_list_and_smallest_pictures():
         FrameEngine(20, 16, 1, 8)                         # not a multiple of the minimum coding block
 
 
+def ccp_blob(w, h, bd, seed, corrupt=False):
+    """a 4:4:4 picture of cross-component-prediction blocks built through the recorder API the way the shim does it
+    (hevcdsp_init_b200.c: rec_cross_component): luma block, the same luma block parked, the chroma block's own residual parked
+    (or none), and the record that combines them -- half of the blocks intra predicted (result parked for the intra stage)"""
+    import ctypes as C
+    from openhevc_b200 import _lib
+    lib = _lib.load()
+    rng = np.random.default_rng(seed)
+    cfg = _lib.B200Config(0, w, h, 3, bd, 6, 2, 2, 0, None, 0)
+    r = C.c_void_p()
+    assert lib.b200_rec_create(C.byref(cfg), C.byref(r)) == 0
+    assert lib.b200_rec_begin(r, 0, 0) == 0
+    for y in range(0, h, 16):
+        for x in range(0, w, 16):
+            log2 = int(rng.choice([2, 3, 4]))
+            n = 1 << log2
+            intra = bool(rng.integers(2))
+
+            def coeffs():
+                c = np.zeros((n, n), np.int16)
+                k = int(rng.integers(1, 6))
+                c[rng.integers(0, min(n, 4), k), rng.integers(0, min(n, 4), k)] = rng.integers(-300, 300, k)
+                return np.ascontiguousarray(c)
+            cy = coeffs()
+            if intra:
+                assert lib.b200_rec_intra(r, 0, x, y, log2, 1, 0, 0, 0) == 0
+            assert lib.b200_rec_tu(r, 0, x, y, log2, W.TU_IDCT, 0, n, cy.ctypes.data, -1) == 0
+            off_y = C.c_uint32()
+            assert lib.b200_rec_tu_parked(r, 0, x, y, log2, W.TU_IDCT, 0, n, cy.ctypes.data, C.byref(off_y)) == 0
+            for plane in (1, 2):
+                if intra:
+                    assert lib.b200_rec_intra(r, plane, x, y, log2, 1, 0, 0, 0) == 0
+                has_c = bool(rng.integers(2))
+                off_c = C.c_uint32()
+                if has_c:
+                    cc = coeffs()
+                    assert lib.b200_rec_tu_parked(r, plane, x, y, log2, W.TU_IDCT, 0, n, cc.ctypes.data, C.byref(off_c)) == 0
+                scale = int(rng.choice([1, 2, 4, 8])) * int(rng.choice([-1, 1]))
+                assert lib.b200_rec_ccp(r, plane, x, y, log2, scale, off_y.value, int(has_c), off_c.value) == 0
+    blob_p, nbytes = C.c_void_p(), C.c_uint64()
+    assert lib.b200_rec_finish(r, C.byref(blob_p), C.byref(nbytes)) == 0
+    blob = np.ctypeslib.as_array(C.cast(blob_p, C.POINTER(C.c_uint8)), (nbytes.value,)).copy()
+    lib.b200_rec_destroy(r)
+    if corrupt:
+        hdr, _ = W.parse_blob(blob)
+        off = int(hdr["ccp"]["off"])
+        blob[off + 8:off + 12] = np.frombuffer(np.uint32(0x7fffff00).tobytes(), np.uint8)      # off_y of the first record far outside the pool
+    return blob
+
+
+@pytest.mark.late
+@pytest.mark.parametrize("bd", [8, 10])
+def test_cross_component_prediction(bd):
+    """range-extension cross-component prediction (hevc.c:1295-1360): chroma residual += (res_scale_val * luma residual) >> 3"""
+    w, h = 96, 64
+    eng = FrameEngine(w, h, 3, bd, n_slots=2)
+    try:
+        before = smooth_frame(w, h, 3, bd, 4)
+        for seed in (1, 2):
+            eng.upload_slot(0, before)
+            blob = ccp_blob(w, h, bd, seed)
+            got = eng.decode(blob)
+            want = oracle_lib.execute(blob, [[p.copy() for p in before], [np.zeros_like(p) for p in before]])
+            for p in range(3):
+                assert np.array_equal(got[p], want[p]), f"plane {p} differs (seed {seed})"
+        with pytest.raises(B200Error, match="rejected on the device"):
+            eng.decode(ccp_blob(w, h, bd, 3, corrupt=True))
+        eng.upload_slot(0, before)
+        blob = ccp_blob(w, h, bd, 1)
+        again = eng.decode(blob)
+        want = oracle_lib.execute(blob, [[p.copy() for p in before], [np.zeros_like(p) for p in before]])
+        assert all(np.array_equal(a, b) for a, b in zip(again, want))
+    finally:
+        eng.close()
+
+
 def test_cyclic_intra_dependencies_time_out_instead_of_hanging():
     """a work list whose intra TUs wait on each other (cannot come from a real decode order) must not hang the device"""
     w, h = 128, 64

@@ -68,6 +68,13 @@ def test_sequence_all_stages_on_the_emulated_kernels(emulated, w, h, cfi, bd):
 
 
 @needs_emul
+@pytest.mark.parametrize("bd", [8, 10])
+def test_cross_component_prediction_on_the_emulated_kernels(emulated, bd):
+    import test_parity_gpu
+    test_parity_gpu.test_cross_component_prediction(bd)
+
+
+@needs_emul
 @pytest.mark.parametrize("cfi,bd", [(1, 8), (2, 10)])
 def test_grey_reference_fill_on_the_emulated_kernels(emulated, cfi, bd):
     import test_parity_gpu
@@ -129,7 +136,7 @@ def test_address_sanitizer_sees_no_out_of_bounds_access_in_the_kernels():
     assert r.returncode == 0 and "ERROR: AddressSanitizer" not in r.stderr, r.stderr[-4000:]
 
 
-@pytest.mark.parametrize("stream", [s for s in SMALL if os.path.basename(s).startswith(("b_416", "cip_416x240_8b", "tqb_416x240_10b", "c422_416"))], ids=os.path.basename)
+@pytest.mark.parametrize("stream", [s for s in SMALL if os.path.basename(s).startswith(("b_416", "cip_416x240_8b", "tqb_416x240_10b", "c422_416", "ccp_416x240_8b"))], ids=os.path.basename)
 def test_thread_sanitizer_sees_no_data_race_in_the_kernels(stream):
     """the emulated library built with -fsanitize=thread: every CUDA thread is a TSan fiber, and the only happens-before edges
     are the ones the CUDA model gives -- a completed warp collective among its participants, __syncthreads in the block, block

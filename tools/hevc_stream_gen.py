@@ -230,7 +230,7 @@ SIG_CTX_4x4 = [0, 1, 4, 5, 2, 3, 4, 5, 6, 6, 8, 8, 7, 7, 8, 8]
 
 
 class StreamGen:
-    def __init__(self, width, height, bit_depth=8, seed=1, qp=30, sao=True, ctb_log2=6, weighted=False, wpp=False, cip=False, tqb=0.0, tiles=None, lf_across_tiles=True, tskip=0.0, pcm=0.0, pcm_lf_off=False, slices=1, lf_across_slices=True, cfi=1, calm=0.0):
+    def __init__(self, width, height, bit_depth=8, seed=1, qp=30, sao=True, ctb_log2=6, weighted=False, wpp=False, cip=False, tqb=0.0, tiles=None, lf_across_tiles=True, tskip=0.0, pcm=0.0, pcm_lf_off=False, slices=1, lf_across_slices=True, cfi=1, calm=0.0, ccp=False):
         self.W, self.H, self.bd, self.qp, self.sao, self.ctb_log2 = width, height, bit_depth, qp, sao, ctb_log2
         self.weighted = weighted
         self.cip = cip                      # pps constrained_intra_pred_flag (hevcpred_template.c:116-249)
@@ -240,6 +240,8 @@ class StreamGen:
         self.slices, self.lf_across_slices = slices, lf_across_slices   # independent slices per picture, each starting a CTB row
         assert slices == 1 or not (tiles or wpp), "several slices are generated without tiles / WPP only"
         self.pcm, self.pcm_lf_off = pcm, pcm_lf_off   # share of 2Nx2N intra CUs (8x8 .. 32x32) coded as PCM; pcm_loop_filter_disabled_flag
+        self.ccp = ccp                      # pps cross_component_prediction_enabled_flag (4:4:4 only, hevc.c:1186-1197, 1295-1360)
+        assert not ccp or cfi == 3
         self.calm = calm                    # 0 = densely coded random content (default), 1 = lightly coded: more skipped / larger CUs, fewer and sparser residual blocks
         self.tskip = tskip                  # share of 4x4 TUs with transform_skip_flag (pps transform_skip_enabled_flag when > 0)
         self.cu_bypass = 0
@@ -342,7 +344,15 @@ class StreamGen:
         w.u(1, 0)                                                          # lists modification
         w.ue(0)                                                            # log2_parallel_merge_level - 2
         w.u(1, 0)                                                          # slice header extension
-        w.u(1, 0)                                                          # pps extension
+        if self.ccp:
+            w.u(1, 1); w.u(1, 1); w.u(7, 0)                                # pps_extension_present, pps_range_extensions_flag, 7 more (hevc_ps.c:2421-2423)
+            if self.tskip > 0:
+                w.ue(0)                                                    # log2_max_transform_skip_block_size_minus2
+            w.u(1, 1)                                                      # cross_component_prediction_enabled_flag
+            w.u(1, 0)                                                      # chroma_qp_offset_list_enabled_flag
+            w.ue(0); w.ue(0)                                               # log2_sao_offset_scale_luma / _chroma
+        else:
+            w.u(1, 0)                                                      # pps extension
         w.trailing()
         return nal(34, w.bytes())
 
@@ -753,17 +763,18 @@ class StreamGen:
             modes.append(int(mode))
             self.ipm[(y0 + dy) >> 2:(y0 + dy + pb) >> 2, (x0 + dx) >> 2:(x0 + dx + pb) >> 2] = mode
         table = [0, 26, 10, 1]
-        modes_c = []
+        modes_c, cms = [], []
         for m in (modes if self.cfi == 3 else modes[:1]):                   # 4:4:4: one intra_chroma_pred_mode per luma block (hevc.c:2270-2283)
             cm = int(r.integers(0, 5))                                     # intra_chroma_pred_mode (4 = derived from luma)
             c.encode(o["intra_chroma_pred_mode"], int(cm != 4))
             if cm != 4:
                 c.bypass_bits(2, cm)
             modes_c.append(m if cm == 4 else (34 if m == table[cm] else table[cm]))
+            cms.append(cm)
         mode_c = modes_c[0]
         if self.cfi == 2:
             mode_c = self.tab_mode_idx[mode_c]                              # 4:2:2: process of 8.4.3, table read from hevc.c:2252
-        self.modes_c = modes_c
+        self.modes_c, self.cms, self.cm_tu = modes_c, cms, cms[0]
         self.ct_depth[y0 >> 3:(y0 + size) >> 3, x0 >> 3:(x0 + size) >> 3] = depth
         self.transform_tree(x0, y0, log2, 0, 0, nxn, modes, mode_c, [0, 0], self.max_th_depth_intra + nxn, modes[0])
 
@@ -773,6 +784,7 @@ class StreamGen:
             mode = modes[blk]                                               # lc->tu.intra_pred_mode of this quadrant (hevc.c:1452)
             if self.cfi == 3:
                 mode_c = self.modes_c[blk]                                  # ... and its own chroma mode at 4:4:4 (hevc.c:1463-1465)
+                self.cm_tu = self.cms[blk]
         if log2 <= self.max_tb_log2 and log2 > self.min_tb_log2 and tdepth < max_depth and not (nxn and tdepth == 0):
             split = int(r.random() < 0.3)
             c.encode(o["split_transform_flag"] + 5 - log2, split)
@@ -820,10 +832,22 @@ class StreamGen:
             self.residual(log2, scan_of(mode, log2) if log2 < 4 else 0, 0)
         if chroma_here:
             log2_c = log2 if self.cfi == 3 else (log2 - 1 if log2 > 2 else 2)
+            # cross-component prediction (hevc.c:1295-1300): chroma residual += (res_scale_val * luma residual) >> 3
+            cross = bool(self.ccp and cbf_luma and (inter or self.cm_tu == 4))
             for k in range(2):                                              # Cb blocks, then Cr blocks (hevc.c:1302-1362)
+                if cross:
+                    v = int(r.choice([0, 1, 2, 3, 4], p=[0.2, 0.2, 0.2, 0.2, 0.2]))          # log2_res_scale_abs_plus1 (hevc_cabac.c:1056-1063)
+                    for i in range(v):
+                        c.encode(o["log2_res_scale_abs"] + 4 * k + i, 1)
+                    if v < 4:
+                        c.encode(o["log2_res_scale_abs"] + 4 * k + v, 0)
+                    if v:
+                        c.encode(o["res_scale_sign_flag"] + k, int(r.random() < 0.5))
                 for i in range(nblk):
                     if flags[k][i]:
                         self.residual(log2_c, scan_of(mode_c, log2) if log2 < 4 else 0, k + 1)
+                    elif cross:
+                        self.cnt["transform_add"] += 1                       # the scaled luma residual alone is added (hevc.c:1314-1329)
 
     def residual(self, log2, scan_idx, cidx):
         c, o, r = self.c, self.off, self.rng
@@ -1032,11 +1056,12 @@ def main():
     ap.add_argument("--tskip", type=float, default=0.0, help="share of 4x4 TUs coded with transform_skip_flag")
     ap.add_argument("--tiles", default="", help="COLSxROWS uniformly spaced tiles, e.g. 3x2")
     ap.add_argument("--no-lf-across-tiles", action="store_true", help="loop_filter_across_tiles_enabled_flag = 0")
+    ap.add_argument("--ccp", action="store_true", help="cross_component_prediction_enabled_flag (needs --cfi 3)")
     ap.add_argument("--calm", type=float, default=0.0, help="0 = dense random content (default) .. 1 = lightly coded (more skip, larger CUs, sparse residuals)")
     ap.add_argument("--wpp", action="store_true", help="entropy_coding_sync_enabled_flag: one substream per CTB row + entry points")
     a = ap.parse_args()
     verify_tables_against_reference()
-    g = StreamGen(a.width, a.height, a.bit_depth, a.seed, a.qp, sao=not a.no_sao, weighted=a.weighted, wpp=a.wpp, cip=a.cip, tqb=a.tqb, tskip=a.tskip, pcm=a.pcm, pcm_lf_off=a.pcm_lf_off, slices=a.slices, lf_across_slices=not a.no_lf_across_slices, cfi=a.cfi, calm=a.calm,
+    g = StreamGen(a.width, a.height, a.bit_depth, a.seed, a.qp, sao=not a.no_sao, weighted=a.weighted, wpp=a.wpp, cip=a.cip, tqb=a.tqb, tskip=a.tskip, pcm=a.pcm, pcm_lf_off=a.pcm_lf_off, slices=a.slices, lf_across_slices=not a.no_lf_across_slices, cfi=a.cfi, calm=a.calm, ccp=a.ccp,
                   tiles=tuple(int(v) for v in a.tiles.split("x")) if a.tiles else None, lf_across_tiles=not a.no_lf_across_tiles)
     data = g.stream(a.frames, a.pattern)
     open(a.out, "wb").write(data)
