@@ -27,7 +27,7 @@ def run(binary, stream, threads=1, env=None, want_stderr=False):
 # streams whose decoding reads s->is_pcm[] (transquant bypass, PCM with the loop filter off): the reference never clears that
 # array between pictures (hevc.c:147), so its own output depends on which pictures a context decoded before, i.e. on the
 # number of frame threads; the arbiter for such runs is the reference run the same way, not the committed single-thread MD5
-IS_PCM_STREAMS = ("tqb_", "pcm_416x240_10b_lfoff", "tskip_416x240_8b")
+IS_PCM_STREAMS = ("tqb_", "pcm_416x240_10b_lfoff", "tskip_416x240_8b", "ccp_416x240_8b_ra")
 REPEATED = [s for s in STREAMS if os.path.basename(s).startswith(("b_", "p_", "wpp_416", "tiles_416", "cip_416", "ra_416"))]
 WPP_STREAMS = [s for s in STREAMS if os.path.basename(s).startswith(("wpp_", "tiles_"))]      # streams with entry points: slice threads really run
 
