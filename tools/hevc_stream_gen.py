@@ -230,7 +230,7 @@ SIG_CTX_4x4 = [0, 1, 4, 5, 2, 3, 4, 5, 6, 6, 8, 8, 7, 7, 8, 8]
 
 
 class StreamGen:
-    def __init__(self, width, height, bit_depth=8, seed=1, qp=30, sao=True, ctb_log2=6, weighted=False, wpp=False, cip=False, tqb=0.0, tiles=None, lf_across_tiles=True, tskip=0.0, pcm=0.0, pcm_lf_off=False, slices=1, lf_across_slices=True, cfi=1, calm=0.0, ccp=False):
+    def __init__(self, width, height, bit_depth=8, seed=1, qp=30, sao=True, ctb_log2=6, weighted=False, wpp=False, cip=False, tqb=0.0, tiles=None, lf_across_tiles=True, tskip=0.0, pcm=0.0, pcm_lf_off=False, slices=1, lf_across_slices=True, cfi=1, calm=0.0, ccp=False, amp=False):
         self.W, self.H, self.bd, self.qp, self.sao, self.ctb_log2 = width, height, bit_depth, qp, sao, ctb_log2
         self.weighted = weighted
         self.cip = cip                      # pps constrained_intra_pred_flag (hevcpred_template.c:116-249)
@@ -240,6 +240,7 @@ class StreamGen:
         self.slices, self.lf_across_slices = slices, lf_across_slices   # independent slices per picture, each starting a CTB row
         assert slices == 1 or not (tiles or wpp), "several slices are generated without tiles / WPP only"
         self.pcm, self.pcm_lf_off = pcm, pcm_lf_off   # share of 2Nx2N intra CUs (8x8 .. 32x32) coded as PCM; pcm_loop_filter_disabled_flag
+        self.amp = amp                      # sps amp_enabled_flag: asymmetric motion partitions 2NxnU / 2NxnD / nLx2N / nRx2N above the minimum CB size
         self.ccp = ccp                      # pps cross_component_prediction_enabled_flag (4:4:4 only, hevc.c:1186-1197, 1295-1360)
         assert not ccp or cfi == 3
         self.calm = calm                    # 0 = densely coded random content (default), 1 = lightly coded: more skipped / larger CUs, fewer and sparser residual blocks
@@ -302,7 +303,7 @@ class StreamGen:
         w.ue(self.min_tb_log2 - 2); w.ue(self.max_tb_log2 - self.min_tb_log2)
         w.ue(2); w.ue(self.max_th_depth_intra)                             # max_transform_hierarchy_depth inter / intra
         w.u(1, 0)                                                          # scaling lists
-        w.u(1, 0)                                                          # amp
+        w.u(1, 1 if self.amp else 0)                                       # amp_enabled_flag
         w.u(1, 1 if self.sao else 0)                                       # sample_adaptive_offset_enabled
         w.u(1, int(self.pcm > 0))                                          # pcm_enabled_flag
         if self.pcm > 0:
@@ -703,11 +704,19 @@ class StreamGen:
             if not intra:
                 self.ipm[y0 >> 2:(y0 + size) >> 2, x0 >> 2:(x0 + size) >> 2] = 1
                 u = r.random()
-                part = 0 if u < 0.6 else (1 if u < 0.8 else 2)             # 2Nx2N, 2NxN, Nx2N (amp off, no inter NxN at 8x8)
+                part = 0 if u < 0.6 else (1 if u < 0.8 else 2)             # 2Nx2N, 2NxN, Nx2N (no inter NxN at 8x8)
                 c.encode(o["part_mode"], int(part == 0))
+                pus = {0: [(size, size)], 1: [(size, size // 2)] * 2, 2: [(size // 2, size)] * 2}[part]
                 if part:
                     c.encode(o["part_mode"] + 1, int(part == 1))
-                pus = {0: [(size, size)], 1: [(size, size // 2)] * 2, 2: [(size // 2, size)] * 2}[part]
+                    if self.amp and log2 > self.min_cb_log2:                # hevc_cabac.c:863-875
+                        asym = int(r.integers(0, 3))                       # 0 = symmetric, 1 = small part first (nU / nL), 2 = small part last (nD / nR)
+                        c.encode(o["part_mode"] + 3, int(asym == 0))
+                        if asym:
+                            c.bypass(int(asym == 2))
+                            q = size // 4
+                            a, b = (q, size - q) if asym == 1 else (size - q, q)
+                            pus = [(size, a), (size, b)] if part == 1 else [(a, size), (b, size)]
                 merge = 0
                 for (pw_, ph_) in pus:
                     merge = self.prediction_unit(pw_, ph_, depth, False)
@@ -1056,12 +1065,13 @@ def main():
     ap.add_argument("--tskip", type=float, default=0.0, help="share of 4x4 TUs coded with transform_skip_flag")
     ap.add_argument("--tiles", default="", help="COLSxROWS uniformly spaced tiles, e.g. 3x2")
     ap.add_argument("--no-lf-across-tiles", action="store_true", help="loop_filter_across_tiles_enabled_flag = 0")
+    ap.add_argument("--amp", action="store_true", help="amp_enabled_flag: asymmetric motion partitions")
     ap.add_argument("--ccp", action="store_true", help="cross_component_prediction_enabled_flag (needs --cfi 3)")
     ap.add_argument("--calm", type=float, default=0.0, help="0 = dense random content (default) .. 1 = lightly coded (more skip, larger CUs, sparse residuals)")
     ap.add_argument("--wpp", action="store_true", help="entropy_coding_sync_enabled_flag: one substream per CTB row + entry points")
     a = ap.parse_args()
     verify_tables_against_reference()
-    g = StreamGen(a.width, a.height, a.bit_depth, a.seed, a.qp, sao=not a.no_sao, weighted=a.weighted, wpp=a.wpp, cip=a.cip, tqb=a.tqb, tskip=a.tskip, pcm=a.pcm, pcm_lf_off=a.pcm_lf_off, slices=a.slices, lf_across_slices=not a.no_lf_across_slices, cfi=a.cfi, calm=a.calm, ccp=a.ccp,
+    g = StreamGen(a.width, a.height, a.bit_depth, a.seed, a.qp, sao=not a.no_sao, weighted=a.weighted, wpp=a.wpp, cip=a.cip, tqb=a.tqb, tskip=a.tskip, pcm=a.pcm, pcm_lf_off=a.pcm_lf_off, slices=a.slices, lf_across_slices=not a.no_lf_across_slices, cfi=a.cfi, calm=a.calm, ccp=a.ccp, amp=a.amp,
                   tiles=tuple(int(v) for v in a.tiles.split("x")) if a.tiles else None, lf_across_tiles=not a.no_lf_across_tiles)
     data = g.stream(a.frames, a.pattern)
     open(a.out, "wb").write(data)
