@@ -230,7 +230,7 @@ SIG_CTX_4x4 = [0, 1, 4, 5, 2, 3, 4, 5, 6, 6, 8, 8, 7, 7, 8, 8]
 
 
 class StreamGen:
-    def __init__(self, width, height, bit_depth=8, seed=1, qp=30, sao=True, ctb_log2=6, weighted=False, wpp=False, cip=False, tqb=0.0, tiles=None, lf_across_tiles=True, tskip=0.0, pcm=0.0, pcm_lf_off=False, slices=1, lf_across_slices=True, cfi=1, calm=0.0, ccp=False, amp=False):
+    def __init__(self, width, height, bit_depth=8, seed=1, qp=30, sao=True, ctb_log2=6, weighted=False, wpp=False, cip=False, tqb=0.0, tiles=None, lf_across_tiles=True, tskip=0.0, pcm=0.0, pcm_lf_off=False, slices=1, lf_across_slices=True, cfi=1, calm=0.0, ccp=False, amp=False, qpd=False):
         self.W, self.H, self.bd, self.qp, self.sao, self.ctb_log2 = width, height, bit_depth, qp, sao, ctb_log2
         self.weighted = weighted
         self.cip = cip                      # pps constrained_intra_pred_flag (hevcpred_template.c:116-249)
@@ -240,6 +240,8 @@ class StreamGen:
         self.slices, self.lf_across_slices = slices, lf_across_slices   # independent slices per picture, each starting a CTB row
         assert slices == 1 or not (tiles or wpp), "several slices are generated without tiles / WPP only"
         self.pcm, self.pcm_lf_off = pcm, pcm_lf_off   # share of 2Nx2N intra CUs (8x8 .. 32x32) coded as PCM; pcm_loop_filter_disabled_flag
+        self.qpd = qpd                      # pps cu_qp_delta_enabled_flag, one delta per 32x32 quantisation group (diff_cu_qp_delta_depth = log2_ctb - 5)
+        self.qp_coded = 1
         self.amp = amp                      # sps amp_enabled_flag: asymmetric motion partitions 2NxnU / 2NxnD / nLx2N / nRx2N above the minimum CB size
         self.ccp = ccp                      # pps cross_component_prediction_enabled_flag (4:4:4 only, hevc.c:1186-1197, 1295-1360)
         assert not ccp or cfi == 3
@@ -329,7 +331,9 @@ class StreamGen:
         w.se(0)                                                            # init_qp_minus26
         w.u(1, int(self.cip))                                              # constrained intra pred
         w.u(1, int(self.tskip > 0))                                        # transform skip (log2_max_transform_skip_block_size = 2)
-        w.u(1, 0)                                                          # cu_qp_delta
+        w.u(1, int(self.qpd))                                              # cu_qp_delta_enabled_flag
+        if self.qpd:
+            w.ue(max(self.ctb_log2 - 5, 0))                                # diff_cu_qp_delta_depth
         w.se(0); w.se(0)                                                   # cb / cr qp offsets
         w.u(1, 0)                                                          # slice chroma qp offsets present
         w.u(1, int(self.weighted)); w.u(1, int(self.weighted))             # weighted pred / bipred
@@ -566,6 +570,8 @@ class StreamGen:
     def quadtree(self, x0, y0, log2, depth):
         c, o = self.c, self.off
         size = 1 << log2
+        if self.qpd and log2 >= min(self.ctb_log2, 5):
+            self.qp_coded = 0                                               # new quantisation group (hevc.c:2525-2529)
         if x0 + size <= self.W and y0 + size <= self.H and log2 > self.min_cb_log2:
             inc = 0
             if self.left_ok(x0):
@@ -825,6 +831,15 @@ class StreamGen:
             cbf_luma = int(r.random() < 0.7 - 0.3 * self.calm)
             c.encode(o["cbf_luma"] + (1 if tdepth == 0 else 0), cbf_luma)
 
+        if self.qpd and not self.qp_coded and (cbf_luma or cbf_c[0][0] or cbf_c[1][0] or (self.cfi == 2 and (cbf_c[0][1] or cbf_c[1][1]))):
+            d = int(r.integers(-4, 5))                                      # cu_qp_delta_abs: prefix only (< 5), hevc_cabac.c:731-755
+            for i in range(abs(d)):
+                c.encode(o["cu_qp_delta"] + (1 if i else 0), 1)
+            c.encode(o["cu_qp_delta"] + (1 if d else 0), 0)
+            if d:
+                c.bypass(int(d < 0))                                        # cu_qp_delta_sign_flag
+            self.qp_coded = 1
+
         def scan_of(m, lg):
             if lg < 4 and not inter:
                 if 6 <= m <= 14:
@@ -1065,13 +1080,14 @@ def main():
     ap.add_argument("--tskip", type=float, default=0.0, help="share of 4x4 TUs coded with transform_skip_flag")
     ap.add_argument("--tiles", default="", help="COLSxROWS uniformly spaced tiles, e.g. 3x2")
     ap.add_argument("--no-lf-across-tiles", action="store_true", help="loop_filter_across_tiles_enabled_flag = 0")
+    ap.add_argument("--qpd", action="store_true", help="cu_qp_delta_enabled_flag: a QP delta per 32x32 quantisation group")
     ap.add_argument("--amp", action="store_true", help="amp_enabled_flag: asymmetric motion partitions")
     ap.add_argument("--ccp", action="store_true", help="cross_component_prediction_enabled_flag (needs --cfi 3)")
     ap.add_argument("--calm", type=float, default=0.0, help="0 = dense random content (default) .. 1 = lightly coded (more skip, larger CUs, sparse residuals)")
     ap.add_argument("--wpp", action="store_true", help="entropy_coding_sync_enabled_flag: one substream per CTB row + entry points")
     a = ap.parse_args()
     verify_tables_against_reference()
-    g = StreamGen(a.width, a.height, a.bit_depth, a.seed, a.qp, sao=not a.no_sao, weighted=a.weighted, wpp=a.wpp, cip=a.cip, tqb=a.tqb, tskip=a.tskip, pcm=a.pcm, pcm_lf_off=a.pcm_lf_off, slices=a.slices, lf_across_slices=not a.no_lf_across_slices, cfi=a.cfi, calm=a.calm, ccp=a.ccp, amp=a.amp,
+    g = StreamGen(a.width, a.height, a.bit_depth, a.seed, a.qp, sao=not a.no_sao, weighted=a.weighted, wpp=a.wpp, cip=a.cip, tqb=a.tqb, tskip=a.tskip, pcm=a.pcm, pcm_lf_off=a.pcm_lf_off, slices=a.slices, lf_across_slices=not a.no_lf_across_slices, cfi=a.cfi, calm=a.calm, ccp=a.ccp, amp=a.amp, qpd=a.qpd,
                   tiles=tuple(int(v) for v in a.tiles.split("x")) if a.tiles else None, lf_across_tiles=not a.no_lf_across_tiles)
     data = g.stream(a.frames, a.pattern)
     open(a.out, "wb").write(data)
