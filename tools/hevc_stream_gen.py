@@ -230,7 +230,7 @@ SIG_CTX_4x4 = [0, 1, 4, 5, 2, 3, 4, 5, 6, 6, 8, 8, 7, 7, 8, 8]
 
 
 class StreamGen:
-    def __init__(self, width, height, bit_depth=8, seed=1, qp=30, sao=True, ctb_log2=6, weighted=False, wpp=False, cip=False, tqb=0.0, tiles=None, lf_across_tiles=True, tskip=0.0, pcm=0.0, pcm_lf_off=False, slices=1, lf_across_slices=True, cfi=1, calm=0.0, ccp=False, amp=False, qpd=False):
+    def __init__(self, width, height, bit_depth=8, seed=1, qp=30, sao=True, ctb_log2=6, weighted=False, wpp=False, cip=False, tqb=0.0, tiles=None, lf_across_tiles=True, tskip=0.0, pcm=0.0, pcm_lf_off=False, slices=1, lf_across_slices=True, cfi=1, calm=0.0, ccp=False, amp=False, qpd=False, dbk_offsets=(0, 0), chroma_qp_offsets=(0, 0)):
         self.W, self.H, self.bd, self.qp, self.sao, self.ctb_log2 = width, height, bit_depth, qp, sao, ctb_log2
         self.weighted = weighted
         self.cip = cip                      # pps constrained_intra_pred_flag (hevcpred_template.c:116-249)
@@ -240,6 +240,7 @@ class StreamGen:
         self.slices, self.lf_across_slices = slices, lf_across_slices   # independent slices per picture, each starting a CTB row
         assert slices == 1 or not (tiles or wpp), "several slices are generated without tiles / WPP only"
         self.pcm, self.pcm_lf_off = pcm, pcm_lf_off   # share of 2Nx2N intra CUs (8x8 .. 32x32) coded as PCM; pcm_loop_filter_disabled_flag
+        self.dbk_offsets, self.chroma_qp_offsets = dbk_offsets, chroma_qp_offsets   # pps_beta_offset_div2 / pps_tc_offset_div2 (-6..6); pps_cb / cr_qp_offset (-12..12)
         self.qpd = qpd                      # pps cu_qp_delta_enabled_flag, one delta per 32x32 quantisation group (diff_cu_qp_delta_depth = log2_ctb - 5)
         self.qp_coded = 1
         self.amp = amp                      # sps amp_enabled_flag: asymmetric motion partitions 2NxnU / 2NxnD / nLx2N / nRx2N above the minimum CB size
@@ -334,7 +335,7 @@ class StreamGen:
         w.u(1, int(self.qpd))                                              # cu_qp_delta_enabled_flag
         if self.qpd:
             w.ue(max(self.ctb_log2 - 5, 0))                                # diff_cu_qp_delta_depth
-        w.se(0); w.se(0)                                                   # cb / cr qp offsets
+        w.se(self.chroma_qp_offsets[0]); w.se(self.chroma_qp_offsets[1])   # pps_cb_qp_offset / pps_cr_qp_offset
         w.u(1, 0)                                                          # slice chroma qp offsets present
         w.u(1, int(self.weighted)); w.u(1, int(self.weighted))             # weighted pred / bipred
         w.u(1, int(self.tqb > 0))                                          # transquant bypass
@@ -344,7 +345,11 @@ class StreamGen:
             w.u(1, 1)                                                      # uniform_spacing_flag
             w.u(1, int(self.lf_across_tiles))                              # loop_filter_across_tiles_enabled_flag
         w.u(1, 1)                                                          # loop filter across slices
-        w.u(1, 0)                                                          # deblocking filter control present
+        if self.dbk_offsets != (0, 0):
+            w.u(1, 1); w.u(1, 0); w.u(1, 0)                                # deblocking_filter_control_present, override_enabled = 0, pps_deblocking_filter_disabled = 0
+            w.se(self.dbk_offsets[0]); w.se(self.dbk_offsets[1])           # pps_beta_offset_div2, pps_tc_offset_div2 (hevc_ps.c:2354-2363)
+        else:
+            w.u(1, 0)                                                      # deblocking filter control present
         w.u(1, 0)                                                          # scaling list data
         w.u(1, 0)                                                          # lists modification
         w.ue(0)                                                            # log2_parallel_merge_level - 2
@@ -1080,6 +1085,8 @@ def main():
     ap.add_argument("--tskip", type=float, default=0.0, help="share of 4x4 TUs coded with transform_skip_flag")
     ap.add_argument("--tiles", default="", help="COLSxROWS uniformly spaced tiles, e.g. 3x2")
     ap.add_argument("--no-lf-across-tiles", action="store_true", help="loop_filter_across_tiles_enabled_flag = 0")
+    ap.add_argument("--dbk-offsets", default="0,0", help="pps_beta_offset_div2,pps_tc_offset_div2")
+    ap.add_argument("--chroma-qp-offsets", default="0,0", help="pps_cb_qp_offset,pps_cr_qp_offset")
     ap.add_argument("--qpd", action="store_true", help="cu_qp_delta_enabled_flag: a QP delta per 32x32 quantisation group")
     ap.add_argument("--amp", action="store_true", help="amp_enabled_flag: asymmetric motion partitions")
     ap.add_argument("--ccp", action="store_true", help="cross_component_prediction_enabled_flag (needs --cfi 3)")
@@ -1087,7 +1094,7 @@ def main():
     ap.add_argument("--wpp", action="store_true", help="entropy_coding_sync_enabled_flag: one substream per CTB row + entry points")
     a = ap.parse_args()
     verify_tables_against_reference()
-    g = StreamGen(a.width, a.height, a.bit_depth, a.seed, a.qp, sao=not a.no_sao, weighted=a.weighted, wpp=a.wpp, cip=a.cip, tqb=a.tqb, tskip=a.tskip, pcm=a.pcm, pcm_lf_off=a.pcm_lf_off, slices=a.slices, lf_across_slices=not a.no_lf_across_slices, cfi=a.cfi, calm=a.calm, ccp=a.ccp, amp=a.amp, qpd=a.qpd,
+    g = StreamGen(a.width, a.height, a.bit_depth, a.seed, a.qp, sao=not a.no_sao, weighted=a.weighted, wpp=a.wpp, cip=a.cip, tqb=a.tqb, tskip=a.tskip, pcm=a.pcm, pcm_lf_off=a.pcm_lf_off, slices=a.slices, lf_across_slices=not a.no_lf_across_slices, cfi=a.cfi, calm=a.calm, ccp=a.ccp, amp=a.amp, qpd=a.qpd, dbk_offsets=tuple(int(v) for v in a.dbk_offsets.split(",")), chroma_qp_offsets=tuple(int(v) for v in a.chroma_qp_offsets.split(",")),
                   tiles=tuple(int(v) for v in a.tiles.split("x")) if a.tiles else None, lf_across_tiles=not a.no_lf_across_tiles)
     data = g.stream(a.frames, a.pattern)
     open(a.out, "wb").write(data)
