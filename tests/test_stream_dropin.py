@@ -65,8 +65,15 @@ def test_reference_decoder_frame_threads(stream):
     assert run("decode_ref", stream, threads=4) == open(stream[:-5] + ".md5").read().splitlines()
 
 
+# frame threads on the GPU: one or two streams per feature (every stream runs with 4 frame threads in the CPU suite, recorder ->
+# oracle, tests/test_stream_oracle_cpu.py; here every run starts processes and CUDA contexts)
+THREADED = [s for s in STREAMS if os.path.basename(s).startswith((
+    "b_", "p_", "c3_", "i_416", "wpp_", "cip_416", "ra_", "tiles_832", "slices_416x240_10b", "tqb_416x240_10b", "pcm_416x240_10b", "tskip_416x240_8b",
+    "missing_", "c422_832", "c444_416x240_8b", "ccp_", "amp_416", "tmvp_416x240_10b", "calm_416", "qpd_416x240_10b"))]
+
+
 @pytest.mark.gpu
-@pytest.mark.parametrize("stream", STREAMS, ids=os.path.basename)
+@pytest.mark.parametrize("stream", THREADED, ids=os.path.basename)
 def test_hooked_decoder_with_frame_threads(stream):
     """4 frame threads: thread-local recorders, pictures reach the GPU in decode order through the shim's ticket.
     The arbiter is the unmodified reference run with the same thread count (on streams shorter than the thread
