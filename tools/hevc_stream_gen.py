@@ -230,7 +230,7 @@ SIG_CTX_4x4 = [0, 1, 4, 5, 2, 3, 4, 5, 6, 6, 8, 8, 7, 7, 8, 8]
 
 
 class StreamGen:
-    def __init__(self, width, height, bit_depth=8, seed=1, qp=30, sao=True, ctb_log2=6, weighted=False, wpp=False, cip=False, tqb=0.0, tiles=None, lf_across_tiles=True, tskip=0.0, pcm=0.0, pcm_lf_off=False, slices=1, lf_across_slices=True, cfi=1, calm=0.0, ccp=False, amp=False, qpd=False, dbk_offsets=(0, 0), chroma_qp_offsets=(0, 0), tmvp=False):
+    def __init__(self, width, height, bit_depth=8, seed=1, qp=30, sao=True, ctb_log2=6, weighted=False, wpp=False, cip=False, tqb=0.0, tiles=None, lf_across_tiles=True, tskip=0.0, pcm=0.0, pcm_lf_off=False, slices=1, lf_across_slices=True, cfi=1, calm=0.0, ccp=False, amp=False, qpd=False, dbk_offsets=(0, 0), chroma_qp_offsets=(0, 0), tmvp=False, no_dbk=False):
         self.W, self.H, self.bd, self.qp, self.sao, self.ctb_log2 = width, height, bit_depth, qp, sao, ctb_log2
         self.weighted = weighted
         self.cip = cip                      # pps constrained_intra_pred_flag (hevcpred_template.c:116-249)
@@ -241,6 +241,7 @@ class StreamGen:
         assert slices == 1 or not (tiles or wpp), "several slices are generated without tiles / WPP only"
         self.pcm, self.pcm_lf_off = pcm, pcm_lf_off   # share of 2Nx2N intra CUs (8x8 .. 32x32) coded as PCM; pcm_loop_filter_disabled_flag
         self.dbk_offsets, self.chroma_qp_offsets = dbk_offsets, chroma_qp_offsets   # pps_beta_offset_div2 / pps_tc_offset_div2 (-6..6); pps_cb / cr_qp_offset (-12..12)
+        self.no_dbk = no_dbk                # pps_deblocking_filter_disabled_flag: no deblocking at all (pictures without a deblock section)
         self.tmvp = tmvp                    # sps_temporal_mvp_enabled_flag: temporal merge / AMVP candidates from the collocated picture (host side only)
         self.qpd = qpd                      # pps cu_qp_delta_enabled_flag, one delta per 32x32 quantisation group (diff_cu_qp_delta_depth = log2_ctb - 5)
         self.qp_coded = 1
@@ -346,7 +347,9 @@ class StreamGen:
             w.u(1, 1)                                                      # uniform_spacing_flag
             w.u(1, int(self.lf_across_tiles))                              # loop_filter_across_tiles_enabled_flag
         w.u(1, 1)                                                          # loop filter across slices
-        if self.dbk_offsets != (0, 0):
+        if self.no_dbk:
+            w.u(1, 1); w.u(1, 0); w.u(1, 1)                                # deblocking_filter_control_present, override_enabled = 0, pps_deblocking_filter_disabled = 1
+        elif self.dbk_offsets != (0, 0):
             w.u(1, 1); w.u(1, 0); w.u(1, 0)                                # deblocking_filter_control_present, override_enabled = 0, pps_deblocking_filter_disabled = 0
             w.se(self.dbk_offsets[0]); w.se(self.dbk_offsets[1])           # pps_beta_offset_div2, pps_tc_offset_div2 (hevc_ps.c:2354-2363)
         else:
@@ -441,7 +444,8 @@ class StreamGen:
                 self.pred_weight_table(w)
             w.ue(5 - self.max_merge)                                       # five_minus_max_num_merge_cand
         w.se(self.qp - 26)                                                 # slice_qp_delta
-        w.u(1, int(self.lf_across_slices))                                 # slice_loop_filter_across_slices_enabled
+        if self.sao or not self.no_dbk:                                    # hevc.c:990-994
+            w.u(1, int(self.lf_across_slices))                             # slice_loop_filter_across_slices_enabled
         self.c = Cabac(self.init_rows[2 - slice_type], self.qp)
         self.substreams = []
         self.slice_data(ctb_start, ctb_end)
@@ -1097,6 +1101,7 @@ def main():
     ap.add_argument("--no-lf-across-tiles", action="store_true", help="loop_filter_across_tiles_enabled_flag = 0")
     ap.add_argument("--dbk-offsets", default="0,0", help="pps_beta_offset_div2,pps_tc_offset_div2")
     ap.add_argument("--chroma-qp-offsets", default="0,0", help="pps_cb_qp_offset,pps_cr_qp_offset")
+    ap.add_argument("--no-dbk", action="store_true", help="pps_deblocking_filter_disabled_flag")
     ap.add_argument("--tmvp", action="store_true", help="temporal motion vector prediction")
     ap.add_argument("--qpd", action="store_true", help="cu_qp_delta_enabled_flag: a QP delta per 32x32 quantisation group")
     ap.add_argument("--amp", action="store_true", help="amp_enabled_flag: asymmetric motion partitions")
@@ -1105,7 +1110,7 @@ def main():
     ap.add_argument("--wpp", action="store_true", help="entropy_coding_sync_enabled_flag: one substream per CTB row + entry points")
     a = ap.parse_args()
     verify_tables_against_reference()
-    g = StreamGen(a.width, a.height, a.bit_depth, a.seed, a.qp, sao=not a.no_sao, weighted=a.weighted, wpp=a.wpp, cip=a.cip, tqb=a.tqb, tskip=a.tskip, pcm=a.pcm, pcm_lf_off=a.pcm_lf_off, slices=a.slices, lf_across_slices=not a.no_lf_across_slices, cfi=a.cfi, calm=a.calm, ccp=a.ccp, amp=a.amp, qpd=a.qpd, tmvp=a.tmvp, dbk_offsets=tuple(int(v) for v in a.dbk_offsets.split(",")), chroma_qp_offsets=tuple(int(v) for v in a.chroma_qp_offsets.split(",")),
+    g = StreamGen(a.width, a.height, a.bit_depth, a.seed, a.qp, sao=not a.no_sao, weighted=a.weighted, wpp=a.wpp, cip=a.cip, tqb=a.tqb, tskip=a.tskip, pcm=a.pcm, pcm_lf_off=a.pcm_lf_off, slices=a.slices, lf_across_slices=not a.no_lf_across_slices, cfi=a.cfi, calm=a.calm, ccp=a.ccp, amp=a.amp, qpd=a.qpd, tmvp=a.tmvp, no_dbk=a.no_dbk, dbk_offsets=tuple(int(v) for v in a.dbk_offsets.split(",")), chroma_qp_offsets=tuple(int(v) for v in a.chroma_qp_offsets.split(",")),
                   tiles=tuple(int(v) for v in a.tiles.split("x")) if a.tiles else None, lf_across_tiles=not a.no_lf_across_tiles)
     data = g.stream(a.frames, a.pattern)
     open(a.out, "wb").write(data)
