@@ -230,7 +230,7 @@ SIG_CTX_4x4 = [0, 1, 4, 5, 2, 3, 4, 5, 6, 6, 8, 8, 7, 7, 8, 8]
 
 
 class StreamGen:
-    def __init__(self, width, height, bit_depth=8, seed=1, qp=30, sao=True, ctb_log2=6, weighted=False, wpp=False, cip=False, tqb=0.0, tiles=None, lf_across_tiles=True, tskip=0.0, pcm=0.0, pcm_lf_off=False, slices=1, lf_across_slices=True, cfi=1, calm=0.0, ccp=False, amp=False, qpd=False, dbk_offsets=(0, 0), chroma_qp_offsets=(0, 0), tmvp=False, no_dbk=False):
+    def __init__(self, width, height, bit_depth=8, seed=1, qp=30, sao=True, ctb_log2=6, weighted=False, wpp=False, cip=False, tqb=0.0, tiles=None, lf_across_tiles=True, tskip=0.0, pcm=0.0, pcm_lf_off=False, slices=1, lf_across_slices=True, cfi=1, calm=0.0, ccp=False, amp=False, qpd=False, dbk_offsets=(0, 0), chroma_qp_offsets=(0, 0), tmvp=False, no_dbk=False, sao_planes="both"):
         self.W, self.H, self.bd, self.qp, self.sao, self.ctb_log2 = width, height, bit_depth, qp, sao, ctb_log2
         self.weighted = weighted
         self.cip = cip                      # pps constrained_intra_pred_flag (hevcpred_template.c:116-249)
@@ -241,6 +241,7 @@ class StreamGen:
         assert slices == 1 or not (tiles or wpp), "several slices are generated without tiles / WPP only"
         self.pcm, self.pcm_lf_off = pcm, pcm_lf_off   # share of 2Nx2N intra CUs (8x8 .. 32x32) coded as PCM; pcm_loop_filter_disabled_flag
         self.dbk_offsets, self.chroma_qp_offsets = dbk_offsets, chroma_qp_offsets   # pps_beta_offset_div2 / pps_tc_offset_div2 (-6..6); pps_cb / cr_qp_offset (-12..12)
+        self.sao_planes = sao_planes        # slice_sao_luma_flag / slice_sao_chroma_flag: "both", "luma" or "chroma"
         self.no_dbk = no_dbk                # pps_deblocking_filter_disabled_flag: no deblocking at all (pictures without a deblock section)
         self.tmvp = tmvp                    # sps_temporal_mvp_enabled_flag: temporal merge / AMVP candidates from the collocated picture (host side only)
         self.qpd = qpd                      # pps cu_qp_delta_enabled_flag, one delta per 32x32 quantisation group (diff_cu_qp_delta_depth = log2_ctb - 5)
@@ -426,7 +427,7 @@ class StreamGen:
         if self.tmvp and not idr:
             w.u(1, 1)                                                      # slice_temporal_mvp_enabled_flag
         if self.sao:
-            w.u(1, 1); w.u(1, 1)                                           # slice_sao_luma / chroma
+            w.u(1, int(self.sao_planes != "chroma")); w.u(1, int(self.sao_planes != "luma"))   # slice_sao_luma_flag / slice_sao_chroma_flag
         if slice_type != 2:
             w.u(1, 1)                                                      # num_ref_idx_active_override_flag
             w.ue(nref - 1)
@@ -563,6 +564,8 @@ class StreamGen:
             if m:
                 return
         for cidx in range(2):                                              # Cr shares type / class with Cb
+            if (cidx == 0 and self.sao_planes == "chroma") or (cidx == 1 and self.sao_planes == "luma"):
+                continue                                                   # hevc.c:1133-1136: not applied, nothing coded
             t = int(r.choice([0, 1, 2], p=[0.3, 0.3, 0.4]))
             c.encode(o["sao_type_idx"], int(t != 0))
             if t:
@@ -1101,6 +1104,7 @@ def main():
     ap.add_argument("--no-lf-across-tiles", action="store_true", help="loop_filter_across_tiles_enabled_flag = 0")
     ap.add_argument("--dbk-offsets", default="0,0", help="pps_beta_offset_div2,pps_tc_offset_div2")
     ap.add_argument("--chroma-qp-offsets", default="0,0", help="pps_cb_qp_offset,pps_cr_qp_offset")
+    ap.add_argument("--sao-planes", default="both", choices=["both", "luma", "chroma"], help="which slice_sao_*_flag is set")
     ap.add_argument("--no-dbk", action="store_true", help="pps_deblocking_filter_disabled_flag")
     ap.add_argument("--tmvp", action="store_true", help="temporal motion vector prediction")
     ap.add_argument("--qpd", action="store_true", help="cu_qp_delta_enabled_flag: a QP delta per 32x32 quantisation group")
@@ -1110,7 +1114,7 @@ def main():
     ap.add_argument("--wpp", action="store_true", help="entropy_coding_sync_enabled_flag: one substream per CTB row + entry points")
     a = ap.parse_args()
     verify_tables_against_reference()
-    g = StreamGen(a.width, a.height, a.bit_depth, a.seed, a.qp, sao=not a.no_sao, weighted=a.weighted, wpp=a.wpp, cip=a.cip, tqb=a.tqb, tskip=a.tskip, pcm=a.pcm, pcm_lf_off=a.pcm_lf_off, slices=a.slices, lf_across_slices=not a.no_lf_across_slices, cfi=a.cfi, calm=a.calm, ccp=a.ccp, amp=a.amp, qpd=a.qpd, tmvp=a.tmvp, no_dbk=a.no_dbk, dbk_offsets=tuple(int(v) for v in a.dbk_offsets.split(",")), chroma_qp_offsets=tuple(int(v) for v in a.chroma_qp_offsets.split(",")),
+    g = StreamGen(a.width, a.height, a.bit_depth, a.seed, a.qp, sao=not a.no_sao, weighted=a.weighted, wpp=a.wpp, cip=a.cip, tqb=a.tqb, tskip=a.tskip, pcm=a.pcm, pcm_lf_off=a.pcm_lf_off, slices=a.slices, lf_across_slices=not a.no_lf_across_slices, cfi=a.cfi, calm=a.calm, ccp=a.ccp, amp=a.amp, qpd=a.qpd, tmvp=a.tmvp, no_dbk=a.no_dbk, sao_planes=a.sao_planes, dbk_offsets=tuple(int(v) for v in a.dbk_offsets.split(",")), chroma_qp_offsets=tuple(int(v) for v in a.chroma_qp_offsets.split(",")),
                   tiles=tuple(int(v) for v in a.tiles.split("x")) if a.tiles else None, lf_across_tiles=not a.no_lf_across_tiles)
     data = g.stream(a.frames, a.pattern)
     open(a.out, "wb").write(data)
