@@ -9,7 +9,8 @@
  *   ff_videodsp_init_b200  like ff_videodsp_init_x86 (libavcodec/videodsp.c:51-58, videodsp.h:94-97)
  *   b200_frame_begin       after hevc_frame_start() has chosen the DPB slot      (libavcodec/hevc.c:3245)
  *   b200_frame_end         when every CTB of the picture has been parsed and filtered (libavcodec/hevc.c:3447-3449, after tiles_filters)
- *   b200_frame_readback    before the picture is hashed or output                 (libavcodec/hevc.c:4145, 4178)
+ *   b200_frame_readback    when the packet has been decoded, before the picture is hashed or output (libavcodec/hevc.c:4141);
+ *                          frame == NULL: no complete picture came out of the packet -- an abandoned one is closed
  *   b200_frame_fill        when generate_missing_ref() has filled a grey reference  (libavcodec/hevc_refs.c:538-606)
  *   b200_host_pixels_unused  OPTIONAL, performance only: guard at the top of copy_CTB()  (libavcodec/hevc_filter.c:151-161) --
  *                          sao_filter_CTB copies every CTB between the host frame and sao_frame before it calls the SAO

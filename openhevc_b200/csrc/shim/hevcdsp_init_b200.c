@@ -86,6 +86,7 @@ typedef struct ShimThread {
     /* cross-component prediction (4:4:4 range extension): the owner's decoder context, this thread's local context (found by
      * the coefficient pointer), and the luma transform block the chroma blocks of the same TU refer to */
     HEVCContext *s; int ccp; HEVCLocalContext *lc;
+    int pic_cip, pic_tqb;                                /* the picture in progress needs the PU-type / is_pcm hand-over at its end */
     struct { int x, y, log2, kind, flags, cl, parked; uint32_t park; } last_y;
     uint8_t fill_slot[16]; int n_fill;                  /* generate_missing_ref (hevc_refs.c:538): grey references this picture needs */
 } ShimThread;
@@ -589,11 +590,16 @@ static void deactivate(void)                       /* the picture is no longer o
     pthread_mutex_unlock(&G.mu);
 }
 
+static void finish_abandoned(HEVCContext *s);
+static void picture_flags(HEVCContext *s);
+
 int b200_frame_begin(HEVCContext *s)
 {
     if (g.err) return g.err;
-    if (g.in_frame == 1) { deactivate(); ticket_release(); }   /* previous picture of this thread was abandoned */
+    if (g.in_frame == 1) finish_abandoned(s);                  /* previous picture of this thread was abandoned */
+    if (g.err) return g.err;
     g.in_frame = 0;
+    picture_flags(s);
     /* cross-component prediction (4:4:4): host arithmetic between two table calls, undone and redone on the device (rec_cross_component) */
     g.s = s; g.lc = NULL; g.last_y.log2 = 0;
     g.ccp = s->sps->chroma_array_type == 3 && s->pps->cross_component_prediction_enabled_flag;
@@ -630,7 +636,7 @@ int b200_frame_begin(HEVCContext *s)
 }
 
 
-int b200_frame_end(HEVCContext *s)
+static int frame_end_of(HEVCContext *s, HEVCFrame *ref)
 {
     if (g.in_frame != 1) return g.err ? g.err : B200_ESTATE;
     deactivate();                                   /* all execute2 jobs of the picture have returned (hevc.c:3087) */
@@ -644,20 +650,19 @@ int b200_frame_end(HEVCContext *s)
         w->in_frame = 0;
     }
     if (mrc) fail(mrc, "merging the worker threads' work lists failed");
-    if (!g.err && s->pps && s->pps->constrained_intra_pred_flag && s->ref && s->ref->tab_mvf) {
+    if (!g.err && g.pic_cip && ref && ref->tab_mvf) {
         /* the device applies the constrained-intra rules itself (hevcpred_template.c:116-249): hand it the PU types */
         const int pw = s->sps->min_pu_width, ph = s->sps->min_pu_height;
         uint8_t *map = malloc((size_t)pw * ph);
         if (!map) fail(B200_ENOMEM, "constrained_intra_pred map");
         else {
-            for (int i = 0; i < pw * ph; i++) map[i] = s->ref->tab_mvf[i].pred_flag == PF_INTRA;
+            for (int i = 0; i < pw * ph; i++) map[i] = ref->tab_mvf[i].pred_flag == PF_INTRA;
             int crc = b200_rec_set_cip(g.rec, s->sps->log2_min_pu_size, pw, ph, map);
             if (crc) fail(crc, "b200_rec_set_cip failed");
             free(map);
         }
     }
-    if (!g.err && s->sps->sao_enabled && s->is_pcm &&
-        (s->pps->transquant_bypass_enable_flag || (s->sps->pcm.loop_filter_disable_flag && s->sps->pcm_enabled_flag))) {
+    if (!g.err && g.pic_tqb && s->is_pcm) {
         /* restore_tqb_pixels (hevc_filter.c:163-193) is pixel work outside the tables: the device redoes it from is_pcm[] */
         int crc = b200_rec_set_tqb(g.rec, s->sps->log2_min_pu_size, s->sps->min_pu_width, s->sps->min_pu_height, s->is_pcm);
         if (crc) fail(crc, "b200_rec_set_tqb failed");
@@ -697,6 +702,29 @@ int b200_frame_end(HEVCContext *s)
     if (rc) fail(rc, G.ctx ? b200_last_error(G.ctx) : "frame_end failed");
     return rc;
 }
+static void picture_flags(HEVCContext *s)
+{
+    g.pic_cip = s->pps->constrained_intra_pred_flag;
+    g.pic_tqb = s->sps->sao_enabled && (s->pps->transquant_bypass_enable_flag || (s->sps->pcm.loop_filter_disable_flag && s->sps->pcm_enabled_flag));
+}
+int b200_frame_end(HEVCContext *s)
+{
+    picture_flags(s);                               /* the parameter sets of the picture that ends (at b200_frame_begin of the NEXT one they may have changed) */
+    return frame_end_of(s, s->ref);
+}
+
+static int readback_into(HEVCContext *s, AVFrame *frame);
+/* A picture that was begun but never ended (corrupt slice data).  It is finished with what was recorded -- the part the
+ * reference has reconstructed as well -- and copied into its host frame, which the decoder will still output. */
+static void finish_abandoned(HEVCContext *s)
+{
+    HEVCFrame *old = g.cur_slot >= 0 && g.cur_slot < 32 ? &s->DPB[g.cur_slot] : NULL;
+    if (!old || !old->frame || !old->frame->data[0] || old->frame->data[0] != g.cur_base[0]) {      /* the frame is gone: nothing to show */
+        deactivate(); ticket_release();
+        return;
+    }
+    if (!frame_end_of(s, old)) readback_into(s, old->frame);
+}
 
 /* hevc_refs.c:538-606 generate_missing_ref: a reference the stream does not contain is replaced by a grey picture the host
  * fills with memset; the device slot must hold the same.  Called while the RPS of the NEXT picture of this thread is set up
@@ -714,6 +742,22 @@ int b200_frame_fill(HEVCContext *s, HEVCFrame *frame)
 int b200_frame_readback(HEVCContext *s, AVFrame *frame)
 {
     if (g.err) return g.err;
+    if (!frame) {
+        /* The packet ended without a complete picture.  If one was begun, it was abandoned (corrupt slice data: hls_slice_data came
+         * back short of the picture, hevc.c:3444-3446, and decode_nal_unit swallowed the error).  It is finished here with what was
+         * recorded -- the part the reference has reconstructed as well -- for two reasons: the decoder may hand the frame to the
+         * application as soon as this call returns (low-delay output), and with frame threads the pictures behind it wait for its
+         * ticket in b200_frame_end while this thread only gets its next packet after one of THEM has been delivered: a dead lock
+         * unless the picture is closed now.  (Packets are access units: a picture never continues in the next packet.) */
+        if (!(g.in_frame == 1 && s->ref)) return 0;
+        const int rc = b200_frame_end(s);
+        if (rc) return rc;
+        frame = s->ref->frame;
+    }
+    return readback_into(s, frame);
+}
+static int readback_into(HEVCContext *s, AVFrame *frame)
+{
     if (G.dump_dir) return 0;                 /* record-only run: there is no device picture */
     int slot = -1;
     for (int i = 0; i < 32; i++) if (s->DPB[i].frame && s->DPB[i].frame->data[0] == frame->data[0]) slot = i;

@@ -21,11 +21,11 @@ sed -i -e "0,/^#include/s//$inc\n#include/" \
        -e 's/^\(\s*\)if (ARCH_X86) ff_hevcpred_init_x86(hpc, bit_depth);/&\n\1ff_hevcpred_init_b200(hpc, bit_depth);/' "$P/hevcpred.c"
 sed -i -e "0,/^#include/s//$inc\n#include/" \
        -e '/ff_videodsp_init_x86(ctx, bpc);/a\    ff_videodsp_init_b200(ctx, bpc);' "$P/videodsp.c"
-# frame life cycle (hevc.c:3271 / 3446 / 4145)
+# frame life cycle (hevc.c:3271 / 3446 / 4141: the read-back hook sits right behind decode_nal_units, before its result is looked at)
 sed -i -e "0,/^#include/s//$inc\n#include/" \
        -e 's/^\(\s*\)ff_thread_finish_setup(s->avctx);/\1if ((ret = b200_frame_begin(s)) < 0) goto fail;\n&/' \
        -e '/^\s*s->is_decoded = 1;/,/tiles_filters(s);/ s/^\(\s*\)tiles_filters(s);/&\n\1if ((ret = b200_frame_end(s)) < 0) goto fail;   \/* after the filters of tile threads *\//' \
-       -e 's|^\(\s*\)/\* verify the SEI checksum \*/|\1if (s->is_decoded \&\& s->ref) b200_frame_readback(s, s->ref->frame);\n&|' "$P/hevc.c"
+       -e 's|^\(\s*\)ret    = decode_nal_units(s, avpkt->data, avpkt->size);|&\n\1b200_frame_readback(s, s->is_decoded \&\& s->ref ? s->ref->frame : NULL);   /* NULL: no complete picture came out of the packet */|' "$P/hevc.c"
 # a reference picture the stream does not contain (hevc_refs.c:538-606 fills a grey frame on the host): the device slot gets the same fill
 sed -i -e "0,/^#include/s//$inc\n#include/" \
        -e '/^static HEVCFrame \*generate_missing_ref/,/^}/ s/^    return frame;/    b200_frame_fill(s, frame);\n&/' "$P/hevc_refs.c"

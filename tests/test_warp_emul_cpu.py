@@ -202,3 +202,39 @@ def test_tables_through_shim_on_the_emulated_kernels():
             "T.test_tables_through_shim_equal_reference_tables(192, 128, 2, 8, [1], dict(cip=True, p_intra=0.6))\n" % (ROOT, HERE))
     r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=900, env=dict(os.environ, LD_PRELOAD=EMUL))
     assert r.returncode == 0, r.stderr[-3000:]
+
+
+def corrupted_copy(stream, seed, path):
+    """three single-bit errors in the last two thirds of the file (slice data, occasionally a header)"""
+    import random
+    rnd = random.Random(seed)
+    data = bytearray(open(stream, "rb").read())
+    for _ in range(3):
+        data[rnd.randrange(len(data) // 3, len(data))] ^= 1 << rnd.randrange(8)
+    open(path, "wb").write(data)
+
+
+@needs_emul
+@pytest.mark.parametrize("threads", ["1", "4"])
+@pytest.mark.parametrize("seed", [1, 4, 0])
+def test_corrupted_stream_neither_hangs_nor_loses_pictures(tmp_path, seed, threads):
+    """Bit errors make the reference abandon a picture in the middle (hls_slice_data comes back short, the error is swallowed) and
+    carry on.  The drop-in must do the same: same number of pictures, no error, no dead lock -- with frame threads the pictures
+    behind an abandoned one wait for its ticket, so it is closed (with what was recorded: the part the reference reconstructed
+    too) when its packet ends (b200_frame_readback(s, NULL)).  Seeds 1 and 4 abandon a picture; before that
+    fix they hung with four frame threads.  Pictures decoded before the first damaged one must be identical; the damaged ones
+    differ only where neither decoder wrote anything (stale buffer contents)."""
+    if not os.path.exists(os.path.join(REFDIR, "decode_b200")):
+        pytest.skip("oracle/_ref/decode_b200 not built (needs /root/reference)")
+    stream = os.path.join(HERE, "golden", "streams", "b_416x240_10b_weighted.hevc")
+    bad = str(tmp_path / "corrupt.hevc")
+    corrupted_copy(stream, seed, bad)
+    ref = subprocess.run([os.path.join(REFDIR, "decode_ref"), bad, threads], capture_output=True, text=True, timeout=120)
+    want = [l for l in ref.stdout.splitlines() if l.startswith("frame ")]
+    got = decode_emulated(bad, threads)                      # asserts returncode 0; its own timeout catches a dead lock
+    assert len(got) == len(want)
+    clean = open(stream[:-5] + ".md5").read().splitlines()
+    n_clean = 0
+    while n_clean < len(want) and want[n_clean] == clean[n_clean]:
+        n_clean += 1
+    assert got[:n_clean] == want[:n_clean]
