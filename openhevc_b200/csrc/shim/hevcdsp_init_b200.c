@@ -57,6 +57,7 @@ static struct {
      * through the CPU oracle and compare with the unmodified decoder: the recorder + wire format + oracle, end to end. */
     const char *dump_dir;
     int dump_no, configured;
+    int in_flight;                      /* pictures begun whose packet has not ended yet (b200_frame_begin .. b200_frame_readback) */
 } G = { .mu = PTHREAD_MUTEX_INITIALIZER, .cv = PTHREAD_COND_INITIALIZER };
 
 /* per thread: the owner of a picture (the thread that runs hevc_frame_start .. the end of decode_nal_unit for it; with
@@ -86,6 +87,7 @@ typedef struct ShimThread {
     /* cross-component prediction (4:4:4 range extension): the owner's decoder context, this thread's local context (found by
      * the coefficient pointer), and the luma transform block the chroma blocks of the same TU refer to */
     HEVCContext *s; int ccp; HEVCLocalContext *lc;
+    int counted;                                         /* this thread's picture is part of G.in_flight */
     int pic_cip, pic_tqb;                                /* the picture in progress needs the PU-type / is_pcm hand-over at its end */
     struct { int x, y, log2, kind, flags, cl, parked; uint32_t park; } last_y;
     uint8_t fill_slot[16]; int n_fill;                  /* generate_missing_ref (hevc_refs.c:538): grey references this picture needs */
@@ -546,6 +548,10 @@ static int ensure_ctx(const HEVCContext *s)       /* called with G.mu held */
     G.dump_dir = getenv("B200_SHIM_DUMP");
     if (!((G.ctx || (G.dump_dir && G.configured)) && G.cfg.width == sps->width && G.cfg.height == sps->height && G.cfg.bit_depth == sps->bit_depth &&
           G.cfg.chroma_format_idc == sps->chroma_format_idc && G.cfg.log2_ctb_size == (int)sps->log2_ctb_size)) {
+        /* New geometry (a new SPS, hence an IRAP picture: nothing older is referenced any more).  With frame threads older pictures
+         * may still be parsing on other threads against the old context, plane sizes and sample width: wait until their packets
+         * have ended (they do not depend on this thread), then switch. */
+        while (G.in_flight > 0) pthread_cond_wait(&G.cv, &G.mu);
         G.gen++;
         if (G.ctx) { b200_ctx_destroy(G.ctx); G.ctx = NULL; }
         memset(&G.cfg, 0, sizeof(G.cfg));
@@ -605,7 +611,7 @@ int b200_frame_begin(HEVCContext *s)
     g.ccp = s->sps->chroma_array_type == 3 && s->pps->cross_component_prediction_enabled_flag;
     pthread_mutex_lock(&G.mu);
     const int erc = ensure_ctx(s);
-    if (!erc) g.ticket = G.next_ticket++;
+    if (!erc) { g.ticket = G.next_ticket++; G.in_flight++; g.counted = 1; }
     pthread_mutex_unlock(&G.mu);
     if (erc) return g.err;
     g.n_reg = 0;
@@ -739,7 +745,20 @@ int b200_frame_fill(HEVCContext *s, HEVCFrame *frame)
     return 0;
 }
 
+static int packet_end(HEVCContext *s, AVFrame *frame);
 int b200_frame_readback(HEVCContext *s, AVFrame *frame)
+{
+    const int rc = packet_end(s, frame);
+    if (g.counted) {                                /* this thread's picture no longer needs the context it was begun with */
+        pthread_mutex_lock(&G.mu);
+        g.counted = 0;
+        G.in_flight--;
+        pthread_cond_broadcast(&G.cv);
+        pthread_mutex_unlock(&G.mu);
+    }
+    return rc;
+}
+static int packet_end(HEVCContext *s, AVFrame *frame)
 {
     if (g.err) return g.err;
     if (!frame) {

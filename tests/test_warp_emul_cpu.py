@@ -238,3 +238,22 @@ def test_corrupted_stream_neither_hangs_nor_loses_pictures(tmp_path, seed, threa
     while n_clean < len(want) and want[n_clean] == clean[n_clean]:
         n_clean += 1
     assert got[:n_clean] == want[:n_clean]
+
+
+@needs_emul
+@pytest.mark.parametrize("threads", ["1", "4"])
+def test_geometry_change_in_mid_stream(tmp_path, threads):
+    """three streams back to back: 416x240 8-bit, 256x128 8-bit, 416x240 10-bit.  A new SPS means a new device context, plane
+    sizes and sample width; with frame threads the pictures of the old sequence are still being parsed on other threads when the
+    first picture of the new one begins, so the shim drains them first (G.in_flight)."""
+    if not os.path.exists(os.path.join(REFDIR, "decode_b200")):
+        pytest.skip("oracle/_ref/decode_b200 not built (needs /root/reference)")
+    names = ["p_416x240_8b", "i_256x128_8b_nosao", "b_416x240_10b_weighted"]
+    path = str(tmp_path / "concat.hevc")
+    with open(path, "wb") as f:
+        for n in names:
+            f.write(open(os.path.join(HERE, "golden", "streams", n + ".hevc"), "rb").read())
+    ref = subprocess.run([os.path.join(REFDIR, "decode_ref"), path, threads], capture_output=True, text=True, timeout=120)
+    want = [l for l in ref.stdout.splitlines() if l.startswith("frame ")]
+    assert len(want) == 13
+    assert decode_emulated(path, threads) == want
