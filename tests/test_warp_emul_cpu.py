@@ -257,3 +257,29 @@ def test_geometry_change_in_mid_stream(tmp_path, threads):
     want = [l for l in ref.stdout.splitlines() if l.startswith("frame ")]
     assert len(want) == 13
     assert decode_emulated(path, threads) == want
+
+
+def damaged(kind):
+    src = open(os.path.join(HERE, "golden", "streams", "ra_416x240_8b.hevc"), "rb").read()
+    if kind == "truncated":
+        return src[:int(len(src) * 0.7)]                                   # ends in the middle of a NAL unit
+    starts = [i for i in range(len(src) - 3) if src[i:i + 3] == b"\x00\x00\x01"]
+    units = [src[i:j] for i, j in zip(starts, starts[1:] + [len(src)])]
+    first_irap = next(k for k, u in enumerate(units) if (u[3] >> 1) & 0x3f in (19, 20))
+    return b"\x00" + b"".join(u for k, u in enumerate(units) if k != first_irap)     # the IDR picture is gone: every reference of the first GOP is missing
+
+
+@needs_emul
+@pytest.mark.parametrize("threads", ["1", "4"])
+@pytest.mark.parametrize("kind", ["truncated", "no_idr"])
+def test_damaged_streams_behave_like_the_reference(tmp_path, kind, threads):
+    """a stream cut off in the middle of a NAL unit, and one whose first picture was lost (the decoder generates grey references,
+    hevc_refs.c:538-606 -> b200_frame_fill): same pictures as the unmodified decoder, no error, no dead lock"""
+    if not os.path.exists(os.path.join(REFDIR, "decode_b200")):
+        pytest.skip("oracle/_ref/decode_b200 not built (needs /root/reference)")
+    path = str(tmp_path / (kind + ".hevc"))
+    open(path, "wb").write(damaged(kind))
+    ref = subprocess.run([os.path.join(REFDIR, "decode_ref"), path, threads], capture_output=True, text=True, timeout=120)
+    want = [l for l in ref.stdout.splitlines() if l.startswith("frame ")]
+    assert want
+    assert decode_emulated(path, threads) == want
