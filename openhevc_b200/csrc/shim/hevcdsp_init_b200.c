@@ -551,7 +551,7 @@ static int ensure_ctx(const HEVCContext *s)       /* called with G.mu held */
         /* New geometry (a new SPS, hence an IRAP picture: nothing older is referenced any more).  With frame threads older pictures
          * may still be parsing on other threads against the old context, plane sizes and sample width: wait until their packets
          * have ended (they do not depend on this thread), then switch. */
-        while (G.in_flight > 0) pthread_cond_wait(&G.cv, &G.mu);
+        while (G.in_flight > (g.counted ? 1 : 0)) pthread_cond_wait(&G.cv, &G.mu);      /* (this thread's own packet does not count) */
         G.gen++;
         if (G.ctx) { b200_ctx_destroy(G.ctx); G.ctx = NULL; }
         memset(&G.cfg, 0, sizeof(G.cfg));
@@ -611,7 +611,10 @@ int b200_frame_begin(HEVCContext *s)
     g.ccp = s->sps->chroma_array_type == 3 && s->pps->cross_component_prediction_enabled_flag;
     pthread_mutex_lock(&G.mu);
     const int erc = ensure_ctx(s);
-    if (!erc) { g.ticket = G.next_ticket++; G.in_flight++; g.counted = 1; }
+    if (!erc) {
+        g.ticket = G.next_ticket++;
+        if (!g.counted) { G.in_flight++; g.counted = 1; }      /* once per packet, however many pictures it starts */
+    }
     pthread_mutex_unlock(&G.mu);
     if (erc) return g.err;
     g.n_reg = 0;
