@@ -56,7 +56,7 @@ static struct {
      * nothing is sent to a GPU -- no device is needed, the decoder's output pictures stay untouched.  tests/ replay the dumps
      * through the CPU oracle and compare with the unmodified decoder: the recorder + wire format + oracle, end to end. */
     const char *dump_dir;
-    int dump_no, configured;
+    int dump_no, configured, env_read;
     int in_flight;                      /* pictures begun whose packet has not ended yet (b200_frame_begin .. b200_frame_readback) */
 } G = { .mu = PTHREAD_MUTEX_INITIALIZER, .cv = PTHREAD_COND_INITIALIZER };
 
@@ -499,13 +499,13 @@ static void rec_intra_5(HEVCContext *s, int x0, int y0, int c) { rec_intra(s, x0
 /* The host copies of the picture are dead once the tables record instead of computing: the one place where the reference
  * still moves whole CTBs of them around (copy_CTB in sao_filter_CTB, hevc_filter.c:151-161, 269, 305; 6 % of the hooked
  * decoder's CPU time on a dense 4K stream, 24 % on a lightly coded one) may skip the work. */
-static int g_tables_installed;
-int b200_host_pixels_unused(void) { return g_tables_installed; }
+static int g_tables_installed;          /* 0 -> 1 once, by whichever thread initialises its tables first */
+int b200_host_pixels_unused(void) { return __atomic_load_n(&g_tables_installed, __ATOMIC_RELAXED); }
 
 void ff_hevcdsp_init_b200(HEVCDSPContext *c, const int bit_depth)
 {
     (void)bit_depth;
-    g_tables_installed = 1;
+    __atomic_store_n(&g_tables_installed, 1, __ATOMIC_RELAXED);
     c->put_pcm = rec_put_pcm;
     c->transform_add[0] = rec_add4; c->transform_add[1] = rec_add8; c->transform_add[2] = rec_add16; c->transform_add[3] = rec_add32;
     c->transform_skip = rec_transform_skip;
@@ -545,7 +545,7 @@ void ff_videodsp_init_b200(VideoDSPContext *c, int bpc)
 static int ensure_ctx(const HEVCContext *s)       /* called with G.mu held */
 {
     const HEVCSPS *sps = s->sps;
-    G.dump_dir = getenv("B200_SHIM_DUMP");
+    if (!G.env_read) { G.dump_dir = getenv("B200_SHIM_DUMP"); G.env_read = 1; }     /* once, under G.mu: read without it afterwards */
     if (!((G.ctx || (G.dump_dir && G.configured)) && G.cfg.width == sps->width && G.cfg.height == sps->height && G.cfg.bit_depth == sps->bit_depth &&
           G.cfg.chroma_format_idc == sps->chroma_format_idc && G.cfg.log2_ctb_size == (int)sps->log2_ctb_size)) {
         /* New geometry (a new SPS, hence an IRAP picture: nothing older is referenced any more).  With frame threads older pictures
