@@ -80,6 +80,81 @@ def stream_mix():
     return mix
 
 
+# ---- the REAL decoder on a real Annex-B stream (BASELINE.json `metric`) --------------------------------------
+# oracle/_ref/decode_ref = the unmodified reference (pure-C build of /root/reference, headless main_hm/main.c) and
+# oracle/_ref/decode_b200 = the same decoder with the hook lines of INTEGRATION.md, pixel reconstruction on the GPU, both through
+# the public libOpenHevc* API: Annex-B bytes in, host frames out.  Streams: committed recipes (tools/make_bench_streams.sh).
+STREAM_DIR = os.path.join(ROOT, "oracle", "_ref", "streams")
+STREAMS = {  # name: what it is
+    "c3_4k_ra8_calm_65": "3840x2160 Main10 RA GOP 8, intra period 32, 65 pictures, lightly coded (~11 Mbit/s at 30 Hz: real-content bit rate)",
+    "c3_4k_ra8_mid_65": "3840x2160 Main10 RA GOP 8, 65 pictures, --calm 0.5",
+    "c3_4k_ra8_dense_33": "3840x2160 Main10 RA GOP 8, 33 pictures, dense random content (~110 Mbit/s: parse-bound worst case)",
+    "c2_1080p_ra8_65": "1920x1080 8-bit RA GOP 8, 65 pictures",
+    "c1_832x480_i_16": "832x480 8-bit all-intra, 16 pictures",
+}
+HEADLINE_STREAM = {"c3_4k_main10_ra": "c3_4k_ra8_calm_65", "c2_1080p_main_ra": "c2_1080p_ra8_65", "c1_832x480_main": "c1_832x480_i_16"}
+
+
+def run_decoder(binary, stream, threads, passes, env=None, timeout=900):
+    """one run of decode_ref / decode_b200 in timing mode (no MD5 work): the file is decoded `passes` times back to back by ONE
+    decoder instance; returns frames, wall seconds and the steady-state rate (passes 2..n: start-up excluded)"""
+    import re
+    r = subprocess.run([os.path.join(ROOT, "oracle", "_ref", binary), stream, str(threads), "time", str(passes)], capture_output=True, text=True,
+                       timeout=timeout, env=dict(os.environ, **(env or {})))
+    m = re.search(r"frames (\d+) time ([\d.]+) fps ([\d.]+) first_frame_s ([\d.]+) steady_fps ([\d.]+)", r.stdout)
+    if r.returncode or not m:
+        return {"error": (r.stderr or r.stdout)[-300:], "rc": r.returncode}
+    out = {"frames": int(m.group(1)), "sec": float(m.group(2)), "fps_incl_startup": float(m.group(3)), "first_pass_s": float(m.group(4)),
+           "steady_fps": float(m.group(5)), "passes": passes, "threads": threads}
+    rep = re.search(r"b200 shim: pictures (\d+) h2d_bytes (\d+) d2h_bytes (\d+)", r.stderr)     # B200_SHIM_REPORT=1
+    if rep and int(rep.group(1)):
+        out.update(h2d_bytes_per_picture=int(rep.group(2)) / int(rep.group(1)), d2h_bytes_per_picture=int(rep.group(3)) / int(rep.group(1)))
+    return out
+
+
+def decoder_md5_ok(binary, stream, threads, env=None):
+    """every output picture's plane MD5s equal the ones the unmodified decoder wrote (single thread) when the stream was made"""
+    want_path = stream[:-5] + ".md5"
+    if not os.path.exists(want_path):
+        return None
+    r = subprocess.run([os.path.join(ROOT, "oracle", "_ref", binary), stream, str(threads)], capture_output=True, text=True, timeout=900, env=dict(os.environ, **(env or {})))
+    got = [l for l in r.stdout.splitlines() if l.startswith("frame ")]
+    want = open(want_path).read().splitlines()
+    return r.returncode == 0 and got == want
+
+
+def stream_block(name, arms, threads_all, device, budget_s=2.5, with_single=True):
+    """fps of the arms ("reference", "b200") on one stream, 1 thread and `threads_all` frame threads.  Pass counts are chosen so
+    that every timed (steady) region lasts about budget_s or more."""
+    path = os.path.join(STREAM_DIR, name + ".hevc")
+    if not os.path.exists(path) or not os.path.exists(os.path.join(ROOT, "oracle", "_ref", "decode_ref")):
+        return {"unavailable": "stream or decoder binaries missing (tools/make_bench_streams.sh, __graft_entry__.build())"}
+    n = len(open(path[:-5] + ".md5").read().splitlines()) if os.path.exists(path[:-5] + ".md5") else 65
+    env = {"B200_DEVICE": str(device), "B200_SHIM_REPORT": "1"}
+    out = {"what": STREAMS.get(name, name), "bytes": os.path.getsize(path), "pictures": n, "host_threads": threads_all}
+    tset = sorted({1, threads_all}) if with_single else [threads_all]
+    for arm in arms:
+        binary = "decode_ref" if arm == "reference" else "decode_b200"
+        res = {}
+        for t in tset:
+            probe = run_decoder(binary, path, t, 2, env)
+            if "error" in probe:
+                res[f"threads_{t}"] = probe
+                continue
+            passes = int(min(64, max(2, 1 + budget_s * probe["steady_fps"] / n + 0.999)))
+            best = probe if passes <= 2 else run_decoder(binary, path, t, passes, env)
+            res[f"threads_{t}"] = best if "error" not in best else probe
+        if arm == "b200":
+            res["md5_equal_reference_decoder"] = {f"threads_{t}": decoder_md5_ok(binary, path, t, env) for t in tset}
+        out[arm] = res
+    try:
+        for t in tset:
+            out[f"speedup_threads_{t}"] = out["b200"][f"threads_{t}"]["steady_fps"] / out["reference"][f"threads_{t}"]["steady_fps"]
+    except Exception:
+        pass
+    return out
+
+
 class ClockSampler:
     Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
 
@@ -156,6 +231,16 @@ def run_reference(args, wl, rank):
         stages = {k: {"ms_per_picture_one_core": 1e3 * v / n} for k, v in oracle_lib.ref_bench_stages().items()}
     except Exception:
         stages = None
+    e2e = {"value": fps, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0, "what": "replay of the work lists (no stream available)"}
+    sb = None
+    hs = HEADLINE_STREAM.get(args.workload)
+    if hs and not args.no_stream:
+        sb = stream_block(hs, ["reference"], threads, 0, with_single=False)
+        try:
+            e2e = {"value": sb["reference"][f"threads_{threads}"]["steady_fps"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0,
+                   "what": f"unmodified reference decoder (oracle/_ref/decode_ref) on {hs}.hevc, {threads} frame threads, Annex-B bytes in, frames out"}
+        except Exception:
+            pass
     line = {"metric": METRIC, "value": fps, "unit": UNIT, "impl": "reference", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": 1e3 * sec / max(1, n / 8), "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u16" if wl["bit_depth"] > 8 else "u8",
             "data": "synthetic", "config": {"workload": args.workload, "gop": "hierarchical-B 8, intra period 32", "pictures_timed": n},
@@ -163,7 +248,7 @@ def run_reference(args, wl, rank):
             "cpu_baseline": {"value": fps, "unit": UNIT, "cores": threads, "kind": "reference",
                              "sample": f"{n} pictures of the bench stream mix, {threads} threads x {it} pictures, reference C tables (-O3 -fno-tree-vectorize, no asm)",
                              "stages": stages},
-            "e2e": {"value": fps, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+            "e2e": e2e, "stream_e2e": sb}
     print(json.dumps(line), file=_REAL_STDOUT, flush=True)
 
 
@@ -184,6 +269,8 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="c3_4k_main10_ra", choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-stream", action="store_true", help="skip the real-decoder stream block (e2e falls back to the work-list replay)")
+    ap.add_argument("--streams", default="headline,mid,dense", help="which streams the stream_e2e block decodes")
     args = ap.parse_args()
     wl = WORKLOADS[args.workload]
     rank, world, local = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1)), int(os.environ.get("LOCAL_RANK", 0))
@@ -324,8 +411,6 @@ def main():
     e2e_fps = e2e_steps * 8 * world / float(w1.item())
     h2d = sum(blobs[b].nbytes * mix[b] for b in mix) / npic_mix * 8
     d2h = sum(int(np.prod(eng.plane_shape(p))) for p in range(3)) * B * 8
-    for b in range(FP.N_BLOBS):                  # e2e rotated the arenas: restore nothing needed, blobs are re-uploaded on demand
-        pass
 
     # ---- CPU baseline: the reference's own C path on this box's host cores (rank 0, N=1 only) --------------------
     cpu = None
@@ -353,6 +438,34 @@ def main():
         except Exception as ex:                  # the baseline is a report, never a reason to lose the bench line
             cpu = {"value": None, "unit": UNIT, "cores": 0, "kind": "reference", "sample": f"failed: {ex}"}
 
+    # ---- the real decoder on real streams: THE end-to-end number (BASELINE.json metric: decoded fps vs the reference CPU decoder) ----
+    # Every rank decodes the stream on its own GPU with its share of the host cores (replicas: the host parse is what limits it).
+    e2e_replay = {"value": e2e_fps, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h), "steps": e2e_steps,
+                  "mpixels_per_s": e2e_fps * wl["width"] * wl["height"] / 1e6,
+                  "what": "work-list replay: pinned host blob -> H2D -> K0..K5 -> D2H of every picture through the C ABI (no parse)"}
+    e2e_line, stream_e2e = dict(e2e_replay), None
+    hs = HEADLINE_STREAM.get(args.workload)
+    if hs and not args.no_stream:
+        eng.sync()
+        threads_all = max(1, usable_cpus() // world)
+        mine = stream_block(hs, ["b200"] if world > 1 else ["reference", "b200"], threads_all, local, with_single=(world == 1))
+        sfps = torch.tensor([mine.get("b200", {}).get(f"threads_{threads_all}", {}).get("steady_fps", 0.0) or 0.0], device=f"cuda:{local}", dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(sfps, op=dist.ReduceOp.SUM)
+        stream_e2e = {hs: mine}
+        if rank == 0 and world == 1:
+            for tag, nm in (("mid", "c3_4k_ra8_mid_65"), ("dense", "c3_4k_ra8_dense_33")):
+                if tag in args.streams.split(",") and args.workload == "c3_4k_main10_ra":
+                    stream_e2e[nm] = stream_block(nm, ["reference", "b200"], threads_all, local, budget_s=1.5, with_single=False)
+        if float(sfps.item()) > 0:
+            b = mine["b200"][f"threads_{threads_all}"]
+            e2e_line = {"value": float(sfps.item()), "unit": UNIT,
+                        "h2d_bytes_per_step": int(8 * b.get("h2d_bytes_per_picture", 0)), "d2h_bytes_per_step": int(8 * b.get("d2h_bytes_per_picture", 0)),
+                        "mpixels_per_s": float(sfps.item()) * wl["width"] * wl["height"] / 1e6,
+                        "what": f"hooked reference decoder (oracle/_ref/decode_b200: CABAC parse on {threads_all} host frame threads per GPU, pixel path on the GPU) on {hs}.hevc: "
+                                "Annex-B bytes in, every picture read back to pinned host frames; steady state of one decoder instance (first pass excluded)",
+                        "md5_equal_reference_decoder": mine["b200"].get("md5_equal_reference_decoder")}
+
     if rank == 0:
         line = {"metric": METRIC, "value": fps, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
                 "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -362,8 +475,7 @@ def main():
                            "l2": "inputs larger than L2: 9 work lists (%.0f MB) + %d-slot DPB (%.0f MB) cycled" % (sum(b.nbytes for b in blobs) / 1e6, FP.N_SLOTS, FP.N_SLOTS * slot_bytes / 1e6)},
                 "mpixels_per_s": fps * wl["width"] * wl["height"] / 1e6,
                 "gpu_launches": int(launches), "clocks": clocks,
-                "e2e": {"value": e2e_fps, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h), "steps": e2e_steps,
-                        "mpixels_per_s": e2e_fps * wl["width"] * wl["height"] / 1e6},
+                "e2e": e2e_line, "e2e_replay": e2e_replay, "stream_e2e": stream_e2e,
                 "roofline": roofline, "cpu_baseline": cpu,
                 "nccl_bcast_bytes_per_step": int(slot_bytes) if world > 1 else 0}
         print(json.dumps(line), file=_REAL_STDOUT, flush=True)

@@ -34,6 +34,13 @@ extern "C" {
 typedef struct B200Ctx B200Ctx;
 typedef struct B200Rec B200Rec;
 
+/* Threading contract.  A B200Ctx is driven by ONE submitting thread at a time: every call that takes a B200Ctx and is not
+ * listed below mutates un-locked context state (slot hazards, arenas, lanes) and must come from that thread, pictures in
+ * decode order (the table-level shim runs a dedicated submission thread for exactly this reason).  Callable from ANY
+ * thread, concurrently with the submitting thread: b200_upload_wait, b200_readback_wait (they touch an immutable event
+ * handle only), b200_last_error, the b200_host_* functions and every b200_rec_* function (a B200Rec belongs to the thread
+ * that records into it).  b200_ctx_create / b200_ctx_destroy are serialised internally. */
+
 typedef struct B200Config {
     int32_t device;             /* CUDA device ordinal                                               */
     int32_t width, height;      /* luma samples: sps->width / sps->height (libavcodec/hevc.h)        */
@@ -68,6 +75,8 @@ int         b200_slot_end_access(B200Ctx *ctx, int slot, void *stream, int write
 /* ---- pinned host memory for blobs / frames ---------------------------------------------------- */
 void *b200_host_alloc(uint64_t bytes);
 void  b200_host_free(void *p);
+int   b200_host_register(void *p, uint64_t bytes);         /* page-lock memory the caller allocated (cudaHostRegister) */
+int   b200_host_unregister(void *p);
 
 /* ---- per-frame execution ---------------------------------------------------------------------- */
 /* Upload `blob` (include/b200hevc_worklist.h) into arena `arena` on the copy stream (asynchronous when the blob
@@ -80,11 +89,21 @@ int b200_frame_execute(B200Ctx *ctx, int arena);
 int b200_frame_execute_ex(B200Ctx *ctx, int arena, int cur_slot, const uint8_t *ref_slots, int n_ref);
 /* upload + execute, arenas used round-robin: the call the recorder's frame_end makes (hevc.c:3446). */
 int b200_frame_submit(B200Ctx *ctx, const void *blob, uint64_t nbytes);
+/* Same; *upload_token names the upload so that the owner of `blob` -- possibly another thread -- can wait until the blob
+ * has left host memory (b200_upload_wait) before it writes the next picture into the same memory. */
+int b200_frame_submit_ex(B200Ctx *ctx, const void *blob, uint64_t nbytes, uint32_t *upload_token);
+int b200_upload_wait(B200Ctx *ctx, uint32_t upload_token);   /* any thread */
 
 /* Planes are exchanged in the reference's AVFrame layout: planar, uint8 samples for 8-bit,
  * little-endian uint16 above; strides in bytes.  (libavcodec/hevc_ps.c:1666-1688) */
 int b200_slot_upload(B200Ctx *ctx, int slot, const void *const planes[3], const int64_t strides[3]);
 int b200_slot_readback(B200Ctx *ctx, int slot, void *const planes[3], const int64_t strides[3]); /* async after the slot's last writer */
+/* read-back another thread will wait for (the decoder's output path, hevc_refs.c:182-307: a picture leaves the decoder long
+ * after it was decoded): asynchronous like b200_slot_readback, *token names its completion for b200_readback_wait */
+int b200_slot_readback_async(B200Ctx *ctx, int slot, void *const planes[3], const int64_t strides[3], uint32_t *token);
+int b200_readback_wait(B200Ctx *ctx, uint32_t token);        /* any thread; host blocks until that read-back has landed */
+int b200_poll_errors(B200Ctx *ctx);                          /* device-side error latches (rejected work list, intra dependency time-out)
+                                                                WITHOUT synchronising: 0 or the error b200_sync would report */
 int b200_slot_wait_readback(B200Ctx *ctx, int slot);         /* host blocks until the slot's last read-back has landed (not for the whole queue) */
 int b200_slot_fill(B200Ctx *ctx, int slot, int value);    /* generate_missing_ref, hevc_refs.c:538-606 */
 int b200_wait_uploads(B200Ctx *ctx);                       /* wait until submitted blobs have left host memory (not for the kernels) */

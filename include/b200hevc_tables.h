@@ -11,6 +11,11 @@
  *   b200_frame_end         when every CTB of the picture has been parsed and filtered (libavcodec/hevc.c:3447-3449, after tiles_filters)
  *   b200_frame_readback    when the packet has been decoded, before the picture is hashed or output (libavcodec/hevc.c:4141);
  *                          frame == NULL: no complete picture came out of the packet -- an abandoned one is closed
+ *   b200_output_wait       where hevc_decode_frame hands a picture to its caller (libavcodec/hevc.c:4177-4180, and the flush path
+ *                          :4116): the read-back of a picture is issued with the picture and only waited for here -- a picture
+ *                          leaves the decoder long after it was decoded (bumping, hevc_refs.c:182-307)
+ *   b200_frame_buffer_alloc  allocator for the decoder's frame pool in place of av_buffer_allocz (libavcodec/utils.c:558-561):
+ *                          picture planes in page-locked memory, so that read-backs are asynchronous DMAs at full PCIe rate
  *   b200_frame_fill        when generate_missing_ref() has filled a grey reference  (libavcodec/hevc_refs.c:538-606)
  *   b200_host_pixels_unused  OPTIONAL, performance only: guard at the top of copy_CTB()  (libavcodec/hevc_filter.c:151-161) --
  *                          sao_filter_CTB copies every CTB between the host frame and sao_frame before it calls the SAO
@@ -35,6 +40,7 @@ struct VideoDSPContext;
 struct HEVCContext;
 struct AVFrame;
 struct HEVCFrame;
+struct AVBufferRef;
 
 void ff_hevcdsp_init_b200(struct HEVCDSPContext *c, const int bit_depth);
 void ff_hevcpred_init_b200(struct HEVCPredContext *c, const int bit_depth);
@@ -43,6 +49,8 @@ void ff_videodsp_init_b200(struct VideoDSPContext *c, int bpc);
 int  b200_frame_begin(struct HEVCContext *s);
 int  b200_frame_end(struct HEVCContext *s);
 int  b200_frame_readback(struct HEVCContext *s, struct AVFrame *frame);
+int  b200_output_wait(struct HEVCContext *s, struct AVFrame *frame);        /* the frame leaves the decoder: its pixels have landed when this returns */
+struct AVBufferRef *b200_frame_buffer_alloc(int size);                      /* frame-pool allocator: pinned host memory */
 int  b200_frame_fill(struct HEVCContext *s, struct HEVCFrame *frame);       /* grey reference picture (generate_missing_ref) */
 int  b200_frame_upload_ref(struct HEVCContext *s, struct AVFrame *frame);   /* host-only reference picture -> device slot */
 int  b200_host_pixels_unused(void);                                         /* 1 once the B200 tables are installed */

@@ -19,6 +19,7 @@ EXPORTS = [  # every symbol include/b200hevc.h declares
     "b200_stream", "b200_join", "b200_slot_begin_access", "b200_slot_end_access", "b200_host_alloc", "b200_host_free", "b200_frame_upload", "b200_frame_execute", "b200_frame_execute_ex", "b200_frame_submit",
     "b200_slot_upload", "b200_slot_readback", "b200_slot_wait_readback", "b200_slot_fill", "b200_wait_uploads", "b200_sync", "b200_set_profiling", "b200_get_stage_ms",
     "b200_launch_count", "b200_rec_create", "b200_rec_destroy", "b200_rec_begin", "b200_rec_set_refs", "b200_rec_tu", "b200_rec_pcm",
+    "b200_host_register", "b200_host_unregister", "b200_frame_submit_ex", "b200_upload_wait", "b200_slot_readback_async", "b200_readback_wait", "b200_poll_errors",
     "b200_rec_intra", "b200_rec_mc", "b200_rec_deblock", "b200_rec_sao", "b200_rec_set_cip", "b200_rec_set_tqb", "b200_rec_tu_parked", "b200_rec_ccp", "b200_rec_merge", "b200_rec_finish", "b200_intra_level_order",
 ]
 
@@ -37,6 +38,13 @@ def load():
         "b200_slot_bytes": (u64, [vp]),
         "b200_slot_devptr": (vp, [vp, i32, i32, C.POINTER(u64)]),
         "b200_stream": (vp, [vp]),
+        "b200_host_register": (i32, [vp, u64]),
+        "b200_host_unregister": (i32, [vp]),
+        "b200_frame_submit_ex": (i32, [vp, vp, u64, C.POINTER(C.c_uint32)]),
+        "b200_upload_wait": (i32, [vp, C.c_uint32]),
+        "b200_slot_readback_async": (i32, [vp, i32, C.POINTER(vp), C.POINTER(i64), C.POINTER(C.c_uint32)]),
+        "b200_readback_wait": (i32, [vp, C.c_uint32]),
+        "b200_poll_errors": (i32, [vp]),
         "b200_join": (i32, [vp]),
         "b200_slot_begin_access": (i32, [vp, i32, vp, i32]),
         "b200_slot_end_access": (i32, [vp, i32, vp, i32]),

@@ -31,10 +31,12 @@
 #define RD_DOWN MAX_LANES            // reader index of the read-back stream
 #define RD_EXT (MAX_LANES + 1)       // reader index of caller-owned streams (b200_slot_end_access)
 #define N_RD (MAX_LANES + 2)
+#define RB_RING 64
 
 struct Arena {
     uint8_t *dev = nullptr;
     uint8_t *stage = nullptr;       // pinned staging for blobs that are not in pinned memory
+    uint64_t stage_bytes = 0;
     B200CipHeader cip_hdr = {};     // host copy of the resident blob's CIP section header (constrained_intra_pred pictures)
     B200CipHeader tqb_hdr = {};     // ... and of its TQB section header (restore_tqb_pixels)
     B200BlobHeader hdr;             // host copy of the resident blob's header
@@ -81,6 +83,12 @@ struct B200Ctx {
     cudaEvent_t prof[B200_ST_COUNT + 1];
     bool profiling = false, prof_valid = false;
     uint64_t launches = 0;
+    // read-backs whose completion other threads wait for (b200_readback_wait): a ring of events on the read-back stream
+    cudaEvent_t rb_ev[RB_RING] = {};
+    uint32_t rb_next = 0;
+    // device-side error latches mirrored in mapped host memory (one word per lane): readable without a synchronisation
+    volatile uint32_t *err_host = nullptr;
+    uint32_t *err_dev = nullptr;
     B200DbkLayout dbk;
     int ctb_w, ctb_h;
     char err[512];
@@ -121,16 +129,7 @@ static void geometry(const B200Config *c, int pw[3], int ph[3], int pitch[3], si
     *slot_bytes = o;
 }
 
-static uint64_t worst_blob_bytes(const B200Config *c)
-{
-    // every sample coded (int16) + a record per 4x4 of every list + grids + slack
-    uint64_t samples = 0;
-    for (int p = 0; p < 3; p++) { int w, h; b200_plane_dims(c->width, c->height, c->chroma_format_idc, p, &w, &h); samples += (uint64_t)w * h; }
-    B200DbkLayout L;
-    b200_dbk_layout(c->width, c->height, c->chroma_format_idc, &L);
-    const uint64_t u = samples / 16;
-    return 4096 + samples * 2 + u * (16 + 16 + 32) + (uint64_t)L.total * 2 + (1u << 20);
-}
+extern "C" uint64_t b200_worst_blob_bytes(const B200Config *c);      // recorder.cpp: the one definition of the largest blob of a geometry
 
 static bool config_ok(const B200Config *c)
 {
@@ -256,6 +255,8 @@ extern "C" void b200_ctx_destroy(B200Ctx *ctx)
         for (int l = 0; l < N_RD; l++) if (ctx->slot[i].rd[l]) cudaEventDestroy(ctx->slot[i].rd[l]);
     }
     for (int i = 0; i <= B200_ST_COUNT; i++) if (ctx->prof[i]) cudaEventDestroy(ctx->prof[i]);
+    for (int i = 0; i < RB_RING; i++) if (ctx->rb_ev[i]) cudaEventDestroy(ctx->rb_ev[i]);
+    if (ctx->err_host) cudaFreeHost((void *)ctx->err_host);
     if (ctx->own_dpb && ctx->dpb) cudaFree(ctx->dpb);
     if (ctx->dpb_desc_dev) cudaFree(ctx->dpb_desc_dev);
     for (int l = 0; l < MAX_LANES; l++) {
@@ -299,7 +300,7 @@ static int ctx_init(B200Ctx *ctx)
     for (int s = 0; s < c.n_slots; s++) describe(ctx->slot_desc[s], ctx->dpb + (size_t)s * ctx->slot_bytes);
     CU(cudaMalloc(&ctx->dpb_desc_dev, sizeof(FrameDesc) * c.n_slots));
     CU(cudaMemcpy(ctx->dpb_desc_dev, ctx->slot_desc, sizeof(FrameDesc) * c.n_slots, cudaMemcpyHostToDevice));
-    ctx->arena_bytes = c.max_blob_bytes ? c.max_blob_bytes : worst_blob_bytes(&c);
+    ctx->arena_bytes = c.max_blob_bytes ? c.max_blob_bytes : b200_worst_blob_bytes(&c);
     ctx->arena_bytes = (ctx->arena_bytes + 4095) & ~(uint64_t)4095;
     ctx->n_lanes = c.n_lanes > 0 ? c.n_lanes : 8;
     if (const char *e = getenv("B200_LANES")) if (atoi(e) > 0) ctx->n_lanes = atoi(e);
@@ -307,6 +308,15 @@ static int ctx_init(B200Ctx *ctx)
     ctx->trace_path = getenv("B200_TRACE");
     if (ctx->trace_path) ctx->trace.reserve(4096);      // TraceRec pointers stay valid while a picture is being submitted
     for (int p = 0; p < 3; p++) ctx->flag_stride[p] = (ctx->pw[p] + 3) / 4 + 1;
+    {   // one error word per lane in mapped host memory: kernels store to it on their (rare) error paths, the host polls it
+        void *eh = nullptr, *ed = nullptr;
+        CU(cudaHostAlloc(&eh, 256, cudaHostAllocMapped));
+        memset(eh, 0, 256);
+        ctx->err_host = (volatile uint32_t *)eh;
+        CU(cudaHostGetDevicePointer(&ed, eh, 0));
+        ctx->err_dev = (uint32_t *)ed;
+    }
+    for (int i = 0; i < RB_RING; i++) CU(cudaEventCreateWithFlags(&ctx->rb_ev[i], cudaEventDisableTiming));
     for (int l = 0; l < ctx->n_lanes; l++) {
         Lane &L = ctx->lane[l];
         CU(cudaStreamCreateWithFlags(&L.st, cudaStreamNonBlocking));
@@ -320,6 +330,10 @@ static int ctx_init(B200Ctx *ctx)
         }
         CU(cudaMalloc(&L.counter, 256));
         CU(cudaMemset(L.counter, 0, 256));
+        {   // counter[4..5]: device address of this lane's mapped host error word
+            const unsigned long long hp = (unsigned long long)(uintptr_t)(ctx->err_dev + l);
+            CU(cudaMemcpy(L.counter + 4, &hp, sizeof(hp), cudaMemcpyHostToDevice));
+        }
         CU(cudaMalloc(&L.parked, ctx->arena_bytes));
         CU(cudaEventCreateWithFlags(&L.tail, cudaEventDisableTiming));
     }
@@ -518,8 +532,14 @@ extern "C" int b200_frame_upload(B200Ctx *ctx, const void *blob, uint64_t nbytes
     bool pinned = cudaPointerGetAttributes(&at, blob) == cudaSuccess && at.type == cudaMemoryTypeHost;
     cudaGetLastError();
     if (!pinned) {   // stage through pinned memory so the copy stays asynchronous w.r.t. compute
-        if (!a.stage) CU(host_alloc_near_gpu((void **)&a.stage, ctx->arena_bytes));
         if (a.resident) CU(cudaEventSynchronize(a.ev_uploaded));
+        if (a.stage_bytes < nbytes) {                       // staging grows with the blobs it has seen (a worst-case blob is ~4x a typical one)
+            if (a.stage) { cudaFreeHost(a.stage); a.stage = nullptr; a.stage_bytes = 0; }
+            uint64_t want = (nbytes + (nbytes >> 2) + ((1u << 22) - 1)) & ~(uint64_t)((1u << 22) - 1);
+            if (want > ctx->arena_bytes) want = ctx->arena_bytes;
+            CU(host_alloc_near_gpu((void **)&a.stage, want));
+            a.stage_bytes = want;
+        }
         memcpy(a.stage, blob, nbytes);
         src = a.stage;
     }
@@ -654,14 +674,26 @@ extern "C" int b200_frame_execute_ex(B200Ctx *ctx, int arena, int cur_slot, cons
     return 0;
 }
 
-extern "C" int b200_frame_submit(B200Ctx *ctx, const void *blob, uint64_t nbytes)
+extern "C" int b200_frame_submit_ex(B200Ctx *ctx, const void *blob, uint64_t nbytes, uint32_t *upload_token)
 {
     if (!ctx) return B200_EINVAL;
     const int a = ctx->next_arena;
     int rc = b200_frame_upload(ctx, blob, nbytes, a);
     if (rc) return rc;
     ctx->next_arena = (a + 1) % ctx->cfg.n_arenas;
+    if (upload_token) *upload_token = (uint32_t)a;
     return b200_frame_execute(ctx, a);
+}
+extern "C" int b200_frame_submit(B200Ctx *ctx, const void *blob, uint64_t nbytes) { return b200_frame_submit_ex(ctx, blob, nbytes, nullptr); }
+
+// Safe from any thread: touches the arena's event handle only.  The copy stream is FIFO, so if the arena has been re-used
+// since, the wait is for a later upload -- which implies this one.
+extern "C" int b200_upload_wait(B200Ctx *ctx, uint32_t upload_token)
+{
+    if (!ctx || upload_token >= (uint32_t)ctx->cfg.n_arenas) return B200_EINVAL;
+    cudaSetDevice(ctx->cfg.device);
+    const cudaError_t e = cudaEventSynchronize(ctx->arena[upload_token].ev_uploaded);
+    return e == cudaSuccess ? 0 : B200_ECUDA;
 }
 
 extern "C" int b200_slot_upload(B200Ctx *ctx, int slot, const void *const planes[3], const int64_t strides[3])
@@ -690,6 +722,57 @@ extern "C" int b200_slot_readback(B200Ctx *ctx, int slot, void *const planes[3],
             CU(cudaMemcpy2DAsync(planes[p], (size_t)strides[p], ctx->slot_desc[slot].p[p].base, ctx->pitch[p], (size_t)ctx->pw[p] * B, ctx->ph[p], cudaMemcpyDeviceToHost, ctx->st_down));
     }
     return slot_release(ctx, slot, ctx->st_down, RD_DOWN, false);
+}
+
+// read-back whose completion ANOTHER thread waits for (the decoder's output path): the token names an event of a ring on the
+// read-back stream; b200_readback_wait may be called from any thread (it touches that event handle only; the stream is
+// FIFO, so a recycled ring entry stands for a later read-back, which implies this one)
+extern "C" int b200_slot_readback_async(B200Ctx *ctx, int slot, void *const planes[3], const int64_t strides[3], uint32_t *token)
+{
+    int rc = b200_slot_readback(ctx, slot, planes, strides);
+    if (rc) return rc;
+    const uint32_t i = ctx->rb_next;
+    ctx->rb_next = (i + 1) % RB_RING;
+    CU(cudaEventRecord(ctx->rb_ev[i], ctx->st_down));
+    if (token) *token = i;
+    return 0;
+}
+extern "C" int b200_readback_wait(B200Ctx *ctx, uint32_t token)
+{
+    if (!ctx || token >= RB_RING) return B200_EINVAL;
+    cudaSetDevice(ctx->cfg.device);
+    const cudaError_t e = cudaEventSynchronize(ctx->rb_ev[token]);
+    return e == cudaSuccess ? 0 : B200_ECUDA;
+}
+
+// Device-side error latches without a synchronisation: the kernels mirror them into mapped host memory (one word per lane)
+extern "C" int b200_poll_errors(B200Ctx *ctx)
+{
+    if (!ctx) return B200_EINVAL;
+    if (ctx->err_code) return ctx->err_code;
+    for (int l = 0; l < ctx->n_lanes; l++) {
+        const uint32_t v = ctx->err_host[l];
+        if (!v) continue;
+        ctx->err_host[l] = 0;
+        if (v & 0x80000000u) return fail(ctx, B200_EINVAL, "intra work list is not in decode order (dependency wait timed out)");
+        int rc = fail(ctx, B200_EINVAL, "work list rejected on the device: invalid record in section mask 0x%x (picture not executed)", v);
+        ctx->err_code = 0;
+        return rc;
+    }
+    return 0;
+}
+
+extern "C" int b200_host_register(void *p, uint64_t bytes)
+{
+    if (!p || !bytes) return B200_EINVAL;
+    if (cudaHostRegister(p, bytes, cudaHostRegisterDefault) != cudaSuccess) { cudaGetLastError(); return B200_ECUDA; }
+    return 0;
+}
+extern "C" int b200_host_unregister(void *p)
+{
+    if (!p) return B200_EINVAL;
+    if (cudaHostUnregister(p) != cudaSuccess) { cudaGetLastError(); return B200_ECUDA; }
+    return 0;
 }
 
 extern "C" int b200_slot_wait_readback(B200Ctx *ctx, int slot)
@@ -733,6 +816,7 @@ extern "C" int b200_sync(B200Ctx *ctx)
         if (st[2]) return fail(ctx, B200_EINVAL, "intra work list is not in decode order (dependency wait timed out)");
         if (st[3]) {                                     // k_validate closed the gate of a picture on this lane: it was not executed
             CU(cudaMemset(ctx->lane[l].counter + 3, 0, sizeof(uint32_t)));
+            ctx->err_host[l] = 0;
             int rc = fail(ctx, B200_EINVAL, "work list rejected on the device: invalid record in section mask 0x%x (picture not executed)", st[3]);
             ctx->err_code = 0;                           // the context stays usable, like after a rejected upload
             return rc;

@@ -53,6 +53,14 @@ __host__ __device__ constexpr int hevc_T(int k, int n)
 // gate layout (uint32, one per compute lane): [0] K3 ticket, [1] gate of the picture in progress, [2] K3 time-out latch,
 // [3] validation latch.
 // --------------------------------------------------------------------------------------------
+// Error latches are mirrored into mapped host memory (engine.cu: gate[4..5] = device address of this lane's host word), so that
+// the host can notice a rejected picture without synchronising with the device (b200_poll_errors).
+__device__ __forceinline__ void latch_host(uint32_t *gate, uint32_t code)
+{
+    uint32_t *hp = *reinterpret_cast<uint32_t *const *>(gate + 4);
+    if (hp) { *reinterpret_cast<volatile uint32_t *>(hp) = code; __threadfence_system(); }
+}
+
 struct ValidateArgs {
     const uint8_t *blob;                 // device copy of the blob
     B200Section sec[B200_SEC_COUNT];
@@ -110,7 +118,7 @@ __global__ void __launch_bounds__(256) k_validate(ValidateArgs a, uint32_t *gate
             ((m.w > 16) ? m.h > 8 : m.h > 16) || (i >= a.mc_big && !B200_MC_IS_SMALL(m.w, m.h)))
             bad |= 1u << B200_SEC_MC;
     }
-    if (bad) { gate[1] = 1u; atomicOr(gate + 3, bad); }
+    if (bad) { gate[1] = 1u; atomicOr(gate + 3, bad); latch_host(gate, bad); }
 }
 
 int launch_validate(cudaStream_t st, const uint8_t *blob_dev, const B200BlobHeader &h, const int pw[3], const int ph[3], unsigned long long arena_bytes, uint32_t *gate)
@@ -363,7 +371,7 @@ __global__ void __launch_bounds__(128) k_ccp(const B200CcpRec *__restrict__ recs
     const unsigned long long cap = arena_bytes / 2;                           // int16 entries of the parked pool
     if ((plane != 1 && plane != 2) || log2 < 2 || log2 > 5 || x + n > pd.w || y + n > pd.h || (unsigned long long)off_y + nn > cap ||
         ((flags & B200_CCPF_HAS_C) && (unsigned long long)off_c + nn > cap) || ((flags & B200_CCPF_TO_PARK) && (unsigned long long)off_out + nn > cap)) {
-        if (threadIdx.x == 0) { gate[1] = 1u; atomicOr(gate + 3, 1u << B200_SEC_COUNT); }
+        if (threadIdx.x == 0) { gate[1] = 1u; atomicOr(gate + 3, 1u << B200_SEC_COUNT); latch_host(gate, 1u << B200_SEC_COUNT); }
         return;
     }
     const int maxv = (1 << bd) - 1;
@@ -916,7 +924,7 @@ __device__ __forceinline__ void fetch_edges(const uint2 *pa, const uint2 *pa_alt
         __nanosleep(20);
         if ((++spins & 1023) == 0) {
             const bool abort = spins > (1u << 21) || ld_relaxed(counter + 2) != 0;
-            if (__any_sync(0xffffffffu, abort)) { st_relaxed(counter + 2, 1u); break; }
+            if (__any_sync(0xffffffffu, abort)) { st_relaxed(counter + 2, 1u); latch_host(counter, 0x80000000u); break; }
         }
     }
 }

@@ -19,7 +19,7 @@ struct B200Rec {
     int ctb_w, ctb_h;
     uint8_t *blob = nullptr;
     bool pinned = false;
-    uint64_t cap = 0;
+    uint64_t cap = 0, cap_max = 0;
     uint32_t off_dbk, off_sao, off_pool;
     uint32_t ncoef = 0;
     uint32_t npark = 0;          // int16 used in the parked-residual pool
@@ -95,14 +95,43 @@ extern "C" int b200_rec_set_refs(B200Rec *r, const uint8_t *slots, int n)
     return 0;
 }
 
-static uint64_t rec_capacity(const B200Config *c, const B200DbkLayout &L, int nctb)
+// Largest blob a picture of this geometry can produce: every sample coded (one int16 each; with 4:4:4 cross-component
+// prediction every luma block travels twice, the second time park-only), a TU + intra + MC record and the two-int16 park
+// prefix per 4x4 unit, the grids, slack for the section alignment.  The device arenas (engine.cu) and the recorder's
+// growth limit are both this number.
+extern "C" uint64_t b200_worst_blob_bytes(const B200Config *c)
 {
-    uint64_t samples = 0;
-    for (int p = 0; p < 3; p++) { int w, h; b200_plane_dims(c->width, c->height, c->chroma_format_idc, p, &w, &h); samples += (uint64_t)w * h; }
-    const uint64_t u = samples / 16;
-    uint64_t v = 4096 + samples * 2 + u * (16 + 16 + 32) + (uint64_t)L.total * 2 + (uint64_t)nctb * 3 * 16 + (1u << 20);
+    if (!c) return 0;
+    uint64_t samples = 0, luma = 0;
+    for (int p = 0; p < 3; p++) { int w, h; b200_plane_dims(c->width, c->height, c->chroma_format_idc, p, &w, &h); samples += (uint64_t)w * h; if (!p) luma = (uint64_t)w * h; }
+    B200DbkLayout L;
+    b200_dbk_layout(c->width, c->height, c->chroma_format_idc, &L);
+    const int ctb = 1 << c->log2_ctb_size;
+    const uint64_t nctb = (uint64_t)((c->width + ctb - 1) >> c->log2_ctb_size) * ((c->height + ctb - 1) >> c->log2_ctb_size);
+    const uint64_t u = samples / 16 + (c->chroma_format_idc == 3 ? luma / 16 : 0);
+    uint64_t v = 4096 + (samples + (c->chroma_format_idc == 3 ? luma : 0)) * 2 + u * (16 + 16 + 32 + 16 + 32) + (uint64_t)L.total * 2 + nctb * 3 * 16 +
+                 (samples >> 4) /* CIP + TQB bitmaps */ + (1u << 20);
     if (c->max_blob_bytes && c->max_blob_bytes < v) v = c->max_blob_bytes;
     return (v + 4095) & ~(uint64_t)4095;
+}
+
+// The blob starts at a fraction of the worst case and grows on demand (pinned memory is expensive to allocate: a worst-case
+// 4K blob is ~100 MB, a typical one 1-10 MB, and every decoding thread owns two recorders).
+static int rec_grow(B200Rec *r, uint64_t need)
+{
+    if (need <= r->cap) return 0;
+    if (need > r->cap_max) return B200_ENOMEM;
+    uint64_t cap = r->cap * 2 > need ? r->cap * 2 : need;
+    if (cap > r->cap_max) cap = r->cap_max;
+    cap = (cap + 4095) & ~(uint64_t)4095;
+    uint8_t *nb = r->pinned ? (uint8_t *)b200_host_alloc(cap) : nullptr;
+    const bool np = nb != nullptr;
+    if (!nb && posix_memalign((void **)&nb, 4096, cap)) return B200_ENOMEM;
+    const uint64_t used = (uint64_t)r->off_pool + (uint64_t)r->ncoef * 2;
+    memcpy(nb, r->blob, used < r->cap ? used : r->cap);
+    if (r->pinned) b200_host_free(r->blob); else free(r->blob);
+    r->blob = nb; r->cap = cap; r->pinned = np;
+    return 0;
 }
 
 extern "C" int b200_rec_create(const B200Config *cfg, B200Rec **out)
@@ -118,13 +147,16 @@ extern "C" int b200_rec_create(const B200Config *cfg, B200Rec **out)
     const int ctb = 1 << cfg->log2_ctb_size;
     r->ctb_w = (cfg->width + ctb - 1) >> cfg->log2_ctb_size;
     r->ctb_h = (cfg->height + ctb - 1) >> cfg->log2_ctb_size;
-    r->cap = rec_capacity(cfg, r->dbk, r->ctb_w * r->ctb_h);
-    r->blob = (uint8_t *)b200_host_alloc(r->cap);           // pinned when a GPU is present
-    r->pinned = r->blob != nullptr;
-    if (!r->blob && posix_memalign((void **)&r->blob, 4096, r->cap)) { delete r; return B200_ENOMEM; }
     r->off_dbk = 256;
     r->off_sao = b200_align_u32(r->off_dbk + r->dbk.total * 2, 256);
     r->off_pool = b200_align_u32(r->off_sao + (uint32_t)(3 * r->ctb_w * r->ctb_h) * 16, 256);
+    r->cap_max = b200_worst_blob_bytes(cfg);
+    r->cap = (r->off_pool + (r->cap_max >> 4) + (2u << 20) + 4095) & ~(uint64_t)4095;
+    if (r->cap > r->cap_max) r->cap = r->cap_max;
+    if (r->cap < (uint64_t)r->off_pool + (1u << 17)) { delete r; return B200_EINVAL; }     // max_blob_bytes below the fixed sections
+    r->blob = (uint8_t *)b200_host_alloc(r->cap);           // pinned when a GPU is present
+    r->pinned = r->blob != nullptr;
+    if (!r->blob && posix_memalign((void **)&r->blob, 4096, r->cap)) { delete r; return B200_ENOMEM; }
     *out = r;
     return 0;
 }
@@ -151,7 +183,7 @@ extern "C" int b200_rec_begin(B200Rec *r, int cur_slot, int poc)
 static int16_t *pool_take(B200Rec *r, int n, uint32_t *off)
 {
     const uint32_t o = (r->ncoef + 7) & ~7u;
-    if ((uint64_t)r->off_pool + ((uint64_t)o + n) * 2 + (1u << 16) > r->cap) return nullptr;
+    if ((uint64_t)r->off_pool + ((uint64_t)o + n) * 2 + (1u << 16) > r->cap && rec_grow(r, (uint64_t)r->off_pool + ((uint64_t)o + n) * 2 + (1u << 16))) return nullptr;
     *off = o;
     r->ncoef = o + n;
     return (int16_t *)(r->blob + r->off_pool) + o;
@@ -353,7 +385,7 @@ extern "C" int b200_rec_merge(B200Rec *d, B200Rec *s)
         map[i] = (uint8_t)j;
     }
     const uint32_t base = (d->ncoef + 7) & ~7u, pbase = (d->npark + 7) & ~7u;
-    if ((uint64_t)d->off_pool + ((uint64_t)base + s->ncoef) * 2 + (1u << 16) > d->cap) return B200_ENOMEM;
+    if (rec_grow(d, (uint64_t)d->off_pool + ((uint64_t)base + s->ncoef) * 2 + (1u << 16))) return B200_ENOMEM;
     int16_t *dp = (int16_t *)(d->blob + d->off_pool);
     if (s->ncoef) memcpy(dp + base, s->blob + s->off_pool, (size_t)s->ncoef * 2);
     d->ncoef = base + s->ncoef;
@@ -464,6 +496,13 @@ extern "C" int b200_rec_set_tqb(B200Rec *r, int log2_min_pu_size, int min_pu_wid
 extern "C" int b200_rec_finish(B200Rec *r, const void **blob, uint64_t *nbytes)
 {
     if (!r || !r->open || !blob || !nbytes) return B200_EINVAL;
+    {   // room for the lists and the optional sections behind the pool, before any pointer into the blob is taken
+        uint64_t need = b200_align_u32(r->off_pool + ((r->ncoef + 7) & ~7u) * 2, 256);
+        for (int s = 0; s < 4; s++) need += ((uint64_t)r->tu[s].size() * 16 + 255) & ~(uint64_t)255;
+        need += (((uint64_t)r->intra.size() * 16 + 255) & ~(uint64_t)255) + (((uint64_t)r->mc.size() * 32 + 255) & ~(uint64_t)255);
+        need += r->cip.size() * 4 + r->tqb.size() * 4 + r->ccp.size() * sizeof(B200CcpRec) + 4 * 256;
+        if (rec_grow(r, need)) return B200_ENOMEM;
+    }
     B200BlobHeader *h = (B200BlobHeader *)r->blob;
     memset(h, 0, sizeof(*h));
     h->magic = B200_BLOB_MAGIC; h->version = B200_BLOB_VERSION;

@@ -16,8 +16,13 @@
  * threads of ONE picture (-f 2, execute2 jobs, hevc.c:3082): a worker attaches itself to the picture in progress on its
  * first table call, records into its own B200Rec, and b200_frame_end folds the workers into the owner's recorder
  * (b200_rec_merge).  Frame and slice threads combined (-f 4) are rejected: a table call carries no context, so a worker
- * cannot tell which of several pictures in progress it belongs to.  One decoder instance per process.  4:4:4 cross-component prediction is
- * rejected with an error from b200_frame_end.
+ * cannot tell which of several pictures in progress it belongs to.  One decoder instance per process.
+ *
+ * Pictures reach the device through ONE submission thread (the engine's threading contract, include/b200hevc.h): a decoding
+ * thread that has parsed its picture hands the finished work list over (a queue ordered by the ticket taken at
+ * b200_frame_begin, i.e. decode order) and goes on with its next packet at once; the submission thread uploads, launches and
+ * issues the read-back of the picture into its (pinned, b200_frame_buffer_alloc) host frame.  Nobody waits for the device
+ * until the picture LEAVES the decoder: b200_output_wait, hooked where hevc_decode_frame hands a frame to its caller.
  */
 #include <stdint.h>
 #include <stdio.h>
@@ -30,10 +35,13 @@
 #include "libavcodec/get_bits.h"
 #include "b200hevc.h"
 #include "b200hevc_tables.h"
+#include <dlfcn.h>
 
 #define MAX_REG 33
 #define MAX_WORKERS 64
 #define MAX_ACTIVE 64
+#define MAX_JOBS 64
+#define MAX_RB 128
 
 typedef struct RegPlane { const uint8_t *base; ptrdiff_t linesize, size; uint64_t inv; int slot, plane, w, h; } RegPlane;
 
@@ -58,12 +66,40 @@ static struct {
     const char *dump_dir;
     int dump_no, configured, env_read;
     int in_flight;                      /* pictures begun whose packet has not ended yet (b200_frame_begin .. b200_frame_readback) */
-} G = { .mu = PTHREAD_MUTEX_INITIALIZER, .cv = PTHREAD_COND_INITIALIZER };
+    /* the submission thread: jobs by ticket (a decoding thread owns at most two tickets, MAX_JOBS covers 32 threads) */
+    struct Job *jobq[MAX_JOBS];
+    pthread_t sub_thread;
+    pthread_cond_t cv_sub;
+    int sub_running, sub_stop;
+    int err_code; char errmsg[256];     /* latched by the submission thread, returned by the next b200_frame_begin / _end */
+    /* read-backs in flight, keyed by the host frame's luma pointer (b200_output_wait) */
+    struct { const uint8_t *data0; uint32_t token; int state; unsigned seq; } rb[MAX_RB];
+    unsigned rb_seq;
+    uint64_t n_pictures, h2d_bytes, d2h_bytes;   /* B200_SHIM_REPORT=1: totals on stderr when the process ends */
+} G = { .mu = PTHREAD_MUTEX_INITIALIZER, .cv = PTHREAD_COND_INITIALIZER, .cv_sub = PTHREAD_COND_INITIALIZER };
+
+/* one picture on its way to the device (lives in the ShimThread that recorded it: two per thread, used alternately, so that
+ * a thread can parse its next picture while the previous one's work list is still being uploaded) */
+typedef struct Job {
+    unsigned ticket;
+    int kind;                           /* JOB_SKIP: the ticket only (abandoned / failed picture); JOB_PICTURE */
+    const void *blob; uint64_t nbytes;
+    uint8_t fill_slot[16]; int n_fill;  /* grey reference pictures this picture needs (generate_missing_ref), in front of it */
+    int slot; void *planes[3]; int64_t strides[3]; int rb; unsigned rb_seq;   /* read-back into the host frame: entry of G.rb (and its generation) or -1 */
+    int pending, done;                  /* pending: handed to the submission thread, its memory must not be reused before done */
+    uint32_t upload_token; int uploaded;
+} Job;
+enum { JOB_SKIP = 0, JOB_PICTURE = 1 };
 
 /* per thread: the owner of a picture (the thread that runs hevc_frame_start .. the end of decode_nal_unit for it; with
  * frame threads one per picture in flight, pthread_frame.c) or a slice / WPP worker attached to an owner's picture */
+struct Job;
 typedef struct ShimThread {
-    B200Rec *rec;
+    B200Rec *rec;                       /* the recorder of the picture in progress: recs[cur] (workers: recs[0]) */
+    B200Rec *recs[2];
+    struct Job *jobs;                   /* [3], allocated with the first recorder */
+    int rb_at; unsigned rb_seq;         /* entry of G.rb announced at b200_frame_begin for the picture in progress, or -1 */
+    int cur;
     unsigned rec_gen;
     unsigned ticket;
     RegPlane reg[MAX_REG * 3];
@@ -139,6 +175,7 @@ static void fail(int code, const char *msg)
 }
 const char *b200_shim_error(void) { return g.err ? g.errmsg : (G.ctx ? b200_last_error(G.ctx) : ""); }
 
+static int thread_recorder(int k);
 /* A table call on a thread that owns no picture: a slice / WPP / tile worker (execute2 job).  Attach it to the picture
  * in progress: own recorder, own reference table, a copy of the owner's plane registry. */
 static int attach_slow(void)
@@ -151,11 +188,7 @@ static int attach_slow(void)
         rc = -1;
     } else {
         ShimThread *o = G.active[0];
-        if (g.rec && g.rec_gen != G.gen) { b200_rec_destroy(g.rec); g.rec = NULL; }
-        if (!g.rec) {
-            g.rec_gen = G.gen;
-            if (b200_rec_create(&G.cfg, &g.rec)) { fail(B200_ENOMEM, "b200_rec_create failed (worker)"); rc = -1; }
-        }
+        if (thread_recorder(0)) { fail(B200_ENOMEM, "b200_rec_create failed (worker)"); rc = -1; }
         if (!rc && o->n_workers == MAX_WORKERS) { fail(B200_ENOTSUP, "too many worker threads"); rc = -1; }
         if (!rc) {
             memcpy(g.reg, o->reg, sizeof(g.reg)); g.n_reg = o->n_reg;
@@ -542,6 +575,146 @@ void ff_videodsp_init_b200(VideoDSPContext *c, int bpc)
 }
 
 /* ---- frame life cycle ----------------------------------------------------------------------------------------- */
+/* recorder k (0 / 1) of the calling thread, created on first use and re-created when the geometry changed; becomes g.rec.
+ * Called with G.mu held. */
+static int thread_recorder(int k)
+{
+    ShimThread *t = &g;
+    if (t->rec_gen != G.gen) {
+        for (int i = 0; i < 2; i++) if (t->recs[i]) { b200_rec_destroy(t->recs[i]); t->recs[i] = NULL; }
+        t->rec_gen = G.gen;
+    }
+    if (!t->jobs && !(t->jobs = calloc(3, sizeof(Job)))) return B200_ENOMEM;     /* [2]: the ticket-only job of ticket_skip */
+    if (!t->recs[k]) {
+        int rc = b200_rec_create(&G.cfg, &t->recs[k]);
+        if (rc) return rc;
+    }
+    t->rec = t->recs[k];
+    return 0;
+}
+
+static void latch_global(int code, const char *msg)         /* G.mu held */
+{
+    if (!G.err_code) { G.err_code = code; snprintf(G.errmsg, sizeof(G.errmsg), "%s", msg ? msg : "B200 back end failed"); }
+}
+static int global_error(void)                                /* a failure of the submission thread reaches every decoding thread */
+{
+    int e = __atomic_load_n(&G.err_code, __ATOMIC_ACQUIRE);
+    if (e && !g.err) {
+        pthread_mutex_lock(&G.mu);
+        fail(G.err_code, G.errmsg);
+        pthread_mutex_unlock(&G.mu);
+    }
+    return e;
+}
+
+/* ---- the submission thread: the only thread that drives the device context ---- */
+static int process_job(Job *j, char *msg, size_t msg_n)
+{
+    int rc = 0;
+    const int drop = G.dump_dir && !strcmp(G.dump_dir, "-");      /* "-": record and drop (host-side timing without a device) */
+    for (int i = 0; i < j->n_fill && !rc; i++) {                  /* grey reference pictures, in decode order with everything else */
+        const int grey = 1 << (G.bd - 1);
+        if (drop) continue;
+        if (G.dump_dir) {
+            char path[1024];
+            snprintf(path, sizeof(path), "%s/pic_%05d.fill", G.dump_dir, G.dump_no);
+            FILE *f = fopen(path, "a");
+            if (f) { fprintf(f, "%d %d\n", j->fill_slot[i], grey); fclose(f); } else rc = B200_EINVAL;
+        } else rc = b200_slot_fill(G.ctx, j->fill_slot[i], grey);
+    }
+    if (rc) { snprintf(msg, msg_n, "grey reference fill failed: %s", G.ctx ? b200_last_error(G.ctx) : "dump"); return rc; }
+    if (j->kind != JOB_PICTURE) return 0;
+    if (drop) { G.dump_no++; return 0; }
+    if (G.dump_dir) {
+        char path[1024];
+        snprintf(path, sizeof(path), "%s/pic_%05d.blob", G.dump_dir, G.dump_no++);
+        FILE *f = fopen(path, "wb");
+        if (!f || fwrite(j->blob, 1, (size_t)j->nbytes, f) != (size_t)j->nbytes) { rc = B200_EINVAL; snprintf(msg, msg_n, "B200_SHIM_DUMP: cannot write the work list"); }
+        if (f) fclose(f);
+        return rc;
+    }
+    rc = b200_frame_submit_ex(G.ctx, j->blob, j->nbytes, &j->upload_token);
+    if (!rc) { j->uploaded = 1; G.n_pictures++; G.h2d_bytes += j->nbytes; if (j->rb >= 0) for (int p = 0; p < 3; p++) G.d2h_bytes += (uint64_t)G.pw[p] * G.ph[p] * G.B; }
+    uint32_t token = 0;
+    if (!rc && j->rb >= 0) rc = b200_slot_readback_async(G.ctx, j->slot, j->planes, j->strides, &token);
+    if (!rc) rc = b200_poll_errors(G.ctx);
+    if (rc) snprintf(msg, msg_n, "%s", b200_last_error(G.ctx));
+    if (j->rb >= 0) {
+        pthread_mutex_lock(&G.mu);
+        if (G.rb[j->rb].seq == j->rb_seq && G.rb[j->rb].state == 1) {      /* else: the host buffer went to a newer picture meanwhile */
+            G.rb[j->rb].token = token;
+            G.rb[j->rb].state = rc ? 3 : 2;                       /* 2 issued, 3 failed: a waiter must not wait for it */
+        }
+        pthread_mutex_unlock(&G.mu);
+    }
+    return rc;
+}
+
+static void *submit_main(void *arg)
+{
+    (void)arg;
+    pthread_mutex_lock(&G.mu);
+    for (;;) {
+        Job *j;
+        while (!(j = G.jobq[G.turn % MAX_JOBS]) && !G.sub_stop) pthread_cond_wait(&G.cv_sub, &G.mu);
+        if (!j) break;
+        G.jobq[G.turn % MAX_JOBS] = NULL;
+        pthread_mutex_unlock(&G.mu);
+        char msg[256] = "";
+        const int rc = process_job(j, msg, sizeof(msg));
+        pthread_mutex_lock(&G.mu);
+        if (rc) latch_global(rc, msg);
+        j->done = 1;
+        G.turn++;
+        pthread_cond_broadcast(&G.cv);
+    }
+    pthread_mutex_unlock(&G.mu);
+    return NULL;
+}
+
+/* the process ends (exit() or return from main) while work lists may still be queued: let them through -- record-only runs
+ * (B200_SHIM_DUMP) write their files on the submission thread */
+static void drain_at_exit(void)
+{
+    pthread_mutex_lock(&G.mu);
+    while (G.sub_running && G.turn != G.next_ticket && !G.err_code) pthread_cond_wait(&G.cv, &G.mu);
+    pthread_mutex_unlock(&G.mu);
+    if (getenv("B200_SHIM_REPORT"))
+        fprintf(stderr, "b200 shim: pictures %llu h2d_bytes %llu d2h_bytes %llu\n", (unsigned long long)G.n_pictures, (unsigned long long)G.h2d_bytes, (unsigned long long)G.d2h_bytes);
+}
+
+static void enqueue(Job *j)                        /* j->ticket is this thread's ticket */
+{
+    pthread_mutex_lock(&G.mu);
+    if (!G.sub_running) {
+        static int registered;
+        G.sub_stop = 0;
+        if (pthread_create(&G.sub_thread, NULL, submit_main, NULL)) latch_global(B200_ENOMEM, "cannot start the submission thread");
+        else { G.sub_running = 1; if (!registered) { registered = 1; atexit(drain_at_exit); } }
+    }
+    j->pending = 1; j->done = 0;
+    if (!G.sub_running) { j->done = 1; G.turn++; pthread_cond_broadcast(&G.cv); }      /* nobody will run it: keep the tickets moving */
+    else { G.jobq[j->ticket % MAX_JOBS] = j; pthread_cond_signal(&G.cv_sub); }
+    pthread_mutex_unlock(&G.mu);
+}
+
+/* the job's memory (recorder blob, Job itself) may be written again */
+static void job_reclaim(Job *j)
+{
+    if (!j->pending) return;
+    pthread_mutex_lock(&G.mu);
+    while (!j->done) pthread_cond_wait(&G.cv, &G.mu);
+    pthread_mutex_unlock(&G.mu);
+    if (j->uploaded && G.ctx) b200_upload_wait(G.ctx, j->upload_token);
+    j->pending = 0; j->uploaded = 0;
+}
+
+static void drain_queue(void)                      /* G.mu held: every ticket handed out so far has been through the submission thread */
+{
+    while (G.turn != G.next_ticket) pthread_cond_wait(&G.cv, &G.mu);
+}
+
 static int ensure_ctx(const HEVCContext *s)       /* called with G.mu held */
 {
     const HEVCSPS *sps = s->sps;
@@ -550,10 +723,12 @@ static int ensure_ctx(const HEVCContext *s)       /* called with G.mu held */
           G.cfg.chroma_format_idc == sps->chroma_format_idc && G.cfg.log2_ctb_size == (int)sps->log2_ctb_size)) {
         /* New geometry (a new SPS, hence an IRAP picture: nothing older is referenced any more).  With frame threads older pictures
          * may still be parsing on other threads against the old context, plane sizes and sample width: wait until their packets
-         * have ended (they do not depend on this thread), then switch. */
+         * have ended (they do not depend on this thread) and their work lists have gone through the submission thread, then switch. */
         while (G.in_flight > (g.counted ? 1 : 0)) pthread_cond_wait(&G.cv, &G.mu);      /* (this thread's own packet does not count) */
+        drain_queue();
         G.gen++;
-        if (G.ctx) { b200_ctx_destroy(G.ctx); G.ctx = NULL; }
+        if (G.ctx) { b200_sync(G.ctx); b200_ctx_destroy(G.ctx); G.ctx = NULL; }
+        for (int i = 0; i < MAX_RB; i++) G.rb[i].state = 0;
         memset(&G.cfg, 0, sizeof(G.cfg));
         const char *dev = getenv("B200_DEVICE");
         G.cfg.device = dev ? atoi(dev) : 0;
@@ -569,22 +744,26 @@ static int ensure_ctx(const HEVCContext *s)       /* called with G.mu held */
         G.bd = sps->bit_depth; G.B = G.bd > 8 ? 2 : 1; G.cfi = sps->chroma_format_idc;
         for (int p = 0; p < 3; p++) b200_plane_dims(sps->width, sps->height, G.cfi, p, &G.pw[p], &G.ph[p]);
     }
-    if (g.rec && g.rec_gen != G.gen) { b200_rec_destroy(g.rec); g.rec = NULL; }
-    if (!g.rec) {
-        g.rec_gen = G.gen;
-        int rc = b200_rec_create(&G.cfg, &g.rec);
-        if (rc) { fail(rc, "b200_rec_create failed"); return rc; }
-    }
     return 0;
 }
 
-static void ticket_release(void)                   /* let the next picture (in decode order) submit */
+/* this thread's ticket is spent without a picture (abandoned picture whose frame is gone, or a failure before the hand-over) */
+static void rb_cancel(void)                        /* no pixels will come for the announced read-back: release whoever waits for it */
 {
+    if (g.rb_at < 0) return;
     pthread_mutex_lock(&G.mu);
-    while (G.turn != g.ticket) pthread_cond_wait(&G.cv, &G.mu);
-    G.turn++;
-    pthread_cond_broadcast(&G.cv);
+    if (G.rb[g.rb_at].seq == g.rb_seq && G.rb[g.rb_at].state == 1) { G.rb[g.rb_at].state = 3; pthread_cond_broadcast(&G.cv); }
     pthread_mutex_unlock(&G.mu);
+    g.rb_at = -1;
+}
+static void ticket_skip(void)
+{
+    rb_cancel();
+    Job *skip = &g.jobs[2];                        /* heap, like the other two: the submission thread may outlive this thread */
+    job_reclaim(skip);
+    memset(skip, 0, sizeof(*skip));
+    skip->ticket = g.ticket; skip->kind = JOB_SKIP; skip->rb = -1;
+    enqueue(skip);
 }
 
 static void deactivate(void)                       /* the picture is no longer open for worker threads */
@@ -598,19 +777,25 @@ static void deactivate(void)                       /* the picture is no longer o
 
 static void finish_abandoned(HEVCContext *s);
 static void picture_flags(HEVCContext *s);
+static int rb_insert(const uint8_t *data0);
 
 int b200_frame_begin(HEVCContext *s)
 {
     if (g.err) return g.err;
     if (g.in_frame == 1) finish_abandoned(s);                  /* previous picture of this thread was abandoned */
-    if (g.err) return g.err;
+    if (g.err || global_error()) return g.err;
     g.in_frame = 0;
+    g.rb_at = -1;
     picture_flags(s);
     /* cross-component prediction (4:4:4): host arithmetic between two table calls, undone and redone on the device (rec_cross_component) */
     g.s = s; g.lc = NULL; g.last_y.log2 = 0;
     g.ccp = s->sps->chroma_array_type == 3 && s->pps->cross_component_prediction_enabled_flag;
+    /* the other of this thread's two recorders; its previous picture (two pictures back) has left host memory by now */
+    g.cur ^= 1;
+    if (g.jobs) job_reclaim(&g.jobs[g.cur]);
     pthread_mutex_lock(&G.mu);
-    const int erc = ensure_ctx(s);
+    int erc = ensure_ctx(s);
+    if (!erc && (erc = thread_recorder(g.cur))) fail(erc, "b200_rec_create failed");
     if (!erc) {
         g.ticket = G.next_ticket++;
         if (!g.counted) { G.in_flight++; g.counted = 1; }      /* once per packet, however many pictures it starts */
@@ -635,15 +820,33 @@ int b200_frame_begin(HEVCContext *s)
     g.n_ref = 0; g.pend_ptr = NULL; g.first_tmp = NULL; g.emu[0].buf = g.emu[1].buf = NULL;
     g.poc = s->poc; g.n_workers = 0;
     int rc = b200_rec_begin(g.rec, g.cur_slot, s->poc);
-    if (rc) { fail(rc, "b200_rec_begin failed"); ticket_release(); return rc; }
+    if (rc) { fail(rc, "b200_rec_begin failed"); ticket_skip(); return rc; }
     pthread_mutex_lock(&G.mu);
     g.frame_seq++;
     g.in_frame = 1;
     if (G.n_active < MAX_ACTIVE) G.active[G.n_active++] = &g;
+    /* announce the read-back NOW: the frame may be picked for output (bumping, by the thread of a later picture) while this
+     * thread is still parsing it, and whoever hands it to the application must wait for pixels that are not even queued yet */
+    g.rb_at = -1;
+    if (!G.dump_dir && s->frame->data[0]) { g.rb_at = rb_insert(s->frame->data[0]); if (g.rb_at >= 0) g.rb_seq = G.rb[g.rb_at].seq; }
     pthread_mutex_unlock(&G.mu);
     return 0;
 }
 
+/* a read-back into `data0`'s frame is on its way: remembered until the frame leaves the decoder (b200_output_wait).  G.mu held. */
+static int rb_insert(const uint8_t *data0)
+{
+    int at = -1, oldest = -1;
+    for (int i = 0; i < MAX_RB; i++) {
+        if (G.rb[i].state && G.rb[i].data0 == data0) { at = i; break; }       /* the buffer was recycled without having been output */
+        if (!G.rb[i].state) { if (at < 0) at = i; }
+        else if (G.rb[i].state >= 2 && (oldest < 0 || (int)(G.rb[i].seq - G.rb[oldest].seq) < 0)) oldest = i;
+    }
+    if (at < 0) at = oldest;                       /* table full of pictures nobody asked for: forget the oldest one */
+    if (at < 0) return -1;
+    G.rb[at].data0 = data0; G.rb[at].state = 1; G.rb[at].seq = G.rb_seq++; G.rb[at].token = 0;
+    return at;
+}
 
 static int frame_end_of(HEVCContext *s, HEVCFrame *ref)
 {
@@ -676,40 +879,28 @@ static int frame_end_of(HEVCContext *s, HEVCFrame *ref)
         int crc = b200_rec_set_tqb(g.rec, s->sps->log2_min_pu_size, s->sps->min_pu_width, s->sps->min_pu_height, s->is_pcm);
         if (crc) fail(crc, "b200_rec_set_tqb failed");
     }
-    if (g.err) { ticket_release(); return g.err; }
+    if (g.err) { ticket_skip(); return g.err; }
     if (getenv("B200_SHIM_STATS"))
         fprintf(stderr, "b200 picture %d: intra_pred %d transform_add %d mc %d deblock %d sao %d\n", g.frame_no, g.n_intra, g.n_tu, g.n_pu, g.n_dbk, g.n_sao);
     g.frame_no++; g.n_tu = g.n_intra = g.n_pu = g.n_dbk = g.n_sao = 0;
     const void *blob; uint64_t n;
     int rc = b200_rec_finish(g.rec, &blob, &n);
-    /* pictures enter the compute stream in decode order, whatever order the frame threads finish parsing in */
-    pthread_mutex_lock(&G.mu);
-    while (G.turn != g.ticket) pthread_cond_wait(&G.cv, &G.mu);
-    for (int i = 0; i < g.n_fill && !rc; i++) {      /* grey reference pictures, in decode order with everything else */
-        const int grey = 1 << (G.bd - 1);
-        if (G.dump_dir && !strcmp(G.dump_dir, "-")) continue;
-        if (G.dump_dir) {
-            char path[1024];
-            snprintf(path, sizeof(path), "%s/pic_%05d.fill", G.dump_dir, G.dump_no);
-            FILE *f = fopen(path, "a");
-            if (f) { fprintf(f, "%d %d\n", g.fill_slot[i], grey); fclose(f); } else rc = B200_EINVAL;
-        } else rc = b200_slot_fill(G.ctx, g.fill_slot[i], grey);
-    }
-    g.n_fill = 0;
-    if (!rc && G.dump_dir && !strcmp(G.dump_dir, "-")) G.dump_no++;     /* "-": record and drop (host-side timing without a device) */
-    else if (!rc && G.dump_dir) {
-        char path[1024];
-        snprintf(path, sizeof(path), "%s/pic_%05d.blob", G.dump_dir, G.dump_no++);
-        FILE *f = fopen(path, "wb");
-        if (!f || fwrite(blob, 1, (size_t)n, f) != (size_t)n) { fail(B200_EINVAL, "B200_SHIM_DUMP: cannot write the work list"); rc = B200_EINVAL; }
-        if (f) fclose(f);
-    } else if (!rc) rc = b200_frame_submit(G.ctx, blob, n);
-    G.turn++;
-    pthread_cond_broadcast(&G.cv);
-    pthread_mutex_unlock(&G.mu);
-    if (!rc && !G.dump_dir) rc = b200_wait_uploads(G.ctx);  /* this thread's recorder memory is reused by its next picture */
-    if (rc) fail(rc, G.ctx ? b200_last_error(G.ctx) : "frame_end failed");
-    return rc;
+    if (rc) { fail(rc, "b200_rec_finish failed"); ticket_skip(); return rc; }
+    /* hand the picture to the submission thread: it enters the device queue in decode order (ticket), whatever order the
+     * frame threads finish parsing in, and this thread is free for its next packet */
+    Job *j = &g.jobs[g.cur];
+    j->ticket = g.ticket; j->kind = JOB_PICTURE; j->blob = blob; j->nbytes = n;
+    j->n_fill = g.n_fill; memcpy(j->fill_slot, g.fill_slot, sizeof(j->fill_slot)); g.n_fill = 0;
+    j->uploaded = 0; j->rb = -1;
+    AVFrame *hf = ref ? ref->frame : NULL;
+    if (!G.dump_dir && hf && hf->data[0] && hf->data[0] == g.cur_base[0] && g.rb_at >= 0) {    /* the read-back into the picture's host frame is part of the job */
+        j->slot = g.cur_slot;
+        for (int p = 0; p < 3; p++) { j->planes[p] = hf->data[p]; j->strides[p] = hf->linesize[p]; }
+        j->rb = g.rb_at; j->rb_seq = g.rb_seq;
+    } else rb_cancel();
+    g.rb_at = -1;
+    enqueue(j);
+    return global_error();
 }
 static void picture_flags(HEVCContext *s)
 {
@@ -722,22 +913,21 @@ int b200_frame_end(HEVCContext *s)
     return frame_end_of(s, s->ref);
 }
 
-static int readback_into(HEVCContext *s, AVFrame *frame);
 /* A picture that was begun but never ended (corrupt slice data).  It is finished with what was recorded -- the part the
  * reference has reconstructed as well -- and copied into its host frame, which the decoder will still output. */
 static void finish_abandoned(HEVCContext *s)
 {
     HEVCFrame *old = g.cur_slot >= 0 && g.cur_slot < 32 ? &s->DPB[g.cur_slot] : NULL;
     if (!old || !old->frame || !old->frame->data[0] || old->frame->data[0] != g.cur_base[0]) {      /* the frame is gone: nothing to show */
-        deactivate(); ticket_release();
+        deactivate(); ticket_skip();
         return;
     }
-    if (!frame_end_of(s, old)) readback_into(s, old->frame);
+    frame_end_of(s, old);
 }
 
 /* hevc_refs.c:538-606 generate_missing_ref: a reference the stream does not contain is replaced by a grey picture the host
  * fills with memset; the device slot must hold the same.  Called while the RPS of the NEXT picture of this thread is set up
- * (before its b200_frame_begin), executed in decode order at that picture's b200_frame_end. */
+ * (before its b200_frame_begin), executed in decode order in front of that picture. */
 int b200_frame_fill(HEVCContext *s, HEVCFrame *frame)
 {
     if (g.err) return g.err;
@@ -746,6 +936,29 @@ int b200_frame_fill(HEVCContext *s, HEVCFrame *frame)
     if (g.n_fill == 16) { fail(B200_ENOTSUP, "more than 16 missing reference pictures"); return g.err; }
     g.fill_slot[g.n_fill++] = (uint8_t)slot;
     return 0;
+}
+
+/* The frame is about to leave the decoder (hevc_decode_frame hands it to its caller) or to be read on the host (SEI
+ * checksum): wait until the device picture has landed in it.  Frames the shim knows nothing about return at once. */
+int b200_output_wait(HEVCContext *s, AVFrame *frame)
+{
+    (void)s;
+    if (!frame || !frame->data[0] || G.dump_dir) return 0;
+    pthread_mutex_lock(&G.mu);
+    int at = -1;
+    for (int i = 0; i < MAX_RB; i++) if (G.rb[i].state && G.rb[i].data0 == frame->data[0]) { at = i; break; }
+    if (at < 0) { pthread_mutex_unlock(&G.mu); return 0; }
+    const unsigned seq = G.rb[at].seq;
+    while (G.rb[at].state == 1 && G.rb[at].seq == seq && !G.err_code) pthread_cond_wait(&G.cv, &G.mu);
+    const int st = G.rb[at].seq == seq ? G.rb[at].state : 0;
+    const uint32_t token = G.rb[at].token;
+    if (G.rb[at].seq == seq) G.rb[at].state = 0;
+    B200Ctx *ctx = G.ctx;
+    pthread_mutex_unlock(&G.mu);
+    int rc = 0;
+    if (st == 2 && ctx) rc = b200_readback_wait(ctx, token);
+    if (rc) fail(rc, "waiting for the read-back of an output picture failed");
+    return rc ? rc : global_error();
 }
 
 static int packet_end(HEVCContext *s, AVFrame *frame);
@@ -763,59 +976,91 @@ int b200_frame_readback(HEVCContext *s, AVFrame *frame)
 }
 static int packet_end(HEVCContext *s, AVFrame *frame)
 {
-    if (g.err) return g.err;
     if (!frame) {
         /* The packet ended without a complete picture.  If one was begun, it was abandoned (corrupt slice data: hls_slice_data came
          * back short of the picture, hevc.c:3444-3446, and decode_nal_unit swallowed the error).  It is finished here with what was
-         * recorded -- the part the reference has reconstructed as well -- for two reasons: the decoder may hand the frame to the
-         * application as soon as this call returns (low-delay output), and with frame threads the pictures behind it wait for its
-         * ticket in b200_frame_end while this thread only gets its next packet after one of THEM has been delivered: a dead lock
-         * unless the picture is closed now.  (Packets are access units: a picture never continues in the next packet.) */
-        if (!(g.in_frame == 1 && s->ref)) return 0;
-        const int rc = b200_frame_end(s);
-        if (rc) return rc;
-        frame = s->ref->frame;
+         * recorded -- the part the reference has reconstructed as well: the decoder may still output the frame, and the pictures
+         * behind it in decode order wait for its ticket.  Even after an error the ticket must not be lost.
+         * (Packets are access units: a picture never continues in the next packet.) */
+        if (g.in_frame == 1) {
+            if (g.err || !s->ref) { deactivate(); ticket_skip(); }
+            else {
+                const int rc = b200_frame_end(s);
+                if (rc) return rc;
+                frame = s->ref->frame;
+            }
+        }
+        if (!frame) return g.err;
     }
-    return readback_into(s, frame);
-}
-static int readback_into(HEVCContext *s, AVFrame *frame)
-{
-    if (G.dump_dir) return 0;                 /* record-only run: there is no device picture */
-    int slot = -1;
-    for (int i = 0; i < 32; i++) if (s->DPB[i].frame && s->DPB[i].frame->data[0] == frame->data[0]) slot = i;
-    if (slot < 0) { fail(B200_EINVAL, "readback of a frame that is not in the DPB"); return g.err; }
-    void *planes[3] = { frame->data[0], frame->data[1], frame->data[2] };
-    int64_t strides[3] = { frame->linesize[0], frame->linesize[1], frame->linesize[2] };
-    int rc = b200_slot_readback(G.ctx, slot, planes, strides);
-    if (!rc) rc = b200_sync(G.ctx);
-    if (rc) fail(rc, b200_last_error(G.ctx));
-    return rc;
+    if (g.err) return g.err;
+    /* the read-back was issued with the picture; only a decoder that reads the pixels itself (SEI checksum, hevc.c:4146) waits here */
+    if (s->decode_checksum_sei) return b200_output_wait(s, frame);
+    return global_error();
 }
 
 /* reference pictures that exist only on the host (e.g. produced before the hook was active) */
 int b200_frame_upload_ref(HEVCContext *s, AVFrame *frame)
 {
     pthread_mutex_lock(&G.mu);
-    const int erc = ensure_ctx(s);
+    int rc = ensure_ctx(s);
+    if (!rc && !G.dump_dir) {
+        drain_queue();                               /* the submission thread is idle and stays so while G.mu is held */
+        int slot = -1;
+        for (int i = 0; i < 32; i++) if (s->DPB[i].frame && s->DPB[i].frame->data[0] == frame->data[0]) slot = i;
+        if (slot < 0) { fail(B200_EINVAL, "upload of a frame that is not in the DPB"); rc = g.err; }
+        else {
+            const void *planes[3] = { frame->data[0], frame->data[1], frame->data[2] };
+            int64_t strides[3] = { frame->linesize[0], frame->linesize[1], frame->linesize[2] };
+            rc = b200_slot_upload(G.ctx, slot, planes, strides);
+            if (!rc) rc = b200_sync(G.ctx);
+            if (rc) fail(rc, b200_last_error(G.ctx));
+        }
+    }
     pthread_mutex_unlock(&G.mu);
-    if (erc) return g.err;
-    if (G.dump_dir) return 0;
-    int slot = -1;
-    for (int i = 0; i < 32; i++) if (s->DPB[i].frame && s->DPB[i].frame->data[0] == frame->data[0]) slot = i;
-    if (slot < 0) { fail(B200_EINVAL, "upload of a frame that is not in the DPB"); return g.err; }
-    const void *planes[3] = { frame->data[0], frame->data[1], frame->data[2] };
-    int64_t strides[3] = { frame->linesize[0], frame->linesize[1], frame->linesize[2] };
-    int rc = b200_slot_upload(G.ctx, slot, planes, strides);
-    if (!rc) rc = b200_sync(G.ctx);
-    if (rc) fail(rc, b200_last_error(G.ctx));
-    return rc;
+    return rc ? g.err : 0;
+}
+
+/* ---- pinned host frames ------------------------------------------------------------------------------------------
+ * Allocator for the decoder's frame pool (libavcodec/utils.c:558-561 passes av_buffer_allocz): the picture planes live in
+ * page-locked memory, so the read-back of a picture is one asynchronous DMA at full PCIe rate instead of a staged,
+ * synchronous copy.  Falls back to the stock allocator without a device.  libavutil is reached through dlsym: the shim
+ * must load on its own (tests, tools) without the decoder library. */
+typedef struct AVBufferRef *(*av_buffer_create_fn)(uint8_t *, int, void (*)(void *, uint8_t *), void *, int);
+typedef struct AVBufferRef *(*av_buffer_allocz_fn)(int);
+static void frame_buffer_free(void *opaque, uint8_t *data) { (void)opaque; b200_host_free(data); }
+struct AVBufferRef *b200_frame_buffer_alloc(int size)
+{
+    static av_buffer_create_fn create; static av_buffer_allocz_fn allocz;
+    if (!create) { create = (av_buffer_create_fn)dlsym(RTLD_DEFAULT, "av_buffer_create"); allocz = (av_buffer_allocz_fn)dlsym(RTLD_DEFAULT, "av_buffer_allocz"); }
+    if (!create || !allocz) return NULL;
+    static int use_pinned = -1;
+    if (use_pinned < 0) use_pinned = !getenv("B200_SHIM_DUMP") && !(getenv("B200_PINNED_FRAMES") && !atoi(getenv("B200_PINNED_FRAMES")));
+    uint8_t *p = use_pinned && size > 0 ? b200_host_alloc((uint64_t)size) : NULL;
+    if (!p) return allocz(size);
+    memset(p, 0, (size_t)size);
+    struct AVBufferRef *r = create(p, size, frame_buffer_free, NULL, 0);
+    if (!r) { b200_host_free(p); return NULL; }
+    return r;
 }
 
 void b200_shim_close(void)
 {
-    if (g.rec) b200_rec_destroy(g.rec);      /* recorders of other threads die with their threads' process */
-    if (G.ctx) b200_ctx_destroy(G.ctx);
-    G.ctx = NULL; G.next_ticket = G.turn = 0;
+    pthread_mutex_lock(&G.mu);
+    if (G.sub_running) {
+        drain_queue();
+        G.sub_stop = 1;
+        pthread_cond_broadcast(&G.cv_sub);
+        pthread_mutex_unlock(&G.mu);
+        pthread_join(G.sub_thread, NULL);
+        pthread_mutex_lock(&G.mu);
+        G.sub_running = 0;
+    }
     ShimThread *t = &g;
-    if (t != &g_oom) { const unsigned seq = t->frame_seq; memset(t, 0, sizeof(*t)); t->frame_seq = seq; }   /* workers compare (att, att_seq) */
+    for (int i = 0; i < 2; i++) if (t->recs[i]) { b200_rec_destroy(t->recs[i]); t->recs[i] = NULL; }      /* recorders of other threads die with the process */
+    t->rec = NULL;
+    if (G.ctx) { b200_sync(G.ctx); b200_ctx_destroy(G.ctx); }
+    G.ctx = NULL; G.next_ticket = G.turn = 0; G.err_code = 0; G.configured = 0;
+    for (int i = 0; i < MAX_RB; i++) G.rb[i].state = 0;
+    pthread_mutex_unlock(&G.mu);
+    if (t != &g_oom) { const unsigned seq = t->frame_seq; Job *jobs = t->jobs; if (jobs) memset(jobs, 0, 3 * sizeof(Job)); memset(t, 0, sizeof(*t)); t->frame_seq = seq; t->jobs = jobs; }   /* workers compare (att, att_seq) */
 }

@@ -12,7 +12,7 @@ if [ ! -d "$REF/libavcodec" ]; then echo "build_patched: $REF not present - keep
 [ -f "$OUT/libohevc_ref.so" ] || "$HERE/build_ref.sh"
 P=$OUT/patched/libavcodec
 mkdir -p "$P" "$OUT/obj_b200"
-for f in hevc.c hevcdsp.c hevcpred.c videodsp.c hevc_refs.c hevc_filter.c; do cp "$REF/libavcodec/$f" "$P/$f"; done
+for f in hevc.c hevcdsp.c hevcpred.c videodsp.c hevc_refs.c hevc_filter.c utils.c; do cp "$REF/libavcodec/$f" "$P/$f"; done
 inc='#include "b200hevc_tables.h"'
 # table hooks: one more arch-init call, exactly where the x86 / arm ones are (hevcdsp.c:1326-1327, hevcpred.c:84, videodsp.c:57-58)
 sed -i -e "0,/^#include/s//$inc\n#include/" \
@@ -25,7 +25,12 @@ sed -i -e "0,/^#include/s//$inc\n#include/" \
 sed -i -e "0,/^#include/s//$inc\n#include/" \
        -e 's/^\(\s*\)ff_thread_finish_setup(s->avctx);/\1if ((ret = b200_frame_begin(s)) < 0) goto fail;\n&/' \
        -e '/^\s*s->is_decoded = 1;/,/tiles_filters(s);/ s/^\(\s*\)tiles_filters(s);/&\n\1if ((ret = b200_frame_end(s)) < 0) goto fail;   \/* after the filters of tile threads *\//' \
-       -e 's|^\(\s*\)ret    = decode_nal_units(s, avpkt->data, avpkt->size);|&\n\1b200_frame_readback(s, s->is_decoded \&\& s->ref ? s->ref->frame : NULL);   /* NULL: no complete picture came out of the packet */|' "$P/hevc.c"
+       -e 's|^\(\s*\)ret    = decode_nal_units(s, avpkt->data, avpkt->size);|&\n\1b200_frame_readback(s, s->is_decoded \&\& s->ref ? s->ref->frame : NULL);   /* NULL: no complete picture came out of the packet */|' \
+       -e 's|^\(\s*\)av_frame_move_ref(data, s->output_frame);|\1b200_output_wait(s, s->output_frame);   /* the picture leaves the decoder: its read-back has landed */\n&|' \
+       -e '/^\s*ret = ff_hevc_output_frame(s, data, 1);/,/^\s*return ret;/ s|^\(\s*\)return ret;|&\n        if (ret > 0) b200_output_wait(s, data);|' "$P/hevc.c"
+# the decoder's frame pool in pinned memory (utils.c:558-561 passes av_buffer_allocz)
+sed -i -e "0,/^#include/s//$inc\n#include/" \
+       -e '/^static int update_frame_pool/,/^}/ s/^\(\s*\)av_buffer_allocz);/\1b200_frame_buffer_alloc);/' "$P/utils.c"
 # a reference picture the stream does not contain (hevc_refs.c:538-606 fills a grey frame on the host): the device slot gets the same fill
 sed -i -e "0,/^#include/s//$inc\n#include/" \
        -e '/^static HEVCFrame \*generate_missing_ref/,/^}/ s/^    return frame;/    b200_frame_fill(s, frame);\n&/' "$P/hevc_refs.c"
@@ -36,15 +41,15 @@ if [ -z "${B200_NO_COPY_GUARD:-}" ]; then
          -e '/^static void copy_CTB/,/^}/ s/^    int i;/&\n    if (b200_host_pixels_unused()) return;/' "$P/hevc_filter.c"
   grep -q "b200_host_pixels_unused" "$P/hevc_filter.c" || { echo "hook b200_host_pixels_unused was not inserted" >&2; exit 1; }
 fi
-for pat in ff_hevcdsp_init_b200 ff_hevcpred_init_b200 ff_videodsp_init_b200 b200_frame_begin b200_frame_end b200_frame_readback b200_frame_fill; do
+for pat in ff_hevcdsp_init_b200 ff_hevcpred_init_b200 ff_videodsp_init_b200 b200_frame_begin b200_frame_end b200_frame_readback b200_frame_fill b200_frame_buffer_alloc; do
   grep -q "$pat" "$P"/*.c || { echo "hook $pat was not inserted" >&2; exit 1; }
 done
 CFLAGS=$(cat "$OUT/cflags.txt")
-for f in hevc hevcdsp hevcpred videodsp hevc_refs hevc_filter; do
+for f in hevc hevcdsp hevcpred videodsp hevc_refs hevc_filter utils; do
   gcc $CFLAGS -fPIC -std=gnu99 -w -DPIC -I"$OUT/gen" -I"$REF/libavcodec" -I"$REF" -I"$REF/gpac/modules/openhevc_dec" -I"$ROOT/include" \
       -c "$P/$f.c" -o "$OUT/obj_b200/libavcodec_$f.o"
 done
-objs=$(ls "$OUT"/obj/*.o | grep -v -e 'libavcodec_hevc\.o' -e 'libavcodec_hevcdsp\.o' -e 'libavcodec_hevcpred\.o' -e 'libavcodec_videodsp\.o' -e 'libavcodec_hevc_refs\.o' -e 'libavcodec_hevc_filter\.o')
+objs=$(ls "$OUT"/obj/*.o | grep -v -e 'libavcodec_hevc\.o' -e 'libavcodec_hevcdsp\.o' -e 'libavcodec_hevcpred\.o' -e 'libavcodec_videodsp\.o' -e 'libavcodec_hevc_refs\.o' -e 'libavcodec_hevc_filter\.o' -e 'libavcodec_utils\.o')
 gcc -shared -o "$OUT/libohevc_b200.so" $objs "$OUT"/obj_b200/*.o -L"$ROOT/openhevc_b200" -lb200hevc_shim -lb200hevc \
     -Wl,-rpath,'$ORIGIN/../../openhevc_b200' -lm -lpthread
 echo "built $OUT/libohevc_b200.so"

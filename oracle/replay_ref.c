@@ -342,8 +342,9 @@ int ref_execute_blob_b200(const uint8_t *blob, uint8_t **planes, const int64_t *
     int (*fend)(HEVCContext *) = dlsym(so, "b200_frame_end");
     int (*fread)(HEVCContext *, AVFrame *) = dlsym(so, "b200_frame_readback");
     int (*fup)(HEVCContext *, AVFrame *) = dlsym(so, "b200_frame_upload_ref");
+    int (*fwait)(HEVCContext *, AVFrame *) = dlsym(so, "b200_output_wait");
     const char *(*ferr)(void) = dlsym(so, "b200_shim_error");
-    if (!init_dsp || !init_pred || !init_vdsp || !fbegin || !fend || !fread || !fup || !ferr) { snprintf(err, errlen, "shim lacks an entry point"); return -11; }
+    if (!init_dsp || !init_pred || !init_vdsp || !fbegin || !fend || !fread || !fup || !ferr || !fwait) { snprintf(err, errlen, "shim lacks an entry point"); return -11; }
     RefCtx *c = ref_ctx_new(h);
     init_dsp(&c->s->hevcdsp, c->bd);          /* exactly what ff_hevc_dsp_init would do last (hevcdsp.c:1326) */
     init_pred(&c->s->hpc, c->bd);
@@ -364,6 +365,7 @@ int ref_execute_blob_b200(const uint8_t *blob, uint8_t **planes, const int64_t *
     if (!rc) rc = execute(c, blob, planes, strides, n_slots);
     if (!rc) rc = fend(c->s); else fend(c->s);
     if (!rc) rc = fread(c->s, &fr[h->cur_slot]);
+    if (!rc) rc = fwait(c->s, &fr[h->cur_slot]);       /* hevc_decode_frame's hook where the picture leaves the decoder */
     if (rc) snprintf(err, errlen, "%s", ferr());
     c->fr = keep;
     free(fr);

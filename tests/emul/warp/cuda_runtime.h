@@ -92,6 +92,7 @@ static inline unsigned atomicOr(unsigned *p, unsigned v) { return __atomic_fetch
 static inline unsigned atomicMax(unsigned *p, unsigned v) { unsigned o = __atomic_load_n(p, __ATOMIC_RELAXED); while (v > o && !__atomic_compare_exchange_n(p, &o, v, false, __ATOMIC_RELAXED, __ATOMIC_RELAXED)) {} return o; }
 static inline void __nanosleep(unsigned) { emu_yield(); }
 static inline void __threadfence() { __atomic_thread_fence(__ATOMIC_SEQ_CST); }
+static inline void __threadfence_system() { __atomic_thread_fence(__ATOMIC_SEQ_CST); }
 static inline unsigned long long gtime() { return 0; }
 static inline uint32_t ld_relaxed(const uint32_t *p) { emu_yield(); return __atomic_load_n(p, __ATOMIC_RELAXED); }
 static inline void st_relaxed(uint32_t *p, uint32_t v) { __atomic_store_n(p, v, __ATOMIC_RELAXED); }
@@ -138,7 +139,7 @@ enum { cudaSuccess = 0, cudaErrorInvalidValue = 1 };
 typedef struct EmuStream *cudaStream_t;
 typedef struct EmuEvent *cudaEvent_t;
 enum cudaMemcpyKind { cudaMemcpyHostToHost, cudaMemcpyHostToDevice, cudaMemcpyDeviceToHost, cudaMemcpyDeviceToDevice, cudaMemcpyDefault };
-enum { cudaStreamNonBlocking = 1, cudaEventDisableTiming = 2, cudaHostAllocDefault = 0 };
+enum { cudaStreamNonBlocking = 1, cudaEventDisableTiming = 2, cudaHostAllocDefault = 0, cudaHostAllocMapped = 2, cudaHostRegisterDefault = 0 };
 enum cudaMemoryType { cudaMemoryTypeUnregistered = 0, cudaMemoryTypeHost = 1, cudaMemoryTypeDevice = 2 };
 struct cudaPointerAttributes { cudaMemoryType type; int device; void *devicePointer, *hostPointer; };
 struct cudaDeviceProp { char name[256]; int multiProcessorCount; int major, minor; size_t totalGlobalMem; int pciBusID, pciDeviceID, pciDomainID; };
@@ -149,6 +150,9 @@ cudaError_t cudaFree(void *p);
 cudaError_t cudaHostAlloc(void **p, size_t n, unsigned flags);
 template <typename T> static inline cudaError_t cudaHostAlloc(T **p, size_t n, unsigned flags) { return cudaHostAlloc((void **)p, n, flags); }
 cudaError_t cudaFreeHost(void *p);
+static inline cudaError_t cudaHostGetDevicePointer(void **d, void *h, unsigned) { *d = h; return cudaSuccess; }
+static inline cudaError_t cudaHostRegister(void *, size_t, unsigned) { return cudaSuccess; }
+static inline cudaError_t cudaHostUnregister(void *) { return cudaSuccess; }
 cudaError_t cudaPointerGetAttributes(cudaPointerAttributes *a, const void *p);
 static inline cudaError_t cudaMemcpy(void *d, const void *s, size_t n, cudaMemcpyKind) { memmove(d, s, n); return cudaSuccess; }
 static inline cudaError_t cudaMemcpyAsync(void *d, const void *s, size_t n, cudaMemcpyKind, cudaStream_t = nullptr) { memmove(d, s, n); return cudaSuccess; }

@@ -1054,17 +1054,35 @@ class StreamGen:
 
     def stream(self, frames, pattern="I"):
         """pattern: picture types in decode order after the leading IDR, cycled, e.g. "PB"; "I" = all IDR;
-        "RA" = random access: hierarchical-B GOPs of 4 (decode order I0 P4 B2 B1 B3 P8 B6 B5 B7 ..., output in POC order)"""
-        if pattern == "RA":
-            self.reorder = 2
+        "RA" = random access: hierarchical-B GOPs of 4 (decode order I0 P4 B2 B1 B3 P8 B6 B5 B7 ..., output in POC order);
+        "RA8" = hierarchical-B GOPs of 8 with an I picture every 32 (BASELINE.json configs 2-4)"""
+        if pattern in ("RA", "RA8"):
             self.plan = [dict(poc=0, type=2, neg=[], pos=[])]
-            a = 4
-            while len(self.plan) < frames:
-                self.plan += [dict(poc=a, type=1, neg=[a - 4], pos=[]),
-                              dict(poc=a - 2, type=0, neg=[a - 4], pos=[a]),
-                              dict(poc=a - 3, type=0, neg=[a - 4], pos=[a - 2, a]),
-                              dict(poc=a - 1, type=0, neg=[a - 2], pos=[a])]
-                a += 4
+            if pattern == "RA":
+                self.reorder = 2
+                a = 4
+                while len(self.plan) < frames:
+                    self.plan += [dict(poc=a, type=1, neg=[a - 4], pos=[]),
+                                  dict(poc=a - 2, type=0, neg=[a - 4], pos=[a]),
+                                  dict(poc=a - 3, type=0, neg=[a - 4], pos=[a - 2, a]),
+                                  dict(poc=a - 1, type=0, neg=[a - 2], pos=[a])]
+                    a += 4
+            else:
+                # BASELINE.json configs 2-4: hierarchical-B GOP 8 (decode order A8 B4 B2 B1 B3 B6 B5 B7), intra period 32 (the
+                # anchor at POC % 32 == 0 is an I picture, open GOP: the B pictures in front of it still reference the previous
+                # anchor).  Every picture's RPS lists what must stay in the DPB; its lists use the two nearest on either side.
+                self.reorder = 3
+                a = 8
+                while len(self.plan) < frames:
+                    self.plan += [dict(poc=a, type=2 if a % 32 == 0 else 1, neg=[a - 8], pos=[]),
+                                  dict(poc=a - 4, type=0, neg=[a - 8], pos=[a]),
+                                  dict(poc=a - 6, type=0, neg=[a - 8], pos=[a - 4, a]),
+                                  dict(poc=a - 7, type=0, neg=[a - 8], pos=[a - 6, a - 4, a]),
+                                  dict(poc=a - 5, type=0, neg=[a - 6], pos=[a - 4, a]),
+                                  dict(poc=a - 2, type=0, neg=[a - 4], pos=[a]),
+                                  dict(poc=a - 3, type=0, neg=[a - 4], pos=[a - 2, a]),
+                                  dict(poc=a - 1, type=0, neg=[a - 2], pos=[a])]
+                    a += 8
             self.plan = self.plan[:frames]
             out = self.vps() + self.sps() + self.pps()
             for k, pl in enumerate(self.plan):
@@ -1090,7 +1108,7 @@ def main():
     ap.add_argument("--seed", type=int, default=1)
     ap.add_argument("--qp", type=int, default=30)
     ap.add_argument("--no-sao", action="store_true")
-    ap.add_argument("--pattern", default="I", help='"RA" = random access (hierarchical-B GOP 4); else picture types after the IDR, e.g. "PB" (low-delay, 2 references)')
+    ap.add_argument("--pattern", default="I", help='"RA" = random access (hierarchical-B GOP 4), "RA8" = GOP 8 with intra period 32; else picture types after the IDR, e.g. "PB" (low-delay, 2 references)')
     ap.add_argument("--weighted", action="store_true")
     ap.add_argument("--cip", action="store_true", help="constrained_intra_pred_flag")
     ap.add_argument("--tqb", type=float, default=0.0, help="share of CUs coded with cu_transquant_bypass_flag")
