@@ -150,6 +150,19 @@ int  b200_rec_set_tqb(B200Rec *r, int log2_min_pu_size, int min_pu_width, int mi
 int  b200_rec_tu_parked(B200Rec *r, int plane, int x, int y, int log2, int kind, int flags, int col_limit, const int16_t *coeffs,
                         uint32_t *park_off);
 int  b200_rec_ccp(B200Rec *r, int plane, int x, int y, int log2, int scale, uint32_t off_y, int has_c, uint32_t off_c);
+/* Deblocking parameters derived on the device (B200DbdHeader in b200hevc_worklist.h): instead of the
+ * reference's per-edge filter calls (b200_rec_deblock) the picture carries their inputs.  b200_rec_bs_leaf = one call of
+ * ff_hevc_deblocking_boundary_strengths() (hevc_filter.c:805; top / left: that edge of the block takes part, :832-839 /
+ * :870-877 evaluated by the caller); b200_rec_set_dbd, once all CTBs are parsed, hands over s->qp_y_tab, s->deblock[] and
+ * -- for streams with PCM-loop-filter-off / transquant-bypass blocks -- s->is_pcm (else NULL). */
+typedef struct B200DbdInput {
+    int32_t log2_min_cb_size, min_cb_width, min_cb_height; const int8_t *qp_y;       /* s->qp_y_tab */
+    int32_t log2_min_pu_size, min_pu_width, min_pu_height; const uint8_t *is_pcm;    /* s->is_pcm or NULL */
+    const int8_t *ctb_offsets;                                                       /* s->deblock[]: beta_offset, tc_offset per CTB */
+    int32_t cb_qp_offset, cr_qp_offset;                                              /* pps */
+} B200DbdInput;
+int  b200_rec_bs_leaf(B200Rec *r, int x0, int y0, int log2_size, int top, int left);
+int  b200_rec_set_dbd(B200Rec *r, const B200DbdInput *in);
 /* host helper shared by the recorder and by external blob builders: permutation (perm[new] = old) that sorts decode-order
  * intra records by dependency level (stable); returns the number of levels (>= 0) or a negative error */
 int  b200_intra_level_order(const B200IntraRec *recs, uint32_t n, int width, int height, int chroma_format_idc, uint32_t *perm);

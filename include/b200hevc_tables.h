@@ -17,6 +17,10 @@
  *   b200_frame_buffer_alloc  allocator for the decoder's frame pool in place of av_buffer_allocz (libavcodec/utils.c:558-561):
  *                          picture planes in page-locked memory, so that read-backs are asynchronous DMAs at full PCIe rate
  *   b200_frame_fill        when generate_missing_ref() has filled a grey reference  (libavcodec/hevc_refs.c:538-606)
+ *   b200_bs_on_device      first statement of ff_hevc_deblocking_boundary_strengths() (libavcodec/hevc_filter.c:808): the call is
+ *                          recorded as one word and the function returns (non-zero result)
+ *   b200_deblock_on_device first statement of deblocking_filter_CTB() (libavcodec/hevc_filter.c:347): non-zero = the device
+ *                          derives boundary strengths, tc and beta itself, nothing to do on the host
  *   b200_host_pixels_unused  OPTIONAL, performance only: guard at the top of copy_CTB()  (libavcodec/hevc_filter.c:151-161) --
  *                          sao_filter_CTB copies every CTB between the host frame and sao_frame before it calls the SAO
  *                          tables; with the tables on the device nobody reads those host pixels
@@ -53,6 +57,8 @@ int  b200_output_wait(struct HEVCContext *s, struct AVFrame *frame);        /* t
 struct AVBufferRef *b200_frame_buffer_alloc(int size);                      /* frame-pool allocator: pinned host memory */
 int  b200_frame_fill(struct HEVCContext *s, struct HEVCFrame *frame);       /* grey reference picture (generate_missing_ref) */
 int  b200_frame_upload_ref(struct HEVCContext *s, struct AVFrame *frame);   /* host-only reference picture -> device slot */
+int  b200_bs_on_device(struct HEVCContext *s, int x0, int y0, int log2_size);
+int  b200_deblock_on_device(void);
 int  b200_host_pixels_unused(void);                                         /* 1 once the B200 tables are installed */
 void b200_shim_close(void);
 const char *b200_shim_error(void);

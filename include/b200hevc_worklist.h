@@ -72,8 +72,36 @@ typedef struct B200BlobHeader {
                                     (restore_tqb_pixels, hevc_filter.c:163-193 -- with its two quirks, see k_sao.cuh)                        */
     B200Section ccp;             /* 4:4:4 pictures of streams with cross_component_prediction_enabled_flag (else count = 0): B200CcpRec[count],
                                     executed between the residual stage and the intra stage                                            */
-    uint32_t reserved[64 - 19 - 2 * B200_SEC_COUNT];
+    B200Section dbd;             /* deblocking parameters derived ON THE DEVICE (else count = 0): uint32 words, a
+                                    B200DbdHeader followed by the arrays it names.  A picture carries either the DBK grids (the
+                                    reference's own per-edge calls, recorded) or this section (its inputs: transform-tree leaves,
+                                    QP map, per-CTB offsets; motion and cbf come from the MC / TU records), never both -- except in
+                                    check mode (B200_DBD_CHECK), where the device compares what it derived with the recorded grids */
+    uint32_t reserved[64 - 21 - 2 * B200_SEC_COUNT];
 } B200BlobHeader;               /* 256 bytes */
+
+/* ---- on-device derivation of the deblocking parameters (hevc_filter.c:345-581 control half, :584-941) --------------------
+ * What the reference computes on the host between the parse and the filter calls -- boundary strengths from the motion field
+ * and the coded-block flags (ff_hevc_deblocking_boundary_strengths), then tc / beta per edge from the QP map and the slice
+ * offsets (deblocking_filter_CTB) -- from inputs that are already in the blob (MC records: motion; luma TU records: cbf) plus:
+ *   leaves   one uint32 per ff_hevc_deblocking_boundary_strengths() call (hevc.c:1578, 1607, 2400, 2484):
+ *            bits 0..11 x0 >> 2, 12..23 y0 >> 2, 24..26 log2_size - 2 (transform blocks 4x4 .. coding blocks 64x64), bit 28 the top edge
+ *            takes part (hevc_filter.c:832-839 evaluated on the host: slice / tile boundary rules), bit 29 the left edge (:870-877)
+ *   qp       int8 per min coding block (s->qp_y_tab), row-major
+ *   ctb      2 x int8 per CTB: beta_offset, tc_offset (s->deblock[], hevc.c:2677-2678)
+ *   pcm      uint8 per min PU (s->is_pcm), only when flags & B200_DBDF_PCM (pcm loop filter off / transquant bypass: no_p / no_q) */
+#define B200_DBD_LEAF(x0, y0, log2, top, left) \
+    ((uint32_t)((x0) >> 2) | ((uint32_t)((y0) >> 2) << 12) | ((uint32_t)((log2) - 2) << 24) | ((uint32_t)((top) != 0) << 28) | ((uint32_t)((left) != 0) << 29))
+#define B200_DBDF_PCM 1u
+typedef struct B200DbdHeader {   /* 16 words */
+    uint32_t flags;              /* B200_DBDF_* */
+    uint32_t log2_min_cb_size, min_cb_width, min_cb_height;     /* geometry of qp[] */
+    uint32_t log2_min_pu_size, min_pu_width, min_pu_height;     /* geometry of pcm[] */
+    int32_t  cb_qp_offset, cr_qp_offset;                        /* pps, chroma_tc() hevc_filter.c:62-88 */
+    uint32_t n_leaf;
+    uint32_t off_leaf, off_qp, off_ctb, off_pcm;                /* byte offsets from the start of the section, 16-byte aligned */
+    uint32_t reserved[2];
+} B200DbdHeader;
 
 typedef struct B200CipHeader {   /* first 4 words of the CIP section */
     uint32_t log2_min_pu_size;   /* sps->log2_min_pu_size */

@@ -20,6 +20,7 @@ EXPORTS = [  # every symbol include/b200hevc.h declares
     "b200_slot_upload", "b200_slot_readback", "b200_slot_wait_readback", "b200_slot_fill", "b200_wait_uploads", "b200_sync", "b200_set_profiling", "b200_get_stage_ms",
     "b200_launch_count", "b200_rec_create", "b200_rec_destroy", "b200_rec_begin", "b200_rec_set_refs", "b200_rec_tu", "b200_rec_pcm",
     "b200_host_register", "b200_host_unregister", "b200_frame_submit_ex", "b200_upload_wait", "b200_slot_readback_async", "b200_readback_wait", "b200_poll_errors",
+    "b200_rec_bs_leaf", "b200_rec_set_dbd",
     "b200_rec_intra", "b200_rec_mc", "b200_rec_deblock", "b200_rec_sao", "b200_rec_set_cip", "b200_rec_set_tqb", "b200_rec_tu_parked", "b200_rec_ccp", "b200_rec_merge", "b200_rec_finish", "b200_intra_level_order",
 ]
 
@@ -38,6 +39,8 @@ def load():
         "b200_slot_bytes": (u64, [vp]),
         "b200_slot_devptr": (vp, [vp, i32, i32, C.POINTER(u64)]),
         "b200_stream": (vp, [vp]),
+        "b200_rec_bs_leaf": (i32, [vp, i32, i32, i32, i32, i32]),
+        "b200_rec_set_dbd": (i32, [vp, vp]),
         "b200_host_register": (i32, [vp, u64]),
         "b200_host_unregister": (i32, [vp]),
         "b200_frame_submit_ex": (i32, [vp, vp, u64, C.POINTER(C.c_uint32)]),

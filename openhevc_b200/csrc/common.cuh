@@ -109,6 +109,17 @@ int launch_ccp(cudaStream_t st, const B200CcpRec *recs, int count, int16_t *park
 int launch_intra(cudaStream_t st, const B200IntraRec *recs, int count, const int16_t *pool, const FrameDesc &cur, int bd,
                  uint2 *edges[3], const int edge_stride[3], uint32_t *counter, const uint32_t *cip_words, const B200CipHeader *cip_hdr, int cfi);
 int launch_deblock(cudaStream_t st, const uint16_t *grid, const B200DbkLayout &L, const FrameDesc &cur, int bd);
+// on-device derivation of the deblocking parameters (k_dbd.cuh): per-lane scratch, one allocation starting at `mot`
+struct DbdMaps {
+    uint4 *mot;             // per 4x4 luma unit: x = mv0 (x | y << 16), y = mv1, z = ref0 | ref1 << 8 | pred << 16 (0 intra, 1 one mv (in mv0), 3 two)
+    uint8_t *cbf;           // per unit: a luma transform block with coefficients covers it
+    uint8_t *bsv, *bsh;     // per unit: bs of its left / top edge
+    uint16_t *grid;         // B200_SEC_DBK layout
+    int uw, uh;             // units per row / rows
+};
+
+int launch_dbd(cudaStream_t st, const uint8_t *blob_dev, const B200BlobHeader &h, const B200DbdHeader &hd, const uint8_t *dbd, const DbdMaps &maps, size_t maps_bytes,
+               const B200DbkLayout &L, const RefTable &rt, int ctb_w, uint32_t *gate, const uint16_t *check);
 int launch_sao(cudaStream_t st, const B200SaoRec *grid, const FrameDesc &src, const FrameDesc &dst, int bd,
                int log2_ctb, int ctb_w, int ctb_h, int chroma_format_idc, const uint32_t *tqb_words, const B200CipHeader *tqb_hdr);
 int set_intra_trace(unsigned long long *p);

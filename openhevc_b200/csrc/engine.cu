@@ -39,6 +39,7 @@ struct Arena {
     uint64_t stage_bytes = 0;
     B200CipHeader cip_hdr = {};     // host copy of the resident blob's CIP section header (constrained_intra_pred pictures)
     B200CipHeader tqb_hdr = {};     // ... and of its TQB section header (restore_tqb_pixels)
+    B200DbdHeader dbd_hdr = {};     // ... and of its DBD section header (deblocking parameters derived on the device)
     B200BlobHeader hdr;             // host copy of the resident blob's header
     bool resident = false;
     cudaEvent_t ev_uploaded = nullptr;
@@ -53,6 +54,8 @@ struct Lane {
     uint2 *flags[3] = { nullptr, nullptr, nullptr };   // intra edge records, 16 B per 4x4 unit
     uint32_t *counter = nullptr;        // [0] K3 ticket, [1] validation gate of the picture in progress, [2] K3 time-out latch, [3] validation latch
     int16_t *parked = nullptr;          // residuals of intra TUs (K2 -> K3), indexed like the coefficient pool
+    DbdMaps dbd = {};                   // scratch of the on-device deblocking derivation, allocated with the first picture that needs it
+    size_t dbd_bytes = 0;
     cudaEvent_t tail = nullptr;         // end of the last picture of this lane
     bool used = false;
 };
@@ -265,6 +268,7 @@ extern "C" void b200_ctx_destroy(B200Ctx *ctx)
         for (int p = 0; p < 3; p++) if (L.flags[p]) cudaFree(L.flags[p]);
         if (L.counter) cudaFree(L.counter);
         if (L.parked) cudaFree(L.parked);
+        if (L.dbd.mot) cudaFree(L.dbd.mot);
         if (L.tail) cudaEventDestroy(L.tail);
         if (L.st) cudaStreamDestroy(L.st);
     }
@@ -417,6 +421,18 @@ static int check_blob(B200Ctx *ctx, const B200BlobHeader *h, uint64_t nbytes)
         if (!(h->flags & B200_FRAME_CCP) || !h->ccp.count || (h->ccp.off & 15) || end > nbytes || c.chroma_format_idc != 3)
             return fail(ctx, B200_EINVAL, "CCP section out of bounds (or not a 4:4:4 picture)");
     }
+    if (h->dbd.count) {                                          // deblocking parameters derived on the device: header + arrays inside the section
+        const uint64_t sec_bytes = 4ull * h->dbd.count, end = (uint64_t)h->dbd.off + sec_bytes;
+        if ((h->dbd.off & 15) || end > nbytes || sec_bytes < sizeof(B200DbdHeader)) return fail(ctx, B200_EINVAL, "DBD section out of bounds");
+        const B200DbdHeader *dh = (const B200DbdHeader *)((const uint8_t *)h + h->dbd.off);
+        const uint64_t nqp = (uint64_t)dh->min_cb_width * dh->min_cb_height, npcm = (dh->flags & B200_DBDF_PCM) ? (uint64_t)dh->min_pu_width * dh->min_pu_height : 0;
+        if (dh->log2_min_cb_size < 3 || dh->log2_min_cb_size > 6 || dh->min_cb_width != ((uint32_t)c.width >> dh->log2_min_cb_size) || dh->min_cb_height != ((uint32_t)c.height >> dh->log2_min_cb_size) ||
+            (npcm && (dh->log2_min_pu_size < 2 || dh->log2_min_pu_size > 5 || dh->min_pu_width != ((uint32_t)c.width >> dh->log2_min_pu_size) || dh->min_pu_height != ((uint32_t)c.height >> dh->log2_min_pu_size))) ||
+            ((dh->off_leaf | dh->off_qp | dh->off_ctb | dh->off_pcm) & 3) || (uint64_t)dh->off_leaf + 4ull * dh->n_leaf > sec_bytes || (uint64_t)dh->off_qp + nqp > sec_bytes ||
+            (uint64_t)dh->off_ctb + 2ull * ctx->ctb_w * ctx->ctb_h > sec_bytes || (uint64_t)dh->off_pcm + npcm > sec_bytes ||
+            dh->cb_qp_offset < -12 || dh->cb_qp_offset > 12 || dh->cr_qp_offset < -12 || dh->cr_qp_offset > 12)
+            return fail(ctx, B200_EINVAL, "DBD section does not match the picture geometry");
+    }
     if (h->mc_big_count > h->sec[B200_SEC_MC].count) return fail(ctx, B200_EINVAL, "mc_big_count %u > %u MC records", h->mc_big_count, h->sec[B200_SEC_MC].count);
     if (h->sec[B200_SEC_DBK].count && h->sec[B200_SEC_DBK].count != ctx->dbk.total) return fail(ctx, B200_EINVAL, "deblock grid size %u != %u", h->sec[B200_SEC_DBK].count, ctx->dbk.total);
     if (h->sec[B200_SEC_SAO].count && h->sec[B200_SEC_SAO].count != (uint32_t)(3 * ctx->ctb_w * ctx->ctb_h)) return fail(ctx, B200_EINVAL, "SAO grid size mismatch");
@@ -551,6 +567,7 @@ extern "C" int b200_frame_upload(B200Ctx *ctx, const void *blob, uint64_t nbytes
     a.hdr = *h;
     if (h->cip.count) a.cip_hdr = *(const B200CipHeader *)((const uint8_t *)blob + h->cip.off);
     if (h->tqb.count) a.tqb_hdr = *(const B200CipHeader *)((const uint8_t *)blob + h->tqb.off);
+    if (h->dbd.count) a.dbd_hdr = *(const B200DbdHeader *)((const uint8_t *)blob + h->dbd.off);
     a.resident = true;
     return 0;
 }
@@ -647,9 +664,24 @@ extern "C" int b200_frame_execute_ex(B200Ctx *ctx, int arena, int cur_slot, cons
                                   (h.flags & B200_FRAME_CIP) && h.cip.count ? (const uint32_t *)(a.dev + h.cip.off) : nullptr, &a.cip_hdr, ctx->cfg.chroma_format_idc);
     if (pf) CU(cudaEventRecord(ctx->prof[3], st));
     if (tr) CU(cudaEventRecord(tr->ev[3], st));
-    // K4 deblock
-    if (h.sec[B200_SEC_DBK].count)
-        ctx->launches += launch_deblock(st, (const uint16_t *)(a.dev + h.sec[B200_SEC_DBK].off), ctx->dbk, cur, bd);
+    // K4 deblock: the edge parameters come recorded from the reference's own filter calls (DBK grids) or are derived here from
+    // the picture's motion, coded-block flags and QP map (DBD section, k_dbd.cuh); with both present the two are compared
+    const uint16_t *grid = h.sec[B200_SEC_DBK].count ? (const uint16_t *)(a.dev + h.sec[B200_SEC_DBK].off) : nullptr;
+    if (h.dbd.count) {
+        if (!L.dbd.mot) {
+            const size_t U = (size_t)(ctx->pw[0] / 4) * (ctx->ph[0] / 4);
+            const size_t o_cbf = 16 * U, o_bsv = o_cbf + ((U + 15) & ~(size_t)15), o_bsh = o_bsv + ((U + 15) & ~(size_t)15), o_grid = o_bsh + ((U + 15) & ~(size_t)15);
+            L.dbd_bytes = o_grid + 2 * (size_t)ctx->dbk.total;
+            uint8_t *m = nullptr;
+            CU(cudaMalloc(&m, L.dbd_bytes));
+            L.dbd.mot = (uint4 *)m; L.dbd.cbf = m + o_cbf; L.dbd.bsv = m + o_bsv; L.dbd.bsh = m + o_bsh; L.dbd.grid = (uint16_t *)(m + o_grid);
+            L.dbd.uw = ctx->pw[0] / 4; L.dbd.uh = ctx->ph[0] / 4;
+        }
+        ctx->launches += launch_dbd(st, a.dev, h, a.dbd_hdr, a.dev + h.dbd.off, L.dbd, L.dbd_bytes, ctx->dbk, rt, ctx->ctb_w, L.counter, grid);
+        grid = L.dbd.grid;
+    }
+    if (grid)
+        ctx->launches += launch_deblock(st, grid, ctx->dbk, cur, bd);
     if (pf) CU(cudaEventRecord(ctx->prof[4], st));
     if (tr) CU(cudaEventRecord(tr->ev[4], st));
     // K5 SAO

@@ -1303,6 +1303,11 @@ __global__ void __launch_bounds__(256, 2) k_sao(const B200SaoRec *__restrict__ g
     sao_thread<PIX>(grid, src, dst, bd, log2_ctb, ctb_w, ctb_h, cfi, tile_base, tiles_x, tq, blockIdx.x * 8 + (threadIdx.x >> 5), threadIdx.x & 31);
 }
 
+// --------------------------------------------------------------------------------------------
+// K4a-c: deblocking parameters derived on the device (k_dbd.cuh)
+// --------------------------------------------------------------------------------------------
+#include "k_dbd.cuh"
+
 template <typename PIX>
 __global__ void k_fill(FrameDesc f, int value)
 {
@@ -1434,6 +1439,35 @@ int launch_deblock(cudaStream_t st, const uint16_t *grid, const B200DbkLayout &L
     if (bd > 8) B200_LAUNCH(g, DBK_THREADS, 0, st, k_deblock<uint16_t>)(grid, L, cur, bd);
     else        B200_LAUNCH(g, DBK_THREADS, 0, st, k_deblock<uint8_t>)(grid, L, cur, bd);
     return 1;
+}
+
+// Derives the picture's deblocking grids on the device into `maps.grid`; `check` (device pointer to the grid recorded from the
+// reference's own calls, or null) compares the two.  `dbd` = device copy of the blob's DBD section, `hd` = host copy of its header.
+int launch_dbd(cudaStream_t st, const uint8_t *blob_dev, const B200BlobHeader &h, const B200DbdHeader &hd, const uint8_t *dbd, const DbdMaps &maps, size_t maps_bytes,
+               const B200DbkLayout &L, const RefTable &rt, int ctb_w, uint32_t *gate, const uint16_t *check)
+{
+    DbdArgs a;
+    a.blob = blob_dev;
+    a.mc = h.sec[B200_SEC_MC];
+    for (int k = 0; k < 4; k++) a.tu[k] = h.sec[B200_SEC_TU4 + k];
+    a.leaf = reinterpret_cast<const uint32_t *>(dbd + hd.off_leaf); a.n_leaf = (int)hd.n_leaf;
+    a.qp = reinterpret_cast<const int8_t *>(dbd + hd.off_qp); a.log2_min_cb = (int)hd.log2_min_cb_size; a.min_cb_w = (int)hd.min_cb_width;
+    a.ctb = reinterpret_cast<const int8_t *>(dbd + hd.off_ctb);
+    a.pcm = (hd.flags & B200_DBDF_PCM) ? dbd + hd.off_pcm : nullptr;
+    a.log2_min_pu = (int)hd.log2_min_pu_size; a.min_pu_w = (int)hd.min_pu_width; a.min_pu_h = (int)hd.min_pu_height;
+    a.cb_qp_offset = hd.cb_qp_offset; a.cr_qp_offset = hd.cr_qp_offset;
+    a.width = h.width; a.height = h.height; a.cfi = h.chroma_format_idc; a.log2_ctb = h.log2_ctb_size; a.ctb_w = ctb_w;
+    a.rt = rt;
+    cudaMemsetAsync(maps.mot, 0, maps_bytes, st);                    // one allocation: motion map (0 = intra), cbf, bs, grid
+    int n = 0;
+    uint32_t most = a.mc.count;
+    for (int k = 0; k < 4; k++) if (a.tu[k].count > most) most = a.tu[k].count;
+    if (most) { B200_LAUNCH((most + 255) / 256, 256, 0, st, k_dbd_raster)(a, maps, gate); n++; }
+    if (a.n_leaf) { B200_LAUNCH((a.n_leaf + 7) / 8, 256, 0, st, k_dbd_bs)(a, maps, gate); n++; }
+    const dim3 g((a.width / 8 + 255) / 256, a.height / 8, 4);
+    B200_LAUNCH(g, 256, 0, st, k_dbd_params)(a, maps, L, gate); n++;
+    if (check) { B200_LAUNCH((L.total + 255) / 256, 256, 0, st, k_dbd_compare)(maps.grid, check, L.total, gate); n++; }
+    return n;
 }
 
 int launch_sao(cudaStream_t st, const B200SaoRec *grid, const FrameDesc &src, const FrameDesc &dst, int bd,

@@ -29,6 +29,8 @@ struct B200Rec {
     std::vector<uint32_t> cip;   // B200CipHeader + bitmap of a constrained_intra_pred picture (b200_rec_set_cip), else empty
     std::vector<B200CcpRec> ccp; // cross-component prediction records (b200_rec_ccp), executed between the residual and the intra stage
     std::vector<uint32_t> tqb;   // B200CipHeader + bitmap of the PUs restore_tqb_pixels gives their deblocked samples back (b200_rec_set_tqb)
+    std::vector<uint32_t> leaf;  // on-device deblocking derivation: one word per ff_hevc_deblocking_boundary_strengths() call (b200_rec_bs_leaf)
+    std::vector<uint32_t> dbd;   // ... and the finished B200DbdHeader + arrays (b200_rec_set_dbd), else empty
     int last_intra[3];
     bool any_dbk = false, any_sao = false, open = false;
     bool merged = false;         // holds lists of several recording threads: intra records need re-ordering at finish
@@ -110,7 +112,7 @@ extern "C" uint64_t b200_worst_blob_bytes(const B200Config *c)
     const uint64_t nctb = (uint64_t)((c->width + ctb - 1) >> c->log2_ctb_size) * ((c->height + ctb - 1) >> c->log2_ctb_size);
     const uint64_t u = samples / 16 + (c->chroma_format_idc == 3 ? luma / 16 : 0);
     uint64_t v = 4096 + (samples + (c->chroma_format_idc == 3 ? luma : 0)) * 2 + u * (16 + 16 + 32 + 16 + 32) + (uint64_t)L.total * 2 + nctb * 3 * 16 +
-                 (samples >> 4) /* CIP + TQB bitmaps */ + (1u << 20);
+                 (samples >> 4) /* CIP + TQB bitmaps */ + luma / 16 * 4 + luma / 64 + luma / 16 + nctb * 2 /* DBD: leaves, QP, PCM, offsets */ + (1u << 20);
     if (c->max_blob_bytes && c->max_blob_bytes < v) v = c->max_blob_bytes;
     return (v + 4095) & ~(uint64_t)4095;
 }
@@ -173,7 +175,7 @@ extern "C" int b200_rec_begin(B200Rec *r, int cur_slot, int poc)
     if (!r || cur_slot < 0 || cur_slot > 255) return B200_EINVAL;
     memset(r->blob + r->off_dbk, 0, r->off_pool - r->off_dbk);
     for (int s = 0; s < 4; s++) r->tu[s].clear();
-    r->intra.clear(); r->mc.clear(); r->cip.clear(); r->tqb.clear(); r->ccp.clear();
+    r->intra.clear(); r->mc.clear(); r->cip.clear(); r->tqb.clear(); r->ccp.clear(); r->leaf.clear(); r->dbd.clear();
     r->ncoef = 0; r->npark = 0; r->any_dbk = r->any_sao = false;
     r->last_intra[0] = r->last_intra[1] = r->last_intra[2] = -1;
     r->cur_slot = cur_slot; r->poc = poc; r->open = true; r->nbytes = 0; r->n_ref = 0; r->merged = false;
@@ -415,6 +417,7 @@ extern "C" int b200_rec_merge(B200Rec *d, B200Rec *s)
         if (m.flags & B200_MCF_BI) m.ref1 = map[m.ref1];
         d->mc.push_back(m);
     }
+    d->leaf.insert(d->leaf.end(), s->leaf.begin(), s->leaf.end());
     if (s->any_dbk) {
         uint16_t *dg = (uint16_t *)(d->blob + d->off_dbk);
         const uint16_t *sg = (const uint16_t *)(s->blob + s->off_dbk);
@@ -493,6 +496,47 @@ extern "C" int b200_rec_set_tqb(B200Rec *r, int log2_min_pu_size, int min_pu_wid
     return 0;
 }
 
+// ---- deblocking parameters derived on the device (B200DbdHeader, include/b200hevc_worklist.h) ----
+// one call of ff_hevc_deblocking_boundary_strengths(s, x0, y0, log2_size): top / left = that edge of the block takes part
+// (hevc_filter.c:832-839, 870-877, evaluated by the caller)
+extern "C" int b200_rec_bs_leaf(B200Rec *r, int x0, int y0, int log2, int top, int left)
+{
+    if (!r || !r->open || log2 < 2 || log2 > 6 || x0 < 0 || y0 < 0 || (x0 & 3) || (y0 & 3) || x0 >= r->cfg.width || y0 >= r->cfg.height) return B200_EINVAL;
+    r->leaf.push_back(B200_DBD_LEAF(x0, y0, log2, top, left));
+    return 0;
+}
+
+extern "C" int b200_rec_set_dbd(B200Rec *r, const B200DbdInput *in)
+{
+    if (!r || !r->open || !in || !in->qp_y || !in->ctb_offsets) return B200_EINVAL;
+    const int W = r->cfg.width, H = r->cfg.height;
+    if (in->log2_min_cb_size < 3 || in->log2_min_cb_size > 6 || in->min_cb_width != (W >> in->log2_min_cb_size) || in->min_cb_height != (H >> in->log2_min_cb_size)) return B200_EINVAL;
+    if (in->is_pcm && (in->log2_min_pu_size < 2 || in->log2_min_pu_size > 5 || in->min_pu_width != (W >> in->log2_min_pu_size) || in->min_pu_height != (H >> in->log2_min_pu_size)))
+        return B200_EINVAL;
+    const uint32_t nqp = (uint32_t)in->min_cb_width * in->min_cb_height, nctb = (uint32_t)r->ctb_w * r->ctb_h;
+    const uint32_t npcm = in->is_pcm ? (uint32_t)in->min_pu_width * in->min_pu_height : 0;
+    B200DbdHeader h;
+    memset(&h, 0, sizeof(h));
+    h.flags = in->is_pcm ? B200_DBDF_PCM : 0;
+    h.log2_min_cb_size = (uint32_t)in->log2_min_cb_size; h.min_cb_width = (uint32_t)in->min_cb_width; h.min_cb_height = (uint32_t)in->min_cb_height;
+    h.log2_min_pu_size = (uint32_t)in->log2_min_pu_size; h.min_pu_width = (uint32_t)in->min_pu_width; h.min_pu_height = (uint32_t)in->min_pu_height;
+    h.cb_qp_offset = in->cb_qp_offset; h.cr_qp_offset = in->cr_qp_offset;
+    h.n_leaf = (uint32_t)r->leaf.size();
+    uint32_t o = sizeof(B200DbdHeader);
+    h.off_leaf = o; o = b200_align_u32(o + 4 * h.n_leaf, 16);
+    h.off_qp = o;   o = b200_align_u32(o + nqp, 16);
+    h.off_ctb = o;  o = b200_align_u32(o + 2 * nctb, 16);
+    h.off_pcm = o;  o = b200_align_u32(o + npcm, 16);
+    r->dbd.assign(o / 4, 0u);
+    uint8_t *b = (uint8_t *)r->dbd.data();
+    memcpy(b, &h, sizeof(h));
+    if (h.n_leaf) memcpy(b + h.off_leaf, r->leaf.data(), 4 * (size_t)h.n_leaf);
+    memcpy(b + h.off_qp, in->qp_y, nqp);
+    memcpy(b + h.off_ctb, in->ctb_offsets, 2 * (size_t)nctb);
+    if (npcm) memcpy(b + h.off_pcm, in->is_pcm, npcm);
+    return 0;
+}
+
 extern "C" int b200_rec_finish(B200Rec *r, const void **blob, uint64_t *nbytes)
 {
     if (!r || !r->open || !blob || !nbytes) return B200_EINVAL;
@@ -500,7 +544,7 @@ extern "C" int b200_rec_finish(B200Rec *r, const void **blob, uint64_t *nbytes)
         uint64_t need = b200_align_u32(r->off_pool + ((r->ncoef + 7) & ~7u) * 2, 256);
         for (int s = 0; s < 4; s++) need += ((uint64_t)r->tu[s].size() * 16 + 255) & ~(uint64_t)255;
         need += (((uint64_t)r->intra.size() * 16 + 255) & ~(uint64_t)255) + (((uint64_t)r->mc.size() * 32 + 255) & ~(uint64_t)255);
-        need += r->cip.size() * 4 + r->tqb.size() * 4 + r->ccp.size() * sizeof(B200CcpRec) + 4 * 256;
+        need += r->cip.size() * 4 + r->tqb.size() * 4 + r->dbd.size() * 4 + r->ccp.size() * sizeof(B200CcpRec) + 5 * 256;
         if (rec_grow(r, need)) return B200_ENOMEM;
     }
     B200BlobHeader *h = (B200BlobHeader *)r->blob;
@@ -589,6 +633,13 @@ extern "C" int b200_rec_finish(B200Rec *r, const void **blob, uint64_t *nbytes)
                     }
                 if (any) for (int pl = 0; pl < 3; pl++) g[(pl * r->ctb_h + cy) * r->ctb_w + cx].tqb = 1;
             }
+    }
+    if (!r->dbd.empty()) {                                   // deblocking parameters derived on the device
+        if (o + r->dbd.size() * 4 + 256 > r->cap) return B200_ENOMEM;
+        h->dbd.off = (uint32_t)o; h->dbd.count = (uint32_t)r->dbd.size();
+        memcpy(r->blob + o, r->dbd.data(), r->dbd.size() * 4);
+        o = (o + r->dbd.size() * 4 + 255) & ~(uint64_t)255;
+        h->flags |= B200_FRAME_HAS_DEBLOCK;
     }
     h->total_bytes = (uint32_t)o;
     r->nbytes = o; r->open = false;

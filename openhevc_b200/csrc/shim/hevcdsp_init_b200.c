@@ -125,6 +125,7 @@ typedef struct ShimThread {
     HEVCContext *s; int ccp; HEVCLocalContext *lc;
     int counted;                                         /* this thread's picture is part of G.in_flight */
     int pic_cip, pic_tqb;                                /* the picture in progress needs the PU-type / is_pcm hand-over at its end */
+    int dbd;                                             /* deblocking parameters of the picture in progress: 0 recorded from the host's filter calls, 1 derived on the device, 2 both (check) */
     struct { int x, y, log2, kind, flags, cl, parked; uint32_t park; } last_y;
     uint8_t fill_slot[16]; int n_fill;                  /* generate_missing_ref (hevc_refs.c:538): grey references this picture needs */
 } ShimThread;
@@ -194,7 +195,7 @@ static int attach_slow(void)
             memcpy(g.reg, o->reg, sizeof(g.reg)); g.n_reg = o->n_reg;
             for (int p = 0; p < 3; p++) { g.cur_base[p] = o->cur_base[p]; g.cur_ls[p] = o->cur_ls[p]; g.cur_size[p] = o->cur_size[p]; g.cur_inv[p] = o->cur_inv[p]; }
             g.cur_slot = o->cur_slot; g.poc = o->poc;
-            g.s = o->s; g.ccp = o->ccp; g.lc = NULL; g.last_y.log2 = 0;
+            g.s = o->s; g.ccp = o->ccp; g.lc = NULL; g.last_y.log2 = 0; g.dbd = o->dbd;
             g.n_ref = 0; g.pend_ptr = NULL; g.first_tmp = NULL; g.emu[0].buf = g.emu[1].buf = NULL;
             g.n_tu = g.n_intra = g.n_pu = g.n_dbk = g.n_sao = 0;
             if (b200_rec_begin(g.rec, g.cur_slot, g.poc)) { fail(B200_ESTATE, "b200_rec_begin failed (worker)"); rc = -1; }
@@ -376,10 +377,11 @@ static int mc_fill(B200McRec *m, int list, const uint8_t *src, int mx, int my, i
     if (plane < 0) return -1;
     (void)chroma_hint;
     const int ri = ref_index(slot);
-    /* positions far outside the picture clamp sample by sample: pre-clamp the origin so that it fits int16 */
-    const int pw = G.pw[plane], ph = G.ph[plane];
-    if (sx < -80) sx = -80; if (sx > pw + 16) sx = pw + 16;
-    if (sy < -80) sy = -80; if (sy > ph + 16) sy = ph + 16;
+    /* The origin travels as int16.  A legal motion vector reaches 2^13 samples beyond a picture of at most 2^14, so this clamp
+     * never acts on a legal stream -- and must not: the device reads the block's motion vector back from source position
+     * and fraction (k_dbd.cuh).  Samples outside the picture clamp one by one on the device (videodsp_template.c:26-100). */
+    if (sx < -16384) sx = -16384; if (sx > 32767) sx = 32767;
+    if (sy < -16384) sy = -16384; if (sy > 32767) sy = 32767;
     if (list == 0) { m->ref0 = (uint8_t)ri; m->sx0 = (int16_t)sx; m->sy0 = (int16_t)sy; m->frac0 = (uint8_t)(mx | (my << 4)); }
     else           { m->ref1 = (uint8_t)ri; m->sx1 = (int16_t)sx; m->sy1 = (int16_t)sy; m->frac1 = (uint8_t)(mx | (my << 4)); }
     return plane;
@@ -527,6 +529,46 @@ static void rec_intra_2(HEVCContext *s, int x0, int y0, int c) { rec_intra(s, x0
 static void rec_intra_3(HEVCContext *s, int x0, int y0, int c) { rec_intra(s, x0, y0, 3, c); }
 static void rec_intra_4(HEVCContext *s, int x0, int y0, int c) { rec_intra(s, x0, y0, 4, c); }
 static void rec_intra_5(HEVCContext *s, int x0, int y0, int c) { rec_intra(s, x0, y0, 5, c); }
+
+/* ---- deblocking control on the device -------------------------------------------------------------------
+ * Two guards in hevc_filter.c: b200_bs_on_device() as the first statement of
+ * ff_hevc_deblocking_boundary_strengths() records the call as one word (position, size, and whether the block's top / left
+ * edge takes part: the slice / tile boundary rules of :832-839 / :870-877 need the local context, so they are evaluated here)
+ * and lets the function return; b200_deblock_on_device() does the same for deblocking_filter_CTB().  The device derives
+ * boundary strengths, tc and beta from the picture's own records (k_dbd.cuh).  B200_DBD=0: off (the reference derives, its
+ * filter calls are recorded); 2: both, and the device compares.  Pictures of tile streams decoded with several threads keep
+ * the host path (tiles_filters recomputes the strengths at tile borders with its own rules, hevc.c:2967-3003). */
+static int dbd_mode(void)
+{
+    static int mode = -1;
+    if (mode < 0) { const char *e = getenv("B200_DBD"); mode = e ? atoi(e) : 1; if (mode < 0 || mode > 2) mode = 0; }
+    return mode;
+}
+int b200_bs_on_device(HEVCContext *s, int x0, int y0, int log2_size)
+{
+    if (!attached() || !g.dbd) return 0;
+    const HEVCLocalContext *lc = s->HEVClc;
+    const int ctb_mask = (1 << s->sps->log2_ctb_size) - 1;
+    int top = 0, left = 0;
+    if (y0 > 0 && (y0 & 7) == 0) {
+        const int bd_slice = s->sh.slice_loop_filter_across_slices_enabled_flag || !(lc->slice_or_tiles_up_boundary & 1);
+        const int bd_tiles = s->pps->loop_filter_across_tiles_enabled_flag || !(lc->slice_or_tiles_up_boundary & 2);
+        top = (bd_slice && bd_tiles) || (y0 & ctb_mask);
+    }
+    if (x0 > 0 && (x0 & 7) == 0) {
+        const int bd_slice = s->sh.slice_loop_filter_across_slices_enabled_flag || !(lc->slice_or_tiles_left_boundary & 1);
+        const int bd_tiles = s->pps->loop_filter_across_tiles_enabled_flag || !(lc->slice_or_tiles_left_boundary & 2);
+        left = (bd_slice && bd_tiles) || (x0 & ctb_mask);
+    }
+    int rc = b200_rec_bs_leaf(g.rec, x0, y0, log2_size, top, left);
+    if (rc) fail(rc, "b200_rec_bs_leaf failed");
+    return g.dbd == 1;
+}
+int b200_deblock_on_device(void)
+{
+    ShimThread *t = g_self;
+    return t && (t->in_frame == 1 || (t->in_frame == 2 && t->att->in_frame == 1 && t->att->frame_seq == t->att_seq)) && t->dbd == 1;
+}
 
 /* ---- table installation ------------------------------------------------------------------------------------- */
 /* The host copies of the picture are dead once the tables record instead of computing: the one place where the reference
@@ -790,6 +832,8 @@ int b200_frame_begin(HEVCContext *s)
     /* cross-component prediction (4:4:4): host arithmetic between two table calls, undone and redone on the device (rec_cross_component) */
     g.s = s; g.lc = NULL; g.last_y.log2 = 0;
     g.ccp = s->sps->chroma_array_type == 3 && s->pps->cross_component_prediction_enabled_flag;
+    /* (a caller that drives the tables without the decoder's own state -- oracle/replay_ref.c -- has no QP map: its filter calls are recorded) */
+    g.dbd = ((s->pps->tiles_enabled_flag && s->threads_number != 1) || !s->qp_y_tab || !s->deblock) ? 0 : dbd_mode();
     /* the other of this thread's two recorders; its previous picture (two pictures back) has left host memory by now */
     g.cur ^= 1;
     if (g.jobs) job_reclaim(&g.jobs[g.cur]);
@@ -878,6 +922,19 @@ static int frame_end_of(HEVCContext *s, HEVCFrame *ref)
         /* restore_tqb_pixels (hevc_filter.c:163-193) is pixel work outside the tables: the device redoes it from is_pcm[] */
         int crc = b200_rec_set_tqb(g.rec, s->sps->log2_min_pu_size, s->sps->min_pu_width, s->sps->min_pu_height, s->is_pcm);
         if (crc) fail(crc, "b200_rec_set_tqb failed");
+    }
+    if (!g.err && g.dbd) {
+        /* deblocking parameters on the device: the QP map, the per-CTB slice offsets and (PCM loop filter off / bypass) is_pcm */
+        B200DbdInput in;
+        memset(&in, 0, sizeof(in));
+        in.log2_min_cb_size = s->sps->log2_min_cb_size; in.min_cb_width = s->sps->min_cb_width; in.min_cb_height = s->sps->min_cb_height; in.qp_y = s->qp_y_tab;
+        in.log2_min_pu_size = s->sps->log2_min_pu_size; in.min_pu_width = s->sps->min_pu_width; in.min_pu_height = s->sps->min_pu_height;
+        const int pcmf = (s->sps->pcm_enabled_flag && s->sps->pcm.loop_filter_disable_flag) || s->pps->transquant_bypass_enable_flag;
+        in.is_pcm = pcmf ? s->is_pcm : NULL;
+        in.ctb_offsets = (const int8_t *)s->deblock;
+        in.cb_qp_offset = s->pps->cb_qp_offset; in.cr_qp_offset = s->pps->cr_qp_offset;
+        int drc = sizeof(DBParams) == 2 ? b200_rec_set_dbd(g.rec, &in) : B200_ENOTSUP;
+        if (drc) fail(drc, "b200_rec_set_dbd failed");
     }
     if (g.err) { ticket_skip(); return g.err; }
     if (getenv("B200_SHIM_STATS"))

@@ -36,12 +36,15 @@ sed -i -e "0,/^#include/s//$inc\n#include/" \
        -e '/^static HEVCFrame \*generate_missing_ref/,/^}/ s/^    return frame;/    b200_frame_fill(s, frame);\n&/' "$P/hevc_refs.c"
 # optional, performance only (B200_NO_COPY_GUARD=1 builds without it): sao_filter_CTB's CTB copies between the host frame and
 # sao_frame feed nothing once the SAO tables record (hevc_filter.c:151-161)
+# deblocking control on the device: the two host functions that derive boundary strengths / tc / beta hand over
+sed -i -e '/^void ff_hevc_deblocking_boundary_strengths(HEVCContext \*s, int x0, int y0,/,/^}/ s/^    int i, j, bs;/&\n    if (b200_bs_on_device(s, x0, y0, log2_trafo_size)) return;/' \
+       -e '/^static void deblocking_filter_CTB/,/^}/ s/^    uint8_t \*src;/    uint8_t *src = NULL;\n    if (b200_deblock_on_device()) return;/' "$P/hevc_filter.c"
 if [ -z "${B200_NO_COPY_GUARD:-}" ]; then
   sed -i -e "0,/^#include/s//$inc\n#include/" \
          -e '/^static void copy_CTB/,/^}/ s/^    int i;/&\n    if (b200_host_pixels_unused()) return;/' "$P/hevc_filter.c"
   grep -q "b200_host_pixels_unused" "$P/hevc_filter.c" || { echo "hook b200_host_pixels_unused was not inserted" >&2; exit 1; }
 fi
-for pat in ff_hevcdsp_init_b200 ff_hevcpred_init_b200 ff_videodsp_init_b200 b200_frame_begin b200_frame_end b200_frame_readback b200_frame_fill b200_frame_buffer_alloc; do
+for pat in ff_hevcdsp_init_b200 ff_hevcpred_init_b200 ff_videodsp_init_b200 b200_frame_begin b200_frame_end b200_frame_readback b200_frame_fill b200_frame_buffer_alloc b200_bs_on_device b200_deblock_on_device; do
   grep -q "$pat" "$P"/*.c || { echo "hook $pat was not inserted" >&2; exit 1; }
 done
 CFLAGS=$(cat "$OUT/cflags.txt")

@@ -578,6 +578,239 @@ static void deblock_plane(pix_t *pl, int pw, int ph, int plane, const uint16_t *
 }
 
 /* ------------------------------------------------------------------------------------------
+ * Deblocking parameters derived from the picture's records (product: openhevc_b200/csrc/k_dbd.cuh).
+ * Restates, in the reference's own order, what the reference computes on the host:
+ *   the motion field and cbf_luma as the parse leaves them        hevc.c:1568-1576 (cbf), hevc.c hls_prediction_unit (tab_mvf)
+ *   ff_hevc_deblocking_boundary_strengths()                       hevc_filter.c:805-941, boundary_strength() :583-700
+ *   deblocking_filter_CTB(), CTB by CTB, its filter calls written into the grids the way the recorder writes the
+ *   reference's real calls (b200_rec_deblock)                     hevc_filter.c:345-581
+ * ---------------------------------------------------------------------------------------- */
+typedef struct OrcMvf { int16_t mx[2], my[2]; int ref[2]; int pred; } OrcMvf;     /* pred: 0 intra, 1 one motion vector (index 0), 3 two */
+typedef struct OrcDbd {
+    const B200BlobHeader *h; const B200DbdHeader *d; const uint8_t *sec;
+    int uw, uh; OrcMvf *mvf; uint8_t *cbf, *vbs, *hbs;
+    uint16_t *grid; B200DbkLayout L;
+} OrcDbd;
+static int orc_far(int ax, int ay, int bx, int by) { return abs(ax - bx) >= 4 || abs(ay - by) >= 4; }
+static int orc_boundary_strength(const OrcMvf *c, const OrcMvf *n)
+{
+    if (c->pred == 3 && n->pred == 3) {
+        if (c->ref[0] == n->ref[0] && c->ref[0] == c->ref[1] && n->ref[0] == n->ref[1])
+            return (orc_far(n->mx[0], n->my[0], c->mx[0], c->my[0]) || orc_far(n->mx[1], n->my[1], c->mx[1], c->my[1])) &&
+                   (orc_far(n->mx[1], n->my[1], c->mx[0], c->my[0]) || orc_far(n->mx[0], n->my[0], c->mx[1], c->my[1]));
+        if (n->ref[0] == c->ref[0] && n->ref[1] == c->ref[1])
+            return orc_far(n->mx[0], n->my[0], c->mx[0], c->my[0]) || orc_far(n->mx[1], n->my[1], c->mx[1], c->my[1]);
+        if (n->ref[1] == c->ref[0] && n->ref[0] == c->ref[1])
+            return orc_far(n->mx[1], n->my[1], c->mx[0], c->my[0]) || orc_far(n->mx[0], n->my[0], c->mx[1], c->my[1]);
+        return 1;
+    }
+    if (c->pred != 3 && n->pred != 3) return c->ref[0] == n->ref[0] ? orc_far(c->mx[0], c->my[0], n->mx[0], n->my[0]) : 1;
+    return 1;
+}
+static const OrcMvf *orc_mvf_at(const OrcDbd *o, int x, int y) { return &o->mvf[(y >> 2) * o->uw + (x >> 2)]; }
+static int orc_bs_tu_edge(const OrcDbd *o, int xc, int yc, int xn, int yn)
+{
+    const OrcMvf *c = orc_mvf_at(o, xc, yc), *n = orc_mvf_at(o, xn, yn);
+    if (!c->pred || !n->pred) return 2;
+    if (o->cbf[(yc >> 2) * o->uw + (xc >> 2)] || o->cbf[(yn >> 2) * o->uw + (xn >> 2)]) return 1;
+    return orc_boundary_strength(c, n);
+}
+static void orc_bs_leaf(OrcDbd *o, uint32_t leaf)
+{
+    const int x0 = (int)(leaf & 0xfff) << 2, y0 = (int)((leaf >> 12) & 0xfff) << 2, log2 = (int)((leaf >> 24) & 7) + 2, size = 1 << log2;
+    const int W = o->h->width, H = o->h->height;
+    if (x0 >= W || y0 >= H) return;
+    if ((leaf >> 28) & 1)
+        for (int i = 0; i < size && x0 + i < W; i += 4) o->hbs[(y0 >> 2) * o->uw + ((x0 + i) >> 2)] = (uint8_t)orc_bs_tu_edge(o, x0 + i, y0, x0 + i, y0 - 1);
+    if ((leaf >> 29) & 1)
+        for (int i = 0; i < size && y0 + i < H; i += 4) o->vbs[((y0 + i) >> 2) * o->uw + (x0 >> 2)] = (uint8_t)orc_bs_tu_edge(o, x0, y0 + i, x0 - 1, y0 + i);
+    if (log2 > (int)o->d->log2_min_pu_size && orc_mvf_at(o, x0, y0)->pred) {
+        for (int i = 0; i < size && x0 + i < W; i += 4) {             /* :906-922, the running `top` */
+            const OrcMvf *top = orc_mvf_at(o, x0 + i, y0 + 8 - 1);
+            for (int j = 8; j < size && y0 + j < H; j += 8) {
+                const OrcMvf *curr = orc_mvf_at(o, x0 + i, y0 + j);
+                o->hbs[((y0 + j) >> 2) * o->uw + ((x0 + i) >> 2)] = (uint8_t)((curr->pred && top->pred) ? orc_boundary_strength(curr, top) : 1);
+                top = curr;
+            }
+        }
+        for (int j = 0; j < size && y0 + j < H; j += 4) {             /* :924-940 */
+            const OrcMvf *left = orc_mvf_at(o, x0 + 8 - 1, y0 + j);
+            for (int i = 8; i < size && x0 + i < W; i += 8) {
+                const OrcMvf *curr = orc_mvf_at(o, x0 + i, y0 + j);
+                o->vbs[((y0 + j) >> 2) * o->uw + ((x0 + i) >> 2)] = (uint8_t)((curr->pred && left->pred) ? orc_boundary_strength(curr, left) : 1);
+                left = curr;
+            }
+        }
+    }
+}
+static const uint8_t orc_tctable[54] = { 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 1, 1, 1, 1, 1, 1, 1, 1, 1, 2, 2, 2, 2, 3, 3, 3, 3, 4, 4, 4,
+                                         5, 5, 6, 6, 7, 8, 9, 10, 11, 13, 14, 16, 18, 20, 22, 24 };
+static const uint8_t orc_betatable[52] = { 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 6, 7, 8, 9, 10, 11, 12, 13, 14, 15, 16, 17, 18, 20, 22, 24, 26, 28, 30, 32, 34, 36,
+                                           38, 40, 42, 44, 46, 48, 50, 52, 54, 56, 58, 60, 62, 64 };
+static int orc_qpy(const OrcDbd *o, int x, int y)
+{
+    const int8_t *qp = (const int8_t *)(o->sec + o->d->off_qp);
+    int xc = x >> o->d->log2_min_cb_size, yc = y >> o->d->log2_min_cb_size;
+    if (yc >= (int)o->d->min_cb_height) yc = (int)o->d->min_cb_height - 1;      /* (the reference reads past the table there; the value is never used) */
+    if (xc >= (int)o->d->min_cb_width) xc = (int)o->d->min_cb_width - 1;
+    return qp[xc + yc * (int)o->d->min_cb_width];
+}
+static int orc_get_pcm(const OrcDbd *o, int x, int y)
+{
+    if (x < 0 || y < 0) return 2;
+    const int xp = x >> o->d->log2_min_pu_size, yp = y >> o->d->log2_min_pu_size;
+    if (xp >= (int)o->d->min_pu_width || yp >= (int)o->d->min_pu_height) return 2;
+    return o->sec[o->d->off_pcm + yp * o->d->min_pu_width + xp];
+}
+static int orc_chroma_tc(const OrcDbd *o, int qp_y, int c_idx, int tc_offset)
+{
+    static const int qp_c[] = { 29, 30, 31, 32, 33, 33, 34, 34, 35, 35, 36, 36, 37, 37 };
+    const int qp_i = clip3(qp_y + (c_idx == 1 ? o->d->cb_qp_offset : o->d->cr_qp_offset), 0, 57);
+    int qp;
+    if (o->h->chroma_format_idc == 1) qp = qp_i < 30 ? qp_i : qp_i > 43 ? qp_i - 6 : qp_c[qp_i - 30];
+    else qp = clip3(qp_i, 0, 51);
+    return orc_tctable[clip3(qp + 2 + tc_offset, 0, 53)];
+}
+#define ORC_TC_CALC(qp, bs) orc_tctable[clip3((qp) + 2 * ((bs) - 1) + (tc_offset >> 1 << 1), 0, 53)]
+/* one filter call of the reference, as the recorder writes it (recorder.cpp b200_rec_deblock) */
+static void orc_dbk_call(OrcDbd *o, int plane, int vertical, int x, int y, int beta, const int tc[2], const int no_p[2], const int no_q[2])
+{
+    int pw, ph;
+    b200_plane_dims(o->h->width, o->h->height, o->h->chroma_format_idc, plane, &pw, &ph);
+    uint16_t *g = o->grid + o->L.off[plane][vertical ? 0 : 1];
+    const int gs = (int)o->L.stride[plane][vertical ? 0 : 1];
+    for (int j = 0; j < 2; j++) {
+        const int sx = vertical ? x : x + 4 * j, sy = vertical ? y + 4 * j : y;
+        if (sx >= pw || sy >= ph) continue;
+        g[vertical ? (sy >> 2) * gs + (sx >> 3) : (sy >> 3) * gs + (sx >> 2)] = B200_DBK_PACK(tc[j], plane ? 0 : beta, no_p[j] != 0, no_q[j] != 0);
+    }
+}
+static void orc_deblocking_filter_ctb(OrcDbd *o, int x0, int y0)          /* hevc_filter.c:345-581 */
+{
+    const int W = o->h->width, H = o->h->height, log2_ctb = o->h->log2_ctb_size, ctb_size = 1 << log2_ctb;
+    const int ctb_w = (W + ctb_size - 1) >> log2_ctb;
+    const int ctb = (x0 >> log2_ctb) + (y0 >> log2_ctb) * ctb_w;
+    const int8_t *off = (const int8_t *)(o->sec + o->d->off_ctb);
+    const int cur_tc_offset = off[2 * ctb + 1], cur_beta_offset = off[2 * ctb];
+    const int left_tc_offset = x0 ? off[2 * (ctb - 1) + 1] : 0, left_beta_offset = x0 ? off[2 * (ctb - 1)] : 0;
+    const int pcmf = (o->d->flags & B200_DBDF_PCM) != 0;
+    const int cfi = o->h->chroma_format_idc, hs = cfi != 3, vs = cfi == 1;
+    int x_end = x0 + ctb_size > W ? W : x0 + ctb_size, y_end = y0 + ctb_size > H ? H : y0 + ctb_size;
+    int tc_offset = cur_tc_offset, beta_offset = cur_beta_offset;
+    int tc[2], c_tc[2], c_tc2[2], no_p[2] = { 0, 0 }, no_q[2] = { 0, 0 };
+#define VBS(x, y) ((y) < H && (x) < W ? o->vbs[((y) >> 2) * o->uw + ((x) >> 2)] : 0)
+#define HBS(x, y) ((y) < H && (x) < W ? o->hbs[((y) >> 2) * o->uw + ((x) >> 2)] : 0)
+    for (int y = y0; y < y_end; y += 8)                                   /* vertical edges, luma */
+        for (int x = x0 ? x0 : 8; x < x_end; x += 8) {
+            const int bs0 = VBS(x, y), bs1 = VBS(x, y + 4);
+            if (!bs0 && !bs1) continue;
+            const int qp = (orc_qpy(o, x - 1, y) + orc_qpy(o, x, y) + 1) >> 1;
+            const int beta = orc_betatable[clip3(qp + beta_offset, 0, 51)];
+            tc[0] = bs0 ? ORC_TC_CALC(qp, bs0) : 0; tc[1] = bs1 ? ORC_TC_CALC(qp, bs1) : 0;
+            if (pcmf) { no_p[0] = orc_get_pcm(o, x - 1, y); no_p[1] = orc_get_pcm(o, x - 1, y + 4); no_q[0] = orc_get_pcm(o, x, y); no_q[1] = orc_get_pcm(o, x, y + 4); }
+            orc_dbk_call(o, 0, 1, x, y, beta, tc, no_p, no_q);
+        }
+    if (cfi) {                                                            /* vertical edges, chroma */
+        const int h = 1 << hs, v = 1 << vs;
+        for (int y = y0; y < y_end; y += 8 * v)
+            for (int x = x0 ? x0 : 8 * h; x < x_end; x += 8 * h) {
+                const int bs0 = VBS(x, y), bs1 = VBS(x, y + 4 * v);
+                if (bs0 != 2 && bs1 != 2) continue;
+                const int qp0 = (orc_qpy(o, x - 1, y) + orc_qpy(o, x, y) + 1) >> 1, qp1 = (orc_qpy(o, x - 1, y + 4 * v) + orc_qpy(o, x, y + 4 * v) + 1) >> 1;
+                c_tc[0] = bs0 == 2 ? orc_chroma_tc(o, qp0, 1, tc_offset) : 0; c_tc[1] = bs1 == 2 ? orc_chroma_tc(o, qp1, 1, tc_offset) : 0;
+                c_tc2[0] = bs0 == 2 ? orc_chroma_tc(o, qp0, 2, tc_offset) : 0; c_tc2[1] = bs1 == 2 ? orc_chroma_tc(o, qp1, 2, tc_offset) : 0;
+                if (pcmf) { no_p[0] = orc_get_pcm(o, x - 1, y); no_p[1] = orc_get_pcm(o, x - 1, y + 4 * v); no_q[0] = orc_get_pcm(o, x, y); no_q[1] = orc_get_pcm(o, x, y + 4 * v); }
+                orc_dbk_call(o, 1, 1, x >> hs, y >> vs, 0, c_tc, no_p, no_q);
+                orc_dbk_call(o, 2, 1, x >> hs, y >> vs, 0, c_tc2, no_p, no_q);
+            }
+    }
+    const int x_end2 = x_end;                                             /* horizontal edges, luma */
+    if (x_end != W) x_end -= 8;
+    for (int y = y0 ? y0 : 8; y < y_end; y += 8) {
+        beta_offset = x0 ? left_beta_offset : cur_beta_offset;
+        for (int x = x0 ? x0 - 8 : 0; x < x_end; x += 8) {
+            const int bs0 = HBS(x, y), bs1 = HBS(x + 4, y);
+            if (bs0 || bs1) {
+                const int qp = (orc_qpy(o, x, y - 1) + orc_qpy(o, x, y) + 1) >> 1;
+                const int beta = orc_betatable[clip3(qp + beta_offset, 0, 51)];
+                tc[0] = bs0 ? ORC_TC_CALC(qp, bs0) : 0; tc[1] = bs1 ? ORC_TC_CALC(qp, bs1) : 0;
+                if (pcmf) { no_p[0] = orc_get_pcm(o, x, y - 1); no_p[1] = orc_get_pcm(o, x + 4, y - 1); no_q[0] = orc_get_pcm(o, x, y); no_q[1] = orc_get_pcm(o, x + 4, y); }
+                orc_dbk_call(o, 0, 0, x, y, beta, tc, no_p, no_q);
+            }
+            beta_offset = cur_beta_offset;
+        }
+    }
+    if (cfi) {                                                            /* horizontal edges, chroma */
+        const int h = 1 << hs, v = 1 << vs;
+        if (x_end2 != W) x_end = x_end2 - 8 * h;
+        for (int y = y0 ? y0 : 8 * v; y < y_end; y += 8 * v) {
+            tc_offset = x0 ? left_tc_offset : cur_tc_offset;
+            for (int x = x0 ? x0 - 8 * h : 0; x < x_end; x += 8 * h) {
+                const int bs0 = HBS(x, y), bs1 = HBS(x + 4 * h, y);
+                if (bs0 == 2 || bs1 == 2) {
+                    const int qp0 = bs0 == 2 ? (orc_qpy(o, x, y - 1) + orc_qpy(o, x, y) + 1) >> 1 : 0;
+                    const int qp1 = bs1 == 2 ? (orc_qpy(o, x + 4 * h, y - 1) + orc_qpy(o, x + 4 * h, y) + 1) >> 1 : 0;
+                    c_tc[0] = bs0 == 2 ? orc_chroma_tc(o, qp0, 1, tc_offset) : 0; c_tc[1] = bs1 == 2 ? orc_chroma_tc(o, qp1, 1, cur_tc_offset) : 0;
+                    c_tc2[0] = bs0 == 2 ? orc_chroma_tc(o, qp0, 2, tc_offset) : 0; c_tc2[1] = bs1 == 2 ? orc_chroma_tc(o, qp1, 2, cur_tc_offset) : 0;
+                    if (pcmf) { no_p[0] = orc_get_pcm(o, x, y - 1); no_p[1] = orc_get_pcm(o, x + 4 * h, y - 1); no_q[0] = orc_get_pcm(o, x, y); no_q[1] = orc_get_pcm(o, x + 4 * h, y); }
+                    orc_dbk_call(o, 1, 0, x >> hs, y >> vs, 0, c_tc, no_p, no_q);
+                    orc_dbk_call(o, 2, 0, x >> hs, y >> vs, 0, c_tc2, no_p, no_q);
+                }
+                tc_offset = cur_tc_offset;
+            }
+        }
+    }
+#undef VBS
+#undef HBS
+}
+/* grid (b200_dbk_layout, zero-filled by the caller) <- the picture's DBD section + MC / TU records */
+int orc_dbd_derive(const uint8_t *blob, uint16_t *grid)
+{
+    const B200BlobHeader *h = (const B200BlobHeader *)blob;
+    if (!h->dbd.count) return -1;
+    OrcDbd o;
+    memset(&o, 0, sizeof(o));
+    o.h = h; o.sec = blob + h->dbd.off; o.d = (const B200DbdHeader *)o.sec; o.grid = grid;
+    b200_dbk_layout(h->width, h->height, h->chroma_format_idc, &o.L);
+    o.uw = h->width / 4; o.uh = h->height / 4;
+    const size_t U = (size_t)o.uw * o.uh;
+    o.mvf = (OrcMvf *)calloc(U, sizeof(OrcMvf)); o.cbf = (uint8_t *)calloc(U, 1); o.vbs = (uint8_t *)calloc(U, 1); o.hbs = (uint8_t *)calloc(U, 1);
+    if (!o.mvf || !o.cbf || !o.vbs || !o.hbs) { free(o.mvf); free(o.cbf); free(o.vbs); free(o.hbs); return -3; }
+    const B200McRec *mc = (const B200McRec *)(blob + h->sec[B200_SEC_MC].off);
+    for (uint32_t i = 0; i < h->sec[B200_SEC_MC].count; i++) {           /* the motion field: what hls_prediction_unit left in tab_mvf */
+        const B200McRec *m = &mc[i];
+        if (m->plane) continue;
+        OrcMvf v;
+        memset(&v, 0, sizeof(v));
+        v.pred = (m->flags & B200_MCF_BI) ? 3 : 1;
+        v.mx[0] = (int16_t)(((m->sx0 - m->x) << 2) | (m->frac0 & 3)); v.my[0] = (int16_t)(((m->sy0 - m->y) << 2) | ((m->frac0 >> 4) & 3));
+        v.ref[0] = h->ref_slot[m->ref0 & 15];
+        if (v.pred == 3) {
+            v.mx[1] = (int16_t)(((m->sx1 - m->x) << 2) | (m->frac1 & 3)); v.my[1] = (int16_t)(((m->sy1 - m->y) << 2) | ((m->frac1 >> 4) & 3));
+            v.ref[1] = h->ref_slot[m->ref1 & 15];
+        }
+        for (int y = m->y; y < m->y + m->h && y < h->height; y += 4)
+            for (int x = m->x; x < m->x + m->w && x < h->width; x += 4) o.mvf[(y >> 2) * o.uw + (x >> 2)] = v;
+    }
+    for (int s = B200_SEC_TU4; s <= B200_SEC_TU32; s++) {                /* cbf_luma, hevc.c:1568-1576 */
+        const B200TuRec *tu = (const B200TuRec *)(blob + h->sec[s].off);
+        const int n = 4 << (s - B200_SEC_TU4);
+        for (uint32_t i = 0; i < h->sec[s].count; i++) {
+            if (tu[i].plane || tu[i].kind == B200_TU_PCM) continue;
+            for (int y = tu[i].y; y < tu[i].y + n && y < h->height; y += 4)
+                for (int x = tu[i].x; x < tu[i].x + n && x < h->width; x += 4) o.cbf[(y >> 2) * o.uw + (x >> 2)] = 1;
+        }
+    }
+    const uint32_t *leaf = (const uint32_t *)(o.sec + o.d->off_leaf);
+    for (uint32_t i = 0; i < o.d->n_leaf; i++) orc_bs_leaf(&o, leaf[i]);
+    const int ctb = 1 << h->log2_ctb_size;
+    for (int y0 = 0; y0 < h->height; y0 += ctb)
+        for (int x0 = 0; x0 < h->width; x0 += ctb) orc_deblocking_filter_ctb(&o, x0, y0);
+    free(o.mvf); free(o.cbf); free(o.vbs); free(o.hbs);
+    return 0;
+}
+
+/* ------------------------------------------------------------------------------------------
  * SAO.  Reference: hevcdsp_template.c:340-365 (band), :372-567 (edge + border / restore rules);
  * driver hevc_filter.c:197-322.  src = deblocked picture (never modified), dst = output.
  * ---------------------------------------------------------------------------------------- */
@@ -756,11 +989,20 @@ int orc_execute_blob(const uint8_t *blob, uint16_t **planes, int n_slots)
     }
     free(parked);
     /* K4 deblock */
-    if (h->sec[B200_SEC_DBK].count) {
+    if (h->sec[B200_SEC_DBK].count || h->dbd.count) {
         B200DbkLayout L;
         b200_dbk_layout(h->width, h->height, cfi, &L);
-        const uint16_t *grid = (const uint16_t *)(blob + h->sec[B200_SEC_DBK].off);
+        const uint16_t *grid = h->sec[B200_SEC_DBK].count ? (const uint16_t *)(blob + h->sec[B200_SEC_DBK].off) : NULL;
+        uint16_t *derived = NULL;
+        if (h->dbd.count) {                           /* parameters derived from the records (8f N2); with both present they must agree */
+            derived = (uint16_t *)calloc(L.total, sizeof(uint16_t));
+            if (!derived) return -3;
+            if (orc_dbd_derive(blob, derived)) { free(derived); return -9; }
+            if (grid && memcmp(grid, derived, (size_t)L.total * 2)) { free(derived); return -10; }
+            grid = derived;
+        }
         for (int p = 0; p < 3; p++) deblock_plane(cur[p], pw[p], ph[p], p, grid, &L, bd);
+        free(derived);
     }
     /* K5 SAO */
     const uint32_t *tqb_bits = NULL;

@@ -25,12 +25,19 @@ STREAMS = sorted(glob.glob(os.path.join(HERE, "golden", "streams", "*.hevc")))
 SMALL = [s for s in STREAMS if os.path.getsize(s) < 400_000]          # the 1080p / 4K streams run in the GPU suite
 
 
+@pytest.mark.parametrize("dbd", ["derive", "check"])
 @pytest.mark.parametrize("threads", ["1", "4", "4w"])
 @pytest.mark.parametrize("stream", SMALL, ids=[os.path.basename(s) for s in SMALL])
-def test_recorded_work_lists_through_the_oracle_equal_the_reference_decoder(stream, threads):
+def test_recorded_work_lists_through_the_oracle_equal_the_reference_decoder(stream, threads, dbd):
     """threads: "1"; "4" = four frame threads (pictures recorded concurrently, dumped in decode order by the shim's ticket);
     "4w" = four slice-thread workers (WPP rows, or tiles) recording one picture together (merged by b200_rec_merge) -- streams with
-    entry points only"""
+    entry points only.
+    dbd: "derive" (the default of the drop-in) = the work lists carry the INPUTS of the deblocking control
+    (transform-tree leaves, QP map, slice offsets; motion and cbf are in the MC / TU records) and the oracle derives boundary
+    strengths, tc and beta itself (orc_dbd_derive, restating hevc_filter.c:345-581, 583-700, 805-941); "check" (B200_DBD=2) = the
+    reference's own filter calls are recorded as well and the oracle requires the two grids to be identical (error -10)."""
+    if dbd == "check" and threads != "1":
+        pytest.skip("the comparison runs single-threaded")
     binary = os.path.join(REFDIR, "decode_b200")
     if not os.path.exists(binary):
         pytest.skip("oracle/_ref/decode_b200 not built (needs /root/reference)")

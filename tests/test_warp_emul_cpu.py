@@ -178,6 +178,40 @@ def test_hooked_decoder_on_the_emulated_kernels(stream):
     assert decode_emulated(stream, "1") == want
 
 
+# the streams that stress the deblocking control: QP deltas, beta / tc and chroma QP offsets, PCM with the loop filter off,
+# transquant bypass, slices / tiles without filtering across, asymmetric partitions, 4:2:2 / 4:4:4 chroma edge spacing, B pictures
+DBD_CHECKED = [s for s in EMULATED if os.path.basename(s).startswith(("amp_", "b_", "c422_", "c444_", "dbkoff_", "pcm_", "qpd_", "ra_416", "slices_", "tiles_", "tqb_"))]
+
+
+@needs_emul
+@pytest.mark.parametrize("stream", DBD_CHECKED, ids=os.path.basename)
+def test_device_derived_deblocking_parameters_equal_the_recorded_ones(stream):
+    """SURVEY.md 8f N2.  By default the device derives boundary strengths, tc and beta itself (k_dbd.cuh) and the two host
+    functions that do it in the reference return at once; with B200_DBD=2 the reference derives them as well, its filter calls
+    are recorded, and the device compares its grid with the recorded one entry by entry (k_dbd_compare -> an error from the
+    decoder).  Pictures must also still equal the unmodified decoder's."""
+    if not os.path.exists(os.path.join(REFDIR, "decode_b200")):
+        pytest.skip("oracle/_ref/decode_b200 not built (needs /root/reference)")
+    out = subprocess.run([os.path.join(REFDIR, "decode_b200"), stream, "1"], capture_output=True, text=True, timeout=900, env=dict(os.environ, LD_PRELOAD=EMUL, B200_DBD="2"))
+    assert out.returncode == 0 and "Error" not in out.stderr, out.stderr[-2000:]
+    assert [l for l in out.stdout.splitlines() if l.startswith("frame ")] == open(stream[:-5] + ".md5").read().splitlines()
+
+
+@needs_emul
+def test_the_check_mode_catches_a_wrong_derivation():
+    """the same with a library whose derivation is deliberately wrong in a few entries (tests/emul/Makefile, -DB200_DBD_FAULT):
+    the comparison must fail loudly, i.e. the check above has teeth"""
+    fault = os.path.join(REFDIR, "libb200hevc_emul_fault.so")
+    if not os.path.exists(fault) or not os.path.exists(os.path.join(REFDIR, "decode_b200")):
+        pytest.skip("fault-injection build missing")
+    stream = os.path.join(HERE, "golden", "streams", "p_416x240_8b.hevc")
+    out = subprocess.run([os.path.join(REFDIR, "decode_b200"), stream, "1"], capture_output=True, text=True, timeout=900, env=dict(os.environ, LD_PRELOAD=fault, B200_DBD="2"))
+    assert "Error" in out.stderr
+    out = subprocess.run([os.path.join(REFDIR, "decode_b200"), stream, "1"], capture_output=True, text=True, timeout=900, env=dict(os.environ, LD_PRELOAD=fault, B200_DBD="0"))
+    assert "Error" not in out.stderr                      # the fault only sits in the derivation
+    assert [l for l in out.stdout.splitlines() if l.startswith("frame ")] == open(stream[:-5] + ".md5").read().splitlines()
+
+
 @needs_emul
 @pytest.mark.parametrize("stream", [s for s in SMALL if os.path.basename(s).startswith(("b_", "ra_416", "wpp_416", "tiles_416x240_10b", "cip_416"))], ids=os.path.basename)
 @pytest.mark.parametrize("threads", ["4", "4w"])
