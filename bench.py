@@ -25,7 +25,8 @@ import numpy as np  # noqa: E402
 WORKLOADS = {
     "c3_4k_main10_ra": dict(width=3840, height=2160, cfi=1, bit_depth=10),
     "c2_1080p_main_ra": dict(width=1920, height=1080, cfi=1, bit_depth=8),
-    "c1_832x480_main": dict(width=832, height=480, cfi=1, bit_depth=8),
+    "c1_832x480_main": dict(width=832, height=480, cfi=1, bit_depth=8, all_intra=True),
+    "c3_4k_main10_intra": dict(width=3840, height=2160, cfi=1, bit_depth=10, all_intra=True),
     "c5_8k_422_main10": dict(width=7680, height=4320, cfi=2, bit_depth=10),
 }
 METRIC, UNIT = "decoded_frames_per_sec", "frames/s"
@@ -59,6 +60,8 @@ def make_blobs(wl, out_alloc=None):
     from openhevc_b200 import frame_parallel as FP
     blobs, stats = [], []
     for i, (name, n_ref) in enumerate(FP.blob_specs()):
+        if wl.get("all_intra"):                  # BASELINE.json config 1: I pictures only (the schedule still rotates the DPB slots)
+            n_ref = 0
         s = FrameSynth(wl["width"], wl["height"], wl["cfi"], wl["bit_depth"], seed=0xB2000003 + i, refs=list(range(n_ref)),
                        cur_slot=2, poc=i, p_intra=0.08 if n_ref else 1.0, weighted=False)
         blob, st = s.generate()
@@ -341,6 +344,7 @@ def main():
     eng.set_profiling(True)
     stage_ms = {k: 0.0 for k in ("mc", "residual", "intra", "deblock", "sao", "total")}
     reps = 3
+    stage_by_blob = {}
     for b in range(FP.N_BLOBS):
         pic = next(p for g in range(FP.INTRA_PERIOD_GOPS) for p in FP.gop_pictures(g) if p.blob == b)
         acc = {k: 0.0 for k in stage_ms}
@@ -348,6 +352,7 @@ def main():
             eng.execute(b, pic.cur_slot, pic.ref_slots)
             for k, v in eng.stage_ms().items():
                 acc[k] += v / reps
+        stage_by_blob[FP.blob_specs()[b][0] + f"#{b}"] = {k: round(v, 4) for k, v in acc.items()}
         for k in stage_ms:
             stage_ms[k] += acc[k] * mix[b] / npic_mix
     eng.set_profiling(False)
@@ -375,6 +380,7 @@ def main():
     roofline = {"bound": "hbm", "kernel": {"mc": "k_mc", "residual": "k_residual", "intra": "k_intra", "deblock": "k_deblock", "sao": "k_sao"}[dom],
                 "achieved": stages[dom]["gbps"], "peak": peak, "unit": "GB/s", "frac": stages[dom]["gbps"] / peak, "peak_source": peak_src,
                 "traffic": traffic, "traffic_note": traffic_note, "share_of_step": stage_ms[dom] / stage_ms["total"], "stages": stages,
+                "stage_ms_by_picture": stage_by_blob, "intra_levels": {FP.blob_specs()[b][0] + f"#{b}": (stats[b].get("intra_levels"), stats[b].get("intra_levels_in_ctb")) for b in range(FP.N_BLOBS)},
                 "whole_picture": {"algorithmic_bytes": sum(abytes.values()), "ms": stage_ms["total"],
                                   "gbps": sum(abytes.values()) / (stage_ms["total"] * 1e-3) / 1e9}}
 

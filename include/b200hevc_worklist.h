@@ -77,7 +77,11 @@ typedef struct B200BlobHeader {
                                     reference's own per-edge calls, recorded) or this section (its inputs: transform-tree leaves,
                                     QP map, per-CTB offsets; motion and cbf come from the MC / TU records), never both -- except in
                                     check mode (B200_DBD_CHECK), where the device compares what it derived with the recorded grids */
-    uint32_t reserved[64 - 21 - 2 * B200_SEC_COUNT];
+    B200Section ictb;            /* CTB-granular intra stage (else count = 0): uint32[ctb_count + 1], records [ictb[c], ictb[c + 1]) of B200_SEC_INTRA
+                                    belong to CTB c (raster index); the list is then ordered by CTB and, inside a CTB, by the dependency
+                                    level counted inside the CTB (B200IntraRec.pad[0], 1 ..): b200_intra_ctb_order().  Without this section
+                                    the list is in picture-wide dependency-level order (b200_intra_level_order) */
+    uint32_t reserved[64 - 23 - 2 * B200_SEC_COUNT];
 } B200BlobHeader;               /* 256 bytes */
 
 /* ---- on-device derivation of the deblocking parameters (hevc_filter.c:345-581 control half, :584-941) --------------------
@@ -184,7 +188,7 @@ typedef struct B200IntraRec {    /* 16 bytes */
     uint8_t  flags;              /* B200_INF_* */
     uint8_t  top_right_size;     /* samples really inside the picture, hevcpred_template.c:108-109 */
     uint8_t  bottom_left_size;   /* hevcpred_template.c:106-107 */
-    uint8_t  pad[2];
+    uint8_t  pad[2];             /* pad[0]: dependency level inside the CTB when the blob carries B200BlobHeader.ictb */
     uint32_t resid_off;          /* int16 index of the parked residual in COEFF, 0xFFFFFFFF = cbf 0 */
 } B200IntraRec;
 #define B200_NO_RESID 0xFFFFFFFFu

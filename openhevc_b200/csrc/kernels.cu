@@ -1254,6 +1254,8 @@ __global__ void __launch_bounds__(128) k_intra(const B200IntraRec *__restrict__ 
     }
 }
 
+#include "k_intra_ctb.cuh"
+
 // --------------------------------------------------------------------------------------------
 // K4: deblocking, both directions in ONE pass (k_deblock.cuh: one thread per 4-line edge segment).
 // --------------------------------------------------------------------------------------------
@@ -1431,6 +1433,40 @@ int launch_intra(cudaStream_t st, const B200IntraRec *recs, int count, const int
     if (bd > 8) B200_LAUNCH(grid, 128, 0, st, k_intra<uint16_t>)(recs, count, pool, cur, bd, ed, counter, cd);
     else        B200_LAUNCH(grid, 128, 0, st, k_intra<uint8_t>)(recs, count, pool, cur, bd, ed, counter, cd);
     return 3;
+}
+
+// K3, CTB-granular (k_intra_ctb.cuh): `ctb_start` = the blob's ictb section, `done` = one flag per CTB (compared with `gen`)
+int launch_intra_ctb(cudaStream_t st, const B200IntraRec *recs, int count, const uint32_t *ctb_start, int ctb_w, int ctb_h, int log2_ctb, int cfi, const int16_t *parked,
+                     unsigned long long parked_cap, const FrameDesc &cur, int bd, uint32_t *counter, uint32_t *done, uint32_t gen)
+{
+    if (!count) return 0;
+    IntraCtbArgs a;
+    a.recs = recs; a.ctb_start = ctb_start; a.parked = parked; a.counter = counter; a.done = done; a.gen = gen;
+    a.n_ctb = ctb_w * ctb_h; a.ctb_w = ctb_w; a.log2_ctb = log2_ctb; a.cfi = cfi; a.bd = bd; a.count = count; a.parked_cap = parked_cap;
+    const int ctb = 1 << log2_ctb;
+    int off = 0;
+    a.rec_off = off; off += ICTB_MAXREC * 16;
+    a.scratch_off = off; off += ICTB_WARPS * 400 * 4;
+    for (int p = 0; p < 3; p++) {
+        const int hs = p && cfi != 3, vs = p && cfi == 1, cw = ctb >> hs, ch = ctb >> vs;
+        const int ext = cw < 32 ? cw : 32;
+        a.tile_stride[p] = (1 + cw + ext + 1) & ~1;
+        a.tile_off[p] = off; off += ((a.tile_stride[p] * (ch + 1) * 2) + 15) & ~15;
+        a.rt_stride[p] = cw;
+        a.rt_off[p] = off; off += (cw * ch * 2 + 15) & ~15;
+    }
+    int grid = a.n_ctb < 148 * 2 ? a.n_ctb : 148 * 2;
+    static const int max_ctas = getenv("B200_INTRA_CTAS") ? atoi(getenv("B200_INTRA_CTAS")) : 0;
+    if (max_ctas > 0 && grid > max_ctas) grid = max_ctas;
+    static bool attr_set[2] = { false, false };
+    if (!attr_set[bd > 8]) {                             // more than 48 KB of dynamic shared memory needs the opt-in, once per kernel
+        if (bd > 8) cudaFuncSetAttribute(k_intra_ctb<uint16_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
+        else        cudaFuncSetAttribute(k_intra_ctb<uint8_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
+        attr_set[bd > 8] = true;
+    }
+    if (bd > 8) B200_LAUNCH(grid, ICTB_WARPS * 32, off, st, k_intra_ctb<uint16_t>)(a, cur);
+    else        B200_LAUNCH(grid, ICTB_WARPS * 32, off, st, k_intra_ctb<uint8_t>)(a, cur);
+    return 1;
 }
 
 int launch_deblock(cudaStream_t st, const uint16_t *grid, const B200DbkLayout &L, const FrameDesc &cur, int bd)
