@@ -916,10 +916,12 @@ __device__ __forceinline__ void fetch_edges(const uint2 *pa, const uint2 *pa_alt
     va = vb = make_uint2(0, 0);
     for (;;) {
         if (!ha) {
-            va = ld_edge(pa); ha = va.x & EDGE_VALID;
-            if (!ha && pa_alt) { const uint2 t = ld_edge(pa_alt); if (t.x & EDGE_VALID) { va = t; ha = true; } }
+            // (every 16-bit half carries EDGE_VALID: both words of the record must have arrived -- the two halves of a vector
+            // access are two accesses to the memory model)
+            va = ld_edge(pa); ha = va.x & va.y & EDGE_VALID;
+            if (!ha && pa_alt) { const uint2 t = ld_edge(pa_alt); if (t.x & t.y & EDGE_VALID) { va = t; ha = true; } }
         }
-        if (!hb) { vb = ld_edge(pb); hb = vb.x & EDGE_VALID; }
+        if (!hb) { vb = ld_edge(pb); hb = vb.x & vb.y & EDGE_VALID; }
         if (__all_sync(0xffffffffu, ha && hb)) break;
         __nanosleep(20);
         if ((++spins & 1023) == 0) {

@@ -103,23 +103,33 @@ extern "C" int b200_intra_ctb_order(const B200IntraRec *recs, uint32_t n, int wi
     const int ctb_w = (width + (1 << log2_ctb) - 1) >> log2_ctb, ctb_h = (height + (1 << log2_ctb) - 1) >> log2_ctb;
     const uint32_t nctb = (uint32_t)ctb_w * ctb_h;
     int fs[3], pw[3], ph[3];
+    // the unit maps stay allocated and CLEAN between calls: a picture with a few intra blocks must not pay for zeroing ~3 MB of maps,
+    // so whatever a call writes it resets before it returns (undo)
     for (int p = 0; p < 3; p++) {
         b200_plane_dims(width, height, cfi, p, &pw[p], &ph[p]);
         fs[p] = pw[p] / 4 + 2;
-        lvl[p].assign((size_t)fs[p] * (ph[p] / 4 + 2), 0);
+        const size_t need = (size_t)fs[p] * (ph[p] / 4 + 2);
+        if (lvl[p].size() != need) lvl[p].assign(need, 0);
     }
+    auto undo = [&](uint32_t upto) {
+        for (uint32_t i = 0; i < upto; i++) {
+            const B200IntraRec &r = recs[i];
+            const int s = fs[r.plane], u = 1 << (r.log2 - 2), ux = r.x >> 2, uy = r.y >> 2;
+            for (int y = 0; y < u; y++) for (int x = 0; x < u; x++) lvl[r.plane][(size_t)(uy + y) * s + ux + x] = 0;
+        }
+    };
     level.assign(n, 0); ctb_of.assign(n, 0);
     uint32_t maxl = 0;
     for (uint32_t i = 0; i < n; i++) {
         const B200IntraRec &r = recs[i];
-        if (r.plane > 2 || r.log2 < 2 || r.log2 > 5) return B200_EINVAL;
+        if (r.plane > 2 || r.log2 < 2 || r.log2 > 5) { undo(i); return B200_EINVAL; }
         const int p = r.plane, hs = p && cfi != 3, vs = p && cfi == 1;
         const int lu = log2_ctb - 2;                                   // log2 of the CTB in luma units
         std::vector<uint32_t> &L = lvl[p];
         const int s = fs[p], u = 1 << (r.log2 - 2), ux = r.x >> 2, uy = r.y >> 2;
-        if ((size_t)(uy + u) * s + ux + u >= L.size() + s) return B200_EINVAL;
+        if ((size_t)(uy + u) * s + ux + u >= L.size() + s) { undo(i); return B200_EINVAL; }
         const int cx = (ux << hs) >> lu, cy = (uy << vs) >> lu;
-        if (cx >= ctb_w || cy >= ctb_h) return B200_EINVAL;
+        if (cx >= ctb_w || cy >= ctb_h) { undo(i); return B200_EINVAL; }
         ctb_of[i] = (uint32_t)(cy * ctb_w + cx);
         auto at = [&](int x, int y) -> uint32_t {                      // level of a unit, 0 when it lies in another CTB
             if (x < 0 || y < 0) return 0;
@@ -143,6 +153,7 @@ extern "C" int b200_intra_ctb_order(const B200IntraRec *recs, uint32_t n, int wi
         if (level[i] > maxl) maxl = level[i];
         for (int y = 0; y < u; y++) for (int x = 0; x < u; x++) L[(size_t)(uy + y) * s + ux + x] = m + 1;
     }
+    undo(n);
     if (maxl > 255) return B200_ENOTSUP;
     // LSD radix: by level (stable), then by CTB (stable)
     tmp.resize(n);
@@ -242,7 +253,7 @@ extern "C" void b200_rec_destroy(B200Rec *r)
 extern "C" int b200_rec_begin(B200Rec *r, int cur_slot, int poc)
 {
     if (!r || cur_slot < 0 || cur_slot > 255) return B200_EINVAL;
-    memset(r->blob + r->off_dbk, 0, r->off_pool - r->off_dbk);
+    memset(r->blob + r->off_sao, 0, r->off_pool - r->off_sao);            // the deblock grids (1 MB at 4K) are cleared by the first call that needs them
     for (int s = 0; s < 4; s++) r->tu[s].clear();
     r->intra.clear(); r->mc.clear(); r->cip.clear(); r->tqb.clear(); r->ccp.clear(); r->leaf.clear(); r->dbd.clear();
     r->ncoef = 0; r->npark = 0; r->any_dbk = r->any_sao = false;
@@ -488,6 +499,7 @@ extern "C" int b200_rec_merge(B200Rec *d, B200Rec *s)
     }
     d->leaf.insert(d->leaf.end(), s->leaf.begin(), s->leaf.end());
     if (s->any_dbk) {
+        if (!d->any_dbk) memset(d->blob + d->off_dbk, 0, d->off_sao - d->off_dbk);
         uint16_t *dg = (uint16_t *)(d->blob + d->off_dbk);
         const uint16_t *sg = (const uint16_t *)(s->blob + s->off_dbk);
         for (uint32_t i = 0; i < d->dbk.total; i++) if (sg[i]) dg[i] = sg[i];
@@ -512,6 +524,7 @@ extern "C" int b200_rec_deblock(B200Rec *r, int plane, int vertical, int x, int 
     if (x < 0 || y < 0 || x >= r->pw[plane] || y >= r->ph[plane]) return B200_EINVAL;
     if (vertical ? ((x & 7) || (y & 3) || !x) : ((y & 7) || (x & 3) || !y)) return B200_EINVAL;
     if (beta < 0 || beta > 127 || tc[0] < 0 || tc[0] > 63 || tc[1] < 0 || tc[1] > 63) return B200_ENOTSUP;
+    if (!r->any_dbk) memset(r->blob + r->off_dbk, 0, r->off_sao - r->off_dbk);
     uint16_t *g = (uint16_t *)(r->blob + r->off_dbk) + r->dbk.off[plane][vertical ? 0 : 1];
     const int gs = (int)r->dbk.stride[plane][vertical ? 0 : 1];
     for (int j = 0; j < 2; j++) {
@@ -655,7 +668,12 @@ extern "C" int b200_rec_finish(B200Rec *r, const void **blob, uint64_t *nbytes)
     if (!r->intra.empty()) {
         static thread_local std::vector<uint32_t> perm;
         static thread_local std::vector<uint8_t> lev;
-        static const int intra_mode = getenv("B200_INTRA") ? atoi(getenv("B200_INTRA")) : 2;      // 1: picture-wide level order (TU wavefront), 2: CTB order
+        // 1 (default): picture-wide level order, TU-granular wavefront (k_intra); 2: CTB order, CTB-granular stage (k_intra_ctb.cuh).
+        // Measured on a B200 (round 2, 4K Main10): the CTB-granular stage is bit-exact (whole GPU suite) but SLOWER -- 11.6 ms for an
+        // intra picture against 4.07 ms, 1.2 ms against 0.09 ms for the intra blocks of a B picture: a CTB has up to ~80 dependency
+        // levels and a level costs ~1 us either way (the dependent instruction chain of one block, not the memory hop), so waiting
+        // for whole neighbour CTBs triples the number of serial steps (~10 k against the ~3.4 k of the block-level graph).
+        static const int intra_mode = getenv("B200_INTRA") ? atoi(getenv("B200_INTRA")) : 1;
         perm.resize(r->intra.size());
         B200IntraRec *dst = (B200IntraRec *)(r->blob + o);
         const uint32_t nctb = (uint32_t)(r->ctb_w * r->ctb_h);

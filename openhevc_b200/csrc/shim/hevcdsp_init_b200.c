@@ -103,7 +103,7 @@ typedef struct ShimThread {
     unsigned rec_gen;
     unsigned ticket;
     RegPlane reg[MAX_REG * 3];
-    int n_reg, reg_hit;
+    int n_reg, reg_hit, reg_hit2;
     const uint8_t *cur_base[3]; ptrdiff_t cur_ls[3], cur_size[3]; uint64_t cur_inv[3]; int cur_slot;
     uint8_t ref_slot[16]; int n_ref;
     /* pending in-place transform on the per-thread coefficient scratch (hevc.h:1063) */
@@ -248,16 +248,18 @@ static int locate_ref(const uint8_t *p, int plane_hint, int *slot, int *x, int *
             *slot = t->emu[e].slot; *y = t->emu[e].y + (int)(off / t->emu[e].ls); *x = t->emu[e].x + (int)(off % t->emu[e].ls) / G.B;
             return t->emu[e].plane;
         }
-    /* the plane of the previous hit first: consecutive blocks mostly read the same reference picture */
-    for (int k = -1; k < t->n_reg; k++) {
-        const int i = k < 0 ? t->reg_hit : k;
-        if (i >= t->n_reg) continue;
+    /* The two reference pictures hit last come first (planes are registered three per picture, Y Cb Cr): a block's calls go
+     * luma L0, luma L1, Cb L0, Cb L1, Cr L0, Cr L1, and neighbouring blocks mostly use the same one or two pictures. */
+    for (int k = -6; k < t->n_reg; k++) {
+        const int i = k < -3 ? t->reg_hit + (k + 6) : k < 0 ? t->reg_hit2 + (k + 3) : k;
+        if (i < 0 || i >= t->n_reg) continue;
         const RegPlane *r = &t->reg[i];
         ptrdiff_t off = p - r->base;
         if (off >= 0 && off < r->size && (plane_hint < 0 || r->plane == plane_hint)) {
             const uint32_t o = (uint32_t)off, ls = (uint32_t)r->linesize, row = row_of(o, ls, r->inv);
             *slot = r->slot; *y = (int)row; *x = (int)((o - row * ls) >> (G.B - 1));
-            t->reg_hit = i;
+            const int first = i - r->plane;                      /* index of the picture's luma plane */
+            if (first != t->reg_hit) { t->reg_hit2 = t->reg_hit; t->reg_hit = first; }
             return r->plane;
         }
     }

@@ -436,10 +436,10 @@ class FrameSynth:
             ro = a[:, 8]
             assert (ro != -2).all()
             intra["resid_off"] = np.where(ro < 0, W.NO_RESID, ro).astype(np.uint32)
-            # B200_INTRA=1: picture-wide dependency-level order (TU-granular stage); default: CTB order (CTB-granular stage).
-            # constrained_intra_pred pictures always take the former.
+            # B200_INTRA=2: CTB order (CTB-granular stage, k_intra_ctb.cuh -- measured slower, see recorder.cpp); default (1): picture-wide
+            # dependency-level order (TU-granular stage).  constrained_intra_pred pictures always take the latter.
             _, self.stats["intra_levels"] = W.level_order(intra, self.W, self.H, self.cfi)
-            co = None if (self.cip or os.environ.get("B200_INTRA", "2") == "1") else W.ctb_order(intra, self.W, self.H, self.cfi, self.log2_ctb)
+            co = None if (self.cip or os.environ.get("B200_INTRA", "1") != "2") else W.ctb_order(intra, self.W, self.H, self.cfi, self.log2_ctb)
             if co is not None:
                 perm, ictb, lev, self.stats["intra_levels_in_ctb"] = co
                 intra = intra[perm]

@@ -1,5 +1,7 @@
 """GPU parity (-m gpu): the CUDA path, called through the C ABI (libb200hevc.so), against the CPU oracle
 on the same seeded work lists.  Bit-exact or fail."""
+import os
+
 import numpy as np
 import pytest
 
@@ -364,3 +366,19 @@ def test_out_of_order_lanes_keep_slot_hazards(lanes):
                 assert np.array_equal(got[p], want[p]), f"picture {k} plane {p} differs ({lanes} lanes)"
     finally:
         eng.close()
+
+
+@pytest.mark.gpu
+def test_frame_parallel_over_two_gpus_equals_sequential_decode():
+    """tools/verify_multi_gpu.py under torchrun, 2 ranks: the product schedule (ownership by intra period, the one anchor per
+    period sent to the next GPU with NCCL send / recv inside the engine's slot-hazard protocol, 8 lanes) -- every picture of
+    every rank against the sequential decode by the CPU oracle.  Needs two visible GPUs (the driver's multi-GPU tier)."""
+    import subprocess
+    import sys
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("one GPU visible")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1", "--master-port", "29517",
+                        os.path.join(root, "tools", "verify_multi_gpu.py"), "--gops", "8"], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0 and '"verify_multi_gpu": "ok"' in r.stdout, (r.stdout[-2000:], r.stderr[-2000:])

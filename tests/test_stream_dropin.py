@@ -132,3 +132,36 @@ def test_table_calls_equal_what_the_generator_wrote(stream, threads):
     assert len(got) == len(gen)
     for (gi, gt, gm), (wi, wt, wp) in zip(got, gen):
         assert (gi, gt) == (wi, wt) and gm == 3 * wp
+
+
+# ---- BASELINE.json configs at their stated shape (>= 64 pictures, random access GOP 8): RECIPES, not committed bytes --
+# tools/make_bench_streams.sh regenerates the streams (fixed seeds) into oracle/_ref/streams/ and pins each with the per-picture
+# MD5s of the unmodified decoder (decode_ref, one thread); __graft_entry__.build() runs it when the files are missing.
+RECIPE_DIR = os.path.join(REFDIR, "streams")
+RECIPES = ["c1_832x480_i_16", "c2_1080p_ra8_65", "c3_4k_ra8_calm_65", "c3_4k_ra8_mid_65", "c3_4k_ra8_dense_33"]
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("threads", [1, 8])
+@pytest.mark.parametrize("name", RECIPES)
+def test_baseline_shape_streams_are_bit_exact(name, threads):
+    """832x480 all-intra (config 1), 1920x1080 8-bit and 3840x2160 Main10 random access, GOP 8, intra period 32, 65 pictures
+    (configs 2-4; lightly, moderately and densely coded): the hooked decoder, 1 thread and 8 frame threads, every picture against
+    the MD5s of the unmodified decoder"""
+    stream, md5 = os.path.join(RECIPE_DIR, name + ".hevc"), os.path.join(RECIPE_DIR, name + ".md5")
+    if not (os.path.exists(stream) and os.path.exists(md5) and os.path.exists(os.path.join(REFDIR, "decode_b200"))):
+        pytest.skip("recipe stream not generated (tools/make_bench_streams.sh)")
+    if threads == 8 and name == "c1_832x480_i_16":
+        pytest.skip("16 pictures: the reference's flush logic drops delayed pictures with that many threads")
+    assert run("decode_b200", stream, threads) == open(md5).read().splitlines()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", ["c1_832x480_i_16", "c2_1080p_ra8_65"])
+def test_ctb_granular_intra_stage_is_bit_exact(name):
+    """B200_INTRA=2: the CTB-granular intra stage (k_intra_ctb.cuh; not the default -- measured slower) on an all-intra
+    stream and on a random-access one"""
+    stream, md5 = os.path.join(RECIPE_DIR, name + ".hevc"), os.path.join(RECIPE_DIR, name + ".md5")
+    if not (os.path.exists(stream) and os.path.exists(md5) and os.path.exists(os.path.join(REFDIR, "decode_b200"))):
+        pytest.skip("recipe stream not generated (tools/make_bench_streams.sh)")
+    assert run("decode_b200", stream, 1, env={"B200_INTRA": "2"}) == open(md5).read().splitlines()

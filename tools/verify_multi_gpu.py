@@ -2,7 +2,7 @@
 """Multi-GPU parity check (run under torchrun, one rank per GPU):
     python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 tools/verify_multi_gpu.py
 Every rank runs the product schedule (openhevc_b200/frame_parallel.py: GOP ownership, NCCL anchor broadcast through the
-engine's slot-hazard protocol, 8 compute lanes) and reads every picture it decodes back; rank 0 then decodes the same
+engine's slot-hazard protocol -- ownership by intra period, one anchor per period sent to the next GPU --, 8 compute lanes) and reads every picture it decodes back; rank 0 then decodes the same
 stream sequentially with the CPU oracle (test infrastructure) and compares the MD5 of every picture of every rank.
 Also run by hand with --nproc-per-node 1 (lanes only)."""
 import argparse
@@ -20,7 +20,7 @@ sys.path.insert(0, os.path.join(ROOT, "tests"))
 
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument("--gops", type=int, default=4, help="GOPs per rank")
+    ap.add_argument("--gops", type=int, default=8, help="GOPs per rank (whole intra periods of 4)")
     ap.add_argument("--size", default="832x480")
     ap.add_argument("--bit-depth", type=int, default=10)
     args = ap.parse_args()
@@ -56,11 +56,9 @@ def main():
             super().__init__(*a)
             self.out, self.g, self.last_anchor = {}, -1, -1
 
-        def decode(self, pic):
-            if pic.anchor:
-                self.g = self.last_anchor = self.last_anchor + world if self.last_anchor >= 0 else rank
-            super().decode(pic)
-            self.out[(self.g, pic.blob)] = self.eng.readback(pic.cur_slot, self.eng.new_host_frame(pinned=True), sync=False)
+        def decode(self, pic, g=None):
+            super().decode(pic, g)
+            self.out[(g, pic.blob)] = self.eng.readback(pic.cur_slot, self.eng.new_host_frame(pinned=True), sync=False)
 
     be = Checked(eng, dpb, slot_bytes, world, list(range(FP.N_BLOBS)))
     FP.run_schedule(be, rank, world, args.gops)
@@ -81,7 +79,7 @@ def main():
         ref_dpb = [[np.zeros_like(p) for p in start] for _ in range(FP.N_SLOTS)]
         ref_dpb[FP.anchor_slot(-1)] = start
         want = {}
-        for g in range(args.gops * world):
+        for g in range(-(-args.gops // FP.INTRA_PERIOD_GOPS) * FP.INTRA_PERIOD_GOPS * world):
             for pic in FP.gop_pictures(g):
                 blob = blobs[pic.blob].copy()
                 hdr = blob[:256].view(W.header_dt)
