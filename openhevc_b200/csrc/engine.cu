@@ -313,6 +313,11 @@ static int ctx_init(B200Ctx *ctx)
     if (const char *e = getenv("B200_LANES")) if (atoi(e) > 0) ctx->n_lanes = atoi(e);
     if (ctx->n_lanes > MAX_LANES) ctx->n_lanes = MAX_LANES;
     ctx->trace_path = getenv("B200_TRACE");
+    if (ctx->trace_path && strstr(ctx->trace_path, "%d")) {           // one file per device when several ranks share the environment
+        static char per_dev[MAX_LANES][512];
+        snprintf(per_dev[c.device % MAX_LANES], 512, ctx->trace_path, c.device);
+        ctx->trace_path = per_dev[c.device % MAX_LANES];
+    }
     if (ctx->trace_path) ctx->trace.reserve(4096);      // TraceRec pointers stay valid while a picture is being submitted
     for (int p = 0; p < 3; p++) ctx->flag_stride[p] = (ctx->pw[p] + 3) / 4 + 1;
     {   // one error word per lane in mapped host memory: kernels store to it on their (rare) error paths, the host polls it

@@ -133,6 +133,17 @@ class GpuBackend:
         self.compute = torch.cuda.ExternalStream(engine.lib.b200_stream(engine.h))
         self.comm = torch.cuda.Stream() if world > 1 else None
         self.bcast_bytes = 0
+        if world > 1:
+            # Open the point-to-point connections of the ring once, SYMMETRICALLY (every rank sends right and receives from the
+            # left in one group): NCCL sets a pair's channels up at their first use and expects both ends in matching groups --
+            # the schedule's first exchange is not (rank 0 only sends), which NCCL 2.28 answers with "Message truncated".
+            import torch.distributed as dist
+            rank = dist.get_rank()
+            a, b = torch.zeros(16, device=dpb_tensor.device), torch.zeros(16, device=dpb_tensor.device)
+            with torch.cuda.stream(self.comm):
+                for w in dist.batch_isend_irecv([dist.P2POp(dist.isend, a, (rank + 1) % world), dist.P2POp(dist.irecv, b, (rank - 1) % world)]):
+                    w.wait()
+            self.comm.synchronize()
 
     def decode(self, pic, g=None):
         self.eng.execute(self.arena[pic.blob], pic.cur_slot, pic.ref_slots)
