@@ -254,7 +254,7 @@ class StreamGen:
         self.cu_bypass = 0
         self.tiles = tiles                  # (columns, rows), uniform spacing: one CABAC substream + entry point per tile, tile scan
         self.lf_across_tiles = lf_across_tiles
-        assert not (tiles and wpp), "WPP inside tiles is not generated"
+        # tiles and WPP together (BASELINE.json config 5; hevc.c:2834 hls_decode_entry_wpp_in_tiles): one substream per CTB row of every tile
         self.wpp = wpp                                                    # entropy_coding_sync: one CABAC substream per CTB row
         self.slice_type = 2                                               # 0 B, 1 P, 2 I
         self.nrefs = [0, 0]
@@ -508,33 +508,38 @@ class StreamGen:
             ncol, nrow = self.tiles
             cb = [(i * self.cw) // ncol for i in range(ncol + 1)]
             rb = [(j * self.ch) // nrow for j in range(nrow + 1)]
-            order = [(x, y, cb[i], rb[j]) for j in range(nrow) for i in range(ncol) for y in range(rb[j], rb[j + 1]) for x in range(cb[i], cb[i + 1])]
+            order = [(x, y, cb[i], rb[j], cb[i + 1]) for j in range(nrow) for i in range(ncol) for y in range(rb[j], rb[j + 1]) for x in range(cb[i], cb[i + 1])]
         else:
-            order = [(a % self.cw, a // self.cw, 0, 0) for a in range(n)]
+            order = [(a % self.cw, a // self.cw, 0, 0, self.cw) for a in range(n)]
         for a in range(ctb_start, ctb_end):
-            self.rx, self.ry, self.tile_x0, self.tile_y0 = order[a]
-            if self.tiles and a and (self.rx, self.ry) == (self.tile_x0, self.tile_y0):
+            self.rx, self.ry, self.tile_x0, self.tile_y0, tile_x1 = order[a]
+            tw = tile_x1 - self.tile_x0                                    # width of the tile (of the picture without tiles) in CTBs
+            tile_start = self.tiles and (self.rx, self.ry) == (self.tile_x0, self.tile_y0)
+            if tile_start and a:
                 # first CTB of a tile: new substream, the arithmetic coder and the contexts start afresh (9.3.1)
                 self.substreams.append(self.c.bits)
                 self.c = Cabac(self.init_rows[2 - self.slice_type], self.qp)
-            if self.wpp and self.rx == 0 and a:
-                # new substream: arithmetic coder restarts, contexts come from the state stored after the 2nd CTB of the
-                # row above (9.3.1: synchronization; a picture one CTB wide re-initialises instead)
+            elif self.wpp and self.rx == self.tile_x0 and a:
+                # new substream (a CTB row of the picture, or of the tile): arithmetic coder restarts, contexts come from the state
+                # stored after the 2nd CTB of the row above (9.3.1: synchronization; a row one CTB wide re-initialises instead,
+                # hevc_cabac.c:647-650)
                 self.substreams.append(self.c.bits)
                 fresh = Cabac(self.init_rows[2 - self.slice_type], self.qp)
-                if self.cw > 1:
+                if tw > 1:
                     fresh.state = [list(st) for st in saved]
                 self.c = fresh
             if self.sao:
                 self.sao_syntax()
             self.quadtree(self.rx << self.ctb_log2, self.ry << self.ctb_log2, self.ctb_log2, 0)
             self.c.terminate(1 if a == ctb_end - 1 else 0)                 # end_of_slice_segment_flag
+            row_end = False
             if self.wpp:
-                if self.rx == 1 or (self.cw == 1):
-                    saved = [list(st) for st in self.c.state]              # storage process after the 2nd CTB of a row
-                if self.rx == self.cw - 1 and a != ctb_end - 1:
+                if self.rx == self.tile_x0 + 1 or tw == 1:
+                    saved = [list(st) for st in self.c.state]              # storage process after the 2nd CTB of a row (hevc_cabac.c:552-560)
+                if self.rx == tile_x1 - 1 and a != ctb_end - 1:
                     self.c.terminate(1)                                    # end_of_subset_one_bit, then byte_alignment()
-            if self.tiles and a != ctb_end - 1 and order[a + 1][:2] == order[a + 1][2:]:
+                    row_end = True
+            if self.tiles and not row_end and a != ctb_end - 1 and order[a + 1][:2] == order[a + 1][2:4]:
                 self.c.terminate(1)                                        # last CTB of a tile: end_of_subset_one_bit
 
     def left_ok(self, x0):
