@@ -10,6 +10,8 @@
 #   c3_4k_ra8_dense_33.hevc  dense random content (~460 KB per picture, ~110 Mbit/s: the parse-bound worst case)
 #   c2_1080p_ra8_65.hevc     1920x1080 8-bit, GOP 8 (BASELINE.json config 2)
 #   c1_832x480_i_16.hevc     832x480 8-bit all-intra (config 1)
+#   c5_8k_422_wpp_tiles_9.hevc  7680x4320 4:2:2 Main10 (RExt), entropy_coding_sync + 4x2 tiles (one substream per CTB row of every
+#                            tile, hevc.c:2834), GOP 8, 9 pictures, lightly coded (config 5)
 set -e
 cd "$(dirname "$0")/.."
 D=oracle/_ref/streams
@@ -27,6 +29,7 @@ gen c3_4k_ra8_calm_65 --width 3840 --height 2160 --bit-depth 10 --frames 65 --pa
 gen c3_4k_ra8_mid_65 --width 3840 --height 2160 --bit-depth 10 --frames 65 --pattern RA8 --calm 0.5 --seed 10 &
 gen c2_1080p_ra8_65 --width 1920 --height 1080 --bit-depth 8 --frames 65 --pattern RA8 --calm 0.7 --seed 11 &
 gen c1_832x480_i_16 --width 832 --height 480 --bit-depth 8 --frames 16 --pattern I --seed 12 &
+gen c5_8k_422_wpp_tiles_9 --width 7680 --height 4320 --bit-depth 10 --cfi 2 --frames 9 --pattern RA8 --wpp --tiles 4x2 --calm 1.0 --seed 55 &
 if [ -z "$SKIP_DENSE" ]; then gen c3_4k_ra8_dense_33 --width 3840 --height 2160 --bit-depth 10 --frames 33 --pattern RA8 --seed 33 & fi
 wait
 ls -la $D
