@@ -25,7 +25,10 @@ struct B200Rec {
     uint32_t npark = 0;          // int16 used in the parked-residual pool
     std::vector<B200TuRec> tu[4];
     std::vector<B200IntraRec> intra;
-    std::vector<B200McRec> mc;
+    // MC tiles, already in the buckets of the wire format: [0] tiles of any shape (one warp each), [1 + B200_MC_SMALL_KEY] tiles of
+    // <= 8x8 samples by (chroma, bi).  Plain arrays: this is the hottest append of the recorder (~10 tiles per prediction block).
+    struct McBucket { B200McRec *p = nullptr; size_t n = 0, cap = 0; } mcb[5];
+    size_t mc_count() const { return mcb[0].n + mcb[1].n + mcb[2].n + mcb[3].n + mcb[4].n; }
     std::vector<uint32_t> cip;   // B200CipHeader + bitmap of a constrained_intra_pred picture (b200_rec_set_cip), else empty
     std::vector<B200CcpRec> ccp; // cross-component prediction records (b200_rec_ccp), executed between the residual and the intra stage
     std::vector<uint32_t> tqb;   // B200CipHeader + bitmap of the PUs restore_tqb_pixels gives their deblocked samples back (b200_rec_set_tqb)
@@ -247,6 +250,7 @@ extern "C" void b200_rec_destroy(B200Rec *r)
 {
     if (!r) return;
     if (r->pinned) b200_host_free(r->blob); else free(r->blob);
+    for (int k = 0; k < 5; k++) free(r->mcb[k].p);
     delete r;
 }
 
@@ -255,7 +259,7 @@ extern "C" int b200_rec_begin(B200Rec *r, int cur_slot, int poc)
     if (!r || cur_slot < 0 || cur_slot > 255) return B200_EINVAL;
     memset(r->blob + r->off_sao, 0, r->off_pool - r->off_sao);            // the deblock grids (1 MB at 4K) are cleared by the first call that needs them
     for (int s = 0; s < 4; s++) r->tu[s].clear();
-    r->intra.clear(); r->mc.clear(); r->cip.clear(); r->tqb.clear(); r->ccp.clear(); r->leaf.clear(); r->dbd.clear();
+    r->intra.clear(); for (int k = 0; k < 5; k++) r->mcb[k].n = 0; r->cip.clear(); r->tqb.clear(); r->ccp.clear(); r->leaf.clear(); r->dbd.clear();
     r->ncoef = 0; r->npark = 0; r->any_dbk = r->any_sao = false;
     r->last_intra[0] = r->last_intra[1] = r->last_intra[2] = -1;
     r->cur_slot = cur_slot; r->poc = poc; r->open = true; r->nbytes = 0; r->n_ref = 0; r->merged = false;
@@ -440,7 +444,14 @@ extern "C" int b200_rec_mc(B200Rec *r, const B200McRec *b)
             t.x = (uint16_t)(b->x + tx); t.y = (uint16_t)(b->y + ty); t.w = (uint8_t)tw; t.h = (uint8_t)th;
             t.sx0 = (int16_t)(b->sx0 + tx); t.sy0 = (int16_t)(b->sy0 + ty);
             t.sx1 = (int16_t)(b->sx1 + tx); t.sy1 = (int16_t)(b->sy1 + ty);
-            r->mc.push_back(t);
+            B200Rec::McBucket &bk = r->mcb[B200_MC_IS_SMALL(tw, th) ? 1 + B200_MC_SMALL_KEY(b->flags) : 0];
+            if (bk.n == bk.cap) {
+                const size_t cap = bk.cap ? 2 * bk.cap : 4096;
+                B200McRec *np = (B200McRec *)realloc(bk.p, cap * sizeof(B200McRec));
+                if (!np) return B200_ENOMEM;
+                bk.p = np; bk.cap = cap;
+            }
+            bk.p[bk.n++] = t;
         }
         tx += tw;
     }
@@ -491,11 +502,22 @@ extern "C" int b200_rec_merge(B200Rec *d, B200Rec *s)
         if (ir.resid_off != B200_NO_RESID) ir.resid_off += pbase;
         d->intra.push_back(ir);
     }
-    for (B200McRec m : s->mc) {
-        if (m.ref0 >= s->n_ref || ((m.flags & B200_MCF_BI) && m.ref1 >= s->n_ref)) return B200_EINVAL;
-        m.ref0 = map[m.ref0];
-        if (m.flags & B200_MCF_BI) m.ref1 = map[m.ref1];
-        d->mc.push_back(m);
+    for (int k = 0; k < 5; k++) {
+        B200Rec::McBucket &db = d->mcb[k];
+        const B200Rec::McBucket &sb = s->mcb[k];
+        if (db.n + sb.n > db.cap) {
+            const size_t cap = db.n + sb.n + 4096;
+            B200McRec *np = (B200McRec *)realloc(db.p, cap * sizeof(B200McRec));
+            if (!np) return B200_ENOMEM;
+            db.p = np; db.cap = cap;
+        }
+        for (size_t i = 0; i < sb.n; i++) {
+            B200McRec m = sb.p[i];
+            if (m.ref0 >= s->n_ref || ((m.flags & B200_MCF_BI) && m.ref1 >= s->n_ref)) return B200_EINVAL;
+            m.ref0 = map[m.ref0];
+            if (m.flags & B200_MCF_BI) m.ref1 = map[m.ref1];
+            db.p[db.n++] = m;
+        }
     }
     d->leaf.insert(d->leaf.end(), s->leaf.begin(), s->leaf.end());
     if (s->any_dbk) {
@@ -625,7 +647,7 @@ extern "C" int b200_rec_finish(B200Rec *r, const void **blob, uint64_t *nbytes)
     {   // room for the lists and the optional sections behind the pool, before any pointer into the blob is taken
         uint64_t need = b200_align_u32(r->off_pool + ((r->ncoef + 7) & ~7u) * 2, 256);
         for (int s = 0; s < 4; s++) need += ((uint64_t)r->tu[s].size() * 16 + 255) & ~(uint64_t)255;
-        need += (((uint64_t)r->intra.size() * 16 + 255) & ~(uint64_t)255) + (((uint64_t)r->mc.size() * 32 + 255) & ~(uint64_t)255);
+        need += (((uint64_t)r->intra.size() * 16 + 255) & ~(uint64_t)255) + (((uint64_t)r->mc_count() * 32 + 255) & ~(uint64_t)255);
         need += r->cip.size() * 4 + r->tqb.size() * 4 + r->dbd.size() * 4 + r->ccp.size() * sizeof(B200CcpRec) + 4 * ((size_t)r->ctb_w * r->ctb_h + 1) + 6 * 256;
         if (rec_grow(r, need)) return B200_ENOMEM;
     }
@@ -645,7 +667,7 @@ extern "C" int b200_rec_finish(B200Rec *r, const void **blob, uint64_t *nbytes)
     uint64_t o = b200_align_u32(r->off_pool + h->sec[B200_SEC_COEFF].count * 2, 256);
     uint64_t need = o;
     for (int s = 0; s < 4; s++) need += ((uint64_t)r->tu[s].size() * 16 + 255) & ~(uint64_t)255;
-    need += (((uint64_t)r->intra.size() * 16 + 255) & ~(uint64_t)255) + (((uint64_t)r->mc.size() * 32 + 255) & ~(uint64_t)255);
+    need += (((uint64_t)r->intra.size() * 16 + 255) & ~(uint64_t)255) + (((uint64_t)r->mc_count() * 32 + 255) & ~(uint64_t)255);
     if (need > r->cap) return B200_ENOMEM;
     for (int s = 0; s < 4; s++) {
         h->sec[B200_SEC_TU4 + s].off = (uint32_t)o; h->sec[B200_SEC_TU4 + s].count = (uint32_t)r->tu[s].size();
@@ -694,17 +716,13 @@ extern "C" int b200_rec_finish(B200Rec *r, const void **blob, uint64_t *nbytes)
         memcpy(r->blob + o, ictb.data(), ictb.size() * 4);
         o = (o + ictb.size() * 4 + 255) & ~(uint64_t)255;
     }
-    h->sec[B200_SEC_MC].off = (uint32_t)o; h->sec[B200_SEC_MC].count = (uint32_t)r->mc.size();
+    h->sec[B200_SEC_MC].off = (uint32_t)o; h->sec[B200_SEC_MC].count = (uint32_t)r->mc_count();
     {   // big tiles first (decode order), then the <= 8x8 tiles bucketed by (chroma, bi): see B200BlobHeader.mc_big_count
-        size_t n[5] = { 0, 0, 0, 0, 0 }, at[5];
-        for (const B200McRec &m : r->mc) n[B200_MC_IS_SMALL(m.w, m.h) ? 1 + B200_MC_SMALL_KEY(m.flags) : 0]++;
-        at[0] = 0;
-        for (int k = 1; k < 5; k++) at[k] = at[k - 1] + n[k - 1];
         B200McRec *dst = (B200McRec *)(r->blob + o);
-        for (const B200McRec &m : r->mc) dst[at[B200_MC_IS_SMALL(m.w, m.h) ? 1 + B200_MC_SMALL_KEY(m.flags) : 0]++] = m;
-        h->mc_big_count = (uint32_t)n[0];
+        for (int k = 0; k < 5; k++) { if (r->mcb[k].n) memcpy(dst, r->mcb[k].p, r->mcb[k].n * sizeof(B200McRec)); dst += r->mcb[k].n; }
+        h->mc_big_count = (uint32_t)r->mcb[0].n;
     }
-    o = (o + r->mc.size() * 32 + 255) & ~(uint64_t)255;
+    o = (o + r->mc_count() * 32 + 255) & ~(uint64_t)255;
     if (!r->cip.empty()) {                                   // constrained_intra_pred picture: B200CipHeader + intra bitmap
         if (o + r->cip.size() * 4 + 256 > r->cap) return B200_ENOMEM;
         h->cip.off = (uint32_t)o; h->cip.count = (uint32_t)r->cip.size();

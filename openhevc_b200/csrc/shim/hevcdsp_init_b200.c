@@ -825,6 +825,14 @@ static int rb_insert(const uint8_t *data0);
 
 int b200_frame_begin(HEVCContext *s)
 {
+    /* a failure of one picture (unsupported tool, out of memory, a work list the device rejected) must not disable the decoder for
+     * the rest of the process: a random-access point starts afresh.  CUDA errors are sticky and stay latched. */
+    if (g.err && g.err != B200_ECUDA && IS_IRAP(s) && g.in_frame != 1) {
+        pthread_mutex_lock(&G.mu);
+        if (G.err_code != B200_ECUDA) G.err_code = 0;
+        pthread_mutex_unlock(&G.mu);
+        g.err = 0;
+    }
     if (g.err) return g.err;
     if (g.in_frame == 1) finish_abandoned(s);                  /* previous picture of this thread was abandoned */
     if (g.err || global_error()) return g.err;
