@@ -58,16 +58,26 @@ extern "C" int b200_intra_level_order(const B200IntraRec *recs, uint32_t n, int 
         int pw, ph;
         b200_plane_dims(width, height, cfi, p, &pw, &ph);
         fs[p] = pw / 4 + 2;
-        lvl[p].assign((size_t)fs[p] * (ph / 4 + 2), 0);
+        // the unit maps stay allocated and CLEAN between calls (a picture with a few intra blocks must not pay for zeroing ~3 MB
+        // of maps): whatever a call writes it resets before it returns
+        const size_t need = (size_t)fs[p] * (ph / 4 + 2);
+        if (lvl[p].size() != need) lvl[p].assign(need, 0);
     }
+    auto undo = [&](uint32_t upto) {
+        for (uint32_t i = 0; i < upto; i++) {
+            const B200IntraRec &r = recs[i];
+            const int s = fs[r.plane], u = 1 << (r.log2 - 2), ux = r.x >> 2, uy = r.y >> 2;
+            for (int y = 0; y < u; y++) for (int x = 0; x < u; x++) lvl[r.plane][(size_t)(uy + y) * s + ux + x] = 0;
+        }
+    };
     level.assign(n, 0);
     uint32_t maxl = 0;
     for (uint32_t i = 0; i < n; i++) {
         const B200IntraRec &r = recs[i];
-        if (r.plane > 2 || r.log2 < 2 || r.log2 > 5) return B200_EINVAL;
+        if (r.plane > 2 || r.log2 < 2 || r.log2 > 5) { undo(i); return B200_EINVAL; }
         std::vector<uint32_t> &L = lvl[r.plane];
         const int s = fs[r.plane], u = 1 << (r.log2 - 2), ux = r.x >> 2, uy = r.y >> 2, nn = 1 << r.log2;
-        if ((size_t)(uy + u) * s + ux + u >= L.size() + s) return B200_EINVAL;
+        if ((size_t)(uy + u) * s + ux + u >= L.size() + s) { undo(i); return B200_EINVAL; }
         uint32_t m = 0;
         if ((r.flags & B200_INF_UP_LEFT) && ux && uy) m = L[(size_t)(uy - 1) * s + ux - 1];
         if (uy) {
@@ -85,6 +95,7 @@ extern "C" int b200_intra_level_order(const B200IntraRec *recs, uint32_t n, int 
         if (level[i] > maxl) maxl = level[i];
         for (int y = 0; y < u; y++) for (int x = 0; x < u; x++) L[(size_t)(uy + y) * s + ux + x] = m + 1;
     }
+    undo(n);
     start.assign(maxl + 2, 0);
     for (uint32_t i = 0; i < n; i++) start[level[i] + 1]++;
     for (uint32_t k = 0; k <= maxl; k++) start[k + 1] += start[k];
