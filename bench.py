@@ -370,7 +370,7 @@ def main():
     traffic, traffic_note = None, None
     try:
         tj = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))
-        kname = {"mc": "k_mc<unsigned short, 32>", "residual": "k_residual<unsigned short>", "intra": "k_intra<unsigned short>",
+        kname = {"mc": "k_mc_v1<unsigned short, 32>", "residual": "k_residual<unsigned short>", "intra": "k_intra<unsigned short>",
                  "deblock": "k_deblock<unsigned short>", "sao": "k_sao<unsigned short>"}[dom]
         if wl["bit_depth"] > 8 and wl["width"] == 3840 and kname in tj["kernels"]:
             traffic = tj["kernels"][kname]["dram_bytes_per_launch"]
