@@ -26,7 +26,7 @@
 #define MC_TMP_MAX 512      // 15 x 32, 23 x 16 plain; 8 row pairs x 32 x 2, 12 row pairs x 16 x 2 interleaved
 template <int GS> struct McSmem;
 template <> struct McSmem<32> { static constexpr int WIN = MC_WIN_MAX, TMP = MC_TMP_MAX; };
-template <> struct McSmem<8>  { static constexpr int WIN = 256 /* 15 x 16 */, TMP = 128 /* 15 x 8 */; };
+template <> struct McSmem<8>  { static constexpr int WIN = 256 /* 15 x 16 */, TMP = 160 /* 15 x 8, 15 x 10 padded */; };
 
 // ---- filter taps (ff_hevc_qpel_filters / ff_hevc_epel_filters, hevcdsp.c:1028-1042), four per register ----
 HD constexpr uint32_t mc_pack4(int a, int b, int c, int d)

@@ -406,6 +406,7 @@ __device__ __forceinline__ int ref_slot_of(const RefTable &rt, int i)
 struct DpbLayout {
     FrameDesc slot0;
     unsigned long long slot_bytes;
+    int tmp_pad;                // B200_MC_PAD (McGeom.ts)
 };
 __device__ __forceinline__ PlaneDesc ref_plane(const DpbLayout &L, const FrameDesc *__restrict__ dpb, int slot, int plane)
 {
@@ -419,6 +420,8 @@ struct McGeom {
     int w, h;
     int wsh, parts, rows_per;   // stage B: lane = column (1 << wsh per row group), `parts` row groups of rows_per rows
     int wpad, lsh, q;           // stage A: 4 outputs per lane, q quads per row, (1 << lsh) lanes per row
+    int ts;                     // row stride of the 16-bit intermediate in shared memory: wpad, or wpad + 2 (B200_MC_PAD=1: the row
+                                // groups of stage B then start on different banks; with a stride of 16 or 8 samples they collide)
 };
 
 // A tile is processed by a GROUP of GS lanes: GS = 32 (one warp per tile) for the big tiles, GS = 8 (four tiles per
@@ -527,7 +530,7 @@ __device__ __forceinline__ void mc_list_fir(const McWin1 &m, int mx, int my, con
                     for (int k = 0; k < TAPS; k++) acc += fx[k] * p[j + k];
                     o[j] = (acc >> sh) & 0xffff;
                 }
-                uint32_t *d = reinterpret_cast<uint32_t *>(tmp + r * g.wpad + 4 * qi);
+                uint32_t *d = reinterpret_cast<uint32_t *>(tmp + r * g.ts + 4 * qi);
                 d[0] = (uint32_t)o[0] | ((uint32_t)o[1] << 16);
                 d[1] = (uint32_t)o[2] | ((uint32_t)o[3] << 16);
             }
@@ -540,9 +543,9 @@ __device__ __forceinline__ void mc_list_fir(const McWin1 &m, int mx, int my, con
     const int xl = gl & ((1 << g.wsh) - 1), y0 = (gl >> g.wsh) * g.rows_per;
     int a[8 + TAPS - 1];
     if (mx) {
-        const int16_t *s = tmp + y0 * g.wpad + xl;
+        const int16_t *s = tmp + y0 * g.ts + xl;
 #pragma unroll
-        for (int k = 0; k < 8 + TAPS - 1; k++) a[k] = s[k * g.wpad];
+        for (int k = 0; k < 8 + TAPS - 1; k++) a[k] = s[k * g.ts];
     } else {
         const WT *s = win + y0 * Ws + skew + xl;
 #pragma unroll
@@ -588,7 +591,7 @@ __device__ __forceinline__ McRec1 mc_rec1(const int4 ra, const int4 rb)
     return t;
 }
 template <int GS>
-__device__ __forceinline__ McGeom mc_geom1(int w, int h)
+__device__ __forceinline__ McGeom mc_geom1(int w, int h, int pad = 0)
 {
     McGeom g;
     g.w = w; g.h = h;
@@ -598,6 +601,7 @@ __device__ __forceinline__ McGeom mc_geom1(int w, int h)
     g.wpad = (w + 3) & ~3;
     g.q = g.wpad >> 2;
     g.lsh = g.q <= 1 ? 0 : g.q <= 2 ? 1 : g.q <= 4 ? 2 : 3;
+    g.ts = g.wpad + (pad && g.wpad < 32 ? 2 : 0);
     return g;
 }
 // combine the lists' 14-bit intermediates (hevcdsp_template.c put_hevc_*_uni / _bi / _w) and store the tile
@@ -649,7 +653,7 @@ __global__ void __launch_bounds__(256) k_mc_v1(const B200McRec *__restrict__ rec
     const int4 *rp4 = reinterpret_cast<const int4 *>(recs + ri);
     const McRec1 t = mc_rec1<GS>(__ldg(rp4), __ldg(rp4 + 1));
     const bool chroma = t.flags & B200_MCF_CHROMA, bi = t.flags & B200_MCF_BI;
-    const McGeom g = mc_geom1<GS>(t.w, t.h);
+    const McGeom g = mc_geom1<GS>(t.w, t.h, lay.tmp_pad);
     int v0[8], v1[8];
     {
         const PlaneDesc rp = ref_plane(lay, dpb, ref_slot_of(rt, t.ref0), t.plane);
@@ -1484,8 +1488,9 @@ int launch_mc(cudaStream_t st, const B200McRec *recs, int count, int n_big, cons
     // B200_MC_DESC=1: reference planes described from kernel parameters (see DpbLayout); default 0 = descriptor table, the
     // path every GPU run of round 1 used -- the switch exists so that the next GPU visit can measure the difference at once
     static const bool by_param = getenv("B200_MC_DESC") && atoi(getenv("B200_MC_DESC"));
+    static const int tmp_pad = getenv("B200_MC_PAD") ? atoi(getenv("B200_MC_PAD")) : 0;
     DpbLayout lay;
-    lay.slot0 = slot0; lay.slot_bytes = by_param ? slot_bytes : 0ull;
+    lay.slot0 = slot0; lay.slot_bytes = by_param ? slot_bytes : 0ull; lay.tmp_pad = tmp_pad;
     // 1 = scalar FIRs, one IMAD per tap (default); 2 = IDP.2A on packed pairs (k_mc.cuh).  Version 2 is bit-exact on the GPU
     // (full parity suite) but SLOWER: 145 vs 109 us per 4K B picture, 38.9 M + 29.7 M vs 35.4 M + 22.8 M warp instructions --
     // the pair shuffles and the 16-bit interleaved stores cost more than the halved multiplies save, and ncu shows the
@@ -1495,7 +1500,7 @@ int launch_mc(cudaStream_t st, const B200McRec *recs, int count, int n_big, cons
     // 4 = persistent groups, windows double-buffered through 16-byte cp.async, descriptors from kernel parameters (k_mc_v4)
     static const int version = getenv("B200_MC") ? atoi(getenv("B200_MC")) : 1;
     DpbLayout lay4;
-    lay4.slot0 = slot0; lay4.slot_bytes = slot_bytes;
+    lay4.slot0 = slot0; lay4.slot_bytes = slot_bytes; lay4.tmp_pad = 0;
     int n = 0;
     const int n_small = count - n_big;
     if (n_big) {                        // one warp per tile
