@@ -126,7 +126,7 @@ def decoder_md5_ok(binary, stream, threads, env=None):
     return r.returncode == 0 and got == want
 
 
-def stream_block(name, arms, threads_all, device, budget_s=2.5, with_single=True):
+def stream_block(name, arms, threads_all, device, budget_s=2.5, with_single=True, oversubscribe=False):
     """fps of the arms ("reference", "b200") on one stream, 1 thread and `threads_all` frame threads.  Pass counts are chosen so
     that every timed (steady) region lasts about budget_s or more."""
     path = os.path.join(STREAM_DIR, name + ".hevc")
@@ -135,7 +135,12 @@ def stream_block(name, arms, threads_all, device, budget_s=2.5, with_single=True
     n = len(open(path[:-5] + ".md5").read().splitlines()) if os.path.exists(path[:-5] + ".md5") else 65
     env = {"B200_DEVICE": str(device), "B200_SHIM_REPORT": "1"}
     out = {"what": STREAMS.get(name, name), "bytes": os.path.getsize(path), "pictures": n, "host_threads": threads_all}
+    # oversubscribe: also 2 x the usable cores as frame threads, for BOTH arms -- frame threads block on each other's progress
+    # (ff_thread_await_progress), so more threads than cores fill the gaps; SURVEY.md 8d(i): "report the best multithreaded fps with
+    # the core count".  `best` names the fastest multithreaded run of each arm.
     tset = sorted({1, threads_all}) if with_single else [threads_all]
+    if oversubscribe:
+        tset = sorted(set(tset) | {2 * threads_all})
     for arm in arms:
         binary = "decode_ref" if arm == "reference" else "decode_b200"
         res = {}
@@ -150,9 +155,15 @@ def stream_block(name, arms, threads_all, device, budget_s=2.5, with_single=True
         if arm == "b200":
             res["md5_equal_reference_decoder"] = {f"threads_{t}": decoder_md5_ok(binary, path, t, env) for t in tset}
         out[arm] = res
+    for arm in arms:
+        multi = {t: out[arm][f"threads_{t}"]["steady_fps"] for t in tset if t > 1 and "steady_fps" in out[arm].get(f"threads_{t}", {})}
+        if multi:
+            bt = max(multi, key=multi.get)
+            out[arm]["best"] = {"threads": bt, "steady_fps": multi[bt]}
     try:
         for t in tset:
             out[f"speedup_threads_{t}"] = out["b200"][f"threads_{t}"]["steady_fps"] / out["reference"][f"threads_{t}"]["steady_fps"]
+        out["speedup_best_vs_best"] = out["b200"]["best"]["steady_fps"] / out["reference"]["best"]["steady_fps"]
     except Exception:
         pass
     return out
@@ -238,10 +249,11 @@ def run_reference(args, wl, rank):
     sb = None
     hs = HEADLINE_STREAM.get(args.workload)
     if hs and not args.no_stream:
-        sb = stream_block(hs, ["reference"], threads, 0, with_single=False)
+        sb = stream_block(hs, ["reference"], threads, 0, with_single=False, oversubscribe=True)
         try:
-            e2e = {"value": sb["reference"][f"threads_{threads}"]["steady_fps"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0,
-                   "what": f"unmodified reference decoder (oracle/_ref/decode_ref) on {hs}.hevc, {threads} frame threads, Annex-B bytes in, frames out"}
+            best = sb["reference"]["best"]
+            e2e = {"value": best["steady_fps"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0,
+                   "what": f"unmodified reference decoder (oracle/_ref/decode_ref) on {hs}.hevc, best of {threads} and {2 * threads} frame threads ({best['threads']}) on {threads} usable cores, Annex-B bytes in, frames out"}
         except Exception:
             pass
     line = {"metric": METRIC, "value": fps, "unit": UNIT, "impl": "reference", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
@@ -454,8 +466,9 @@ def main():
     if hs and not args.no_stream:
         eng.sync()
         threads_all = max(1, usable_cpus() // world)
-        mine = stream_block(hs, ["b200"] if world > 1 else ["reference", "b200"], threads_all, local, with_single=(world == 1))
-        sfps = torch.tensor([mine.get("b200", {}).get(f"threads_{threads_all}", {}).get("steady_fps", 0.0) or 0.0], device=f"cuda:{local}", dtype=torch.float64)
+        mine = stream_block(hs, ["b200"] if world > 1 else ["reference", "b200"], threads_all, local, with_single=(world == 1), oversubscribe=True)
+        best = mine.get("b200", {}).get("best", {})
+        sfps = torch.tensor([best.get("steady_fps", 0.0) or 0.0], device=f"cuda:{local}", dtype=torch.float64)
         if world > 1:
             dist.all_reduce(sfps, op=dist.ReduceOp.SUM)
         stream_e2e = {hs: mine}
@@ -464,11 +477,11 @@ def main():
                 if tag in args.streams.split(",") and args.workload == "c3_4k_main10_ra":
                     stream_e2e[nm] = stream_block(nm, ["reference", "b200"], threads_all, local, budget_s=1.5, with_single=False)
         if float(sfps.item()) > 0:
-            b = mine["b200"][f"threads_{threads_all}"]
+            b = mine["b200"][f"threads_{best['threads']}"]
             e2e_line = {"value": float(sfps.item()), "unit": UNIT,
                         "h2d_bytes_per_step": int(8 * b.get("h2d_bytes_per_picture", 0)), "d2h_bytes_per_step": int(8 * b.get("d2h_bytes_per_picture", 0)),
                         "mpixels_per_s": float(sfps.item()) * wl["width"] * wl["height"] / 1e6,
-                        "what": f"hooked reference decoder (oracle/_ref/decode_b200: CABAC parse on {threads_all} host frame threads per GPU, pixel path on the GPU) on {hs}.hevc: "
+                        "what": f"hooked reference decoder (oracle/_ref/decode_b200: CABAC parse on {best['threads']} host frame threads per GPU -- best of {threads_all} and {2 * threads_all} on {threads_all} usable cores --, pixel path on the GPU) on {hs}.hevc: "
                                 "Annex-B bytes in, every picture read back to pinned host frames; steady state of one decoder instance (first pass excluded)",
                         "md5_equal_reference_decoder": mine["b200"].get("md5_equal_reference_decoder")}
 

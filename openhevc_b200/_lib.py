@@ -4,7 +4,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libb200hevc.so")
+LIB_PATH = os.environ.get("B200_LIB_PATH") or os.path.join(_HERE, "libb200hevc.so")     # (B200_LIB_PATH: tuning builds of the same library, tools/)
 
 
 class B200Config(C.Structure):

@@ -4,7 +4,9 @@
 #pragma once
 #include "common.cuh"
 
-#define SAO_R 4
+#ifndef SAO_R
+#define SAO_R 4          // rows per thread (tuning builds: -DSAO_R=2)
+#endif
 
 // 8 consecutive samples (x multiple of 8: 16-byte / 8-byte aligned; rows are padded to the pitch, so a vector that
 // starts inside the plane may be read whole), as four registers of two 16-bit samples

@@ -1440,8 +1440,11 @@ __global__ void __launch_bounds__(DBK_THREADS, 3) k_deblock(const uint16_t *__re
 // --------------------------------------------------------------------------------------------
 #include "k_sao.cuh"
 
+#ifndef SAO_MINB
+#define SAO_MINB 2
+#endif
 template <typename PIX>
-__global__ void __launch_bounds__(256, 2) k_sao(const B200SaoRec *__restrict__ grid, FrameDesc src, FrameDesc dst, int bd,
+__global__ void __launch_bounds__(256, SAO_MINB) k_sao(const B200SaoRec *__restrict__ grid, FrameDesc src, FrameDesc dst, int bd,
                                                 int log2_ctb, int ctb_w, int ctb_h, int cfi, int4 tile_base, int3 tiles_x, TqbDesc tq)
 {
     sao_thread<PIX>(grid, src, dst, bd, log2_ctb, ctb_w, ctb_h, cfi, tile_base, tiles_x, tq, blockIdx.x * 8 + (threadIdx.x >> 5), threadIdx.x & 31);
