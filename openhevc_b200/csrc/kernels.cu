@@ -1441,7 +1441,7 @@ __global__ void __launch_bounds__(DBK_THREADS, 3) k_deblock(const uint16_t *__re
 #include "k_sao.cuh"
 
 #ifndef SAO_MINB
-#define SAO_MINB 2
+#define SAO_MINB 3
 #endif
 template <typename PIX>
 __global__ void __launch_bounds__(256, SAO_MINB) k_sao(const B200SaoRec *__restrict__ grid, FrameDesc src, FrameDesc dst, int bd,
