@@ -81,7 +81,11 @@ typedef struct B200BlobHeader {
                                     belong to CTB c (raster index); the list is then ordered by CTB and, inside a CTB, by the dependency
                                     level counted inside the CTB (B200IntraRec.pad[0], 1 ..): b200_intra_ctb_order().  Without this section
                                     the list is in picture-wide dependency-level order (b200_intra_level_order) */
-    uint32_t reserved[64 - 23 - 2 * B200_SEC_COUNT];
+    uint32_t mc_tile_count[5];   /* all zero: the records of B200_SEC_MC are TILES (<= 256 samples, ordered as mc_big_count says).  Else they are
+                                    whole PREDICTION BLOCKS (w, h <= 64) in decode order and the DEVICE splits them (k_mc_expand): [0] tiles of
+                                    any shape, [1 + B200_MC_SMALL_KEY] tiles of <= 8x8 samples; B200McRec.pad = index of the block's first
+                                    tile inside its bucket (24 bits, little endian); all tiles of one record fall into one bucket */
+    uint32_t reserved[64 - 28 - 2 * B200_SEC_COUNT];
 } B200BlobHeader;               /* 256 bytes */
 
 /* ---- on-device derivation of the deblocking parameters (hevc_filter.c:345-581 control half, :584-941) --------------------
@@ -116,6 +120,11 @@ typedef struct B200CipHeader {   /* first 4 words of the CIP section */
 #define B200_CIP_WORDS(pw, ph) (4u + (((uint32_t)(pw) * (uint32_t)(ph) + 31u) >> 5))
 
 #define B200_MC_IS_SMALL(w, h) ((w) <= 8 && (h) <= 8)
+/* How a prediction block of w x h samples is cut into tiles (recorder.cpp b200_rec_mc on the host, k_mc_expand on the device -- the
+ * one definition): columns of <= 16 samples when the block is taller than 8 rows (the squarer tile has the smaller filter halo),
+ * else <= 32; rows of <= 16 (tile width <= 16) or <= 8. */
+#define B200_MC_TILE_WMAX(h) ((h) > 8 ? 16 : 32)
+#define B200_MC_TILE_HMAX(tw) ((tw) > 16 ? 8 : 16)
 #define B200_MC_SMALL_KEY(flags) ((((flags) & B200_MCF_CHROMA) ? 2 : 0) | (((flags) & B200_MCF_BI) ? 1 : 0))   /* 0..3 */
 
 #define B200_FRAME_HAS_DEBLOCK 1u

@@ -54,6 +54,7 @@ struct Lane {
     uint2 *flags[3] = { nullptr, nullptr, nullptr };   // intra edge records, 16 B per 4x4 unit
     uint32_t *counter = nullptr;        // [0] K3 ticket, [1] validation gate of the picture in progress, [2] K3 time-out latch, [3] validation latch
     int16_t *parked = nullptr;          // residuals of intra TUs (K2 -> K3), indexed like the coefficient pool
+    B200McRec *mc_tiles = nullptr;      // tile list k_mc_expand writes when the blob carries whole prediction blocks (B200BlobHeader.mc_tile_count)
     uint32_t *ictb_done = nullptr;      // CTB-granular intra stage: one flag per CTB, == ictb_gen once the CTB of the picture in progress is done
     uint32_t ictb_gen = 0;
     DbdMaps dbd = {};                   // scratch of the on-device deblocking derivation, allocated with the first picture that needs it
@@ -83,6 +84,7 @@ struct B200Ctx {
     SlotState slot[MAX_SLOTS];
     Arena arena[MAX_ARENAS];
     uint64_t arena_bytes = 0;
+    uint64_t mc_tile_cap = 0;        // tiles a picture can expand to: the smallest blocks are 8x4 luma (32 samples) with their chroma
     int next_arena = 0;
     cudaStream_t st_copy = nullptr, st_compute = nullptr /* == lane[0].st */, st_down = nullptr;
     cudaEvent_t prof[B200_ST_COUNT + 1];
@@ -272,6 +274,7 @@ extern "C" void b200_ctx_destroy(B200Ctx *ctx)
         if (L.parked) cudaFree(L.parked);
         if (L.dbd.mot) cudaFree(L.dbd.mot);
         if (L.ictb_done) cudaFree(L.ictb_done);
+        if (L.mc_tiles) cudaFree(L.mc_tiles);
         if (L.tail) cudaEventDestroy(L.tail);
         if (L.st) cudaStreamDestroy(L.st);
     }
@@ -309,6 +312,7 @@ static int ctx_init(B200Ctx *ctx)
     CU(cudaMemcpy(ctx->dpb_desc_dev, ctx->slot_desc, sizeof(FrameDesc) * c.n_slots, cudaMemcpyHostToDevice));
     ctx->arena_bytes = c.max_blob_bytes ? c.max_blob_bytes : b200_worst_blob_bytes(&c);
     ctx->arena_bytes = (ctx->arena_bytes + 4095) & ~(uint64_t)4095;
+    ctx->mc_tile_cap = 3ull * ((uint64_t)ctx->pw[0] * ctx->ph[0] / 32) + 4096;
     ctx->n_lanes = c.n_lanes > 0 ? c.n_lanes : 8;
     if (const char *e = getenv("B200_LANES")) if (atoi(e) > 0) ctx->n_lanes = atoi(e);
     if (ctx->n_lanes > MAX_LANES) ctx->n_lanes = MAX_LANES;
@@ -445,6 +449,12 @@ static int check_blob(B200Ctx *ctx, const B200BlobHeader *h, uint64_t nbytes)
             dh->cb_qp_offset < -12 || dh->cb_qp_offset > 12 || dh->cr_qp_offset < -12 || dh->cr_qp_offset > 12)
             return fail(ctx, B200_EINVAL, "DBD section does not match the picture geometry");
     }
+    {   // prediction blocks split on the device: the tile list they expand to must fit the lane's buffer
+        uint64_t tiles = 0;
+        for (int k = 0; k < 5; k++) tiles += h->mc_tile_count[k];
+        if (tiles && (tiles > ctx->mc_tile_cap || tiles < h->sec[B200_SEC_MC].count || h->mc_big_count))
+            return fail(ctx, B200_EINVAL, "MC tile counts %llu do not fit (blocks %u, capacity %llu)", (unsigned long long)tiles, h->sec[B200_SEC_MC].count, (unsigned long long)ctx->mc_tile_cap);
+    }
     if (h->mc_big_count > h->sec[B200_SEC_MC].count) return fail(ctx, B200_EINVAL, "mc_big_count %u > %u MC records", h->mc_big_count, h->sec[B200_SEC_MC].count);
     if (h->sec[B200_SEC_DBK].count && h->sec[B200_SEC_DBK].count != ctx->dbk.total) return fail(ctx, B200_EINVAL, "deblock grid size %u != %u", h->sec[B200_SEC_DBK].count, ctx->dbk.total);
     if (h->sec[B200_SEC_SAO].count && h->sec[B200_SEC_SAO].count != (uint32_t)(3 * ctx->ctb_w * ctx->ctb_h)) return fail(ctx, B200_EINVAL, "SAO grid size mismatch");
@@ -487,9 +497,17 @@ static int deep_check(B200Ctx *ctx, const uint8_t *blob)
             return fail(ctx, B200_EINVAL, "intra record %u invalid", i);
     }
     const B200McRec *mc = (const B200McRec *)(blob + h->sec[B200_SEC_MC].off);
+    const bool blocks = (h->mc_tile_count[0] | h->mc_tile_count[1] | h->mc_tile_count[2] | h->mc_tile_count[3] | h->mc_tile_count[4]) != 0;
     for (uint32_t i = 0; i < h->sec[B200_SEC_MC].count; i++) {
         const B200McRec &m = mc[i];
         const int maxf = (m.flags & B200_MCF_CHROMA) ? 7 : 3;
+        if (blocks) {                                // whole prediction blocks (the device cuts them and validates the tiles again)
+            if (m.plane > 2 || !m.w || !m.h || m.w > 64 || m.h > 64 || m.x + m.w > ctx->pw[m.plane] || m.y + m.h > ctx->ph[m.plane] ||
+                m.ref0 >= h->n_ref || ((m.flags & B200_MCF_BI) && m.ref1 >= h->n_ref) ||
+                (m.frac0 & 15) > maxf || (m.frac0 >> 4) > maxf || (m.frac1 & 15) > maxf || (m.frac1 >> 4) > maxf || m.denom > 7)
+                return fail(ctx, B200_EINVAL, "MC block record %u invalid", i);
+            continue;
+        }
         if (m.plane > 2 || !m.w || !m.h || m.w > 32 || m.w * m.h > 256 || m.x + m.w > ctx->pw[m.plane] || m.y + m.h > ctx->ph[m.plane] ||
             m.ref0 >= h->n_ref || ((m.flags & B200_MCF_BI) && m.ref1 >= h->n_ref) ||
             (m.frac0 & 15) > maxf || (m.frac0 >> 4) > maxf || (m.frac1 & 15) > maxf || (m.frac1 >> 4) > maxf || m.denom > 7 ||
@@ -645,7 +663,19 @@ extern "C" int b200_frame_execute_ex(B200Ctx *ctx, int arena, int cur_slot, cons
     { int rc = slot_acquire(ctx, h.cur_slot, st, li, true); if (rc) return rc; }
     CU(cudaStreamWaitEvent(st, a.ev_uploaded, 0));
     CU(cudaMemsetAsync(L.counter, 0, 2 * sizeof(uint32_t), st));          // K3 ticket + this picture's validation gate
-    if (validate_mode() == 1) ctx->launches += launch_validate(st, a.dev, h, ctx->pw, ctx->ph, ctx->arena_bytes, L.counter);
+    // whole prediction blocks in the list: cut them into tiles first (k_mc_expand); everything behind works on the tile list
+    const B200McRec *mc_list = (const B200McRec *)(a.dev + h.sec[B200_SEC_MC].off);
+    uint32_t mc_count = h.sec[B200_SEC_MC].count, mc_big = h.mc_big_count;
+    {
+        uint64_t tiles = 0;
+        for (int k = 0; k < 5; k++) tiles += h.mc_tile_count[k];
+        if (tiles) {
+            if (!L.mc_tiles) CU(cudaMalloc(&L.mc_tiles, ctx->mc_tile_cap * sizeof(B200McRec)));
+            ctx->launches += launch_mc_expand(st, mc_list, mc_count, L.mc_tiles, h.mc_tile_count, L.counter);
+            mc_list = L.mc_tiles; mc_count = (uint32_t)tiles; mc_big = h.mc_tile_count[0];
+        }
+    }
+    if (validate_mode() == 1) ctx->launches += launch_validate(st, a.dev, h, ctx->pw, ctx->ph, ctx->arena_bytes, L.counter, mc_list == L.mc_tiles ? mc_list : nullptr, mc_count, mc_big);
     B200Ctx::TraceRec *tr = nullptr;
     if (ctx->trace_path && ctx->trace.size() < 4096) {
         ctx->trace.emplace_back();
@@ -657,7 +687,7 @@ extern "C" int b200_frame_execute_ex(B200Ctx *ctx, int arena, int cur_slot, cons
     }
     if (pf) CU(cudaEventRecord(ctx->prof[0], st));
     // K1 inter
-    ctx->launches += launch_mc(st, (const B200McRec *)(a.dev + h.sec[B200_SEC_MC].off), (int)h.sec[B200_SEC_MC].count, (int)h.mc_big_count, cur, ctx->dpb_desc_dev, rt, bd, L.counter,
+    ctx->launches += launch_mc(st, mc_list, (int)mc_count, (int)mc_big, cur, ctx->dpb_desc_dev, rt, bd, L.counter,
                                ctx->slot_desc[0], (unsigned long long)ctx->slot_bytes);
     if (pf) CU(cudaEventRecord(ctx->prof[1], st));
     if (tr) CU(cudaEventRecord(tr->ev[1], st));

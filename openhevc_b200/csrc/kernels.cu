@@ -67,6 +67,7 @@ struct ValidateArgs {
     int pw[3], ph[3];
     uint32_t ncoef, mc_big, n_ref;
     unsigned long long arena_bytes;
+    const uint8_t *mc; uint32_t mc_count;      // the MC tile records: the blob's section, or the list k_mc_expand wrote
 };
 
 __global__ void __launch_bounds__(256) k_validate(ValidateArgs a, uint32_t *gate)
@@ -103,8 +104,8 @@ __global__ void __launch_bounds__(256) k_validate(ValidateArgs a, uint32_t *gate
             ((r.flags & (B200_INF_LEFT | B200_INF_BOTTOM_LEFT | B200_INF_UP_LEFT)) && r.x == 0))
             bad |= 1u << B200_SEC_INTRA;
     }
-    if (i < a.sec[B200_SEC_MC].count) {
-        const int4 *p = reinterpret_cast<const int4 *>(a.blob + a.sec[B200_SEC_MC].off) + 2 * (size_t)i;
+    if (i < a.mc_count) {
+        const int4 *p = reinterpret_cast<const int4 *>(a.mc) + 2 * (size_t)i;
         const int4 ra = __ldg(p), rb = __ldg(p + 1);
         B200McRec m;
         memcpy(&m, &ra, 16);
@@ -121,14 +122,17 @@ __global__ void __launch_bounds__(256) k_validate(ValidateArgs a, uint32_t *gate
     if (bad) { gate[1] = 1u; atomicOr(gate + 3, bad); latch_host(gate, bad); }
 }
 
-int launch_validate(cudaStream_t st, const uint8_t *blob_dev, const B200BlobHeader &h, const int pw[3], const int ph[3], unsigned long long arena_bytes, uint32_t *gate)
+int launch_validate(cudaStream_t st, const uint8_t *blob_dev, const B200BlobHeader &h, const int pw[3], const int ph[3], unsigned long long arena_bytes, uint32_t *gate,
+                    const B200McRec *mc_tiles, uint32_t mc_count, uint32_t mc_big)
 {
     ValidateArgs a;
     a.blob = blob_dev;
-    uint32_t most = 0;
-    for (int s = 0; s < B200_SEC_COUNT; s++) { a.sec[s] = h.sec[s]; if (s >= B200_SEC_TU4 && s <= B200_SEC_MC && h.sec[s].count > most) most = h.sec[s].count; }
+    a.mc = mc_tiles ? reinterpret_cast<const uint8_t *>(mc_tiles) : blob_dev + h.sec[B200_SEC_MC].off;
+    a.mc_count = mc_tiles ? mc_count : h.sec[B200_SEC_MC].count;
+    uint32_t most = a.mc_count;
+    for (int s = 0; s < B200_SEC_COUNT; s++) { a.sec[s] = h.sec[s]; if (s >= B200_SEC_TU4 && s <= B200_SEC_INTRA && h.sec[s].count > most) most = h.sec[s].count; }
     for (int p = 0; p < 3; p++) { a.pw[p] = pw[p]; a.ph[p] = ph[p]; }
-    a.ncoef = h.sec[B200_SEC_COEFF].count; a.mc_big = h.mc_big_count; a.n_ref = h.n_ref; a.arena_bytes = arena_bytes;
+    a.ncoef = h.sec[B200_SEC_COEFF].count; a.mc_big = mc_tiles ? mc_big : h.mc_big_count; a.n_ref = h.n_ref; a.arena_bytes = arena_bytes;
     if (!most) return 0;
     B200_LAUNCH((most + 255) / 256, 256, 0, st, k_validate)(a, gate);
     return 1;
@@ -392,6 +396,66 @@ __global__ void __launch_bounds__(128) k_ccp(const B200CcpRec *__restrict__ recs
 // separable FIR with the 14-bit intermediate of the reference.
 // --------------------------------------------------------------------------------------------
 #include "k_mc.cuh"
+
+// K1a: prediction blocks -> tiles.  The host records ONE record per table call (a block of up to 64x64 samples, hevc.c:1641-1949)
+// instead of cutting it into up to 24 tiles itself (6-9 % of the hooked decoder's host time, and 60 % of the upload of a lightly
+// coded picture): one thread per block writes the block's tiles -- the cut of B200_MC_TILE_WMAX / _HMAX, the one definition the
+// recorder's fallback uses too -- into the lane's tile list at the place the host reserved (bucket base + B200McRec.pad), laid
+// out like a B200_SEC_MC section in tile mode.  Only memory safety is checked here (index inside the bucket); the tiles are
+// validated like any other list by k_validate, which runs behind this kernel.
+struct McExpandArgs {
+    const B200McRec *blocks; uint32_t n_blocks;
+    B200McRec *tiles;
+    uint32_t base[5], count[5];
+};
+__global__ void __launch_bounds__(256) k_mc_expand(McExpandArgs a, uint32_t *gate)
+{
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= a.n_blocks) return;
+    const int4 *p = reinterpret_cast<const int4 *>(a.blocks) + 2 * (size_t)i;
+    const int4 ra = __ldg(p), rb = __ldg(p + 1);
+    const int x = ra.x & 0xffff, y = (unsigned)ra.x >> 16, w = ra.y & 0xff, h = (ra.y >> 8) & 0xff, flags = (unsigned)ra.y >> 24;
+    const int sx0 = (int16_t)(ra.z & 0xffff), sy0 = (int16_t)((unsigned)ra.z >> 16), sx1 = (int16_t)(ra.w & 0xffff), sy1 = (int16_t)((unsigned)ra.w >> 16);
+    const uint32_t off = ((unsigned)rb.w >> 8) & 0xffffff;            // pad[0..2]
+    bool bad = !w || !h || w > 64 || h > 64;
+    int bucket = -1;
+    uint32_t k = 0;
+    if (!bad) {
+        const int twmax = B200_MC_TILE_WMAX(h);
+        for (int tx = 0; tx < w && !bad;) {
+            const int tw = w - tx > twmax ? twmax : w - tx, maxh = B200_MC_TILE_HMAX(tw);
+            for (int ty = 0; ty < h; ty += maxh) {
+                const int th = h - ty > maxh ? maxh : h - ty;
+                const int b = B200_MC_IS_SMALL(tw, th) ? 1 + B200_MC_SMALL_KEY(flags) : 0;
+                if (bucket < 0) bucket = b;
+                const uint32_t cnt = bucket == 0 ? a.count[0] : bucket == 1 ? a.count[1] : bucket == 2 ? a.count[2] : bucket == 3 ? a.count[3] : a.count[4];
+                const uint32_t bs = bucket == 0 ? a.base[0] : bucket == 1 ? a.base[1] : bucket == 2 ? a.base[2] : bucket == 3 ? a.base[3] : a.base[4];
+                if (b != bucket || off + k >= cnt) { bad = true; break; }
+                int4 ta = ra, tb = rb;
+                ta.x = ((x + tx) & 0xffff) | ((y + ty) << 16);
+                ta.y = (ra.y & 0xffff0000) | tw | (th << 8);
+                ta.z = ((sx0 + tx) & 0xffff) | ((sy0 + ty) << 16);
+                ta.w = ((sx1 + tx) & 0xffff) | ((sy1 + ty) << 16);
+                tb.w = rb.w & 0xff;                                       // denom; pad cleared
+                int4 *o = reinterpret_cast<int4 *>(a.tiles + bs + off + k);
+                o[0] = ta; o[1] = tb;
+                k++;
+            }
+            tx += tw;
+        }
+    }
+    if (bad) { gate[1] = 1u; atomicOr(gate + 3, 1u << B200_SEC_MC); latch_host(gate, 1u << B200_SEC_MC); }
+}
+int launch_mc_expand(cudaStream_t st, const B200McRec *blocks, uint32_t n_blocks, B200McRec *tiles, const uint32_t count[5], uint32_t *gate)
+{
+    if (!n_blocks) return 0;
+    McExpandArgs a;
+    a.blocks = blocks; a.n_blocks = n_blocks; a.tiles = tiles;
+    uint32_t o = 0;
+    for (int k = 0; k < 5; k++) { a.base[k] = o; a.count[k] = count[k]; o += count[k]; }
+    B200_LAUNCH((n_blocks + 255) / 256, 256, 0, st, k_mc_expand)(a, gate);
+    return 1;
+}
 
 __device__ __forceinline__ int ref_slot_of(const RefTable &rt, int i)
 {
