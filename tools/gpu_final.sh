@@ -1,17 +1,23 @@
 #!/bin/bash
-# Last GPU visit of the round: full parity suite on the default build, bench with both K1 versions, launch list, full ncu capture.
+# What the driver does at round end, in one visit: GPU suite, smoke, both bench arms.
 tag=${1:-f}
 mkdir -p gpurun_out
-nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm --format=csv,noheader > gpurun_out/${tag}_gpu.txt 2>&1
-( time timeout 600 python -m pytest tests -m gpu -x -q --durations=5 ) > gpurun_out/${tag}_pytest.log 2>&1
-tail -12 gpurun_out/${tag}_pytest.log
-timeout 300 python bench.py > gpurun_out/${tag}_bench.json 2> gpurun_out/${tag}_bench.err
-cat gpurun_out/${tag}_bench.json
-B200_MC=1 timeout 200 python bench.py --no-cpu-baseline > gpurun_out/${tag}_bench_mc1.json 2>> gpurun_out/${tag}_bench.err
-cat gpurun_out/${tag}_bench_mc1.json
-timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none -c 1200 --csv --log-file gpurun_out/${tag}_launches.csv python bench.py --steps 2 --warmup 3 --no-cpu-baseline > gpurun_out/${tag}_ncu_bench.log 2>&1
-timeout 300 ncu --set full --clock-control none --import-source on -c 20 -o gpurun_out/${tag}_bpic python tools/run_pictures.py --only 4 --reps 2 > gpurun_out/${tag}_ncu_full.log 2>&1
-B200_TRACE=gpurun_out/${tag}_trace.csv timeout 200 python bench.py --steps 24 --warmup 4 --no-cpu-baseline > gpurun_out/${tag}_trace_bench.json 2>> gpurun_out/${tag}_bench.err
-python tools/timeline.py gpurun_out/${tag}_trace.csv --from 64 --to 224 | tee gpurun_out/${tag}_timeline.txt
-timeout 200 python bench.py --workload c2_1080p_main_ra --no-cpu-baseline > gpurun_out/${tag}_bench_1080p.json 2>> gpurun_out/${tag}_bench.err
-cat gpurun_out/${tag}_bench_1080p.json
+( time timeout 1200 python -m pytest tests -m gpu -x -q --durations=6 ) > gpurun_out/${tag}_pytest.log 2>&1
+tail -10 gpurun_out/${tag}_pytest.log
+timeout 300 python __graft_entry__.py smoke 2>&1 | tail -2 | tee gpurun_out/${tag}_smoke.txt
+( time timeout 900 python bench.py --impl reference ) > gpurun_out/${tag}_bench_ref.json 2> gpurun_out/${tag}_bench_ref.err
+tail -3 gpurun_out/${tag}_bench_ref.err
+( time timeout 900 python bench.py ) > gpurun_out/${tag}_bench.json 2> gpurun_out/${tag}_bench.err
+tail -3 gpurun_out/${tag}_bench.err
+python - <<PY
+import json
+for f in ("gpurun_out/${tag}_bench_ref.json","gpurun_out/${tag}_bench.json"):
+    try:
+        d=json.loads([l for l in open(f).read().splitlines() if l.startswith("{")][-1])
+    except Exception as e:
+        print(f,"ERR",e); continue
+    print(f, "value %.1f"%d["value"], "e2e", d["e2e"]["value"], d["e2e"].get("md5_equal_reference_decoder"), d.get("clocks"))
+    for k,v in (d.get("stream_e2e") or {}).items():
+        if isinstance(v,dict): print("  ",k,{a:v[a].get("best") for a in ("reference","b200") if a in v}, {a:b for a,b in v.items() if a.startswith("speedup")})
+    if "roofline" in d: print("  roofline", d["roofline"]["kernel"], round(d["roofline"]["frac"],4), {k:round(x["ms"]*1000,1) for k,x in d["roofline"]["stages"].items()}, "launches", d.get("gpu_launches"))
+PY
