@@ -32,6 +32,14 @@ WORKLOADS = {
 METRIC, UNIT = "decoded_frames_per_sec", "frames/s"
 
 
+def workload_config(workload, wl, n_gpus):
+    """the `config` of the JSON line: identical in both arms (the workload, not the implementation; what is specific to an arm --
+    lanes, L2 note, launches -- lives in `arm`)"""
+    return {"workload": workload, "picture": f"{wl['width']}x{wl['height']} 4:2:{'0' if wl['cfi'] == 1 else '2' if wl['cfi'] == 2 else '4'} {wl['bit_depth']}-bit",
+            "gop": "all intra" if wl.get("all_intra") else "hierarchical-B 8, intra period 32", "step": "1 GOP (8 pictures) per rank",
+            "stream": HEADLINE_STREAM.get(workload), "n_gpus": n_gpus}
+
+
 def usable_cpus():
     """host threads this process can really run at once: the affinity mask, capped by the cgroup CPU quota
     (os.cpu_count() reports the machine, not the container)"""
@@ -151,6 +159,11 @@ def stream_block(name, arms, threads_all, device, budget_s=2.5, with_single=True
                 continue
             passes = int(min(64, max(2, 1 + budget_s * probe["steady_fps"] / n + 0.999)))
             best = probe if passes <= 2 else run_decoder(binary, path, t, passes, env)
+            if t > 1 and "error" not in best:            # frame-threaded runs vary by +-10 % from run to run (scheduling): the better of two, both arms alike
+                again = run_decoder(binary, path, t, max(2, passes), env)
+                if "error" not in again and again["steady_fps"] > best["steady_fps"]:
+                    best = again
+                best["runs"] = 2
             res[f"threads_{t}"] = best if "error" not in best else probe
         if arm == "b200":
             res["md5_equal_reference_decoder"] = {f"threads_{t}": decoder_md5_ok(binary, path, t, env) for t in tset}
@@ -258,7 +271,7 @@ def run_reference(args, wl, rank):
             pass
     line = {"metric": METRIC, "value": fps, "unit": UNIT, "impl": "reference", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": 1e3 * sec / max(1, n / 8), "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u16" if wl["bit_depth"] > 8 else "u8",
-            "data": "synthetic", "config": {"workload": args.workload, "gop": "hierarchical-B 8, intra period 32", "pictures_timed": n},
+            "data": "synthetic", "config": workload_config(args.workload, wl, args.gpus), "arm": {"pictures_timed": n},
             "mpixels_per_s": fps * wl["width"] * wl["height"] / 1e6,
             "cpu_baseline": {"value": fps, "unit": UNIT, "cores": threads, "kind": "reference",
                              "sample": f"{n} pictures of the bench stream mix, {threads} threads x {it} pictures, reference C tables (-O3 -fno-tree-vectorize, no asm)",
@@ -279,7 +292,7 @@ def main():
     os.dup2(2, 1)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=256, help="GOPs (8 pictures) per rank in the timed region")
+    ap.add_argument("--steps", type=int, default=512, help="GOPs (8 pictures) per rank in the timed region (512: > 1 s at 4K)")
     ap.add_argument("--warmup", type=int, default=8)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="c3_4k_main10_ra", choices=sorted(WORKLOADS))
@@ -489,9 +502,9 @@ def main():
         line = {"metric": METRIC, "value": fps, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
                 "ms_per_step": ms / (n_mine / 8), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                 "dtype": "u16" if wl["bit_depth"] > 8 else "u8", "data": "synthetic",
-                "config": {"workload": args.workload, "picture": f"{wl['width']}x{wl['height']} 4:2:0 {wl['bit_depth']}-bit", "gop": "hierarchical-B 8, intra period 32",
-                           "step": "1 GOP (8 pictures) per rank", "lanes": int(os.environ.get("B200_LANES", "8")), "parallelism": f"frame-parallel x{world}: intra periods (32 pictures) per GPU, one anchor per period sent to the next GPU over NCCL (send/recv)" if world > 1 else "single GPU",
-                           "l2": "inputs larger than L2: 9 work lists (%.0f MB) + %d-slot DPB (%.0f MB) cycled" % (sum(b.nbytes for b in blobs) / 1e6, FP.N_SLOTS, FP.N_SLOTS * slot_bytes / 1e6)},
+                "config": workload_config(args.workload, wl, world),
+                "arm": {"lanes": int(os.environ.get("B200_LANES", "8")), "parallelism": f"frame-parallel x{world}: intra periods (32 pictures) per GPU, one anchor per period sent to the next GPU over NCCL (send/recv)" if world > 1 else "single GPU",
+                        "l2": "inputs larger than L2: 9 work lists (%.0f MB) + %d-slot DPB (%.0f MB) cycled" % (sum(b.nbytes for b in blobs) / 1e6, FP.N_SLOTS, FP.N_SLOTS * slot_bytes / 1e6)},
                 "mpixels_per_s": fps * wl["width"] * wl["height"] / 1e6,
                 "gpu_launches": int(launches), "clocks": clocks,
                 "e2e": e2e_line, "e2e_replay": e2e_replay, "stream_e2e": stream_e2e,
