@@ -36,6 +36,8 @@
 #include "b200hevc.h"
 #include "b200hevc_tables.h"
 #include <dlfcn.h>
+#include <time.h>
+static inline uint64_t now_ns(void) { struct timespec t; clock_gettime(CLOCK_MONOTONIC, &t); return (uint64_t)t.tv_sec * 1000000000ull + (uint64_t)t.tv_nsec; }
 
 #define MAX_REG 33
 #define MAX_WORKERS 64
@@ -76,6 +78,7 @@ static struct {
     struct { const uint8_t *data0; uint32_t token; int state; unsigned seq; } rb[MAX_RB];
     unsigned rb_seq;
     uint64_t n_pictures, h2d_bytes, d2h_bytes;   /* B200_SHIM_REPORT=1: totals on stderr when the process ends */
+    uint64_t ns_ctx, ns_rec, ns_pool, n_pool, bytes_pool, ns_first_submit;   /* ... and where the start-up time went */
 } G = { .mu = PTHREAD_MUTEX_INITIALIZER, .cv = PTHREAD_COND_INITIALIZER, .cv_sub = PTHREAD_COND_INITIALIZER };
 
 /* one picture on its way to the device (lives in the ShimThread that recorded it: two per thread, used alternately, so that
@@ -630,7 +633,9 @@ static int thread_recorder(int k)
     }
     if (!t->jobs && !(t->jobs = calloc(3, sizeof(Job)))) return B200_ENOMEM;     /* [2]: the ticket-only job of ticket_skip */
     if (!t->recs[k]) {
+        const uint64_t t0 = now_ns();
         int rc = b200_rec_create(&G.cfg, &t->recs[k]);
+        G.ns_rec += now_ns() - t0;
         if (rc) return rc;
     }
     t->rec = t->recs[k];
@@ -725,7 +730,9 @@ static void drain_at_exit(void)
     while (G.sub_running && G.turn != G.next_ticket && !G.err_code) pthread_cond_wait(&G.cv, &G.mu);
     pthread_mutex_unlock(&G.mu);
     if (getenv("B200_SHIM_REPORT"))
-        fprintf(stderr, "b200 shim: pictures %llu h2d_bytes %llu d2h_bytes %llu\n", (unsigned long long)G.n_pictures, (unsigned long long)G.h2d_bytes, (unsigned long long)G.d2h_bytes);
+        fprintf(stderr, "b200 shim: pictures %llu h2d_bytes %llu d2h_bytes %llu\nb200 shim start-up: device context %.0f ms, recorders %.0f ms, pinned frame buffers %llu x (%.0f MB total) %.0f ms\n",
+                (unsigned long long)G.n_pictures, (unsigned long long)G.h2d_bytes, (unsigned long long)G.d2h_bytes,
+                G.ns_ctx * 1e-6, G.ns_rec * 1e-6, (unsigned long long)G.n_pool, G.bytes_pool * 1e-6, G.ns_pool * 1e-6);
 }
 
 static void enqueue(Job *j)                        /* j->ticket is this thread's ticket */
@@ -781,7 +788,9 @@ static int ensure_ctx(const HEVCContext *s)       /* called with G.mu held */
         G.cfg.n_slots = 32;                /* == FF_ARRAY_ELEMS(s->DPB), hevc.h:1207 */
         G.cfg.n_arenas = 8;
         if (!G.dump_dir) {
+            const uint64_t t0 = now_ns();
             int rc = b200_ctx_create(&G.cfg, &G.ctx);
+            G.ns_ctx += now_ns() - t0;
             if (rc) { fail(rc, b200_last_error(NULL)); return rc; }
         }
         G.configured = 1;
@@ -1102,9 +1111,11 @@ struct AVBufferRef *b200_frame_buffer_alloc(int size)
     if (!create || !allocz) return NULL;
     static int use_pinned = -1;
     if (use_pinned < 0) use_pinned = !getenv("B200_SHIM_DUMP") && !(getenv("B200_PINNED_FRAMES") && !atoi(getenv("B200_PINNED_FRAMES")));
+    const uint64_t t0 = now_ns();
     uint8_t *p = use_pinned && size > 0 ? b200_host_alloc((uint64_t)size) : NULL;
     if (!p) return allocz(size);
     memset(p, 0, (size_t)size);
+    __atomic_fetch_add(&G.ns_pool, now_ns() - t0, __ATOMIC_RELAXED); __atomic_fetch_add(&G.n_pool, 1, __ATOMIC_RELAXED); __atomic_fetch_add(&G.bytes_pool, (uint64_t)size, __ATOMIC_RELAXED);
     struct AVBufferRef *r = create(p, size, frame_buffer_free, NULL, 0);
     if (!r) { b200_host_free(p); return NULL; }
     return r;
