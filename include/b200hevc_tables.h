@@ -16,6 +16,8 @@
  *                          leaves the decoder long after it was decoded (bumping, hevc_refs.c:182-307)
  *   b200_frame_buffer_alloc  allocator for the decoder's frame pool in place of av_buffer_allocz (libavcodec/utils.c:558-561):
  *                          picture planes in page-locked memory, so that read-backs are asynchronous DMAs at full PCIe rate
+ *   b200_worker_begin      first statement of hls_decode_entry_wpp / _tiles / _wpp_in_tiles (libavcodec/hevc.c:2764, 2847, 2931):
+ *                          the slice / WPP / tile worker thread records for the picture of THIS context (frame + slice threads)
  *   b200_frame_fill        when generate_missing_ref() has filled a grey reference  (libavcodec/hevc_refs.c:538-606)
  *   b200_bs_on_device      first statement of ff_hevc_deblocking_boundary_strengths() (libavcodec/hevc_filter.c:808): the call is
  *                          recorded as one word and the function returns (non-zero result)
@@ -59,6 +61,7 @@ int  b200_frame_fill(struct HEVCContext *s, struct HEVCFrame *frame);       /* g
 int  b200_frame_upload_ref(struct HEVCContext *s, struct AVFrame *frame);   /* host-only reference picture -> device slot */
 int  b200_bs_on_device(struct HEVCContext *s, int x0, int y0, int log2_size);
 int  b200_deblock_on_device(void);
+int  b200_worker_begin(struct HEVCContext *owner);                          /* first statement of an execute2 job: owner = avctx->priv_data */
 int  b200_host_pixels_unused(void);                                         /* 1 once the B200 tables are installed */
 void b200_shim_close(void);
 const char *b200_shim_error(void);

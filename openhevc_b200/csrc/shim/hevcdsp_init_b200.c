@@ -15,8 +15,8 @@
  * the picture it decodes, pictures are submitted to the GPU in decode order through a ticket.  Slice / WPP / tile worker
  * threads of ONE picture (-f 2, execute2 jobs, hevc.c:3082): a worker attaches itself to the picture in progress on its
  * first table call, records into its own B200Rec, and b200_frame_end folds the workers into the owner's recorder
- * (b200_rec_merge).  Frame and slice threads combined (-f 4) are rejected: a table call carries no context, so a worker
- * cannot tell which of several pictures in progress it belongs to.  One decoder instance per process.
+ * (b200_rec_merge).  Frame and slice threads combined (-f 4): several pictures are in progress and a table call carries no
+ * context, so the execute2 jobs say which picture they belong to (b200_worker_begin).  One decoder instance per process.
  *
  * Pictures reach the device through ONE submission thread (the engine's threading contract, include/b200hevc.h): a decoding
  * thread that has parsed its picture hands the finished work list over (a queue ordered by the ticket taken at
@@ -182,16 +182,19 @@ const char *b200_shim_error(void) { return g.err ? g.errmsg : (G.ctx ? b200_last
 static int thread_recorder(int k);
 /* A table call on a thread that owns no picture: a slice / WPP / tile worker (execute2 job).  Attach it to the picture
  * in progress: own recorder, own reference table, a copy of the owner's plane registry. */
-static int attach_slow(void)
+static int attach_to(const HEVCContext *owner)     /* owner: the context b200_frame_begin was called with, or NULL = "the one picture in progress" */
 {
     pthread_mutex_lock(&G.mu);
     int rc = 0;
-    if (G.n_active != 1) {
-        fail(B200_ENOTSUP, G.n_active ? "table call from a worker thread with several pictures in progress (frame + slice threads combined)"
-                                      : "table call outside b200_frame_begin / b200_frame_end");
+    ShimThread *o = NULL;
+    if (owner) { for (int i = 0; i < G.n_active; i++) if (G.active[i]->s == owner) o = G.active[i]; }
+    else if (G.n_active == 1) o = G.active[0];
+    if (!o) {
+        fail(B200_ENOTSUP, owner || !G.n_active ? "table call outside b200_frame_begin / b200_frame_end"
+                                                : "table call from a worker thread with several pictures in progress (frame + slice threads combined) "
+                                                  "and no b200_worker_begin hook in the decoder");
         rc = -1;
     } else {
-        ShimThread *o = G.active[0];
         if (thread_recorder(0)) { fail(B200_ENOMEM, "b200_rec_create failed (worker)"); rc = -1; }
         if (!rc && o->n_workers == MAX_WORKERS) { fail(B200_ENOTSUP, "too many worker threads"); rc = -1; }
         if (!rc) {
@@ -213,7 +216,21 @@ static inline int attached(void)
     if (g.in_frame == 1) return 1;
     if (g.err) return 0;
     if (g.in_frame == 2 && g.att->in_frame == 1 && g.att->frame_seq == g.att_seq) return 1;
-    return attach_slow() == 0;
+    return attach_to(NULL) == 0;
+}
+/* First statement of the decoder's execute2 jobs (hls_decode_entry_wpp / _tiles / _wpp_in_tiles, hevc.c:2751-2931), called with
+ * the context the job belongs to (avctx->priv_data): the worker thread records for THAT picture.  With this hook frame threads
+ * whose pictures are decoded by slice threads (-f 4, pthread.c:57-71) work: several pictures are in progress at once and a table
+ * call alone cannot tell which one it belongs to.  Without it (-f 2 only) a worker attaches itself on its first table call. */
+int b200_worker_begin(HEVCContext *owner)
+{
+    ShimThread *t = &g;
+    if (t->in_frame == 1 && t->s == owner) return 0;                       /* the owner thread runs a job itself */
+    if (t->err) return t->err;
+    if (t->in_frame == 2 && t->att->s == owner && t->att->in_frame == 1 && t->att->frame_seq == t->att_seq) return 0;
+    if (t->in_frame == 1) { fail(B200_ESTATE, "b200_worker_begin on a thread that owns another picture"); return t->err; }
+    t->in_frame = 0;
+    return attach_to(owner) ? t->err : 0;
 }
 
 /* ---- pointer -> (slot, plane, x, y) ---------------------------------------------------------------- */
@@ -545,9 +562,10 @@ static void rec_intra_5(HEVCContext *s, int x0, int y0, int c) { rec_intra(s, x0
  * the host path (tiles_filters recomputes the strengths at tile borders with its own rules, hevc.c:2967-3003). */
 static int dbd_mode(void)
 {
-    static int mode = -1;
-    if (mode < 0) { const char *e = getenv("B200_DBD"); mode = e ? atoi(e) : 1; if (mode < 0 || mode > 2) mode = 0; }
-    return mode;
+    static int mode = -1;                          /* every frame thread asks: relaxed atomics, the value is the same whoever writes it */
+    int m = __atomic_load_n(&mode, __ATOMIC_RELAXED);
+    if (m < 0) { const char *e = getenv("B200_DBD"); m = e ? atoi(e) : 1; if (m < 0 || m > 2) m = 0; __atomic_store_n(&mode, m, __ATOMIC_RELAXED); }
+    return m;
 }
 int b200_bs_on_device(HEVCContext *s, int x0, int y0, int log2_size)
 {
@@ -1104,13 +1122,20 @@ int b200_frame_upload_ref(HEVCContext *s, AVFrame *frame)
 typedef struct AVBufferRef *(*av_buffer_create_fn)(uint8_t *, int, void (*)(void *, uint8_t *), void *, int);
 typedef struct AVBufferRef *(*av_buffer_allocz_fn)(int);
 static void frame_buffer_free(void *opaque, uint8_t *data) { (void)opaque; b200_host_free(data); }
+static struct { av_buffer_create_fn create; av_buffer_allocz_fn allocz; int use_pinned; } g_pool_fn;
+static pthread_once_t g_pool_fn_once = PTHREAD_ONCE_INIT;
+static void pool_fn_lookup(void)                   /* once: every frame thread's pool calls the allocator */
+{
+    g_pool_fn.create = (av_buffer_create_fn)dlsym(RTLD_DEFAULT, "av_buffer_create");
+    g_pool_fn.allocz = (av_buffer_allocz_fn)dlsym(RTLD_DEFAULT, "av_buffer_allocz");
+    g_pool_fn.use_pinned = !getenv("B200_SHIM_DUMP") && !(getenv("B200_PINNED_FRAMES") && !atoi(getenv("B200_PINNED_FRAMES")));
+}
 struct AVBufferRef *b200_frame_buffer_alloc(int size)
 {
-    static av_buffer_create_fn create; static av_buffer_allocz_fn allocz;
-    if (!create) { create = (av_buffer_create_fn)dlsym(RTLD_DEFAULT, "av_buffer_create"); allocz = (av_buffer_allocz_fn)dlsym(RTLD_DEFAULT, "av_buffer_allocz"); }
+    pthread_once(&g_pool_fn_once, pool_fn_lookup);
+    const av_buffer_create_fn create = g_pool_fn.create; const av_buffer_allocz_fn allocz = g_pool_fn.allocz;
     if (!create || !allocz) return NULL;
-    static int use_pinned = -1;
-    if (use_pinned < 0) use_pinned = !getenv("B200_SHIM_DUMP") && !(getenv("B200_PINNED_FRAMES") && !atoi(getenv("B200_PINNED_FRAMES")));
+    const int use_pinned = g_pool_fn.use_pinned;
     const uint64_t t0 = now_ns();
     uint8_t *p = use_pinned && size > 0 ? b200_host_alloc((uint64_t)size) : NULL;
     if (!p) return allocz(size);

@@ -27,6 +27,8 @@ sed -i -e "0,/^#include/s//$inc\n#include/" \
        -e '/^\s*s->is_decoded = 1;/,/tiles_filters(s);/ s/^\(\s*\)tiles_filters(s);/&\n\1if ((ret = b200_frame_end(s)) < 0) goto fail;   \/* after the filters of tile threads *\//' \
        -e 's|^\(\s*\)ret    = decode_nal_units(s, avpkt->data, avpkt->size);|&\n\1b200_frame_readback(s, s->is_decoded \&\& s->ref ? s->ref->frame : NULL);   /* NULL: no complete picture came out of the packet */|' \
        -e 's|^\(\s*\)av_frame_move_ref(data, s->output_frame);|\1b200_output_wait(s, s->output_frame);   /* the picture leaves the decoder: its read-back has landed */\n&|' \
+       -e 's/^\(\s*\)s = s1->sList\[self_id\];/\1b200_worker_begin(s1);   \/* execute2 job: this worker records for s1'"'"'s picture *\/\n&/' \
+       -e 's/^\(\s*\)s = s->sList\[self_id\];/\1b200_worker_begin(s);\n&/' \
        -e '/^\s*ret = ff_hevc_output_frame(s, data, 1);/,/^\s*return ret;/ s|^\(\s*\)return ret;|&\n        if (ret > 0) b200_output_wait(s, data);|' "$P/hevc.c"
 # the decoder's frame pool in pinned memory (utils.c:558-561 passes av_buffer_allocz)
 sed -i -e "0,/^#include/s//$inc\n#include/" \
@@ -44,7 +46,7 @@ if [ -z "${B200_NO_COPY_GUARD:-}" ]; then
          -e '/^static void copy_CTB/,/^}/ s/^    int i;/&\n    if (b200_host_pixels_unused()) return;/' "$P/hevc_filter.c"
   grep -q "b200_host_pixels_unused" "$P/hevc_filter.c" || { echo "hook b200_host_pixels_unused was not inserted" >&2; exit 1; }
 fi
-for pat in ff_hevcdsp_init_b200 ff_hevcpred_init_b200 ff_videodsp_init_b200 b200_frame_begin b200_frame_end b200_frame_readback b200_frame_fill b200_frame_buffer_alloc b200_bs_on_device b200_deblock_on_device; do
+for pat in ff_hevcdsp_init_b200 ff_hevcpred_init_b200 ff_videodsp_init_b200 b200_frame_begin b200_frame_end b200_frame_readback b200_frame_fill b200_frame_buffer_alloc b200_bs_on_device b200_deblock_on_device b200_worker_begin; do
   grep -q "$pat" "$P"/*.c || { echo "hook $pat was not inserted" >&2; exit 1; }
 done
 CFLAGS=$(cat "$OUT/cflags.txt")

@@ -26,15 +26,16 @@ static void plane_md5(const uint8_t *p, int pitch, int w_bytes, int h, char *hex
 
 int main(int argc, char **argv)
 {
-    if (argc < 2) { fprintf(stderr, "usage: %s stream.hevc [threads[w] [quiet|time [passes]]]   (N: frame threads, hevc -p N -f 1; Nw: slice / WPP threads, -f 2)\n", argv[0]); return 2; }
+    if (argc < 2) { fprintf(stderr, "usage: %s stream.hevc [threads[w] [quiet|time [passes]]]   (N: frame threads, hevc -p N -f 1; Nw: slice / WPP threads, -f 2; Nx: N slice threads inside frame threads, -f 4)\n", argv[0]); return 2; }
     const int threads = argc > 2 ? atoi(argv[2]) : 1;
     const int slice_threads = argc > 2 && strchr(argv[2], 'w') != NULL;
+    const int frame_slice = argc > 2 && strchr(argv[2], 'x') != NULL;   /* pthread.c:57-71: frames = cpus / N + 1 */
     const int quiet = argc > 3 && strcmp(argv[3], "md5");      /* "md5": print the per-picture lines even with a pass count */
     const int loops = argc > 4 ? atoi(argv[4]) : 1;             /* decode the file this many times back to back (the stream
                                                                    starts with parameter sets + IDR, so the concatenation is a valid
                                                                    stream); the steady-state fps excludes the first pass (start-up) */
     const int timing = argc > 3 && !strcmp(argv[3], "time");    /* fps run: no MD5 work inside the timed loop */
-    OpenHevc_Handle h = libOpenHevcInit(threads > 0 ? threads : 1, slice_threads ? 2 /* slice */ : 1 /* frame */);
+    OpenHevc_Handle h = libOpenHevcInit(threads > 0 ? threads : 1, frame_slice ? 4 /* frame + slice */ : slice_threads ? 2 /* slice */ : 1 /* frame */);
     if (!h) return 3;
     libOpenHevcSetCheckMD5(h, 0);
     av_register_all();

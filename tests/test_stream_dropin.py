@@ -111,6 +111,10 @@ def test_hooked_decoder_with_wpp_threads(stream):
     want = open(stream[:-5] + ".md5").read().splitlines()
     for rep in range(2 if stream in REPEATED else 1):
         assert run("decode_b200", stream, threads="4w") == want
+    if len(want) >= 4:
+        # hevc -f 4: frame threads with two slice threads each (pthread.c:57-71) -- several pictures in progress, every one of
+        # them recorded by several workers (b200_worker_begin)
+        assert run("decode_b200", stream, threads="2x") == want
 
 
 @pytest.mark.gpu
@@ -138,7 +142,7 @@ def test_table_calls_equal_what_the_generator_wrote(stream, threads):
 # tools/make_bench_streams.sh regenerates the streams (fixed seeds) into oracle/_ref/streams/ and pins each with the per-picture
 # MD5s of the unmodified decoder (decode_ref, one thread); __graft_entry__.build() runs it when the files are missing.
 RECIPE_DIR = os.path.join(REFDIR, "streams")
-RECIPES = ["c1_832x480_i_16", "c2_1080p_ra8_65", "c3_4k_ra8_calm_65", "c3_4k_ra8_mid_65", "c3_4k_ra8_dense_33", "c5_8k_422_wpp_tiles_9"]
+RECIPES = ["c1_832x480_i_16", "c2_1080p_ra8_65", "c2_1080p_wpp_ra8_33", "c3_4k_ra8_calm_65", "c3_4k_ra8_mid_65", "c3_4k_ra8_dense_33", "c5_8k_422_wpp_tiles_9"]
 
 
 @pytest.mark.gpu
@@ -155,6 +159,19 @@ def test_baseline_shape_streams_are_bit_exact(name, threads):
         pytest.skip("recipe stream not generated (tools/make_bench_streams.sh)")
     if threads == 8 and name in ("c1_832x480_i_16", "c5_8k_422_wpp_tiles_9"):
         pytest.skip("fewer pictures than delayed frames: the reference's flush logic (main_hm/main.c:283) drops pictures with that many threads")
+    assert run("decode_b200", stream, threads) == open(md5).read().splitlines()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("threads", ["4w", "2x", "4x"])
+def test_frame_threads_with_slice_threads_inside_are_bit_exact(threads):
+    """VERDICT r1 item 9, hevc -f 4 (libavcodec/pthread.c:57-71: N slice threads per picture, cpus / N + 1 frame threads): several
+    pictures are in progress at once and every one of them is recorded by several WPP workers.  A table call carries no context,
+    so the execute2 jobs announce the picture they work for (b200_worker_begin, hevc.c:2764 / 2847 / 2931); b200_frame_end folds
+    the workers' lists into their picture's.  1920x1080 WPP stream, hierarchical-B GOP 8, 33 pictures; "4w" = slice threads only."""
+    stream, md5 = os.path.join(RECIPE_DIR, "c2_1080p_wpp_ra8_33.hevc"), os.path.join(RECIPE_DIR, "c2_1080p_wpp_ra8_33.md5")
+    if not (os.path.exists(stream) and os.path.exists(md5) and os.path.exists(os.path.join(REFDIR, "decode_b200"))):
+        pytest.skip("recipe stream not generated (tools/make_bench_streams.sh)")
     assert run("decode_b200", stream, threads) == open(md5).read().splitlines()
 
 

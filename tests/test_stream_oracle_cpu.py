@@ -26,12 +26,13 @@ SMALL = [s for s in STREAMS if os.path.getsize(s) < 400_000]          # the 1080
 
 
 @pytest.mark.parametrize("dbd", ["derive", "check"])
-@pytest.mark.parametrize("threads", ["1", "4", "4w"])
+@pytest.mark.parametrize("threads", ["1", "4", "4w", "2x"])
 @pytest.mark.parametrize("stream", SMALL, ids=[os.path.basename(s) for s in SMALL])
 def test_recorded_work_lists_through_the_oracle_equal_the_reference_decoder(stream, threads, dbd):
     """threads: "1"; "4" = four frame threads (pictures recorded concurrently, dumped in decode order by the shim's ticket);
     "4w" = four slice-thread workers (WPP rows, or tiles) recording one picture together (merged by b200_rec_merge) -- streams with
-    entry points only.
+    entry points only; "2x" = frame threads whose pictures are decoded by two slice threads each (hevc -f 4, pthread.c:57-71:
+    several pictures in progress, each recorded by several workers -- b200_worker_begin tells a worker which one it is on).
     dbd: "derive" (the default of the drop-in) = the work lists carry the INPUTS of the deblocking control
     (transform-tree leaves, QP map, slice offsets; motion and cbf are in the MC / TU records) and the oracle derives boundary
     strengths, tc and beta itself (orc_dbd_derive, restating hevc_filter.c:345-581, 583-700, 805-941); "check" (B200_DBD=2) = the
@@ -41,7 +42,7 @@ def test_recorded_work_lists_through_the_oracle_equal_the_reference_decoder(stre
     binary = os.path.join(REFDIR, "decode_b200")
     if not os.path.exists(binary):
         pytest.skip("oracle/_ref/decode_b200 not built (needs /root/reference)")
-    if threads == "4w" and not os.path.basename(stream).startswith(("wpp_", "tiles_")):
+    if threads in ("4w", "2x") and not os.path.basename(stream).startswith(("wpp_", "tiles_")):
         pytest.skip("no entry points: slice threads fall back to one thread")
     # the arbiter is the UNMODIFIED decoder run the same way.  Single thread: that is the committed MD5 file.  With threads
     # the reference may differ from itself: it never clears s->is_pcm between pictures (hevc.c:147, only allocated zeroed), so
@@ -59,7 +60,7 @@ def test_recorded_work_lists_through_the_oracle_equal_the_reference_decoder(stre
                            env=dict(os.environ, B200_SHIM_DUMP=d, B200_SHIM_STATS="1"))
         assert r.returncode == 0, r.stderr[-2000:]
         gen_path = stream[:-5] + ".gen.txt"
-        if os.path.exists(gen_path) and threads != "4":      # B200_SHIM_STATS: the table calls per picture == what the generator wrote
+        if os.path.exists(gen_path) and threads not in ("4", "2x"):      # B200_SHIM_STATS: the table calls per picture == what the generator wrote
             import re                                        # (with frame threads the lines come in completion order)
             gen = [tuple(int(v) for v in m.groups()) for m in re.finditer(r"intra_pred (\d+) transform_add (\d+) prediction units (\d+)", open(gen_path).read())]
             got = [tuple(int(v) for v in m.groups()) for m in re.finditer(r"b200 picture \d+: intra_pred (\d+) transform_add (\d+) mc (\d+)", r.stderr)]

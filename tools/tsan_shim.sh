@@ -9,11 +9,11 @@ gcc -O1 -g -std=gnu99 -fPIC -w -shared -fsanitize=thread -Ioracle/_ref/gen -I/ro
 rt=$(gcc -print-file-name=libtsan.so)
 cd oracle/_ref
 S=../../tests/golden/streams
-for args in "$S/b_416x240_10b_weighted.hevc 4" "$S/ra_416x240_8b.hevc 4" "$S/wpp_416x240_8b_lowdelay.hevc 4w" "streams/c2_1080p_ra8_65.hevc 8"; do
+for args in "$S/b_416x240_10b_weighted.hevc 4" "$S/ra_416x240_8b.hevc 4" "$S/wpp_416x240_8b_lowdelay.hevc 4w" "$S/wpp_832x480_10b_weighted.hevc 2x" "streams/c2_1080p_wpp_ra8_33.hevc 2x" "streams/c2_1080p_ra8_65.hevc 8"; do
   B200_SHIM_DUMP=- TSAN_OPTIONS="halt_on_error=0 report_signal_unsafe=0" LD_PRELOAD="$rt /tmp/libb200hevc_shim_tsan.so" timeout 900 ./decode_b200 $args quiet > /dev/null 2> /tmp/tsan_err.txt || true
   echo "record-only  $args: $(grep -c 'WARNING: ThreadSanitizer' /tmp/tsan_err.txt) reports"
 done
-for args in "$S/b_416x240_10b_weighted.hevc 4" "$S/ra_416x240_8b.hevc 4"; do
+for args in "$S/b_416x240_10b_weighted.hevc 4" "$S/ra_416x240_8b.hevc 4" "$S/wpp_416x240_8b_lowdelay.hevc 2x"; do
   TSAN_OPTIONS="halt_on_error=0 report_signal_unsafe=0" LD_PRELOAD="$rt /tmp/libb200hevc_shim_tsan.so $PWD/libb200hevc_emul.so" timeout 900 ./decode_b200 $args > /tmp/tsan_out.txt 2> /tmp/tsan_err.txt || true
   echo "emulated dev $args: $(grep -c 'WARNING: ThreadSanitizer' /tmp/tsan_err.txt) reports, pictures $(grep '^frame ' /tmp/tsan_out.txt | diff -q - ${args%% *} > /dev/null 2>&1; grep '^frame ' /tmp/tsan_out.txt | diff -q - $(echo ${args%% *} | sed 's/.hevc$/.md5/') > /dev/null && echo identical || echo DIFFERENT)"
 done
