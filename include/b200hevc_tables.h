@@ -18,6 +18,8 @@
  *                          picture planes in page-locked memory, so that read-backs are asynchronous DMAs at full PCIe rate
  *   b200_worker_begin      first statement of hls_decode_entry_wpp / _tiles / _wpp_in_tiles (libavcodec/hevc.c:2764, 2847, 2931):
  *                          the slice / WPP / tile worker thread records for the picture of THIS context (frame + slice threads)
+ *   b200_decoder_close     first statement of hevc_decode_free() (libavcodec/hevc.c:4193): the decoder's device context, its
+ *                          submission thread and its entry in the shim's instance table are given back
  *   b200_frame_fill        when generate_missing_ref() has filled a grey reference  (libavcodec/hevc_refs.c:538-606)
  *   b200_bs_on_device      first statement of ff_hevc_deblocking_boundary_strengths() (libavcodec/hevc_filter.c:808): the call is
  *                          recorded as one word and the function returns (non-zero result)
@@ -63,6 +65,7 @@ int  b200_bs_on_device(struct HEVCContext *s, int x0, int y0, int log2_size);
 int  b200_deblock_on_device(void);
 int  b200_worker_begin(struct HEVCContext *owner);                          /* first statement of an execute2 job: owner = avctx->priv_data */
 int  b200_host_pixels_unused(void);                                         /* 1 once the B200 tables are installed */
+void b200_decoder_close(struct HEVCContext *s);                             /* hevc_decode_free: this decoder's device context is released */
 void b200_shim_close(void);
 const char *b200_shim_error(void);
 

@@ -49,9 +49,13 @@ typedef struct RegPlane { const uint8_t *base; ptrdiff_t linesize, size; uint64_
 
 #include <pthread.h>
 
-/* shared by every decoding thread: the device context, the geometry, and the ticket that keeps pictures in decode
- * order on the GPU (frame threads reach b200_frame_end out of order; hevc_frame_start is called in decode order) */
-static struct {
+/* One per decoder instance (an avcodec context the application opened; with frame threads all its thread copies): shared by
+ * every decoding thread of that decoder -- the device context, the geometry, and the ticket that keeps pictures in decode
+ * order on the GPU (frame threads reach b200_frame_end out of order; hevc_frame_start is called in decode order).  A thread
+ * reaches the instance it is working for through its ShimThread (`G` below). */
+#define MAX_INST 8
+typedef struct Instance {
+    const void *key;                    /* instance_key() of the decoder that owns this entry, NULL = free */
     B200Ctx *ctx;
     B200Config cfg;
     int bd, B, cfi;
@@ -79,7 +83,10 @@ static struct {
     unsigned rb_seq;
     uint64_t n_pictures, h2d_bytes, d2h_bytes;   /* B200_SHIM_REPORT=1: totals on stderr when the process ends */
     uint64_t ns_ctx, ns_rec, ns_pool, n_pool, bytes_pool, ns_first_submit;   /* ... and where the start-up time went */
-} G = { .mu = PTHREAD_MUTEX_INITIALIZER, .cv = PTHREAD_COND_INITIALIZER, .cv_sub = PTHREAD_COND_INITIALIZER };
+} Instance;
+static Instance g_insts[MAX_INST] = { [0 ... MAX_INST - 1] = { .mu = PTHREAD_MUTEX_INITIALIZER, .cv = PTHREAD_COND_INITIALIZER, .cv_sub = PTHREAD_COND_INITIALIZER } };
+static pthread_mutex_t g_insts_mu = PTHREAD_MUTEX_INITIALIZER;      /* guards the keys */
+static unsigned g_gen_counter;          /* context generations are unique across instances (a thread's recorders follow (instance, generation)) */
 
 /* one picture on its way to the device (lives in the ShimThread that recorded it: two per thread, used alternately, so that
  * a thread can parse its next picture while the previous one's work list is still being uploaded) */
@@ -98,6 +105,8 @@ enum { JOB_SKIP = 0, JOB_PICTURE = 1 };
  * frame threads one per picture in flight, pthread_frame.c) or a slice / WPP worker attached to an owner's picture */
 struct Job;
 typedef struct ShimThread {
+    Instance *inst;                     /* the decoder instance this block belongs to: a thread has one block per instance it works for */
+    struct ShimThread *next_mine;       /* the same thread's block for another instance */
     B200Rec *rec;                       /* the recorder of the picture in progress: recs[cur] (workers: recs[0]) */
     B200Rec *recs[2];
     struct Job *jobs;                   /* [3], allocated with the first recorder */
@@ -136,48 +145,86 @@ typedef struct ShimThread {
  * shared library costs a __tls_get_addr call per table call (2.4% of the hooked decoder's CPU time plus the PLT), and the
  * struct itself is too large for the static TLS surplus if libOpenHevc is dlopen()ed.  Blocks of threads that exited are
  * recycled, never freed: workers keep pointers to their owner's block (att), and frame_seq must stay monotonic. */
-static __thread struct ShimThread *g_self __attribute__((tls_model("initial-exec")));
+static __thread struct ShimThread *g_self __attribute__((tls_model("initial-exec")));      /* this thread's block for the instance it is working for */
+static __thread struct ShimThread *g_mine __attribute__((tls_model("initial-exec")));      /* all blocks of this thread (next_mine) */
 static pthread_key_t g_key;
 static pthread_once_t g_key_once = PTHREAD_ONCE_INIT;
 static pthread_mutex_t g_pool_mu = PTHREAD_MUTEX_INITIALIZER;
 static ShimThread *g_pool[256]; static int g_pool_n;
-static ShimThread g_oom = { .err = B200_ENOMEM, .errmsg = "out of memory (per-thread state of the B200 shim)" };
+static ShimThread g_oom = { .inst = &g_insts[0], .err = B200_ENOMEM, .errmsg = "out of memory (per-thread state of the B200 shim)" };
 
 static void shim_thread_exit(void *p)
 {
-    ShimThread *t = p;
-    if (t == &g_oom) return;
     pthread_mutex_lock(&g_pool_mu);
-    t->in_frame = 0;
-    if (g_pool_n < 256) g_pool[g_pool_n++] = t;         /* else: leaked, 256 exited threads are already parked */
+    for (ShimThread *t = p, *next; t; t = next) {
+        next = t->next_mine;
+        if (t == &g_oom) continue;
+        t->in_frame = 0; t->next_mine = NULL;
+        if (g_pool_n < 256) g_pool[g_pool_n++] = t;     /* else: leaked, 256 blocks of exited threads are already parked */
+    }
     pthread_mutex_unlock(&g_pool_mu);
 }
 static void shim_key_make(void) { pthread_key_create(&g_key, shim_thread_exit); }
-static __attribute__((noinline)) ShimThread *shim_self_slow(void)
+/* this thread's block for instance I (created on first use) becomes the current one */
+static __attribute__((noinline)) ShimThread *shim_block_for(Instance *I)
 {
+    for (ShimThread *t = g_mine; t; t = t->next_mine) if (t->inst == I) return g_self = t;
     pthread_once(&g_key_once, shim_key_make);
     pthread_mutex_lock(&g_pool_mu);
     ShimThread *t = g_pool_n ? g_pool[--g_pool_n] : NULL;
     pthread_mutex_unlock(&g_pool_mu);
     if (t) { t->err = 0; t->n_fill = 0; t->n_workers = 0; t->att = NULL; }
     else t = calloc(1, sizeof(*t));
-    if (!t) t = &g_oom;
-    g_self = t;
+    if (!t) return g_self = &g_oom;
+    t->inst = I;
+    t->next_mine = g_mine; g_mine = t;
     pthread_setspecific(g_key, t);
-    return t;
+    return g_self = t;
 }
+static __attribute__((noinline)) ShimThread *shim_self_slow(void) { return shim_block_for(&g_insts[0]); }
 static inline ShimThread *shim_self(void)
 {
     ShimThread *t = g_self;
     return __builtin_expect(t != NULL, 1) ? t : shim_self_slow();
 }
 #define g (*shim_self())
+#define G (*g.inst)
 
 static void fail(int code, const char *msg)
 {
     if (!g.err) { g.err = code; snprintf(g.errmsg, sizeof(g.errmsg), "%s", msg); }
 }
 const char *b200_shim_error(void) { return g.err ? g.errmsg : (G.ctx ? b200_last_error(G.ctx) : ""); }
+
+/* ---- decoder instances ---------------------------------------------------------------------------------------------
+ * Which decoder does a context belong to?  Unthreaded and slice-threaded decoders: the AVCodecContext.  Frame threads decode on
+ * COPIES of the context (pthread_frame.c:758-800), which all belong to the application's one decoder: a copy's
+ * internal->thread_ctx_frame is its PerThreadContext, whose first member is the FrameThreadContext they share
+ * (pthread_frame.c:56-57).  Callers that drive the tables without an AVCodecContext (oracle/replay_ref.c) are their own key. */
+#include "libavcodec/internal.h"
+static const void *instance_key(const HEVCContext *s)
+{
+    const AVCodecContext *a = s->avctx;
+    if (!a) return s;
+    /* (the copy of thread 0 is not marked is_copy, pthread_frame.c:797-812; the application's own context never decodes) */
+    if ((a->active_thread_type & FF_THREAD_FRAME) && a->internal && a->internal->thread_ctx_frame) return *(void *const *)a->internal->thread_ctx_frame;
+    return a;
+}
+/* the calling thread works for the decoder of `s` from here on (every hook that is handed a context starts with this) */
+static int use_instance(const HEVCContext *s)
+{
+    const void *key = instance_key(s);
+    ShimThread *t = shim_self();
+    if (__atomic_load_n(&t->inst->key, __ATOMIC_RELAXED) == key) return 0;
+    Instance *I = NULL;
+    pthread_mutex_lock(&g_insts_mu);
+    for (int i = 0; i < MAX_INST && !I; i++) if (g_insts[i].key == key) I = &g_insts[i];
+    for (int i = 0; i < MAX_INST && !I; i++) if (!g_insts[i].key) { I = &g_insts[i]; __atomic_store_n(&I->key, key, __ATOMIC_RELAXED); }
+    pthread_mutex_unlock(&g_insts_mu);
+    if (!I) { fail(B200_ENOTSUP, "more than 8 decoders open in this process"); return B200_ENOTSUP; }
+    shim_block_for(I);
+    return 0;
+}
 
 static int thread_recorder(int k);
 /* A table call on a thread that owns no picture: a slice / WPP / tile worker (execute2 job).  Attach it to the picture
@@ -193,6 +240,8 @@ static int attach_to(const HEVCContext *owner)     /* owner: the context b200_fr
         fail(B200_ENOTSUP, owner || !G.n_active ? "table call outside b200_frame_begin / b200_frame_end"
                                                 : "table call from a worker thread with several pictures in progress (frame + slice threads combined) "
                                                   "and no b200_worker_begin hook in the decoder");
+        /* nobody would collect this thread's error (it is on no picture's worker list): the whole decoder hears of it */
+        if (!G.err_code) { G.err_code = g.err; snprintf(G.errmsg, sizeof(G.errmsg), "%s", g.errmsg); }
         rc = -1;
     } else {
         if (thread_recorder(0)) { fail(B200_ENOMEM, "b200_rec_create failed (worker)"); rc = -1; }
@@ -224,6 +273,7 @@ static inline int attached(void)
  * call alone cannot tell which one it belongs to.  Without it (-f 2 only) a worker attaches itself on its first table call. */
 int b200_worker_begin(HEVCContext *owner)
 {
+    if (use_instance(owner)) return g.err;
     ShimThread *t = &g;
     if (t->in_frame == 1 && t->s == owner) return 0;                       /* the owner thread runs a job itself */
     if (t->err) return t->err;
@@ -720,7 +770,7 @@ static int process_job(Job *j, char *msg, size_t msg_n)
 
 static void *submit_main(void *arg)
 {
-    (void)arg;
+    shim_block_for((Instance *)arg);               /* G = the instance this thread was started for */
     pthread_mutex_lock(&G.mu);
     for (;;) {
         Job *j;
@@ -744,23 +794,30 @@ static void *submit_main(void *arg)
  * (B200_SHIM_DUMP) write their files on the submission thread */
 static void drain_at_exit(void)
 {
-    pthread_mutex_lock(&G.mu);
-    while (G.sub_running && G.turn != G.next_ticket && !G.err_code) pthread_cond_wait(&G.cv, &G.mu);
-    pthread_mutex_unlock(&G.mu);
+    uint64_t tot[8] = { 0 };
+    for (int i = 0; i < MAX_INST; i++) {
+        Instance *I = &g_insts[i];
+        pthread_mutex_lock(&I->mu);
+        while (I->sub_running && I->turn != I->next_ticket && !I->err_code) pthread_cond_wait(&I->cv, &I->mu);
+        pthread_mutex_unlock(&I->mu);
+        const uint64_t v[8] = { I->n_pictures, I->h2d_bytes, I->d2h_bytes, I->ns_ctx, I->ns_rec, I->n_pool, I->bytes_pool, I->ns_pool };
+        for (int k = 0; k < 8; k++) tot[k] += v[k];
+    }
     if (getenv("B200_SHIM_REPORT"))
         fprintf(stderr, "b200 shim: pictures %llu h2d_bytes %llu d2h_bytes %llu\nb200 shim start-up: device context %.0f ms, recorders %.0f ms, pinned frame buffers %llu x (%.0f MB total) %.0f ms\n",
-                (unsigned long long)G.n_pictures, (unsigned long long)G.h2d_bytes, (unsigned long long)G.d2h_bytes,
-                G.ns_ctx * 1e-6, G.ns_rec * 1e-6, (unsigned long long)G.n_pool, G.bytes_pool * 1e-6, G.ns_pool * 1e-6);
+                (unsigned long long)tot[0], (unsigned long long)tot[1], (unsigned long long)tot[2],
+                tot[3] * 1e-6, tot[4] * 1e-6, (unsigned long long)tot[5], tot[6] * 1e-6, tot[7] * 1e-6);
 }
 
+static void register_drain_at_exit(void) { atexit(drain_at_exit); }
 static void enqueue(Job *j)                        /* j->ticket is this thread's ticket */
 {
     pthread_mutex_lock(&G.mu);
     if (!G.sub_running) {
-        static int registered;
+        static pthread_once_t registered = PTHREAD_ONCE_INIT;
         G.sub_stop = 0;
-        if (pthread_create(&G.sub_thread, NULL, submit_main, NULL)) latch_global(B200_ENOMEM, "cannot start the submission thread");
-        else { G.sub_running = 1; if (!registered) { registered = 1; atexit(drain_at_exit); } }
+        if (pthread_create(&G.sub_thread, NULL, submit_main, &G)) latch_global(B200_ENOMEM, "cannot start the submission thread");
+        else { G.sub_running = 1; pthread_once(&registered, register_drain_at_exit); }
     }
     j->pending = 1; j->done = 0;
     if (!G.sub_running) { j->done = 1; G.turn++; pthread_cond_broadcast(&G.cv); }      /* nobody will run it: keep the tickets moving */
@@ -795,7 +852,7 @@ static int ensure_ctx(const HEVCContext *s)       /* called with G.mu held */
          * have ended (they do not depend on this thread) and their work lists have gone through the submission thread, then switch. */
         while (G.in_flight > (g.counted ? 1 : 0)) pthread_cond_wait(&G.cv, &G.mu);      /* (this thread's own packet does not count) */
         drain_queue();
-        G.gen++;
+        G.gen = __atomic_add_fetch(&g_gen_counter, 1, __ATOMIC_RELAXED);
         if (G.ctx) { b200_sync(G.ctx); b200_ctx_destroy(G.ctx); G.ctx = NULL; }
         for (int i = 0; i < MAX_RB; i++) G.rb[i].state = 0;
         memset(&G.cfg, 0, sizeof(G.cfg));
@@ -852,6 +909,7 @@ static int rb_insert(const uint8_t *data0);
 
 int b200_frame_begin(HEVCContext *s)
 {
+    if (use_instance(s)) return g.err;
     /* a failure of one picture (unsupported tool, out of memory, a work list the device rejected) must not disable the decoder for
      * the rest of the process: a random-access point starts afresh.  CUDA errors are sticky and stay latched. */
     if (g.err && g.err != B200_ECUDA && IS_IRAP(s) && g.in_frame != 1) {
@@ -1003,6 +1061,7 @@ static void picture_flags(HEVCContext *s)
 }
 int b200_frame_end(HEVCContext *s)
 {
+    if (use_instance(s)) return g.err;
     picture_flags(s);                               /* the parameter sets of the picture that ends (at b200_frame_begin of the NEXT one they may have changed) */
     return frame_end_of(s, s->ref);
 }
@@ -1024,6 +1083,7 @@ static void finish_abandoned(HEVCContext *s)
  * (before its b200_frame_begin), executed in decode order in front of that picture. */
 int b200_frame_fill(HEVCContext *s, HEVCFrame *frame)
 {
+    if (use_instance(s)) return g.err;
     if (g.err) return g.err;
     const int slot = (int)(frame - s->DPB);
     if (slot < 0 || slot >= 32) { fail(B200_EINVAL, "generate_missing_ref: frame is not in the DPB"); return g.err; }
@@ -1036,7 +1096,7 @@ int b200_frame_fill(HEVCContext *s, HEVCFrame *frame)
  * checksum): wait until the device picture has landed in it.  Frames the shim knows nothing about return at once. */
 int b200_output_wait(HEVCContext *s, AVFrame *frame)
 {
-    (void)s;
+    if (s && use_instance(s)) return g.err;
     if (!frame || !frame->data[0] || G.dump_dir) return 0;
     pthread_mutex_lock(&G.mu);
     int at = -1;
@@ -1058,6 +1118,7 @@ int b200_output_wait(HEVCContext *s, AVFrame *frame)
 static int packet_end(HEVCContext *s, AVFrame *frame);
 int b200_frame_readback(HEVCContext *s, AVFrame *frame)
 {
+    if (use_instance(s)) return g.err;
     const int rc = packet_end(s, frame);
     if (g.counted) {                                /* this thread's picture no longer needs the context it was begun with */
         pthread_mutex_lock(&G.mu);
@@ -1095,6 +1156,7 @@ static int packet_end(HEVCContext *s, AVFrame *frame)
 /* reference pictures that exist only on the host (e.g. produced before the hook was active) */
 int b200_frame_upload_ref(HEVCContext *s, AVFrame *frame)
 {
+    if (use_instance(s)) return g.err;
     pthread_mutex_lock(&G.mu);
     int rc = ensure_ctx(s);
     if (!rc && !G.dump_dir) {
@@ -1146,9 +1208,9 @@ struct AVBufferRef *b200_frame_buffer_alloc(int size)
     return r;
 }
 
-void b200_shim_close(void)
+/* the device side of the calling thread's instance goes away: queue drained, submission thread joined, context destroyed.  G.mu held. */
+static void instance_shutdown(void)
 {
-    pthread_mutex_lock(&G.mu);
     if (G.sub_running) {
         drain_queue();
         G.sub_stop = 1;
@@ -1158,12 +1220,48 @@ void b200_shim_close(void)
         pthread_mutex_lock(&G.mu);
         G.sub_running = 0;
     }
-    ShimThread *t = &g;
-    for (int i = 0; i < 2; i++) if (t->recs[i]) { b200_rec_destroy(t->recs[i]); t->recs[i] = NULL; }      /* recorders of other threads die with the process */
-    t->rec = NULL;
     if (G.ctx) { b200_sync(G.ctx); b200_ctx_destroy(G.ctx); }
-    G.ctx = NULL; G.next_ticket = G.turn = 0; G.err_code = 0; G.configured = 0;
+    G.ctx = NULL; G.next_ticket = G.turn = 0; G.err_code = 0; G.configured = 0; G.n_active = 0; G.in_flight = 0;
+    memset(&G.cfg, 0, sizeof(G.cfg));
     for (int i = 0; i < MAX_RB; i++) G.rb[i].state = 0;
+}
+
+/* hevc_decode_free (hevc.c:4187): the decoder is being closed.  With frame threads every copy and then the application's own
+ * context come through here (pthread_frame.c:676, utils.c avcodec_close); the first call that still finds the instance gives the
+ * device context, the submission thread and the entry back -- another decoder may open later in the same process. */
+void b200_decoder_close(HEVCContext *s)
+{
+    const void *key = instance_key(s);
+    Instance *I = NULL;
+    pthread_mutex_lock(&g_insts_mu);
+    for (int i = 0; i < MAX_INST && !I; i++) if (g_insts[i].key == key) I = &g_insts[i];
+    pthread_mutex_unlock(&g_insts_mu);
+    if (!I) return;
+    ShimThread *prev = g_self;
+    shim_block_for(I);
+    pthread_mutex_lock(&G.mu);
+    instance_shutdown();
     pthread_mutex_unlock(&G.mu);
-    if (t != &g_oom) { const unsigned seq = t->frame_seq; Job *jobs = t->jobs; if (jobs) memset(jobs, 0, 3 * sizeof(Job)); memset(t, 0, sizeof(*t)); t->frame_seq = seq; t->jobs = jobs; }   /* workers compare (att, att_seq) */
+    pthread_mutex_lock(&g_insts_mu);
+    __atomic_store_n(&I->key, NULL, __ATOMIC_RELAXED);
+    pthread_mutex_unlock(&g_insts_mu);
+    if (prev) g_self = prev;
+}
+
+void b200_shim_close(void)                         /* every instance; for hosts that unload the library */
+{
+    ShimThread *prev = g_self;
+    for (int i = 0; i < MAX_INST; i++) {
+        shim_block_for(&g_insts[i]);
+        pthread_mutex_lock(&G.mu);
+        instance_shutdown();
+        pthread_mutex_unlock(&G.mu);
+        ShimThread *t = &g;
+        for (int k = 0; k < 2; k++) if (t->recs[k]) { b200_rec_destroy(t->recs[k]); t->recs[k] = NULL; }      /* recorders of other threads die with the process */
+        t->rec = NULL; t->in_frame = 0; t->err = 0; t->counted = 0;
+        pthread_mutex_lock(&g_insts_mu);
+        __atomic_store_n(&g_insts[i].key, NULL, __ATOMIC_RELAXED);
+        pthread_mutex_unlock(&g_insts_mu);
+    }
+    if (prev) g_self = prev;
 }

@@ -21,7 +21,7 @@ sed -i -e "0,/^#include/s//$inc\n#include/" \
        -e 's/^\(\s*\)if (ARCH_X86) ff_hevcpred_init_x86(hpc, bit_depth);/&\n\1ff_hevcpred_init_b200(hpc, bit_depth);/' "$P/hevcpred.c"
 sed -i -e "0,/^#include/s//$inc\n#include/" \
        -e '/ff_videodsp_init_x86(ctx, bpc);/a\    ff_videodsp_init_b200(ctx, bpc);' "$P/videodsp.c"
-# frame life cycle (hevc.c:3271 / 3446 / 4141: the read-back hook sits right behind decode_nal_units, before its result is looked at)
+# frame life cycle, worker jobs, decoder close (hevc.c:3271 / 3446 / 4141; 2764 / 2847 / 2931; 4193: the read-back hook sits right behind decode_nal_units, before its result is looked at)
 sed -i -e "0,/^#include/s//$inc\n#include/" \
        -e 's/^\(\s*\)ff_thread_finish_setup(s->avctx);/\1if ((ret = b200_frame_begin(s)) < 0) goto fail;\n&/' \
        -e '/^\s*s->is_decoded = 1;/,/tiles_filters(s);/ s/^\(\s*\)tiles_filters(s);/&\n\1if ((ret = b200_frame_end(s)) < 0) goto fail;   \/* after the filters of tile threads *\//' \
@@ -29,6 +29,8 @@ sed -i -e "0,/^#include/s//$inc\n#include/" \
        -e 's|^\(\s*\)av_frame_move_ref(data, s->output_frame);|\1b200_output_wait(s, s->output_frame);   /* the picture leaves the decoder: its read-back has landed */\n&|' \
        -e 's/^\(\s*\)s = s1->sList\[self_id\];/\1b200_worker_begin(s1);   \/* execute2 job: this worker records for s1'"'"'s picture *\/\n&/' \
        -e 's/^\(\s*\)s = s->sList\[self_id\];/\1b200_worker_begin(s);\n&/' \
+       -e '/^static int hls_decode_entry(AVCodecContext \*avctxt, void \*isFilterThread)/,/^}/ s/^\(\s*\)int ctb_addr_ts = .*;$/&\n\1b200_worker_begin(s);   \/* execute(): with slice threads this runs on a worker thread too *\//' \
+       -e '/^static av_cold int hevc_decode_free/,/^}/ s/^\(\s*\)pic_arrays_free(s);/\1b200_decoder_close(s);   \/* the device side of this decoder goes away with it *\/\n&/' \
        -e '/^\s*ret = ff_hevc_output_frame(s, data, 1);/,/^\s*return ret;/ s|^\(\s*\)return ret;|&\n        if (ret > 0) b200_output_wait(s, data);|' "$P/hevc.c"
 # the decoder's frame pool in pinned memory (utils.c:558-561 passes av_buffer_allocz)
 sed -i -e "0,/^#include/s//$inc\n#include/" \
@@ -46,7 +48,7 @@ if [ -z "${B200_NO_COPY_GUARD:-}" ]; then
          -e '/^static void copy_CTB/,/^}/ s/^    int i;/&\n    if (b200_host_pixels_unused()) return;/' "$P/hevc_filter.c"
   grep -q "b200_host_pixels_unused" "$P/hevc_filter.c" || { echo "hook b200_host_pixels_unused was not inserted" >&2; exit 1; }
 fi
-for pat in ff_hevcdsp_init_b200 ff_hevcpred_init_b200 ff_videodsp_init_b200 b200_frame_begin b200_frame_end b200_frame_readback b200_frame_fill b200_frame_buffer_alloc b200_bs_on_device b200_deblock_on_device b200_worker_begin; do
+for pat in ff_hevcdsp_init_b200 ff_hevcpred_init_b200 ff_videodsp_init_b200 b200_frame_begin b200_frame_end b200_frame_readback b200_frame_fill b200_frame_buffer_alloc b200_bs_on_device b200_deblock_on_device b200_worker_begin b200_decoder_close; do
   grep -q "$pat" "$P"/*.c || { echo "hook $pat was not inserted" >&2; exit 1; }
 done
 CFLAGS=$(cat "$OUT/cflags.txt")

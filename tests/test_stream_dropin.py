@@ -176,6 +176,28 @@ def test_frame_threads_with_slice_threads_inside_are_bit_exact(threads):
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("threads", ["1", "4", "2x"])
+def test_two_decoders_in_one_process(threads):
+    """two decoder instances open at once in one process, fed alternately from one thread, then the first is
+    closed and a third opened on its stream (oracle/decode_two.c).  The shim keeps a device context, a submission thread and a ticket
+    order per instance; hevc_decode_free gives them back (b200_decoder_close)."""
+    binary = os.path.join(REFDIR, "decode_two_b200")
+    if not os.path.exists(binary):
+        pytest.skip("oracle/_ref/decode_two_b200 not built")
+    if threads == "2x":
+        a, b = os.path.join(RECIPE_DIR, "c2_1080p_wpp_ra8_33"), os.path.join(HERE, "golden", "streams", "tiles_832x480_8b_lowdelay")
+    else:
+        a, b = os.path.join(RECIPE_DIR, "c2_1080p_ra8_65"), os.path.join(HERE, "golden", "streams", "ra_416x240_8b")
+    if not (os.path.exists(a + ".hevc") and os.path.exists(a + ".md5")):
+        pytest.skip("recipe stream not generated (tools/make_bench_streams.sh)")
+    out = subprocess.run([binary, a + ".hevc", b + ".hevc", threads], capture_output=True, text=True, timeout=900)
+    assert out.returncode == 0, out.stderr[-2000:]
+    for tag, name in (("A", a), ("B", b), ("C", a)):
+        got = [l[2:] for l in out.stdout.splitlines() if l.startswith(tag + " frame ")]
+        assert got == open(name + ".md5").read().splitlines(), f"decoder {tag} ({os.path.basename(name)})"
+
+
+@pytest.mark.gpu
 @pytest.mark.parametrize("name", ["c1_832x480_i_16", "c2_1080p_ra8_65"])
 def test_ctb_granular_intra_stage_is_bit_exact(name):
     """B200_INTRA=2: the CTB-granular intra stage (k_intra_ctb.cuh; not the default -- measured slower) on an all-intra

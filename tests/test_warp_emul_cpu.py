@@ -182,6 +182,27 @@ def test_hooked_decoder_on_the_emulated_kernels(stream):
         assert decode_emulated(stream, "2x") == want
 
 
+@needs_emul
+@pytest.mark.parametrize("threads", ["1", "4", "2x"])
+def test_two_decoders_in_one_process_on_the_emulated_kernels(threads):
+    """the shim's state is per decoder instance (device context, submission thread, ticket order, read-back
+    table), found through the context every hook is handed.  oracle/decode_two.c opens two decoders, feeds them alternately from
+    one thread, closes the first and opens a third on the same stream (hevc_decode_free -> b200_decoder_close gives the instance
+    back); every picture of all three must equal the unmodified single decoder's.  "4": frame threads, "2x": frame threads with two
+    slice threads each on WPP / tile streams."""
+    binary = os.path.join(REFDIR, "decode_two_b200")
+    if not os.path.exists(binary):
+        pytest.skip("oracle/_ref/decode_two_b200 not built (needs /root/reference)")
+    gold = os.path.join(HERE, "golden", "streams")
+    a, b = ("wpp_416x240_8b_lowdelay", "tiles_832x480_8b_lowdelay") if threads == "2x" else ("b_416x240_10b_weighted", "ra_416x240_8b")
+    out = subprocess.run([binary, os.path.join(gold, a + ".hevc"), os.path.join(gold, b + ".hevc"), threads], capture_output=True, text=True, timeout=900,
+                         env=dict(os.environ, LD_PRELOAD=EMUL))
+    assert out.returncode == 0, out.stderr[-2000:]
+    for tag, name in (("A", a), ("B", b), ("C", a)):
+        got = [l[2:] for l in out.stdout.splitlines() if l.startswith(tag + " frame ")]
+        assert got == open(os.path.join(gold, name + ".md5")).read().splitlines(), f"decoder {tag} ({name})"
+
+
 # the streams that stress the deblocking control: QP deltas, beta / tc and chroma QP offsets, PCM with the loop filter off,
 # transquant bypass, slices / tiles without filtering across, asymmetric partitions, 4:2:2 / 4:4:4 chroma edge spacing, B pictures
 DBD_CHECKED = [s for s in EMULATED if os.path.basename(s).startswith(("amp_", "b_", "c422_", "c444_", "dbkoff_", "pcm_", "qpd_", "ra_416", "slices_", "tiles_", "tqb_"))]

@@ -17,3 +17,8 @@ for args in "$S/b_416x240_10b_weighted.hevc 4" "$S/ra_416x240_8b.hevc 4" "$S/wpp
   TSAN_OPTIONS="halt_on_error=0 report_signal_unsafe=0" LD_PRELOAD="$rt /tmp/libb200hevc_shim_tsan.so $PWD/libb200hevc_emul.so" timeout 900 ./decode_b200 $args > /tmp/tsan_out.txt 2> /tmp/tsan_err.txt || true
   echo "emulated dev $args: $(grep -c 'WARNING: ThreadSanitizer' /tmp/tsan_err.txt) reports, pictures $(grep '^frame ' /tmp/tsan_out.txt | diff -q - ${args%% *} > /dev/null 2>&1; grep '^frame ' /tmp/tsan_out.txt | diff -q - $(echo ${args%% *} | sed 's/.hevc$/.md5/') > /dev/null && echo identical || echo DIFFERENT)"
 done
+# two decoder instances in one process, fed alternately, one closed and re-opened (oracle/decode_two.c)
+for args in "$S/b_416x240_10b_weighted.hevc $S/ra_416x240_8b.hevc 4" "$S/wpp_416x240_8b_lowdelay.hevc $S/tiles_832x480_8b_lowdelay.hevc 2x"; do
+  TSAN_OPTIONS="halt_on_error=0 report_signal_unsafe=0" LD_PRELOAD="$rt /tmp/libb200hevc_shim_tsan.so $PWD/libb200hevc_emul.so" timeout 900 ./decode_two_b200 $args > /tmp/tsan_out.txt 2> /tmp/tsan_err.txt || true
+  echo "two decoders $args: $(grep -c 'WARNING: ThreadSanitizer' /tmp/tsan_err.txt) reports, $(grep -c ' frame ' /tmp/tsan_out.txt) pictures"
+done
