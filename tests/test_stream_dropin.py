@@ -111,10 +111,6 @@ def test_hooked_decoder_with_wpp_threads(stream):
     want = open(stream[:-5] + ".md5").read().splitlines()
     for rep in range(2 if stream in REPEATED else 1):
         assert run("decode_b200", stream, threads="4w") == want
-    if len(want) >= 4:
-        # hevc -f 4: frame threads with two slice threads each (pthread.c:57-71) -- several pictures in progress, every one of
-        # them recorded by several workers (b200_worker_begin)
-        assert run("decode_b200", stream, threads="2x") == want
 
 
 @pytest.mark.gpu
@@ -184,11 +180,13 @@ def test_two_decoders_in_one_process(threads):
     binary = os.path.join(REFDIR, "decode_two_b200")
     if not os.path.exists(binary):
         pytest.skip("oracle/_ref/decode_two_b200 not built")
+    # (streams longer than the frame-thread count, which for "2x" is cpus / 2 + 1, at most 16: the reference's flush logic drops
+    #  pictures of shorter ones, main_hm/main.c:283)
     if threads == "2x":
-        a, b = os.path.join(RECIPE_DIR, "c2_1080p_wpp_ra8_33"), os.path.join(HERE, "golden", "streams", "tiles_832x480_8b_lowdelay")
+        a, b = os.path.join(RECIPE_DIR, "c2_1080p_wpp_ra8_33"), os.path.join(RECIPE_DIR, "c2_1080p_ra8_65")
     else:
         a, b = os.path.join(RECIPE_DIR, "c2_1080p_ra8_65"), os.path.join(HERE, "golden", "streams", "ra_416x240_8b")
-    if not (os.path.exists(a + ".hevc") and os.path.exists(a + ".md5")):
+    if not (os.path.exists(a + ".hevc") and os.path.exists(a + ".md5") and os.path.exists(b + ".md5")):
         pytest.skip("recipe stream not generated (tools/make_bench_streams.sh)")
     out = subprocess.run([binary, a + ".hevc", b + ".hevc", threads], capture_output=True, text=True, timeout=900)
     assert out.returncode == 0, out.stderr[-2000:]
