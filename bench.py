@@ -101,6 +101,7 @@ STREAMS = {  # name: what it is
     "c3_4k_ra8_mid_65": "3840x2160 Main10 RA GOP 8, 65 pictures, --calm 0.5",
     "c3_4k_ra8_dense_33": "3840x2160 Main10 RA GOP 8, 33 pictures, dense random content (~110 Mbit/s: parse-bound worst case)",
     "c2_1080p_ra8_65": "1920x1080 8-bit RA GOP 8, 65 pictures",
+    "c3_4k_wpp_ra8_calm_33": "3840x2160 Main10 RA GOP 8, 33 pictures, lightly coded, entropy_coding_sync (WPP: one substream per CTB row)",
     "c1_832x480_i_16": "832x480 8-bit all-intra, 16 pictures",
 }
 HEADLINE_STREAM = {"c3_4k_main10_ra": "c3_4k_ra8_calm_65", "c2_1080p_main_ra": "c2_1080p_ra8_65", "c1_832x480_main": "c1_832x480_i_16"}
@@ -176,6 +177,48 @@ def stream_block(name, arms, threads_all, device, budget_s=2.5, with_single=True
     try:
         for t in tset:
             out[f"speedup_threads_{t}"] = out["b200"][f"threads_{t}"]["steady_fps"] / out["reference"][f"threads_{t}"]["steady_fps"]
+        out["speedup_best_vs_best"] = out["b200"]["best"]["steady_fps"] / out["reference"]["best"]["steady_fps"]
+    except Exception:
+        pass
+    return out
+
+
+def thread_modes_block(name, threads_all, device, budget_s=1.5):
+    """the reference's three ways of using host threads -- frame threads (hevc -f 1), slice / WPP threads inside one
+    picture (-f 2) and slice threads inside frame threads (-f 4, pthread.c:57-71) -- on a stream that carries entry points (WPP), both
+    arms, steady fps.  The hooked decoder's pictures are checked against the single-threaded reference in every mode (the reference's
+    own slice-threaded runs are not deterministic on 4K WPP streams -- its pictures are timed, not compared)."""
+    path = os.path.join(STREAM_DIR, name + ".hevc")
+    if not os.path.exists(path) or not os.path.exists(os.path.join(ROOT, "oracle", "_ref", "decode_ref")):
+        return {"unavailable": "stream or decoder binaries missing (tools/make_bench_streams.sh, __graft_entry__.build())"}
+    n = len(open(path[:-5] + ".md5").read().splitlines()) if os.path.exists(path[:-5] + ".md5") else 33
+    env = {"B200_DEVICE": str(device), "B200_SHIM_REPORT": "1"}
+    ns = max(2, min(threads_all, 16))
+    modes = {"frame": str(threads_all), "slice": f"{ns}w", "frame_slice": "4x"}
+    out = {"what": STREAMS.get(name, name), "pictures": n, "host_threads": threads_all,
+           "modes": {"frame": f"-f 1, {threads_all} frame threads", "slice": f"-f 2, {ns} WPP threads in one picture",
+                     "frame_slice": f"-f 4, 4 WPP threads per picture x {min(threads_all // 4 + 1, 16)} frame threads"}}
+    for arm in ("reference", "b200"):
+        binary = "decode_ref" if arm == "reference" else "decode_b200"
+        res = {}
+        for mode, t in modes.items():
+            probe = run_decoder(binary, path, t, 2, env)
+            if "error" in probe:
+                res[mode] = probe
+                continue
+            passes = int(min(64, max(2, 1 + budget_s * probe["steady_fps"] / n + 0.999)))
+            best = probe if passes <= 2 else run_decoder(binary, path, t, passes, env)
+            res[mode] = best if "error" not in best else probe
+        if arm == "b200":
+            res["md5_equal_reference_decoder"] = {mode: decoder_md5_ok(binary, path, t, env) for mode, t in modes.items()}
+        ok = {m: r["steady_fps"] for m, r in res.items() if isinstance(r, dict) and "steady_fps" in r}
+        if ok:
+            bm = max(ok, key=ok.get)
+            res["best"] = {"mode": bm, "steady_fps": ok[bm]}
+        out[arm] = res
+    try:
+        for mode in modes:
+            out[f"speedup_{mode}"] = out["b200"][mode]["steady_fps"] / out["reference"][mode]["steady_fps"]
         out["speedup_best_vs_best"] = out["b200"]["best"]["steady_fps"] / out["reference"]["best"]["steady_fps"]
     except Exception:
         pass
@@ -298,7 +341,7 @@ def main():
     ap.add_argument("--workload", default="c3_4k_main10_ra", choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-stream", action="store_true", help="skip the real-decoder stream block (e2e falls back to the work-list replay)")
-    ap.add_argument("--streams", default="headline,mid,dense", help="which streams the stream_e2e block decodes")
+    ap.add_argument("--streams", default="headline,mid,dense,modes", help="which streams the stream_e2e block decodes")
     args = ap.parse_args()
     wl = WORKLOADS[args.workload]
     rank, world, local = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1)), int(os.environ.get("LOCAL_RANK", 0))
@@ -489,6 +532,8 @@ def main():
             for tag, nm in (("mid", "c3_4k_ra8_mid_65"), ("dense", "c3_4k_ra8_dense_33")):
                 if tag in args.streams.split(",") and args.workload == "c3_4k_main10_ra":
                     stream_e2e[nm] = stream_block(nm, ["reference", "b200"], threads_all, local, budget_s=1.5, with_single=False)
+            if "modes" in args.streams.split(",") and args.workload == "c3_4k_main10_ra":
+                stream_e2e["thread_modes_c3_4k_wpp_ra8_calm_33"] = thread_modes_block("c3_4k_wpp_ra8_calm_33", threads_all, local)
         if float(sfps.item()) > 0:
             b = mine["b200"][f"threads_{best['threads']}"]
             e2e_line = {"value": float(sfps.item()), "unit": UNIT,

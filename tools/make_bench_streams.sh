@@ -9,6 +9,7 @@
 #   c3_4k_ra8_mid_65.hevc    the same at --calm 0.5
 #   c3_4k_ra8_dense_33.hevc  dense random content (~460 KB per picture, ~110 Mbit/s: the parse-bound worst case)
 #   c2_1080p_ra8_65.hevc     1920x1080 8-bit, GOP 8 (BASELINE.json config 2)
+#   c3_4k_wpp_ra8_calm_33.hevc  3840x2160 Main10, GOP 8, WPP, lightly coded: the stream bench.py times the three threading modes on (-f 1 / 2 / 4)
 #   c2_1080p_wpp_ra8_33.hevc 1920x1080 8-bit, GOP 8, entropy_coding_sync (WPP): the stream of the frame + slice thread (-f 4) tests
 #   c1_832x480_i_16.hevc     832x480 8-bit all-intra (config 1)
 #   c5_8k_422_wpp_tiles_9.hevc  7680x4320 4:2:2 Main10 (RExt), entropy_coding_sync + 4x2 tiles (one substream per CTB row of every
@@ -29,6 +30,7 @@ gen() {   # name, then generator arguments
 gen c3_4k_ra8_calm_65 --width 3840 --height 2160 --bit-depth 10 --frames 65 --pattern RA8 --calm 1.0 --seed 9 &
 gen c3_4k_ra8_mid_65 --width 3840 --height 2160 --bit-depth 10 --frames 65 --pattern RA8 --calm 0.5 --seed 10 &
 gen c2_1080p_ra8_65 --width 1920 --height 1080 --bit-depth 8 --frames 65 --pattern RA8 --calm 0.7 --seed 11 &
+gen c3_4k_wpp_ra8_calm_33 --width 3840 --height 2160 --bit-depth 10 --frames 33 --pattern RA8 --wpp --calm 1.0 --seed 19 &
 gen c2_1080p_wpp_ra8_33 --width 1920 --height 1080 --bit-depth 8 --frames 33 --pattern RA8 --wpp --calm 0.7 --seed 21 &
 gen c1_832x480_i_16 --width 832 --height 480 --bit-depth 8 --frames 16 --pattern I --seed 12 &
 gen c5_8k_422_wpp_tiles_9 --width 7680 --height 4320 --bit-depth 10 --cfi 2 --frames 9 --pattern RA8 --wpp --tiles 4x2 --calm 1.0 --seed 55 &
