@@ -1662,8 +1662,11 @@ int launch_intra(cudaStream_t st, const B200IntraRec *recs, int count, const int
     B200_LAUNCH((count + 255) / 256, 256, 0, st, k_intra_prepass)(recs, count, ed, counter);
     int grid = (count + 3) / 4;
     // persistent warps.  The list is sorted by dependency level, so the TUs that can run together are adjacent and a
-    // small window exposes all the parallelism there is; more waiting warps would only add polling traffic on L2.
-    static const int max_ctas = getenv("B200_INTRA_CTAS") ? atoi(getenv("B200_INTRA_CTAS")) : 148 * 2;
+    // small window exposes all the parallelism there is; more waiting warps only take issue slots from the other pictures
+    // in flight.  Measured on a B200 (4K Main10 RA mix, 8 lanes; gpurun_out/b10_*, b12_*), pictures/s with 1184 / 592 / 296 /
+    // 148 / 74 blocks: 2980 / 3507 / 3842 / 4027 / 4045; the I picture takes 4.07 ms down to 148 blocks and 4.19 ms with 74,
+    // the intra blocks of a B picture 70 / 75 / 90 / 116 / 174 us when timed alone.  One block per SM.
+    static const int max_ctas = getenv("B200_INTRA_CTAS") ? atoi(getenv("B200_INTRA_CTAS")) : 148;
     if (grid > max_ctas) grid = max_ctas;
     CipDesc cd;
     memset(&cd, 0, sizeof(cd));
