@@ -43,6 +43,16 @@ sed -i -e "0,/^#include/s//$inc\n#include/" \
 # deblocking control on the device: the two host functions that derive boundary strengths / tc / beta hand over
 sed -i -e '/^void ff_hevc_deblocking_boundary_strengths(HEVCContext \*s, int x0, int y0,/,/^}/ s/^    int i, j, bs;/&\n    if (b200_bs_on_device(s, x0, y0, log2_trafo_size)) return;/' \
        -e '/^static void deblocking_filter_CTB/,/^}/ s/^    uint8_t \*src;/    uint8_t *src = NULL;\n    if (b200_deblock_on_device()) return;/' "$P/hevc_filter.c"
+# experiment, NOT applied by default (B200_AWAIT_GUARD=1 builds with it): hevc_await_progress (hevc.c:1951-1958) makes a frame thread wait
+# until the rows of a reference picture its motion vector reaches have been reconstructed by another thread -- for pixels nobody reads on
+# the host once the MC tables record (the device runs the pictures in decode order; the TMVP wait, hevc_mvs.c:260, would stay).  Bit-exact
+# (CPU suite, emulated device with 4 / 8 frame threads, MD5 on the GPU at 32 threads); host-only (record and drop, 8 cores) +5 % at 8 and
+# +12 % at 16 threads, but on the B200 box 886 vs 986 fps at 32 threads and 802 vs 808 at 16 (gpurun_out/b13_await_guard.txt): no gain
+# where it counts, so the decoder keeps its own synchronisation.
+if [ -n "${B200_AWAIT_GUARD:-}" ]; then
+  sed -i -e '/^static void hevc_await_progress(HEVCContext \*s, HEVCFrame \*ref,/,/^}/ s/^    int y = (mv->y >> 2) + y0 + height + 9;/&\n    if (b200_host_pixels_unused()) return;   \/* reference PIXELS are not read on the host *\//' "$P/hevc.c"
+  grep -q "b200_host_pixels_unused()) return;   /\* reference PIXELS" "$P/hevc.c" || { echo "await guard was not inserted" >&2; exit 1; }
+fi
 if [ -z "${B200_NO_COPY_GUARD:-}" ]; then
   sed -i -e "0,/^#include/s//$inc\n#include/" \
          -e '/^static void copy_CTB/,/^}/ s/^    int i;/&\n    if (b200_host_pixels_unused()) return;/' "$P/hevc_filter.c"
