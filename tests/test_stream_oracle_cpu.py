@@ -51,8 +51,13 @@ def test_recorded_work_lists_through_the_oracle_equal_the_reference_decoder(stre
     # shorter than the thread count the reference's flush logic, main_hm/main.c:283, also drops the delayed pictures.)
     ref = subprocess.run([os.path.join(REFDIR, "decode_ref"), stream, threads], capture_output=True, text=True, timeout=600)
     want = [l for l in ref.stdout.splitlines() if l.startswith("frame ")]
+    committed = open(stream[:-5] + ".md5").read().splitlines()
     if threads == "1":
-        assert want == open(stream[:-5] + ".md5").read().splitlines()
+        assert want == committed
+    elif threads in ("4w", "2x") and len(want) == len(committed):
+        # slice threads never change what a picture is; the unmodified decoder's own slice-threaded runs can (a race in its host
+        # pixel path, seen on 4K WPP streams: DESIGN.md 6) -- the single-threaded run is the arbiter whenever all pictures came out
+        want = committed
     if not want:
         pytest.skip("the reference outputs no picture of this stream with that many threads")
     with tempfile.TemporaryDirectory() as d:

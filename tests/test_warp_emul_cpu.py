@@ -207,9 +207,9 @@ def test_two_decoders_in_one_process_on_the_emulated_kernels(threads):
         got = [l[2:] for l in out.stdout.splitlines() if l.startswith(tag + " frame ")]
         want = [l[2:] for l in ref.stdout.splitlines() if l.startswith(tag + " frame ")]
         committed = open(os.path.join(gold, name + ".md5")).read().splitlines()
-        assert got == want, f"decoder {tag} ({name})"
-        if len(want) == len(committed):
-            assert want == committed
+        # (where the reference outputs every picture the committed single-decoder MD5s are the arbiter: its own slice-threaded runs
+        #  are not race-free in the host pixel path)
+        assert got == (committed if len(want) == len(committed) else want), f"decoder {tag} ({name})"
     assert any(l.startswith("A frame ") for l in out.stdout.splitlines())
 
 
