@@ -111,8 +111,11 @@ def run_decoder(binary, stream, threads, passes, env=None, timeout=900):
     """one run of decode_ref / decode_b200 in timing mode (no MD5 work): the file is decoded `passes` times back to back by ONE
     decoder instance; returns frames, wall seconds and the steady-state rate (passes 2..n: start-up excluded)"""
     import re
-    r = subprocess.run([os.path.join(ROOT, "oracle", "_ref", binary), stream, str(threads), "time", str(passes)], capture_output=True, text=True,
-                       timeout=timeout, env=dict(os.environ, **(env or {})))
+    try:
+        r = subprocess.run([os.path.join(ROOT, "oracle", "_ref", binary), stream, str(threads), "time", str(passes)], capture_output=True, text=True,
+                           timeout=timeout, env=dict(os.environ, **(env or {})))
+    except subprocess.TimeoutExpired:               # (the unmodified decoder's slice-threaded modes have been seen to hang on tile streams)
+        return {"error": f"no result within {timeout} s", "rc": None}
     m = re.search(r"frames (\d+) time ([\d.]+) fps ([\d.]+) first_frame_s ([\d.]+) steady_fps ([\d.]+)", r.stdout)
     if r.returncode or not m:
         return {"error": (r.stderr or r.stdout)[-300:], "rc": r.returncode}
@@ -129,7 +132,10 @@ def decoder_md5_ok(binary, stream, threads, env=None):
     want_path = stream[:-5] + ".md5"
     if not os.path.exists(want_path):
         return None
-    r = subprocess.run([os.path.join(ROOT, "oracle", "_ref", binary), stream, str(threads)], capture_output=True, text=True, timeout=900, env=dict(os.environ, **(env or {})))
+    try:
+        r = subprocess.run([os.path.join(ROOT, "oracle", "_ref", binary), stream, str(threads)], capture_output=True, text=True, timeout=300, env=dict(os.environ, **(env or {})))
+    except subprocess.TimeoutExpired:
+        return False
     got = [l for l in r.stdout.splitlines() if l.startswith("frame ")]
     want = open(want_path).read().splitlines()
     return r.returncode == 0 and got == want
@@ -202,12 +208,12 @@ def thread_modes_block(name, threads_all, device, budget_s=1.5):
         binary = "decode_ref" if arm == "reference" else "decode_b200"
         res = {}
         for mode, t in modes.items():
-            probe = run_decoder(binary, path, t, 2, env)
+            probe = run_decoder(binary, path, t, 2, env, timeout=90)
             if "error" in probe:
                 res[mode] = probe
                 continue
             passes = int(min(64, max(2, 1 + budget_s * probe["steady_fps"] / n + 0.999)))
-            best = probe if passes <= 2 else run_decoder(binary, path, t, passes, env)
+            best = probe if passes <= 2 else run_decoder(binary, path, t, passes, env, timeout=90)
             res[mode] = best if "error" not in best else probe
         if arm == "b200":
             res["md5_equal_reference_decoder"] = {mode: decoder_md5_ok(binary, path, t, env) for mode, t in modes.items()}
